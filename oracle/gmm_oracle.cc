@@ -1,0 +1,319 @@
+/*
+ * gmm_oracle.cc -- CPU restatement of the reference's diagonal-covariance GMM feature scorers.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED by reference tests: the reference has no
+ * unit test for any Mm scorer; the restatement follows the cited lines, including accumulation
+ * order and the f32/f64 mixing.
+ *
+ * Build with -ffp-contract=off.  use_fma selects the contraction the reference's default build
+ * (gcc -O2 -march=native, -ffp-contract=fast) applies to `s += x * x`.
+ */
+#include "oracle.h"
+
+#include <immintrin.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace {
+
+/* Mm::gaussLogNormFactor src/Mm/Utilities.hh:71-76 (+ logNorm :53-59) */
+double gaussLogNormFactor(const float* var, unsigned dim) {
+    double sumLog = 0;
+    for (unsigned d = 0; d < dim; ++d)
+        sumLog += log(std::fabs(var[d]));
+    return (double)dim * log((double)2 * M_PI) + sumLog;
+}
+
+/* Mm::inverseSquareRoot<f32> src/Mm/Utilities.hh:86-91 */
+inline float inverseSquareRoot(float x) {
+    return (float)1 / (float)sqrt(x);
+}
+
+float* alignedFloats(size_t n) {
+    void* p = 0;
+    if (posix_memalign(&p, 32, std::max<size_t>(n, 8) * sizeof(float)) != 0)
+        return 0;
+    std::memset(p, 0, std::max<size_t>(n, 8) * sizeof(float));
+    return (float*)p;
+}
+
+/* ------------------------------------------------------------------ Mm::BatchFloatFeatureScorer
+ * init src/Mm/BatchFeatureScorer.cc:164-197, setFeature :157-162, fillScoreCacheTpl :207-253 */
+struct BatchFloat {
+    unsigned              dim, padded, nMix, nDens;
+    std::vector<unsigned> offsets;
+    float *               isd, *means, *consts;
+
+    BatchFloat() : isd(0), means(0), consts(0) {}
+    ~BatchFloat() {
+        free(isd);
+        free(means);
+        free(consts);
+    }
+
+    int init(const orc_mixture_set& ms) {
+        if (ms.n_covariances != 1)
+            return -2; /* "feature scorer supports only globally pooled covariance" */
+        dim    = ms.dim;
+        padded = ((dim + 7) / 8) * 8;
+        nMix   = ms.n_mixtures;
+        offsets.assign(nMix + 1, 0);
+        nDens = 0;
+        for (unsigned m = 0; m < nMix; ++m) {
+            offsets[m] = nDens;
+            nDens += ms.mix_offsets[m + 1] - ms.mix_offsets[m];
+        }
+        offsets[nMix] = nDens;
+        isd           = alignedFloats(padded);
+        means         = alignedFloats((size_t)nDens * padded);
+        consts        = alignedFloats(nDens);
+        for (unsigned d = 0; d < dim; ++d)
+            isd[d] = inverseSquareRoot(ms.variances[d]);
+        const float logNormFactor = gaussLogNormFactor(ms.variances, dim);
+        for (unsigned m = 0; m < nMix; ++m) {
+            float* mean = means + (size_t)offsets[m] * padded;
+            float* c    = consts + offsets[m];
+            for (unsigned e = ms.mix_offsets[m]; e < ms.mix_offsets[m + 1]; ++e) {
+                unsigned dns = ms.mix_density[e];
+                if (ms.dens_cov[dns] != 0)
+                    return -3;
+                const float* mu = ms.means + (size_t)ms.dens_mean[dns] * dim;
+                for (unsigned d = 0; d < dim; ++d)
+                    mean[d] = mu[d] * isd[d];
+                mean += padded;
+                *c = logNormFactor - 2 * ms.mix_log_weight[e];
+                ++c;
+            }
+        }
+        return 0;
+    }
+
+    template<bool Fuse>
+    void scoreFrames(const float* feats, long t0, long t1, float* scores) const {
+        float* x = alignedFloats(padded);
+        for (long t = t0; t < t1; ++t) {
+            std::memset(x, 0, sizeof(float) * padded);
+            const float* f = feats + (size_t)t * dim;
+            for (unsigned d = 0; d < dim; ++d)
+                x[d] = f[d] * isd[d];
+            for (unsigned m = 0; m < nMix; ++m) {
+                float best = FLT_MAX;
+                for (unsigned dns = offsets[m]; dns < offsets[m + 1]; ++dns) {
+                    const float* mean = means + (size_t)dns * padded;
+                    __m128       s1   = _mm_load_ss(consts + dns);
+                    __m128       s2   = _mm_setzero_ps();
+                    for (unsigned d = 0; d < padded; d += 8) {
+                        __m128 x1 = _mm_sub_ps(_mm_load_ps(mean + d), _mm_load_ps(x + d));
+                        __m128 x2 = _mm_sub_ps(_mm_load_ps(mean + d + 4), _mm_load_ps(x + d + 4));
+                        if (Fuse) {
+                            s1 = _mm_fmadd_ps(x1, x1, s1);
+                            s2 = _mm_fmadd_ps(x2, x2, s2);
+                        }
+                        else {
+                            s1 = _mm_add_ps(s1, _mm_mul_ps(x1, x1));
+                            s2 = _mm_add_ps(s2, _mm_mul_ps(x2, x2));
+                        }
+                    }
+                    s1 = _mm_add_ps(s1, s2);
+                    s2 = s1;
+                    s1 = _mm_shuffle_ps(s1, s2, _MM_SHUFFLE(1, 0, 3, 2));
+                    s1 = _mm_add_ps(s1, s2);
+                    s2 = s1;
+                    s1 = _mm_shuffle_ps(s1, s2, _MM_SHUFFLE(2, 3, 0, 1));
+                    s1 = _mm_add_ps(s1, s2);
+                    _mm_store_ss(&best, _mm_min_ps(_mm_load_ss(&best), s1));
+                }
+                if (best < FLT_MAX)
+                    best *= 0.5;
+                scores[(size_t)t * nMix + m] = best;
+            }
+        }
+        free(x);
+    }
+};
+
+/* ------------------------------------------------------------------ Mm::GaussDiagonalMaximumFeatureScorer
+ * init src/Mm/GaussDiagonalMaximumFeatureScorer.cc:65-87 (+ MixtureFeatureScorerElement.cc:21-34,
+ * CovarianceFeatureScorerElement.cc:21-51), distance :144-233 (SSE3 branch: the reference always
+ * builds with -msse3), calculateScoreAndDensity :116-142; Sum variant :239-290. */
+struct DiagonalScorer {
+    unsigned                        dim;
+    const orc_mixture_set*          ms;
+    std::vector<std::vector<float>> minus2LogWeights;  // per mixture
+    std::vector<std::vector<float>> isd;               // per covariance
+    std::vector<float>              logNorm;           // per covariance
+
+    void init(const orc_mixture_set& m, float mixtureWeightScale, float gaussianScaleParam) {
+        ms  = &m;
+        dim = m.dim;
+        /* gaussianScale_ = std::sqrt(paramGaussianScale(c)) :49 -- f64 parameter, f32 member */
+        float gaussianScale = std::sqrt((double)gaussianScaleParam);
+        minus2LogWeights.resize(m.n_mixtures);
+        for (unsigned i = 0; i < m.n_mixtures; ++i) {
+            unsigned n = m.mix_offsets[i + 1] - m.mix_offsets[i];
+            minus2LogWeights[i].resize(n);
+            for (unsigned k = 0; k < n; ++k) {
+                float v                = -2 * m.mix_log_weight[m.mix_offsets[i] + k];
+                minus2LogWeights[i][k] = v * mixtureWeightScale;
+            }
+        }
+        isd.resize(m.n_covariances);
+        logNorm.resize(m.n_covariances);
+        for (unsigned c = 0; c < m.n_covariances; ++c) {
+            const float* var = m.variances + (size_t)c * dim;
+            isd[c].resize(dim);
+            for (unsigned d = 0; d < dim; ++d)
+                isd[c][d] = inverseSquareRoot(var[d]) * gaussianScale;
+            float lnf  = gaussLogNormFactor(var, dim);
+            logNorm[c] = lnf * (gaussianScale * gaussianScale);
+        }
+    }
+
+    template<bool Fuse>
+    float distance(const float* feature, const float* mean, const float* isrv) const {
+        unsigned cmp = 0;
+        float    result = 0;
+        __m128   sum    = _mm_setzero_ps();
+        unsigned eff    = dim & (~3u);
+        while (cmp < eff) {
+            __m128 m  = _mm_loadu_ps(mean + cmp);
+            __m128 f  = _mm_loadu_ps(feature + cmp);
+            __m128 v  = _mm_loadu_ps(isrv + cmp);
+            __m128 df = _mm_mul_ps(_mm_sub_ps(m, f), v);
+            sum       = Fuse ? _mm_fmadd_ps(df, df, sum) : _mm_add_ps(sum, _mm_mul_ps(df, df));
+            cmp += 4u;
+        }
+        sum = _mm_hadd_ps(sum, sum);
+        float buffer[4];
+        _mm_storeu_ps(buffer, sum);
+        result += buffer[0] + buffer[1];
+        for (; cmp < dim; ++cmp) {
+            float df = (mean[cmp] - feature[cmp]) * isrv[cmp];
+            result   = Fuse ? std::fmaf(df, df, result) : (result + df * df);
+        }
+        return result;
+    }
+
+    template<bool Fuse>
+    void scoreMax(const float* feats, long T, float* scores, uint32_t* best) const {
+        for (long t = 0; t < T; ++t) {
+            const float* x = feats + (size_t)t * dim;
+            for (unsigned m = 0; m < ms->n_mixtures; ++m) {
+                float    bestScore   = FLT_MAX;
+                uint32_t bestDensity = 0xffffffffu;
+                unsigned n           = ms->mix_offsets[m + 1] - ms->mix_offsets[m];
+                for (unsigned k = 0; k < n; ++k) {
+                    unsigned dns = ms->mix_density[ms->mix_offsets[m] + k];
+                    unsigned cov = ms->dens_cov[dns];
+                    double   score = (double)minus2LogWeights[m][k] + (double)logNorm[cov] +
+                                   (double)distance<Fuse>(x, ms->means + (size_t)ms->dens_mean[dns] * dim,
+                                                          isd[cov].data());
+                    if (bestScore > score) {
+                        bestScore   = score;
+                        bestDensity = k;
+                    }
+                }
+                scores[(size_t)t * ms->n_mixtures + m] = 0.5 * bestScore;
+                if (best)
+                    best[(size_t)t * ms->n_mixtures + m] = bestDensity;
+            }
+        }
+    }
+
+    template<bool Fuse>
+    void scoreSum(const float* feats, long T, float* scores, uint32_t* best) const {
+        std::vector<float> s;
+        for (long t = 0; t < T; ++t) {
+            const float* x = feats + (size_t)t * dim;
+            for (unsigned m = 0; m < ms->n_mixtures; ++m) {
+                unsigned n = ms->mix_offsets[m + 1] - ms->mix_offsets[m];
+                s.resize(n);
+                for (unsigned k = 0; k < n; ++k) {
+                    unsigned dns   = ms->mix_density[ms->mix_offsets[m] + k];
+                    unsigned cov   = ms->dens_cov[dns];
+                    float    score = minus2LogWeights[m][k] + logNorm[cov] +
+                                  distance<Fuse>(x, ms->means + (size_t)ms->dens_mean[dns] * dim, isd[cov].data());
+                    s[k] = 0.5 * score;
+                }
+                float    bestScore   = FLT_MAX;
+                uint32_t bestDensity = 0xffffffffu;
+                for (unsigned k = 0; k < n; ++k)
+                    if (bestScore > s[k]) {
+                        bestScore   = s[k];
+                        bestDensity = k;
+                    }
+                float sumExp = 0;
+                for (unsigned k = 0; k < n; ++k)
+                    sumExp += std::exp(bestScore - s[k]);
+                scores[(size_t)t * ms->n_mixtures + m] = bestScore - std::log(sumExp);
+                if (best)
+                    best[(size_t)t * ms->n_mixtures + m] = bestDensity;
+            }
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int orc_gmm_batch_float(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma) {
+    BatchFloat s;
+    int        rc = s.init(*ms);
+    if (rc)
+        return rc;
+    if (use_fma)
+        s.scoreFrames<true>(feats, 0, T, scores);
+    else
+        s.scoreFrames<false>(feats, 0, T, scores);
+    return 0;
+}
+
+extern "C" int orc_gmm_batch_float_mt(const orc_mixture_set* ms, const float* feats, long T, float* scores,
+                                      int use_fma, int n_threads) {
+    BatchFloat s;
+    int        rc = s.init(*ms);
+    if (rc)
+        return rc;
+    if (n_threads < 1)
+        n_threads = 1;
+    std::vector<std::thread> pool;
+    for (int i = 0; i < n_threads; ++i) {
+        long a = T * i / n_threads, b = T * (i + 1) / n_threads;
+        pool.emplace_back([&s, feats, scores, a, b, use_fma]() {
+            if (use_fma)
+                s.scoreFrames<true>(feats, a, b, scores);
+            else
+                s.scoreFrames<false>(feats, a, b, scores);
+        });
+    }
+    for (auto& th : pool)
+        th.join();
+    return 0;
+}
+
+extern "C" int orc_gmm_diag_max(const orc_mixture_set* ms, float mixture_weight_scale, float gaussian_scale,
+                                const float* feats, long T, float* scores, uint32_t* best, int use_fma) {
+    DiagonalScorer s;
+    s.init(*ms, mixture_weight_scale, gaussian_scale);
+    if (use_fma)
+        s.scoreMax<true>(feats, T, scores, best);
+    else
+        s.scoreMax<false>(feats, T, scores, best);
+    return 0;
+}
+
+extern "C" int orc_gmm_diag_sum(const orc_mixture_set* ms, float mixture_weight_scale, float gaussian_scale,
+                                const float* feats, long T, float* scores, uint32_t* best, int use_fma) {
+    DiagonalScorer s;
+    s.init(*ms, mixture_weight_scale, gaussian_scale);
+    if (use_fma)
+        s.scoreSum<true>(feats, T, scores, best);
+    else
+        s.scoreSum<false>(feats, T, scores, best);
+    return 0;
+}

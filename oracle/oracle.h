@@ -1,0 +1,132 @@
+/*
+ * oracle.h -- C interface of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  The oracle is a CPU restatement of the reference's
+ * (rwth-i6/rasr) algorithms for the acoustic front-end and the emission scorers.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it; the product (rasr_b200/) never links or calls anything in oracle/.
+ *
+ * Every function names the reference file:line it follows (paths relative to the
+ * reference checkout).  Parity status:
+ *   - Nn layers:   pinned by the reference's own unit-test vectors
+ *                  (src/Test/Nn_LinearAndActivationLayer.cc:79-179, src/Test/Nn_NeuralNetwork.cc:37-120)
+ *   - FFT:         pinned against the reference's own TU src/Math/FastFourierTransform.cc compiled
+ *                  from where it lies into oracle/_ref (see oracle/Makefile)
+ *   - everything else (pre-emphasis, framing, window, amplitude, filterbank, log, DCT,
+ *     regression, all Mm scorers): PARITY UNPINNED by reference tests (none exist); the
+ *     restatement follows the cited source lines and is checked by self-derived KATs.
+ */
+#ifndef RASR_ORACLE_H
+#define RASR_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- front-end */
+
+typedef struct {
+    double sample_rate;       /* "sample-rate" attribute of the samples stream, e.g. 16000 */
+    double window_length_s;   /* signal-window length=  (mfcc.flow:12-13), 0.025 */
+    double window_shift_s;    /* signal-window shift=   , 0.01 */
+    double fft_max_input_s;   /* signal-real-fast-fourier-transform maximum-input-size= , 0.025 */
+    double filter_width;      /* signal-filterbank filter-width= (mel), 268.258 */
+    float  preemphasis_alpha; /* signal-preemphasis alpha= , 1.0 */
+    int    n_cepstra;         /* signal-cosine-transform nr-outputs= */
+    int    derivatives;       /* 0: static cepstra only; 1: static || delta || delta-delta */
+    int    use_fma;           /* 1: floating-point contraction as gcc -O2 -march=native does for the
+                                 reference's default build; 0: every operation rounded separately */
+} orc_frontend_cfg;
+
+typedef struct {
+    int win_length;  /* samples */
+    int win_shift;   /* samples */
+    int fft_length;  /* points */
+    int n_bins;      /* fft_length/2+1 */
+    int n_filters;
+    int n_weights;   /* total non-zero filterbank taps */
+    int feat_dim;    /* n_cepstra * (derivatives ? 3 : 1) */
+} orc_frontend_geometry;
+
+int orc_frontend_get_geometry(const orc_frontend_cfg* cfg, orc_frontend_geometry* g);
+
+/* number of frames the window node emits for n samples in one segment */
+long orc_frontend_nframes(const orc_frontend_cfg* cfg, long n_samples);
+
+/* Tables: window[win_length]; fb_start/fb_end[n_filters]; fb_weights dense [n_filters * n_bins]
+ * (zero outside [start,end)); dct [n_cepstra * n_filters].  Any pointer may be NULL. */
+int orc_frontend_tables(const orc_frontend_cfg* cfg, float* window, int* fb_start, int* fb_end,
+                        float* fb_weights, float* dct);
+
+/* Whole pipeline on one segment, fed to the network in packets of `chunk` samples (<=0: one packet).
+ * feats [T * feat_dim]; t_start/t_end [T] are the timestamps of the final packets.
+ * Optional per-stage dumps (NULL to skip): spectrum [T*(fft_length+2)], amplitude [T*n_bins],
+ * fbank [T*n_filters] (before log), cepstra [T*n_cepstra].  Returns T or <0. */
+long orc_mfcc(const orc_frontend_cfg* cfg, const float* samples, long n_samples, long chunk,
+              float* feats, double* t_start, double* t_end, float* spectrum, float* amplitude,
+              float* fbank, float* cepstra);
+
+/* in-place real FFT of `n` (power of two) f32 values in the packed layout of
+ * Math::FastFourierTransform::transformReal (restatement). */
+void orc_fft_real_packed(float* v, int n);
+
+/* ---------------------------------------------------------------- GMM scorers */
+
+typedef struct {
+    uint32_t        dim;
+    uint32_t        n_mixtures;
+    uint32_t        n_densities;
+    uint32_t        n_means;
+    uint32_t        n_covariances;
+    const uint32_t* mix_offsets;    /* [n_mixtures+1] into mix_density / mix_log_weight */
+    const uint32_t* mix_density;    /* density index of each mixture entry */
+    const double*   mix_log_weight; /* natural-log weight of each mixture entry (Mm::Weight = f64) */
+    const uint32_t* dens_mean;      /* [n_densities] mean index */
+    const uint32_t* dens_cov;       /* [n_densities] covariance index */
+    const float*    means;          /* [n_means * dim] */
+    const float*    variances;      /* [n_covariances * dim] diagonal */
+} orc_mixture_set;
+
+/* Mm::BatchFloatFeatureScorer, all mixtures x all frames. scores [T * n_mixtures]. */
+int orc_gmm_batch_float(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma);
+/* Mm::GaussDiagonalMaximumFeatureScorer. best [T * n_mixtures] density-in-mixture index (may be NULL). */
+int orc_gmm_diag_max(const orc_mixture_set* ms, float mixture_weight_scale, float gaussian_scale,
+                     const float* feats, long T, float* scores, uint32_t* best, int use_fma);
+/* Mm::GaussDiagonalSumFeatureScorer (log-sum-exp). */
+int orc_gmm_diag_sum(const orc_mixture_set* ms, float mixture_weight_scale, float gaussian_scale,
+                     const float* feats, long T, float* scores, uint32_t* best, int use_fma);
+/* multi-threaded driver over frame slices (the reference's only parallel mode is independent
+ * processes over corpus partitions; threads over frame ranges are the same thing for a dense scorer) */
+int orc_gmm_batch_float_mt(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma,
+                           int n_threads);
+
+/* ---------------------------------------------------------------- Nn scorer */
+
+enum { ORC_ACT_LINEAR = 0, ORC_ACT_SIGMOID = 1, ORC_ACT_RELU = 2, ORC_ACT_SOFTMAX = 3, ORC_ACT_TANH = 4 };
+enum { ORC_NN_F32 = 0, ORC_NN_F64ACC = 1, ORC_NN_BF16 = 2 };
+
+/* Feed-forward network.  dims[n_layers+1]; weights[l] is in x out column-major exactly as
+ * Nn::LinearLayer keeps it (element (i,o) at [o*in+i]); bias[l] is [out].  x is [T * dims[0]]
+ * (a frame is a contiguous column of the reference's dim x T matrix); out is [T * dims[n_layers]]. */
+int orc_nn_forward(int n_layers, const int* dims, const int* act, const float* const* weights,
+                   const float* const* bias, const float* x, long T, float* out, int mode);
+
+/* Nn::BatchFeatureScorer: softmax of the top layer not evaluated, scaled log-prior removed from the
+ * output bias, score = -activation.  log_prior may be NULL (scale 0). */
+int orc_nn_scores(int n_layers, const int* dims, const int* act, const float* const* weights,
+                  const float* const* bias, const float* log_prior, float prior_scale, const float* x,
+                  long T, float* scores, int mode);
+
+/* double-precision variants used to check the reference's own f64 unit-test vectors */
+int orc_nn_forward_f64(int n_layers, const int* dims, const int* act, const double* const* weights,
+                       const double* const* bias, const double* x, long T, double* out);
+
+const char* orc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,253 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so, oracle/_ref/libref_fft*.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package rasr_b200 never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+ACT = {"linear": 0, "sigmoid": 1, "relu": 2, "rectified": 2, "softmax": 3, "tanh": 4}
+NN_F32, NN_F64ACC, NN_BF16 = 0, 1, 2
+
+
+def build(ref=True):
+    """(Re)build liboracle.so and, when the reference checkout is present, oracle/_ref."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    if ref and os.path.isdir("/root/reference/src/Math"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "_ref"])
+
+
+class FrontendCfg(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_double),
+        ("window_length_s", C.c_double),
+        ("window_shift_s", C.c_double),
+        ("fft_max_input_s", C.c_double),
+        ("filter_width", C.c_double),
+        ("preemphasis_alpha", C.c_float),
+        ("n_cepstra", C.c_int),
+        ("derivatives", C.c_int),
+        ("use_fma", C.c_int),
+    ]
+
+
+class FrontendGeometry(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("win_length", "win_shift", "fft_length", "n_bins", "n_filters", "n_weights", "feat_dim")]
+
+
+class MixtureSetC(C.Structure):
+    _fields_ = [
+        ("dim", C.c_uint32),
+        ("n_mixtures", C.c_uint32),
+        ("n_densities", C.c_uint32),
+        ("n_means", C.c_uint32),
+        ("n_covariances", C.c_uint32),
+        ("mix_offsets", C.POINTER(C.c_uint32)),
+        ("mix_density", C.POINTER(C.c_uint32)),
+        ("mix_log_weight", C.POINTER(C.c_double)),
+        ("dens_mean", C.POINTER(C.c_uint32)),
+        ("dens_cov", C.POINTER(C.c_uint32)),
+        ("means", C.POINTER(C.c_float)),
+        ("variances", C.POINTER(C.c_float)),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        _lib = C.CDLL(path)
+        _lib.orc_frontend_nframes.restype = C.c_long
+        _lib.orc_frontend_nframes.argtypes = [C.POINTER(FrontendCfg), C.c_long]
+        _lib.orc_mfcc.restype = C.c_long
+        _lib.orc_version.restype = C.c_char_p
+    return _lib
+
+
+def ref_fft(native=False):
+    """The reference's own FFT object code (None when oracle/_ref has not been built)."""
+    path = os.path.join(_HERE, "_ref", "libref_fft_native.so" if native else "libref_fft.so")
+    if not os.path.exists(path):
+        return None
+    return C.CDLL(path)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def frontend_cfg(sample_rate=16000.0, window_length_s=0.025, window_shift_s=0.01, fft_max_input_s=0.025,
+                 filter_width=268.258, alpha=1.0, n_cepstra=13, derivatives=True, use_fma=True):
+    return FrontendCfg(sample_rate, window_length_s, window_shift_s, fft_max_input_s, filter_width, alpha,
+                       n_cepstra, int(derivatives), int(use_fma))
+
+
+def geometry(cfg):
+    g = FrontendGeometry()
+    rc = lib().orc_frontend_get_geometry(C.byref(cfg), C.byref(g))
+    if rc:
+        raise ValueError("invalid front-end configuration (%d)" % rc)
+    return g
+
+
+def nframes(cfg, n):
+    return int(lib().orc_frontend_nframes(C.byref(cfg), n))
+
+
+def tables(cfg):
+    g = geometry(cfg)
+    window = np.zeros(g.win_length, np.float32)
+    start = np.zeros(g.n_filters, np.int32)
+    end = np.zeros(g.n_filters, np.int32)
+    w = np.zeros((g.n_filters, g.n_bins), np.float32)
+    dct = np.zeros((cfg.n_cepstra, g.n_filters), np.float32)
+    lib().orc_frontend_tables(C.byref(cfg), _p(window, C.c_float), _p(start, C.c_int), _p(end, C.c_int),
+                              _p(w, C.c_float), _p(dct, C.c_float))
+    return dict(window=window, fb_start=start, fb_end=end, fb_weights=w, dct=dct)
+
+
+def mfcc(cfg, samples, chunk=0, stages=False):
+    samples = np.ascontiguousarray(samples, np.float32)
+    g = geometry(cfg)
+    T = nframes(cfg, samples.size)
+    feats = np.zeros((T, g.feat_dim), np.float32)
+    ts = np.zeros(T, np.float64)
+    te = np.zeros(T, np.float64)
+    spec = amp = fb = cep = None
+    if stages:
+        spec = np.zeros((T, g.fft_length + 2), np.float32)
+        amp = np.zeros((T, g.n_bins), np.float32)
+        fb = np.zeros((T, g.n_filters), np.float32)
+        cep = np.zeros((T, cfg.n_cepstra), np.float32)
+    n = lib().orc_mfcc(C.byref(cfg), _p(samples, C.c_float), C.c_long(samples.size), C.c_long(chunk),
+                       _p(feats, C.c_float), _p(ts, C.c_double), _p(te, C.c_double), _p(spec, C.c_float),
+                       _p(amp, C.c_float), _p(fb, C.c_float), _p(cep, C.c_float))
+    if n != T:
+        raise RuntimeError("oracle frame count %d != closed form %d" % (n, T))
+    out = dict(feats=feats, t_start=ts, t_end=te)
+    if stages:
+        out.update(spectrum=spec, amplitude=amp, fbank=fb, cepstra=cep)
+    return out
+
+
+def fft_real_packed(v):
+    v = np.ascontiguousarray(v, np.float32).copy()
+    lib().orc_fft_real_packed(_p(v, C.c_float), C.c_int(v.size))
+    return v
+
+
+class MixtureSet:
+    """Holds the numpy arrays alive behind an orc_mixture_set."""
+
+    def __init__(self, dim, mix_offsets, mix_density, mix_log_weight, dens_mean, dens_cov, means, variances):
+        self.a = dict(
+            mix_offsets=np.ascontiguousarray(mix_offsets, np.uint32),
+            mix_density=np.ascontiguousarray(mix_density, np.uint32),
+            mix_log_weight=np.ascontiguousarray(mix_log_weight, np.float64),
+            dens_mean=np.ascontiguousarray(dens_mean, np.uint32),
+            dens_cov=np.ascontiguousarray(dens_cov, np.uint32),
+            means=np.ascontiguousarray(means, np.float32).reshape(-1, dim),
+            variances=np.ascontiguousarray(variances, np.float32).reshape(-1, dim),
+        )
+        a = self.a
+        self.c = MixtureSetC(dim, a["mix_offsets"].size - 1, a["dens_mean"].size, a["means"].shape[0],
+                             a["variances"].shape[0], _p(a["mix_offsets"], C.c_uint32),
+                             _p(a["mix_density"], C.c_uint32), _p(a["mix_log_weight"], C.c_double),
+                             _p(a["dens_mean"], C.c_uint32), _p(a["dens_cov"], C.c_uint32),
+                             _p(a["means"], C.c_float), _p(a["variances"], C.c_float))
+        self.dim = dim
+        self.n_mixtures = a["mix_offsets"].size - 1
+
+
+def gmm_batch_float(ms, feats, use_fma=True, threads=1):
+    feats = np.ascontiguousarray(feats, np.float32)
+    T = feats.shape[0]
+    scores = np.zeros((T, ms.n_mixtures), np.float32)
+    if threads > 1:
+        rc = lib().orc_gmm_batch_float_mt(C.byref(ms.c), _p(feats, C.c_float), C.c_long(T), _p(scores, C.c_float),
+                                          int(use_fma), int(threads))
+    else:
+        rc = lib().orc_gmm_batch_float(C.byref(ms.c), _p(feats, C.c_float), C.c_long(T), _p(scores, C.c_float),
+                                       int(use_fma))
+    if rc:
+        raise RuntimeError("orc_gmm_batch_float failed: %d" % rc)
+    return scores
+
+
+def _gmm_diag(fn, ms, feats, mixture_weight_scale, gaussian_scale, use_fma):
+    feats = np.ascontiguousarray(feats, np.float32)
+    T = feats.shape[0]
+    scores = np.zeros((T, ms.n_mixtures), np.float32)
+    best = np.zeros((T, ms.n_mixtures), np.uint32)
+    rc = fn(C.byref(ms.c), C.c_float(mixture_weight_scale), C.c_float(gaussian_scale), _p(feats, C.c_float),
+            C.c_long(T), _p(scores, C.c_float), _p(best, C.c_uint32), int(use_fma))
+    if rc:
+        raise RuntimeError("oracle gmm scorer failed: %d" % rc)
+    return scores, best
+
+
+def gmm_diag_max(ms, feats, mixture_weight_scale=1.0, gaussian_scale=1.0, use_fma=True):
+    return _gmm_diag(lib().orc_gmm_diag_max, ms, feats, mixture_weight_scale, gaussian_scale, use_fma)
+
+
+def gmm_diag_sum(ms, feats, mixture_weight_scale=1.0, gaussian_scale=1.0, use_fma=True):
+    return _gmm_diag(lib().orc_gmm_diag_sum, ms, feats, mixture_weight_scale, gaussian_scale, use_fma)
+
+
+def _nn_args(dims, acts, weights, biases, dtype, ctype):
+    n = len(weights)
+    dims_a = np.asarray(dims, np.int32)
+    act_a = np.asarray([ACT[a] if isinstance(a, str) else a for a in acts], np.int32)
+    ws = [np.ascontiguousarray(w, dtype) for w in weights]
+    bs = [np.ascontiguousarray(b, dtype) for b in biases]
+    wp = (C.POINTER(ctype) * n)(*[_p(w, ctype) for w in ws])
+    bp = (C.POINTER(ctype) * n)(*[_p(b, ctype) for b in bs])
+    return n, dims_a, act_a, ws, bs, wp, bp
+
+
+def nn_forward(dims, acts, weights, biases, x, mode=NN_F32):
+    """weights[l]: array of shape (out, in) == the reference's in x out column-major storage."""
+    n, dims_a, act_a, ws, bs, wp, bp = _nn_args(dims, acts, weights, biases, np.float32, C.c_float)
+    x = np.ascontiguousarray(x, np.float32)
+    T = x.shape[0]
+    out = np.zeros((T, dims[-1]), np.float32)
+    rc = lib().orc_nn_forward(n, _p(dims_a, C.c_int), _p(act_a, C.c_int), wp, bp, _p(x, C.c_float), C.c_long(T),
+                              _p(out, C.c_float), int(mode))
+    if rc:
+        raise RuntimeError("orc_nn_forward failed: %d" % rc)
+    return out
+
+
+def nn_forward_f64(dims, acts, weights, biases, x):
+    n, dims_a, act_a, ws, bs, wp, bp = _nn_args(dims, acts, weights, biases, np.float64, C.c_double)
+    x = np.ascontiguousarray(x, np.float64)
+    T = x.shape[0]
+    out = np.zeros((T, dims[-1]), np.float64)
+    rc = lib().orc_nn_forward_f64(n, _p(dims_a, C.c_int), _p(act_a, C.c_int), wp, bp, _p(x, C.c_double),
+                                  C.c_long(T), _p(out, C.c_double))
+    if rc:
+        raise RuntimeError("orc_nn_forward_f64 failed: %d" % rc)
+    return out
+
+
+def nn_scores(dims, acts, weights, biases, log_prior, prior_scale, x, mode=NN_F32):
+    n, dims_a, act_a, ws, bs, wp, bp = _nn_args(dims, acts, weights, biases, np.float32, C.c_float)
+    x = np.ascontiguousarray(x, np.float32)
+    lp = np.ascontiguousarray(log_prior, np.float32) if log_prior is not None else None
+    T = x.shape[0]
+    out = np.zeros((T, dims[-1]), np.float32)
+    rc = lib().orc_nn_scores(n, _p(dims_a, C.c_int), _p(act_a, C.c_int), wp, bp, _p(lp, C.c_float),
+                             C.c_float(prior_scale), _p(x, C.c_float), C.c_long(T), _p(out, C.c_float), int(mode))
+    if rc:
+        raise RuntimeError("orc_nn_scores failed: %d" % rc)
+    return out

@@ -1,0 +1,124 @@
+"""Oracle pins for the GMM scorers: closed-form KATs and an independent float64 model.  CPU only.
+The reference has no unit test for any Mm scorer: parity unpinned by the
+reference, pinned here by derivation from the cited source."""
+import os
+
+import numpy as np
+import pytest
+
+from rasr_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def f64_scores(msd, feats, mode):
+    """-log p(x|m) under max approximation ('max') or exact mixture likelihood ('sum'), in float64."""
+    dim = msd["dim"]
+    mu = msd["means"].astype(np.float64)[msd["dens_mean"]]
+    var = msd["variances"].astype(np.float64)[msd["dens_cov"]]
+    x = feats.astype(np.float64)
+    lognorm = dim * np.log(2 * np.pi) + np.log(var).sum(1)
+    nm = msd["mix_offsets"].size - 1
+    out = np.zeros((x.shape[0], nm))
+    best = np.zeros((x.shape[0], nm), np.int64)
+    for m in range(nm):
+        e = slice(msd["mix_offsets"][m], msd["mix_offsets"][m + 1])
+        d = msd["mix_density"][e]
+        dist = (((x[:, None, :] - mu[d][None]) ** 2) / var[d][None]).sum(2)
+        s = 0.5 * (dist + lognorm[d][None] - 2 * msd["mix_log_weight"][e][None])
+        best[:, m] = s.argmin(1)
+        if mode == "max":
+            out[:, m] = s.min(1)
+        else:
+            mn = s.min(1)
+            out[:, m] = mn - np.log(np.exp(mn[:, None] - s).sum(1))
+    return out, best
+
+
+def test_single_density_closed_form(oracle):
+    """One mixture, one density, unit variance, weight 1: score = 0.5*(D*ln(2 pi) + |x-mu|^2)."""
+    D = 8
+    msd = dict(dim=D, mix_offsets=[0, 1], mix_density=[0], mix_log_weight=[0.0], dens_mean=[0], dens_cov=[0],
+               means=np.arange(D, dtype=np.float32)[None], variances=np.ones((1, D), np.float32))
+    ms = oracle.MixtureSet(**msd)
+    x = np.zeros((1, D), np.float32)
+    want = 0.5 * (D * np.log(2 * np.pi) + float((np.arange(D) ** 2).sum()))
+    for fn in (oracle.gmm_batch_float, lambda m, f: oracle.gmm_diag_max(m, f)[0], lambda m, f: oracle.gmm_diag_sum(m, f)[0]):
+        assert fn(ms, x)[0, 0] == pytest.approx(want, rel=1e-6)
+
+
+@pytest.mark.parametrize("dim", [39, 40, 13, 7])
+def test_batch_float_matches_f64(oracle, dim):
+    msd = synth.mixture_set(dim=dim, n_mixtures=24, densities_per_mixture=16, seed=11)
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(200, dim, seed=3)
+    want, _ = f64_scores(msd, f, "max")
+    for fma in (True, False):
+        got = oracle.gmm_batch_float(ms, f, use_fma=fma)
+        np.testing.assert_allclose(got, want, rtol=3e-6)
+    a = oracle.gmm_batch_float(ms, f, use_fma=True, threads=4)
+    assert np.array_equal(a, oracle.gmm_batch_float(ms, f, use_fma=True))
+
+
+@pytest.mark.parametrize("ncov", [1, 3])
+def test_diag_max_and_sum_match_f64(oracle, ncov):
+    msd = synth.ragged_mixture_set(dim=39, n_covariances=ncov, seed=21)
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(150, 39, seed=4)
+    want, wbest = f64_scores(msd, f, "max")
+    got, best = oracle.gmm_diag_max(ms, f)
+    np.testing.assert_allclose(got, want, rtol=3e-6)
+    # argmin may legitimately differ only on f32 near-ties
+    bad = best != wbest
+    if bad.any():
+        t, m = np.nonzero(bad)
+        assert np.all(np.abs(want[t, m] - got[t, m]) <= 3e-6 * np.abs(want[t, m]))
+    swant, _ = f64_scores(msd, f, "sum")
+    sgot, sbest = oracle.gmm_diag_sum(ms, f)
+    np.testing.assert_allclose(sgot, swant, rtol=5e-6, atol=1e-5)
+    assert np.array_equal(sbest, best) or (sbest != best).mean() < 1e-3
+    # log-sum-exp is never worse than the max approximation
+    assert np.all(sgot <= got + 1e-4)
+
+
+def test_pooled_batch_equals_diag_max_to_rounding(oracle):
+    """With one pooled covariance the two max scorers compute the same quantity in different order."""
+    msd = synth.mixture_set(dim=39, n_mixtures=16, densities_per_mixture=16, seed=5)
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(100, 39, seed=6)
+    a = oracle.gmm_batch_float(ms, f)
+    b, _ = oracle.gmm_diag_max(ms, f)
+    np.testing.assert_allclose(a, b, rtol=5e-6)
+
+
+def test_batch_float_rejects_multiple_covariances(oracle):
+    msd = synth.ragged_mixture_set(n_covariances=2)
+    ms = oracle.MixtureSet(**msd)
+    with pytest.raises(RuntimeError):
+        oracle.gmm_batch_float(ms, synth.features(2, 39))
+
+
+def test_scales(oracle):
+    msd = synth.ragged_mixture_set(dim=39, n_covariances=2, seed=8)
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(20, 39, seed=9)
+    # gaussian-scale g multiplies distance and log-norm by g (sqrt applied to isd, squared on the norm)
+    s1, _ = oracle.gmm_diag_max(ms, f, mixture_weight_scale=1.0, gaussian_scale=1.0)
+    zero_w = dict(msd)
+    zero_w["mix_log_weight"] = np.zeros_like(msd["mix_log_weight"])
+    msz = oracle.MixtureSet(**zero_w)
+    a, _ = oracle.gmm_diag_max(msz, f, 1.0, 1.0)
+    b, _ = oracle.gmm_diag_max(msz, f, 1.0, 4.0)
+    np.testing.assert_allclose(b, 4.0 * a, rtol=2e-6)
+    assert s1.shape == a.shape
+
+
+def test_golden_fixture(oracle):
+    g = np.load(os.path.join(GOLDEN, "gmm_ragged.npz"))
+    ms = oracle.MixtureSet(**synth.ragged_mixture_set(dim=39, n_covariances=1))
+    f = synth.features(64, 39, seed=5)
+    assert np.array_equal(oracle.gmm_batch_float(ms, f), g["batch"])
+    mx, mb = oracle.gmm_diag_max(ms, f)
+    assert np.array_equal(mx, g["max"]) and np.array_equal(mb, g["max_best"])
+    sm, sb = oracle.gmm_diag_sum(ms, f)
+    assert np.array_equal(sm, g["sum"]) and np.array_equal(sb, g["sum_best"])
