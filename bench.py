@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- acoustic frames scored/sec on B200 (BASELINE.json metric), one JSON line per run.
+
+Default workload (N=1) = BASELINE config C2: GMM FeatureScorer, 39-dim MFCC, 4096 diagonal Gaussians in
+256 mixtures, 100 000 frames.  A "step" = one dense scoring pass of the hot path over that batch.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+  value   frames/s with inputs resident in HBM (device pointers, rb_gmm_score_dev)
+  e2e     frames/s through the host-buffer C-ABI call rb_gmm_score (pinned host memory, H2D + D2H inside)
+  roofline  dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle restatement of Mm::BatchFloatFeatureScorer on the box's host cores
+
+Other workloads for profiling (not the contract line): --workload frontend | pipeline | nn | gmm-diag
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "acoustic_frames_scored_per_sec"
+UNIT = "frames/s"
+C2 = dict(dim=39, n_mixtures=256, densities_per_mixture=16, frames=100000)
+ALGO_BYTES_PER_FRAME = {"gmm": 39 * 4 + 256 * 4, "frontend": 160 * 4 + 39 * 4, "pipeline": 160 * 4 + 256 * 4,
+                        "nn": 429 * 4 + 12000 * 4}
+NN_FLOP_PER_FRAME = 2 * (429 * 2048 + 5 * 2048 * 2048 + 2048 * 12000)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), bf16=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1400.0))),
+                    source="measured")
+    return dict(hbm=6650.0, bf16=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle restatement of the reference's CPU scorer
+# --------------------------------------------------------------------------------------------
+
+def cpu_baseline_gmm(seconds=12.0):
+    """Oracle port of Mm::BatchFloatFeatureScorer on all host cores over a bounded sample of C2."""
+    from oracle import pyoracle as o
+    from rasr_b200 import synth
+
+    o.build(ref=False)
+    cores = os.cpu_count() or 1
+    ms = o.MixtureSet(**synth.mixture_set())
+    probe = synth.features(64 * cores, 39)
+    o.gmm_batch_float(ms, probe[:cores * 8], threads=cores)  # warm-up
+    t = time.perf_counter()
+    o.gmm_batch_float(ms, probe, threads=cores)
+    rate = probe.shape[0] / (time.perf_counter() - t)
+    n = int(min(C2["frames"], max(1024, rate * seconds)))
+    f = synth.features(C2["frames"], 39)[:n]
+    t = time.perf_counter()
+    o.gmm_batch_float(ms, f, threads=cores)
+    dt = time.perf_counter() - t
+    return dict(value=n / dt, unit=UNIT, cores=cores, kind="port",
+                sample="first %d of the 100000 C2 frames, all 256 mixtures, %d threads over frame ranges" % (n, cores))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as o
+    from rasr_b200 import synth
+
+    o.build(ref=False)
+    cores = os.cpu_count() or 1
+    ms = o.MixtureSet(**synth.mixture_set())
+    f_all = synth.features(C2["frames"], 39)
+    probe = f_all[:64 * cores]
+    o.gmm_batch_float(ms, probe, threads=cores)
+    t = time.perf_counter()
+    o.gmm_batch_float(ms, probe, threads=cores)
+    rate = probe.shape[0] / (time.perf_counter() - t)
+    budget = 150.0 / max(1, args.steps + args.warmup)  # the whole run ends within a few minutes
+    n = int(min(C2["frames"], max(1024, rate * min(budget, 20.0))))
+    f = f_all[:n]
+    for _ in range(args.warmup):
+        o.gmm_batch_float(ms, f, threads=cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        o.gmm_batch_float(ms, f, threads=cores)
+    dt = (time.perf_counter() - t) / args.steps
+    value = n / dt
+    sample = "first %d of the 100000 C2 frames per step, %d threads" % (n, cores)
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload="C2: GMM FeatureScorer, 39-dim, 4096 densities / 256 mixtures, 100k frames",
+                            note="reference cannot be built here (no libxml2/boost/BLAS); this is the oracle port of "
+                                 "Mm::BatchFloatFeatureScorer (SSE lane order) on the host cores"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "frontend", "pipeline", "nn"])
+    ap.add_argument("--frames", type=int, default=0, help="override the frame count of the workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from rasr_b200 import capi, flow, mm, nn, pipeline, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    peaks = measured_peaks()
+    wl = args.workload
+    R = 4  # rotating buffer sets so that no step finds its data in L2
+
+    # ---------------- workload set-up: every rank owns its own shard (weak scaling, no collective)
+    e2e_fn = None
+    if wl in ("gmm", "gmm-diag", "gmm-tensor"):
+        T = args.frames or C2["frames"]
+        msd = synth.mixture_set()
+        mode = {"gmm": "batch-float", "gmm-diag": "diagonal-maximum", "gmm-tensor": "batch-tensor"}[wl]
+        scorer = mm.GmmScorer(mm.MixtureSet.from_dict(msd), mode, device=local_rank)
+        feats_h = synth.features(T, 39, seed=2024 + rank)
+        d_in = [torch.from_numpy(feats_h).to(dev) for _ in range(R)]
+        d_out = [torch.empty((T, 256), dtype=torch.float32, device=dev) for _ in range(R)]
+
+        def step(i):
+            scorer.score_dev(d_in[i % R], T, d_out[i % R], None, sptr)
+
+        h_in = torch.from_numpy(feats_h).pin_memory()
+        h_out = torch.empty((T, 256), dtype=torch.float32).pin_memory()
+
+        def e2e_fn():
+            scorer.score(h_in, out=h_out)
+
+        h2d, d2h = T * 39 * 4, T * 256 * 4
+        units = T
+        workload = "C2: GMM FeatureScorer (%s), 39-dim, 4096 densities / 256 mixtures, %d frames per GPU" % (mode, T)
+        algo_bytes = ALGO_BYTES_PER_FRAME["gmm"] * T
+        bound, dtype = "hbm", "f32"
+    elif wl in ("frontend", "pipeline"):
+        n_utt = 125
+        if args.frames:
+            n_utt = max(1, args.frames // 1000)
+        samples_h, offs = synth.corpus(n_utt, n_samples=160240, seed0=3000 + 1000 * rank)
+        fe = flow.FrontEnd(device=local_rank)
+        fo = fe.count_frames(offs)
+        T = int(fo[-1])
+        d_samples = [torch.from_numpy(samples_h).to(dev) for _ in range(R)]
+        d_feats = [torch.empty((T, 39), dtype=torch.float32, device=dev) for _ in range(R)]
+        if wl == "frontend":
+            def step(i):
+                fe.process_dev(d_samples[i % R], offs, d_feats[i % R], sptr)
+
+            def e2e_fn():
+                fe.process(samples_h, offs, timestamps=False)
+
+            h2d, d2h = samples_h.size * 4, T * 39 * 4
+        else:
+            scorer = mm.GmmScorer(mm.MixtureSet.from_dict(synth.mixture_set()), device=local_rank)
+            d_scores = [torch.empty((T, 256), dtype=torch.float32, device=dev) for _ in range(R)]
+
+            def step(i):
+                pipeline.score_utterances_dev(fe, scorer, d_samples[i % R], offs, d_feats[i % R], d_scores[i % R], sptr)
+
+            def e2e_fn():
+                pipeline.score_utterances(fe, scorer, samples_h, offs)
+
+            h2d, d2h = samples_h.size * 4, T * 256 * 4
+        units = T
+        workload = "C3 shard: %s on %d utterances x 1000 frames per GPU (%d frames)" % (wl, n_utt, T)
+        algo_bytes = ALGO_BYTES_PER_FRAME[wl] * T
+        bound, dtype = "hbm", "f32"
+    else:  # nn
+        T = args.frames or 65536
+        net = synth.network()
+        sc = nn.NnScorer(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, "bf16",
+                         device=local_rank)
+        x_h = synth.features(T, 429, seed=4096 + rank, scale=1.0)
+        d_in = [torch.from_numpy(x_h).to(dev) for _ in range(2)]
+        d_out = [torch.empty((T, 12000), dtype=torch.float32, device=dev) for _ in range(2)]
+
+        def step(i):
+            sc.score_dev(d_in[i % 2], T, d_out[i % 2], sptr)
+
+        h_in = torch.from_numpy(x_h).pin_memory()
+        h_out = torch.empty((T, 12000), dtype=torch.float32).pin_memory()
+
+        def e2e_fn():
+            sc.score(h_in, out=h_out)
+
+        h2d, d2h = T * 429 * 4, T * 12000 * 4
+        units = T
+        workload = "C4: Nn 429 -> 6x2048 -> 12000 senones, bf16 tcgen05, %d frames per GPU" % T
+        algo_bytes = ALGO_BYTES_PER_FRAME["nn"] * T
+        bound, dtype = "tensor", "bf16"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = capi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev_all = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    t_wall = time.perf_counter()
+    ev_all[0].record(stream)
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        step(i)
+        ev[i][1].record(stream)
+    ev_all[1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop()
+    # dominant-kernel time: per-step event pairs on the launching stream (one step = one scoring launch)
+    dev_ms = float(np.sum([a.elapsed_time(b) for a, b in ev])) / args.steps
+    # step time: one event pair around EXACTLY K steps (inter-step gaps included), max over ranks
+    ms = torch.tensor([t_wall * 1e3 / args.steps], dtype=torch.float64, device=dev)
+    kms = torch.tensor([ev_all[0].elapsed_time(ev_all[1]) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(kms.item())
+    value = units * world / (ms_per_step * 1e-3)
+
+    # ---------------- end to end through the host-buffer C-ABI call
+    for _ in range(2):
+        e2e_fn()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_fn()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = units * world / (float(e2e_ms.item()) * 1e-3)
+
+    if rank == 0:
+        if bound == "hbm":
+            achieved = algo_bytes / (dev_ms * 1e-3) / 1e9
+            roof = dict(bound="hbm", achieved=achieved, peak=peaks["hbm"], unit="GB/s", frac=achieved / peaks["hbm"],
+                        traffic=None, peak_source=peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)")
+            if wl.startswith("gmm"):
+                sm_mhz = clocks.get("sm_mhz") or 1965.0
+                # CUDA-core ceiling of the reference-order arithmetic: sub + fma per (frame, density, dim)
+                fp32_ceiling = 148 * 128 * sm_mhz * 1e6 / (2 * 39 * 4096)
+                roof["fp32_alu"] = dict(ceiling_frames_per_s=fp32_ceiling, frac=(units / (dev_ms * 1e-3)) / fp32_ceiling,
+                                        note="direct-form GMM is FP32-issue bound: 2 FMA-pipe ops per "
+                                             "(frame,density,dim) at the sampled SM clock")
+        else:
+            achieved = NN_FLOP_PER_FRAME * units / (dev_ms * 1e-3) / 1e12
+            roof = dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
+                        frac=achieved / peaks["bf16"], traffic=None,
+                        peak_source=peaks["source"] + " (bf16_tflops_sustained)")
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            roof["traffic"] = json.load(open(tpath)).get(wl)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=dtype,
+                    data="synthetic",
+                    config=dict(workload=workload, sharding="independent frame/utterance shards per GPU, no collective",
+                                l2="rotating %d input/output buffer sets (> 126 MB L2) between timed steps" % R,
+                                wall_ms_per_step=float(ms.item())),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                             ms_per_step=float(e2e_ms.item()), api="host-buffer C-ABI call, pinned host memory"),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof)
+        if world == 1 and not args.no_cpu_baseline and wl == "gmm":
+            line["cpu_baseline"] = cpu_baseline_gmm()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,232 @@
+/*
+ * rasr_b200.h -- C ABI of librasr_b200.so: the B200-native acoustic front-end and emission-score
+ * engine that sits behind RASR's Flow::Node and Mm::FeatureScorer interfaces.
+ *
+ * The reference (rwth-i6/rasr) has no FFI / plugin ABI of its own: extensions are C++ classes that
+ * register themselves into Flow::Registry and Mm::FeatureScorerFactory at link time
+ * (src/Flow/Registry.hh:49-51, src/Mm/FeatureScorerFactory.hh:54-66).  The entry points below are
+ * what those two adapter classes (adapters/B200MfccNode.cc, adapters/B200FeatureScorer.cc, see
+ * INTEGRATION.md) bind; each one names the reference interface it replaces.  All paths are
+ * relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain C: opaque handles, plain pointers and sizes, no C++/torch types.
+ *   - every call returns RB_OK (0) or a negative rb_status; rb_last_error() gives the text of the
+ *     last failure on the calling thread.  Nothing throws, nothing aborts (the reference's
+ *     "no exceptions" rule, doc/architecture.rst:168; the adapter maps != 0 to criticalError()).
+ *   - host buffers are caller-owned; the library never frees or keeps caller memory.
+ *   - "*_dev" variants take DEVICE pointers on the handle's device and a cudaStream_t passed as
+ *     void* (NULL = the handle's own stream); they only enqueue work.
+ *   - a handle is bound to one CUDA device and is not thread-safe (the Flow pull graph and the
+ *     recognizer are single-threaded: src/Flow/Network.cc:507-538).
+ *   - there is NO CPU fallback: without a usable CUDA device every create call fails with
+ *     RB_ERR_NO_DEVICE.
+ */
+#ifndef RASR_B200_H
+#define RASR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RB_OK              = 0,
+    RB_ERR_INVALID     = -1, /* bad argument / configuration */
+    RB_ERR_NO_DEVICE   = -2, /* no CUDA device, or device is not sm_100 */
+    RB_ERR_CUDA        = -3, /* a CUDA runtime call or kernel failed */
+    RB_ERR_UNSUPPORTED = -4, /* valid in the reference but outside this engine (documented) */
+    RB_ERR_STATE       = -5, /* call order violates the node / scorer protocol */
+    RB_ERR_NOMEM       = -6
+} rb_status;
+
+const char* rb_last_error(void);
+const char* rb_version(void);
+/* number of usable sm_100 devices (0 when there is none; never fails) */
+int rb_device_count(void);
+/* kernels launched by this library since load (all handles, all threads) */
+uint64_t rb_launch_count(void);
+
+/* =====================================================================================
+ * Front-end: the Flow network of src/Tools/FeatureExtraction/share/mfcc.flow:8-34
+ *   signal-preemphasis -> signal-window (hamming) -> signal-real-fast-fourier-transform ->
+ *   signal-vector-alternating-complex-f32-amplitude -> signal-filterbank (mel) ->
+ *   generic-vector-f32-log -> signal-cosine-transform
+ * followed by derivationWithRegression.flow:7-27 (signal-delay / signal-regression x2 /
+ * generic-vector-f32-concat) when derivatives != 0.
+ * ===================================================================================== */
+
+typedef struct rb_frontend rb_frontend;
+
+typedef struct {
+    double sample_rate;       /* "sample-rate" attribute of the incoming samples stream */
+    double window_length_s;   /* signal-window length=   (src/Signal/Window.cc:69-82) */
+    double window_shift_s;    /* signal-window shift= */
+    double fft_max_input_s;   /* signal-real-fast-fourier-transform maximum-input-size=
+                                 (src/Signal/FastFourierTransform.hh:298-308) */
+    double filter_width;      /* signal-filterbank filter-width= in mel (mfcc.flow:24) */
+    float  preemphasis_alpha; /* signal-preemphasis alpha= (src/Signal/Preemphasis.cc:79) */
+    int    n_cepstra;         /* signal-cosine-transform nr-outputs= */
+    int    derivatives;       /* 0: static cepstra; 1: static || delta || delta-delta */
+    int    device;            /* CUDA device ordinal */
+} rb_frontend_cfg;
+
+typedef struct {
+    int win_length; /* samples */
+    int win_shift;  /* samples */
+    int fft_length; /* points */
+    int n_bins;     /* fft_length/2+1 */
+    int n_filters;
+    int n_weights;  /* non-zero filterbank taps */
+    int feat_dim;   /* n_cepstra * (derivatives ? 3 : 1) */
+} rb_frontend_geometry;
+
+/* fills *cfg with the mfcc.flow defaults for 16 kHz audio (13 cepstra + derivatives) */
+void rb_frontend_default_cfg(rb_frontend_cfg* cfg);
+
+/* node construction + configure(): builds window / twiddle / filterbank / DCT tables on the host in
+ * f64 exactly as the reference's init code does and uploads them.
+ * replaces: PreemphasisNode, WindowNode, FastFourierTransformNode, FilterBankNode::init
+ * (src/Signal/Filterbank.cc:765-797), CosineTransformNode::configure (src/Signal/CosineTransform.cc:199-211) */
+int rb_frontend_create(const rb_frontend_cfg* cfg, rb_frontend** out);
+void rb_frontend_destroy(rb_frontend* h);
+int rb_frontend_get_geometry(const rb_frontend* h, rb_frontend_geometry* g);
+/* host copies of the tables the kernels use (any pointer may be NULL):
+ * window[win_length], fb_start/fb_end[n_filters], fb_weights dense [n_filters*n_bins], dct[n_cepstra*n_filters] */
+int rb_frontend_get_tables(const rb_frontend* h, float* window, int* fb_start, int* fb_end, float* fb_weights,
+                           float* dct);
+/* frames the window node emits for one segment of n samples (WindowBuffer get/flush protocol,
+ * src/Signal/WindowBuffer.cc:50-126, flush-all=false) */
+long rb_frontend_nframes_for(const rb_frontend* h, long n_samples);
+
+/* --- streaming protocol = what Flow::Node::work() sees (src/Signal/SlidingAlgorithmNode.hh:60-80):
+ * packets of samples arrive in time order; on the EOS sentinel the segment is computed. */
+int  rb_frontend_reset(rb_frontend* h); /* EOS / new segment: state reset (src/Signal/Preemphasis.cc:96-106) */
+int  rb_frontend_push(rb_frontend* h, const float* samples, long n, double start_time);
+int  rb_frontend_finish(rb_frontend* h); /* runs the kernels on everything pushed since reset */
+long rb_frontend_nframes(const rb_frontend* h);
+/* feats [T*feat_dim] row-major (a frame = one Flow::Vector<f32>); t_start/t_end [T] = Timestamp of
+ * each emitted packet (src/Flow/Timestamp.hh:39-44); any pointer may be NULL */
+int rb_frontend_read(rb_frontend* h, float* feats, double* t_start, double* t_end);
+
+/* --- batch of independent segments (utterances) in one call: samples of utterance u are
+ * samples[offsets[u] .. offsets[u+1]).  frame_offsets [n_utt+1] receives the frame prefix sums;
+ * feats [frame_offsets[n_utt] * feat_dim].  Use rb_frontend_count_frames first to size buffers. */
+long rb_frontend_count_frames(const rb_frontend* h, const int64_t* offsets, int n_utt, int64_t* frame_offsets);
+int  rb_frontend_process(rb_frontend* h, const float* samples, const int64_t* offsets, int n_utt, float* feats,
+                         double* t_start, double* t_end);
+/* device variant: d_samples / d_feats are device pointers, offsets stays on the host.
+ * d_stage (optional, device, [total_frames*n_cepstra] floats) receives the static cepstra. */
+int rb_frontend_process_dev(rb_frontend* h, const float* d_samples, const int64_t* offsets, int n_utt,
+                            float* d_feats, void* stream);
+/* per-stage dumps of the last process/finish call for parity tests (host pointers, any may be NULL):
+ * amplitude [T*n_bins], fbank [T*n_filters] (before log), cepstra [T*n_cepstra].  Only filled when
+ * rb_frontend_set_debug(h, 1) was called before processing. */
+int rb_frontend_set_debug(rb_frontend* h, int on);
+int rb_frontend_read_stages(rb_frontend* h, float* amplitude, float* fbank, float* cepstra);
+
+/* =====================================================================================
+ * GMM emission scorer behind Mm::FeatureScorer (src/Mm/FeatureScorer.hh:28-167)
+ * ===================================================================================== */
+
+typedef struct rb_gmm rb_gmm;
+
+/* flat view of Mm::MixtureSet (src/Mm/MixtureSet.hh:123-201): mixtures -> (density, log weight),
+ * density -> (mean, covariance), means f32[dim], diagonal variances f32[dim] */
+typedef struct {
+    uint32_t        dim;
+    uint32_t        n_mixtures;
+    uint32_t        n_densities;
+    uint32_t        n_means;
+    uint32_t        n_covariances;
+    const uint32_t* mix_offsets;    /* [n_mixtures+1] into mix_density / mix_log_weight */
+    const uint32_t* mix_density;    /* density index of each mixture entry */
+    const double*   mix_log_weight; /* natural-log weight of each entry (Mm::Weight is f64) */
+    const uint32_t* dens_mean;      /* [n_densities] */
+    const uint32_t* dens_cov;       /* [n_densities] */
+    const float*    means;          /* [n_means*dim] */
+    const float*    variances;      /* [n_covariances*dim] */
+} rb_mixture_set;
+
+typedef enum {
+    /* Mm::BatchFloatFeatureScorer (src/Mm/BatchFeatureScorer.cc:164-253): one pooled covariance,
+     * maximum approximation, arithmetic in the reference's SSE lane order (bit-identical scores) */
+    RB_GMM_BATCH_FLOAT = 0,
+    /* Mm::GaussDiagonalMaximumFeatureScorer (src/Mm/GaussDiagonalMaximumFeatureScorer.cc:116-233):
+     * per-density covariance, maximum approximation, returns the best density */
+    RB_GMM_DIAG_MAX = 1,
+    /* Mm::GaussDiagonalSumFeatureScorer (same file :239-290): log-sum-exp over the mixture */
+    RB_GMM_DIAG_SUM = 2,
+    /* tensor-core formulation of RB_GMM_BATCH_FLOAT (split-precision GEMM |x|^2 - 2 x.mu + |mu|^2 on
+     * tcgen05, f32 accumulate); scores within 1e-4 relative of the reference, not bit-identical */
+    RB_GMM_BATCH_TENSOR = 3
+} rb_gmm_mode;
+
+/* contraction: 1 = fused multiply-add where the reference's default build (gcc -O2 -march=native,
+ * -ffp-contract=fast) fuses; 0 = every operation rounded separately (strict build) */
+int  rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_weight_scale, float gaussian_scale,
+                   int contraction, int device, rb_gmm** out);
+void rb_gmm_destroy(rb_gmm* h);
+int  rb_gmm_n_mixtures(const rb_gmm* h);
+int  rb_gmm_dim(const rb_gmm* h);
+/* dense scoring of T frames against ALL mixtures: scores [T*n_mixtures] row-major,
+ * scores[t][m] = -log p(x_t | m) (natural log, f32; Mm::Score, src/Mm/Types.hh:26).
+ * best_density (optional, modes DIAG_*): index within the mixture of the best density.
+ * replaces: fillScoreCacheTpl (src/Mm/BatchFeatureScorer.cc:207-253) for every emission and frame,
+ * i.e. what Speech::FeatureScorerNode materialises per frame (src/Speech/FeatureScorerNode.cc:95-111) */
+int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores, uint32_t* best_density);
+int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* d_scores, uint32_t* d_best_density,
+                     void* stream);
+
+/* =====================================================================================
+ * Legacy Nn feed-forward scorer (src/Nn/BatchFeatureScorer.cc:45-171, src/Nn/NeuralNetwork.cc:313-425)
+ * ===================================================================================== */
+
+typedef struct rb_nn rb_nn;
+
+enum { RB_ACT_LINEAR = 0, RB_ACT_SIGMOID = 1, RB_ACT_RELU = 2, RB_ACT_SOFTMAX = 3, RB_ACT_TANH = 4 };
+/* F32: f32 operands and accumulation on CUDA cores (parity with cblas_sgemm to 1e-4);
+ * BF16: bf16 operands on tcgen05 tensor cores, f32 accumulation in TMEM (the fast path) */
+enum { RB_NN_F32 = 0, RB_NN_BF16 = 1 };
+
+/* dims[n_layers+1]; weights[l] is the memory of the reference's in x out column-major matrix
+ * (element (i,o) at [o*in+i], src/Nn/LinearLayer.cc:402-420); bias[l] is [out] (may be NULL);
+ * log_prior [dims[n_layers]] or NULL (src/Nn/Prior.cc:159-188, removed from the output bias scaled by
+ * prior_scale: src/Nn/LinearLayer.cc:499-519). */
+int  rb_nn_create(int n_layers, const int* dims, const int* act, const float* const* weights,
+                  const float* const* bias, const float* log_prior, float prior_scale, int precision,
+                  int device, rb_nn** out);
+void rb_nn_destroy(rb_nn* h);
+int  rb_nn_n_outputs(const rb_nn* h);
+int  rb_nn_n_inputs(const rb_nn* h);
+/* scores [T*n_out]: score = -(w.h + b - prior_scale*log_prior), top-layer softmax NOT evaluated
+ * (src/Nn/BatchFeatureScorer.cc:64,148-171) */
+int rb_nn_score(rb_nn* h, const float* feats, long T, float* scores);
+int rb_nn_score_dev(rb_nn* h, const float* d_feats, long T, float* d_scores, void* stream);
+/* plain forward pass incl. the top-layer activation = neural-network-forward Flow node
+ * (src/Nn/NeuralNetworkForwardNode.cc:187-256) */
+int rb_nn_forward(rb_nn* h, const float* feats, long T, float* out);
+int rb_nn_forward_dev(rb_nn* h, const float* d_feats, long T, float* d_out, void* stream);
+
+/* =====================================================================================
+ * Fused audio -> scores pipeline (config C3): front-end and GMM scorer chained on the device,
+ * features never leave HBM.  scores [total_frames * n_mixtures].
+ * ===================================================================================== */
+int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samples, const int64_t* offsets, int n_utt,
+                      float* scores, float* feats /* optional host copy */);
+int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, const int64_t* offsets, int n_utt,
+                          float* d_feats, float* d_scores, void* stream);
+
+/* =====================================================================================
+ * Test hook: one bf16 tcgen05 GEMM  D[M x N] = A[M x K] * B[N x K]^T (+bias, activation),
+ * A/B f32 on the host, rounded to bf16 on the device.  Used by tests/ only.
+ * ===================================================================================== */
+int rb_test_gemm_bf16(const float* a, const float* b, const float* bias, int M, int N, int K, int act,
+                      float* d, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

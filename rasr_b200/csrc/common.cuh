@@ -1,0 +1,213 @@
+// common.cuh -- shared host/device helpers of librasr_b200 (error plumbing, launch accounting,
+// device buffers, PTX wrappers for cp.async.bulk / mbarrier used by the SIMT kernels).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rasr_b200.h"
+
+namespace rb {
+
+// ---------------------------------------------------------------- errors
+void        set_error(const char* fmt, ...);
+const char* get_error();
+
+#define RB_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            rb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return RB_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+#define RB_CHECK(expr)            \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != RB_OK)        \
+            return rc__;          \
+    } while (0)
+
+#define RB_REQUIRE(cond, ...)          \
+    do {                               \
+        if (!(cond)) {                 \
+            rb::set_error(__VA_ARGS__); \
+            return RB_ERR_INVALID;     \
+        }                              \
+    } while (0)
+
+// ---------------------------------------------------------------- launch accounting
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) {
+    g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+}
+// checks the launch itself (not completion)
+#define RB_LAUNCH_CHECK()                                                                          \
+    do {                                                                                           \
+        rb::count_launch();                                                                        \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) {                                                                  \
+            rb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return RB_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+// ---------------------------------------------------------------- device selection
+struct DeviceInfo {
+    int    ordinal = -1;
+    int    sm_count = 0;
+    int    cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+};
+// selects `device`, verifies it is sm_100, fills info.  RB_ERR_NO_DEVICE otherwise.
+int use_device(int device, DeviceInfo* info);
+
+// ---------------------------------------------------------------- RAII device / pinned buffers
+template<typename T>
+struct DevBuf {
+    T*     p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&)            = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    // grows only; contents are not preserved
+    int reserve(size_t count) {
+        if (count <= n)
+            return RB_OK;
+        release();
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            return RB_ERR_NOMEM;
+        }
+        n = count;
+        return RB_OK;
+    }
+    int upload(const T* host, size_t count, cudaStream_t s) {
+        RB_CHECK(reserve(count));
+        if (count)
+            RB_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        return RB_OK;
+    }
+    int upload(const std::vector<T>& v, cudaStream_t s) { return upload(v.data(), v.size(), s); }
+};
+
+template<typename T>
+struct PinnedBuf {
+    T*     p = nullptr;
+    size_t n = 0;
+    PinnedBuf() {}
+    PinnedBuf(const PinnedBuf&)            = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() {
+        if (p)
+            cudaFreeHost(p);
+    }
+    int reserve(size_t count) {
+        if (count <= n)
+            return RB_OK;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMallocHost of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            return RB_ERR_NOMEM;
+        }
+        n = count;
+        return RB_OK;
+    }
+};
+
+inline size_t round_up(size_t v, size_t m) {
+    return (v + m - 1) / m * m;
+}
+
+}  // namespace rb
+
+// ---------------------------------------------------------------- device-side PTX wrappers
+#ifdef __CUDACC__
+namespace rbdev {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    // make the init visible to the async proxy (TMA / tcgen05.commit)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as
+// a hung GPU.  try_wait itself suspends the thread for a HW-defined time slice per call.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    long long t0   = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ffu) == 0) {
+            long long now = clock64();
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+                printf("rasr_b200: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x,
+                       threadIdx.x, parity);
+                __trap();
+            }
+        }
+    }
+}
+// 1-D bulk copy global -> shared through the TMA unit (SASS: UBLKCP); bytes % 16 == 0, both
+// addresses 16-byte aligned; completion is signalled as transaction bytes on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+}  // namespace rbdev
+#endif

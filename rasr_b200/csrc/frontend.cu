@@ -1,0 +1,902 @@
+// frontend.cu -- the Flow MFCC pipeline as two frame-batched kernels (sm_100a).
+//
+// Replaces the per-frame pull chain of src/Tools/FeatureExtraction/share/mfcc.flow:8-34 and
+// derivationWithRegression.flow:7-27:
+//   Signal::Preemphasis::apply                         src/Signal/Preemphasis.cc:51-74
+//   Signal::WindowBuffer get/flush + Window::transform  src/Signal/WindowBuffer.cc:50-126, Window.cc:84-96
+//   HammingWindowFunction                               src/Signal/WindowFunction.cc:92-101
+//   RealFastFourierTransform (zero pad, radix-2, split) src/Signal/FastFourierTransform.cc:51-100,
+//                                                       src/Math/FastFourierTransform.cc:59-146
+//   alternatingComplexVectorAmplitude                   src/Signal/ComplexVectorFunction.hh:29-45
+//   FilterBank::apply (mel, triangular)                 src/Signal/Filterbank.cc:65-71,640-672
+//   VectorLogFunction (log10)                           src/Flow/SimpleFunction.hh:39-48
+//   CosineTransform::apply                              src/Signal/CosineTransform.cc:76-83
+//   Delay + Regression (first/second order) + concat    src/Signal/Delay.cc:137-183, Regression.cc:25-63
+//
+// Kernel 1 (mfcc_static_kernel): persistent CTAs; a CTA takes a tile of 32 consecutive frames of one
+// utterance, stages the 21 KB of samples the tile touches with one TMA bulk copy (the 2.5x frame
+// overlap is served from shared memory, HBM sees each sample once), keeps window / twiddles / mel
+// weights / DCT matrix in shared memory (one bulk copy per CTA), and each warp turns frames into
+// cepstra entirely on chip: pre-emphasis+window on the fly, 256-point complex FFT in shared memory,
+// real split, |.|, sparse mel taps, log10, DCT.  Only 13 floats per frame leave the SM.
+// Kernel 2 (mfcc_derivative_kernel): delta / delta-delta over the +-2 frame window with edge
+// replication, concatenated output, arithmetic in the reference's operation order.
+#include <cmath>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace {
+
+using namespace rbdev;
+
+constexpr int kWarps      = 8;
+constexpr int kThreads    = kWarps * 32;
+constexpr int kTileFrames = 32;
+
+struct Tile {
+    int utt;  // utterance index
+    int f0;   // first frame of the tile within the utterance
+    int nf;   // frames in the tile (<= kTileFrames)
+    int pad;
+};
+
+struct FeParams {
+    const float*   samples;     // concatenated utterances
+    const int64_t* sampleOff;   // [U+1]
+    const int64_t* frameOff;    // [U+1]
+    const Tile*    tiles;
+    int            nTiles;
+    const float*   tables;      // blob, see TableLayout
+    int            tableFloats;
+    // geometry
+    int   L, S, N, nBins, nFilters, nCep, featDim, derivatives;
+    float alpha, scale;
+    // table offsets (in floats) inside the blob
+    int oWindow, oTw, oTws, oFbStart, oFbEnd, oFbOff, oFbW, oDct;
+    // outputs
+    float* cep;        // [T * nCep]
+    float* feats;      // [T * featDim]
+    float* dbgAmp;     // [T * nBins] or null
+    float* dbgFbank;   // [T * nFilters] or null
+    int64_t totalSamples;
+};
+
+__device__ __forceinline__ int bitrev(int x, int bits) {
+    return (int)(__brev((unsigned)x) >> (32 - bits));
+}
+
+// dynamic shared memory layout (floats):
+//   tables[tableFloats] | samples[sampleCap] | per warp: z[N] amp[nBinsPad] fb[fbPad]
+__global__ void __launch_bounds__(kThreads) mfcc_static_kernel(const FeParams p, int sampleCap, int nBinsPad,
+                                                               int fbPad, int log2M) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t bar;
+
+    float* sTab     = smem;
+    float* sSamples = sTab + ((p.tableFloats + 3) & ~3);
+    float* sWarp    = sSamples + sampleCap;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int perWarp = p.N + nBinsPad + fbPad;
+    float*  z   = sWarp + warp * perWarp;
+    float*  amp = z + p.N;
+    float*  fb  = amp + nBinsPad;
+    float2* zc  = reinterpret_cast<float2*>(z);
+
+    const float*  sWindow = sTab + p.oWindow;
+    const float2* sTw     = reinterpret_cast<const float2*>(sTab + p.oTw);
+    const float2* sTws    = reinterpret_cast<const float2*>(sTab + p.oTws);
+    const int*    sFbStart = reinterpret_cast<const int*>(sTab + p.oFbStart);
+    const int*    sFbEnd   = reinterpret_cast<const int*>(sTab + p.oFbEnd);
+    const int*    sFbOff   = reinterpret_cast<const int*>(sTab + p.oFbOff);
+    const float*  sFbW     = sTab + p.oFbW;
+    const float*  sDct     = sTab + p.oDct;
+
+    uint32_t phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)p.tableFloats * 4u;  // blob is padded to 16 bytes on the host
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(sTab, p.tables, bytes, &bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+
+    const int M = p.N >> 1;  // complex points
+
+    for (int tileIdx = blockIdx.x; tileIdx < p.nTiles; tileIdx += gridDim.x) {
+        const Tile    tile   = p.tiles[tileIdx];
+        const int64_t uBeg   = p.sampleOff[tile.utt];
+        const int64_t uLen   = p.sampleOff[tile.utt + 1] - uBeg;
+        const int64_t fOut   = p.frameOff[tile.utt] + tile.f0;
+        // samples the tile touches, relative to the utterance: [s0 - 1, s1)
+        const int64_t s0 = (int64_t)tile.f0 * p.S;
+        int64_t       s1 = s0 + (int64_t)(tile.nf - 1) * p.S + p.L;
+        if (s1 > uLen)
+            s1 = uLen;
+        const int64_t gFirst = uBeg + (s0 > 0 ? s0 - 1 : 0);   // first global sample needed
+        const int64_t gLast  = uBeg + s1;                       // one past the last
+        const int64_t gA     = gFirst & ~(int64_t)3;            // 16-byte aligned start of the staged span
+        const int64_t gB     = gLast & ~(int64_t)3;             // aligned end of the bulk part
+        const int     lead   = (int)(gFirst - gA);              // smem index of sample gFirst
+        __syncthreads();  // previous tile fully consumed before the staging buffer is overwritten
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)(gB - gA) * 4u;
+            if (bytes) {
+                mbar_expect_tx(&bar, bytes);
+                bulk_g2s(sSamples, p.samples + gA, bytes, &bar);
+            }
+            else {
+                mbar_arrive(&bar);
+            }
+        }
+        // ragged tail (< 4 samples) with plain loads
+        if (threadIdx.x < (int)(gLast - gB))
+            sSamples[(int)(gB - gA) + threadIdx.x] = p.samples[gB + threadIdx.x];
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        __syncthreads();
+        // smem index of utterance sample i is  i - (s0>0 ? s0-1 : 0) + lead
+        const int base = lead - (int)(s0 > 0 ? s0 - 1 : 0);
+
+        for (int fi = warp; fi < tile.nf; fi += kWarps) {
+            const int64_t fs  = (int64_t)(tile.f0 + fi) * p.S;  // first sample of the frame
+            int           len = p.L;
+            if (fs + len > uLen)
+                len = (int)(uLen - fs);  // short last frame (WindowBuffer::flush)
+            // ---- pre-emphasis + window + zero padding, written in bit-reversed complex order
+            for (int n = lane; n < p.N; n += 32) {
+                float v = 0.0f;
+                if (n < len) {
+                    const int64_t i   = fs + n;
+                    const float   cur = sSamples[base + (int)i];
+                    // the first sample of a segment is its own predecessor (Preemphasis.cc:54-55)
+                    const float prev = i > 0 ? sSamples[base + (int)i - 1] : cur;
+                    const float e    = p.alpha == 1.0f ? __fsub_rn(cur, prev) : __fmaf_rn(-p.alpha, prev, cur);
+                    v                = __fmul_rn(sWindow[n], e);
+                }
+                z[2 * bitrev(n >> 1, log2M) + (n & 1)] = v;
+            }
+            __syncwarp();
+            // ---- radix-2 decimation-in-time, twiddles e^{+i 2 pi k / M}
+            for (int h = 1; h < M; h <<= 1) {
+                const int tstep = (M >> 1) / h;
+                for (int bf = lane; bf < (M >> 1); bf += 32) {
+                    const int    pos = bf & (h - 1);
+                    const int    i   = ((bf - pos) << 1) + pos;
+                    const int    j   = i + h;
+                    const float2 w   = sTw[pos * tstep];
+                    const float2 a = zc[i], b = zc[j];
+                    const float  tR = __fmaf_rn(w.x, b.x, -__fmul_rn(w.y, b.y));
+                    const float  tI = __fmaf_rn(w.x, b.y, __fmul_rn(w.y, b.x));
+                    zc[j]           = make_float2(__fsub_rn(a.x, tR), __fsub_rn(a.y, tI));
+                    zc[i]           = make_float2(__fadd_rn(a.x, tR), __fadd_rn(a.y, tI));
+                }
+                __syncwarp();
+            }
+            // ---- split into the spectrum of the real sequence, scale by 1/sampleRate, amplitude
+            for (int k = lane; k <= (M >> 1); k += 32) {
+                if (k == 0) {
+                    const float2 a = zc[0];
+                    const float  x0 = __fmul_rn(__fadd_rn(a.x, a.y), p.scale);
+                    const float  xn = __fmul_rn(__fsub_rn(a.x, a.y), p.scale);
+                    amp[0]          = fabsf(x0);
+                    amp[M]          = fabsf(xn);
+                }
+                else if (k == (M >> 1)) {
+                    const float2 a  = zc[k];
+                    const float  re = __fmul_rn(a.x, p.scale), im = __fmul_rn(a.y, p.scale);
+                    amp[k]          = __fsqrt_rn(__fmaf_rn(re, re, __fmul_rn(im, im)));
+                }
+                else {
+                    const float2 a = zc[k], b = zc[M - k];
+                    const float2 w = sTws[k];
+                    const float  h1R = 0.5f * (a.x + b.x), h1I = 0.5f * (a.y - b.y);
+                    const float  h2R = 0.5f * (a.y + b.y), h2I = -0.5f * (a.x - b.x);
+                    const float  uR = __fmaf_rn(w.x, h2R, -__fmul_rn(w.y, h2I));  // wR*h2R - wI*h2I
+                    const float  uI = __fmaf_rn(w.x, h2I, __fmul_rn(w.y, h2R));   // wR*h2I + wI*h2R
+                    float        re = __fmul_rn(h1R + uR, p.scale), im = __fmul_rn(h1I + uI, p.scale);
+                    amp[k]          = __fsqrt_rn(__fmaf_rn(re, re, __fmul_rn(im, im)));
+                    re              = __fmul_rn(h1R - uR, p.scale);
+                    im              = __fmul_rn(uI - h1I, p.scale);
+                    amp[M - k]      = __fsqrt_rn(__fmaf_rn(re, re, __fmul_rn(im, im)));
+                }
+            }
+            __syncwarp();
+            const int64_t t = fOut + fi;
+            if (p.dbgAmp)
+                for (int k = lane; k < p.nBins; k += 32)
+                    p.dbgAmp[t * p.nBins + k] = amp[k];
+            // ---- mel filter bank: sequential f32 multiply-add over the taps of each filter
+            for (int f = lane; f < p.nFilters; f += 32) {
+                const int    a = sFbStart[f], e = sFbEnd[f];
+                const float* w = sFbW + sFbOff[f];
+                float        r = 0.0f;
+                for (int k = a; k < e; ++k)
+                    r = __fmaf_rn(amp[k], w[k - a], r);
+                if (p.dbgFbank)
+                    p.dbgFbank[t * p.nFilters + f] = r;
+                fb[f] = log10f(r);
+            }
+            __syncwarp();
+            // ---- DCT-II (unnormalised), sequential dot product per cepstral coefficient
+            for (int c = lane; c < p.nCep; c += 32) {
+                const float* row = sDct + c * p.nFilters;
+                float        r   = 0.0f;
+                for (int n = 0; n < p.nFilters; ++n)
+                    r = __fmaf_rn(row[n], fb[n], r);
+                p.cep[t * p.nCep + c] = r;
+                if (!p.derivatives)
+                    p.feats[t * p.featDim + c] = r;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// one thread per (frame, coefficient): static | delta | delta-delta
+__global__ void __launch_bounds__(256) mfcc_derivative_kernel(const FeParams p) {
+    for (int tileIdx = blockIdx.x; tileIdx < p.nTiles; tileIdx += gridDim.x) {
+        const Tile    tile = p.tiles[tileIdx];
+        const int64_t u0   = p.frameOff[tile.utt];
+        const int64_t nU   = p.frameOff[tile.utt + 1] - u0;
+        const int     K    = p.nCep;
+        for (int idx = threadIdx.x; idx < tile.nf * K; idx += blockDim.x) {
+            const int     fi = idx / K, c = idx - fi * K;
+            const int64_t ft = tile.f0 + fi;  // frame within the utterance
+            float         f[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                int64_t u = ft + i - 2;
+                u         = u < 0 ? 0 : (u > nU - 1 ? nU - 1 : u);  // margin-policy copy
+                f[i]      = p.cep[(u0 + u) * K + c];
+            }
+            // regressFirstOrder (Regression.cc:25-39): sum dt*f / sum dt^2, dt = i - 2
+            float d = 0.0f, tm = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const float dt = (float)i - 2.0f;
+                d              = __fmaf_rn(dt, f[i], d);
+                tm             = __fmaf_rn(dt, dt, tm);
+            }
+            d = __fdiv_rn(d, tm);
+            // regressSecondOrder (Regression.cc:41-63)
+            float ns = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const float dt = (float)i - 2.0f;
+                ns             = __fmaf_rn(__fmul_rn(__fmul_rn(dt, dt), dt), dt, ns);
+            }
+            ns       = __fmaf_rn(-5.0f, ns, __fmul_rn(tm, tm));
+            float dd = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const float dt = (float)i - 2.0f;
+                dd             = __fmaf_rn(f[i], tm, dd);
+                const float t  = __fmul_rn(__fmul_rn(f[i], dt), dt);
+                dd             = __fmaf_rn(-t, 5.0f, dd);
+            }
+            dd = (float)((double)dd * (2.0 / (double)ns));
+            float* o  = p.feats + (u0 + ft) * p.featDim;
+            o[c]         = f[2];
+            o[K + c]     = d;
+            o[2 * K + c] = dd;
+        }
+    }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+
+struct rb_frontend {
+    rb::DeviceInfo  dev;
+    rb_frontend_cfg cfg;
+    cudaStream_t    stream = nullptr;
+    // geometry
+    double sampleRate = 0;  // as read back from the text attribute
+    int    L = 0, S = 0, N = 0, nBins = 0, nFilters = 0, nWeights = 0, featDim = 0, log2M = 0;
+    // host tables
+    std::vector<float> window, dct, fbWeights;  // fbWeights: concatenated taps
+    std::vector<int>   fbStart, fbEnd, fbOff;
+    std::vector<float> blob;
+    int oWindow = 0, oTw = 0, oTws = 0, oFbStart = 0, oFbEnd = 0, oFbOff = 0, oFbW = 0, oDct = 0;
+    // launch configuration
+    int    sampleCap = 0, nBinsPad = 0, fbPad = 0, grid = 0;
+    size_t smemBytes = 0;
+    // device buffers
+    rb::DevBuf<float>   dTables, dSamples, dCep, dFeats, dDbgAmp, dDbgFbank;
+    rb::DevBuf<int64_t> dSampleOff, dFrameOff;
+    rb::DevBuf<Tile>    dTiles;
+    rb::PinnedBuf<int64_t> hOff;
+    rb::PinnedBuf<Tile>    hTiles;
+    // streaming state
+    std::vector<float> pending;
+    double             pendingStart = 0;
+    bool               havePending  = false;
+    // results of the last finish()/process()
+    long                 lastFrames = 0;
+    std::vector<float>   lastFeats;
+    std::vector<double>  lastStart, lastEnd;
+    bool                 debug = false;
+    long                 dbgFrames = 0;
+
+    ~rb_frontend() {
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+// Flow attributes travel as text with default ostream precision (src/Flow/Attributes.hh:104-113)
+double attribute_round_trip(double v) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%g", v);  // "%g" == default ostream formatting (6 significant digits)
+    return atof(buf);
+}
+
+bool almost_equal(double a, double b) {  // Core::isAlmostEqual src/Core/Utility.hh:322-327
+    const double eps = 2.2204460492503131e-16, tiny = 2.2250738585072014e-308;
+    return std::fabs(a - b) < (std::fabs(a) + std::fabs(b) + tiny) * eps;
+}
+
+bool almost_integer(double x) {  // FilterBank::isAlmostInteger src/Signal/Filterbank.cc:690-693
+    return std::fabs(x - std::round(x)) < 1e-10;
+}
+
+struct MelScale {
+    double hzPerIndex;  // continuous frequency of one FFT bin
+    double toMel(double index) const { return 2595.0 * std::log10(1.0 + hzPerIndex * index / 700.0); }
+    double toIndex(double mel) const { return (1.0 / hzPerIndex) * ((std::pow(10.0, (1.0 / 2595.0) * mel) - 1.0) * 700.0); }
+    double slope(double index) const { return 2595.0 * (1.0 / std::log(10.0) / (700.0 + hzPerIndex * index)); }
+};
+
+int build_geometry(rb_frontend* h) {
+    const rb_frontend_cfg& c = h->cfg;
+    RB_REQUIRE(c.sample_rate > 0, "sample rate must be positive");
+    RB_REQUIRE(c.n_cepstra >= 1, "nr-outputs of the cosine transform must be >= 1");
+    h->sampleRate = attribute_round_trip(c.sample_rate);
+    h->L          = (int)(unsigned)rint(c.window_length_s * h->sampleRate);  // Window.cc:73-79
+    h->S          = (int)(unsigned)rint(c.window_shift_s * h->sampleRate);
+    RB_REQUIRE(h->L >= 1 && h->S >= 1, "window length/shift round to zero samples");
+    const unsigned maxLen = (unsigned)ceil(c.fft_max_input_s * h->sampleRate);
+    RB_REQUIRE(maxLen >= 1, "maximum-input-size of the FFT is zero");
+    double power = std::log((double)maxLen) / std::log(2.0);  // FastFourierTransform.cc:30-41
+    power        = almost_equal(power, rint(power)) ? rint(power) : ceil(power);
+    RB_REQUIRE(power <= 12, "FFT length 2^%d is outside the supported range (<= 4096)", (int)power);
+    h->N = 1 << (unsigned)power;
+    if (h->N < 64) {
+        rb::set_error("FFT length %d < 64 is not supported by the warp-level transform", h->N);
+        return RB_ERR_UNSUPPORTED;
+    }
+    RB_REQUIRE(h->L <= h->N, "window of %d samples does not fit the %d-point FFT", h->L, h->N);
+    h->nBins = h->N / 2 + 1;
+    h->log2M = (int)power - 1;
+    return RB_OK;
+}
+
+// FilterBankNode::init + StretchToCover + FilterBuilder (src/Signal/Filterbank.cc:144-244,523-569,765-820)
+int build_filterbank(rb_frontend* h) {
+    MelScale mel;
+    const double fftOutRate = attribute_round_trip(h->N / h->sampleRate);  // "sample-rate" after the FFT node
+    mel.hzPerIndex          = 1.0 / fftOutRate;
+    const double lo = 0.0, hi = mel.toMel(h->nBins - 1);
+    double       width = h->cfg.filter_width;
+    RB_REQUIRE(width > 0, "filter-width must be positive");
+    double spacing = 0.5 * width;
+    double count   = (hi - lo - width) / spacing + 1;
+    if (count < 1)
+        count = 1;
+    else if (almost_integer(count))
+        count = std::round(count);
+    const size_t nF       = (size_t)std::floor(count);
+    const double coverage = (spacing * (nF - 1) + width) / (hi - lo);
+    if (!(nF == 1 && coverage > 1 && !almost_equal(coverage, 1))) {
+        width /= coverage;
+        spacing /= coverage;
+    }
+    h->nFilters = (int)nF;
+    h->fbStart.resize(nF);
+    h->fbEnd.resize(nF);
+    h->fbOff.resize(nF);
+    h->fbWeights.clear();
+    for (size_t i = 0; i < nF; ++i) {
+        const double center = lo + spacing * i + 0.5 * width;
+        double       a      = mel.toIndex(std::max(center - 0.5 * width, lo));
+        a                   = almost_integer(a) ? std::round(a) : std::ceil(a);
+        double e            = mel.toIndex(std::min(center + 0.5 * width, hi));
+        e                   = almost_integer(e) ? std::round(e) + 1 : std::ceil(e);
+        h->fbStart[i]       = (int)(size_t)a;
+        h->fbEnd[i]         = (int)(size_t)e;
+        RB_REQUIRE(h->fbStart[i] >= 0 && h->fbEnd[i] <= h->nBins && h->fbStart[i] <= h->fbEnd[i],
+                   "filter %zu covers bins [%d,%d) outside the spectrum", i, h->fbStart[i], h->fbEnd[i]);
+        h->fbOff[i] = (int)h->fbWeights.size();
+        for (int k = h->fbStart[i]; k < h->fbEnd[i]; ++k) {
+            float tri = (float)(1.0 - std::fabs(mel.toMel(k) - center) / (width / 2));
+            if (!(tri >= 0))
+                tri = 0;
+            h->fbWeights.push_back((float)(tri * mel.slope(k)));
+        }
+    }
+    h->nWeights = (int)h->fbWeights.size();
+    return RB_OK;
+}
+
+int build_tables(rb_frontend* h) {
+    // Hamming window, symmetric, M = L-1 (WindowFunction.cc:92-101)
+    h->window.assign(h->L, 0.0f);
+    if (h->L > 1) {
+        const unsigned Mw = h->L - 1;
+        for (unsigned n = 0; n <= Mw / 2; ++n)
+            h->window[n] = h->window[Mw - n] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * n / Mw));
+    }
+    RB_CHECK(build_filterbank(h));
+    // DCT-II, even about N-1/2 (CosineTransform.cc:62-74)
+    const int K = h->cfg.n_cepstra, F = h->nFilters;
+    h->dct.resize((size_t)K * F);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < F; ++n)
+            h->dct[(size_t)k * F + n] = (float)cos(M_PI * (n + 0.5) / F * k);
+    // twiddles: e^{+i 2 pi k / M} for the complex transform (k < M/2) and e^{+i 2 pi k / N} for the split
+    const int M = h->N / 2;
+    std::vector<float> tw((size_t)M, 0.0f), tws((size_t)M, 0.0f);
+    for (int k = 0; k < M / 2; ++k) {
+        tw[2 * k]      = (float)cos(2.0 * M_PI * k / M);
+        tw[2 * k + 1]  = (float)sin(2.0 * M_PI * k / M);
+        tws[2 * k]     = (float)cos(2.0 * M_PI * k / h->N);
+        tws[2 * k + 1] = (float)sin(2.0 * M_PI * k / h->N);
+    }
+    // blob
+    std::vector<float>& b = h->blob;
+    b.clear();
+    auto align4 = [&]() {
+        while (b.size() % 4)
+            b.push_back(0.0f);
+    };
+    auto put_f = [&](const std::vector<float>& v) {
+        align4();
+        int o = (int)b.size();
+        b.insert(b.end(), v.begin(), v.end());
+        return o;
+    };
+    auto put_i = [&](const std::vector<int>& v) {
+        align4();
+        int o = (int)b.size();
+        for (int x : v) {
+            float f;
+            std::memcpy(&f, &x, 4);
+            b.push_back(f);
+        }
+        return o;
+    };
+    h->oWindow  = put_f(h->window);
+    h->oTw      = put_f(tw);
+    h->oTws     = put_f(tws);
+    h->oFbStart = put_i(h->fbStart);
+    h->oFbEnd   = put_i(h->fbEnd);
+    h->oFbOff   = put_i(h->fbOff);
+    h->oFbW     = put_f(h->fbWeights);
+    h->oDct     = put_f(h->dct);
+    align4();
+    return RB_OK;
+}
+
+long frames_for(const rb_frontend* h, long n) {
+    if (n <= 0)
+        return 0;
+    const long M = std::max(h->S, h->L);
+    if (n <= M)
+        return 1;
+    return (n - M + h->S - 1) / h->S + 1;
+}
+
+// Timestamps exactly as the nodes produce them: WindowBuffer accumulates bufferStart by repeated
+// += shift/sampleRate (WindowBuffer.cc:94); merged packets span [min start, max end] of the delay window
+void timestamps(const rb_frontend* h, long nSamples, double start0, long T, double* ts, double* te) {
+    if (!ts && !te)
+        return;
+    std::vector<double> s(T), e(T);
+    double              cur = start0;
+    for (long t = 0; t < T; ++t) {
+        long len = h->L;
+        if ((long)t * h->S + len > nSamples)
+            len = nSamples - (long)t * h->S;
+        s[t] = cur;
+        e[t] = cur + (double)len / (double)h->sampleRate;
+        cur += (double)h->S / (double)h->sampleRate;
+    }
+    for (long t = 0; t < T; ++t) {
+        double a = s[t], b = e[t];
+        if (h->cfg.derivatives)
+            for (int i = -2; i <= 2; ++i) {
+                long u = std::min<long>(std::max<long>(t + i, 0), T - 1);
+                a      = std::min(a, s[u]);
+                b      = std::max(b, e[u]);
+            }
+        if (ts)
+            ts[t] = a;
+        if (te)
+            te[t] = b;
+    }
+}
+
+int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, int nUtt, float* dFeats,
+               cudaStream_t s, int64_t* totalFramesOut) {
+    // frame prefix sums + tile table
+    RB_CHECK(h->hOff.reserve((size_t)2 * (nUtt + 1)));
+    int64_t* sOff = h->hOff.p;
+    int64_t* fOff = h->hOff.p + (nUtt + 1);
+    sOff[0] = offsets[0];
+    fOff[0] = 0;
+    size_t nTiles = 0;
+    for (int u = 0; u < nUtt; ++u) {
+        RB_REQUIRE(offsets[u + 1] >= offsets[u], "sample offsets not monotone at utterance %d", u);
+        sOff[u + 1]  = offsets[u + 1];
+        const long T = frames_for(h, (long)(offsets[u + 1] - offsets[u]));
+        fOff[u + 1]  = fOff[u] + T;
+        nTiles += (size_t)(T + kTileFrames - 1) / kTileFrames;
+    }
+    const int64_t total = fOff[nUtt];
+    if (totalFramesOut)
+        *totalFramesOut = total;
+    if (total == 0)
+        return RB_OK;
+    RB_REQUIRE(nTiles < (size_t)1 << 31, "too many frames in one call");
+    RB_CHECK(h->hTiles.reserve(nTiles));
+    size_t ti = 0;
+    for (int u = 0; u < nUtt; ++u) {
+        const long T = (long)(fOff[u + 1] - fOff[u]);
+        for (long f0 = 0; f0 < T; f0 += kTileFrames) {
+            Tile t;
+            t.utt = u;
+            t.f0  = (int)f0;
+            t.nf  = (int)std::min<long>(kTileFrames, T - f0);
+            t.pad = 0;
+            h->hTiles.p[ti++] = t;
+        }
+    }
+    // the previous call's tables must have been consumed before the pinned staging is rewritten
+    RB_CHECK(h->dSampleOff.reserve(nUtt + 1));
+    RB_CHECK(h->dFrameOff.reserve(nUtt + 1));
+    RB_CHECK(h->dTiles.reserve(nTiles));
+    RB_CHECK(h->dCep.reserve((size_t)total * h->cfg.n_cepstra));
+    RB_CUDA(cudaMemcpyAsync(h->dSampleOff.p, sOff, sizeof(int64_t) * (nUtt + 1), cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaMemcpyAsync(h->dFrameOff.p, fOff, sizeof(int64_t) * (nUtt + 1), cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaMemcpyAsync(h->dTiles.p, h->hTiles.p, sizeof(Tile) * nTiles, cudaMemcpyHostToDevice, s));
+
+    FeParams p;
+    p.samples      = dSamples;
+    p.sampleOff    = h->dSampleOff.p;
+    p.frameOff     = h->dFrameOff.p;
+    p.tiles        = h->dTiles.p;
+    p.nTiles       = (int)nTiles;
+    p.tables       = h->dTables.p;
+    p.tableFloats  = (int)h->blob.size();
+    p.L            = h->L;
+    p.S            = h->S;
+    p.N            = h->N;
+    p.nBins        = h->nBins;
+    p.nFilters     = h->nFilters;
+    p.nCep         = h->cfg.n_cepstra;
+    p.featDim      = h->featDim;
+    p.derivatives  = h->cfg.derivatives;
+    p.alpha        = h->cfg.preemphasis_alpha;
+    p.scale        = h->sampleRate != 1 ? 1 / (float)h->sampleRate : 1.0f;
+    p.oWindow      = h->oWindow;
+    p.oTw          = h->oTw;
+    p.oTws         = h->oTws;
+    p.oFbStart     = h->oFbStart;
+    p.oFbEnd       = h->oFbEnd;
+    p.oFbOff       = h->oFbOff;
+    p.oFbW         = h->oFbW;
+    p.oDct         = h->oDct;
+    p.cep          = h->dCep.p;
+    p.feats        = dFeats;
+    p.dbgAmp       = nullptr;
+    p.dbgFbank     = nullptr;
+    p.totalSamples = offsets[nUtt];
+    if (h->debug) {
+        RB_CHECK(h->dDbgAmp.reserve((size_t)total * h->nBins));
+        RB_CHECK(h->dDbgFbank.reserve((size_t)total * h->nFilters));
+        p.dbgAmp     = h->dDbgAmp.p;
+        p.dbgFbank   = h->dDbgFbank.p;
+        h->dbgFrames = (long)total;
+    }
+    const int grid = (int)std::min<size_t>(nTiles, (size_t)h->grid);
+    mfcc_static_kernel<<<grid, kThreads, h->smemBytes, s>>>(p, h->sampleCap, h->nBinsPad, h->fbPad, h->log2M);
+    RB_LAUNCH_CHECK();
+    if (h->cfg.derivatives) {
+        const int grid2 = (int)std::min<size_t>(nTiles, (size_t)h->dev.sm_count * 8);
+        mfcc_derivative_kernel<<<grid2, 256, 0, s>>>(p);
+        RB_LAUNCH_CHECK();
+    }
+    // the pinned tile/offset staging is reused by the next call
+    RB_CUDA(cudaStreamSynchronize(s));
+    return RB_OK;
+}
+
+}  // namespace
+
+extern "C" void rb_frontend_default_cfg(rb_frontend_cfg* cfg) {
+    if (!cfg)
+        return;
+    cfg->sample_rate       = 16000.0;
+    cfg->window_length_s   = 0.025;
+    cfg->window_shift_s    = 0.01;
+    cfg->fft_max_input_s   = 0.025;
+    cfg->filter_width      = 268.258;
+    cfg->preemphasis_alpha = 1.0f;
+    cfg->n_cepstra         = 13;
+    cfg->derivatives       = 1;
+    cfg->device            = 0;
+}
+
+extern "C" int rb_frontend_create(const rb_frontend_cfg* cfg, rb_frontend** out) {
+    RB_REQUIRE(cfg && out, "NULL argument");
+    *out = nullptr;
+    rb_frontend* h = new (std::nothrow) rb_frontend();
+    if (!h) {
+        rb::set_error("out of host memory");
+        return RB_ERR_NOMEM;
+    }
+    h->cfg = *cfg;
+    auto fail = [&](int code) {
+        delete h;
+        return code;
+    };
+    // geometry and tables first: configuration errors are reported even without a device
+    int rc = build_geometry(h);
+    if (rc == RB_OK)
+        rc = build_tables(h);
+    if (rc != RB_OK)
+        return fail(rc);
+    h->featDim = cfg->n_cepstra * (cfg->derivatives ? 3 : 1);
+    rc = rb::use_device(cfg->device, &h->dev);
+    if (rc != RB_OK)
+        return fail(rc);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        rb::set_error("cudaStreamCreate failed");
+        return fail(RB_ERR_CUDA);
+    }
+    // shared memory plan
+    h->sampleCap = (int)rb::round_up((size_t)(kTileFrames - 1) * h->S + h->L + 1 + 8, 4);
+    h->nBinsPad  = (int)rb::round_up(h->nBins, 4);
+    h->fbPad     = (int)rb::round_up(std::max(h->nFilters, 4), 4);
+    const size_t floats = rb::round_up(h->blob.size(), 4) + h->sampleCap +
+                          (size_t)kWarps * (h->N + h->nBinsPad + h->fbPad);
+    h->smemBytes = floats * sizeof(float);
+    if (h->smemBytes > h->dev.smem_optin) {
+        rb::set_error("front-end configuration needs %zu bytes of shared memory per CTA (limit %zu)", h->smemBytes,
+                      h->dev.smem_optin);
+        return fail(RB_ERR_UNSUPPORTED);
+    }
+    if (cudaFuncSetAttribute(mfcc_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes) !=
+        cudaSuccess) {
+        rb::set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(RB_ERR_CUDA);
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mfcc_static_kernel, kThreads, h->smemBytes) !=
+                cudaSuccess ||
+        occ < 1) {
+        rb::set_error("front-end kernel does not fit on the device");
+        return fail(RB_ERR_CUDA);
+    }
+    h->grid = h->dev.sm_count * occ;
+    if (h->dTables.upload(h->blob, h->stream) != RB_OK || cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        rb::set_error("table upload failed");
+        return fail(RB_ERR_CUDA);
+    }
+    *out = h;
+    return RB_OK;
+}
+
+extern "C" void rb_frontend_destroy(rb_frontend* h) {
+    if (!h)
+        return;
+    cudaSetDevice(h->dev.ordinal);
+    delete h;
+}
+
+extern "C" int rb_frontend_get_geometry(const rb_frontend* h, rb_frontend_geometry* g) {
+    RB_REQUIRE(h && g, "NULL argument");
+    g->win_length = h->L;
+    g->win_shift  = h->S;
+    g->fft_length = h->N;
+    g->n_bins     = h->nBins;
+    g->n_filters  = h->nFilters;
+    g->n_weights  = h->nWeights;
+    g->feat_dim   = h->featDim;
+    return RB_OK;
+}
+
+extern "C" int rb_frontend_get_tables(const rb_frontend* h, float* window, int* fb_start, int* fb_end,
+                                      float* fb_weights, float* dct) {
+    RB_REQUIRE(h != nullptr, "NULL handle");
+    if (window)
+        std::copy(h->window.begin(), h->window.end(), window);
+    for (int f = 0; f < h->nFilters; ++f) {
+        if (fb_start)
+            fb_start[f] = h->fbStart[f];
+        if (fb_end)
+            fb_end[f] = h->fbEnd[f];
+        if (fb_weights) {
+            for (int k = 0; k < h->nBins; ++k)
+                fb_weights[(size_t)f * h->nBins + k] = 0.0f;
+            for (int k = h->fbStart[f]; k < h->fbEnd[f]; ++k)
+                fb_weights[(size_t)f * h->nBins + k] = h->fbWeights[h->fbOff[f] + k - h->fbStart[f]];
+        }
+    }
+    if (dct)
+        std::copy(h->dct.begin(), h->dct.end(), dct);
+    return RB_OK;
+}
+
+extern "C" long rb_frontend_nframes_for(const rb_frontend* h, long n_samples) {
+    return h ? frames_for(h, n_samples) : 0;
+}
+
+extern "C" long rb_frontend_count_frames(const rb_frontend* h, const int64_t* offsets, int n_utt,
+                                         int64_t* frame_offsets) {
+    if (!h || !offsets || n_utt < 0)
+        return -1;
+    int64_t acc = 0;
+    if (frame_offsets)
+        frame_offsets[0] = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        acc += frames_for(h, (long)(offsets[u + 1] - offsets[u]));
+        if (frame_offsets)
+            frame_offsets[u + 1] = acc;
+    }
+    return (long)acc;
+}
+
+extern "C" int rb_frontend_process_dev(rb_frontend* h, const float* d_samples, const int64_t* offsets, int n_utt,
+                                       float* d_feats, void* stream) {
+    RB_REQUIRE(h && offsets && n_utt >= 0, "bad argument");
+    if (n_utt == 0)
+        return RB_OK;
+    RB_REQUIRE(d_samples && d_feats, "NULL device buffer");
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    return run_device(h, d_samples, offsets, n_utt, d_feats, stream ? (cudaStream_t)stream : h->stream, nullptr);
+}
+
+extern "C" int rb_frontend_process(rb_frontend* h, const float* samples, const int64_t* offsets, int n_utt,
+                                   float* feats, double* t_start, double* t_end) {
+    RB_REQUIRE(h && offsets && n_utt >= 0, "bad argument");
+    if (n_utt == 0)
+        return RB_OK;
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    const int64_t base = offsets[0], nS = offsets[n_utt] - base;
+    RB_REQUIRE(nS >= 0, "negative sample count");
+    RB_REQUIRE(samples || nS == 0, "NULL sample buffer");
+    // slack so that the aligned bulk copies never leave the allocation
+    RB_CHECK(h->dSamples.reserve((size_t)nS + 8));
+    if (nS)
+        RB_CUDA(cudaMemcpyAsync(h->dSamples.p, samples + base, (size_t)nS * 4, cudaMemcpyHostToDevice, h->stream));
+    std::vector<int64_t> rel(n_utt + 1);
+    for (int u = 0; u <= n_utt; ++u)
+        rel[u] = offsets[u] - base;
+    const long total = rb_frontend_count_frames(h, rel.data(), n_utt, nullptr);
+    RB_CHECK(h->dFeats.reserve((size_t)total * h->featDim));
+    int64_t got = 0;
+    RB_CHECK(run_device(h, h->dSamples.p, rel.data(), n_utt, h->dFeats.p, h->stream, &got));
+    if (feats && total)
+        RB_CUDA(cudaMemcpyAsync(feats, h->dFeats.p, (size_t)total * h->featDim * 4, cudaMemcpyDeviceToHost,
+                                h->stream));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
+    h->lastFrames = total;
+    if (t_start || t_end) {
+        long f = 0;
+        for (int u = 0; u < n_utt; ++u) {
+            const long n = (long)(rel[u + 1] - rel[u]);
+            const long T = frames_for(h, n);
+            timestamps(h, n, 0.0, T, t_start ? t_start + f : nullptr, t_end ? t_end + f : nullptr);
+            f += T;
+        }
+    }
+    return RB_OK;
+}
+
+extern "C" int rb_frontend_reset(rb_frontend* h) {
+    RB_REQUIRE(h != nullptr, "NULL handle");
+    h->pending.clear();
+    h->havePending  = false;
+    h->pendingStart = 0;
+    h->lastFrames   = 0;
+    h->lastFeats.clear();
+    h->lastStart.clear();
+    h->lastEnd.clear();
+    return RB_OK;
+}
+
+extern "C" int rb_frontend_push(rb_frontend* h, const float* samples, long n, double start_time) {
+    RB_REQUIRE(h != nullptr, "NULL handle");
+    RB_REQUIRE(n >= 0 && (samples || n == 0), "bad packet");
+    if (!h->havePending) {
+        h->pendingStart = start_time;  // WindowBuffer::put on an empty buffer (WindowBuffer.cc:50-58)
+        h->havePending  = true;
+    }
+    h->pending.insert(h->pending.end(), samples, samples + n);
+    return RB_OK;
+}
+
+extern "C" int rb_frontend_finish(rb_frontend* h) {
+    RB_REQUIRE(h != nullptr, "NULL handle");
+    const long    n      = (long)h->pending.size();
+    const long    T      = frames_for(h, n);
+    const int64_t off[2] = {0, n};
+    h->lastFeats.assign((size_t)T * h->featDim, 0.0f);
+    h->lastStart.assign(T, 0.0);
+    h->lastEnd.assign(T, 0.0);
+    if (T > 0) {
+        RB_CHECK(rb_frontend_process(h, h->pending.data(), off, 1, h->lastFeats.data(), nullptr, nullptr));
+        timestamps(h, n, h->pendingStart, T, h->lastStart.data(), h->lastEnd.data());
+    }
+    h->lastFrames = T;
+    h->pending.clear();
+    h->havePending = false;
+    return RB_OK;
+}
+
+extern "C" long rb_frontend_nframes(const rb_frontend* h) {
+    return h ? h->lastFrames : 0;
+}
+
+extern "C" int rb_frontend_read(rb_frontend* h, float* feats, double* t_start, double* t_end) {
+    RB_REQUIRE(h != nullptr, "NULL handle");
+    if ((size_t)h->lastFrames * h->featDim != h->lastFeats.size()) {
+        rb::set_error("rb_frontend_read without a preceding rb_frontend_finish");
+        return RB_ERR_STATE;
+    }
+    if (feats)
+        std::copy(h->lastFeats.begin(), h->lastFeats.end(), feats);
+    if (t_start)
+        std::copy(h->lastStart.begin(), h->lastStart.end(), t_start);
+    if (t_end)
+        std::copy(h->lastEnd.begin(), h->lastEnd.end(), t_end);
+    return RB_OK;
+}
+
+extern "C" int rb_frontend_set_debug(rb_frontend* h, int on) {
+    RB_REQUIRE(h != nullptr, "NULL handle");
+    h->debug = on != 0;
+    return RB_OK;
+}
+
+extern "C" int rb_frontend_read_stages(rb_frontend* h, float* amplitude, float* fbank, float* cepstra) {
+    RB_REQUIRE(h != nullptr, "NULL handle");
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    const size_t T = (size_t)h->lastFrames;
+    if (amplitude || fbank) {
+        if (!h->debug || (size_t)h->dbgFrames != T) {
+            rb::set_error("stage dumps were not recorded: call rb_frontend_set_debug(h, 1) before processing");
+            return RB_ERR_STATE;
+        }
+    }
+    if (amplitude && T)
+        RB_CUDA(cudaMemcpy(amplitude, h->dDbgAmp.p, T * h->nBins * 4, cudaMemcpyDeviceToHost));
+    if (fbank && T)
+        RB_CUDA(cudaMemcpy(fbank, h->dDbgFbank.p, T * h->nFilters * 4, cudaMemcpyDeviceToHost));
+    if (cepstra && T)
+        RB_CUDA(cudaMemcpy(cepstra, h->dCep.p, T * h->cfg.n_cepstra * 4, cudaMemcpyDeviceToHost));
+    return RB_OK;
+}
+
+// accessors for pipeline.cu
+rb::DeviceInfo rb_frontend_device(const rb_frontend* h) {
+    return h->dev;
+}
+cudaStream_t rb_frontend_stream(const rb_frontend* h) {
+    return h->stream;
+}
+int rb_frontend_feat_dim(const rb_frontend* h) {
+    return h->featDim;
+}

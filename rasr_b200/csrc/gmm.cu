@@ -1,0 +1,883 @@
+// gmm.cu -- diagonal-covariance GMM emission scorer on CUDA cores (sm_100a).
+//
+// Replaces, for ALL mixtures and ALL frames at once (dense T x nMix score matrix):
+//   Mm::BatchFloatFeatureScorer::fillScoreCacheTpl          src/Mm/BatchFeatureScorer.cc:207-253
+//   Mm::GaussDiagonalMaximumFeatureScorer::calculateScoreAndDensity  src/Mm/GaussDiagonalMaximumFeatureScorer.cc:116-142
+//   Mm::GaussDiagonalSumFeatureScorer::calculateScoreAndDensity      same file :263-290
+//
+// Design (B200-first, not a port of the SSE loops):
+//   * work item = (block of 512 frames) x (group of mixtures); a persistent grid of
+//     sm_count x occupancy CTAs walks the items, so the grid is always a multiple of the SM count.
+//   * a thread owns TWO frames whose (scaled) feature vectors live in registers for the whole item;
+//     a warp walks the densities of the group in mixture order, so the density row is a
+//     warp-uniform shared-memory broadcast (one LDS.128 feeds 8 sub+fma pairs) and the min /
+//     log-sum-exp over the densities of a mixture is a private register recurrence: no cross-thread
+//     reduction, ragged mixtures cost nothing.
+//   * density rows (scaled mean | constant | flags) are streamed global->shared by the TMA unit
+//     (cp.async.bulk, SASS UBLKCP) through a 3-stage mbarrier ring; the model (0.7 MB for C2) stays
+//     L2-resident, HBM traffic is the algorithmic 156 B in + 1024 B out per frame.
+//   * arithmetic follows the reference's SSE lane structure exactly (lane j of the two 4-wide
+//     accumulators sums dims 8b+j / 8b+4+j, constant added first in lane 0, same horizontal
+//     add tree), so BATCH_FLOAT scores are bit-identical to the CPU path, contraction on or off.
+//   * the kernel is FP32-ALU bound (2 issue slots per (frame,density,dim)); see DESIGN.md.
+#include <cfloat>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace {
+
+using namespace rbdev;
+
+constexpr int kThreads        = 256;
+constexpr int kFramesPerThr   = 2;
+constexpr int kFramesPerBlock = kThreads * kFramesPerThr;  // 512
+constexpr int kStages         = 3;
+constexpr int kChunkRows      = 32;  // density rows per pipeline stage
+
+struct GmmParams {
+    const float*    rows;      // [nRows * rowf]
+    const int*      grp_row;   // [G+1] row boundaries of the mixture groups
+    const int*      grp_mix;   // [G+1] mixture boundaries
+    const float*    isd;       // [dpad] inverse std-dev of the pooled covariance (BATCH only)
+    const float*    feats;     // [T * dim]
+    float*          scores;    // [T * nMix]
+    uint32_t*       best;      // [T * nMix] or null
+    long            T;
+    int             dim;
+    int             nMix;
+    int             nGroups;
+    int             nFrameBlocks;
+    int             vec4;  // 1: nMix % 4 == 0 and scores 16-byte aligned -> float4 stores
+};
+
+__device__ __forceinline__ float sq_acc(float d, float a, bool fuse) {
+    return fuse ? __fmaf_rn(d, d, a) : __fadd_rn(a, __fmul_rn(d, d));
+}
+
+// ------------------------------------------------------------------------------------------
+// BATCH_FLOAT: row = [ mu' (NB*8) | c | flags | 0 | 0 ],  rowf = NB*8+4
+// ------------------------------------------------------------------------------------------
+template<int NB, bool FUSE>
+__global__ void __launch_bounds__(kThreads, (NB <= 5) ? 2 : 1) gmm_batch_kernel(const GmmParams p) {
+    constexpr int ROWF  = NB * 8 + 4;
+    constexpr int CHUNK = kChunkRows * ROWF;  // floats per stage
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float*    buf = reinterpret_cast<float*>(smem_raw);                       // kStages * CHUNK
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * kStages * CHUNK);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s)
+            mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t  seq    = 0;  // chunks consumed so far by this CTA (stage = seq % kStages)
+    const int nItems = p.nGroups * p.nFrameBlocks;
+
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const int  g    = item / p.nFrameBlocks;
+        const int  fb   = item - g * p.nFrameBlocks;
+        const int  row0 = p.grp_row[g], row1 = p.grp_row[g + 1];
+        int        mix  = p.grp_mix[g];
+        const int  nCh  = (row1 - row0 + kChunkRows - 1) / kChunkRows;
+        const long t0   = (long)fb * kFramesPerBlock + tid;
+        const long t1   = t0 + kThreads;
+
+        // producer prologue
+        if (tid == 0) {
+            for (int c = 0; c < kStages - 1 && c < nCh; ++c) {
+                const int      r0    = row0 + c * kChunkRows;
+                const int      nr    = min(kChunkRows, row1 - r0);
+                const uint32_t bytes = (uint32_t)nr * ROWF * 4u;
+                const uint32_t st    = (seq + c) % kStages;
+                mbar_expect_tx(&bar[st], bytes);
+                bulk_g2s(buf + st * CHUNK, p.rows + (size_t)r0 * ROWF, bytes, &bar[st]);
+            }
+        }
+
+        // the two feature vectors of this thread, scaled by 1/sigma (setFeature :157-162)
+        float x0[NB * 8], x1[NB * 8];
+        {
+            const long   ta = t0 < p.T ? t0 : p.T - 1;
+            const long   tb = t1 < p.T ? t1 : p.T - 1;
+            const float* fa = p.feats + (size_t)ta * p.dim;
+            const float* fbp = p.feats + (size_t)tb * p.dim;
+#pragma unroll
+            for (int d = 0; d < NB * 8; ++d) {
+                const float s = d < p.dim ? __ldg(p.isd + d) : 0.0f;
+                x0[d]         = d < p.dim ? __fmul_rn(__ldg(fa + d), s) : 0.0f;
+                x1[d]         = d < p.dim ? __fmul_rn(__ldg(fbp + d), s) : 0.0f;
+            }
+        }
+
+        float best0 = FLT_MAX, best1 = FLT_MAX;
+        float o0a = 0, o1a = 0, o2a = 0, o3a = 0;  // staged outputs of frame t0
+        float o0b = 0, o1b = 0, o2b = 0, o3b = 0;  // staged outputs of frame t1
+        int   nStaged = 0;
+
+        for (int c = 0; c < nCh; ++c) {
+            if (tid == 0 && c + kStages - 1 < nCh) {
+                const int      cc    = c + kStages - 1;
+                const int      r0    = row0 + cc * kChunkRows;
+                const int      nr    = min(kChunkRows, row1 - r0);
+                const uint32_t bytes = (uint32_t)nr * ROWF * 4u;
+                const uint32_t st    = (seq + cc) % kStages;
+                mbar_expect_tx(&bar[st], bytes);
+                bulk_g2s(buf + st * CHUNK, p.rows + (size_t)r0 * ROWF, bytes, &bar[st]);
+            }
+            const uint32_t n  = seq + c;
+            const uint32_t st = n % kStages;
+            mbar_wait(&bar[st], (n / kStages) & 1u);
+            const float* chunk = buf + st * CHUNK;
+            const int    nr    = min(kChunkRows, row1 - (row0 + c * kChunkRows));
+
+            for (int r = 0; r < nr; ++r) {
+                const float4* row  = reinterpret_cast<const float4*>(chunk + r * ROWF);
+                const float4  tail = row[NB * 2];
+                float         a0[8], a1[8];
+                a0[0] = tail.x;  // constant first, in lane 0 of the first accumulator (:217-219)
+                a1[0] = tail.x;
+#pragma unroll
+                for (int j = 1; j < 8; ++j) {
+                    a0[j] = 0.0f;
+                    a1[j] = 0.0f;
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float4 m0 = row[2 * b], m1 = row[2 * b + 1];
+                    const float  m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float d0 = __fsub_rn(m[j], x0[8 * b + j]);
+                        const float d1 = __fsub_rn(m[j], x1[8 * b + j]);
+                        a0[j]          = sq_acc(d0, a0[j], FUSE);
+                        a1[j]          = sq_acc(d1, a1[j], FUSE);
+                    }
+                }
+                // s1 += s2; then the two shuffle/add steps of :236-243: (l0+l2)+(l1+l3)
+                const float r0s = __fadd_rn(__fadd_rn(__fadd_rn(a0[0], a0[4]), __fadd_rn(a0[2], a0[6])),
+                                            __fadd_rn(__fadd_rn(a0[1], a0[5]), __fadd_rn(a0[3], a0[7])));
+                const float r1s = __fadd_rn(__fadd_rn(__fadd_rn(a1[0], a1[4]), __fadd_rn(a1[2], a1[6])),
+                                            __fadd_rn(__fadd_rn(a1[1], a1[5]), __fadd_rn(a1[3], a1[7])));
+                best0 = best0 < r0s ? best0 : r0s;
+                best1 = best1 < r1s ? best1 : r1s;
+
+                if (__float_as_int(tail.y) & 1) {  // last density of its mixture: emit
+                    const float v0 = best0 < FLT_MAX ? __fmul_rn(best0, 0.5f) : best0;
+                    const float v1 = best1 < FLT_MAX ? __fmul_rn(best1, 0.5f) : best1;
+                    best0 = FLT_MAX;
+                    best1 = FLT_MAX;
+                    if (p.vec4) {
+                        o0a = o1a; o1a = o2a; o2a = o3a; o3a = v0;
+                        o0b = o1b; o1b = o2b; o2b = o3b; o3b = v1;
+                        if (++nStaged == 4) {
+                            nStaged = 0;
+                            if (t0 < p.T)
+                                *reinterpret_cast<float4*>(p.scores + (size_t)t0 * p.nMix + (mix - 3)) =
+                                        make_float4(o0a, o1a, o2a, o3a);
+                            if (t1 < p.T)
+                                *reinterpret_cast<float4*>(p.scores + (size_t)t1 * p.nMix + (mix - 3)) =
+                                        make_float4(o0b, o1b, o2b, o3b);
+                        }
+                    }
+                    else {
+                        if (t0 < p.T)
+                            p.scores[(size_t)t0 * p.nMix + mix] = v0;
+                        if (t1 < p.T)
+                            p.scores[(size_t)t1 * p.nMix + mix] = v1;
+                    }
+                    ++mix;
+                }
+            }
+            __syncthreads();  // everyone is done with stage st before it is refilled
+        }
+        seq += (uint32_t)nCh;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DIAG_MAX / DIAG_SUM: row = [ mu (NQ*4) | isd (NQ*4) | -2 log w * scale | logNorm | flags | 0 ]
+// distance(): 4 SSE lanes over the first (dim & ~3) dims, hadd, then the tail dims sequentially
+// (src/Mm/GaussDiagonalMaximumFeatureScorer.cc:144-233, SSE3 branch)
+// ------------------------------------------------------------------------------------------
+template<int NQ, bool FUSE, bool SUM>
+__global__ void __launch_bounds__(kThreads, (NQ <= 10) ? 2 : 1) gmm_diag_kernel(const GmmParams p) {
+    constexpr int ROWF  = NQ * 8 + 4;
+    constexpr int CHUNK = kChunkRows * ROWF;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float*    buf = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * kStages * CHUNK);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s)
+            mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t  seq    = 0;
+    const int nItems = p.nGroups * p.nFrameBlocks;
+    const int nFullQ = p.dim >> 2;  // quads handled by the SSE loop
+    const int nTail  = p.dim & 3;
+
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const int  g    = item / p.nFrameBlocks;
+        const int  fb   = item - g * p.nFrameBlocks;
+        const int  row0 = p.grp_row[g], row1 = p.grp_row[g + 1];
+        int        mix  = p.grp_mix[g];
+        const int  nCh  = (row1 - row0 + kChunkRows - 1) / kChunkRows;
+        const long t0   = (long)fb * kFramesPerBlock + tid;
+        const long t1   = t0 + kThreads;
+
+        if (tid == 0) {
+            for (int c = 0; c < kStages - 1 && c < nCh; ++c) {
+                const int      r0    = row0 + c * kChunkRows;
+                const int      nr    = min(kChunkRows, row1 - r0);
+                const uint32_t bytes = (uint32_t)nr * ROWF * 4u;
+                const uint32_t st    = (seq + c) % kStages;
+                mbar_expect_tx(&bar[st], bytes);
+                bulk_g2s(buf + st * CHUNK, p.rows + (size_t)r0 * ROWF, bytes, &bar[st]);
+            }
+        }
+
+        float x0[NQ * 4], x1[NQ * 4];
+        {
+            const long   ta  = t0 < p.T ? t0 : p.T - 1;
+            const long   tb  = t1 < p.T ? t1 : p.T - 1;
+            const float* fa  = p.feats + (size_t)ta * p.dim;
+            const float* fbp = p.feats + (size_t)tb * p.dim;
+#pragma unroll
+            for (int d = 0; d < NQ * 4; ++d) {
+                x0[d] = d < p.dim ? __ldg(fa + d) : 0.0f;
+                x1[d] = d < p.dim ? __ldg(fbp + d) : 0.0f;
+            }
+        }
+
+        // running state over the densities of the current mixture
+        float    best0 = FLT_MAX, best1 = FLT_MAX;
+        uint32_t bd0 = 0xffffffffu, bd1 = 0xffffffffu;
+        float    se0 = 0.0f, se1 = 0.0f;  // SUM: sum of exp(best - s_k), rescaled when best moves
+        uint32_t k = 0;                   // density index within the mixture
+
+        for (int c = 0; c < nCh; ++c) {
+            if (tid == 0 && c + kStages - 1 < nCh) {
+                const int      cc    = c + kStages - 1;
+                const int      r0    = row0 + cc * kChunkRows;
+                const int      nr    = min(kChunkRows, row1 - r0);
+                const uint32_t bytes = (uint32_t)nr * ROWF * 4u;
+                const uint32_t st    = (seq + cc) % kStages;
+                mbar_expect_tx(&bar[st], bytes);
+                bulk_g2s(buf + st * CHUNK, p.rows + (size_t)r0 * ROWF, bytes, &bar[st]);
+            }
+            const uint32_t n  = seq + c;
+            const uint32_t st = n % kStages;
+            mbar_wait(&bar[st], (n / kStages) & 1u);
+            const float* chunk = buf + st * CHUNK;
+            const int    nr    = min(kChunkRows, row1 - (row0 + c * kChunkRows));
+
+            for (int r = 0; r < nr; ++r) {
+                const float4* row  = reinterpret_cast<const float4*>(chunk + r * ROWF);
+                const float4  tail = row[NQ * 2];
+                const int     flags = __float_as_int(tail.z);
+                float         d0 = 0.0f, d1 = 0.0f;
+                if (!(flags & 2)) {  // not a placeholder row of an empty mixture
+                    float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        if (q < nFullQ) {
+                            const float4 m4 = row[q], v4 = row[NQ + q];
+                            const float  m[4] = {m4.x, m4.y, m4.z, m4.w};
+                            const float  v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float e0 = __fmul_rn(__fsub_rn(m[j], x0[4 * q + j]), v[j]);
+                                const float e1 = __fmul_rn(__fsub_rn(m[j], x1[4 * q + j]), v[j]);
+                                s0[j]          = sq_acc(e0, s0[j], FUSE);
+                                s1[j]          = sq_acc(e1, s1[j], FUSE);
+                            }
+                        }
+                    }
+                    // hadd(sum,sum) -> (s0+s1, s2+s3); result = 0 + ((s0+s1) + (s2+s3))
+                    d0 = __fadd_rn(0.0f, __fadd_rn(__fadd_rn(s0[0], s0[1]), __fadd_rn(s0[2], s0[3])));
+                    d1 = __fadd_rn(0.0f, __fadd_rn(__fadd_rn(s1[0], s1[1]), __fadd_rn(s1[2], s1[3])));
+                    if (nTail) {
+                        const float4 m4 = row[NQ - 1], v4 = row[2 * NQ - 1];
+                        const float  m[4] = {m4.x, m4.y, m4.z, m4.w};
+                        const float  v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            if (j < nTail) {
+                                const float e0 = __fmul_rn(__fsub_rn(m[j], x0[4 * (NQ - 1) + j]), v[j]);
+                                const float e1 = __fmul_rn(__fsub_rn(m[j], x1[4 * (NQ - 1) + j]), v[j]);
+                                d0             = sq_acc(e0, d0, FUSE);
+                                d1             = sq_acc(e1, d1, FUSE);
+                            }
+                        }
+                    }
+                    if (!SUM) {
+                        // f64 sum of the three f32 terms, compared against the f32 running best (:130-137)
+                        const double base = (double)tail.x + (double)tail.y;
+                        const double sc0 = base + (double)d0, sc1 = base + (double)d1;
+                        if ((double)best0 > sc0) {
+                            best0 = (float)sc0;
+                            bd0   = k;
+                        }
+                        if ((double)best1 > sc1) {
+                            best1 = (float)sc1;
+                            bd1   = k;
+                        }
+                    }
+                    else {
+                        // s_k = 0.5 * (w + logNorm + dist) in f32 (:272-276); log-sum-exp around the running
+                        // minimum (the reference's two passes folded into one; exp/log are libm anyway)
+                        const float a0 = __fmul_rn(0.5f, __fadd_rn(__fadd_rn(tail.x, tail.y), d0));
+                        const float a1 = __fmul_rn(0.5f, __fadd_rn(__fadd_rn(tail.x, tail.y), d1));
+                        if (best0 > a0) {
+                            se0   = se0 * expf(a0 - best0) + 1.0f;
+                            best0 = a0;
+                            bd0   = k;
+                        }
+                        else
+                            se0 += expf(best0 - a0);
+                        if (best1 > a1) {
+                            se1   = se1 * expf(a1 - best1) + 1.0f;
+                            best1 = a1;
+                            bd1   = k;
+                        }
+                        else
+                            se1 += expf(best1 - a1);
+                    }
+                    ++k;
+                }
+                if (flags & 1) {  // emit
+                    float v0, v1;
+                    if (!SUM) {
+                        v0 = __fmul_rn(0.5f, best0);
+                        v1 = __fmul_rn(0.5f, best1);
+                    }
+                    else {
+                        v0 = best0 - logf(se0);
+                        v1 = best1 - logf(se1);
+                    }
+                    if (t0 < p.T) {
+                        p.scores[(size_t)t0 * p.nMix + mix] = v0;
+                        if (p.best)
+                            p.best[(size_t)t0 * p.nMix + mix] = bd0;
+                    }
+                    if (t1 < p.T) {
+                        p.scores[(size_t)t1 * p.nMix + mix] = v1;
+                        if (p.best)
+                            p.best[(size_t)t1 * p.nMix + mix] = bd1;
+                    }
+                    best0 = FLT_MAX;
+                    best1 = FLT_MAX;
+                    bd0 = bd1 = 0xffffffffu;
+                    se0 = se1 = 0.0f;
+                    k         = 0;
+                    ++mix;
+                }
+            }
+            __syncthreads();
+        }
+        seq += (uint32_t)nCh;
+    }
+}
+
+typedef void (*GmmKernel)(const GmmParams);
+
+template<int N>
+GmmKernel pick_batch(bool fuse) {
+    return fuse ? gmm_batch_kernel<N, true> : gmm_batch_kernel<N, false>;
+}
+template<int N>
+GmmKernel pick_diag(bool fuse, bool sum) {
+    if (sum)
+        return fuse ? gmm_diag_kernel<N, true, true> : gmm_diag_kernel<N, false, true>;
+    return fuse ? gmm_diag_kernel<N, true, false> : gmm_diag_kernel<N, false, false>;
+}
+
+GmmKernel batch_kernel_for(int nb, bool fuse) {
+    switch (nb) {
+        case 1: return pick_batch<1>(fuse);
+        case 2: return pick_batch<2>(fuse);
+        case 3: return pick_batch<3>(fuse);
+        case 4: return pick_batch<4>(fuse);
+        case 5: return pick_batch<5>(fuse);
+        case 6: return pick_batch<6>(fuse);
+        case 7: return pick_batch<7>(fuse);
+        case 8: return pick_batch<8>(fuse);
+    }
+    return nullptr;
+}
+GmmKernel diag_kernel_for(int nq, bool fuse, bool sum) {
+    switch (nq) {
+        case 1: return pick_diag<1>(fuse, sum);
+        case 2: return pick_diag<2>(fuse, sum);
+        case 3: return pick_diag<3>(fuse, sum);
+        case 4: return pick_diag<4>(fuse, sum);
+        case 5: return pick_diag<5>(fuse, sum);
+        case 6: return pick_diag<6>(fuse, sum);
+        case 7: return pick_diag<7>(fuse, sum);
+        case 8: return pick_diag<8>(fuse, sum);
+        case 9: return pick_diag<9>(fuse, sum);
+        case 10: return pick_diag<10>(fuse, sum);
+        case 11: return pick_diag<11>(fuse, sum);
+        case 12: return pick_diag<12>(fuse, sum);
+        case 13: return pick_diag<13>(fuse, sum);
+        case 14: return pick_diag<14>(fuse, sum);
+        case 15: return pick_diag<15>(fuse, sum);
+        case 16: return pick_diag<16>(fuse, sum);
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+
+struct rb_gmm_tensor;  // gmm_tensor.cu
+int  rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream,
+                          rb_gmm_tensor** out);
+void rb_gmm_tensor_destroy(rb_gmm_tensor* t);
+int  rb_gmm_tensor_score(rb_gmm_tensor* t, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
+
+struct rb_gmm {
+    rb::DeviceInfo dev;
+    int            mode = 0;
+    bool           fuse = true;
+    int            dim = 0, nMix = 0;
+    int            nUnits = 0;  // NB (batch) or NQ (diag)
+    int            rowf = 0;
+    int            nRows = 0;
+    cudaStream_t   stream = nullptr;
+    GmmKernel      kernel = nullptr;
+    size_t         smemBytes = 0;
+    int            ctasPerSm = 1;
+
+    std::vector<int> rowsOfMixture;  // rows each mixture occupies (>= 1)
+    int              curGroups = -1;
+
+    rb::DevBuf<float>    dRows, dIsd;
+    rb::DevBuf<int>      dGrpRow, dGrpMix;
+    rb::DevBuf<float>    dFeats, dScores;  // staging for the host-pointer entry point
+    rb::DevBuf<uint32_t> dBest;
+    rb::PinnedBuf<float> hStage;
+    rb_gmm_tensor*       tensor = nullptr;
+
+    ~rb_gmm() {
+        if (tensor)
+            rb_gmm_tensor_destroy(tensor);
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+// Mm::gaussLogNormFactor: D*log(2 pi) + sum log|var|  (src/Mm/Utilities.hh:53-76), f64
+double log_norm_factor(const float* var, unsigned dim) {
+    double s = 0;
+    for (unsigned d = 0; d < dim; ++d)
+        s += std::log(std::fabs((double)var[d]));
+    return (double)dim * std::log(2.0 * M_PI) + s;
+}
+
+// Mm::inverseSquareRoot<f32> (src/Mm/Utilities.hh:86-91)
+inline float inv_sqrt(float v) {
+    return 1.0f / (float)std::sqrt((double)v);
+}
+
+int validate(const rb_mixture_set* ms) {
+    RB_REQUIRE(ms != nullptr, "mixture set is NULL");
+    RB_REQUIRE(ms->dim >= 1, "mixture set dimension is 0");
+    RB_REQUIRE(ms->n_mixtures >= 1, "mixture set has no mixtures");
+    RB_REQUIRE(ms->mix_offsets && ms->dens_mean && ms->dens_cov && ms->means && ms->variances,
+               "mixture set has NULL tables");
+    const uint32_t nEntries = ms->mix_offsets[ms->n_mixtures];
+    RB_REQUIRE(nEntries == 0 || (ms->mix_density && ms->mix_log_weight), "mixture entries missing");
+    for (uint32_t m = 0; m < ms->n_mixtures; ++m)
+        RB_REQUIRE(ms->mix_offsets[m] <= ms->mix_offsets[m + 1], "mix_offsets not monotone at mixture %u", m);
+    for (uint32_t e = 0; e < nEntries; ++e) {
+        const uint32_t d = ms->mix_density[e];
+        RB_REQUIRE(d < ms->n_densities, "mixture entry %u refers to density %u >= %u", e, d, ms->n_densities);
+        RB_REQUIRE(ms->dens_mean[d] < ms->n_means, "density %u refers to mean %u >= %u", d, ms->dens_mean[d],
+                   ms->n_means);
+        RB_REQUIRE(ms->dens_cov[d] < ms->n_covariances, "density %u refers to covariance %u >= %u", d,
+                   ms->dens_cov[d], ms->n_covariances);
+    }
+    return RB_OK;
+}
+
+inline float int_bits(int v) {
+    float f;
+    std::memcpy(&f, &v, 4);
+    return f;
+}
+
+// BATCH_FLOAT rows, following BatchFloatFeatureScorer::init (src/Mm/BatchFeatureScorer.cc:164-197)
+int build_batch_rows(rb_gmm* h, const rb_mixture_set* ms, std::vector<float>& rows, std::vector<float>& isd) {
+    if (ms->n_covariances != 1) {
+        rb::set_error("batch feature scorer supports only one globally pooled covariance (got %u); use "
+                      "RB_GMM_DIAG_MAX",
+                      ms->n_covariances);
+        return RB_ERR_UNSUPPORTED;
+    }
+    const unsigned D    = ms->dim;
+    const int      NB   = (int)((D + 7) / 8);
+    const int      rowf = NB * 8 + 4;
+    h->nUnits           = NB;
+    h->rowf             = rowf;
+    isd.assign((size_t)NB * 8, 0.0f);
+    for (unsigned d = 0; d < D; ++d)
+        isd[d] = inv_sqrt(ms->variances[d]);
+    const float logNorm = (float)log_norm_factor(ms->variances, D);
+    h->rowsOfMixture.assign(ms->n_mixtures, 0);
+    rows.clear();
+    for (uint32_t m = 0; m < ms->n_mixtures; ++m) {
+        const uint32_t e0 = ms->mix_offsets[m], e1 = ms->mix_offsets[m + 1];
+        const uint32_t n  = e1 - e0;
+        const uint32_t nr = n ? n : 1;  // an empty mixture keeps one placeholder row scoring FLT_MAX
+        h->rowsOfMixture[m] = (int)nr;
+        const size_t base   = rows.size();
+        rows.resize(base + (size_t)nr * rowf, 0.0f);
+        for (uint32_t i = 0; i < nr; ++i) {
+            float* row = rows.data() + base + (size_t)i * rowf;
+            if (n) {
+                const uint32_t dns = ms->mix_density[e0 + i];
+                const float*   mu  = ms->means + (size_t)ms->dens_mean[dns] * D;
+                for (unsigned d = 0; d < D; ++d)
+                    row[d] = mu[d] * isd[d];
+                // f32 logNorm minus f64 2*logWeight, narrowed (:193)
+                row[NB * 8] = (float)((double)logNorm - 2 * ms->mix_log_weight[e0 + i]);
+            }
+            else {
+                row[NB * 8] = FLT_MAX;
+            }
+            row[NB * 8 + 1] = int_bits(i + 1 == nr ? 1 : 0);
+        }
+    }
+    return RB_OK;
+}
+
+// DIAG rows, following GaussDiagonalMaximumFeatureScorer's element caches
+// (MixtureFeatureScorerElement.cc:21-34, CovarianceFeatureScorerElement.cc:21-51)
+int build_diag_rows(rb_gmm* h, const rb_mixture_set* ms, float mixtureWeightScale, float gaussianScaleParam,
+                    std::vector<float>& rows) {
+    const unsigned D    = ms->dim;
+    const int      NQ   = (int)((D + 3) / 4);
+    const int      rowf = NQ * 8 + 4;
+    h->nUnits           = NQ;
+    h->rowf             = rowf;
+    const float gaussianScale = (float)std::sqrt((double)gaussianScaleParam);
+    std::vector<float> isd((size_t)ms->n_covariances * D);
+    std::vector<float> logNorm(ms->n_covariances);
+    for (uint32_t c = 0; c < ms->n_covariances; ++c) {
+        const float* var = ms->variances + (size_t)c * D;
+        for (unsigned d = 0; d < D; ++d)
+            isd[(size_t)c * D + d] = inv_sqrt(var[d]) * gaussianScale;
+        const float lnf = (float)log_norm_factor(var, D);
+        logNorm[c]      = lnf * (gaussianScale * gaussianScale);
+    }
+    h->rowsOfMixture.assign(ms->n_mixtures, 0);
+    rows.clear();
+    for (uint32_t m = 0; m < ms->n_mixtures; ++m) {
+        const uint32_t e0 = ms->mix_offsets[m], e1 = ms->mix_offsets[m + 1];
+        const uint32_t n  = e1 - e0;
+        const uint32_t nr = n ? n : 1;
+        h->rowsOfMixture[m] = (int)nr;
+        const size_t base   = rows.size();
+        rows.resize(base + (size_t)nr * rowf, 0.0f);
+        for (uint32_t i = 0; i < nr; ++i) {
+            float* row   = rows.data() + base + (size_t)i * rowf;
+            int    flags = (i + 1 == nr) ? 1 : 0;
+            if (n) {
+                const uint32_t dns = ms->mix_density[e0 + i];
+                const uint32_t cov = ms->dens_cov[dns];
+                const float*   mu  = ms->means + (size_t)ms->dens_mean[dns] * D;
+                for (unsigned d = 0; d < D; ++d) {
+                    row[d]          = mu[d];
+                    row[NQ * 4 + d] = isd[(size_t)cov * D + d];
+                }
+                const float v   = (float)(-2 * ms->mix_log_weight[e0 + i]);
+                row[NQ * 8]     = v * mixtureWeightScale;
+                row[NQ * 8 + 1] = logNorm[cov];
+            }
+            else {
+                flags |= 2;
+            }
+            row[NQ * 8 + 2] = int_bits(flags);
+        }
+    }
+    return RB_OK;
+}
+
+// split the mixtures into G groups of ~equal row count; all cuts on multiples of 4 mixtures
+void make_groups(const rb_gmm* h, int G, std::vector<int>& grpRow, std::vector<int>& grpMix) {
+    const int nMix = h->nMix;
+    grpRow.assign(1, 0);
+    grpMix.assign(1, 0);
+    long total = 0;
+    for (int m = 0; m < nMix; ++m)
+        total += h->rowsOfMixture[m];
+    long acc = 0;
+    int  g   = 1;
+    for (int m = 0; m < nMix; ++m) {
+        acc += h->rowsOfMixture[m];
+        const bool boundaryOk = ((m + 1) % 4 == 0) && (m + 1 < nMix);
+        if (g < G && boundaryOk && acc * G >= total * g) {
+            grpRow.push_back((int)acc);
+            grpMix.push_back(m + 1);
+            ++g;
+        }
+    }
+    grpRow.push_back((int)total);
+    grpMix.push_back(nMix);
+}
+
+int choose_groups(const rb_gmm* h, long T, int slots) {
+    const long FB   = (T + kFramesPerBlock - 1) / kFramesPerBlock;
+    const int  gmax = std::max(1, std::min(64, std::min(h->nMix / 4, h->nRows / 128)));
+    int        best = 1;
+    double     bestEff = -1;
+    for (int G = 1; G <= gmax; ++G) {
+        const long   items = FB * G;
+        const long   waves = (items + slots - 1) / slots;
+        const double eff   = (double)items / (double)(waves * slots);
+        if (eff > bestEff + 0.02) {  // prefer few groups unless the wave efficiency gain is real
+            bestEff = eff;
+            best    = G;
+        }
+    }
+    return best;
+}
+
+int launch_simt(rb_gmm* h, const float* dFeats, long T, float* dScores, uint32_t* dBest, cudaStream_t s) {
+    const int slots = h->dev.sm_count * h->ctasPerSm;
+    const int G     = choose_groups(h, T, slots);
+    if (G != h->curGroups) {
+        std::vector<int> grpRow, grpMix;
+        make_groups(h, G, grpRow, grpMix);
+        // synchronous small copies: the tables must not be overwritten while a previous launch reads them
+        RB_CUDA(cudaStreamSynchronize(s));
+        RB_CHECK(h->dGrpRow.reserve(66));
+        RB_CHECK(h->dGrpMix.reserve(66));
+        RB_CUDA(cudaMemcpy(h->dGrpRow.p, grpRow.data(), grpRow.size() * sizeof(int), cudaMemcpyHostToDevice));
+        RB_CUDA(cudaMemcpy(h->dGrpMix.p, grpMix.data(), grpMix.size() * sizeof(int), cudaMemcpyHostToDevice));
+        h->curGroups = (int)grpRow.size() - 1;
+    }
+    GmmParams p;
+    p.rows         = h->dRows.p;
+    p.grp_row      = h->dGrpRow.p;
+    p.grp_mix      = h->dGrpMix.p;
+    p.isd          = h->dIsd.p;
+    p.feats        = dFeats;
+    p.scores       = dScores;
+    p.best         = dBest;
+    p.T            = T;
+    p.dim          = h->dim;
+    p.nMix         = h->nMix;
+    p.nGroups      = h->curGroups;
+    p.nFrameBlocks = (int)((T + kFramesPerBlock - 1) / kFramesPerBlock);
+    p.vec4         = (h->nMix % 4 == 0 && ((uintptr_t)dScores % 16 == 0)) ? 1 : 0;
+    const long items = (long)p.nGroups * p.nFrameBlocks;
+    const int  grid  = (int)std::min<long>(items, slots);
+    h->kernel<<<grid, kThreads, h->smemBytes, s>>>(p);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+}  // namespace
+
+extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_weight_scale, float gaussian_scale,
+                             int contraction, int device, rb_gmm** out) {
+    RB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    RB_CHECK(validate(ms));
+    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_BATCH_TENSOR, "unknown gmm mode %d", mode);
+    rb_gmm* h = new (std::nothrow) rb_gmm();
+    if (!h) {
+        rb::set_error("out of host memory");
+        return RB_ERR_NOMEM;
+    }
+    int rc = rb::use_device(device, &h->dev);
+    if (rc != RB_OK) {
+        delete h;
+        return rc;
+    }
+    auto fail = [&](int code) {
+        delete h;
+        return code;
+    };
+    h->mode = mode;
+    h->fuse = contraction != 0;
+    h->dim  = (int)ms->dim;
+    h->nMix = (int)ms->n_mixtures;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        rb::set_error("cudaStreamCreate failed");
+        return fail(RB_ERR_CUDA);
+    }
+    std::vector<float> rows, isd;
+    if (mode == RB_GMM_BATCH_FLOAT || mode == RB_GMM_BATCH_TENSOR) {
+        if (ms->dim > 64) {
+            rb::set_error("batch scorer supports feature dimension <= 64 (got %u)", ms->dim);
+            return fail(RB_ERR_UNSUPPORTED);
+        }
+        rc = build_batch_rows(h, ms, rows, isd);
+        if (rc != RB_OK)
+            return fail(rc);
+        h->kernel = batch_kernel_for(h->nUnits, h->fuse);
+    }
+    else {
+        if (ms->dim > 64) {
+            rb::set_error("diagonal scorer supports feature dimension <= 64 (got %u)", ms->dim);
+            return fail(RB_ERR_UNSUPPORTED);
+        }
+        rc = build_diag_rows(h, ms, mixture_weight_scale, gaussian_scale, rows);
+        if (rc != RB_OK)
+            return fail(rc);
+        isd.assign(4, 0.0f);
+        h->kernel = diag_kernel_for(h->nUnits, h->fuse, mode == RB_GMM_DIAG_SUM);
+    }
+    if (!h->kernel) {
+        rb::set_error("no kernel instance for dimension %d", h->dim);
+        return fail(RB_ERR_UNSUPPORTED);
+    }
+    h->nRows     = (int)(rows.size() / h->rowf);
+    h->smemBytes = sizeof(float) * kStages * kChunkRows * h->rowf + sizeof(uint64_t) * kStages;
+    if (cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes) !=
+        cudaSuccess) {
+        rb::set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", h->smemBytes,
+                      cudaGetErrorString(cudaGetLastError()));
+        return fail(RB_ERR_CUDA);
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, kThreads, h->smemBytes) != cudaSuccess ||
+        occ < 1) {
+        rb::set_error("gmm kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(RB_ERR_CUDA);
+    }
+    h->ctasPerSm = occ;
+    if (h->dRows.upload(rows, h->stream) != RB_OK || h->dIsd.upload(isd, h->stream) != RB_OK)
+        return fail(RB_ERR_CUDA);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        rb::set_error("model upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(RB_ERR_CUDA);
+    }
+    if (mode == RB_GMM_BATCH_TENSOR) {
+        rc = rb_gmm_tensor_create(ms, h->dev, h->stream, &h->tensor);
+        if (rc != RB_OK)
+            return fail(rc);
+    }
+    *out = h;
+    return RB_OK;
+}
+
+extern "C" void rb_gmm_destroy(rb_gmm* h) {
+    if (!h)
+        return;
+    cudaSetDevice(h->dev.ordinal);
+    delete h;
+}
+
+extern "C" int rb_gmm_n_mixtures(const rb_gmm* h) {
+    return h ? h->nMix : 0;
+}
+
+extern "C" int rb_gmm_dim(const rb_gmm* h) {
+    return h ? h->dim : 0;
+}
+
+extern "C" int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* d_scores, uint32_t* d_best,
+                                void* stream) {
+    RB_REQUIRE(h != nullptr, "gmm handle is NULL");
+    RB_REQUIRE(T >= 0, "negative frame count");
+    if (T == 0)
+        return RB_OK;
+    RB_REQUIRE(d_feats && d_scores, "NULL device buffer");
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    if (h->mode == RB_GMM_BATCH_TENSOR) {
+        RB_REQUIRE(d_best == nullptr, "best-density output is not available in tensor mode");
+        return rb_gmm_tensor_score(h->tensor, d_feats, T, d_scores, s);
+    }
+    if (h->mode == RB_GMM_BATCH_FLOAT)
+        RB_REQUIRE(d_best == nullptr, "Mm::BatchFloatFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
+    return launch_simt(h, d_feats, T, d_scores, d_best, s);
+}
+
+// Host-pointer entry point: frames are cut into slabs; H2D of slab i+1, scoring of slab i and D2H of
+// slab i-1 overlap on three streams (PCIe is the end-to-end bound: 1 KB of scores per frame).
+extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores, uint32_t* best_density) {
+    RB_REQUIRE(h != nullptr, "gmm handle is NULL");
+    RB_REQUIRE(T >= 0, "negative frame count");
+    if (T == 0)
+        return RB_OK;
+    RB_REQUIRE(feats && scores, "NULL host buffer");
+    if (h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_BATCH_TENSOR)
+        RB_REQUIRE(best_density == nullptr, "this scorer mode does not report densities; use RB_GMM_DIAG_MAX");
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    const size_t D = h->dim, M = h->nMix;
+    RB_CHECK(h->dFeats.reserve((size_t)T * D));
+    RB_CHECK(h->dScores.reserve((size_t)T * M));
+    if (best_density)
+        RB_CHECK(h->dBest.reserve((size_t)T * M));
+
+    // slabs: multiples of the frame block, ~16 per call but at least 8192 frames each
+    long slab = std::max<long>(8192, rb::round_up((size_t)((T + 15) / 16), kFramesPerBlock));
+    const int nSlabs = (int)((T + slab - 1) / slab);
+    cudaStream_t sIn = nullptr, sOut = nullptr;
+    RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> evIn(nSlabs), evK(nSlabs);
+    int                      rc = RB_OK;
+    for (int i = 0; i < nSlabs; ++i) {
+        cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming);
+    }
+    for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
+        const long a = (long)i * slab, n = std::min<long>(slab, T - a);
+        if (cudaMemcpyAsync(h->dFeats.p + a * D, feats + a * D, (size_t)n * D * 4, cudaMemcpyHostToDevice, sIn) !=
+            cudaSuccess)
+            rc = RB_ERR_CUDA;
+        cudaEventRecord(evIn[i], sIn);
+        cudaStreamWaitEvent(h->stream, evIn[i], 0);
+        if (rc == RB_OK)
+            rc = rb_gmm_score_dev(h, h->dFeats.p + a * D, n, h->dScores.p + a * M,
+                                  best_density ? h->dBest.p + a * M : nullptr, h->stream);
+        cudaEventRecord(evK[i], h->stream);
+        cudaStreamWaitEvent(sOut, evK[i], 0);
+        if (rc == RB_OK &&
+            cudaMemcpyAsync(scores + a * M, h->dScores.p + a * M, (size_t)n * M * 4, cudaMemcpyDeviceToHost, sOut) !=
+                    cudaSuccess)
+            rc = RB_ERR_CUDA;
+        if (rc == RB_OK && best_density &&
+            cudaMemcpyAsync(best_density + a * M, h->dBest.p + a * M, (size_t)n * M * 4, cudaMemcpyDeviceToHost,
+                            sOut) != cudaSuccess)
+            rc = RB_ERR_CUDA;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(sIn);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaError_t e3 = cudaStreamSynchronize(sOut);
+    for (int i = 0; i < nSlabs; ++i) {
+        cudaEventDestroy(evIn[i]);
+        cudaEventDestroy(evK[i]);
+    }
+    cudaStreamDestroy(sIn);
+    cudaStreamDestroy(sOut);
+    if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
+        rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != RB_OK)
+        return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        rb::set_error("gmm scoring failed on the device: %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
+    return RB_OK;
+}

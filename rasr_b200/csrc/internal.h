@@ -1,0 +1,10 @@
+// internal.h -- cross-translation-unit accessors (not part of the C ABI)
+#pragma once
+#include "common.cuh"
+
+struct rb_frontend;
+struct rb_gmm;
+
+cudaStream_t   rb_frontend_stream(const rb_frontend* h);
+rb::DeviceInfo rb_frontend_device(const rb_frontend* h);
+int            rb_frontend_feat_dim(const rb_frontend* h);

@@ -1,0 +1,191 @@
+"""Host-side mirror of the Flow::Node contract for the MFCC front-end (src/Flow/Node.hh:38-185).
+
+`MfccNode` behaves like the adapter class adapters/B200MfccNode.cc: XML attributes arrive through
+`set_parameter(name, value)` as text (src/Flow/AbstractNode.hh:149-159), `configure()` reads the
+incoming "sample-rate" attribute and publishes the outgoing attributes, samples arrive as packets
+with a start time, and on the EOS sentinel the whole segment is computed on the device and emitted
+one `Vector<f32>` packet per frame (the batch-node pattern of src/Nn/NeuralNetworkForwardNode.cc:187-256).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class Packet:
+    """Flow::Vector<f32> = Timestamp{start,end} + std::vector<f32> (src/Flow/Vector.hh:32-57)."""
+    __slots__ = ("start", "end", "data")
+
+    def __init__(self, data, start, end):
+        self.data, self.start, self.end = data, start, end
+
+
+EOS = object()  # Flow::Data::eos() sentinel
+
+
+class FrontEnd:
+    """Thin RAII wrapper of rb_frontend_* (one handle = one node instance = one CUDA stream)."""
+
+    def __init__(self, sample_rate=16000.0, window_length=0.025, window_shift=0.01, fft_max_input=0.025,
+                 filter_width=268.258, alpha=1.0, n_cepstra=13, derivatives=True, device=0):
+        L = capi.lib()
+        self.cfg = capi.FrontendCfg(sample_rate, window_length, window_shift, fft_max_input, filter_width, alpha,
+                                    n_cepstra, int(derivatives), device)
+        self._h = C.c_void_p()
+        capi.check(L.rb_frontend_create(C.byref(self.cfg), C.byref(self._h)))
+        g = capi.FrontendGeometry()
+        capi.check(L.rb_frontend_get_geometry(self._h, C.byref(g)))
+        self.geometry = g
+        self.feat_dim = g.feat_dim
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().rb_frontend_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def tables(self):
+        g = self.geometry
+        window = np.zeros(g.win_length, np.float32)
+        start = np.zeros(g.n_filters, np.int32)
+        end = np.zeros(g.n_filters, np.int32)
+        w = np.zeros((g.n_filters, g.n_bins), np.float32)
+        dct = np.zeros((self.cfg.n_cepstra, g.n_filters), np.float32)
+        capi.check(capi.lib().rb_frontend_get_tables(self._h, capi.ptr(window), capi.ptr(start), capi.ptr(end),
+                                                     capi.ptr(w), capi.ptr(dct)))
+        return dict(window=window, fb_start=start, fb_end=end, fb_weights=w, dct=dct)
+
+    def nframes_for(self, n_samples):
+        return int(capi.lib().rb_frontend_nframes_for(self._h, n_samples))
+
+    def count_frames(self, offsets):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        fo = np.zeros(offsets.size, np.int64)
+        n = capi.lib().rb_frontend_count_frames(self._h, capi.ptr(offsets), offsets.size - 1, capi.ptr(fo))
+        if n < 0:
+            raise capi.RasrB200Error(-1, "bad offsets")
+        return fo
+
+    def process(self, samples, offsets=None, timestamps=True, stages=False):
+        """Batch of independent segments (host buffers).  Returns dict(feats, frame_offsets, t_start, t_end)."""
+        samples = np.ascontiguousarray(samples, np.float32)
+        if offsets is None:
+            offsets = np.array([0, samples.size], np.int64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        fo = self.count_frames(offsets)
+        T = int(fo[-1])
+        feats = np.zeros((T, self.feat_dim), np.float32)
+        ts = np.zeros(T, np.float64) if timestamps else None
+        te = np.zeros(T, np.float64) if timestamps else None
+        L = capi.lib()
+        if stages:
+            capi.check(L.rb_frontend_set_debug(self._h, 1))
+        try:
+            capi.check(L.rb_frontend_process(self._h, capi.ptr(samples), capi.ptr(offsets), offsets.size - 1,
+                                             capi.ptr(feats), capi.ptr(ts), capi.ptr(te)))
+            out = dict(feats=feats, frame_offsets=fo, t_start=ts, t_end=te)
+            if stages:
+                g = self.geometry
+                amp = np.zeros((T, g.n_bins), np.float32)
+                fb = np.zeros((T, g.n_filters), np.float32)
+                cep = np.zeros((T, self.cfg.n_cepstra), np.float32)
+                capi.check(L.rb_frontend_read_stages(self._h, capi.ptr(amp), capi.ptr(fb), capi.ptr(cep)))
+                out.update(amplitude=amp, fbank=fb, cepstra=cep)
+        finally:
+            if stages:
+                L.rb_frontend_set_debug(self._h, 0)
+        return out
+
+    def process_dev(self, d_samples, offsets, d_feats, stream=None):
+        """Device buffers (torch tensors or raw pointers); only enqueues + syncs the tile tables."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        capi.check(capi.lib().rb_frontend_process_dev(self._h, capi.ptr(d_samples), capi.ptr(offsets),
+                                                      offsets.size - 1, capi.ptr(d_feats), capi.ptr(stream)))
+
+    # streaming protocol
+    def reset(self):
+        capi.check(capi.lib().rb_frontend_reset(self._h))
+
+    def push(self, samples, start_time):
+        samples = np.ascontiguousarray(samples, np.float32)
+        capi.check(capi.lib().rb_frontend_push(self._h, capi.ptr(samples), samples.size, float(start_time)))
+
+    def finish(self):
+        L = capi.lib()
+        capi.check(L.rb_frontend_finish(self._h))
+        T = int(L.rb_frontend_nframes(self._h))
+        feats = np.zeros((T, self.feat_dim), np.float32)
+        ts = np.zeros(T, np.float64)
+        te = np.zeros(T, np.float64)
+        capi.check(L.rb_frontend_read(self._h, capi.ptr(feats), capi.ptr(ts), capi.ptr(te)))
+        return feats, ts, te
+
+
+class MfccNode:
+    """Flow::Node-shaped adapter: filter name, setParameter, configure, work (pull until EOS, then emit)."""
+
+    PARAMS = {"alpha": ("alpha", float), "length": ("window_length", float), "shift": ("window_shift", float),
+              "maximum-input-size": ("fft_max_input", float), "filter-width": ("filter_width", float),
+              "nr-outputs": ("n_cepstra", int), "derivatives": ("derivatives", lambda v: v in ("true", "1", "yes")),
+              "device": ("device", int)}
+
+    @staticmethod
+    def filter_name():
+        return "b200-mfcc"
+
+    def __init__(self):
+        self._kw = {}
+        self._fe = None
+        self._out = []
+        self._segment_open = False
+        self.output_attributes = {}
+
+    def set_parameter(self, name, value):
+        """Returns False for unknown names, like Flow::AbstractNode::setParameter."""
+        if name not in self.PARAMS:
+            return False
+        key, conv = self.PARAMS[name]
+        self._kw[key] = conv(value)
+        self._fe = None
+        return True
+
+    def configure(self, input_attributes):
+        """input_attributes: dict of text attributes; needs "sample-rate" (src/Signal/Window.cc:158-177)."""
+        if input_attributes.get("datatype", "vector-f32") != "vector-f32":
+            return False
+        if "sample-rate" not in input_attributes:
+            return False
+        sr = float(input_attributes["sample-rate"])
+        self._fe = FrontEnd(sample_rate=sr, **self._kw)
+        g = self._fe.geometry
+        self.output_attributes = {"datatype": "vector-f32", "sample-rate": "%g" % (sr / g.win_shift),
+                                  "frame-shift": "%g" % (g.win_shift / sr)}
+        return True
+
+    def put(self, packet):
+        """Input side of work(): a Packet of samples, or EOS."""
+        if self._fe is None:
+            raise capi.RasrB200Error(-5, "node used before configure()")
+        if packet is EOS:
+            feats, ts, te = self._fe.finish()
+            self._out = [Packet(feats[t], ts[t], te[t]) for t in range(feats.shape[0])]
+            self._out.append(EOS)
+            self._fe.reset()
+            self._segment_open = False
+            return
+        if not self._segment_open:
+            self._fe.reset()
+            self._segment_open = True
+        self._fe.push(packet.data, packet.start)
+
+    def work(self):
+        """Output side: one packet per call; EOS terminates the segment."""
+        if not self._out:
+            return None
+        return self._out.pop(0)

@@ -1,0 +1,61 @@
+"""Fused audio -> emission scores (BASELINE config C3) and utterance sharding across ranks.
+
+The reference's only parallel mode is N independent processes over corpus partitions
+(src/Bliss/CorpusDescription.cc:173-180,482-491); `partition()` reproduces that with a
+longest-first greedy bin-pack so ranks finish together.  There is no collective in the compute
+path; `gather_scores()` is the optional all-gather for a single decoder rank.
+"""
+import numpy as np
+
+from . import capi
+
+
+def score_utterances(frontend, gmm, samples, offsets, want_feats=False):
+    """Host buffers in, scores [total_frames x n_mixtures] out; features stay on the device."""
+    samples = np.ascontiguousarray(samples, np.float32)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    fo = frontend.count_frames(offsets)
+    T = int(fo[-1])
+    scores = np.zeros((T, gmm.n_mixtures), np.float32)
+    feats = np.zeros((T, frontend.feat_dim), np.float32) if want_feats else None
+    capi.check(capi.lib().rb_pipeline_score(frontend.handle, gmm.handle, capi.ptr(samples), capi.ptr(offsets),
+                                            offsets.size - 1, capi.ptr(scores), capi.ptr(feats)))
+    return (scores, feats, fo) if want_feats else (scores, fo)
+
+
+def score_utterances_dev(frontend, gmm, d_samples, offsets, d_feats, d_scores, stream=None):
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    capi.check(capi.lib().rb_pipeline_score_dev(frontend.handle, gmm.handle, capi.ptr(d_samples), capi.ptr(offsets),
+                                                offsets.size - 1, capi.ptr(d_feats), capi.ptr(d_scores),
+                                                capi.ptr(stream)))
+
+
+def partition(lengths, world_size):
+    """Assign utterances to ranks: longest first onto the least loaded rank.  Returns a list of index
+    arrays (one per rank, each sorted ascending so a rank walks the corpus in order)."""
+    lengths = np.asarray(lengths, np.int64)
+    order = np.argsort(-lengths, kind="stable")
+    load = np.zeros(world_size, np.int64)
+    parts = [[] for _ in range(world_size)]
+    for u in order:
+        r = int(np.argmin(load))
+        parts[r].append(int(u))
+        load[r] += int(lengths[u])
+    return [np.array(sorted(p), np.int64) for p in parts]
+
+
+def gather_scores(local_scores, dist, group=None):
+    """All-gather of the per-rank score slabs (equal-padded) for a single decoder rank.
+    `local_scores` is a torch tensor [T_r x M] on this rank's device; returns the list of slabs."""
+    import torch
+
+    world = dist.get_world_size(group)
+    n = torch.tensor([local_scores.shape[0]], dtype=torch.int64, device=local_scores.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    tmax = int(max(int(c.item()) for c in counts))
+    padded = torch.zeros((tmax, local_scores.shape[1]), dtype=local_scores.dtype, device=local_scores.device)
+    padded[:local_scores.shape[0]] = local_scores
+    slabs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(slabs, padded, group=group)
+    return [s[:int(c.item())] for s, c in zip(slabs, counts)]

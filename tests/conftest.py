@@ -1,3 +1,4 @@
+import json
 import os
 import sys
 
@@ -14,7 +15,24 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def oracle():
+    """The CPU oracle (test infrastructure): built on demand, checker only."""
     from oracle import pyoracle
 
     pyoracle.build(ref=True)
     return pyoracle
+
+
+@pytest.fixture(scope="session")
+def diag():
+    """Append one JSON line per measurement to gpurun_out/diag.jsonl (comes back from the GPU box)."""
+    path = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(path, exist_ok=True)
+    f = open(os.path.join(path, "diag.jsonl"), "a")
+
+    def report(name, **kv):
+        kv = {k: (v.item() if hasattr(v, "item") else v) for k, v in kv.items()}
+        f.write(json.dumps(dict(test=name, **kv)) + "\n")
+        f.flush()
+
+    yield report
+    f.close()
