@@ -189,8 +189,12 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream()
+    # a non-default stream: the C ABI treats a NULL stream as "the handle's own stream", and the
+    # events below must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     peaks = measured_peaks()
     wl = args.workload
     R = 4  # rotating buffer sets so that no step finds its data in L2
