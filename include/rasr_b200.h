@@ -225,6 +225,9 @@ int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, 
  * ===================================================================================== */
 int rb_test_gemm_bf16(const float* a, const float* b, const float* bias, int M, int N, int K, int act,
                       float* d, int device);
+/* times `iters` launches of one GEMM variant (0: 128x256 tile, 1: 256x256 tile) on device-resident
+ * operands with the bf16 hidden-layer epilogue; *ms_per_iter from CUDA events.  Used by scripts/ only. */
+int rb_test_gemm_bench(int M, int N, int K, int variant, int iters, float* ms_per_iter, int device);
 
 #ifdef __cplusplus
 }

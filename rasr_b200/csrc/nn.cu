@@ -39,7 +39,9 @@ struct EpiHiddenBf16 {  // bf16 activations for the next layer, row pitch ldo (m
     const float*   bias;
     __nv_bfloat16* out;
     int            ldo, N, act;
-    __device__ void operator()(int row, int col0, const float (&v)[32]) const {
+    struct State {};
+    __device__ void begin(State&, int) const {}
+    __device__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
         if (col0 >= ldo)
             return;
         uint32_t packed[16];
@@ -63,7 +65,9 @@ struct EpiFinalF32 {  // f32 output [M x N], out = sign * act(acc + bias)
     float*       out;
     int          ldo, N, act;
     float        sign;
-    __device__ void operator()(int row, int col0, const float (&v)[32]) const {
+    struct State {};
+    __device__ void begin(State&, int) const {}
+    __device__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
         if (col0 >= N)
             return;
         float* dst = out + (size_t)row * ldo + col0;
@@ -218,7 +222,7 @@ struct rb_nn {
     int                  nLayers = 0;
     std::vector<NnLayer*> layers;
     cudaStream_t         stream = nullptr;
-    long                 chunk = 16384;  // frames per pass
+    long                 chunk = 18944;  // frames per pass: 74 row blocks of 256 -> whole waves on 148 SMs
     // bf16 path: ping-pong activation buffers [chunk x maxKPad] and their TMA maps per layer input
     rb::DevBuf<__nv_bfloat16> actA, actB;
     std::vector<CUtensorMap>  mapIn;  // map of the input activation of layer l
@@ -260,8 +264,8 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
                 epi.ldo  = h->layers[l + 1]->kPad;
                 epi.N    = ly->out;
                 epi.act  = ly->act;
-                RB_CHECK(rbgemm::launch(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
-                                        h->dev.sm_count, s));
+                RB_CHECK(rbgemm::launch_mt2(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
+                                            h->dev.sm_count, s));
                 std::swap(cur, nxt);
             }
             else {
@@ -272,8 +276,8 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
                 epi.N    = ly->out;
                 epi.act  = (scoreMode || ly->act == RB_ACT_SOFTMAX) ? RB_ACT_LINEAR : ly->act;
                 epi.sign = scoreMode ? -1.0f : 1.0f;
-                RB_CHECK(rbgemm::launch(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
-                                        h->dev.sm_count, s));
+                RB_CHECK(rbgemm::launch_mt2(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
+                                            h->dev.sm_count, s));
             }
         }
     }
@@ -370,6 +374,7 @@ extern "C" int rb_nn_create(int n_layers, const int* dims, const int* act, const
     }
     h->precision = precision;
     h->nLayers   = n_layers;
+    h->chunk     = (long)rbgemm::MT2_BM * std::max(1, h->dev.sm_count / 2);
     int maxKPad = 0, maxDim = 0;
     for (int l = 0; l < n_layers; ++l) {
         NnLayer* ly = new NnLayer();
@@ -429,7 +434,7 @@ extern "C" int rb_nn_create(int n_layers, const int* dims, const int* act, const
         for (int l = 0; l < n_layers; ++l) {
             const __nv_bfloat16* buf = (l % 2 == 0) ? h->actA.p : h->actB.p;
             rc = rbgemm::make_map(&h->mapIn[l], buf, (uint64_t)h->chunk, (uint64_t)h->layers[l]->kPad,
-                                  (uint64_t)h->layers[l]->kPad, rbgemm::BM, true);
+                                  (uint64_t)h->layers[l]->kPad, rbgemm::MT2_BM, true);
             if (rc != RB_OK)
                 return fail(rc);
         }
@@ -506,7 +511,8 @@ extern "C" int rb_test_gemm_bf16(const float* a, const float* b, const float* bi
         convert_pad_bf16_kernel<<<256, 256, 0, s>>>(dB32.p, dB.p, N, K, kPad);
         rb::count_launch(2);
         CUtensorMap mA, mB;
-        if ((rc = rbgemm::make_map(&mA, dA.p, M, kPad, kPad, rbgemm::BM, true)) != RB_OK) break;
+        const bool  mt2 = M >= rbgemm::MT2_BM;  // both kernels are exercised by the parity tests
+        if ((rc = rbgemm::make_map(&mA, dA.p, M, kPad, kPad, mt2 ? rbgemm::MT2_BM : rbgemm::BM, true)) != RB_OK) break;
         if ((rc = rbgemm::make_map(&mB, dB.p, N, kPad, kPad, rbgemm::BN, true)) != RB_OK) break;
         EpiFinalF32 epi;
         epi.bias = bias ? dBias.p : nullptr;
@@ -515,7 +521,9 @@ extern "C" int rb_test_gemm_bf16(const float* a, const float* b, const float* bi
         epi.N    = N;
         epi.act  = act;
         epi.sign = 1.0f;
-        if ((rc = rbgemm::launch(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s)) != RB_OK) break;
+        rc = mt2 ? rbgemm::launch_mt2(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s)
+                 : rbgemm::launch(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s);
+        if (rc != RB_OK) break;
         cudaError_t e = cudaMemcpyAsync(d, dD.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess)
             e = cudaStreamSynchronize(s);
@@ -526,4 +534,59 @@ extern "C" int rb_test_gemm_bf16(const float* a, const float* b, const float* bi
     } while (0);
     cudaStreamDestroy(s);
     return rc;
+}
+
+// ---- test hook: time one GEMM variant on device-resident operands (bf16 hidden-layer epilogue) -----
+extern "C" int rb_test_gemm_bench(int M, int N, int K, int variant, int iters, float* ms_per_iter, int device) {
+    RB_REQUIRE(M > 0 && N > 0 && K > 0 && iters > 0 && ms_per_iter, "bad argument");
+    rb::DeviceInfo dev;
+    RB_CHECK(rb::use_device(device, &dev));
+    const int kPad = (int)rb::round_up(K, 64), nPad = (int)rb::round_up(N, 64);
+    rb::DevBuf<__nv_bfloat16> dA, dB, dC;
+    rb::DevBuf<float>         dBias;
+    RB_CHECK(dA.reserve((size_t)M * kPad));
+    RB_CHECK(dB.reserve((size_t)N * kPad));
+    RB_CHECK(dC.reserve((size_t)M * nPad));
+    RB_CHECK(dBias.reserve(N));
+    // 0x3c00 bit pattern = 0.0078 in bf16: finite, non-trivial operands
+    RB_CUDA(cudaMemset(dA.p, 0x3c, (size_t)M * kPad * 2));
+    RB_CUDA(cudaMemset(dB.p, 0x3c, (size_t)N * kPad * 2));
+    RB_CUDA(cudaMemset(dBias.p, 0, (size_t)N * 4));
+    CUtensorMap mA, mB;
+    const bool  mt2 = variant == 1;
+    RB_CHECK(rbgemm::make_map(&mA, dA.p, M, kPad, kPad, mt2 ? rbgemm::MT2_BM : rbgemm::BM, true));
+    RB_CHECK(rbgemm::make_map(&mB, dB.p, N, kPad, kPad, rbgemm::BN, true));
+    EpiHiddenBf16 epi;
+    epi.bias = dBias.p;
+    epi.out  = dC.p;
+    epi.ldo  = nPad;
+    epi.N    = N;
+    epi.act  = RB_ACT_RELU;
+    cudaStream_t s = nullptr;
+    RB_CUDA(cudaStreamCreate(&s));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int rc = RB_OK;
+    for (int i = 0; i < iters + 2 && rc == RB_OK; ++i) {
+        if (i == 2)
+            cudaEventRecord(e0, s);
+        rc = mt2 ? rbgemm::launch_mt2(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s)
+                 : rbgemm::launch(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s);
+    }
+    cudaEventRecord(e1, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    float       ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+    if (rc != RB_OK)
+        return rc;
+    if (e != cudaSuccess) {
+        rb::set_error("GEMM benchmark failed: %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
+    *ms_per_iter = ms / iters;
+    return RB_OK;
 }
