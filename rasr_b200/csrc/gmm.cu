@@ -51,17 +51,53 @@ struct GmmParams {
     int             vec4;  // 1: nMix % 4 == 0 and scores 16-byte aligned -> float4 stores
 };
 
+// packed pairs of f32 in one 64-bit register pair (sm_100 FADD2 / FMUL2 / FFMA2)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(uint64_t v) {
+    return __uint_as_float((uint32_t)v);
+}
+__device__ __forceinline__ float hi2(uint64_t v) {
+    return __uint_as_float((uint32_t)(v >> 32));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// strict (non-contracted) a + d*d per lane.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the
+// explicit rounding modifiers, so the product is formed with scalar FMULs whose .rn is honoured.
+__device__ __forceinline__ uint64_t sqadd2(uint64_t d, uint64_t a) {
+    const float dl = lo2(d), dh = hi2(d);
+    return pack2(__fadd_rn(lo2(a), __fmul_rn(dl, dl)), __fadd_rn(hi2(a), __fmul_rn(dh, dh)));
+}
+
 __device__ __forceinline__ float sq_acc(float d, float a, bool fuse) {
     return fuse ? __fmaf_rn(d, d, a) : __fadd_rn(a, __fmul_rn(d, d));
 }
 
 // ------------------------------------------------------------------------------------------
-// BATCH_FLOAT: row = [ mu' (NB*8) | c | flags | 0 | 0 ],  rowf = NB*8+4
+// BATCH_FLOAT: row = [ mu' (NB*8) | c | 0 | flags | 0 ],  rowf = NB*8+4
 // ------------------------------------------------------------------------------------------
-template<int NB, bool FUSE>
-__global__ void __launch_bounds__(kThreads, (NB <= 5) ? 2 : 1) gmm_batch_kernel(const GmmParams p) {
+template<int NB, bool FUSE, int FPT>
+__global__ void __launch_bounds__(kThreads, (NB <= 5) ? (FPT == 1 ? 3 : (FPT == 2 ? 2 : 1)) : 1) gmm_batch_kernel(const GmmParams p) {
     constexpr int ROWF  = NB * 8 + 4;
     constexpr int CHUNK = kChunkRows * ROWF;  // floats per stage
+    constexpr int FPB   = kThreads * FPT;     // frames per block
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float*    buf = reinterpret_cast<float*>(smem_raw);                       // kStages * CHUNK
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * kStages * CHUNK);
@@ -83,8 +119,10 @@ __global__ void __launch_bounds__(kThreads, (NB <= 5) ? 2 : 1) gmm_batch_kernel(
         const int  row0 = p.grp_row[g], row1 = p.grp_row[g + 1];
         int        mix  = p.grp_mix[g];
         const int  nCh  = (row1 - row0 + kChunkRows - 1) / kChunkRows;
-        const long t0   = (long)fb * kFramesPerBlock + tid;
-        const long t1   = t0 + kThreads;
+        long       t[FPT];
+#pragma unroll
+        for (int f = 0; f < FPT; ++f)
+            t[f] = (long)fb * FPB + f * kThreads + tid;
 
         // producer prologue
         if (tid == 0) {
@@ -98,25 +136,31 @@ __global__ void __launch_bounds__(kThreads, (NB <= 5) ? 2 : 1) gmm_batch_kernel(
             }
         }
 
-        // the two feature vectors of this thread, scaled by 1/sigma (setFeature :157-162)
-        float x0[NB * 8], x1[NB * 8];
-        {
-            const long   ta = t0 < p.T ? t0 : p.T - 1;
-            const long   tb = t1 < p.T ? t1 : p.T - 1;
-            const float* fa = p.feats + (size_t)ta * p.dim;
-            const float* fbp = p.feats + (size_t)tb * p.dim;
+        // the feature vectors of this thread, scaled by 1/sigma (setFeature :157-162); dims (2i, 2i+1) packed
+        uint64_t x[FPT][NB * 4];
 #pragma unroll
-            for (int d = 0; d < NB * 8; ++d) {
-                const float s = d < p.dim ? __ldg(p.isd + d) : 0.0f;
-                x0[d]         = d < p.dim ? __fmul_rn(__ldg(fa + d), s) : 0.0f;
-                x1[d]         = d < p.dim ? __fmul_rn(__ldg(fbp + d), s) : 0.0f;
+        for (int f = 0; f < FPT; ++f) {
+            const long   tc = t[f] < p.T ? t[f] : p.T - 1;
+            const float* fp = p.feats + (size_t)tc * p.dim;
+#pragma unroll
+            for (int i = 0; i < NB * 4; ++i) {
+                float v[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int d = 2 * i + k;
+                    v[k]        = d < p.dim ? __fmul_rn(__ldg(fp + d), __ldg(p.isd + d)) : 0.0f;
+                }
+                x[f][i] = pack2(v[0], v[1]);
             }
         }
 
-        float best0 = FLT_MAX, best1 = FLT_MAX;
-        float o0a = 0, o1a = 0, o2a = 0, o3a = 0;  // staged outputs of frame t0
-        float o0b = 0, o1b = 0, o2b = 0, o3b = 0;  // staged outputs of frame t1
-        int   nStaged = 0;
+        float best[FPT], o[FPT][4];  // running minimum / staged outputs
+#pragma unroll
+        for (int f = 0; f < FPT; ++f) {
+            best[f] = FLT_MAX;
+            o[f][0] = o[f][1] = o[f][2] = o[f][3] = 0.0f;
+        }
+        int nStaged = 0;
 
         for (int c = 0; c < nCh; ++c) {
             if (tid == 0 && c + kStages - 1 < nCh) {
@@ -135,59 +179,66 @@ __global__ void __launch_bounds__(kThreads, (NB <= 5) ? 2 : 1) gmm_batch_kernel(
             const int    nr    = min(kChunkRows, row1 - (row0 + c * kChunkRows));
 
             for (int r = 0; r < nr; ++r) {
-                const float4* row  = reinterpret_cast<const float4*>(chunk + r * ROWF);
-                const float4  tail = row[NB * 2];
-                float         a0[8], a1[8];
-                a0[0] = tail.x;  // constant first, in lane 0 of the first accumulator (:217-219)
-                a1[0] = tail.x;
+                // packed f32x2 arithmetic (FADD2/FFMA2): lanes (2i, 2i+1) of the reference's 8 partial sums share a
+                // 64-bit register pair; every lane is still one IEEE f32 sub / fma, so the result is unchanged
+                const ulonglong2* row  = reinterpret_cast<const ulonglong2*>(chunk + r * ROWF);
+                const ulonglong2  tail = row[NB * 2];  // (c, 0 | flags, 0)
+                uint64_t          a[FPT][4];
 #pragma unroll
-                for (int j = 1; j < 8; ++j) {
-                    a0[j] = 0.0f;
-                    a1[j] = 0.0f;
+                for (int f = 0; f < FPT; ++f) {
+                    a[f][0] = tail.x;  // constant first, in lane 0 of the first accumulator (:217-219)
+                    a[f][1] = a[f][2] = a[f][3] = 0ull;
                 }
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    const float4 m0 = row[2 * b], m1 = row[2 * b + 1];
-                    const float  m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                    const ulonglong2 m0 = row[2 * b], m1 = row[2 * b + 1];
+                    const uint64_t   m[4] = {m0.x, m0.y, m1.x, m1.y};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float d0 = __fsub_rn(m[j], x0[8 * b + j]);
-                        const float d1 = __fsub_rn(m[j], x1[8 * b + j]);
-                        a0[j]          = sq_acc(d0, a0[j], FUSE);
-                        a1[j]          = sq_acc(d1, a1[j], FUSE);
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int f = 0; f < FPT; ++f) {
+                            const uint64_t d = sub2(m[j], x[f][4 * b + j]);
+                            a[f][j]          = FUSE ? fma2(d, d, a[f][j]) : sqadd2(d, a[f][j]);
+                        }
                     }
                 }
-                // s1 += s2; then the two shuffle/add steps of :236-243: (l0+l2)+(l1+l3)
-                const float r0s = __fadd_rn(__fadd_rn(__fadd_rn(a0[0], a0[4]), __fadd_rn(a0[2], a0[6])),
-                                            __fadd_rn(__fadd_rn(a0[1], a0[5]), __fadd_rn(a0[3], a0[7])));
-                const float r1s = __fadd_rn(__fadd_rn(__fadd_rn(a1[0], a1[4]), __fadd_rn(a1[2], a1[6])),
-                                            __fadd_rn(__fadd_rn(a1[1], a1[5]), __fadd_rn(a1[3], a1[7])));
-                best0 = best0 < r0s ? best0 : r0s;
-                best1 = best1 < r1s ? best1 : r1s;
-
-                if (__float_as_int(tail.y) & 1) {  // last density of its mixture: emit
-                    const float v0 = best0 < FLT_MAX ? __fmul_rn(best0, 0.5f) : best0;
-                    const float v1 = best1 < FLT_MAX ? __fmul_rn(best1, 0.5f) : best1;
-                    best0 = FLT_MAX;
-                    best1 = FLT_MAX;
+                const bool last = (uint32_t)tail.y & 1u;  // last density of its mixture: emit
+                float      v[FPT];
+#pragma unroll
+                for (int f = 0; f < FPT; ++f) {
+                    // s1 += s2; then the two shuffle/add steps of :236-243: (l0+l2)+(l1+l3)
+                    const uint64_t q  = add2(add2(a[f][0], a[f][2]), add2(a[f][1], a[f][3]));
+                    const float    rs = __fadd_rn(lo2(q), hi2(q));
+                    best[f]           = best[f] < rs ? best[f] : rs;
+                }
+                if (last) {
+#pragma unroll
+                    for (int f = 0; f < FPT; ++f) {
+                        v[f]    = best[f] < FLT_MAX ? __fmul_rn(best[f], 0.5f) : best[f];
+                        best[f] = FLT_MAX;
+                    }
                     if (p.vec4) {
-                        o0a = o1a; o1a = o2a; o2a = o3a; o3a = v0;
-                        o0b = o1b; o1b = o2b; o2b = o3b; o3b = v1;
+#pragma unroll
+                        for (int f = 0; f < FPT; ++f) {
+                            o[f][0] = o[f][1];
+                            o[f][1] = o[f][2];
+                            o[f][2] = o[f][3];
+                            o[f][3] = v[f];
+                        }
                         if (++nStaged == 4) {
                             nStaged = 0;
-                            if (t0 < p.T)
-                                *reinterpret_cast<float4*>(p.scores + (size_t)t0 * p.nMix + (mix - 3)) =
-                                        make_float4(o0a, o1a, o2a, o3a);
-                            if (t1 < p.T)
-                                *reinterpret_cast<float4*>(p.scores + (size_t)t1 * p.nMix + (mix - 3)) =
-                                        make_float4(o0b, o1b, o2b, o3b);
+#pragma unroll
+                            for (int f = 0; f < FPT; ++f)
+                                if (t[f] < p.T)
+                                    *reinterpret_cast<float4*>(p.scores + (size_t)t[f] * p.nMix + (mix - 3)) =
+                                            make_float4(o[f][0], o[f][1], o[f][2], o[f][3]);
                         }
                     }
                     else {
-                        if (t0 < p.T)
-                            p.scores[(size_t)t0 * p.nMix + mix] = v0;
-                        if (t1 < p.T)
-                            p.scores[(size_t)t1 * p.nMix + mix] = v1;
+#pragma unroll
+                        for (int f = 0; f < FPT; ++f)
+                            if (t[f] < p.T)
+                                p.scores[(size_t)t[f] * p.nMix + mix] = v[f];
                     }
                     ++mix;
                 }
@@ -390,8 +441,14 @@ __global__ void __launch_bounds__(kThreads, (NQ <= 10) ? 2 : 1) gmm_diag_kernel(
 typedef void (*GmmKernel)(const GmmParams);
 
 template<int N>
-GmmKernel pick_batch(bool fuse) {
-    return fuse ? gmm_batch_kernel<N, true> : gmm_batch_kernel<N, false>;
+GmmKernel pick_batch(bool fuse, int fpt) {
+    if (fpt == 1)
+        return fuse ? gmm_batch_kernel<N, true, 1> : gmm_batch_kernel<N, false, 1>;
+    if constexpr (N <= 5) {
+        if (fpt == 4)
+            return fuse ? gmm_batch_kernel<N, true, 4> : gmm_batch_kernel<N, false, 4>;
+    }
+    return fuse ? gmm_batch_kernel<N, true, 2> : gmm_batch_kernel<N, false, 2>;
 }
 template<int N>
 GmmKernel pick_diag(bool fuse, bool sum) {
@@ -400,16 +457,16 @@ GmmKernel pick_diag(bool fuse, bool sum) {
     return fuse ? gmm_diag_kernel<N, true, false> : gmm_diag_kernel<N, false, false>;
 }
 
-GmmKernel batch_kernel_for(int nb, bool fuse) {
+GmmKernel batch_kernel_for(int nb, bool fuse, int fpt) {
     switch (nb) {
-        case 1: return pick_batch<1>(fuse);
-        case 2: return pick_batch<2>(fuse);
-        case 3: return pick_batch<3>(fuse);
-        case 4: return pick_batch<4>(fuse);
-        case 5: return pick_batch<5>(fuse);
-        case 6: return pick_batch<6>(fuse);
-        case 7: return pick_batch<7>(fuse);
-        case 8: return pick_batch<8>(fuse);
+        case 1: return pick_batch<1>(fuse, fpt);
+        case 2: return pick_batch<2>(fuse, fpt);
+        case 3: return pick_batch<3>(fuse, fpt);
+        case 4: return pick_batch<4>(fuse, fpt);
+        case 5: return pick_batch<5>(fuse, fpt);
+        case 6: return pick_batch<6>(fuse, fpt);
+        case 7: return pick_batch<7>(fuse, fpt);
+        case 8: return pick_batch<8>(fuse, fpt);
     }
     return nullptr;
 }
@@ -459,6 +516,14 @@ struct rb_gmm {
     GmmKernel      kernel = nullptr;
     size_t         smemBytes = 0;
     int            ctasPerSm = 1;
+    int            framesPerBlock = kFramesPerBlock;
+    // BATCH_FLOAT: launch variants with 1 / 2 / 4 frames per thread, picked per call by predicted efficiency
+    struct Variant {
+        GmmKernel kernel = nullptr;
+        int       framesPerBlock = 0, ctasPerSm = 0;
+        double    rate = 0;  // measured relative arithmetic rate at full occupancy (C2 shape, B200)
+    } variants[3];
+    int nVariants = 0, curVariant = -1;
 
     std::vector<int> rowsOfMixture;  // rows each mixture occupies (>= 1)
     int              curGroups = -1;
@@ -559,7 +624,7 @@ int build_batch_rows(rb_gmm* h, const rb_mixture_set* ms, std::vector<float>& ro
             else {
                 row[NB * 8] = FLT_MAX;
             }
-            row[NB * 8 + 1] = int_bits(i + 1 == nr ? 1 : 0);
+            row[NB * 8 + 2] = int_bits(i + 1 == nr ? 1 : 0);
         }
     }
     return RB_OK;
@@ -640,8 +705,8 @@ void make_groups(const rb_gmm* h, int G, std::vector<int>& grpRow, std::vector<i
     grpMix.push_back(nMix);
 }
 
-int choose_groups(const rb_gmm* h, long T, int slots) {
-    const long FB   = (T + kFramesPerBlock - 1) / kFramesPerBlock;
+int choose_groups(const rb_gmm* h, long T, int slots, int framesPerBlock, double* effOut = nullptr) {
+    const long FB   = (T + framesPerBlock - 1) / framesPerBlock;
     const int  gmax = std::max(1, std::min(64, std::min(h->nMix / 4, h->nRows / 128)));
     int        best = 1;
     double     bestEff = -1;
@@ -654,12 +719,33 @@ int choose_groups(const rb_gmm* h, long T, int slots) {
             best    = G;
         }
     }
+    if (effOut)  // wave efficiency x lane fill of the last frame block
+        *effOut = bestEff * (double)T / (double)(FB * framesPerBlock);
     return best;
 }
 
 int launch_simt(rb_gmm* h, const float* dFeats, long T, float* dScores, uint32_t* dBest, cudaStream_t s) {
+    if (h->nVariants > 0) {
+        int    pick = 0;
+        double bestScore = -1;
+        for (int v = 0; v < h->nVariants; ++v) {
+            double eff = 0;
+            choose_groups(h, T, h->dev.sm_count * h->variants[v].ctasPerSm, h->variants[v].framesPerBlock, &eff);
+            if (eff * h->variants[v].rate > bestScore) {
+                bestScore = eff * h->variants[v].rate;
+                pick      = v;
+            }
+        }
+        if (pick != h->curVariant) {
+            h->curVariant     = pick;
+            h->kernel         = h->variants[pick].kernel;
+            h->framesPerBlock = h->variants[pick].framesPerBlock;
+            h->ctasPerSm      = h->variants[pick].ctasPerSm;
+            h->curGroups      = -1;
+        }
+    }
     const int slots = h->dev.sm_count * h->ctasPerSm;
-    const int G     = choose_groups(h, T, slots);
+    const int G     = choose_groups(h, T, slots, h->framesPerBlock);
     if (G != h->curGroups) {
         std::vector<int> grpRow, grpMix;
         make_groups(h, G, grpRow, grpMix);
@@ -683,7 +769,7 @@ int launch_simt(rb_gmm* h, const float* dFeats, long T, float* dScores, uint32_t
     p.dim          = h->dim;
     p.nMix         = h->nMix;
     p.nGroups      = h->curGroups;
-    p.nFrameBlocks = (int)((T + kFramesPerBlock - 1) / kFramesPerBlock);
+    p.nFrameBlocks = (int)((T + h->framesPerBlock - 1) / h->framesPerBlock);
     p.vec4         = (h->nMix % 4 == 0 && ((uintptr_t)dScores % 16 == 0)) ? 1 : 0;
     const long items = (long)p.nGroups * p.nFrameBlocks;
     const int  grid  = (int)std::min<long>(items, slots);
@@ -731,7 +817,23 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         rc = build_batch_rows(h, ms, rows, isd);
         if (rc != RB_OK)
             return fail(rc);
-        h->kernel = batch_kernel_for(h->nUnits, h->fuse);
+        // more frames per thread = fewer LDS.128 of the density rows per FFMA2 (each costs ~3 FMA-pipe cycles of
+        // register-file bandwidth, scripts/micro/fp32_rate.cu) but larger frame blocks; 4 needs dim <= 40
+        static const int    fpts[3]  = {1, 2, 4};
+        static const double rates[3] = {0.947, 0.936, 1.0};
+        const char*         force    = getenv("RB_GMM_FPT");
+        for (int i = 0; i < 3; ++i) {
+            if (force && atoi(force) != fpts[i])
+                continue;
+            GmmKernel k = (fpts[i] == 4 && h->nUnits > 5) ? nullptr : batch_kernel_for(h->nUnits, h->fuse, fpts[i]);
+            if (!k)
+                continue;
+            rb_gmm::Variant& v = h->variants[h->nVariants++];
+            v.kernel           = k;
+            v.framesPerBlock   = kThreads * fpts[i];
+            v.rate             = rates[i];
+        }
+        h->kernel = h->nVariants ? h->variants[0].kernel : nullptr;
     }
     else {
         if (ms->dim > 64) {
@@ -763,6 +865,17 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         return fail(RB_ERR_CUDA);
     }
     h->ctasPerSm = occ;
+    for (int v = 0; v < h->nVariants; ++v) {
+        if (cudaFuncSetAttribute(h->variants[v].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smemBytes) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->variants[v].kernel, kThreads, h->smemBytes) !=
+                    cudaSuccess ||
+            occ < 1) {
+            rb::set_error("gmm kernel variant does not fit on the device: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(RB_ERR_CUDA);
+        }
+        h->variants[v].ctasPerSm = occ;
+    }
     if (h->dRows.upload(rows, h->stream) != RB_OK || h->dIsd.upload(isd, h->stream) != RB_OK)
         return fail(RB_ERR_CUDA);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
