@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(256) mfcc_derivative_kernel(const FeParams p) 
     }
 }
 
+#include "frontend_fft256.cuh"
+
 }  // namespace
 
 // ==========================================================================================
@@ -310,6 +312,11 @@ struct rb_frontend {
     // launch configuration
     int    sampleCap = 0, nBinsPad = 0, fbPad = 0, grid = 0;
     size_t smemBytes = 0;
+    // register-resident kernel for the 512-point geometry (frontend_fft256.cuh)
+    bool       fast = false;
+    F256Tables f256;
+    int        fastSampleCap = 0, fastGrid = 0;
+    size_t     fastSmemBytes = 0;
     // device buffers
     rb::DevBuf<float>   dTables, dSamples, dCep, dFeats, dDbgAmp, dDbgFbank;
     rb::DevBuf<int64_t> dSampleOff, dFrameOff;
@@ -485,6 +492,73 @@ int build_tables(rb_frontend* h) {
     h->oFbW     = put_f(h->fbWeights);
     h->oDct     = put_f(h->dct);
     align4();
+
+    // ---- extra tables of the register-resident 512-point kernel
+    h->fast = h->N == 512 && (h->S % 2) == 0 && F <= 32 && K <= 32 && h->nWeights <= 32 * kTapsPerLane &&
+              getenv("RB_FRONTEND_GENERIC") == nullptr;
+    if (h->fast) {
+        F256Tables& t = h->f256;
+        std::vector<float> twA(7 * 32 * 2), twB(7 * 4 * 2), tws512(256 * 2), win(512, 0.0f);
+        for (int k1 = 1; k1 < 8; ++k1)
+            for (int l = 0; l < 32; ++l) {
+                twA[((k1 - 1) * 32 + l) * 2]     = (float)cos(2.0 * M_PI * (l * k1) / 256.0);
+                twA[((k1 - 1) * 32 + l) * 2 + 1] = (float)sin(2.0 * M_PI * (l * k1) / 256.0);
+            }
+        for (int j1 = 1; j1 < 8; ++j1)
+            for (int m0 = 0; m0 < 4; ++m0) {
+                twB[((j1 - 1) * 4 + m0) * 2]     = (float)cos(2.0 * M_PI * (m0 * j1) / 32.0);
+                twB[((j1 - 1) * 4 + m0) * 2 + 1] = (float)sin(2.0 * M_PI * (m0 * j1) / 32.0);
+            }
+        for (int k = 0; k < 256; ++k) {
+            tws512[2 * k]     = (float)cos(2.0 * M_PI * k / 512.0);
+            tws512[2 * k + 1] = (float)sin(2.0 * M_PI * k / 512.0);
+        }
+        std::copy(h->window.begin(), h->window.end(), win.begin());
+        // mel taps dealt to the lanes in contiguous runs (filter-major); one partial sum per (lane, filter) segment
+        const int        run = std::max(1, (h->nWeights + 31) / 32);
+        std::vector<int> meta(kTapsPerLane * 32, 0), partOff(33, 0);
+        std::vector<float> melW(kTapsPerLane * 32, 0.0f);
+        std::vector<int> tapFilter(h->nWeights), tapBin(h->nWeights);
+        for (int f = 0; f < F; ++f)
+            for (int k = h->fbStart[f]; k < h->fbEnd[f]; ++k) {
+                tapFilter[h->fbOff[f] + k - h->fbStart[f]] = f;
+                tapBin[h->fbOff[f] + k - h->fbStart[f]]    = k;
+            }
+        int nPart = 0, maxPart = 0;
+        std::vector<int> partsOfFilter(F, 0);
+        for (int tap = 0; tap < h->nWeights; ++tap) {
+            const int  lane = tap / run, i = tap % run;
+            const bool last = tap + 1 == h->nWeights || (tap + 1) / run != lane || tapFilter[tap + 1] != tapFilter[tap];
+            meta[i * 32 + lane] = tapBin[tap] | (last ? 0x10000 : 0) | (last ? nPart << 20 : 0);
+            melW[i * 32 + lane] = h->fbWeights[tap];
+            if (last) {
+                ++nPart;
+                ++partsOfFilter[tapFilter[tap]];
+            }
+        }
+        for (int f = 0; f < F; ++f) {
+            partOff[f + 1] = partOff[f] + partsOfFilter[f];
+            maxPart        = std::max(maxPart, partsOfFilter[f]);
+        }
+        for (int f = F; f < 32; ++f)
+            partOff[f + 1] = partOff[f];
+        std::vector<float> dctT((size_t)F * 32, 0.0f);
+        for (int c = 0; c < K; ++c)
+            for (int n = 0; n < F; ++n)
+                dctT[(size_t)n * 32 + c] = h->dct[(size_t)c * F + n];
+        if (nPart > 72)
+            h->fast = false;
+        t.oTwA     = put_f(twA);
+        t.oTwB     = put_f(twB);
+        t.oTws     = put_f(tws512);
+        t.oWin     = put_f(win);
+        t.oMelMeta = put_i(meta);
+        t.oMelW    = put_f(melW);
+        t.oPartOff = put_i(partOff);
+        t.oDctT    = put_f(dctT);
+        t.maxPart  = maxPart;
+        align4();
+    }
     return RB_OK;
 }
 
@@ -609,8 +683,14 @@ int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, in
         p.dbgFbank   = h->dDbgFbank.p;
         h->dbgFrames = (long)total;
     }
-    const int grid = (int)std::min<size_t>(nTiles, (size_t)h->grid);
-    mfcc_static_kernel<<<grid, kThreads, h->smemBytes, s>>>(p, h->sampleCap, h->nBinsPad, h->fbPad, h->log2M);
+    if (h->fast) {
+        const int grid = (int)std::min<size_t>(nTiles, (size_t)h->fastGrid);
+        mfcc_fft256_kernel<<<grid, kF256Threads, h->fastSmemBytes, s>>>(p, h->f256, h->fastSampleCap);
+    }
+    else {
+        const int grid = (int)std::min<size_t>(nTiles, (size_t)h->grid);
+        mfcc_static_kernel<<<grid, kThreads, h->smemBytes, s>>>(p, h->sampleCap, h->nBinsPad, h->fbPad, h->log2M);
+    }
     RB_LAUNCH_CHECK();
     if (h->cfg.derivatives) {
         const int grid2 = (int)std::min<size_t>(nTiles, (size_t)h->dev.sm_count * 8);
@@ -690,6 +770,23 @@ extern "C" int rb_frontend_create(const rb_frontend_cfg* cfg, rb_frontend** out)
         return fail(RB_ERR_CUDA);
     }
     h->grid = h->dev.sm_count * occ;
+    if (h->fast) {
+        h->fastSampleCap = (int)rb::round_up((size_t)(kTileFrames - 1) * h->S + h->N + 16, 4);
+        h->fastSmemBytes = sizeof(float) * (rb::round_up(h->blob.size(), 4) + 2 * (size_t)h->fastSampleCap +
+                                            (size_t)kF256Warps * kWarpScratch);
+        if (h->fastSmemBytes > h->dev.smem_optin ||
+            cudaFuncSetAttribute(mfcc_fft256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->fastSmemBytes) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mfcc_fft256_kernel, kF256Threads,
+                                                          h->fastSmemBytes) != cudaSuccess ||
+            occ < 1) {
+            cudaGetLastError();
+            h->fast = false;  // the generic kernel still fits
+        }
+        else {
+            h->fastGrid = h->dev.sm_count * occ;
+        }
+    }
     if (h->dTables.upload(h->blob, h->stream) != RB_OK || cudaStreamSynchronize(h->stream) != cudaSuccess) {
         rb::set_error("table upload failed");
         return fail(RB_ERR_CUDA);
