@@ -22,6 +22,7 @@
 // Kernel 2 (mfcc_derivative_kernel): delta / delta-delta over the +-2 frame window with edge
 // replication, concatenated output, arithmetic in the reference's operation order.
 #include <cmath>
+#include <functional>
 
 #include "common.cuh"
 #include "internal.h"
@@ -315,7 +316,10 @@ struct rb_frontend {
     // register-resident kernel for the 512-point geometry (frontend_fft256.cuh)
     bool       fast = false;
     F256Tables f256;
-    int        fastSampleCap = 0, fastGrid = 0;
+    std::vector<float> fastBlob;
+    rb::DevBuf<float>  dFastTables;
+    int        fastSampleCap = 0, fastGrid = 0, fastTpl = 0;
+    void (*fastKernel)(const FeParams, const F256Tables, int) = nullptr;
     size_t     fastSmemBytes = 0;
     // device buffers
     rb::DevBuf<float>   dTables, dSamples, dCep, dFeats, dDbgAmp, dDbgFbank;
@@ -493,8 +497,8 @@ int build_tables(rb_frontend* h) {
     h->oDct     = put_f(h->dct);
     align4();
 
-    // ---- extra tables of the register-resident 512-point kernel
-    h->fast = h->N == 512 && (h->S % 2) == 0 && F <= 32 && K <= 32 && h->nWeights <= 32 * kTapsPerLane &&
+    // ---- tables of the register-resident 512-point kernel: their own blob (the generic tables are not needed then)
+    h->fast = h->N == 512 && (h->S % 2) == 0 && F <= 32 && K <= 32 &&               (kTileFrames - 1) * h->S + h->N <= kPreRounds * kF256Threads &&
               getenv("RB_FRONTEND_GENERIC") == nullptr;
     if (h->fast) {
         F256Tables& t = h->f256;
@@ -514,50 +518,91 @@ int build_tables(rb_frontend* h) {
             tws512[2 * k + 1] = (float)sin(2.0 * M_PI * k / 512.0);
         }
         std::copy(h->window.begin(), h->window.end(), win.begin());
-        // mel taps dealt to the lanes in contiguous runs (filter-major); one partial sum per (lane, filter) segment
-        const int        run = std::max(1, (h->nWeights + 31) / 32);
-        std::vector<int> meta(kTapsPerLane * 32, 0), partOff(33, 0);
-        std::vector<float> melW(kTapsPerLane * 32, 0.0f);
-        std::vector<int> tapFilter(h->nWeights), tapBin(h->nWeights);
-        for (int f = 0; f < F; ++f)
-            for (int k = h->fbStart[f]; k < h->fbEnd[f]; ++k) {
-                tapFilter[h->fbOff[f] + k - h->fbStart[f]] = f;
-                tapBin[h->fbOff[f] + k - h->fbStart[f]]    = k;
+        // mel: every lane owns one contiguous piece of one filter; smallest piece length that needs <= 32 lanes
+        int tpl = 0;
+        for (int cand : {16, 24, 32}) {
+            int lanes = 0, worst = 0;
+            for (int f = 0; f < F; ++f) {
+                const int n = h->fbEnd[f] - h->fbStart[f], pcs = std::max(1, (n + cand - 1) / cand);
+                lanes += pcs;
+                worst = std::max(worst, pcs);
             }
-        int nPart = 0, maxPart = 0;
-        std::vector<int> partsOfFilter(F, 0);
-        for (int tap = 0; tap < h->nWeights; ++tap) {
-            const int  lane = tap / run, i = tap % run;
-            const bool last = tap + 1 == h->nWeights || (tap + 1) / run != lane || tapFilter[tap + 1] != tapFilter[tap];
-            meta[i * 32 + lane] = tapBin[tap] | (last ? 0x10000 : 0) | (last ? nPart << 20 : 0);
-            melW[i * 32 + lane] = h->fbWeights[tap];
-            if (last) {
-                ++nPart;
-                ++partsOfFilter[tapFilter[tap]];
+            if (lanes <= 32 && worst <= 4) {
+                tpl = cand;
+                break;
             }
         }
-        for (int f = 0; f < F; ++f) {
-            partOff[f + 1] = partOff[f] + partsOfFilter[f];
-            maxPart        = std::max(maxPart, partsOfFilter[f]);
+        if (!tpl)
+            h->fast = false;
+        h->fastTpl = tpl ? tpl : 32;
+        std::vector<float> melW((size_t)h->fastTpl * 32, 0.0f);
+        std::vector<int>   melBin(32, 257), pieceOf(32, 0), pcBin, pcLen, pcTap;
+        for (int f = 0; f < F && tpl; ++f) {
+            const int n = h->fbEnd[f] - h->fbStart[f], pcs = std::max(1, (n + tpl - 1) / tpl);
+            pieceOf[f] = (int)pcBin.size() | (pcs << 8);
+            for (int q = 0; q < pcs; ++q) {  // pieces of (almost) equal length, in bin order
+                const int a0 = (int)((long)n * q / pcs), a1 = (int)((long)n * (q + 1) / pcs);
+                pcBin.push_back(h->fbStart[f] + a0);
+                pcLen.push_back(a1 - a0);
+                pcTap.push_back(h->fbOff[f] + a0);
+            }
         }
-        for (int f = F; f < 32; ++f)
-            partOff[f + 1] = partOff[f];
+        // a lane may start reading up to (tpl - length) bins early (weight 0 there): pick the starts so that the
+        // 32 lanes hit 32 different banks (bipartite matching pieces -> residues mod 32; kept unshifted if none exists)
+        const int          nPc = (int)pcBin.size();
+        std::vector<int>   owner(32, -1), shift(nPc, 0);
+        std::function<bool(int, std::vector<char>&)> augment = [&](int i, std::vector<char>& seen) {
+            for (int sft = 0; sft <= tpl - pcLen[i] && sft <= pcBin[i]; ++sft) {
+                const int r = (pcBin[i] - sft) & 31;
+                if (seen[r])
+                    continue;
+                seen[r] = 1;
+                if (owner[r] < 0 || augment(owner[r], seen)) {
+                    owner[r] = i;
+                    return true;
+                }
+            }
+            return false;
+        };
+        bool perfect = nPc > 0;
+        for (int i = 0; i < nPc && perfect; ++i) {
+            std::vector<char> seen(32, 0);
+            perfect = augment(i, seen);
+        }
+        if (perfect)
+            for (int r = 0; r < 32; ++r)
+                if (owner[r] >= 0)
+                    shift[owner[r]] = (pcBin[owner[r]] - r) & 31;
+        for (int i = 0; i < nPc; ++i) {
+            melBin[i] = pcBin[i] - shift[i];
+            for (int k = 0; k < pcLen[i]; ++k)
+                melW[(size_t)(k + shift[i]) * 32 + i] = h->fbWeights[pcTap[i] + k];
+        }
+        if (perfect) {  // idle lanes read from the residues nobody uses
+            int lane = nPc;
+            for (int r = 0; r < 32 && lane < 32; ++r)
+                if (owner[r] < 0)
+                    melBin[lane++] = 257 + ((r - 257) & 31);
+        }
         std::vector<float> dctT((size_t)F * 32, 0.0f);
         for (int c = 0; c < K; ++c)
             for (int n = 0; n < F; ++n)
                 dctT[(size_t)n * 32 + c] = h->dct[(size_t)c * F + n];
-        if (nPart > 72)
-            h->fast = false;
-        t.oTwA     = put_f(twA);
-        t.oTwB     = put_f(twB);
-        t.oTws     = put_f(tws512);
-        t.oWin     = put_f(win);
-        t.oMelMeta = put_i(meta);
-        t.oMelW    = put_f(melW);
-        t.oPartOff = put_i(partOff);
-        t.oDctT    = put_f(dctT);
-        t.maxPart  = maxPart;
+        std::vector<float> keep;
+        keep.swap(b);  // b is a reference to h->blob: build the fast blob in it, then swap back
+        t.oTwA         = put_f(twA);
+        t.oTwB         = put_f(twB);
+        t.oMelW        = put_f(melW);
+        t.oMelBin      = put_i(melBin);
+        t.oPiece       = put_i(pieceOf);
+        t.oDctT        = put_f(dctT);
         align4();
+        t.stagedFloats = (int)b.size();
+        t.oTws         = put_f(tws512);
+        t.oWin         = put_f(win);
+        align4();
+        h->fastBlob.swap(b);
+        b.swap(keep);
     }
     return RB_OK;
 }
@@ -685,7 +730,8 @@ int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, in
     }
     if (h->fast) {
         const int grid = (int)std::min<size_t>(nTiles, (size_t)h->fastGrid);
-        mfcc_fft256_kernel<<<grid, kF256Threads, h->fastSmemBytes, s>>>(p, h->f256, h->fastSampleCap);
+        p.tables       = h->dFastTables.p;
+        h->fastKernel<<<grid, kF256Threads, h->fastSmemBytes, s>>>(p, h->f256, h->fastSampleCap);
     }
     else {
         const int grid = (int)std::min<size_t>(nTiles, (size_t)h->grid);
@@ -772,19 +818,29 @@ extern "C" int rb_frontend_create(const rb_frontend_cfg* cfg, rb_frontend** out)
     h->grid = h->dev.sm_count * occ;
     if (h->fast) {
         h->fastSampleCap = (int)rb::round_up((size_t)(kTileFrames - 1) * h->S + h->N + 16, 4);
-        h->fastSmemBytes = sizeof(float) * (rb::round_up(h->blob.size(), 4) + 2 * (size_t)h->fastSampleCap +
+        h->fastSmemBytes = sizeof(float) * (rb::round_up((size_t)h->f256.stagedFloats, 4) + (size_t)h->fastSampleCap +
                                             (size_t)kF256Warps * kWarpScratch);
-        if (h->fastSmemBytes > h->dev.smem_optin ||
-            cudaFuncSetAttribute(mfcc_fft256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)h->fastSmemBytes) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mfcc_fft256_kernel, kF256Threads,
-                                                          h->fastSmemBytes) != cudaSuccess ||
-            occ < 1) {
+        const bool nf20 = h->nFilters == 20;
+        switch (h->fastTpl) {
+            case 16: h->fastKernel = nf20 ? mfcc_fft256_kernel<20, 16> : mfcc_fft256_kernel<0, 16>; break;
+            case 24: h->fastKernel = nf20 ? mfcc_fft256_kernel<20, 24> : mfcc_fft256_kernel<0, 24>; break;
+            default: h->fastKernel = nf20 ? mfcc_fft256_kernel<20, 32> : mfcc_fft256_kernel<0, 32>; break;
+        }
+        bool ok = h->fastSmemBytes <= h->dev.smem_optin;
+        ok = ok && cudaFuncSetAttribute(h->fastKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)h->fastSmemBytes) == cudaSuccess;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->fastKernel, kF256Threads,
+                                                                 h->fastSmemBytes) == cudaSuccess;
+        if (!ok || occ < 1) {
             cudaGetLastError();
             h->fast = false;  // the generic kernel still fits
         }
         else {
             h->fastGrid = h->dev.sm_count * occ;
+            if (h->dFastTables.upload(h->fastBlob, h->stream) != RB_OK) {
+                rb::set_error("table upload failed");
+                return fail(RB_ERR_CUDA);
+            }
         }
     }
     if (h->dTables.upload(h->blob, h->stream) != RB_OK || cudaStreamSynchronize(h->stream) != cudaSuccess) {
