@@ -323,10 +323,13 @@ struct rb_frontend {
     size_t     fastSmemBytes = 0;
     // device buffers
     rb::DevBuf<float>   dTables, dSamples, dCep, dFeats, dDbgAmp, dDbgFbank;
-    rb::DevBuf<int64_t> dSampleOff, dFrameOff;
-    rb::DevBuf<Tile>    dTiles;
-    rb::PinnedBuf<int64_t> hOff;
-    rb::PinnedBuf<Tile>    hTiles;
+    static constexpr int kSlots = 4;
+    struct StageSlot {
+        rb::PinnedBuf<char> host;
+        rb::DevBuf<char>    dev;
+        cudaEvent_t         ev = nullptr;
+    } slots[kSlots];
+    int nextSlot = 0;
     // streaming state
     std::vector<float> pending;
     double             pendingStart = 0;
@@ -339,6 +342,11 @@ struct rb_frontend {
     long                 dbgFrames = 0;
 
     ~rb_frontend() {
+        for (StageSlot& sl : slots)
+            if (sl.ev) {
+                cudaEventSynchronize(sl.ev);
+                cudaEventDestroy(sl.ev);
+            }
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -646,55 +654,64 @@ void timestamps(const rb_frontend* h, long nSamples, double start0, long T, doub
     }
 }
 
+// One call = one staging slot: [sample offsets | frame offsets | tile table] built in pinned memory, sent with a
+// single H2D copy.  Slots form a ring guarded by events, so the call only enqueues work (no stream synchronise):
+// back-to-back calls keep the GPU queue full.
 int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, int nUtt, float* dFeats,
                cudaStream_t s, int64_t* totalFramesOut) {
-    // frame prefix sums + tile table
-    RB_CHECK(h->hOff.reserve((size_t)2 * (nUtt + 1)));
-    int64_t* sOff = h->hOff.p;
-    int64_t* fOff = h->hOff.p + (nUtt + 1);
+    size_t nTiles = 0;
+    {
+        int64_t acc = 0;
+        for (int u = 0; u < nUtt; ++u) {
+            RB_REQUIRE(offsets[u + 1] >= offsets[u], "sample offsets not monotone at utterance %d", u);
+            const long T = frames_for(h, (long)(offsets[u + 1] - offsets[u]));
+            acc += T;
+            nTiles += (size_t)(T + kTileFrames - 1) / kTileFrames;
+        }
+        if (totalFramesOut)
+            *totalFramesOut = acc;
+        if (acc == 0)
+            return RB_OK;
+    }
+    RB_REQUIRE(nTiles < (size_t)1 << 31, "too many frames in one call");
+    rb_frontend::StageSlot& slot = h->slots[h->nextSlot];
+    h->nextSlot                  = (h->nextSlot + 1) % rb_frontend::kSlots;
+    if (!slot.ev)
+        RB_CUDA(cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
+    else
+        RB_CUDA(cudaEventSynchronize(slot.ev));  // the call that used this slot last has finished with it
+    const size_t offBytes = sizeof(int64_t) * (size_t)(nUtt + 1);
+    const size_t bytes    = 2 * offBytes + sizeof(Tile) * nTiles;
+    RB_CHECK(slot.host.reserve(bytes));
+    RB_CHECK(slot.dev.reserve(bytes));
+    int64_t* sOff  = reinterpret_cast<int64_t*>(slot.host.p);
+    int64_t* fOff  = reinterpret_cast<int64_t*>(slot.host.p + offBytes);
+    Tile*    tiles = reinterpret_cast<Tile*>(slot.host.p + 2 * offBytes);
     sOff[0] = offsets[0];
     fOff[0] = 0;
-    size_t nTiles = 0;
+    size_t ti = 0;
     for (int u = 0; u < nUtt; ++u) {
-        RB_REQUIRE(offsets[u + 1] >= offsets[u], "sample offsets not monotone at utterance %d", u);
         sOff[u + 1]  = offsets[u + 1];
         const long T = frames_for(h, (long)(offsets[u + 1] - offsets[u]));
         fOff[u + 1]  = fOff[u] + T;
-        nTiles += (size_t)(T + kTileFrames - 1) / kTileFrames;
-    }
-    const int64_t total = fOff[nUtt];
-    if (totalFramesOut)
-        *totalFramesOut = total;
-    if (total == 0)
-        return RB_OK;
-    RB_REQUIRE(nTiles < (size_t)1 << 31, "too many frames in one call");
-    RB_CHECK(h->hTiles.reserve(nTiles));
-    size_t ti = 0;
-    for (int u = 0; u < nUtt; ++u) {
-        const long T = (long)(fOff[u + 1] - fOff[u]);
         for (long f0 = 0; f0 < T; f0 += kTileFrames) {
             Tile t;
             t.utt = u;
             t.f0  = (int)f0;
             t.nf  = (int)std::min<long>(kTileFrames, T - f0);
             t.pad = 0;
-            h->hTiles.p[ti++] = t;
+            tiles[ti++] = t;
         }
     }
-    // the previous call's tables must have been consumed before the pinned staging is rewritten
-    RB_CHECK(h->dSampleOff.reserve(nUtt + 1));
-    RB_CHECK(h->dFrameOff.reserve(nUtt + 1));
-    RB_CHECK(h->dTiles.reserve(nTiles));
+    const int64_t total = fOff[nUtt];
     RB_CHECK(h->dCep.reserve((size_t)total * h->cfg.n_cepstra));
-    RB_CUDA(cudaMemcpyAsync(h->dSampleOff.p, sOff, sizeof(int64_t) * (nUtt + 1), cudaMemcpyHostToDevice, s));
-    RB_CUDA(cudaMemcpyAsync(h->dFrameOff.p, fOff, sizeof(int64_t) * (nUtt + 1), cudaMemcpyHostToDevice, s));
-    RB_CUDA(cudaMemcpyAsync(h->dTiles.p, h->hTiles.p, sizeof(Tile) * nTiles, cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaMemcpyAsync(slot.dev.p, slot.host.p, bytes, cudaMemcpyHostToDevice, s));
 
     FeParams p;
     p.samples      = dSamples;
-    p.sampleOff    = h->dSampleOff.p;
-    p.frameOff     = h->dFrameOff.p;
-    p.tiles        = h->dTiles.p;
+    p.sampleOff    = reinterpret_cast<const int64_t*>(slot.dev.p);
+    p.frameOff     = reinterpret_cast<const int64_t*>(slot.dev.p + offBytes);
+    p.tiles        = reinterpret_cast<const Tile*>(slot.dev.p + 2 * offBytes);
     p.nTiles       = (int)nTiles;
     p.tables       = h->dTables.p;
     p.tableFloats  = (int)h->blob.size();
@@ -743,8 +760,7 @@ int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, in
         mfcc_derivative_kernel<<<grid2, 256, 0, s>>>(p);
         RB_LAUNCH_CHECK();
     }
-    // the pinned tile/offset staging is reused by the next call
-    RB_CUDA(cudaStreamSynchronize(s));
+    RB_CUDA(cudaEventRecord(slot.ev, s));
     return RB_OK;
 }
 
