@@ -948,19 +948,63 @@ extern "C" int rb_frontend_process(rb_frontend* h, const float* samples, const i
     RB_REQUIRE(samples || nS == 0, "NULL sample buffer");
     // slack so that the aligned bulk copies never leave the allocation
     RB_CHECK(h->dSamples.reserve((size_t)nS + 8));
-    if (nS)
-        RB_CUDA(cudaMemcpyAsync(h->dSamples.p, samples + base, (size_t)nS * 4, cudaMemcpyHostToDevice, h->stream));
-    std::vector<int64_t> rel(n_utt + 1);
+    std::vector<int64_t> rel(n_utt + 1), fo(n_utt + 1);
     for (int u = 0; u <= n_utt; ++u)
         rel[u] = offsets[u] - base;
-    const long total = rb_frontend_count_frames(h, rel.data(), n_utt, nullptr);
+    const long total = rb_frontend_count_frames(h, rel.data(), n_utt, fo.data());
     RB_CHECK(h->dFeats.reserve((size_t)total * h->featDim));
-    int64_t got = 0;
-    RB_CHECK(run_device(h, h->dSamples.p, rel.data(), n_utt, h->dFeats.p, h->stream, &got));
-    if (feats && total)
-        RB_CUDA(cudaMemcpyAsync(feats, h->dFeats.p, (size_t)total * h->featDim * 4, cudaMemcpyDeviceToHost,
-                                h->stream));
-    RB_CUDA(cudaStreamSynchronize(h->stream));
+    // slabs of whole utterances (~8 per call): H2D of slab i+1 overlaps the kernels of slab i and the D2H of i-1.
+    // Debug dumps index frames from 0, so a debug run is a single slab.
+    const long       target = h->debug ? total + 1 : std::max<long>(8192, (total + 7) / 8);
+    std::vector<int> cut(1, 0);
+    for (int u = 1; u <= n_utt; ++u)
+        if (u == n_utt || fo[u] - fo[cut.back()] >= target)
+            cut.push_back(u);
+    const int    nSlabs = (int)cut.size() - 1;
+    cudaStream_t sIn = nullptr, sOut = nullptr;
+    RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> evIn(nSlabs), evK(nSlabs);
+    for (int i = 0; i < nSlabs; ++i) {
+        cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming);
+    }
+    int rc = RB_OK;
+    for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
+        const int     u0 = cut[i], u1 = cut[i + 1];
+        const int64_t sA = rel[u0], sB = rel[u1], fA = fo[u0], fB = fo[u1];
+        if (sB > sA && cudaMemcpyAsync(h->dSamples.p + sA, samples + base + sA, (size_t)(sB - sA) * 4,
+                                       cudaMemcpyHostToDevice, sIn) != cudaSuccess)
+            rc = RB_ERR_CUDA;
+        cudaEventRecord(evIn[i], sIn);
+        cudaStreamWaitEvent(h->stream, evIn[i], 0);
+        if (rc == RB_OK)
+            rc = run_device(h, h->dSamples.p, rel.data() + u0, u1 - u0, h->dFeats.p + fA * h->featDim, h->stream,
+                            nullptr);
+        cudaEventRecord(evK[i], h->stream);
+        cudaStreamWaitEvent(sOut, evK[i], 0);
+        if (rc == RB_OK && feats && fB > fA &&
+            cudaMemcpyAsync(feats + fA * h->featDim, h->dFeats.p + fA * h->featDim, (size_t)(fB - fA) * h->featDim * 4,
+                            cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
+            rc = RB_ERR_CUDA;
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(sIn), e2 = cudaStreamSynchronize(h->stream),
+                      e3 = cudaStreamSynchronize(sOut);
+    for (int i = 0; i < nSlabs; ++i) {
+        cudaEventDestroy(evIn[i]);
+        cudaEventDestroy(evK[i]);
+    }
+    cudaStreamDestroy(sIn);
+    cudaStreamDestroy(sOut);
+    if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
+        rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != RB_OK)
+        return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        rb::set_error("front-end failed on the device: %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
     h->lastFrames = total;
     if (t_start || t_end) {
         long f = 0;

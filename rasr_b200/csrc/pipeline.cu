@@ -37,6 +37,9 @@ extern "C" int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* 
     return RB_OK;
 }
 
+// Host-pointer entry point: the utterances are cut into slabs (whole utterances, ~8 per call); H2D of slab i+1,
+// front-end + scoring of slab i and D2H of slab i-1 overlap on three streams.  PCIe is the end-to-end bound
+// (640 B of samples in, 1 KB of scores out per frame).
 extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samples, const int64_t* offsets, int n_utt,
                                  float* scores, float* feats) {
     RB_REQUIRE(fe && gmm && offsets && n_utt >= 0, "bad argument");
@@ -44,25 +47,77 @@ extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samp
         return RB_OK;
     const int64_t base = offsets[0], nS = offsets[n_utt] - base;
     RB_REQUIRE(nS >= 0 && (samples || nS == 0), "bad sample buffer");
-    std::vector<int64_t> rel(n_utt + 1);
+    std::vector<int64_t> rel(n_utt + 1), fo(n_utt + 1);
     for (int u = 0; u <= n_utt; ++u)
         rel[u] = offsets[u] - base;
-    const long T = rb_frontend_count_frames(fe, rel.data(), n_utt, nullptr);
+    const long T = rb_frontend_count_frames(fe, rel.data(), n_utt, fo.data());
     if (T <= 0)
         return T == 0 ? RB_OK : RB_ERR_INVALID;
     RB_REQUIRE(scores != nullptr, "NULL score buffer");
     RB_CUDA(cudaSetDevice(rb_frontend_device(fe).ordinal));
     Scratch&     sc = scratch_for(fe);
     const int    D = rb_frontend_feat_dim(fe), M = rb_gmm_n_mixtures(gmm);
-    cudaStream_t s = rb_frontend_stream(fe);
+    cudaStream_t sK = rb_frontend_stream(fe);
     RB_CHECK(sc.samples.reserve((size_t)nS + 8));
     RB_CHECK(sc.feats.reserve((size_t)T * D));
     RB_CHECK(sc.scores.reserve((size_t)T * M));
-    RB_CUDA(cudaMemcpyAsync(sc.samples.p, samples + base, (size_t)nS * 4, cudaMemcpyHostToDevice, s));
-    RB_CHECK(rb_pipeline_score_dev(fe, gmm, sc.samples.p, rel.data(), n_utt, sc.feats.p, sc.scores.p, s));
-    RB_CUDA(cudaMemcpyAsync(scores, sc.scores.p, (size_t)T * M * 4, cudaMemcpyDeviceToHost, s));
-    if (feats)
-        RB_CUDA(cudaMemcpyAsync(feats, sc.feats.p, (size_t)T * D * 4, cudaMemcpyDeviceToHost, s));
-    RB_CUDA(cudaStreamSynchronize(s));
+
+    // slab boundaries (utterance indices): about T/8 frames each, at least 8192
+    const long       target = std::max<long>(8192, (T + 7) / 8);
+    std::vector<int> cut(1, 0);
+    for (int u = 1; u <= n_utt; ++u)
+        if (u == n_utt || fo[u] - fo[cut.back()] >= target)
+            cut.push_back(u);
+    const int    nSlabs = (int)cut.size() - 1;
+    cudaStream_t sIn = nullptr, sOut = nullptr;
+    RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> evIn(nSlabs), evK(nSlabs);
+    for (int i = 0; i < nSlabs; ++i) {
+        cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming);
+    }
+    int rc = RB_OK;
+    for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
+        const int     u0 = cut[i], u1 = cut[i + 1];
+        // the aligned bulk copies of the front-end may read up to 3 samples before a slab's first utterance:
+        // they are either the previous slab's (already ordered on sK) or padding, and never used
+        const int64_t sA = rel[u0], sB = rel[u1];
+        const int64_t fA = fo[u0], fB = fo[u1];
+        if (sB > sA && cudaMemcpyAsync(sc.samples.p + sA, samples + base + sA, (size_t)(sB - sA) * 4,
+                                       cudaMemcpyHostToDevice, sIn) != cudaSuccess)
+            rc = RB_ERR_CUDA;
+        cudaEventRecord(evIn[i], sIn);
+        cudaStreamWaitEvent(sK, evIn[i], 0);
+        if (rc == RB_OK && fB > fA)
+            rc = rb_pipeline_score_dev(fe, gmm, sc.samples.p, rel.data() + u0, u1 - u0, sc.feats.p + fA * D,
+                                       sc.scores.p + fA * M, sK);
+        cudaEventRecord(evK[i], sK);
+        cudaStreamWaitEvent(sOut, evK[i], 0);
+        if (rc == RB_OK && fB > fA) {
+            if (cudaMemcpyAsync(scores + fA * M, sc.scores.p + fA * M, (size_t)(fB - fA) * M * 4,
+                                cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
+                rc = RB_ERR_CUDA;
+            if (feats && cudaMemcpyAsync(feats + fA * D, sc.feats.p + fA * D, (size_t)(fB - fA) * D * 4,
+                                         cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
+                rc = RB_ERR_CUDA;
+        }
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(sIn), e2 = cudaStreamSynchronize(sK), e3 = cudaStreamSynchronize(sOut);
+    for (int i = 0; i < nSlabs; ++i) {
+        cudaEventDestroy(evIn[i]);
+        cudaEventDestroy(evK[i]);
+    }
+    cudaStreamDestroy(sIn);
+    cudaStreamDestroy(sOut);
+    if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
+        rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != RB_OK)
+        return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        rb::set_error("pipeline failed on the device: %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
     return RB_OK;
 }

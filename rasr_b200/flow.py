@@ -72,15 +72,17 @@ class FrontEnd:
             raise capi.RasrB200Error(-1, "bad offsets")
         return fo
 
-    def process(self, samples, offsets=None, timestamps=True, stages=False):
-        """Batch of independent segments (host buffers).  Returns dict(feats, frame_offsets, t_start, t_end)."""
-        samples = np.ascontiguousarray(samples, np.float32)
+    def process(self, samples, offsets=None, timestamps=True, stages=False, out=None):
+        """Batch of independent segments (host buffers: numpy, or pinned torch CPU tensors through their
+        data_ptr; `out` receives the features).  Returns dict(feats, frame_offsets, t_start, t_end)."""
+        if isinstance(samples, np.ndarray) or not hasattr(samples, "data_ptr"):
+            samples = np.ascontiguousarray(samples, np.float32)
         if offsets is None:
             offsets = np.array([0, samples.size], np.int64)
         offsets = np.ascontiguousarray(offsets, np.int64)
         fo = self.count_frames(offsets)
         T = int(fo[-1])
-        feats = np.zeros((T, self.feat_dim), np.float32)
+        feats = out if out is not None else np.zeros((T, self.feat_dim), np.float32)
         ts = np.zeros(T, np.float64) if timestamps else None
         te = np.zeros(T, np.float64) if timestamps else None
         L = capi.lib()

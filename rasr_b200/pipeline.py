@@ -10,13 +10,15 @@ import numpy as np
 from . import capi
 
 
-def score_utterances(frontend, gmm, samples, offsets, want_feats=False):
-    """Host buffers in, scores [total_frames x n_mixtures] out; features stay on the device."""
-    samples = np.ascontiguousarray(samples, np.float32)
+def score_utterances(frontend, gmm, samples, offsets, want_feats=False, out=None):
+    """Host buffers in (numpy, or pinned torch CPU tensors), scores [total_frames x n_mixtures] out (`out` if
+    given); features stay on the device."""
+    if isinstance(samples, np.ndarray) or not hasattr(samples, "data_ptr"):
+        samples = np.ascontiguousarray(samples, np.float32)
     offsets = np.ascontiguousarray(offsets, np.int64)
     fo = frontend.count_frames(offsets)
     T = int(fo[-1])
-    scores = np.zeros((T, gmm.n_mixtures), np.float32)
+    scores = out if out is not None else np.zeros((T, gmm.n_mixtures), np.float32)
     feats = np.zeros((T, frontend.feat_dim), np.float32) if want_feats else None
     capi.check(capi.lib().rb_pipeline_score(frontend.handle, gmm.handle, capi.ptr(samples), capi.ptr(offsets),
                                             offsets.size - 1, capi.ptr(scores), capi.ptr(feats)))
