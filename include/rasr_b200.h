@@ -161,7 +161,11 @@ typedef enum {
     RB_GMM_DIAG_SUM = 2,
     /* tensor-core formulation of RB_GMM_BATCH_FLOAT (split-precision GEMM |x|^2 - 2 x.mu + |mu|^2 on
      * tcgen05, f32 accumulate); scores within 1e-4 relative of the reference, not bit-identical */
-    RB_GMM_BATCH_TENSOR = 3
+    RB_GMM_BATCH_TENSOR = 3,
+    /* Mm::BatchIntFeatureScorer / BatchUnrolledIntFeatureScorer ("batch-diagonal-maximum-int" / "-fast",
+     * src/Mm/BatchFeatureScorer.cc:321-510, 581-650): means and features quantised to u8, s32 distances;
+     * integer arithmetic on the tensor cores (IMMA), bit-identical scores */
+    RB_GMM_BATCH_INT = 4
 } rb_gmm_mode;
 
 /* contraction: 1 = fused multiply-add where the reference's default build (gcc -O2 -march=native,

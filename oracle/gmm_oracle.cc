@@ -259,7 +259,162 @@ struct DiagonalScorer {
     }
 };
 
+/* ------------------------------------------------------------------ Mm::BatchIntFeatureScorer
+ * ("batch-diagonal-maximum-int"; BatchUnrolledIntFeatureScorer "batch-diagonal-maximum-fast" computes the same
+ * numbers with the loop over three 16-byte blocks unrolled, src/Mm/BatchFeatureScorer.cc:581-650)
+ * quantize src/Mm/Utilities.hh:190-202, quantizationScale src/Mm/BatchFeatureScorer.cc:355-373, init :375-416,
+ * setFeature :418-424, addDistance / horizontalAdd :427-456, fillScoreCacheTpl :458-510.
+ * Integer arithmetic is exact, so only the f32/f64 mixing of init() and the final division matter. */
+struct BatchInt {
+    unsigned                   dim, padded, nMix, nDens;
+    std::vector<unsigned>      offsets;
+    std::vector<float>         variance; /* isd * scale, zero padded */
+    std::vector<int32_t>       consts;
+    uint8_t*                   means;
+    float                      scale_;
+
+    BatchInt() : means(0), scale_(1) {}
+    ~BatchInt() { free(means); }
+
+    static uint8_t quantize(float x) {
+        /* clip((int)round(x) + offset), offset = (int)round((255 + 0 + 1) / 2) = 128 */
+        int v = (int)roundf(x) + 128;
+        return (uint8_t)std::min(std::max(v, 0), 255);
+    }
+
+    int init(const orc_mixture_set& ms) {
+        if (ms.n_covariances != 1)
+            return -2;
+        dim    = ms.dim;
+        padded = ((dim + 15) / 16) * 16;
+        nMix   = ms.n_mixtures;
+        offsets.assign(nMix + 1, 0);
+        nDens = 0;
+        for (unsigned m = 0; m < nMix; ++m) {
+            offsets[m] = nDens;
+            nDens += ms.mix_offsets[m + 1] - ms.mix_offsets[m];
+        }
+        offsets[nMix] = nDens;
+        variance.assign(padded, 0.0f);
+        for (unsigned d = 0; d < dim; ++d)
+            variance[d] = inverseSquareRoot(ms.variances[d]);
+        /* quantizationScale(): range of mean * isd over ALL densities of the set */
+        float minMean = FLT_MAX, maxMean = -FLT_MAX;
+        for (unsigned i = 0; i < ms.n_densities; ++i) {
+            const float* mu = ms.means + (size_t)ms.dens_mean[i] * dim;
+            for (unsigned d = 0; d < dim; ++d) {
+                float divided = mu[d] * variance[d];
+                minMean       = std::min(minMean, divided);
+                maxMean       = std::max(maxMean, divided);
+            }
+        }
+        const int   quantizedIntervalSize = 255 - 0;
+        const float intervalSize          = 2 * std::max(std::fabs(minMean), std::fabs(maxMean));
+        const float scale                 = static_cast<float>(quantizedIntervalSize) / (1.25 * intervalSize);
+        const float scaleSquared          = scale * scale;
+        scale_                            = 2.0 * scaleSquared;
+        for (unsigned d = 0; d < padded; ++d)
+            variance[d] = variance[d] * scale;
+        const float logNorm       = gaussLogNormFactor(ms.variances, dim); /* Score logNormalizationFactor_ */
+        const float logNormFactor = logNorm * scaleSquared;
+        if (posix_memalign((void**)&means, 16, std::max<size_t>((size_t)nDens * padded, 16)) != 0)
+            return -4;
+        std::memset(means, 0, std::max<size_t>((size_t)nDens * padded, 16));
+        consts.assign(nDens, 0);
+        for (unsigned m = 0; m < nMix; ++m) {
+            uint8_t* mean = means + (size_t)offsets[m] * padded;
+            int32_t* c    = consts.data() + offsets[m];
+            for (unsigned e = ms.mix_offsets[m]; e < ms.mix_offsets[m + 1]; ++e) {
+                unsigned dns = ms.mix_density[e];
+                if (ms.dens_cov[dns] != 0)
+                    return -3;
+                const float* mu = ms.means + (size_t)ms.dens_mean[dns] * dim;
+                for (unsigned d = 0; d < dim; ++d)
+                    mean[d] = quantize(mu[d] * variance[d]);
+                mean += padded;
+                *c = static_cast<int32_t>(logNormFactor - scale_ * ms.mix_log_weight[e]);
+                ++c;
+            }
+        }
+        return 0;
+    }
+
+    void scoreFrames(const float* feats, long t0, long t1, float* scores) const {
+        uint8_t* x = 0;
+        if (posix_memalign((void**)&x, 16, padded) != 0)
+            return;
+        for (long t = t0; t < t1; ++t) {
+            std::memset(x, 0, padded);
+            const float* f = feats + (size_t)t * dim;
+            for (unsigned d = 0; d < dim; ++d)
+                x[d] = quantize(f[d] * variance[d]);
+            for (unsigned m = 0; m < nMix; ++m) {
+                int32_t best = 2147483647;
+                for (unsigned dns = offsets[m]; dns < offsets[m + 1]; ++dns) {
+                    const uint8_t* mean = means + (size_t)dns * padded;
+                    __m128i        sum  = _mm_setzero_si128();
+                    for (unsigned d = 0; d < padded; d += 16) {
+                        __m128i mv = _mm_load_si128((const __m128i*)(mean + d));
+                        __m128i xv = _mm_load_si128((const __m128i*)(x + d));
+                        /* |m - x| per byte, widened to 16 bit, squared and pair-summed to 32 bit */
+                        __m128i ad = _mm_or_si128(_mm_subs_epu8(mv, xv), _mm_subs_epu8(xv, mv));
+                        __m128i hi = _mm_unpackhi_epi8(ad, _mm_setzero_si128());
+                        __m128i lo = _mm_unpacklo_epi8(ad, _mm_setzero_si128());
+                        sum        = _mm_add_epi32(sum, _mm_madd_epi16(hi, hi));
+                        sum        = _mm_add_epi32(sum, _mm_madd_epi16(lo, lo));
+                    }
+                    __m128i s   = _mm_add_epi32(_mm_shuffle_epi32(sum, _MM_SHUFFLE(3, 2, 3, 2)),
+                                                _mm_shuffle_epi32(sum, _MM_SHUFFLE(1, 0, 1, 0)));
+                    int32_t tmp = _mm_cvtsi128_si32(_mm_add_epi32(s, _mm_shuffle_epi32(s, _MM_SHUFFLE(2, 3, 0, 1))));
+                    tmp += consts[dns];
+                    if (tmp < best)
+                        best = tmp;
+                }
+                scores[(size_t)t * nMix + m] = static_cast<float>(best) / scale_;
+            }
+        }
+        free(x);
+    }
+};
+
 }  // namespace
+
+extern "C" int orc_gmm_batch_int(const orc_mixture_set* ms, const float* feats, long T, float* scores, int n_threads) {
+    BatchInt s;
+    int      rc = s.init(*ms);
+    if (rc)
+        return rc;
+    if (n_threads < 1)
+        n_threads = 1;
+    std::vector<std::thread> pool;
+    for (int i = 0; i < n_threads; ++i) {
+        long a = T * i / n_threads, b = T * (i + 1) / n_threads;
+        pool.emplace_back([&s, feats, scores, a, b]() { s.scoreFrames(feats, a, b, scores); });
+    }
+    for (auto& th : pool)
+        th.join();
+    return 0;
+}
+
+/* the quantised model as the scorer holds it (for known-answer tests): means [n_dens * padded], consts [n_dens] */
+extern "C" int orc_gmm_batch_int_model(const orc_mixture_set* ms, uint8_t* means, int32_t* consts, float* variance,
+                                       float* scale, int* padded) {
+    BatchInt s;
+    int      rc = s.init(*ms);
+    if (rc)
+        return rc;
+    if (means)
+        std::memcpy(means, s.means, (size_t)s.nDens * s.padded);
+    if (consts)
+        std::memcpy(consts, s.consts.data(), sizeof(int32_t) * s.nDens);
+    if (variance)
+        std::memcpy(variance, s.variance.data(), sizeof(float) * s.padded);
+    if (scale)
+        *scale = s.scale_;
+    if (padded)
+        *padded = (int)s.padded;
+    return 0;
+}
 
 extern "C" int orc_gmm_batch_float(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma) {
     BatchFloat s;

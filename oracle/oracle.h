@@ -100,6 +100,10 @@ int orc_gmm_diag_sum(const orc_mixture_set* ms, float mixture_weight_scale, floa
                      const float* feats, long T, float* scores, uint32_t* best, int use_fma);
 /* multi-threaded driver over frame slices (the reference's only parallel mode is independent
  * processes over corpus partitions; threads over frame ranges are the same thing for a dense scorer) */
+/* Mm::BatchIntFeatureScorer (u8-quantised means / features, s32 distances; src/Mm/BatchFeatureScorer.cc:321-510) */
+int orc_gmm_batch_int(const orc_mixture_set* ms, const float* feats, long T, float* scores, int n_threads);
+int orc_gmm_batch_int_model(const orc_mixture_set* ms, uint8_t* means, int32_t* consts, float* variance, float* scale,
+                            int* padded);
 int orc_gmm_batch_float_mt(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma,
                            int n_threads);
 

@@ -184,6 +184,33 @@ def gmm_batch_float(ms, feats, use_fma=True, threads=1):
     return scores
 
 
+def gmm_batch_int(ms, feats, threads=1):
+    """Mm::BatchIntFeatureScorer ("batch-diagonal-maximum-int"): dense scores [T x nMix]."""
+    feats = np.ascontiguousarray(feats, np.float32)
+    T = feats.shape[0]
+    scores = np.zeros((T, ms.n_mixtures), np.float32)
+    rc = lib().orc_gmm_batch_int(C.byref(ms.c), _p(feats, C.c_float), C.c_long(T), _p(scores, C.c_float), int(threads))
+    if rc:
+        raise RuntimeError("orc_gmm_batch_int failed: %d" % rc)
+    return scores
+
+
+def gmm_batch_int_model(ms):
+    """The quantised model: dict(means u8 [nDens x padded], consts s32 [nDens], variance f32 [padded], scale)."""
+    n_dens = int(ms.a["mix_offsets"][-1])
+    padded = (ms.dim + 15) // 16 * 16
+    means = np.zeros((n_dens, padded), np.uint8)
+    consts = np.zeros(n_dens, np.int32)
+    variance = np.zeros(padded, np.float32)
+    scale = C.c_float()
+    pad = C.c_int()
+    rc = lib().orc_gmm_batch_int_model(C.byref(ms.c), _p(means, C.c_uint8), _p(consts, C.c_int32),
+                                       _p(variance, C.c_float), C.byref(scale), C.byref(pad))
+    if rc:
+        raise RuntimeError("orc_gmm_batch_int_model failed: %d" % rc)
+    return dict(means=means, consts=consts, variance=variance, scale=scale.value, padded=pad.value)
+
+
 def _gmm_diag(fn, ms, feats, mixture_weight_scale, gaussian_scale, use_fma):
     feats = np.ascontiguousarray(feats, np.float32)
     T = feats.shape[0]

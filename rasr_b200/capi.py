@@ -16,7 +16,7 @@ RB_OK = 0
 STATUS = {0: "RB_OK", -1: "RB_ERR_INVALID", -2: "RB_ERR_NO_DEVICE", -3: "RB_ERR_CUDA", -4: "RB_ERR_UNSUPPORTED",
           -5: "RB_ERR_STATE", -6: "RB_ERR_NOMEM"}
 
-GMM_BATCH_FLOAT, GMM_DIAG_MAX, GMM_DIAG_SUM, GMM_BATCH_TENSOR = 0, 1, 2, 3
+GMM_BATCH_FLOAT, GMM_DIAG_MAX, GMM_DIAG_SUM, GMM_BATCH_TENSOR, GMM_BATCH_INT = 0, 1, 2, 3, 4
 ACT = {"linear": 0, "sigmoid": 1, "relu": 2, "rectified": 2, "softmax": 3, "tanh": 4}
 NN_F32, NN_BF16 = 0, 1
 

@@ -498,6 +498,11 @@ GmmKernel diag_kernel_for(int nq, bool fuse, bool sum) {
 // host side
 // ==========================================================================================
 
+struct rb_gmm_int;  // gmm_int.cu
+int  rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_int** out);
+void rb_gmm_int_destroy(rb_gmm_int* h);
+int  rb_gmm_int_score(rb_gmm_int* h, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
+
 struct rb_gmm_tensor;  // gmm_tensor.cu
 int  rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream,
                           rb_gmm_tensor** out);
@@ -534,10 +539,13 @@ struct rb_gmm {
     rb::DevBuf<uint32_t> dBest;
     rb::PinnedBuf<float> hStage;
     rb_gmm_tensor*       tensor = nullptr;
+    rb_gmm_int*          quantised = nullptr;
 
     ~rb_gmm() {
         if (tensor)
             rb_gmm_tensor_destroy(tensor);
+        if (quantised)
+            rb_gmm_int_destroy(quantised);
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -785,7 +793,7 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
     RB_REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
     RB_CHECK(validate(ms));
-    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_BATCH_TENSOR, "unknown gmm mode %d", mode);
+    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_BATCH_INT, "unknown gmm mode %d", mode);
     rb_gmm* h = new (std::nothrow) rb_gmm();
     if (!h) {
         rb::set_error("out of host memory");
@@ -809,6 +817,13 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         return fail(RB_ERR_CUDA);
     }
     std::vector<float> rows, isd;
+    if (mode == RB_GMM_BATCH_INT) {
+        rc = rb_gmm_int_create(ms, h->dev, h->stream, &h->quantised);
+        if (rc != RB_OK)
+            return fail(rc);
+        *out = h;
+        return RB_OK;
+    }
     if (mode == RB_GMM_BATCH_FLOAT || mode == RB_GMM_BATCH_TENSOR) {
         if (ms->dim > 64) {
             rb::set_error("batch scorer supports feature dimension <= 64 (got %u)", ms->dim);
@@ -919,6 +934,10 @@ extern "C" int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* 
         RB_REQUIRE(d_best == nullptr, "best-density output is not available in tensor mode");
         return rb_gmm_tensor_score(h->tensor, d_feats, T, d_scores, s);
     }
+    if (h->mode == RB_GMM_BATCH_INT) {
+        RB_REQUIRE(d_best == nullptr, "Mm::BatchIntFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
+        return rb_gmm_int_score(h->quantised, d_feats, T, d_scores, s);
+    }
     if (h->mode == RB_GMM_BATCH_FLOAT)
         RB_REQUIRE(d_best == nullptr, "Mm::BatchFloatFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
     return launch_simt(h, d_feats, T, d_scores, d_best, s);
@@ -932,7 +951,7 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     if (T == 0)
         return RB_OK;
     RB_REQUIRE(feats && scores, "NULL host buffer");
-    if (h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_BATCH_TENSOR)
+    if (h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_BATCH_TENSOR || h->mode == RB_GMM_BATCH_INT)
         RB_REQUIRE(best_density == nullptr, "this scorer mode does not report densities; use RB_GMM_DIAG_MAX");
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
     const size_t D = h->dim, M = h->nMix;

@@ -49,7 +49,8 @@ class GmmScorer:
     """RAII wrapper of rb_gmm_*: dense scoring of frames against every mixture."""
 
     MODES = {"batch-float": capi.GMM_BATCH_FLOAT, "diagonal-maximum": capi.GMM_DIAG_MAX,
-             "diagonal-sum": capi.GMM_DIAG_SUM, "batch-tensor": capi.GMM_BATCH_TENSOR}
+             "diagonal-sum": capi.GMM_DIAG_SUM, "batch-tensor": capi.GMM_BATCH_TENSOR,
+             "batch-int": capi.GMM_BATCH_INT}
 
     def __init__(self, mixture_set, mode="batch-float", mixture_weight_scale=1.0, gaussian_scale=1.0,
                  contraction=True, device=0):

@@ -1,0 +1,47 @@
+// Microbenchmark: legacy warp-level mma.sync rates on sm_100a (accumulators in registers), to decide whether an
+// epilogue-heavy small-K scorer is better off there than on tcgen05 (whose TMEM read-back is 64 B/clk/SM).
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+template<int MODE> __global__ void k(int* out, long long* cyc, int iters) {
+  int acc[8][4]; float facc[8][4];
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 4; j++) { acc[i][j] = 0; facc[i][j] = 0.f; }
+  uint32_t a0 = threadIdx.x * 0x01010101u, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 ^ 0x55, b1 = a0 ^ 0xaa;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (MODE == 0)
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(acc[i][0]), "+r"(acc[i][1]), "+r"(acc[i][2]), "+r"(acc[i][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0 + i), "r"(b1));
+      else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(facc[i][0]), "+f"(facc[i][1]), "+f"(facc[i][2]), "+f"(facc[i][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0 + i), "r"(b1));
+    }
+  }
+  long long t1 = clock64();
+  int s = 0; for (int i = 0; i < 8; i++) for (int j = 0; j < 4; j++) s += acc[i][j] + (int)facc[i][j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+template<int MODE> void run(const char* name, int threads, double mac_per_instr) {
+  int* out; long long* cyc; cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
+  const int iters = 20000;
+  k<MODE><<<148, threads>>>(out, cyc, iters); cudaDeviceSynchronize();
+  k<MODE><<<148, threads>>>(out, cyc, iters); cudaDeviceSynchronize();
+  long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  double c = 0; for (int i = 0; i < 148; i++) c += h[i]; c /= 148;
+  double instr = 8.0 * iters * (threads / 32);
+  printf("%-22s warps/SM %2d  MAC/clk/SM %.0f  (instr/clk/SM %.3f)  chip @1.965GHz: %.0f TOPS\n", name, threads / 32,
+         instr * mac_per_instr / c, instr / c, instr * mac_per_instr / c * 2 * 148 * 1.965e9 / 1e12);
+  cudaFree(out); cudaFree(cyc);
+}
+int main() {
+  for (int th : {128, 256, 512}) {
+    run<0>("mma.sync u8 m16n8k32", th, 16 * 8 * 32);
+    run<1>("mma.sync f16 m16n8k16", th, 16 * 8 * 16);
+  }
+  return 0;
+}

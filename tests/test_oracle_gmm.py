@@ -122,3 +122,99 @@ def test_golden_fixture(oracle):
     assert np.array_equal(mx, g["max"]) and np.array_equal(mb, g["max_best"])
     sm, sb = oracle.gmm_diag_sum(ms, f)
     assert np.array_equal(sm, g["sum"]) and np.array_equal(sb, g["sum_best"])
+
+
+# ---------------------------------------------------------------- Mm::BatchIntFeatureScorer (a12)
+
+def int_model_numpy(msd):
+    """Independent restatement of BatchIntFeatureScorer::init / quantizationScale in numpy, keeping the f32 / f64
+    mixing of src/Mm/BatchFeatureScorer.cc:355-416 (every product below is a single rounding)."""
+    f32 = np.float32
+    dim = msd["dim"]
+    isd = (f32(1) / np.sqrt(msd["variances"][0].astype(np.float32)).astype(np.float32)).astype(np.float32)
+    divided = (msd["means"][msd["dens_mean"]].astype(np.float32) * isd[None]).astype(np.float32)
+    interval = f32(2) * max(abs(f32(divided.min())), abs(f32(divided.max())))
+    scale = f32(np.float64(f32(255)) / (1.25 * np.float64(interval)))
+    scale_sq = f32(scale * scale)
+    scale2 = f32(2.0 * np.float64(scale_sq))
+    variance = (isd * scale).astype(np.float32)
+    lognorm = f32(dim * np.log(2 * np.pi) + np.log(np.abs(msd["variances"][0].astype(np.float64))).sum())
+    lognorm_factor = f32(lognorm * scale_sq)
+
+    def quant(v):
+        r = np.where(v >= 0, np.floor(v.astype(np.float64) + 0.5), -np.floor(-v.astype(np.float64) + 0.5))  # roundf
+        return np.clip(r.astype(np.int64) + 128, 0, 255).astype(np.uint8)
+
+    d = msd["mix_density"]
+    means = quant((msd["means"][msd["dens_mean"][d]].astype(np.float32) * variance[None]).astype(np.float32))
+    consts = np.trunc(np.float64(lognorm_factor) - np.float64(scale2) * msd["mix_log_weight"]).astype(np.int32)
+    return dict(means=means, consts=consts, variance=variance, scale=scale2, quant=quant)
+
+
+def int_scores_numpy(msd, feats):
+    m = int_model_numpy(msd)
+    xq = m["quant"]((feats.astype(np.float32) * m["variance"][None]).astype(np.float32)).astype(np.int64)
+    nm = msd["mix_offsets"].size - 1
+    out = np.zeros((feats.shape[0], nm), np.float32)
+    for k in range(nm):
+        e = slice(msd["mix_offsets"][k], msd["mix_offsets"][k + 1])
+        if e.start == e.stop:
+            out[:, k] = np.float32(2147483647) / np.float32(m["scale"])
+            continue
+        dist = ((xq[:, None, :] - m["means"][e].astype(np.int64)[None]) ** 2).sum(2) + m["consts"][e][None]
+        out[:, k] = dist.min(1).astype(np.int32).astype(np.float32) / np.float32(m["scale"])
+    return out
+
+
+@pytest.mark.parametrize("dim", [39, 16, 7, 48])
+def test_batch_int_matches_numpy_restatement(oracle, dim):
+    msd = synth.mixture_set(dim=dim, n_mixtures=24, densities_per_mixture=16, seed=11)
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(200, dim, seed=3)
+    model = oracle.gmm_batch_int_model(ms)
+    ref = int_model_numpy(msd)
+    assert model["padded"] == (dim + 15) // 16 * 16
+    assert model["scale"] == ref["scale"]
+    assert np.array_equal(model["variance"][:dim], ref["variance"])
+    assert np.array_equal(model["means"][:, :dim], ref["means"]) and not model["means"][:, dim:].any()
+    assert np.array_equal(model["consts"], ref["consts"])
+    got = oracle.gmm_batch_int(ms, f)
+    assert np.array_equal(got, int_scores_numpy(msd, f))  # integer path: bit-exact
+    assert np.array_equal(got, oracle.gmm_batch_int(ms, f, threads=4))
+
+
+def test_batch_int_quantisation_kat(oracle):
+    """quantize() = clip(round-half-away(x) + 128, 0, 255) (src/Mm/Utilities.hh:190-202): one density at the
+    origin, unit variance => scale = 255 / (1.25 * 2 * max|mu|); features far away clip at 0 / 255."""
+    D = 4
+    msd = dict(dim=D, mix_offsets=[0, 1], mix_density=[0], mix_log_weight=[0.0], dens_mean=[0], dens_cov=[0],
+               means=np.array([[2.0, -2.0, 0.5, 0.0]], np.float32), variances=np.ones((1, D), np.float32))
+    ms = oracle.MixtureSet(**msd)
+    m = oracle.gmm_batch_int_model(ms)
+    scale = np.float32(255.0 / (1.25 * 4.0))                       # 51
+    assert m["scale"] == np.float32(2.0 * scale * scale)
+    assert list(m["means"][0, :D]) == [230, 26, 154, 128]           # round(2*51)+128, round(-102)+128, round(25.5)+128
+    x = np.array([[100.0, -100.0, 0.0, 0.0]], np.float32)           # clips to 255 / 0
+    got = oracle.gmm_batch_int(ms, x)[0, 0]
+    dist = (255 - 230) ** 2 + (0 - 26) ** 2 + (128 - 154) ** 2 + 0
+    c = int(np.trunc(np.float64(np.float32(np.float32(D * np.log(2 * np.pi)) * np.float32(scale * scale)))))
+    assert got == np.float32(dist + c) / m["scale"]
+
+
+def test_batch_int_close_to_float_scorer(oracle):
+    """The int scorer approximates the float one: same argmin mixtures mostly, scores within quantisation noise."""
+    msd = synth.mixture_set(dim=39, n_mixtures=32, densities_per_mixture=16, seed=5)
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(300, 39, seed=9)
+    a, b = oracle.gmm_batch_int(ms, f), oracle.gmm_batch_float(ms, f)
+    assert np.median(np.abs(a - b) / b) < 0.02
+
+
+def test_batch_int_ragged_and_empty(oracle):
+    msd = synth.mixture_set(dim=39, n_mixtures=5, densities_per_mixture=3, seed=2)
+    msd["mix_offsets"] = np.array([0, 1, 1, 6, 7, 15], np.uint32)  # sizes 1, 0, 5, 1, 8
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(50, 39, seed=4)
+    got = oracle.gmm_batch_int(ms, f)
+    assert np.array_equal(got, int_scores_numpy(msd, f))
+    assert np.all(got[:, 1] == np.float32(2147483647) / np.float32(oracle.gmm_batch_int_model(ms)["scale"]))
