@@ -99,11 +99,28 @@ __device__ __forceinline__ int min3(int a, int b, int c) {
     return __vimin3_s32(a, b, c);
 }
 
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&b)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ int2 lds_int2(uint32_t addr) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_int(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p) {
     constexpr int CHUNK = kChunkTiles * kTileBytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* buf = smem_raw;
-    uint64_t*      bar = reinterpret_cast<uint64_t*>(smem_raw + kStages * CHUNK);
+    unsigned char* buf  = smem_raw;
+    const uint32_t sbuf = smem_u32(smem_raw);
+    uint64_t*      bar  = reinterpret_cast<uint64_t*>(smem_raw + kStages * CHUNK);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
@@ -116,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p)
 
     // ldmatrix.x4 row addresses: lane i -> row (i & 7) of the 16-byte k-chunk (i >> 3) of the tile
     const uint32_t ldsmOff = (uint32_t)((lane & 7) * kRowBytes + (lane >> 3) * 16);
+    const uint32_t ccOff   = (uint32_t)(8 * kRowBytes + q * 8);  // c + |m|^2 of columns 2q, 2q+1
     // after the quad butterfly this lane owns the two rows  mtOwn * 16 + {0, 8} + g  of the warp's 64 frames
     const int mtOwn = 2 * (q & 1) + (q >> 1);
 
@@ -127,7 +145,6 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p)
         const int  grp   = item / p.nFrameBlocks;
         const int  fb    = item - grp * p.nFrameBlocks;
         const int  tile0 = p.grpTile[grp], tile1 = p.grpTile[grp + 1];
-        int        mix   = p.grpMix[grp];
         const int  nCh   = (tile1 - tile0 + kChunkTiles - 1) / kChunkTiles;
         const long f0    = (long)fb * kBlockFrames + warp * kWarpFrames;
 
@@ -159,6 +176,10 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p)
         }
         const long rowA = f0 + mtOwn * 16 + g, rowB = rowA + 8;
         const int  xsA = __ldg(p.xsq + min(rowA, p.T - 1)), xsB = __ldg(p.xsq + min(rowB, p.T - 1));
+        // output cursors: next mixture of this lane's two rows
+        float* outA = p.scores + (size_t)min(rowA, p.T - 1) * p.nMix + p.grpMix[grp];
+        float* outB = p.scores + (size_t)min(rowB, p.T - 1) * p.nMix + p.grpMix[grp];
+        const bool liveA = rowA < p.T, liveB = rowB < p.T;
 
         int   best[8];  // index mt * 2 + h: running min of (c + |m|^2 - 2 x.m) for row mt * 16 + h * 8 + g
         float oA[4] = {0, 0, 0, 0}, oB[4] = {0, 0, 0, 0};
@@ -166,6 +187,75 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p)
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             best[j] = INT_MAX;
+
+        // products of one tile: 8 IMMAs into acc
+        auto products = [&](uint32_t tileAddr, int (&acc)[4][4]) {
+            uint32_t b[4];
+            ldsm_x4(tileAddr + ldsmOff, b);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+                imma_u8(acc[mt], a[mt][0], b[0], b[1], zero);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+                imma_u8(acc[mt], a[mt][1], b[2], b[3], acc[mt]);
+        };
+        // min over the tile's columns, and at the end of a mixture the reduction over the quad + emit
+        auto consume = [&](uint32_t tileAddr, const int (&acc)[4][4]) {
+            const int2 cc    = lds_int2(tileAddr + ccOff);
+            const int  flags = lds_int(tileAddr + 8 * kRowBytes + 32);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                best[mt * 2]     = min3(best[mt * 2], cc.x - 2 * acc[mt][0], cc.y - 2 * acc[mt][1]);
+                best[mt * 2 + 1] = min3(best[mt * 2 + 1], cc.x - 2 * acc[mt][2], cc.y - 2 * acc[mt][3]);
+            }
+            if (flags & 1) {  // last tile of its mixture (warp-uniform)
+                // butterfly: after xor 1 a lane keeps half of the 8 rows, after xor 2 a quarter
+                int v4[4], v2[2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int keep = (q & 1) ? best[j + 4] : best[j];
+                    const int send = (q & 1) ? best[j] : best[j + 4];
+                    v4[j]          = min(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int keep = (q & 2) ? v4[j + 2] : v4[j];
+                    const int send = (q & 2) ? v4[j] : v4[j + 2];
+                    v2[j]          = min(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+                }
+                // empty mixture: the reference's running minimum stays at INT_MAX (:479-481)
+                const int   bA = (flags & 2) ? INT_MAX : v2[0] + xsA, bB = (flags & 2) ? INT_MAX : v2[1] + xsB;
+                const float sA = __fdiv_rn((float)bA, p.scale), sB = __fdiv_rn((float)bB, p.scale);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    best[j] = INT_MAX;
+                if (p.vec4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)  // nStaged is warp-uniform; static register indices
+                        if (nStaged == k) {
+                            oA[k] = sA;
+                            oB[k] = sB;
+                        }
+                    if (++nStaged == 4) {
+                        nStaged = 0;
+                        if (liveA)
+                            *reinterpret_cast<float4*>(outA) = make_float4(oA[0], oA[1], oA[2], oA[3]);
+                        if (liveB)
+                            *reinterpret_cast<float4*>(outB) = make_float4(oB[0], oB[1], oB[2], oB[3]);
+                        outA += 4;
+                        outB += 4;
+                    }
+                }
+                else {
+                    if (liveA)
+                        *outA = sA;
+                    if (liveB)
+                        *outB = sB;
+                    ++outA;
+                    ++outB;
+                }
+            }
+        };
 
         for (int c = 0; c < nCh; ++c) {
             if (tid == 0 && c + kStages - 1 < nCh) {
@@ -179,68 +269,23 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p)
             const uint32_t n  = seq + c;
             const uint32_t st = n % kStages;
             mbar_wait(&bar[st], (n / kStages) & 1u);
-            const unsigned char* chunk = buf + st * CHUNK;
-            const int            nt    = min(kChunkTiles, tile1 - (tile0 + c * kChunkTiles));
+            const int nt   = min(kChunkTiles, tile1 - (tile0 + c * kChunkTiles));
+            uint32_t  addr = sbuf + st * CHUNK;
 
-            for (int t = 0; t < nt; ++t) {
-                const unsigned char* tile = chunk + t * kTileBytes;
-                uint32_t             b[4];
-                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
-                             : "r"(smem_u32(tile) + ldsmOff));
-                const int2 cc    = *reinterpret_cast<const int2*>(tile + 8 * kRowBytes + q * 8);  // columns 2q, 2q+1
-                const int  flags = *reinterpret_cast<const int*>(tile + 8 * kRowBytes + 32);
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    int acc[4];
-                    imma_u8(acc, a[mt][0], b[0], b[1], zero);
-                    imma_u8(acc, a[mt][1], b[2], b[3], acc);
-                    best[mt * 2]     = min3(best[mt * 2], cc.x - 2 * acc[0], cc.y - 2 * acc[1]);
-                    best[mt * 2 + 1] = min3(best[mt * 2 + 1], cc.x - 2 * acc[2], cc.y - 2 * acc[3]);
-                }
-                if (flags & 1) {  // last tile of its mixture (warp-uniform): reduce over the quad and emit
-                    // butterfly: after xor 1 a lane keeps half of the 8 rows, after xor 2 a quarter
-                    int v4[4], v2[2];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int keep = (q & 1) ? best[j + 4] : best[j];
-                        const int send = (q & 1) ? best[j] : best[j + 4];
-                        v4[j]          = min(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int keep = (q & 2) ? v4[j + 2] : v4[j];
-                        const int send = (q & 2) ? v4[j] : v4[j + 2];
-                        v2[j]          = min(keep, __shfl_xor_sync(0xffffffffu, send, 2));
-                    }
-                    // empty mixture: the reference's running minimum stays at INT_MAX (:479-481)
-                    const int   bA = (flags & 2) ? INT_MAX : v2[0] + xsA, bB = (flags & 2) ? INT_MAX : v2[1] + xsB;
-                    const float sA = __fdiv_rn((float)bA, p.scale), sB = __fdiv_rn((float)bB, p.scale);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        best[j] = INT_MAX;
-                    if (p.vec4) {
-                        oA[0] = oA[1]; oA[1] = oA[2]; oA[2] = oA[3]; oA[3] = sA;
-                        oB[0] = oB[1]; oB[1] = oB[2]; oB[2] = oB[3]; oB[3] = sB;
-                        if (++nStaged == 4) {
-                            nStaged = 0;
-                            if (rowA < p.T)
-                                *reinterpret_cast<float4*>(p.scores + (size_t)rowA * p.nMix + (mix - 3)) =
-                                        make_float4(oA[0], oA[1], oA[2], oA[3]);
-                            if (rowB < p.T)
-                                *reinterpret_cast<float4*>(p.scores + (size_t)rowB * p.nMix + (mix - 3)) =
-                                        make_float4(oB[0], oB[1], oB[2], oB[3]);
-                        }
-                    }
-                    else {
-                        if (rowA < p.T)
-                            p.scores[(size_t)rowA * p.nMix + mix] = sA;
-                        if (rowB < p.T)
-                            p.scores[(size_t)rowB * p.nMix + mix] = sB;
-                    }
-                    ++mix;
-                }
+            // software pipeline inside the chunk: the IMMAs of tile t+1 are in flight while tile t is reduced
+            int accA[4][4], accB[4][4];
+            products(addr, accA);
+            int t = 0;
+            for (; t + 2 <= nt; t += 2) {
+                products(addr + kTileBytes, accB);  // tile t+1 exists
+                consume(addr, accA);
+                if (t + 2 < nt)
+                    products(addr + 2 * kTileBytes, accA);
+                consume(addr + kTileBytes, accB);
+                addr += 2 * kTileBytes;
             }
+            if (t < nt)
+                consume(addr, accA);
             __syncthreads();  // everyone is done with stage st before it is refilled
         }
         seq += (uint32_t)nCh;
