@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librasr_b200.so")
+LIB_PATH = os.environ.get("RASR_B200_LIB") or os.path.join(_HERE, "lib", "librasr_b200.so")  # override: experiments
 
 RB_OK = 0
 STATUS = {0: "RB_OK", -1: "RB_ERR_INVALID", -2: "RB_ERR_NO_DEVICE", -3: "RB_ERR_CUDA", -4: "RB_ERR_UNSUPPORTED",

@@ -13,8 +13,11 @@
 // the int -> float conversion and the IEEE division are applied there and only one f32 per (frame, mixture)
 // leaves the SM.  Why not tcgen05: its accumulators live in TMEM and must come back through tcgen05.ld at
 // 64 B/clk/SM (B300_MICROARCH.md; the fp16 tensor scorer in gmm_tensor.cu sits exactly on that bound, 98 us per
-// 100k frames), i.e. >= 88 us for 100k x 4096 accumulators, while the IMMA path needs 44 us for the same products
-// (scripts/micro/mma_rate.cu: 2036 u8 MAC/clk/SM) and has no read-back at all.
+// 100k frames), i.e. >= 88 us for 100k x 4096 accumulators, while the IMMA path needs 44-60 us for the same products
+// (scripts/micro/mma_rate.cu: 2036 u8 MAC/clk/SM peak, 0.37-0.39 IMMA/clk/SM in this kernel's operand pattern) and
+// has no read-back at all.  Measured: 125 us per 100k frames (tensor pipe 38 % busy, the rest is the per-mixture
+// epilogue and its latency).  Tried and rejected: folding the factor 2 into the products ([x|x].[m|m], 12 IMMAs
+// per tile, no subtract: 150 us) and 3 CTAs per SM (register spills: 236 us).
 //
 // Layout: densities in mixture order, every mixture padded to whole 8-column tiles (dummy columns can never win
 // the min).  A tile is one 688-byte block [8 rows x 80 B (64 B of means + 16 B pad: conflict-free ldmatrix) |
@@ -49,7 +52,8 @@ struct IntParams {
     float*               scores;   // [T * nMix]
     long                 T;
     int                  nMix, nGroups, nFrameBlocks, vec4;
-    float                scale;  // scale_ = 2 * quantisation scale^2
+    float                scale;     // scale_ = 2 * quantisation scale^2
+    float                rcpScale;  // RN(1 / scale_); 0 if the three-instruction division is not proven for this scale
 };
 
 // setFeature: u8 = clip(round(f * isd * scale) + 128); 16 lanes per frame, 4 dims (one u32) per lane
@@ -93,6 +97,18 @@ __device__ __forceinline__ void imma_u8(int (&d)[4], const uint32_t (&a)[4], uin
             "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
             : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+}
+
+// (f32)b / scale_, correctly rounded.  For |b| < 2^24 the quotient is formed as q0 = a r, q = fma(fma(-s, q0, a), r, q0)
+// with r = RN(1/s) (Markstein); the host has checked this sequence against IEEE division for EVERY integer in that
+// range for this particular scale (rb_gmm_int_create), otherwise rcpScale is 0 and div.rn is used throughout.
+__device__ __forceinline__ float score_of(int b, float scale, float rcp) {
+    const float a = (float)b;
+    if (rcp != 0.0f && (unsigned)(b + (1 << 24)) < (2u << 24)) {
+        const float q0 = __fmul_rn(a, rcp);
+        return __fmaf_rn(__fmaf_rn(-scale, q0, a), rcp, q0);
+    }
+    return __fdiv_rn(a, scale);
 }
 
 __device__ __forceinline__ int min3(int a, int b, int c) {
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p)
                 }
                 // empty mixture: the reference's running minimum stays at INT_MAX (:479-481)
                 const int   bA = (flags & 2) ? INT_MAX : v2[0] + xsA, bB = (flags & 2) ? INT_MAX : v2[1] + xsB;
-                const float sA = __fdiv_rn((float)bA, p.scale), sB = __fdiv_rn((float)bB, p.scale);
+                const float sA = score_of(bA, p.scale, p.rcpScale), sB = score_of(bB, p.scale, p.rcpScale);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     best[j] = INT_MAX;
@@ -301,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p)
 struct rb_gmm_int {
     rb::DeviceInfo dev;
     int            dim = 0, nMix = 0, nTiles = 0, ctasPerSm = 1, curGroups = -1;
-    float          scale = 1.0f;
+    float          scale = 1.0f, rcpScale = 0.0f;
     size_t         smemBytes = 0;
     std::vector<int> tilesOfMixture;
     rb::DevBuf<unsigned char> dTiles, dXq;
@@ -315,6 +331,24 @@ namespace {
 unsigned char quantize_u8(float x) {
     const int v = (int)std::round(x) + 128;
     return (unsigned char)std::min(std::max(v, 0), 255);
+}
+
+// does q0 = a r, q = fma(fma(-s, q0, a), r, q0) equal the IEEE quotient a / s for every integer |a| <= 2^24 ?
+__attribute__((target("fma"))) bool fast_division_exact_fma(float sc, float r) {
+    bool ok = true;
+    for (int b = -(1 << 24); ok && b <= (1 << 24); ++b) {
+        const float a = (float)b, q0 = a * r;
+        ok = __builtin_fmaf(__builtin_fmaf(-sc, q0, a), r, q0) == a / sc;
+    }
+    return ok;
+}
+bool fast_division_exact_soft(float sc, float r) {
+    bool ok = true;
+    for (int b = -(1 << 24); ok && b <= (1 << 24); ++b) {
+        const float a = (float)b, q0 = a * r;
+        ok = std::fmaf(std::fmaf(-sc, q0, a), r, q0) == a / sc;
+    }
+    return ok;
 }
 
 void make_groups(const rb_gmm_int* h, int G, std::vector<int>& grpTile, std::vector<int>& grpMix) {
@@ -395,6 +429,13 @@ int rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaS
     const float scale        = (float)((double)255.0f / (1.25 * (double)intervalSize));
     const float scaleSquared = scale * scale;
     h->scale                 = (float)(2.0 * (double)scaleSquared);
+    {  // exhaustive proof of the fast division for this scale (33.5 M quotients, 0.06-0.2 s, once per model)
+        const float r  = 1.0f / h->scale;
+        const bool  ok = std::isfinite(r) && r != 0.0f &&
+                        (__builtin_cpu_supports("fma") ? fast_division_exact_fma(h->scale, r)
+                                                       : fast_division_exact_soft(h->scale, r));
+        h->rcpScale = ok ? r : 0.0f;
+    }
     for (unsigned d = 0; d < D; ++d)
         variance[d] = variance[d] * scale;
     double sumLog = 0;
@@ -496,6 +537,7 @@ int rb_gmm_int_score(rb_gmm_int* h, const float* dFeats, long T, float* dScores,
     p.nFrameBlocks = (int)((T + kBlockFrames - 1) / kBlockFrames);
     p.vec4         = (h->nMix % 4 == 0 && ((uintptr_t)dScores % 16 == 0)) ? 1 : 0;
     p.scale        = h->scale;
+    p.rcpScale     = h->rcpScale;
     const long items = (long)p.nGroups * p.nFrameBlocks;
     gmm_int_kernel<<<(int)std::min<long>(items, slots), kThreads, h->smemBytes, s>>>(p);
     RB_LAUNCH_CHECK();

@@ -26,6 +26,56 @@ template<int MODE> __global__ void k(int* out, long long* cyc, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
+// kernel-like pattern of gmm_int_kernel: 4 A fragment sets (m-tiles) x KS k-steps, B shared by the 4 m-tiles of a
+// k-step and reloaded per "tile" (from registers here), accumulators start from a non-zero C and are 3-deep chains
+template<int KS, int VARIANT> __global__ void kpat(int* out, long long* cyc, int iters) {
+  uint32_t a[4][KS][4]; uint32_t b[2 * KS]; int best[8];
+  for (int m = 0; m < 4; m++) for (int k = 0; k < KS; k++) for (int j = 0; j < 4; j++) a[m][k][j] = threadIdx.x * 0x01010101u + m * 17 + k * 5 + j;
+  for (int j = 0; j < 8; j++) best[j] = -2147483647;
+  int c0 = threadIdx.x, c1 = threadIdx.x + 3;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    for (int k = 0; k < 2 * KS; k++) b[k] = (it + k) * 0x01030507u;
+    int acc[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+      asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+                   : "=r"(acc[m][0]), "=r"(acc[m][1]), "=r"(acc[m][2]), "=r"(acc[m][3])
+                   : "r"(a[m][0][0]), "r"(a[m][0][1]), "r"(a[m][0][2]), "r"(a[m][0][3]), "r"(b[0]), "r"(b[1]), "r"(c0), "r"(c1));
+#pragma unroll
+    for (int k = 1; k < KS; k++)
+#pragma unroll
+      for (int m = 0; m < 4; m++)
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+r"(acc[m][0]), "+r"(acc[m][1]), "+r"(acc[m][2]), "+r"(acc[m][3])
+                     : "r"(a[m][k][0]), "r"(a[m][k][1]), "r"(a[m][k][2]), "r"(a[m][k][3]), "r"(b[2 * k]), "r"(b[2 * k + 1]));
+    if (VARIANT == 1) {
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        best[2 * m] = __vimax3_s32(best[2 * m], acc[m][0], acc[m][1]);
+        best[2 * m + 1] = __vimax3_s32(best[2 * m + 1], acc[m][2], acc[m][3]);
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < 4; m++) { best[2 * m] ^= acc[m][0] ^ acc[m][1]; best[2 * m + 1] ^= acc[m][2] ^ acc[m][3]; }
+    }
+  }
+  long long t1 = clock64();
+  int s = 0; for (int j = 0; j < 8; j++) s += best[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+template<int KS, int VARIANT> void runk(const char* name, int threads) {
+  int* out; long long* cyc; cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
+  const int iters = 20000;
+  kpat<KS, VARIANT><<<148, threads>>>(out, cyc, iters); cudaDeviceSynchronize();
+  kpat<KS, VARIANT><<<148, threads>>>(out, cyc, iters); cudaDeviceSynchronize();
+  long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  double c = 0; for (int i = 0; i < 148; i++) c += h[i]; c /= 148;
+  double instr = 4.0 * KS * iters * (threads / 32);
+  printf("%-34s warps/SM %2d  IMMA/clk/SM %.3f  cycles per IMMA per SMSP %.1f\n", name, threads / 32, instr / c, 4.0 * c / instr);
+  cudaFree(out); cudaFree(cyc);
+}
 template<int MODE> void run(const char* name, int threads, double mac_per_instr) {
   int* out; long long* cyc; cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
   const int iters = 20000;
@@ -42,6 +92,11 @@ int main() {
   for (int th : {128, 256, 512}) {
     run<0>("mma.sync u8 m16n8k32", th, 16 * 8 * 32);
     run<1>("mma.sync f16 m16n8k16", th, 16 * 8 * 16);
+  }
+  for (int th : {256, 512}) {
+    runk<2, 0>("kernel pattern KS=2 xor-epilogue", th);
+    runk<2, 1>("kernel pattern KS=2 max3-epilogue", th);
+    runk<3, 1>("kernel pattern KS=3 max3-epilogue", th);
   }
   return 0;
 }
