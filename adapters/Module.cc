@@ -16,6 +16,7 @@ Module_::Module_() {
     f->registerFeatureScorer<FeatureScorerOf<RB_GMM_DIAG_MAX>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 1, "b200-diagonal-maximum");
     f->registerFeatureScorer<FeatureScorerOf<RB_GMM_DIAG_SUM>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 2, "b200-diagonal-sum");
     f->registerFeatureScorer<FeatureScorerOf<RB_GMM_BATCH_TENSOR>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 3, "b200-batch-tensor");
+    f->registerFeatureScorer<FeatureScorerOf<RB_GMM_BATCH_INT>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 4, "b200-batch-int");
     Flow::Registry::instance().registerFilter<MfccNode>();
 }
 
