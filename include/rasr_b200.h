@@ -215,6 +215,40 @@ int rb_nn_forward(rb_nn* h, const float* feats, long T, float* out);
 int rb_nn_forward_dev(rb_nn* h, const float* d_feats, long T, float* d_out, void* stream);
 
 /* =====================================================================================
+ * Feature post-processing between the front-end and the scorers: the nodes of
+ * src/Tools/FeatureExtraction/share/processing.standard_system.flow:25-27 and lda.flow:11-19
+ *   signal-normalization (type mean | mean-and-variance, length / right)   src/Signal/Normalization.cc:41-190
+ *   signal-vector-f32-sequence-concatenation (max-size, right)             src/Signal/VectorSequenceConcatenation.hh:89-103
+ *   signal-matrix-multiplication-f32 (file = rows x cols matrix)           src/Signal/MatrixMult.hh
+ * chained on the device in this order; every stage is optional.
+ * ===================================================================================== */
+
+typedef struct rb_postproc rb_postproc;
+
+typedef struct {
+    int          norm_type;     /* 0: none, 1: mean, 2: mean-and-variance */
+    long         norm_length;   /* sliding window in frames; < 0 = "infinite" (whole segment) */
+    long         norm_right;    /* output point counted from the newest frame; < 0 = "infinite" */
+    int          splice_length; /* max-size of the concatenation window; 0: none */
+    int          splice_right;  /* frames to the right of the present frame */
+    int          matrix_rows;   /* output dimension of the matrix multiplication */
+    int          matrix_cols;   /* must equal the (spliced) input dimension */
+    const float* matrix;        /* row-major rows x cols (Math::Matrix<f32>); NULL: none; copied by create */
+    int          contraction;   /* as rb_gmm_create */
+    int          device;
+} rb_postproc_cfg;
+
+int  rb_postproc_create(const rb_postproc_cfg* cfg, int dim_in, rb_postproc** out);
+void rb_postproc_destroy(rb_postproc* h);
+int  rb_postproc_dim_out(const rb_postproc* h);
+/* feats [frame_offsets[n_utt] * dim_in], segments = [frame_offsets[u], frame_offsets[u+1]) (statistics and
+ * windows never cross a segment boundary: the nodes reset at EOS); out [frames * dim_out].  in and out must not
+ * alias.  The device variant only enqueues work on `stream` (frame_offsets stays on the host). */
+int rb_postproc_process(rb_postproc* h, const float* feats, const int64_t* frame_offsets, int n_utt, float* out);
+int rb_postproc_process_dev(rb_postproc* h, const float* d_feats, const int64_t* frame_offsets, int n_utt,
+                            float* d_out, void* stream);
+
+/* =====================================================================================
  * Fused audio -> scores pipeline (config C3): front-end and GMM scorer chained on the device,
  * features never leave HBM.  scores [total_frames * n_mixtures].
  * ===================================================================================== */

@@ -130,6 +130,13 @@ int orc_nn_forward_f64(int n_layers, const int* dims, const int* act, const doub
 
 const char* orc_version(void);
 
+/* feature post-processing between front-end and scorer (postproc_oracle.cc): signal-normalization
+ * (type 1 mean, 2 mean-and-variance; length / right < 0 = "infinite"), sequence concatenation, matrix multiplication */
+int orc_normalize(int type, long length, long right, const float* feats, const long* frame_offsets, int n_utt, int dim,
+                  float* out, int use_fma);
+int orc_splice(int length, int right, const float* feats, const long* frame_offsets, int n_utt, int dim, float* out);
+int orc_matmul(const float* M, int rows, int cols, const float* x, long T, float* y, int use_fma);
+
 #ifdef __cplusplus
 }
 #endif

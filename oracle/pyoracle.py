@@ -231,6 +231,43 @@ def gmm_diag_sum(ms, feats, mixture_weight_scale=1.0, gaussian_scale=1.0, use_fm
     return _gmm_diag(lib().orc_gmm_diag_sum, ms, feats, mixture_weight_scale, gaussian_scale, use_fma)
 
 
+def _offsets(frame_offsets, T):
+    fo = np.ascontiguousarray(frame_offsets if frame_offsets is not None else [0, T], np.int64)
+    return fo, fo.size - 1
+
+
+def normalize(feats, frame_offsets=None, kind="mean", length=-1, right=-1, use_fma=True):
+    """signal-normalization over segments given by frame_offsets (default: one segment); length/right < 0 = infinite."""
+    feats = np.ascontiguousarray(feats, np.float32)
+    fo, n = _offsets(frame_offsets, feats.shape[0])
+    out = np.zeros_like(feats)
+    rc = lib().orc_normalize({"mean": 1, "mean-and-variance": 2}[kind], C.c_long(length), C.c_long(right),
+                             _p(feats, C.c_float), _p(fo, C.c_long), n, feats.shape[1], _p(out, C.c_float), int(use_fma))
+    if rc:
+        raise RuntimeError("orc_normalize failed: %d" % rc)
+    return out
+
+
+def splice(feats, length, right, frame_offsets=None):
+    feats = np.ascontiguousarray(feats, np.float32)
+    fo, n = _offsets(frame_offsets, feats.shape[0])
+    out = np.zeros((feats.shape[0], length * feats.shape[1]), np.float32)
+    rc = lib().orc_splice(int(length), int(right), _p(feats, C.c_float), _p(fo, C.c_long), n, feats.shape[1],
+                          _p(out, C.c_float))
+    if rc:
+        raise RuntimeError("orc_splice failed: %d" % rc)
+    return out
+
+
+def matmul(M, x, use_fma=True):
+    M = np.ascontiguousarray(M, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.zeros((x.shape[0], M.shape[0]), np.float32)
+    lib().orc_matmul(_p(M, C.c_float), M.shape[0], M.shape[1], _p(x, C.c_float), C.c_long(x.shape[0]),
+                     _p(y, C.c_float), int(use_fma))
+    return y
+
+
 def _nn_args(dims, acts, weights, biases, dtype, ctype):
     n = len(weights)
     dims_a = np.asarray(dims, np.int32)

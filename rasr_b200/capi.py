@@ -30,6 +30,7 @@ SYMBOLS = [
     "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
+    "rb_postproc_create", "rb_postproc_destroy", "rb_postproc_dim_out", "rb_postproc_process", "rb_postproc_process_dev",
 ]
 
 
@@ -48,6 +49,13 @@ class FrontendCfg(C.Structure):
 class FrontendGeometry(C.Structure):
     _fields_ = [(n, C.c_int) for n in
                 ("win_length", "win_shift", "fft_length", "n_bins", "n_filters", "n_weights", "feat_dim")]
+
+
+class PostprocCfg(C.Structure):
+    _fields_ = [("norm_type", C.c_int), ("norm_length", C.c_long), ("norm_right", C.c_long),
+                ("splice_length", C.c_int), ("splice_right", C.c_int), ("matrix_rows", C.c_int),
+                ("matrix_cols", C.c_int), ("matrix", C.POINTER(C.c_float)), ("contraction", C.c_int),
+                ("device", C.c_int)]
 
 
 class MixtureSetC(C.Structure):
@@ -121,6 +129,12 @@ def lib():
     L.rb_nn_forward_dev.argtypes = [vp, vp, C.c_long, vp, vp]
     L.rb_pipeline_score.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
     L.rb_pipeline_score_dev.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp]
+    L.rb_postproc_create.argtypes = [C.POINTER(PostprocCfg), C.c_int, C.POINTER(vp)]
+    L.rb_postproc_destroy.argtypes = [vp]
+    L.rb_postproc_destroy.restype = None
+    L.rb_postproc_dim_out.argtypes = [vp]
+    L.rb_postproc_process.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.rb_postproc_process_dev.argtypes = [vp, vp, vp, C.c_int, vp, vp]
     L.rb_test_gemm_bf16.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.rb_test_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int]
     _lib = L
