@@ -73,6 +73,21 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+            "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
@@ -317,11 +332,16 @@ __global__ void __launch_bounds__(MT2_THREADS, 1)
             if (row < M)
                 epi.begin(st, row);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float v[32];
-                tmem_ld32(tmemBase + ((uint32_t)(q * 32) << 16) + h * BN + c * 32, v);
-                if (row < M)
-                    epi.chunk(st, row, nb * BN + c * 32, v);
+            for (int c = 0; c < BN / 32; c += 2) {  // two TMEM loads in flight per wait
+                float          v0[32], v1[32];
+                const uint32_t ta = tmemBase + ((uint32_t)(q * 32) << 16) + h * BN + c * 32;
+                tmem_ld32_issue(ta, v0);
+                tmem_ld32_issue(ta + 32, v1);
+                tmem_ld_wait();
+                if (row < M) {
+                    epi.chunk(st, row, nb * BN + c * 32, v0);
+                    epi.chunk(st, row, nb * BN + c * 32 + 32, v1);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -385,7 +405,9 @@ int launch_mt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int
     RB_CUDA(cudaFuncSetAttribute(gemm16_mt2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT2_SMEM_BYTES));
     RB_REQUIRE(K % BK == 0 && K > 0, "GEMM K=%d must be a positive multiple of %d", K, BK);
     const int nTiles = ((M + MT2_BM - 1) / MT2_BM) * ((N + BN - 1) / BN);
-    const int grid   = std::min(nTiles, smCount);
+    int       grid   = std::min(nTiles, smCount);
+    if (const char* e = getenv("RB_GEMM_GRID"))  // experiments: fewer CTAs than SMs
+        grid = std::max(1, std::min(grid, atoi(e)));
     gemm16_mt2_kernel<Epi><<<grid, MT2_THREADS, MT2_SMEM_BYTES, s>>>(tmA, tmB, M, N, K, instr_desc(fmt), epi);
     RB_LAUNCH_CHECK();
     return RB_OK;

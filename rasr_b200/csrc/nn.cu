@@ -35,6 +35,49 @@ __device__ __forceinline__ float activate(float x, int act) {
 }
 
 // ---- tcgen05 epilogues -------------------------------------------------------------------
+// bias of 32 consecutive columns: 8 vector loads issued together (the scalar form serialised 32 load latencies
+// inside the exposed, single-buffered TMEM epilogue); columns >= N read as 0
+__device__ __forceinline__ void load_bias32(const float* bias, int col0, int N, float (&b)[32]) {
+    if (bias && col0 + 32 <= N && (((uintptr_t)(bias + col0)) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
+            b[4 * j] = q.x; b[4 * j + 1] = q.y; b[4 * j + 2] = q.z; b[4 * j + 3] = q.w;
+        }
+    }
+    else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            b[j] = (bias && col0 + j < N) ? __ldg(bias + col0 + j) : 0.0f;
+    }
+}
+
+// v[j] = act(v[j] + b[j]) with the activation switch hoisted out of the element loop
+__device__ __forceinline__ void bias_activate32(const float (&v)[32], const float (&b)[32], int act, float (&o)[32]) {
+    if (act == RB_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float x = v[j] + b[j];
+            o[j]          = x < 0.0f ? 0.0f : x;
+        }
+    }
+    else if (act == RB_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            o[j] = 1.0f / (1.0f + expf(-(v[j] + b[j])));
+    }
+    else if (act == RB_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            o[j] = tanhf(v[j] + b[j]);
+    }
+    else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            o[j] = v[j] + b[j];
+    }
+}
+
 struct EpiHiddenBf16 {  // bf16 activations for the next layer, row pitch ldo (multiple of 64)
     const float*   bias;
     __nv_bfloat16* out;
@@ -44,14 +87,14 @@ struct EpiHiddenBf16 {  // bf16 activations for the next layer, row pitch ldo (m
     __device__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
         if (col0 >= ldo)
             return;
+        float b[32], o[32];
+        load_bias32(bias, col0, N, b);
+        bias_activate32(v, b, act, o);
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-            const int n0 = col0 + j, n1 = n0 + 1;
-            float     a = n0 < N ? activate(v[j] + (bias ? __ldg(bias + n0) : 0.0f), act) : 0.0f;
-            float     b = n1 < N ? activate(v[j + 1] + (bias ? __ldg(bias + n1) : 0.0f), act) : 0.0f;
-            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            packed[j >> 1]   = *reinterpret_cast<uint32_t*>(&h);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(col0 + j < N ? o[j] : 0.0f, col0 + j + 1 < N ? o[j + 1] : 0.0f);
+            packed[j >> 1]         = *reinterpret_cast<const uint32_t*>(&h);
         }
         uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * ldo + col0);
 #pragma unroll
@@ -70,23 +113,21 @@ struct EpiFinalF32 {  // f32 output [M x N], out = sign * act(acc + bias)
     __device__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
         if (col0 >= N)
             return;
+        float b[32], o[32];
+        load_bias32(bias, col0, N, b);
+        bias_activate32(v, b, act, o);
         float* dst = out + (size_t)row * ldo + col0;
         if (col0 + 32 <= N && ((ldo & 3) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                o.x = sign * activate(v[j] + (bias ? __ldg(bias + col0 + j) : 0.0f), act);
-                o.y = sign * activate(v[j + 1] + (bias ? __ldg(bias + col0 + j + 1) : 0.0f), act);
-                o.z = sign * activate(v[j + 2] + (bias ? __ldg(bias + col0 + j + 2) : 0.0f), act);
-                o.w = sign * activate(v[j + 3] + (bias ? __ldg(bias + col0 + j + 3) : 0.0f), act);
-                *reinterpret_cast<float4*>(dst + j) = o;
-            }
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) =
+                        make_float4(sign * o[j], sign * o[j + 1], sign * o[j + 2], sign * o[j + 3]);
         }
         else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (col0 + j < N)
-                    dst[j] = sign * activate(v[j] + (bias ? __ldg(bias + col0 + j) : 0.0f), act);
+                    dst[j] = sign * o[j];
         }
     }
 };
