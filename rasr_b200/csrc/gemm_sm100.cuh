@@ -28,6 +28,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS     = 256;
 constexpr int TMEM_COLS   = 512;
 constexpr int SMEM_BYTES  = STAGES * STAGE_BYTES + 256 + 1024;  // ring + barriers + alignment slack
+constexpr int OUT_STAGE_BYTES = 4 * 2 * 32 * 32 * 4;             // TMA-store epilogue: 4 warps x 2 boxes of 32 x 32 f32
+constexpr int SMEM_BYTES_TMA  = STAGES * STAGE_BYTES + 1024 + OUT_STAGE_BYTES + 1024;
 
 enum { FMT_F16 = 0, FMT_BF16 = 1 };
 
@@ -48,6 +50,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                     "r"(dst),
             "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
             : "memory");
+}
+// shared -> global tile store through the TMA unit (SASS: UTMASTG); completion is tracked by bulk groups
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template<int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N bulk groups of this thread still read shared memory
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -108,10 +123,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 //   __device__ void chunk(State&, int row, int col0, const float (&v)[32]) const;   columns col0..col0+31
 // row < M is guaranteed by the caller; columns may exceed N -- the functor masks them.  Chunks of a
 // row arrive in increasing column order.
-template<class Epi>
+// Epilogues with  static constexpr bool kTmaStore = true  provide  transform(col0, v, o)  instead of chunk():
+// the kernel stages each 32 x 32 f32 block in (128-byte swizzled) shared memory and hands it to the TMA unit, which
+// writes whole lines and clips at the matrix edges; the LSU never sees the row-strided stores that otherwise make a
+// wide f32 epilogue 2x longer than the MMAs of a tile.
+template<class Epi, bool TMA_STORE = false>
 __global__ void __launch_bounds__(THREADS, 1)
-        gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                      int K, uint32_t idesc, const Epi epi) {
+        gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmOut, int M, int N, int K, uint32_t idesc, const Epi epi) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw   = smem_u32(smem_dyn);
     const uint32_t pad   = (1024u - (raw & 1023u)) & 1023u;
@@ -129,6 +148,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (TMA_STORE)
+            tma_prefetch_desc(&tmOut);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -193,6 +214,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     else if (warp >= 4) {
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         uint32_t  tc = 0;
+        // TMA-store staging: two 4 KB boxes per epilogue warp behind the operand ring (1024-byte aligned)
+        const uint32_t outStage = sbase + STAGES * STAGE_BYTES + 1024 + q * 2 * 4096;
         for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++tc) {
             const int      mb = tile / nNB, nb = tile - mb * nNB;
             const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
@@ -203,17 +226,50 @@ __global__ void __launch_bounds__(THREADS, 1)
             if (row < M)
                 epi.begin(st, row);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float v[32];
-                tmem_ld32(tmemBase + ((uint32_t)(q * 32) << 16) + a * BN + c * 32, v);
-                if (row < M)
-                    epi.chunk(st, row, nb * BN + c * 32, v);
+            for (int c = 0; c < BN / 32; c += 2) {  // two TMEM loads in flight per wait
+                float          v0[32], v1[32];
+                const uint32_t ta = tmemBase + ((uint32_t)(q * 32) << 16) + a * BN + c * 32;
+                tmem_ld32_issue(ta, v0);
+                tmem_ld32_issue(ta + 32, v1);
+                tmem_ld_wait();
+                if constexpr (TMA_STORE) {
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const int col0 = nb * BN + (c + hlf) * 32;
+                        if (col0 >= N)  // warp-uniform: the whole box lies outside the matrix
+                            continue;
+                        float o[32];
+                        epi.transform(col0, hlf ? v1 : v0, o);
+                        if (lane == 0)
+                            bulk_wait_read<1>();  // the store that used this box two steps ago has read it
+                        __syncwarp();
+                        // row = lane, 16-byte chunk j of the row lives at chunk j ^ (row & 7)  (SWIZZLE_128B)
+                        const uint32_t dst = outStage + hlf * 4096 + lane * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ (lane & 7)) << 4)),
+                                         "f"(o[4 * j]), "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
+                                         : "memory");
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmOut, outStage + hlf * 4096, col0, mb * BM + q * 32);
+                            bulk_commit();
+                        }
+                    }
+                }
+                else if (row < M) {
+                    epi.chunk(st, row, nb * BN + c * 32, v0);
+                    epi.chunk(st, row, nb * BN + c * 32 + 32, v1);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&tempty[a]);
         }
+        if (TMA_STORE && lane == 0)
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -416,12 +472,48 @@ int launch_mt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int
 template<class Epi>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int fmt, const Epi& epi, int smCount,
            cudaStream_t s) {
-    RB_CUDA(cudaFuncSetAttribute(gemm16_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    RB_CUDA(cudaFuncSetAttribute(gemm16_kernel<Epi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     RB_REQUIRE(K % BK == 0 && K > 0, "GEMM K=%d must be a positive multiple of %d", K, BK);
     const int nTiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid   = std::min(nTiles, smCount);
-    gemm16_kernel<Epi><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, M, N, K, instr_desc(fmt), epi);
+    gemm16_kernel<Epi, false><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmA, M, N, K, instr_desc(fmt), epi);
     RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// f32 output through TMA stores; tmOut: map over the [M x N] f32 output with 32 x 32 boxes (make_map_out_f32)
+template<class Epi>
+int launch_tma_store(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, int M, int N, int K,
+                     int fmt, const Epi& epi, int smCount, cudaStream_t s) {
+    RB_CUDA(cudaFuncSetAttribute(gemm16_kernel<Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SMEM_BYTES_TMA));
+    RB_REQUIRE(K % BK == 0 && K > 0, "GEMM K=%d must be a positive multiple of %d", K, BK);
+    const int nTiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid   = std::min(nTiles, smCount);
+    gemm16_kernel<Epi, true><<<grid, THREADS, SMEM_BYTES_TMA, s>>>(tmA, tmB, tmOut, M, N, K, instr_desc(fmt), epi);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+// 2-D map over a row-major [rows x cols] f32 matrix with row pitch ld elements (ld * 4 a multiple of 16); box 32 x 32
+inline int make_map_out_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        rb::set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return RB_ERR_CUDA;
+    }
+    cuuint64_t dims[2]    = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2]     = {32, 32};
+    cuuint32_t estr[2]    = {1, 1};
+    CUresult   r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rb::set_error("cuTensorMapEncodeTiled (f32 output) failed with CUresult %d (rows %llu cols %llu ld %llu)", (int)r,
+                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+        return RB_ERR_CUDA;
+    }
     return RB_OK;
 }
 

@@ -110,6 +110,15 @@ struct EpiFinalF32 {  // f32 output [M x N], out = sign * act(acc + bias)
     float        sign;
     struct State {};
     __device__ void begin(State&, int) const {}
+    // TMA-store path of gemm16_kernel: values only, the kernel stages and stores the 32 x 32 box
+    __device__ void transform(int col0, const float (&v)[32], float (&o)[32]) const {
+        float b[32];
+        load_bias32(bias, col0, N, b);
+        bias_activate32(v, b, act, o);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            o[j] = sign * o[j];
+    }
     __device__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
         if (col0 >= N)
             return;
@@ -264,6 +273,8 @@ struct rb_nn {
     std::vector<NnLayer*> layers;
     cudaStream_t         stream = nullptr;
     long                 chunk = 18944;  // frames per pass: 74 row blocks of 256 -> whole waves on 148 SMs
+    std::vector<CUtensorMap> mapIn128;  // the same inputs with 128-row boxes (double-buffered 128 x 256 kernel)
+    bool                 doubleBuffered = true;
     // bf16 path: ping-pong activation buffers [chunk x maxKPad] and their TMA maps per layer input
     rb::DevBuf<__nv_bfloat16> actA, actB;
     std::vector<CUtensorMap>  mapIn;  // map of the input activation of layer l
@@ -305,8 +316,12 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
                 epi.ldo  = h->layers[l + 1]->kPad;
                 epi.N    = ly->out;
                 epi.act  = ly->act;
-                RB_CHECK(rbgemm::launch_mt2(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
+                if (h->doubleBuffered)
+                    RB_CHECK(rbgemm::launch(h->mapIn128[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
                                             h->dev.sm_count, s));
+                else
+                    RB_CHECK(rbgemm::launch_mt2(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16,
+                                                epi, h->dev.sm_count, s));
                 std::swap(cur, nxt);
             }
             else {
@@ -317,8 +332,22 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
                 epi.N    = ly->out;
                 epi.act  = (scoreMode || ly->act == RB_ACT_SOFTMAX) ? RB_ACT_LINEAR : ly->act;
                 epi.sign = scoreMode ? -1.0f : 1.0f;
-                RB_CHECK(rbgemm::launch_mt2(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
+                // the 128 x 256 kernel double-buffers its accumulator in TMEM: the epilogue of tile i (here 48 KB of
+                // f32 scores per frame) overlaps the MMAs of tile i+1
+                const bool tmaStore = h->doubleBuffered && (ly->out % 4) == 0 && ((uintptr_t)dOut % 16) == 0 &&
+                                      getenv("RB_NN_NO_TMA_STORE") == nullptr;
+                if (tmaStore) {  // wide f32 rows: whole-line stores by the TMA unit instead of row-strided STG
+                    CUtensorMap mapOut;
+                    RB_CHECK(rbgemm::make_map_out_f32(&mapOut, dOut, (uint64_t)T, (uint64_t)ly->out, (uint64_t)ly->out));
+                    RB_CHECK(rbgemm::launch_tma_store(h->mapIn128[l], ly->mapW, mapOut, (int)T, ly->out, ly->kPad,
+                                                      rbgemm::FMT_BF16, epi, h->dev.sm_count, s));
+                }
+                else if (h->doubleBuffered)
+                    RB_CHECK(rbgemm::launch(h->mapIn128[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
                                             h->dev.sm_count, s));
+                else
+                    RB_CHECK(rbgemm::launch_mt2(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16,
+                                                epi, h->dev.sm_count, s));
             }
         }
     }
@@ -472,13 +501,19 @@ extern "C" int rb_nn_create(int n_layers, const int* dims, const int* act, const
         // padding columns of the first layer's input are written by the converter; hidden activations
         // are written up to the next layer's kPad by the epilogue
         h->mapIn.resize(n_layers);
+        h->mapIn128.resize(n_layers);
         for (int l = 0; l < n_layers; ++l) {
             const __nv_bfloat16* buf = (l % 2 == 0) ? h->actA.p : h->actB.p;
             rc = rbgemm::make_map(&h->mapIn[l], buf, (uint64_t)h->chunk, (uint64_t)h->layers[l]->kPad,
                                   (uint64_t)h->layers[l]->kPad, rbgemm::MT2_BM, true);
+            if (rc == RB_OK)
+                rc = rbgemm::make_map(&h->mapIn128[l], buf, (uint64_t)h->chunk, (uint64_t)h->layers[l]->kPad,
+                                      (uint64_t)h->layers[l]->kPad, rbgemm::BM, true);
             if (rc != RB_OK)
                 return fail(rc);
         }
+        if (const char* e = getenv("RB_NN_MT2"))  // experiments: the 256 x 256 single-buffered kernel
+            h->doubleBuffered = atoi(e) == 0;
     }
     else {
         if (h->actFA.reserve((size_t)h->chunk * maxDim) != RB_OK || h->actFB.reserve((size_t)h->chunk * maxDim) != RB_OK)
