@@ -73,6 +73,11 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
     uint64_t r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
@@ -295,16 +300,26 @@ __global__ void __launch_bounds__(kThreads, (NQ <= 10) ? 2 : 1) gmm_diag_kernel(
             }
         }
 
-        float x0[NQ * 4], x1[NQ * 4];
+        uint64_t xp0[NQ * 2], xp1[NQ * 2];  // dims (2i, 2i+1) packed
+        float    x0[4], x1[4];              // scalar copies of the last quad for the tail dims
         {
             const long   ta  = t0 < p.T ? t0 : p.T - 1;
             const long   tb  = t1 < p.T ? t1 : p.T - 1;
             const float* fa  = p.feats + (size_t)ta * p.dim;
             const float* fbp = p.feats + (size_t)tb * p.dim;
 #pragma unroll
-            for (int d = 0; d < NQ * 4; ++d) {
-                x0[d] = d < p.dim ? __ldg(fa + d) : 0.0f;
-                x1[d] = d < p.dim ? __ldg(fbp + d) : 0.0f;
+            for (int i = 0; i < NQ * 2; ++i) {
+                const int   d  = 2 * i;
+                const float a0 = d < p.dim ? __ldg(fa + d) : 0.0f, a1 = d + 1 < p.dim ? __ldg(fa + d + 1) : 0.0f;
+                const float b0 = d < p.dim ? __ldg(fbp + d) : 0.0f, b1 = d + 1 < p.dim ? __ldg(fbp + d + 1) : 0.0f;
+                xp0[i] = pack2(a0, a1);
+                xp1[i] = pack2(b0, b1);
+                if (i >= NQ * 2 - 2) {
+                    x0[2 * (i - (NQ * 2 - 2))]     = a0;
+                    x0[2 * (i - (NQ * 2 - 2)) + 1] = a1;
+                    x1[2 * (i - (NQ * 2 - 2))]     = b0;
+                    x1[2 * (i - (NQ * 2 - 2)) + 1] = b1;
+                }
             }
         }
 
@@ -336,25 +351,27 @@ __global__ void __launch_bounds__(kThreads, (NQ <= 10) ? 2 : 1) gmm_diag_kernel(
                 const int     flags = __float_as_int(tail.z);
                 float         d0 = 0.0f, d1 = 0.0f;
                 if (!(flags & 2)) {  // not a placeholder row of an empty mixture
-                    float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+                    // packed f32x2 (FADD2 / FMUL2 / FFMA2): SSE lanes (0,1) and (2,3) share a register pair; every lane
+                    // is still one IEEE sub, mul and fma (or mul + add) in the reference's order
+                    uint64_t s0[2] = {0ull, 0ull}, s1[2] = {0ull, 0ull};
+                    const ulonglong2* rowp = reinterpret_cast<const ulonglong2*>(row);
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
                         if (q < nFullQ) {
-                            const float4 m4 = row[q], v4 = row[NQ + q];
-                            const float  m[4] = {m4.x, m4.y, m4.z, m4.w};
-                            const float  v[4] = {v4.x, v4.y, v4.z, v4.w};
+                            const ulonglong2 m4 = rowp[q], v4 = rowp[NQ + q];
+                            const uint64_t   m[2] = {m4.x, m4.y}, v[2] = {v4.x, v4.y};
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float e0 = __fmul_rn(__fsub_rn(m[j], x0[4 * q + j]), v[j]);
-                                const float e1 = __fmul_rn(__fsub_rn(m[j], x1[4 * q + j]), v[j]);
-                                s0[j]          = sq_acc(e0, s0[j], FUSE);
-                                s1[j]          = sq_acc(e1, s1[j], FUSE);
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t e0 = mul2(sub2(m[j], xp0[2 * q + j]), v[j]);
+                                const uint64_t e1 = mul2(sub2(m[j], xp1[2 * q + j]), v[j]);
+                                s0[j]             = FUSE ? fma2(e0, e0, s0[j]) : sqadd2(e0, s0[j]);
+                                s1[j]             = FUSE ? fma2(e1, e1, s1[j]) : sqadd2(e1, s1[j]);
                             }
                         }
                     }
                     // hadd(sum,sum) -> (s0+s1, s2+s3); result = 0 + ((s0+s1) + (s2+s3))
-                    d0 = __fadd_rn(0.0f, __fadd_rn(__fadd_rn(s0[0], s0[1]), __fadd_rn(s0[2], s0[3])));
-                    d1 = __fadd_rn(0.0f, __fadd_rn(__fadd_rn(s1[0], s1[1]), __fadd_rn(s1[2], s1[3])));
+                    d0 = __fadd_rn(0.0f, __fadd_rn(__fadd_rn(lo2(s0[0]), hi2(s0[0])), __fadd_rn(lo2(s0[1]), hi2(s0[1]))));
+                    d1 = __fadd_rn(0.0f, __fadd_rn(__fadd_rn(lo2(s1[0]), hi2(s1[0])), __fadd_rn(lo2(s1[1]), hi2(s1[1]))));
                     if (nTail) {
                         const float4 m4 = row[NQ - 1], v4 = row[2 * NQ - 1];
                         const float  m[4] = {m4.x, m4.y, m4.z, m4.w};
@@ -362,8 +379,8 @@ __global__ void __launch_bounds__(kThreads, (NQ <= 10) ? 2 : 1) gmm_diag_kernel(
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
                             if (j < nTail) {
-                                const float e0 = __fmul_rn(__fsub_rn(m[j], x0[4 * (NQ - 1) + j]), v[j]);
-                                const float e1 = __fmul_rn(__fsub_rn(m[j], x1[4 * (NQ - 1) + j]), v[j]);
+                                const float e0 = __fmul_rn(__fsub_rn(m[j], x0[j]), v[j]);
+                                const float e1 = __fmul_rn(__fsub_rn(m[j], x1[j]), v[j]);
                                 d0             = sq_acc(e0, d0, FUSE);
                                 d1             = sq_acc(e1, d1, FUSE);
                             }
