@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "gmm-int", "frontend", "pipeline", "nn"])
+    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "gmm-int", "frontend", "pipeline", "pipeline-nn", "nn"])
     ap.add_argument("--frames", type=int, default=0, help="override the frame count of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -263,6 +263,36 @@ def main():
         workload = "C3 shard: %s on %d utterances x 1000 frames per GPU (%d frames)" % (wl, n_utt, T)
         algo_bytes = ALGO_BYTES_PER_FRAME[wl] * T
         bound, dtype = "hbm", "f32"
+    elif wl == "pipeline-nn":
+        # C4 fed from audio: MFCC -> segment CMVN -> 11-frame window -> 6 x 2048 -> 12000 senone scores
+        from rasr_b200 import postproc
+        n_utt = max(1, (args.frames or 37000) // 1000)
+        samples_h, offs = synth.corpus(n_utt, n_samples=160240, seed0=3000 + 1000 * rank)
+        fe = flow.FrontEnd(device=local_rank)
+        pp = postproc.PostProcessor(39, "mean-and-variance", splice=(11, 5), device=local_rank)
+        net = synth.network()
+        sc = nn.NnScorer(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, "bf16",
+                         device=local_rank)
+        T = int(fe.count_frames(offs)[-1])
+        d_samples = [torch.from_numpy(samples_h).to(dev) for _ in range(2)]
+        d_feats = torch.empty((T, 39), dtype=torch.float32, device=dev)
+        d_post = torch.empty((T, 429), dtype=torch.float32, device=dev)
+        d_out = [torch.empty((T, 12000), dtype=torch.float32, device=dev) for _ in range(2)]
+
+        def step(i):
+            pipeline.nn_score_utterances_dev(fe, pp, sc, d_samples[i % 2], offs, d_feats, d_post, d_out[i % 2], sptr)
+
+        h_samples = torch.from_numpy(samples_h).pin_memory()
+        h_out = torch.empty((T, 12000), dtype=torch.float32).pin_memory()
+
+        def e2e_fn():
+            pipeline.nn_score_utterances(fe, pp, sc, h_samples, offs, out=h_out)
+
+        h2d, d2h = samples_h.size * 4, T * 12000 * 4
+        units = T
+        workload = "C4 from audio: MFCC -> CMVN -> 11-frame window -> Nn 429 -> 6x2048 -> 12000, %d utterances x 1000 frames per GPU" % n_utt
+        algo_bytes = (160 * 4 + 12000 * 4) * T
+        bound, dtype = "tensor", "bf16"
     else:  # nn
         T = args.frames or 65536
         net = synth.network()

@@ -257,6 +257,14 @@ int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samples, const 
 int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, const int64_t* offsets, int n_utt,
                           float* d_feats, float* d_scores, void* stream);
 
+/* audio -> MFCC -> (rb_postproc, may be NULL) -> Nn scores (config C4 fed from audio).  scores [frames * n_outputs];
+ * the device variant needs d_feats [frames * feat_dim] and, with a post-processor, d_post [frames * dim_out]. */
+int rb_pipeline_nn_score(rb_frontend* fe, rb_postproc* pp, rb_nn* nn, const float* samples, const int64_t* offsets,
+                         int n_utt, float* scores);
+int rb_pipeline_nn_score_dev(rb_frontend* fe, rb_postproc* pp, rb_nn* nn, const float* d_samples,
+                             const int64_t* offsets, int n_utt, float* d_feats, float* d_post, float* d_scores,
+                             void* stream);
+
 /* =====================================================================================
  * Test hook: one bf16 tcgen05 GEMM  D[M x N] = A[M x K] * B[N x K]^T (+bias, activation),
  * A/B f32 on the host, rounded to bf16 on the device.  Used by tests/ only.

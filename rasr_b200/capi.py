@@ -30,6 +30,7 @@ SYMBOLS = [
     "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
+    "rb_pipeline_nn_score", "rb_pipeline_nn_score_dev",
     "rb_postproc_create", "rb_postproc_destroy", "rb_postproc_dim_out", "rb_postproc_process", "rb_postproc_process_dev",
 ]
 
@@ -129,6 +130,8 @@ def lib():
     L.rb_nn_forward_dev.argtypes = [vp, vp, C.c_long, vp, vp]
     L.rb_pipeline_score.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
     L.rb_pipeline_score_dev.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp]
+    L.rb_pipeline_nn_score.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.rb_pipeline_nn_score_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     L.rb_postproc_create.argtypes = [C.POINTER(PostprocCfg), C.c_int, C.POINTER(vp)]
     L.rb_postproc_destroy.argtypes = [vp]
     L.rb_postproc_destroy.restype = None

@@ -6,7 +6,7 @@
 
 namespace {
 struct Scratch {
-    rb::DevBuf<float> samples, feats, scores;
+    rb::DevBuf<float> samples, feats, post, scores;
 };
 // one scratch set per front-end handle would be cleaner; pipelines are few, so key by handle
 Scratch& scratch_for(const rb_frontend* fe) {
@@ -107,6 +107,120 @@ extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samp
     for (int i = 0; i < nSlabs; ++i) {
         cudaEventDestroy(evIn[i]);
         cudaEventDestroy(evK[i]);
+    }
+    cudaStreamDestroy(sIn);
+    cudaStreamDestroy(sOut);
+    if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
+        rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != RB_OK)
+        return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        rb::set_error("pipeline failed on the device: %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
+    return RB_OK;
+}
+
+// =====================================================================================================
+// audio -> MFCC -> (normalisation / splice / matrix) -> Nn scores: the C4 model fed from audio.  Same structure
+// as the GMM pipeline above; the post-processing handle may be NULL (features go to the network as they are).
+// =====================================================================================================
+extern "C" int rb_pipeline_nn_score_dev(rb_frontend* fe, rb_postproc* pp, rb_nn* nn, const float* d_samples,
+                                        const int64_t* offsets, int n_utt, float* d_feats, float* d_post,
+                                        float* d_scores, void* stream) {
+    RB_REQUIRE(fe && nn && offsets && n_utt >= 0, "bad argument");
+    const int D = rb_frontend_feat_dim(fe), Dp = pp ? rb_postproc_dim_out(pp) : D;
+    RB_REQUIRE(Dp == rb_nn_n_inputs(nn), "the network expects %d-dim input, the feature pipeline emits %d",
+               rb_nn_n_inputs(nn), Dp);
+    if (n_utt == 0)
+        return RB_OK;
+    std::vector<int64_t> fo(n_utt + 1);
+    const long T = rb_frontend_count_frames(fe, offsets, n_utt, fo.data());
+    RB_REQUIRE(T >= 0, "bad offsets");
+    if (T == 0)
+        return RB_OK;
+    RB_REQUIRE(d_samples && d_feats && d_scores && (d_post || !pp), "NULL device buffer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : rb_frontend_stream(fe);
+    RB_CHECK(rb_frontend_process_dev(fe, d_samples, offsets, n_utt, d_feats, s));
+    const float* in = d_feats;
+    if (pp) {
+        RB_CHECK(rb_postproc_process_dev(pp, d_feats, fo.data(), n_utt, d_post, s));
+        in = d_post;
+    }
+    return rb_nn_score_dev(nn, in, T, d_scores, s);
+}
+
+extern "C" int rb_pipeline_nn_score(rb_frontend* fe, rb_postproc* pp, rb_nn* nn, const float* samples,
+                                    const int64_t* offsets, int n_utt, float* scores) {
+    RB_REQUIRE(fe && nn && offsets && n_utt >= 0, "bad argument");
+    if (n_utt == 0)
+        return RB_OK;
+    const int64_t base = offsets[0], nS = offsets[n_utt] - base;
+    RB_REQUIRE(nS >= 0 && (samples || nS == 0), "bad sample buffer");
+    std::vector<int64_t> rel(n_utt + 1), fo(n_utt + 1);
+    for (int u = 0; u <= n_utt; ++u)
+        rel[u] = offsets[u] - base;
+    const long T = rb_frontend_count_frames(fe, rel.data(), n_utt, fo.data());
+    if (T <= 0)
+        return T == 0 ? RB_OK : RB_ERR_INVALID;
+    RB_REQUIRE(scores != nullptr, "NULL score buffer");
+    RB_CUDA(cudaSetDevice(rb_frontend_device(fe).ordinal));
+    Scratch&     sc = scratch_for(fe);
+    const int    D = rb_frontend_feat_dim(fe), Dp = pp ? rb_postproc_dim_out(pp) : D, M = rb_nn_n_outputs(nn);
+    cudaStream_t sK = rb_frontend_stream(fe);
+    // slabs of whole utterances, ~16384 frames each: the f32 score slab (48 KB per frame for 12k senones) is what
+    // bounds the size, and its D2H copy is what bounds the call
+    const long       target = 16384;
+    std::vector<int> cut(1, 0);
+    for (int u = 1; u <= n_utt; ++u)
+        if (u == n_utt || fo[u] - fo[cut.back()] >= target)
+            cut.push_back(u);
+    const int nSlabs = (int)cut.size() - 1;
+    long      maxSlab = 0;
+    for (int i = 0; i < nSlabs; ++i)
+        maxSlab = std::max<long>(maxSlab, (long)(fo[cut[i + 1]] - fo[cut[i]]));
+    RB_CHECK(sc.samples.reserve((size_t)nS + 8));
+    RB_CHECK(sc.feats.reserve((size_t)T * D));
+    RB_CHECK(sc.post.reserve((size_t)(pp ? T : 1) * Dp));
+    RB_CHECK(sc.scores.reserve((size_t)2 * maxSlab * M));  // two slabs in flight: scoring of i, D2H of i-1
+    cudaStream_t sIn = nullptr, sOut = nullptr;
+    RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> evIn(nSlabs), evK(nSlabs), evOut(nSlabs);
+    for (int i = 0; i < nSlabs; ++i) {
+        cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&evOut[i], cudaEventDisableTiming);
+    }
+    int rc = RB_OK;
+    for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
+        const int     u0 = cut[i], u1 = cut[i + 1];
+        const int64_t sA = rel[u0], sB = rel[u1], fA = fo[u0], fB = fo[u1];
+        float*        dScores = sc.scores.p + (size_t)(i & 1) * maxSlab * M;
+        if (sB > sA && cudaMemcpyAsync(sc.samples.p + sA, samples + base + sA, (size_t)(sB - sA) * 4,
+                                       cudaMemcpyHostToDevice, sIn) != cudaSuccess)
+            rc = RB_ERR_CUDA;
+        cudaEventRecord(evIn[i], sIn);
+        cudaStreamWaitEvent(sK, evIn[i], 0);
+        if (i >= 2)
+            cudaStreamWaitEvent(sK, evOut[i - 2], 0);  // the score buffer of slab i-2 has been copied out
+        if (rc == RB_OK && fB > fA)
+            rc = rb_pipeline_nn_score_dev(fe, pp, nn, sc.samples.p, rel.data() + u0, u1 - u0, sc.feats.p + fA * D,
+                                          pp ? sc.post.p + fA * Dp : nullptr, dScores, sK);
+        cudaEventRecord(evK[i], sK);
+        cudaStreamWaitEvent(sOut, evK[i], 0);
+        if (rc == RB_OK && fB > fA &&
+            cudaMemcpyAsync(scores + fA * M, dScores, (size_t)(fB - fA) * M * 4, cudaMemcpyDeviceToHost, sOut) !=
+                    cudaSuccess)
+            rc = RB_ERR_CUDA;
+        cudaEventRecord(evOut[i], sOut);
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(sIn), e2 = cudaStreamSynchronize(sK), e3 = cudaStreamSynchronize(sOut);
+    for (int i = 0; i < nSlabs; ++i) {
+        cudaEventDestroy(evIn[i]);
+        cudaEventDestroy(evK[i]);
+        cudaEventDestroy(evOut[i]);
     }
     cudaStreamDestroy(sIn);
     cudaStreamDestroy(sOut);

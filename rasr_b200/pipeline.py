@@ -32,6 +32,28 @@ def score_utterances_dev(frontend, gmm, d_samples, offsets, d_feats, d_scores, s
                                                 capi.ptr(stream)))
 
 
+def nn_score_utterances(frontend, postproc, nn, samples, offsets, out=None):
+    """audio -> MFCC -> post-processing (may be None) -> Nn scores; host buffers in, [total_frames x n_outputs] out."""
+    if isinstance(samples, np.ndarray) or not hasattr(samples, "data_ptr"):
+        samples = np.ascontiguousarray(samples, np.float32)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    fo = frontend.count_frames(offsets)
+    T = int(fo[-1])
+    scores = out if out is not None else np.zeros((T, nn.n_outputs), np.float32)
+    capi.check(capi.lib().rb_pipeline_nn_score(frontend.handle, postproc.handle if postproc else None, nn.handle,
+                                               capi.ptr(samples), capi.ptr(offsets), offsets.size - 1,
+                                               capi.ptr(scores)))
+    return scores, fo
+
+
+def nn_score_utterances_dev(frontend, postproc, nn, d_samples, offsets, d_feats, d_post, d_scores, stream=None):
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    capi.check(capi.lib().rb_pipeline_nn_score_dev(frontend.handle, postproc.handle if postproc else None, nn.handle,
+                                                   capi.ptr(d_samples), capi.ptr(offsets), offsets.size - 1,
+                                                   capi.ptr(d_feats), capi.ptr(d_post), capi.ptr(d_scores),
+                                                   capi.ptr(stream)))
+
+
 def partition(lengths, world_size):
     """Assign utterances to ranks: longest first onto the least loaded rank.  Returns a list of index
     arrays (one per rank, each sorted ascending so a rank walks the corpus in order)."""

@@ -34,3 +34,36 @@ def test_launch_counter_moves():
     before = capi.launch_count()
     flow.FrontEnd().process(synth.utterance(4000))
     assert capi.launch_count() >= before + 2
+
+
+def test_audio_to_nn_scores_pipeline(oracle, diag):
+    """audio -> MFCC -> segment CMVN -> 11-frame window (429 dims) -> Nn scores in one call equals the stages run one
+    by one through their own entry points, and the oracle chain within the bf16 tolerance of test_gpu_nn.py."""
+    from rasr_b200 import nn, postproc
+
+    samples, offs = synth.corpus(5, n_samples=24240)
+    fe = flow.FrontEnd()
+    pp = postproc.PostProcessor(39, "mean-and-variance", splice=(11, 5))
+    net = synth.network(dims=(429, 512, 1000), seed=3)
+    sc = nn.NnScorer(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, "bf16")
+    scores, fo = pipeline.nn_score_utterances(fe, pp, sc, samples, offs)
+    r = fe.process(samples, offs)
+    x = pp.process(r["feats"], r["frame_offsets"])
+    assert x.shape[1] == 429
+    assert np.array_equal(scores, sc.score(x))
+    # oracle chain on the first utterance
+    T0 = int(fo[1])
+    of = oracle.mfcc(oracle.frontend_cfg(), samples[:offs[1]])["feats"]
+    ox = oracle.splice(oracle.normalize(of, kind="mean-and-variance"), 11, 5)
+    want = oracle.nn_scores(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, ox,
+                            mode=oracle.NN_BF16)
+    err = np.abs(scores[:T0] - want).max() / np.abs(want).max()
+    diag("pipeline_audio_to_nn", err=err)
+    assert err < 3e-3
+    # without a post-processor the network must take the raw feature dimension
+    net39 = synth.network(dims=(39, 64, 100), seed=4)
+    sc39 = nn.NnScorer(net39["dims"], net39["acts"], net39["weights"], net39["biases"], net39["log_prior"], 1.0, "bf16")
+    s2, _ = pipeline.nn_score_utterances(fe, None, sc39, samples, offs)
+    assert np.array_equal(s2, sc39.score(r["feats"]))
+    with pytest.raises(Exception):
+        pipeline.nn_score_utterances(fe, None, sc, samples, offs)  # 39-dim features into a 429-dim network
