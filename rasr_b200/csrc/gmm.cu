@@ -33,7 +33,7 @@ constexpr int kThreads        = 256;
 constexpr int kFramesPerThr   = 2;
 constexpr int kFramesPerBlock = kThreads * kFramesPerThr;  // 512
 constexpr int kStages         = 3;
-constexpr int kChunkRows      = 32;  // density rows per pipeline stage
+constexpr int kChunkRows      = 64;  // density rows per pipeline stage (64: +1 % over 32, 16: -2 %)
 
 struct GmmParams {
     const float*    rows;      // [nRows * rowf]

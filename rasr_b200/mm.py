@@ -32,6 +32,13 @@ class MixtureSet:
     def from_dict(cls, d):
         return cls(**d)
 
+    @classmethod
+    def read(cls, path):
+        """Load a mixture text file (".pms" / ".pms.gz", doc/file_formats/mixture_file.rst) -- rasr_b200.io"""
+        from . import io as rio
+
+        return cls(**rio.read_mixture_set(path))
+
     @property
     def n_mixtures(self):
         return self.mix_offsets.size - 1
