@@ -549,6 +549,10 @@ struct rb_gmm {
 
     std::vector<int> rowsOfMixture;  // rows each mixture occupies (>= 1)
     int              curGroups = -1;
+    std::vector<int> groupsOf;       // number of groups the table built for G actually has
+    // host-pointer entry point: copy streams and events are created once
+    cudaStream_t             sIn = nullptr, sOut = nullptr;
+    std::vector<cudaEvent_t> events;
 
     rb::DevBuf<float>    dRows, dIsd;
     rb::DevBuf<int>      dGrpRow, dGrpMix;
@@ -563,6 +567,12 @@ struct rb_gmm {
             rb_gmm_tensor_destroy(tensor);
         if (quantised)
             rb_gmm_int_destroy(quantised);
+        for (cudaEvent_t e : events)
+            cudaEventDestroy(e);
+        if (sIn)
+            cudaStreamDestroy(sIn);
+        if (sOut)
+            cudaStreamDestroy(sOut);
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -730,6 +740,8 @@ void make_groups(const rb_gmm* h, int G, std::vector<int>& grpRow, std::vector<i
     grpMix.push_back(nMix);
 }
 
+constexpr int kMaxGroups = 64, kGroupStride = kMaxGroups + 2;
+
 int choose_groups(const rb_gmm* h, long T, int slots, int framesPerBlock, double* effOut = nullptr) {
     const long FB   = (T + framesPerBlock - 1) / framesPerBlock;
     const int  gmax = std::max(1, std::min(64, std::min(h->nMix / 4, h->nRows / 128)));
@@ -771,21 +783,11 @@ int launch_simt(rb_gmm* h, const float* dFeats, long T, float* dScores, uint32_t
     }
     const int slots = h->dev.sm_count * h->ctasPerSm;
     const int G     = choose_groups(h, T, slots, h->framesPerBlock);
-    if (G != h->curGroups) {
-        std::vector<int> grpRow, grpMix;
-        make_groups(h, G, grpRow, grpMix);
-        // synchronous small copies: the tables must not be overwritten while a previous launch reads them
-        RB_CUDA(cudaStreamSynchronize(s));
-        RB_CHECK(h->dGrpRow.reserve(66));
-        RB_CHECK(h->dGrpMix.reserve(66));
-        RB_CUDA(cudaMemcpy(h->dGrpRow.p, grpRow.data(), grpRow.size() * sizeof(int), cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(h->dGrpMix.p, grpMix.data(), grpMix.size() * sizeof(int), cudaMemcpyHostToDevice));
-        h->curGroups = (int)grpRow.size() - 1;
-    }
+    h->curGroups    = h->groupsOf[G];  // make_groups may return fewer groups than asked for
     GmmParams p;
     p.rows         = h->dRows.p;
-    p.grp_row      = h->dGrpRow.p;
-    p.grp_mix      = h->dGrpMix.p;
+    p.grp_row      = h->dGrpRow.p + (size_t)G * kGroupStride;  // tables of every G live on the device (rb_gmm_create)
+    p.grp_mix      = h->dGrpMix.p + (size_t)G * kGroupStride;
     p.isd          = h->dIsd.p;
     p.feats        = dFeats;
     p.scores       = dScores;
@@ -908,6 +910,19 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         }
         h->variants[v].ctasPerSm = occ;
     }
+    {  // group tables for every group count, so that a launch never has to touch them
+        std::vector<int> allRow((size_t)(kMaxGroups + 1) * kGroupStride, 0), allMix(allRow.size(), 0);
+        h->groupsOf.assign(kMaxGroups + 1, 1);
+        for (int G = 1; G <= kMaxGroups; ++G) {
+            std::vector<int> grpRow, grpMix;
+            make_groups(h, G, grpRow, grpMix);
+            std::copy(grpRow.begin(), grpRow.end(), allRow.begin() + (size_t)G * kGroupStride);
+            std::copy(grpMix.begin(), grpMix.end(), allMix.begin() + (size_t)G * kGroupStride);
+            h->groupsOf[G] = (int)grpRow.size() - 1;
+        }
+        if (h->dGrpRow.upload(allRow, h->stream) != RB_OK || h->dGrpMix.upload(allMix, h->stream) != RB_OK)
+            return fail(RB_ERR_CUDA);
+    }
     if (h->dRows.upload(rows, h->stream) != RB_OK || h->dIsd.upload(isd, h->stream) != RB_OK)
         return fail(RB_ERR_CUDA);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
@@ -977,30 +992,37 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     if (best_density)
         RB_CHECK(h->dBest.reserve((size_t)T * M));
 
-    // slabs: multiples of the frame block, ~16 per call but at least 8192 frames each
-    long slab = std::max<long>(8192, rb::round_up((size_t)((T + 15) / 16), kFramesPerBlock));
-    const int nSlabs = (int)((T + slab - 1) / slab);
-    cudaStream_t sIn = nullptr, sOut = nullptr;
-    RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
-    RB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> evIn(nSlabs), evK(nSlabs);
-    int                      rc = RB_OK;
-    for (int i = 0; i < nSlabs; ++i) {
-        cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming);
+    // slabs: H2D of slab i+1, scoring of slab i and D2H of slab i-1 overlap.  The call is bound by the D2H stream
+    // (1 KB of scores per frame), so the first slabs are small (the D2H stream starts early) and grow geometrically
+    // to 16384 frames (large copies run closer to the PCIe rate)
+    std::vector<long> cut(1, 0);
+    for (long n = 2048; cut.back() < T; n = std::min<long>(2 * n, 16384))
+        cut.push_back(std::min(T, cut.back() + n));
+    const int nSlabs = (int)cut.size() - 1;
+    if (!h->sIn) {
+        RB_CUDA(cudaStreamCreateWithFlags(&h->sIn, cudaStreamNonBlocking));
+        RB_CUDA(cudaStreamCreateWithFlags(&h->sOut, cudaStreamNonBlocking));
     }
+    while ((int)h->events.size() < 2 * nSlabs) {
+        cudaEvent_t e;
+        RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->events.push_back(e);
+    }
+    cudaStream_t sIn = h->sIn, sOut = h->sOut;
+    int          rc = RB_OK;
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
-        const long a = (long)i * slab, n = std::min<long>(slab, T - a);
+        const long  a = cut[i], n = cut[i + 1] - cut[i];
+        cudaEvent_t evIn = h->events[2 * i], evK = h->events[2 * i + 1];
         if (cudaMemcpyAsync(h->dFeats.p + a * D, feats + a * D, (size_t)n * D * 4, cudaMemcpyHostToDevice, sIn) !=
             cudaSuccess)
             rc = RB_ERR_CUDA;
-        cudaEventRecord(evIn[i], sIn);
-        cudaStreamWaitEvent(h->stream, evIn[i], 0);
+        cudaEventRecord(evIn, sIn);
+        cudaStreamWaitEvent(h->stream, evIn, 0);
         if (rc == RB_OK)
             rc = rb_gmm_score_dev(h, h->dFeats.p + a * D, n, h->dScores.p + a * M,
                                   best_density ? h->dBest.p + a * M : nullptr, h->stream);
-        cudaEventRecord(evK[i], h->stream);
-        cudaStreamWaitEvent(sOut, evK[i], 0);
+        cudaEventRecord(evK, h->stream);
+        cudaStreamWaitEvent(sOut, evK, 0);
         if (rc == RB_OK &&
             cudaMemcpyAsync(scores + a * M, h->dScores.p + a * M, (size_t)n * M * 4, cudaMemcpyDeviceToHost, sOut) !=
                     cudaSuccess)
@@ -1013,12 +1035,6 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     cudaError_t e1 = cudaStreamSynchronize(sIn);
     cudaError_t e2 = cudaStreamSynchronize(h->stream);
     cudaError_t e3 = cudaStreamSynchronize(sOut);
-    for (int i = 0; i < nSlabs; ++i) {
-        cudaEventDestroy(evIn[i]);
-        cudaEventDestroy(evK[i]);
-    }
-    cudaStreamDestroy(sIn);
-    cudaStreamDestroy(sOut);
     if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
         rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != RB_OK)

@@ -319,7 +319,7 @@ struct rb_gmm_int {
     int            dim = 0, nMix = 0, nTiles = 0, ctasPerSm = 1, curGroups = -1;
     float          scale = 1.0f, rcpScale = 0.0f;
     size_t         smemBytes = 0;
-    std::vector<int> tilesOfMixture;
+    std::vector<int> tilesOfMixture, groupsOf;
     rb::DevBuf<unsigned char> dTiles, dXq;
     rb::DevBuf<float>         dVariance;
     rb::DevBuf<int>           dXsq, dGrpTile, dGrpMix;
@@ -350,6 +350,8 @@ bool fast_division_exact_soft(float sc, float r) {
     }
     return ok;
 }
+
+constexpr int kMaxGroups = 64, kGroupStride = kMaxGroups + 2;
 
 void make_groups(const rb_gmm_int* h, int G, std::vector<int>& grpTile, std::vector<int>& grpMix) {
     grpTile.assign(1, 0);
@@ -492,6 +494,19 @@ int rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaS
         return fail(RB_ERR_CUDA);
     }
     h->ctasPerSm = occ;
+    {  // group tables for every group count: a launch never has to touch them
+        std::vector<int> allTile((size_t)(kMaxGroups + 1) * kGroupStride, 0), allMix(allTile.size(), 0);
+        h->groupsOf.assign(kMaxGroups + 1, 1);
+        for (int G = 1; G <= kMaxGroups; ++G) {
+            std::vector<int> grpTile, grpMix;
+            make_groups(h, G, grpTile, grpMix);
+            std::copy(grpTile.begin(), grpTile.end(), allTile.begin() + (size_t)G * kGroupStride);
+            std::copy(grpMix.begin(), grpMix.end(), allMix.begin() + (size_t)G * kGroupStride);
+            h->groupsOf[G] = (int)grpTile.size() - 1;
+        }
+        if (h->dGrpTile.upload(allTile, stream) != RB_OK || h->dGrpMix.upload(allMix, stream) != RB_OK)
+            return fail(RB_ERR_CUDA);
+    }
     if (h->dTiles.upload(tiles, stream) != RB_OK || h->dVariance.upload(variance, stream) != RB_OK)
         return fail(RB_ERR_CUDA);
     if (cudaStreamSynchronize(stream) != cudaSuccess) {
@@ -514,20 +529,11 @@ int rb_gmm_int_score(rb_gmm_int* h, const float* dFeats, long T, float* dScores,
     RB_LAUNCH_CHECK();
     const int slots = h->dev.sm_count * h->ctasPerSm;
     const int G     = choose_groups(h, T, slots);
-    if (G != h->curGroups) {
-        std::vector<int> grpTile, grpMix;
-        make_groups(h, G, grpTile, grpMix);
-        RB_CUDA(cudaStreamSynchronize(s));  // the tables must not change under a running launch
-        RB_CHECK(h->dGrpTile.reserve(66));
-        RB_CHECK(h->dGrpMix.reserve(66));
-        RB_CUDA(cudaMemcpy(h->dGrpTile.p, grpTile.data(), grpTile.size() * sizeof(int), cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(h->dGrpMix.p, grpMix.data(), grpMix.size() * sizeof(int), cudaMemcpyHostToDevice));
-        h->curGroups = (int)grpTile.size() - 1;
-    }
+    h->curGroups    = h->groupsOf[G];
     IntParams p;
     p.tiles        = h->dTiles.p;
-    p.grpTile      = h->dGrpTile.p;
-    p.grpMix       = h->dGrpMix.p;
+    p.grpTile      = h->dGrpTile.p + (size_t)G * kGroupStride;  // tables of every G live on the device
+    p.grpMix       = h->dGrpMix.p + (size_t)G * kGroupStride;
     p.xq           = h->dXq.p;
     p.xsq          = h->dXsq.p;
     p.scores       = dScores;
