@@ -242,10 +242,13 @@ def main():
 
             h_feats = torch.empty((T, 39), dtype=torch.float32).pin_memory()
 
-            def e2e_fn():
-                fe.process(h_samples, offs, timestamps=False, out=h_feats)
+            # end to end the audio arrives as 16-bit PCM (what the audio nodes deliver): 2 bytes per sample over PCIe
+            h_pcm = torch.from_numpy(samples_h.astype(np.int16)).pin_memory()
 
-            h2d, d2h = samples_h.size * 4, T * 39 * 4
+            def e2e_fn():
+                fe.process_s16(h_pcm, offs, timestamps=False, out=h_feats)
+
+            h2d, d2h = samples_h.size * 2, T * 39 * 4
         else:
             scorer = mm.GmmScorer(mm.MixtureSet.from_dict(synth.mixture_set()), device=local_rank)
             d_scores = [torch.empty((T, 256), dtype=torch.float32, device=dev) for _ in range(R)]

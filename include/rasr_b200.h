@@ -117,6 +117,12 @@ int rb_frontend_read(rb_frontend* h, float* feats, double* t_start, double* t_en
 long rb_frontend_count_frames(const rb_frontend* h, const int64_t* offsets, int n_utt, int64_t* frame_offsets);
 int  rb_frontend_process(rb_frontend* h, const float* samples, const int64_t* offsets, int n_utt, float* feats,
                          double* t_start, double* t_end);
+/* the same fed with 16-bit PCM as the audio nodes deliver it: interleaved s16 frames of n_channels channels, of which
+ * `track` is demultiplexed and converted (generic-vector-s16-demultiplex + generic-convert-vector-s16-to-vector-f32,
+ * src/Tools/FeatureExtraction/share/samples.flow:13-18); offsets count sample frames.  Halves the bytes that cross
+ * PCIe.  signal-dc-detection (samples.flow:35-37) is not applied. */
+int  rb_frontend_process_s16(rb_frontend* h, const int16_t* samples, int n_channels, int track, const int64_t* offsets,
+                             int n_utt, float* feats, double* t_start, double* t_end);
 /* device variant: d_samples / d_feats are device pointers, offsets stays on the host.
  * d_stage (optional, device, [total_frames*n_cepstra] floats) receives the static cepstra. */
 int rb_frontend_process_dev(rb_frontend* h, const float* d_samples, const int64_t* offsets, int n_utt,

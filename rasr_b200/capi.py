@@ -26,7 +26,7 @@ SYMBOLS = [
     "rb_frontend_default_cfg", "rb_frontend_create", "rb_frontend_destroy", "rb_frontend_get_geometry",
     "rb_frontend_get_tables", "rb_frontend_nframes_for", "rb_frontend_reset", "rb_frontend_push",
     "rb_frontend_finish", "rb_frontend_nframes", "rb_frontend_read", "rb_frontend_count_frames",
-    "rb_frontend_process", "rb_frontend_process_dev", "rb_frontend_set_debug", "rb_frontend_read_stages",
+    "rb_frontend_process", "rb_frontend_process_s16", "rb_frontend_process_dev", "rb_frontend_set_debug", "rb_frontend_read_stages",
     "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
@@ -108,6 +108,7 @@ def lib():
     L.rb_frontend_count_frames.argtypes = [vp, vp, C.c_int, vp]
     L.rb_frontend_count_frames.restype = C.c_long
     L.rb_frontend_process.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
+    L.rb_frontend_process_s16.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
     L.rb_frontend_process_dev.argtypes = [vp, vp, vp, C.c_int, vp, vp]
     L.rb_frontend_set_debug.argtypes = [vp, C.c_int]
     L.rb_frontend_read_stages.argtypes = [vp, vp, vp, vp]

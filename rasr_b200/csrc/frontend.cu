@@ -290,6 +290,14 @@ __global__ void __launch_bounds__(256) mfcc_derivative_kernel(const FeParams p) 
     }
 }
 
+// generic-vector-s16-demultiplex (track of an interleaved stream) + generic-convert-vector-s16-to-vector-f32
+// (src/Tools/FeatureExtraction/share/samples.flow:13-18, src/Flow/TypeConverter.hh:113): plain value conversion
+__global__ void __launch_bounds__(256) convert_s16_kernel(const int16_t* __restrict__ in, float* __restrict__ out,
+                                                          long n, int channels, int track) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = (float)in[i * channels + track];
+}
+
 #include "frontend_fft256.cuh"
 
 }  // namespace
@@ -323,6 +331,7 @@ struct rb_frontend {
     size_t     fastSmemBytes = 0;
     // device buffers
     rb::DevBuf<float>   dTables, dSamples, dCep, dFeats, dDbgAmp, dDbgFbank;
+    rb::DevBuf<int16_t> dPcm;  // interleaved s16 input of rb_frontend_process_s16
     static constexpr int kSlots = 4;
     struct StageSlot {
         rb::PinnedBuf<char> host;
@@ -937,15 +946,21 @@ extern "C" int rb_frontend_process_dev(rb_frontend* h, const float* d_samples, c
     return run_device(h, d_samples, offsets, n_utt, d_feats, stream ? (cudaStream_t)stream : h->stream, nullptr);
 }
 
-extern "C" int rb_frontend_process(rb_frontend* h, const float* samples, const int64_t* offsets, int n_utt,
-                                   float* feats, double* t_start, double* t_end) {
+namespace {
+// samples: f32 mono (channels == 0) or interleaved s16 with `channels` channels of which `track` is used
+int process_host(rb_frontend* h, const void* samplesRaw, int channels, int track, const int64_t* offsets, int n_utt,
+                 float* feats, double* t_start, double* t_end) {
     RB_REQUIRE(h && offsets && n_utt >= 0, "bad argument");
     if (n_utt == 0)
         return RB_OK;
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    const float*   samples = channels ? nullptr : static_cast<const float*>(samplesRaw);
+    const int16_t* pcm     = channels ? static_cast<const int16_t*>(samplesRaw) : nullptr;
     const int64_t base = offsets[0], nS = offsets[n_utt] - base;
     RB_REQUIRE(nS >= 0, "negative sample count");
-    RB_REQUIRE(samples || nS == 0, "NULL sample buffer");
+    RB_REQUIRE(samplesRaw || nS == 0, "NULL sample buffer");
+    if (channels)
+        RB_CHECK(h->dPcm.reserve((size_t)nS * channels));
     // slack so that the aligned bulk copies never leave the allocation
     RB_CHECK(h->dSamples.reserve((size_t)nS + 8));
     std::vector<int64_t> rel(n_utt + 1), fo(n_utt + 1);
@@ -973,11 +988,23 @@ extern "C" int rb_frontend_process(rb_frontend* h, const float* samples, const i
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const int     u0 = cut[i], u1 = cut[i + 1];
         const int64_t sA = rel[u0], sB = rel[u1], fA = fo[u0], fB = fo[u1];
-        if (sB > sA && cudaMemcpyAsync(h->dSamples.p + sA, samples + base + sA, (size_t)(sB - sA) * 4,
-                                       cudaMemcpyHostToDevice, sIn) != cudaSuccess)
-            rc = RB_ERR_CUDA;
+        if (sB > sA) {
+            const cudaError_t e =
+                    channels ? cudaMemcpyAsync(h->dPcm.p + sA * channels, pcm + (base + sA) * channels,
+                                               (size_t)(sB - sA) * channels * 2, cudaMemcpyHostToDevice, sIn)
+                             : cudaMemcpyAsync(h->dSamples.p + sA, samples + base + sA, (size_t)(sB - sA) * 4,
+                                               cudaMemcpyHostToDevice, sIn);
+            if (e != cudaSuccess)
+                rc = RB_ERR_CUDA;
+        }
         cudaEventRecord(evIn[i], sIn);
         cudaStreamWaitEvent(h->stream, evIn[i], 0);
+        if (rc == RB_OK && channels && sB > sA) {
+            const long n = (long)(sB - sA);
+            convert_s16_kernel<<<(int)std::min<long>((n + 255) / 256, (long)h->dev.sm_count * 8), 256, 0, h->stream>>>(
+                    h->dPcm.p + sA * channels, h->dSamples.p + sA, n, channels, track);
+            rb::count_launch();
+        }
         if (rc == RB_OK)
             rc = run_device(h, h->dSamples.p, rel.data() + u0, u1 - u0, h->dFeats.p + fA * h->featDim, h->stream,
                             nullptr);
@@ -1016,6 +1043,19 @@ extern "C" int rb_frontend_process(rb_frontend* h, const float* samples, const i
         }
     }
     return RB_OK;
+}
+}  // namespace
+
+extern "C" int rb_frontend_process(rb_frontend* h, const float* samples, const int64_t* offsets, int n_utt,
+                                   float* feats, double* t_start, double* t_end) {
+    return process_host(h, samples, 0, 0, offsets, n_utt, feats, t_start, t_end);
+}
+
+extern "C" int rb_frontend_process_s16(rb_frontend* h, const int16_t* samples, int n_channels, int track,
+                                       const int64_t* offsets, int n_utt, float* feats, double* t_start,
+                                       double* t_end) {
+    RB_REQUIRE(n_channels >= 1 && track >= 0 && track < n_channels, "track %d of %d channels", track, n_channels);
+    return process_host(h, samples, n_channels, track, offsets, n_utt, feats, t_start, t_end);
 }
 
 extern "C" int rb_frontend_reset(rb_frontend* h) {

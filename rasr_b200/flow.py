@@ -104,6 +104,25 @@ class FrontEnd:
                 L.rb_frontend_set_debug(self._h, 0)
         return out
 
+    def process_s16(self, pcm, offsets=None, n_channels=1, track=0, timestamps=True, out=None):
+        """16-bit PCM in (numpy int16 [frames] or [frames, n_channels] interleaved, or a pinned torch tensor);
+        demultiplexed and converted on the device (samples.flow:13-18)."""
+        if isinstance(pcm, np.ndarray) or not hasattr(pcm, "data_ptr"):
+            pcm = np.ascontiguousarray(pcm, np.int16)
+        n_frames = int(pcm.shape[0]) if len(pcm.shape) == 2 else int(pcm.shape[0]) // n_channels
+        if offsets is None:
+            offsets = np.array([0, n_frames], np.int64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        fo = self.count_frames(offsets)
+        T = int(fo[-1])
+        feats = out if out is not None else np.zeros((T, self.feat_dim), np.float32)
+        ts = np.zeros(T, np.float64) if timestamps else None
+        te = np.zeros(T, np.float64) if timestamps else None
+        capi.check(capi.lib().rb_frontend_process_s16(self._h, capi.ptr(pcm), int(n_channels), int(track),
+                                                      capi.ptr(offsets), offsets.size - 1, capi.ptr(feats),
+                                                      capi.ptr(ts), capi.ptr(te)))
+        return dict(feats=feats, frame_offsets=fo, t_start=ts, t_end=te)
+
     def process_dev(self, d_samples, offsets, d_feats, stream=None):
         """Device buffers (torch tensors or raw pointers); only enqueues + syncs the tile tables."""
         offsets = np.ascontiguousarray(offsets, np.int64)

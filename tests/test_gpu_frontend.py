@@ -165,3 +165,23 @@ def test_other_configurations(oracle, diag, kw):
     e = rel_err(r["feats"], o["feats"])
     diag("frontend_cfg", cfg=str(kw), err=e)
     assert e < RTOL
+
+
+def test_s16_pcm_input_equals_float_input():
+    """rb_frontend_process_s16: demultiplex + s16 -> f32 on the device (samples.flow:13-18) is a plain value
+    conversion, so the features are bit-identical to feeding the converted samples."""
+    samples, offs = synth.corpus(4, n_samples=20240)
+    assert np.array_equal(samples, np.round(samples)) and np.abs(samples).max() < 32768
+    fe = flow.FrontEnd()
+    want = fe.process(samples, offs)
+    mono = fe.process_s16(samples.astype(np.int16), offs)
+    assert np.array_equal(mono["feats"], want["feats"]) and np.array_equal(mono["t_start"], want["t_start"])
+    # track 1 of a 3-channel interleaved stream
+    pcm = np.zeros((samples.size, 3), np.int16)
+    pcm[:, 0] = 7
+    pcm[:, 1] = samples.astype(np.int16)
+    pcm[:, 2] = -samples.astype(np.int16)
+    multi = fe.process_s16(pcm, offs, n_channels=3, track=1)
+    assert np.array_equal(multi["feats"], want["feats"])
+    with pytest.raises(Exception):
+        fe.process_s16(pcm, offs, n_channels=3, track=3)
