@@ -260,6 +260,9 @@ int rb_postproc_process_dev(rb_postproc* h, const float* d_feats, const int64_t*
  * ===================================================================================== */
 int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samples, const int64_t* offsets, int n_utt,
                       float* scores, float* feats /* optional host copy */);
+/* the same fed with interleaved 16-bit PCM (see rb_frontend_process_s16) */
+int rb_pipeline_score_s16(rb_frontend* fe, rb_gmm* gmm, const int16_t* samples, int n_channels, int track,
+                          const int64_t* offsets, int n_utt, float* scores, float* feats /* optional host copy */);
 int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, const int64_t* offsets, int n_utt,
                           float* d_feats, float* d_scores, void* stream);
 

@@ -29,7 +29,7 @@ SYMBOLS = [
     "rb_frontend_process", "rb_frontend_process_s16", "rb_frontend_process_dev", "rb_frontend_set_debug", "rb_frontend_read_stages",
     "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_score", "rb_nn_score_dev",
-    "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
+    "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_s16", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
     "rb_pipeline_nn_score", "rb_pipeline_nn_score_dev",
     "rb_postproc_create", "rb_postproc_destroy", "rb_postproc_dim_out", "rb_postproc_process", "rb_postproc_process_dev",
 ]
@@ -130,6 +130,7 @@ def lib():
     L.rb_nn_forward.argtypes = [vp, vp, C.c_long, vp]
     L.rb_nn_forward_dev.argtypes = [vp, vp, C.c_long, vp, vp]
     L.rb_pipeline_score.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+    L.rb_pipeline_score_s16.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]
     L.rb_pipeline_score_dev.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp]
     L.rb_pipeline_nn_score.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.rb_pipeline_nn_score_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]

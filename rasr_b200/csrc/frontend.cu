@@ -1143,6 +1143,17 @@ extern "C" int rb_frontend_read_stages(rb_frontend* h, float* amplitude, float* 
     return RB_OK;
 }
 
+// s16 -> f32 of one track on the device (pipeline.cu)
+int rb_frontend_convert_s16_dev(const rb_frontend* h, const int16_t* d_pcm, float* d_out, long n, int channels,
+                                int track, cudaStream_t s) {
+    if (n <= 0)
+        return RB_OK;
+    convert_s16_kernel<<<(int)std::min<long>((n + 255) / 256, (long)h->dev.sm_count * 8), 256, 0, s>>>(d_pcm, d_out, n,
+                                                                                                      channels, track);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
 // accessors for pipeline.cu
 rb::DeviceInfo rb_frontend_device(const rb_frontend* h) {
     return h->dev;

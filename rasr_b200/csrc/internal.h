@@ -8,3 +8,5 @@ struct rb_gmm;
 cudaStream_t   rb_frontend_stream(const rb_frontend* h);
 rb::DeviceInfo rb_frontend_device(const rb_frontend* h);
 int            rb_frontend_feat_dim(const rb_frontend* h);
+int            rb_frontend_convert_s16_dev(const rb_frontend* h, const int16_t* d_pcm, float* d_out, long n, int channels,
+                                           int track, cudaStream_t s);

@@ -6,7 +6,8 @@
 
 namespace {
 struct Scratch {
-    rb::DevBuf<float> samples, feats, post, scores;
+    rb::DevBuf<float>   samples, feats, post, scores;
+    rb::DevBuf<int16_t> pcm;
 };
 // one scratch set per front-end handle would be cleaner; pipelines are few, so key by handle
 Scratch& scratch_for(const rb_frontend* fe) {
@@ -40,13 +41,17 @@ extern "C" int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* 
 // Host-pointer entry point: the utterances are cut into slabs (whole utterances, ~8 per call); H2D of slab i+1,
 // front-end + scoring of slab i and D2H of slab i-1 overlap on three streams.  PCIe is the end-to-end bound
 // (640 B of samples in, 1 KB of scores out per frame).
-extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samples, const int64_t* offsets, int n_utt,
-                                 float* scores, float* feats) {
+namespace {
+// samples: f32 mono (channels == 0) or interleaved s16 with `channels` channels of which `track` is used
+int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, int channels, int track,
+                        const int64_t* offsets, int n_utt, float* scores, float* feats) {
     RB_REQUIRE(fe && gmm && offsets && n_utt >= 0, "bad argument");
     if (n_utt == 0)
         return RB_OK;
+    const float*   samples = channels ? nullptr : static_cast<const float*>(samplesRaw);
+    const int16_t* pcm     = channels ? static_cast<const int16_t*>(samplesRaw) : nullptr;
     const int64_t base = offsets[0], nS = offsets[n_utt] - base;
-    RB_REQUIRE(nS >= 0 && (samples || nS == 0), "bad sample buffer");
+    RB_REQUIRE(nS >= 0 && (samplesRaw || nS == 0), "bad sample buffer");
     std::vector<int64_t> rel(n_utt + 1), fo(n_utt + 1);
     for (int u = 0; u <= n_utt; ++u)
         rel[u] = offsets[u] - base;
@@ -61,13 +66,18 @@ extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samp
     RB_CHECK(sc.samples.reserve((size_t)nS + 8));
     RB_CHECK(sc.feats.reserve((size_t)T * D));
     RB_CHECK(sc.scores.reserve((size_t)T * M));
+    if (channels)
+        RB_CHECK(sc.pcm.reserve((size_t)nS * channels));
 
-    // slab boundaries (utterance indices): about T/8 frames each, at least 8192
-    const long       target = std::max<long>(8192, (T + 7) / 8);
+    // slab boundaries (utterance indices).  The call is bound by the D2H stream of the scores, so the first slabs are
+    // small (the D2H stream starts early) and grow geometrically to ~16384 frames
     std::vector<int> cut(1, 0);
+    long             target = 2048;
     for (int u = 1; u <= n_utt; ++u)
-        if (u == n_utt || fo[u] - fo[cut.back()] >= target)
+        if (u == n_utt || fo[u] - fo[cut.back()] >= target) {
             cut.push_back(u);
+            target = std::min<long>(2 * target, 16384);
+        }
     const int    nSlabs = (int)cut.size() - 1;
     cudaStream_t sIn = nullptr, sOut = nullptr;
     RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
@@ -84,11 +94,20 @@ extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samp
         // they are either the previous slab's (already ordered on sK) or padding, and never used
         const int64_t sA = rel[u0], sB = rel[u1];
         const int64_t fA = fo[u0], fB = fo[u1];
-        if (sB > sA && cudaMemcpyAsync(sc.samples.p + sA, samples + base + sA, (size_t)(sB - sA) * 4,
-                                       cudaMemcpyHostToDevice, sIn) != cudaSuccess)
-            rc = RB_ERR_CUDA;
+        if (sB > sA) {
+            const cudaError_t e =
+                    channels ? cudaMemcpyAsync(sc.pcm.p + sA * channels, pcm + (base + sA) * channels,
+                                               (size_t)(sB - sA) * channels * 2, cudaMemcpyHostToDevice, sIn)
+                             : cudaMemcpyAsync(sc.samples.p + sA, samples + base + sA, (size_t)(sB - sA) * 4,
+                                               cudaMemcpyHostToDevice, sIn);
+            if (e != cudaSuccess)
+                rc = RB_ERR_CUDA;
+        }
         cudaEventRecord(evIn[i], sIn);
         cudaStreamWaitEvent(sK, evIn[i], 0);
+        if (rc == RB_OK && channels)
+            rc = rb_frontend_convert_s16_dev(fe, sc.pcm.p + sA * channels, sc.samples.p + sA, (long)(sB - sA), channels,
+                                             track, sK);
         if (rc == RB_OK && fB > fA)
             rc = rb_pipeline_score_dev(fe, gmm, sc.samples.p, rel.data() + u0, u1 - u0, sc.feats.p + fA * D,
                                        sc.scores.p + fA * M, sK);
@@ -120,6 +139,18 @@ extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samp
         return RB_ERR_CUDA;
     }
     return RB_OK;
+}
+}  // namespace
+
+extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samples, const int64_t* offsets, int n_utt,
+                                 float* scores, float* feats) {
+    return pipeline_score_host(fe, gmm, samples, 0, 0, offsets, n_utt, scores, feats);
+}
+
+extern "C" int rb_pipeline_score_s16(rb_frontend* fe, rb_gmm* gmm, const int16_t* samples, int n_channels, int track,
+                                     const int64_t* offsets, int n_utt, float* scores, float* feats) {
+    RB_REQUIRE(n_channels >= 1 && track >= 0 && track < n_channels, "track %d of %d channels", track, n_channels);
+    return pipeline_score_host(fe, gmm, samples, n_channels, track, offsets, n_utt, scores, feats);
 }
 
 // =====================================================================================================

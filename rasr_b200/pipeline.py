@@ -10,18 +10,23 @@ import numpy as np
 from . import capi
 
 
-def score_utterances(frontend, gmm, samples, offsets, want_feats=False, out=None):
+def score_utterances(frontend, gmm, samples, offsets, want_feats=False, out=None, pcm_channels=0, track=0):
     """Host buffers in (numpy, or pinned torch CPU tensors), scores [total_frames x n_mixtures] out (`out` if
-    given); features stay on the device."""
+    given); features stay on the device.  pcm_channels > 0: `samples` is interleaved 16-bit PCM."""
     if isinstance(samples, np.ndarray) or not hasattr(samples, "data_ptr"):
-        samples = np.ascontiguousarray(samples, np.float32)
+        samples = np.ascontiguousarray(samples, np.int16 if pcm_channels else np.float32)
     offsets = np.ascontiguousarray(offsets, np.int64)
     fo = frontend.count_frames(offsets)
     T = int(fo[-1])
     scores = out if out is not None else np.zeros((T, gmm.n_mixtures), np.float32)
     feats = np.zeros((T, frontend.feat_dim), np.float32) if want_feats else None
-    capi.check(capi.lib().rb_pipeline_score(frontend.handle, gmm.handle, capi.ptr(samples), capi.ptr(offsets),
-                                            offsets.size - 1, capi.ptr(scores), capi.ptr(feats)))
+    if pcm_channels:
+        capi.check(capi.lib().rb_pipeline_score_s16(frontend.handle, gmm.handle, capi.ptr(samples), int(pcm_channels),
+                                                    int(track), capi.ptr(offsets), offsets.size - 1, capi.ptr(scores),
+                                                    capi.ptr(feats)))
+    else:
+        capi.check(capi.lib().rb_pipeline_score(frontend.handle, gmm.handle, capi.ptr(samples), capi.ptr(offsets),
+                                                offsets.size - 1, capi.ptr(scores), capi.ptr(feats)))
     return (scores, feats, fo) if want_feats else (scores, fo)
 
 

@@ -26,6 +26,9 @@ def test_pipeline_equals_frontend_then_scorer(oracle, diag):
     assert rel.max() < 1e-4
     # scoring the GPU features with the oracle is bit-identical (isolates the scorer)
     assert np.array_equal(scores[:T0], oracle.gmm_batch_float(oms, feats[:T0]))
+    # 16-bit PCM input (the synthetic audio is integer valued): identical scores
+    s16, _ = pipeline.score_utterances(fe, gmm, samples.astype(np.int16), offs, pcm_channels=1)
+    assert np.array_equal(s16, scores)
 
 
 def test_launch_counter_moves():
