@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "gmm-int", "frontend", "pipeline", "pipeline-nn", "nn"])
+    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "gmm-int", "frontend", "pipeline", "pipeline-nn", "pipeline-search", "nn"])
     ap.add_argument("--frames", type=int, default=0, help="override the frame count of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -267,6 +267,39 @@ def main():
         units = T
         workload = "C3 shard: %s on %d utterances x 1000 frames per GPU (%d frames)" % (wl, n_utt, T)
         algo_bytes = ALGO_BYTES_PER_FRAME[wl] * T
+        bound, dtype = "hbm", "f32"
+    elif wl == "pipeline-search":
+        # C5: audio -> MFCC -> GMM scores -> Search::LinearSearch (1000-word synthetic lexicon), scores never leave HBM
+        from rasr_b200 import search
+        n_utt = max(1, (args.frames or 125000) // 1000)
+        samples_h, offs = synth.corpus(n_utt, n_samples=160240, seed0=3000 + 1000 * rank)
+        fe = flow.FrontEnd(device=local_rank)
+        scorer = mm.GmmScorer(mm.MixtureSet.from_dict(synth.mixture_set()), device=local_rank)
+        ls = search.LinearSearch(synth.lexicon(1000, 256), device=local_rank)
+        fo = fe.count_frames(offs)
+        T = int(fo[-1])
+        d_samples = [torch.from_numpy(samples_h).to(dev) for _ in range(R)]
+        d_feats = torch.empty((T, 39), dtype=torch.float32, device=dev)
+        d_scores = torch.empty((T, 256), dtype=torch.float32, device=dev)
+
+        def step(i):
+            pipeline.score_utterances_dev(fe, scorer, d_samples[i % R], offs, d_feats, d_scores, sptr)
+            ls.decode_dev(d_scores, 256, fo, sptr, want_result=False)
+
+        h_pcm = torch.from_numpy(samples_h.astype(np.int16)).pin_memory()
+        d_pcm_f = torch.empty(samples_h.size, dtype=torch.float32, device=dev)
+
+        def e2e_fn():
+            # 16-bit PCM in, word sequences out: H2D of the audio, conversion, the three stages, tracebacks to the host
+            d_pcm_f.copy_(h_pcm.to(dev, non_blocking=True))
+            torch.cuda.current_stream().synchronize()
+            pipeline.score_utterances_dev(fe, scorer, d_pcm_f, offs, d_feats, d_scores, sptr)
+            return ls.decode_dev(d_scores, 256, fo, sptr)
+
+        h2d, d2h = samples_h.size * 2, T * 20
+        units = T
+        workload = "C5: MFCC -> GMM scores -> LinearSearch (1000 words), %d utterances x 1000 frames per GPU" % n_utt
+        algo_bytes = ALGO_BYTES_PER_FRAME["pipeline"] * T
         bound, dtype = "hbm", "f32"
     elif wl == "pipeline-nn":
         # C4 fed from audio: MFCC -> segment CMVN -> 11-frame window -> 6 x 2048 -> 12000 senone scores

@@ -275,6 +275,40 @@ int rb_pipeline_nn_score_dev(rb_frontend* fe, rb_postproc* pp, rb_nn* nn, const 
                              void* stream);
 
 /* =====================================================================================
+ * Score consumer (config C5): Search::LinearSearch -- time-synchronous Viterbi over the linear HMMs of
+ * all pronunciations with a unigram LM and one book-keeping entry per frame (src/Search/LinearSearch.cc:233-432) --
+ * fed from the dense score matrix the scorers above leave on the device, instead of two virtual calls per HMM state
+ * and frame (emissionScores->score(mixture), :346).  The lexicon is passed as flat arrays (what LinearSearch builds
+ * from Bliss::Lexicon + Am::AcousticModel in setModelCombination): every pronunciation is a regular word, single-word
+ * recognition off.
+ * ===================================================================================== */
+
+typedef struct rb_search rb_search;
+
+typedef struct {
+    uint32_t        n_words;
+    const uint32_t* word_offsets;    /* [n_words+1] into the state arrays (Pronunciation::mixtures_) */
+    const uint32_t* state_emission;  /* MixtureItem::mixture of every HMM state */
+    const uint32_t* state_tdp_model; /* MixtureItem::stateTransitionModel, as an index into tdp */
+    uint32_t        n_models;
+    const float*    tdp;             /* [n_models * 4]: loop, forward, skip, exit (src/Am/TransitionModel.hh:32-37) */
+    uint32_t        entry_model;     /* Am::TransitionModel::entryM1 */
+    const float*    unigram;         /* [n_words] WordPronunciationState::unigramScore */
+} rb_lexicon;
+
+int  rb_search_create(const rb_lexicon* lx, int device, rb_search** out);
+void rb_search_destroy(rb_search* h);
+/* restart() + feed() for every frame of every segment (segments are independent, one CTA each); scores
+ * [frames * n_emissions]; results stay in the handle until the next decode */
+int rb_search_decode(rb_search* h, const float* scores, int n_emissions, const int64_t* frame_offsets, int n_utt);
+int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_emissions, const int64_t* frame_offsets, int n_utt,
+                         void* stream);
+/* getCurrentBestSentence of segment utt: word ends in chronological order (word index, 1-based end frame,
+ * Book::score without LM, Book::lmScore); capacity = frames of the segment; returns the number of words or < 0 */
+long rb_search_traceback(const rb_search* h, int utt, uint32_t* words, int32_t* times, float* am_scores,
+                         float* lm_scores);
+
+/* =====================================================================================
  * Test hook: one bf16 tcgen05 GEMM  D[M x N] = A[M x K] * B[N x K]^T (+bias, activation),
  * A/B f32 on the host, rounded to bf16 on the device.  Used by tests/ only.
  * ===================================================================================== */

@@ -137,6 +137,20 @@ int orc_normalize(int type, long length, long right, const float* feats, const l
 int orc_splice(int length, int right, const float* feats, const long* frame_offsets, int n_utt, int dim, float* out);
 int orc_matmul(const float* M, int rows, int cols, const float* x, long T, float* y, int use_fma);
 
+/* Search::LinearSearch on a flat lexicon (search_oracle.cc) */
+typedef struct {
+    uint32_t        n_words;
+    const uint32_t* word_offsets;    /* [n_words+1] into the state arrays */
+    const uint32_t* state_emission;  /* emission (mixture) index of every HMM state */
+    const uint32_t* state_tdp_model; /* transition model of every state */
+    uint32_t        n_models;
+    const float*    tdp;             /* [n_models * 4]: loop, forward, skip, exit */
+    uint32_t        entry_model;     /* Am::TransitionModel::entryM1 */
+    const float*    unigram;         /* [n_words] LM score of entering the word */
+} orc_lexicon;
+long orc_linear_search(const orc_lexicon* lx, const float* scores, long T, int n_emissions, uint32_t* words,
+                       int32_t* times, float* am, float* lm);
+
 #ifdef __cplusplus
 }
 #endif

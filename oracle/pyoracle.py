@@ -268,6 +268,37 @@ def matmul(M, x, use_fma=True):
     return y
 
 
+class LexiconC(C.Structure):
+    _fields_ = [("n_words", C.c_uint32), ("word_offsets", C.POINTER(C.c_uint32)),
+                ("state_emission", C.POINTER(C.c_uint32)), ("state_tdp_model", C.POINTER(C.c_uint32)),
+                ("n_models", C.c_uint32), ("tdp", C.POINTER(C.c_float)), ("entry_model", C.c_uint32),
+                ("unigram", C.POINTER(C.c_float))]
+
+
+def linear_search(lex, scores):
+    """Search::LinearSearch over one segment; lex: dict(word_offsets, state_emission, state_tdp_model, tdp, entry_model,
+    unigram).  Returns dict(words, times, am, lm) in chronological order."""
+    a = dict(word_offsets=np.ascontiguousarray(lex["word_offsets"], np.uint32),
+             state_emission=np.ascontiguousarray(lex["state_emission"], np.uint32),
+             state_tdp_model=np.ascontiguousarray(lex["state_tdp_model"], np.uint32),
+             tdp=np.ascontiguousarray(lex["tdp"], np.float32).reshape(-1, 4),
+             unigram=np.ascontiguousarray(lex["unigram"], np.float32))
+    c = LexiconC(a["word_offsets"].size - 1, _p(a["word_offsets"], C.c_uint32), _p(a["state_emission"], C.c_uint32),
+                 _p(a["state_tdp_model"], C.c_uint32), a["tdp"].shape[0], _p(a["tdp"], C.c_float),
+                 int(lex["entry_model"]), _p(a["unigram"], C.c_float))
+    scores = np.ascontiguousarray(scores, np.float32)
+    T = scores.shape[0]
+    words, times = np.zeros(max(T, 1), np.uint32), np.zeros(max(T, 1), np.int32)
+    am, lm = np.zeros(max(T, 1), np.float32), np.zeros(max(T, 1), np.float32)
+    fn = lib().orc_linear_search
+    fn.restype = C.c_long
+    n = fn(C.byref(c), _p(scores, C.c_float), C.c_long(T), int(scores.shape[1]), _p(words, C.c_uint32),
+           _p(times, C.c_int32), _p(am, C.c_float), _p(lm, C.c_float))
+    if n < 0:
+        raise RuntimeError("orc_linear_search failed: %d" % n)
+    return dict(words=words[:n], times=times[:n], am=am[:n], lm=lm[:n])
+
+
 def _nn_args(dims, acts, weights, biases, dtype, ctype):
     n = len(weights)
     dims_a = np.asarray(dims, np.int32)

@@ -31,6 +31,7 @@ SYMBOLS = [
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_s16", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
     "rb_pipeline_nn_score", "rb_pipeline_nn_score_dev",
+    "rb_search_create", "rb_search_destroy", "rb_search_decode", "rb_search_decode_dev", "rb_search_traceback",
     "rb_postproc_create", "rb_postproc_destroy", "rb_postproc_dim_out", "rb_postproc_process", "rb_postproc_process_dev",
 ]
 
@@ -57,6 +58,13 @@ class PostprocCfg(C.Structure):
                 ("splice_length", C.c_int), ("splice_right", C.c_int), ("matrix_rows", C.c_int),
                 ("matrix_cols", C.c_int), ("matrix", C.POINTER(C.c_float)), ("contraction", C.c_int),
                 ("device", C.c_int)]
+
+
+class LexiconC(C.Structure):
+    _fields_ = [("n_words", C.c_uint32), ("word_offsets", C.POINTER(C.c_uint32)),
+                ("state_emission", C.POINTER(C.c_uint32)), ("state_tdp_model", C.POINTER(C.c_uint32)),
+                ("n_models", C.c_uint32), ("tdp", C.POINTER(C.c_float)), ("entry_model", C.c_uint32),
+                ("unigram", C.POINTER(C.c_float))]
 
 
 class MixtureSetC(C.Structure):
@@ -134,6 +142,13 @@ def lib():
     L.rb_pipeline_score_dev.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp]
     L.rb_pipeline_nn_score.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.rb_pipeline_nn_score_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.rb_search_create.argtypes = [C.POINTER(LexiconC), C.c_int, C.POINTER(vp)]
+    L.rb_search_destroy.argtypes = [vp]
+    L.rb_search_destroy.restype = None
+    L.rb_search_decode.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.rb_search_decode_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp]
+    L.rb_search_traceback.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.rb_search_traceback.restype = C.c_long
     L.rb_postproc_create.argtypes = [C.POINTER(PostprocCfg), C.c_int, C.POINTER(vp)]
     L.rb_postproc_destroy.argtypes = [vp]
     L.rb_postproc_destroy.restype = None

@@ -77,3 +77,24 @@ def network(dims=(429, 2048, 2048, 2048, 2048, 2048, 2048, 12000), hidden="relu"
     z = rng.standard_normal(dims[-1])
     log_prior = (z - z.max() - np.log(np.exp(z - z.max()).sum())).astype(np.float32)
     return dict(dims=list(dims), acts=acts, weights=weights, biases=biases, log_prior=log_prior)
+
+
+def lexicon(n_words=200, n_emissions=256, min_states=3, max_states=12, seed=77):
+    """Synthetic pronunciation lexicon for the score consumer (config C5): every word a linear HMM of 3..12 states
+    with emission indices drawn from the mixture inventory, the transition models of the reference's default
+    topology (phone0 / phone1 / silence-like, plus entryM1) as -log probabilities, unigram LM scores."""
+    rng = np.random.default_rng(seed)
+    n_states = rng.integers(min_states, max_states + 1, n_words)
+    offs = np.zeros(n_words + 1, np.uint32)
+    offs[1:] = np.cumsum(n_states)
+    total = int(offs[-1])
+    # loop, forward, skip, exit
+    tdp = np.array([[3.0, 0.0, 30.0, 0.0],     # phone0
+                    [3.0, 0.0, 30.0, 0.0],     # phone1
+                    [0.7, 0.7, 1e30, 20.0],    # silence-like
+                    [1e30, 0.0, 30.0, 0.0]],   # entryM1
+                   np.float32)
+    p = rng.dirichlet(np.ones(n_words))
+    return dict(word_offsets=offs, state_emission=rng.integers(0, n_emissions, total).astype(np.uint32),
+                state_tdp_model=rng.integers(0, 3, total).astype(np.uint32), tdp=tdp, entry_model=3,
+                unigram=(-10.0 * np.log(p)).astype(np.float32) / 10.0)

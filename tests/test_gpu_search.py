@@ -1,0 +1,75 @@
+"""GPU parity of the score consumer (rb_search_*: Search::LinearSearch over the dense score matrix) against the CPU
+oracle, through the C ABI.  Word sequences, word-end frames (indices) and both scores must be BIT-IDENTICAL."""
+import numpy as np
+import pytest
+
+from rasr_b200 import capi, mm, search, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def same(a, b):
+    return (list(a["words"]) == list(b["words"]) and list(a["times"]) == list(b["times"]) and
+            np.array_equal(a["am"], b["am"]) and np.array_equal(a["lm"], b["lm"]))
+
+
+@pytest.mark.parametrize("n_words,n_emis,T,seed", [(1, 8, 5, 0), (40, 32, 90, 2), (33, 32, 2, 3), (700, 256, 300, 5),
+                                                   (1500, 256, 64, 6)])
+def test_linear_search_bit_exact(oracle, n_words, n_emis, T, seed):
+    lex = synth.lexicon(n_words, n_emis, seed=seed)
+    rng = np.random.default_rng(seed)
+    scores = (rng.random((T, n_emis)) * 25 + 2).astype(np.float32)
+    got = search.LinearSearch(lex).decode(scores)
+    assert len(got) == 1 and same(got[0], oracle.linear_search(lex, scores))
+
+
+def test_segments_are_independent_and_ties_resolve_like_the_reference(oracle):
+    """several segments of different length in one call; quantised scores create exact ties between predecessors and
+    between word ends, which must resolve as in the reference (first predecessor / first word in lexicon order)"""
+    lex = synth.lexicon(120, 64, seed=9)
+    lex["unigram"] = np.round(lex["unigram"] * 2) / 2
+    rng = np.random.default_rng(9)
+    fo = np.array([0, 37, 38, 180, 400], np.int64)
+    scores = rng.integers(1, 6, (400, 64)).astype(np.float32)
+    got = search.LinearSearch(lex).decode(scores, fo)
+    for u in range(4):
+        assert same(got[u], oracle.linear_search(lex, scores[fo[u]:fo[u + 1]])), u
+
+
+def test_scores_from_the_gmm_scorer_on_device(oracle, diag):
+    """config C5 in small: GMM scores stay on the device and feed the search; 24 segments x 250 frames"""
+    import torch
+
+    msd = synth.mixture_set()
+    gmm = mm.GmmScorer(mm.MixtureSet.from_dict(msd), "batch-int")
+    lex = synth.lexicon(1000, 256, seed=11)
+    n_utt, T = 24, 250
+    f = synth.features(n_utt * T, 39, seed=12)
+    fo = np.arange(n_utt + 1, dtype=np.int64) * T
+    d_in = torch.from_numpy(f).cuda()
+    d_sc = torch.empty((n_utt * T, 256), dtype=torch.float32, device="cuda")
+    gmm.score_dev(d_in, n_utt * T, d_sc)
+    ls = search.LinearSearch(lex)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    got = ls.decode_dev(d_sc, 256, fo)
+    ev[1].record()
+    torch.cuda.synchronize()
+    host_scores = d_sc.cpu().numpy()
+    for u in (0, 7, 23):
+        assert same(got[u], oracle.linear_search(lex, host_scores[fo[u]:fo[u + 1]])), u
+    diag("search_c5_small", ms=ev[0].elapsed_time(ev[1]), frames=n_utt * T, words=int(sum(len(g["words"]) for g in got)))
+    assert all(len(g["words"]) > 0 for g in got)
+
+
+def test_rejects_bad_lexicon():
+    lex = synth.lexicon(5, 8)
+    bad = dict(lex)
+    bad["word_offsets"] = np.array([0, 2, 2, 5, 7, 9], np.uint32)  # a word without states
+    with pytest.raises(capi.RasrB200Error):
+        search.LinearSearch(bad)
+    bad = dict(lex)
+    bad["entry_model"] = 9
+    with pytest.raises(capi.RasrB200Error):
+        search.LinearSearch(bad)
