@@ -16,6 +16,13 @@
 // loop is inherently sequential.  All arithmetic is the reference's f32 arithmetic in its order: word sequences, word
 // end times and both scores are bit-identical to the CPU path.
 #include <cfloat>
+#include <cmath>
+#include <algorithm>
+#include <array>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -217,13 +224,308 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
         p.nBooks[u] = sLast + 1;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Register-resident variant.  The per-word kernel above is bound by the latency of its dependent shared-memory chains
+// (13.8 us per frame for 1000 words).  Here a thread owns NPT CONSECUTIVE HMM states of the concatenated lexicon and
+// keeps their hypotheses in registers across all frames; the per-state code is branch-free and the kernel is bound by
+// shared-memory wavefronts, so every table is laid out to be read in one wavefront.
+//  * feed() reads only the PREVIOUS frame's values of a state and its two predecessors, so all states update
+//    independently; within a thread they are walked in descending order, in place.  The last two states of the left
+//    neighbour arrive by warp shuffle, across warps through a double-buffered shared-memory slot per warp.
+//  * The transition penalties a state needs -- its own loop, the forward of state-1 and the skip of state-2, with the
+//    entry model standing in at the word start -- are three 5-bit indices into a table of the (at most 32) DISTINCT
+//    penalty values of the lexicon: 32 words in 32 banks, conflict-free for any access pattern.  A word's first state
+//    has skip-in = +inf: the candidate is formed and never wins, like the reference never forming it.
+//  * A hypothesis carries (score, back pointer) only.  Its lmScore is a function of (word, back pointer): it was set
+//    at the word start to unigram[w] (+ lmScore of the book entry it starts from, :271-290) and is copied unchanged
+//    along the word, so the book keeping recomputes it with the same single rounding for the words it accepts.
+//    (Holds for every hypothesis below FLT_MAX; needs |scores| < 1e30 so that nothing unreached ever gets below it.)
+//  * The score row of the NEXT frame is copied to shared memory with cp.async while this frame is processed.
+//  * Book keeping (:381-432) is a sequential scan "accept w if cand_w < nbScore + nbLm; nbScore = cand_w - lm_w" whose
+//    threshold after accepting w is g_w = fl(fl(cand_w - lm_w) + lm_w), within 2^-24 (2|cand_w| + |lm_w|) of cand_w.
+//    Every warp reduces one 32-word chunk to (min, first lane of the min, second smallest) with REDUX; warp 0 combines
+//    them.  If the second smallest candidate exceeds the smallest M by more than 2^-21 (|M| + max|lm|), every word
+//    accepted before the first argmin j leaves a threshold above M, so j is accepted, and nothing after j beats g_j:
+//    the scan ends at j, and its result is written directly.  Otherwise (ties, near ties) warp 0 replays the scan:
+//    it walks the chunks in word order, opens only those whose minimum beats the current threshold (exists w: cand <
+//    thr  <=>  min cand < thr) and replays the reference's sequential acceptance test inside them.
+// ------------------------------------------------------------------------------------------------------------------
+// meta: first | second << 1 | loop index << 2 | forward-in index << 7 | skip-in index << 12 | last << 17 | word << 18
+constexpr uint32_t kFirst = 1u, kSecond = 2u, kLast = 1u << 17, kWordShift = 18, kMaxValues = 32;
+
+struct SearchParams2 {
+    const uint32_t* stMeta;    // [threads * NPT]
+    const uint32_t* stEmOff;   // [threads * NPT / 2] byte offset of the state's emission in a score row, 16 bits each
+    const float*    values;    // [32] distinct transition penalties
+    const float*    unigram;   // [W]
+    const float*    wordExit;  // [W] exit penalty of the word's last state
+    float           maxAbsUni;
+    uint32_t        W, maxT, rowFloats;  // rowFloats: nEmis rounded up to 4
+    int             forceScan;           // test hook: always replay the sequential scan
+    const float*    scores;
+    const int64_t*  frameOff;
+    int             nEmis;
+    float*          bookScore;
+    float*          bookLm;
+    int*            bookWord;
+    int*            bookBkp;
+    int*            bookTime;
+    int*            nBooks;
+};
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// order-preserving map of f32 onto u32 (and back): a < b  <=>  key(a) < key(b) for non-NaN values
+__device__ __forceinline__ uint32_t float_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+
+template<int NPT>
+__global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const SearchParams2 p) {
+    extern __shared__ __align__(128) unsigned char smemReg[];
+    const uint32_t nThreads = blockDim.x, nWarps = nThreads / 32, nChunks = (p.W + 31) / 32;
+    float*  sT    = reinterpret_cast<float*>(smemReg);                  // [32] penalty values, one per bank
+    float4* xch   = reinterpret_cast<float4*>(sT + 32);                 // [2][nWarps] {s[n-2], s[n-1], b[n-2], b[n-1]} of lane 31
+    uint4*  cInfo = reinterpret_cast<uint4*>(xch + 2 * nWarps);         // [nChunks] {min key, second key, first lane of min}
+    float2* sEnd  = reinterpret_cast<float2*>(cInfo + nChunks);         // [W] word end {candidate score, bkp}
+    float*  rows  = reinterpret_cast<float*>(sEnd + p.W + (p.W & 1));   // [2][rowFloats], 16-byte aligned
+    float*  sUni  = rows + 2 * p.rowFloats;                             // [W]
+    float*  sExit = sUni + p.W;                                         // [W]
+    float*  sBkLm = sExit + p.W;                                        // [maxT] lmScore of the book entries
+    __shared__ int   sLast;
+    __shared__ float sLastScore, sLastLm;
+
+    const int     u  = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t f0 = p.frameOff[u];
+    const int     T  = (int)(p.frameOff[u + 1] - f0);
+    const bool    vec16 = (p.nEmis & 3) == 0 && (reinterpret_cast<uintptr_t>(p.scores) & 15) == 0;
+    auto prefetch_row = [&](int t) {  // row of frame t (1-based) -> rows[t & 1]
+        const float* src = p.scores + (size_t)(f0 + t - 1) * p.nEmis;
+        float*       dst = rows + (t & 1) * p.rowFloats;
+        if (vec16)
+            for (uint32_t i = tid * 4; i < (uint32_t)p.nEmis; i += nThreads * 4)
+                cp_async16(dst + i, src + i);
+        else
+            for (uint32_t i = tid; i < (uint32_t)p.nEmis; i += nThreads)
+                cp_async4(dst + i, src + i);
+    };
+    if (T > 0)
+        prefetch_row(1);
+    if (tid < 32)
+        sT[tid] = p.values[tid];
+    for (uint32_t i = tid; i < p.W; i += nThreads) {
+        sUni[i]  = p.unigram[i];
+        sExit[i] = p.wordExit[i];
+    }
+    // this thread's states
+    const uint32_t i0 = (uint32_t)tid * NPT;
+    float    hs[NPT];
+    int      hb[NPT];
+    uint32_t meta[NPT], emOff[NPT / 2];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        hs[k]   = FLT_MAX;  // restart()
+        hb[k]   = -1;
+        meta[k] = p.stMeta[i0 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < NPT / 2; ++k)
+        emOff[k] = p.stEmOff[i0 / 2 + k];
+    if (lane == 31) {
+        xch[warp]          = make_float4(FLT_MAX, FLT_MAX, __int_as_float(-1), __int_as_float(-1));
+        xch[nWarps + warp] = make_float4(FLT_MAX, FLT_MAX, __int_as_float(-1), __int_as_float(-1));
+    }
+    if (tid == 0) {
+        sLast      = -1;
+        sLastScore = 0.0f;
+        sLastLm    = 0.0f;
+    }
+    float maxAbsBkLm = 0.0f;  // warp 0: bound on |lmScore| of the book entries so far
+    cp_async_wait_all();
+    __syncthreads();
+    const unsigned char* sTb = reinterpret_cast<const unsigned char*>(sT);
+
+    for (int t = 1; t <= T; ++t) {
+        const int par = t & 1;  // score row and boundary states of this frame are in buffer par
+        if (t < T)
+            prefetch_row(t + 1);
+        const unsigned char* row       = reinterpret_cast<const unsigned char*>(rows + par * p.rowFloats);
+        const int            last      = sLast;
+        const float          lastScore = sLastScore, lastLm = sLastLm;  // 0 before the first book entry
+        // previous-frame values of the two states left of my block
+        float pS2 = __shfl_up_sync(0xffffffffu, hs[NPT - 2], 1), pS1 = __shfl_up_sync(0xffffffffu, hs[NPT - 1], 1);
+        int   pB2 = __shfl_up_sync(0xffffffffu, hb[NPT - 2], 1), pB1 = __shfl_up_sync(0xffffffffu, hb[NPT - 1], 1);
+        if (lane == 0) {
+            const float4 nb = xch[par * nWarps + (warp > 0 ? warp - 1 : 0)];
+            pS2 = warp > 0 ? nb.x : FLT_MAX;
+            pS1 = warp > 0 ? nb.y : FLT_MAX;
+            pB2 = warp > 0 ? __float_as_int(nb.z) : -1;
+            pB1 = warp > 0 ? __float_as_int(nb.w) : -1;
+        }
+#pragma unroll
+        for (int k = NPT - 1; k >= 0; --k) {
+            const uint32_t m = meta[k];
+            const uint32_t w = m >> kWordShift;
+            const float    tLoop = *reinterpret_cast<const float*>(sTb + (m & 0x7cu));
+            const float    tFwd  = *reinterpret_cast<const float*>(sTb + ((m >> 5) & 0x7cu));
+            const float    tSkip = *reinterpret_cast<const float*>(sTb + ((m >> 10) & 0x7cu));
+            // word start (:271-290): from the newest book entry, or from scratch
+            const float uni  = sUni[w];
+            const float h0lm = last >= 0 ? __fadd_rn(uni, lastLm) : uni;
+            const float h0s  = __fadd_rn(lastScore, h0lm);
+            const bool  first = m & kFirst, second = m & kSecond;
+            // predecessors in the reference's order pre = sta-2, sta-1, sta (the first strictly smaller one wins)
+            float s1 = k >= 1 ? hs[k >= 1 ? k - 1 : 0] : pS1;
+            int   b1 = k >= 1 ? hb[k >= 1 ? k - 1 : 0] : pB1;
+            float s2 = k >= 2 ? hs[k >= 2 ? k - 2 : 0] : (k == 1 ? pS1 : pS2);
+            int   b2 = k >= 2 ? hb[k >= 2 ? k - 2 : 0] : (k == 1 ? pB1 : pB2);
+            s1 = first ? h0s : s1;
+            b1 = first ? last : b1;
+            s2 = second ? h0s : s2;
+            b2 = second ? last : b2;
+            const float c2 = __fadd_rn(s2, tSkip), c1 = __fadd_rn(s1, tFwd), c0 = __fadd_rn(hs[k], tLoop);
+            const bool  t2 = c2 < FLT_MAX;
+            float       bestS = t2 ? c2 : FLT_MAX;
+            int         bestB = t2 ? b2 : -1;
+            const bool  t1 = c1 < bestS;
+            bestS = t1 ? c1 : bestS;
+            bestB = t1 ? b1 : bestB;
+            const bool t0 = c0 < bestS;
+            bestS = t0 ? c0 : bestS;
+            bestB = t0 ? hb[k] : bestB;
+            const float e = *reinterpret_cast<const float*>(row + ((k & 1) ? emOff[k / 2] >> 16 : emOff[k / 2] & 0xffffu));
+            hs[k] = __fadd_rn(bestS, e);
+            hb[k] = bestB;
+            if (m & kLast)  // word end candidate (:400-404)
+                sEnd[w] = make_float2(__fadd_rn(hs[k], sExit[w]), __int_as_float(bestB));
+        }
+        if (lane == 31)  // publish my last two states for the next warp's next frame
+            xch[(par ^ 1) * nWarps + warp] =
+                    make_float4(hs[NPT - 2], hs[NPT - 1], __int_as_float(hb[NPT - 2]), __int_as_float(hb[NPT - 1]));
+        __syncthreads();
+        // per 32-word chunk: smallest candidate, its first lane, the second smallest
+        for (uint32_t c = warp; c < nChunks; c += nWarps) {
+            const uint32_t w   = c * 32 + lane;
+            const uint32_t key = w < p.W ? float_key(sEnd[w].x) : 0xffffffffu;
+            const uint32_t k1  = __reduce_min_sync(0xffffffffu, key);
+            const int      i1  = __ffs(__ballot_sync(0xffffffffu, key == k1)) - 1;
+            const uint32_t k2  = __reduce_min_sync(0xffffffffu, lane == i1 ? 0xffffffffu : key);
+            if (lane == 0)
+                cInfo[c] = make_uint4(k1, k2, (uint32_t)i1, 0u);
+        }
+        cp_async_wait_all();  // next frame's score row has landed (made visible by the barriers below)
+        __syncthreads();
+        if (warp == 0) {
+            float nbScore = FLT_MAX, nbLm = 0.0f;
+            int   nbWord = -1;
+            // combine the chunks: lane-local over chunks lane, lane + 32, ..., then across lanes
+            uint32_t best1 = 0xffffffffu, best2 = 0xffffffffu, bestJ = 0;
+            for (uint32_t c = lane; c < nChunks; c += 32) {
+                const uint4 ci = cInfo[c];
+                if (ci.x < best1) {
+                    best2 = min(best1, ci.y);
+                    best1 = ci.x;
+                    bestJ = c * 32 + ci.z;
+                }
+                else
+                    best2 = min(best2, ci.x);
+            }
+            const uint32_t kM  = __reduce_min_sync(0xffffffffu, best1);
+            const int      lj  = __ffs(__ballot_sync(0xffffffffu, best1 == kM)) - 1;
+            const uint32_t kM2 = __reduce_min_sync(0xffffffffu, lane == lj ? best2 : best1);
+            const float    M = key_float(kM), M2 = key_float(kM2);
+            const float    slack = __fmul_rn(__fadd_rn(fabsf(M), __fadd_rn(p.maxAbsUni, maxAbsBkLm)), 4.76837158203125e-07f);
+            if (!p.forceScan && M2 > __fadd_rn(M, slack)) {
+                if (M < FLT_MAX) {  // the scan accepts the unique minimum last
+                    nbWord       = (int)__shfl_sync(0xffffffffu, bestJ, lj);
+                    const int bk = __float_as_int(sEnd[nbWord].y);
+                    nbLm         = bk >= 0 ? __fadd_rn(sUni[nbWord], sBkLm[bk]) : sUni[nbWord];
+                    nbScore      = __fsub_rn(M, nbLm);
+                }
+            }
+            else {
+                // the sequential scan over the words, replayed on the chunks that matter
+                for (uint32_t cbase = 0; cbase < nChunks; cbase += 32) {
+                    const uint32_t cc    = cbase + lane;
+                    const float    cmin  = cc < nChunks ? key_float(cInfo[cc].x) : FLT_MAX;
+                    uint32_t       ctodo = 0xffffffffu;
+                    while (true) {
+                        const float    thr   = __fadd_rn(nbScore, nbLm);
+                        const uint32_t chits = __ballot_sync(0xffffffffu, cmin < thr) & ctodo;
+                        if (!chits)
+                            break;
+                        const int      cf   = __ffs(chits) - 1;  // next chunk (in word order) holding a word that beats thr
+                        const uint32_t base = (cbase + cf) * 32;
+                        const uint32_t w    = base + lane;
+                        float          cand = FLT_MAX, lmw = 0.0f;
+                        if (w < p.W) {
+                            const float2 en = sEnd[w];
+                            const int    bk = __float_as_int(en.y);
+                            cand = en.x;
+                            lmw  = bk >= 0 ? __fadd_rn(sUni[w], sBkLm[bk]) : sUni[w];  // the hypothesis' lmScore
+                        }
+                        uint32_t todo = 0xffffffffu;
+                        while (true) {
+                            const float    thr2 = __fadd_rn(nbScore, nbLm);
+                            const uint32_t hits = __ballot_sync(0xffffffffu, cand < thr2) & todo;
+                            if (!hits)
+                                break;
+                            const int   first    = __ffs(hits) - 1;
+                            const float tmpScore = __shfl_sync(0xffffffffu, cand, first);
+                            nbLm    = __shfl_sync(0xffffffffu, lmw, first);
+                            nbScore = __fsub_rn(tmpScore, nbLm);
+                            nbWord  = (int)(base + first);
+                            todo    = first == 31 ? 0u : (0xffffffffu << (first + 1));
+                        }
+                        ctodo = cf == 31 ? 0u : (0xffffffffu << (cf + 1));  // earlier chunks were already passed
+                    }
+                }
+            }
+            if (nbScore != FLT_MAX) {
+                maxAbsBkLm = fmaxf(maxAbsBkLm, fabsf(nbLm));
+                if (lane == 0) {
+                    const int b = sLast + 1;  // entries are only ever appended: the newest is the last
+                    p.bookScore[f0 + b] = nbScore;
+                    p.bookLm[f0 + b]    = nbLm;
+                    p.bookWord[f0 + b]  = nbWord;
+                    p.bookBkp[f0 + b]   = __float_as_int(sEnd[nbWord].y);
+                    p.bookTime[f0 + b]  = t;
+                    sBkLm[b]            = nbLm;
+                    sLast               = b;
+                    sLastScore          = nbScore;
+                    sLastLm             = nbLm;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0)
+        p.nBooks[u] = sLast + 1;
+}
+
 }  // namespace
 
 struct rb_search {
     rb::DeviceInfo dev;
     uint32_t       W = 0, nStates = 0, nModels = 0, entryModel = 0;
     cudaStream_t   stream = nullptr;
-    rb::DevBuf<uint32_t> dWordOff, dStateEmis, dStateTdp;
+    rb::DevBuf<uint32_t> dWordOff, dStateEmis, dStateTdp, dStateMeta, dStateEmOff;
+    rb::DevBuf<float>    dValues, dWordExit;
+    float                maxAbsUni = 0.0f;
+    int                  npt = 0, regThreads = 0;  // states per thread / threads of the register-resident kernel, 0: per-word kernel
+    uint32_t             maxEmis = 0;
     rb::DevBuf<float>    dTdp, dUnigram, dHypScore, dHypLm, dBookScore, dBookLm, dEndScore, dScores;
     rb::DevBuf<int>      dHypBkp, dBookWord, dBookBkp, dBookTime, dNBooks;
     rb::DevBuf<int64_t>  dFrameOff;
@@ -269,6 +571,62 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
     h->nStates    = nStates;
     h->nModels    = lx->n_models;
     h->entryModel = lx->entry_model;
+    // register-resident kernel: per-state descriptor and the table of distinct transition penalties
+    {
+        const float           inf = std::numeric_limits<float>::infinity();
+        std::vector<float>    values;
+        bool                  fits = lx->n_words <= (1u << (32 - kWordShift));
+        auto valueOf = [&](float v) -> uint32_t {
+            for (size_t i = 0; i < values.size(); ++i)
+                if (memcmp(&values[i], &v, 4) == 0)
+                    return (uint32_t)i;
+            values.push_back(v);
+            if (values.size() > kMaxValues)
+                fits = false;
+            return (uint32_t)values.size() - 1;
+        };
+        const uint32_t infIdx  = valueOf(inf);
+        uint32_t       maxEmis = 0;
+        for (uint32_t s = 0; s < nStates; ++s)
+            maxEmis = std::max(maxEmis, lx->state_emission[s]);
+        fits = fits && maxEmis < 16384 && nStates <= (uint32_t)kThreads * 16;
+        const float*          tdp = lx->tdp;
+        const uint32_t        em  = lx->entry_model;
+        const uint32_t*       mo  = lx->state_tdp_model;
+        std::vector<uint32_t> meta((size_t)kThreads * 16, infIdx << 2 | infIdx << 7 | infIdx << 12);  // stays at FLT_MAX
+        std::vector<uint16_t> emOff((size_t)kThreads * 16, 0);
+        std::vector<float>    wordExit(lx->n_words);
+        for (uint32_t w = 0; w < lx->n_words && fits; ++w) {
+            for (uint32_t i = lx->word_offsets[w]; i < lx->word_offsets[w + 1] && fits; ++i) {
+                const uint32_t j     = i - lx->word_offsets[w];
+                const uint32_t oLoop = valueOf(tdp[mo[i] * 4]);
+                const uint32_t oFwd  = valueOf(j == 0 ? tdp[em * 4 + 1] : tdp[mo[i - 1] * 4 + 1]);
+                const uint32_t oSkip = j == 0 ? infIdx : valueOf(j == 1 ? tdp[em * 4 + 2] : tdp[mo[i - 2] * 4 + 2]);
+                meta[i]  = (j == 0 ? kFirst : 0u) | (j == 1 ? kSecond : 0u) | oLoop << 2 | oFwd << 7 | oSkip << 12 |
+                           (i + 1 == lx->word_offsets[w + 1] ? kLast : 0u) | (w << kWordShift);
+                emOff[i] = (uint16_t)(lx->state_emission[i] * 4);
+            }
+            wordExit[w]  = tdp[mo[lx->word_offsets[w + 1] - 1] * 4 + 3];
+            h->maxAbsUni = std::max(h->maxAbsUni, std::fabs(lx->unigram[w]));
+        }
+        if (fits && getenv("RB_SEARCH_PER_WORD") == nullptr) {
+            // few states per thread while that still fills the SM's four schedulers with several warps each
+            h->npt = nStates <= 512 * 2 ? 2 : (nStates <= (uint32_t)kThreads * 4 ? 4 : (nStates <= (uint32_t)kThreads * 8 ? 8 : 16));
+            if (const char* e = getenv("RB_SEARCH_NPT"))
+                if (atoi(e) * (uint32_t)kThreads >= nStates && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16))
+                    h->npt = atoi(e);
+            h->regThreads = (int)(((nStates + h->npt - 1) / h->npt + 31) / 32 * 32);
+            h->maxEmis    = maxEmis;
+            values.resize(kMaxValues, inf);
+            if (h->dStateMeta.upload(meta.data(), meta.size(), h->stream) != RB_OK ||
+                h->dStateEmOff.upload(reinterpret_cast<const uint32_t*>(emOff.data()), emOff.size() / 2, h->stream) != RB_OK ||
+                h->dValues.upload(values.data(), values.size(), h->stream) != RB_OK ||
+                h->dWordExit.upload(wordExit.data(), wordExit.size(), h->stream) != RB_OK) {
+                rb::set_error("lexicon upload failed");
+                return fail(RB_ERR_CUDA);
+            }
+        }
+    }
     if (h->dWordOff.upload(lx->word_offsets, lx->n_words + 1, h->stream) != RB_OK ||
         h->dStateEmis.upload(lx->state_emission, nStates, h->stream) != RB_OK ||
         h->dStateTdp.upload(lx->state_tdp_model, nStates, h->stream) != RB_OK ||
@@ -339,11 +697,47 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
     p.bookTime   = h->dBookTime.p;
     p.nBooks     = h->dNBooks.p;
     p.endScore   = h->dEndScore.p;
+    int64_t maxT = 0;
+    for (int u = 0; u < n_utt; ++u)
+        maxT = std::max(maxT, h->frameOff[u + 1] - h->frameOff[u]);
+    const uint32_t rowFloats = ((uint32_t)n_emissions + 3) & ~3u;
+    const uint32_t nChunks   = (h->W + 31) / 32;
+    const size_t   smem2     = 128 + (size_t)(h->regThreads / 32) * 32 + (size_t)nChunks * 16 + (size_t)(h->W + (h->W & 1)) * 8 +
+                         (size_t)rowFloats * 8 + ((size_t)h->W * 2 + (size_t)maxT) * 4;
+    if (h->npt && h->maxEmis < (uint32_t)n_emissions && smem2 <= h->dev.smem_optin - 1024) {
+        SearchParams2 q;
+        q.stMeta    = h->dStateMeta.p;
+        q.stEmOff   = h->dStateEmOff.p;
+        q.values    = h->dValues.p;
+        q.unigram   = h->dUnigram.p;
+        q.wordExit  = h->dWordExit.p;
+        q.maxAbsUni = h->maxAbsUni;
+        q.W         = h->W;
+        q.maxT      = (uint32_t)maxT;
+        q.rowFloats = rowFloats;
+        q.forceScan = getenv("RB_SEARCH_FORCE_SCAN") != nullptr;
+        q.scores    = d_scores;
+        q.frameOff  = h->dFrameOff.p;
+        q.nEmis     = n_emissions;
+        q.bookScore = h->dBookScore.p;
+        q.bookLm    = h->dBookLm.p;
+        q.bookWord  = h->dBookWord.p;
+        q.bookBkp   = h->dBookBkp.p;
+        q.bookTime  = h->dBookTime.p;
+        q.nBooks    = h->dNBooks.p;
+        auto k = h->npt == 2 ? linear_search_reg_kernel<2>
+                             : (h->npt == 4 ? linear_search_reg_kernel<4>
+                                            : (h->npt == 8 ? linear_search_reg_kernel<8> : linear_search_reg_kernel<16>));
+        RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k<<<n_utt, h->regThreads, smem2, s>>>(q);
+    }
+    else {
     const size_t smem = (stride * 3 + (size_t)h->W * 2 + (h->W + 1) + (size_t)h->nStates * 2) * 4;
     p.useSmem         = smem <= h->dev.smem_optin - 1024 ? 1 : 0;
     if (p.useSmem)
         RB_CUDA(cudaFuncSetAttribute(linear_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     linear_search_kernel<<<n_utt, kThreads, p.useSmem ? smem : 0, s>>>(p);
+    }
     RB_LAUNCH_CHECK();
     h->bookScore.resize(T);
     h->bookLm.resize(T);

@@ -23,6 +23,24 @@ def test_linear_search_bit_exact(oracle, n_words, n_emis, T, seed):
     assert len(got) == 1 and same(got[0], oracle.linear_search(lex, scores))
 
 
+@pytest.mark.parametrize("n_words,min_s,max_s,env", [(2100, 3, 12, None), (300, 1, 3, None), (90, 2, 5, None),
+                                                     (700, 3, 12, "RB_SEARCH_PER_WORD"), (300, 1, 3, "RB_SEARCH_PER_WORD"),
+                                                     (700, 3, 12, "RB_SEARCH_FORCE_SCAN"), (1200, 3, 9, "RB_SEARCH_NPT=16")])
+def test_kernel_variants_bit_exact(oracle, monkeypatch, n_words, min_s, max_s, env):
+    """the register-resident kernel at 2, 4, 8 and 16 states per thread, words of one and two states (the entry
+    hypothesis is both predecessors), its book keeping forced onto the sequential replay, and the per-word kernel that
+    serves lexicons the register kernel does not fit"""
+    if env:
+        monkeypatch.setenv(*(env.split("=") if "=" in env else (env, "1")))
+    lex = synth.lexicon(n_words, 64, min_states=min_s, max_states=max_s, seed=21)
+    rng = np.random.default_rng(21)
+    fo = np.array([0, 120, 121, 200], np.int64)
+    scores = (rng.random((200, 64)) * 25 + 2).astype(np.float32)
+    got = search.LinearSearch(lex).decode(scores, fo)
+    for u in range(3):
+        assert same(got[u], oracle.linear_search(lex, scores[fo[u]:fo[u + 1]])), u
+
+
 def test_segments_are_independent_and_ties_resolve_like_the_reference(oracle):
     """several segments of different length in one call; quantised scores create exact ties between predecessors and
     between word ends, which must resolve as in the reference (first predecessor / first word in lexicon order)"""
