@@ -47,11 +47,7 @@ struct SearchParams {
     float* hypLm;
     int*   hypBkp;
     // per segment book (capacity = frames of the segment, laid out at frameOff[u])
-    float* bookScore;
-    float* bookLm;
-    int*   bookWord;
-    int*   bookBkp;
-    int*   bookTime;
+    int4*  books;  // [frames][2]: {score, lmScore, word, bkp}, {time, -, -, -}; entries of a segment start at its first frame
     int*   nBooks;  // [U]
     // word-end candidates of the current frame, per segment [W]
     float* endScore;
@@ -98,11 +94,7 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
         stateTdp  = sTd;
         unigram   = sUni;
     }
-    float*         bScore = p.bookScore + f0;
-    float*         bLm    = p.bookLm + f0;
-    int*           bWord  = p.bookWord + f0;
-    int*           bBkp   = p.bookBkp + f0;
-    int*           bTime  = p.bookTime + f0;
+    int4*          books  = p.books + 2 * f0;
     __shared__ int   sLast;                  // index of the newest book entry, -1 if none
     __shared__ float sLastScore, sLastLm;
     __shared__ float sTdp[64 * 4];           // transition models (when there are at most 64)
@@ -208,11 +200,8 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
             }
             if (lane == 0 && nbScore != FLT_MAX) {
                 const int b = sLast + 1;  // entries are only ever appended: the newest is the last
-                bScore[b]   = nbScore;
-                bLm[b]      = nbLm;
-                bWord[b]    = nbWord;
-                bBkp[b]     = nbBkp;
-                bTime[b]    = t;
+                books[2 * b]     = make_int4(__float_as_int(nbScore), __float_as_int(nbLm), nbWord, nbBkp);
+                books[2 * b + 1] = make_int4(t, 0, 0, 0);
                 sLast       = b;
                 sLastScore  = nbScore;
                 sLastLm     = nbLm;
@@ -254,23 +243,43 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
 // meta: first | second << 1 | loop index << 2 | forward-in index << 7 | skip-in index << 12 | last << 17 | word << 18
 constexpr uint32_t kFirst = 1u, kSecond = 2u, kLast = 1u << 17, kWordShift = 18, kMaxValues = 32;
 
+struct SmemLayout {  // byte offsets into the dynamic shared memory of the register-resident kernel
+    uint32_t xch, cInfo, end, rows, uni, exit, bkLm, cBkp, total;
+    SmemLayout(uint32_t nWarps, uint32_t W, uint32_t rowFloats, uint32_t maxT) {
+        const uint32_t nChunks = (W + 31) / 32;
+        uint32_t       o       = 128;
+        auto take = [&](uint32_t bytes) {
+            const uint32_t at = o;
+            o += (bytes + 15) & ~15u;
+            return at;
+        };
+        xch   = take(2 * nWarps * 16);
+        cInfo = take(nChunks * 16);
+        end   = take(W * 8);
+        rows  = take(2 * rowFloats * 4);
+        uni   = take(W * 4);
+        exit  = take(W * 4);
+        bkLm  = take(maxT * 4);
+        cBkp  = take(nChunks * 4);
+        total = o;
+    }
+    SmemLayout() = default;
+};
+
 struct SearchParams2 {
+    SmemLayout      lay;
     const uint32_t* stMeta;    // [threads * NPT]
     const uint32_t* stEmOff;   // [threads * NPT / 2] byte offset of the state's emission in a score row, 16 bits each
     const float*    values;    // [32] distinct transition penalties
     const float*    unigram;   // [W]
     const float*    wordExit;  // [W] exit penalty of the word's last state
     float           maxAbsUni;
-    uint32_t        W, maxT, rowFloats;  // rowFloats: nEmis rounded up to 4
+    uint32_t        W, nChunks, maxT, rowFloats, nStates;  // rowFloats: nEmis rounded up to 4
     int             forceScan;           // test hook: always replay the sequential scan
     const float*    scores;
     const int64_t*  frameOff;
     int             nEmis;
-    float*          bookScore;
-    float*          bookLm;
-    int*            bookWord;
-    int*            bookBkp;
-    int*            bookTime;
+    int4*           books;
     int*            nBooks;
 };
 
@@ -295,17 +304,19 @@ __device__ __forceinline__ float key_float(uint32_t k) {
 template<int NPT>
 __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const SearchParams2 p) {
     extern __shared__ __align__(128) unsigned char smemReg[];
-    const uint32_t nThreads = blockDim.x, nWarps = nThreads / 32, nChunks = (p.W + 31) / 32;
-    float*  sT    = reinterpret_cast<float*>(smemReg);                  // [32] penalty values, one per bank
-    float4* xch   = reinterpret_cast<float4*>(sT + 32);                 // [2][nWarps] {s[n-2], s[n-1], b[n-2], b[n-1]} of lane 31
-    uint4*  cInfo = reinterpret_cast<uint4*>(xch + 2 * nWarps);         // [nChunks] {min key, second key, first lane of min}
-    float2* sEnd  = reinterpret_cast<float2*>(cInfo + nChunks);         // [W] word end {candidate score, bkp}
-    float*  rows  = reinterpret_cast<float*>(sEnd + p.W + (p.W & 1));   // [2][rowFloats], 16-byte aligned
-    float*  sUni  = rows + 2 * p.rowFloats;                             // [W]
-    float*  sExit = sUni + p.W;                                         // [W]
-    float*  sBkLm = sExit + p.W;                                        // [maxT] lmScore of the book entries
+    const uint32_t nThreads = blockDim.x, nWarps = nThreads / 32, nChunks = p.nChunks;
+    // the carve-up is computed on the host (SmemLayout): one constant-bank operand per table address
+    float*  sT    = reinterpret_cast<float*>(smemReg);                   // [32] penalty values, one per bank
+    float4* xch   = reinterpret_cast<float4*>(smemReg + p.lay.xch);      // [2][nWarps] {s[n-2], s[n-1], b[n-2], b[n-1]} of lane 31
+    uint4*  cInfo = reinterpret_cast<uint4*>(smemReg + p.lay.cInfo);     // [nChunks] {min key, second key, word, lmScore}
+    float2* sEnd  = reinterpret_cast<float2*>(smemReg + p.lay.end);      // [W] word end {candidate score, bkp}
+    float*  rows  = reinterpret_cast<float*>(smemReg + p.lay.rows);      // [2][rowFloats], 16-byte aligned
+    float*  sUni  = reinterpret_cast<float*>(smemReg + p.lay.uni);       // [W]
+    float*  sExit = reinterpret_cast<float*>(smemReg + p.lay.exit);      // [W]
+    float*  sBkLm = reinterpret_cast<float*>(smemReg + p.lay.bkLm);      // [maxT] lmScore of the book entries
+    int*    cBkp  = reinterpret_cast<int*>(smemReg + p.lay.cBkp);        // [nChunks] back pointer of the chunk's best word
     __shared__ int   sLast;
-    __shared__ float sLastScore, sLastLm;
+    __shared__ float sLastScore, sLastLm, sMaxLm;  // sMaxLm: bound on |lmScore| of the book entries so far
 
     const int     u  = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t f0 = p.frameOff[u];
@@ -351,8 +362,8 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
         sLast      = -1;
         sLastScore = 0.0f;
         sLastLm    = 0.0f;
+        sMaxLm     = 0.0f;
     }
-    float maxAbsBkLm = 0.0f;  // warp 0: bound on |lmScore| of the book entries so far
     cp_async_wait_all();
     __syncthreads();
     const unsigned char* sTb = reinterpret_cast<const unsigned char*>(sT);
@@ -364,99 +375,120 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
         const unsigned char* row       = reinterpret_cast<const unsigned char*>(rows + par * p.rowFloats);
         const int            last      = sLast;
         const float          lastScore = sLastScore, lastLm = sLastLm;  // 0 before the first book entry
-        // previous-frame values of the two states left of my block
-        float pS2 = __shfl_up_sync(0xffffffffu, hs[NPT - 2], 1), pS1 = __shfl_up_sync(0xffffffffu, hs[NPT - 1], 1);
-        int   pB2 = __shfl_up_sync(0xffffffffu, hb[NPT - 2], 1), pB1 = __shfl_up_sync(0xffffffffu, hb[NPT - 1], 1);
-        if (lane == 0) {
-            const float4 nb = xch[par * nWarps + (warp > 0 ? warp - 1 : 0)];
-            pS2 = warp > 0 ? nb.x : FLT_MAX;
-            pS1 = warp > 0 ? nb.y : FLT_MAX;
-            pB2 = warp > 0 ? __float_as_int(nb.z) : -1;
-            pB1 = warp > 0 ? __float_as_int(nb.w) : -1;
-        }
+        if ((uint32_t)(warp * 32 * NPT) < p.nStates) {  // warps behind the last state only take part in the book keeping
+            // previous-frame values of the two states left of my block
+            float pS2 = __shfl_up_sync(0xffffffffu, hs[NPT - 2], 1), pS1 = __shfl_up_sync(0xffffffffu, hs[NPT - 1], 1);
+            int   pB2 = __shfl_up_sync(0xffffffffu, hb[NPT - 2], 1), pB1 = __shfl_up_sync(0xffffffffu, hb[NPT - 1], 1);
+            if (lane == 0) {
+                const float4 nb = xch[par * nWarps + (warp > 0 ? warp - 1 : 0)];
+                pS2 = warp > 0 ? nb.x : FLT_MAX;
+                pS1 = warp > 0 ? nb.y : FLT_MAX;
+                pB2 = warp > 0 ? __float_as_int(nb.z) : -1;
+                pB1 = warp > 0 ? __float_as_int(nb.w) : -1;
+            }
 #pragma unroll
-        for (int k = NPT - 1; k >= 0; --k) {
-            const uint32_t m = meta[k];
-            const uint32_t w = m >> kWordShift;
-            const float    tLoop = *reinterpret_cast<const float*>(sTb + (m & 0x7cu));
-            const float    tFwd  = *reinterpret_cast<const float*>(sTb + ((m >> 5) & 0x7cu));
-            const float    tSkip = *reinterpret_cast<const float*>(sTb + ((m >> 10) & 0x7cu));
-            // word start (:271-290): from the newest book entry, or from scratch
-            const float uni  = sUni[w];
-            const float h0lm = last >= 0 ? __fadd_rn(uni, lastLm) : uni;
-            const float h0s  = __fadd_rn(lastScore, h0lm);
-            const bool  first = m & kFirst, second = m & kSecond;
-            // predecessors in the reference's order pre = sta-2, sta-1, sta (the first strictly smaller one wins)
-            float s1 = k >= 1 ? hs[k >= 1 ? k - 1 : 0] : pS1;
-            int   b1 = k >= 1 ? hb[k >= 1 ? k - 1 : 0] : pB1;
-            float s2 = k >= 2 ? hs[k >= 2 ? k - 2 : 0] : (k == 1 ? pS1 : pS2);
-            int   b2 = k >= 2 ? hb[k >= 2 ? k - 2 : 0] : (k == 1 ? pB1 : pB2);
-            s1 = first ? h0s : s1;
-            b1 = first ? last : b1;
-            s2 = second ? h0s : s2;
-            b2 = second ? last : b2;
-            const float c2 = __fadd_rn(s2, tSkip), c1 = __fadd_rn(s1, tFwd), c0 = __fadd_rn(hs[k], tLoop);
-            const bool  t2 = c2 < FLT_MAX;
-            float       bestS = t2 ? c2 : FLT_MAX;
-            int         bestB = t2 ? b2 : -1;
-            const bool  t1 = c1 < bestS;
-            bestS = t1 ? c1 : bestS;
-            bestB = t1 ? b1 : bestB;
-            const bool t0 = c0 < bestS;
-            bestS = t0 ? c0 : bestS;
-            bestB = t0 ? hb[k] : bestB;
-            const float e = *reinterpret_cast<const float*>(row + ((k & 1) ? emOff[k / 2] >> 16 : emOff[k / 2] & 0xffffu));
-            hs[k] = __fadd_rn(bestS, e);
-            hb[k] = bestB;
-            if (m & kLast)  // word end candidate (:400-404)
-                sEnd[w] = make_float2(__fadd_rn(hs[k], sExit[w]), __int_as_float(bestB));
+            for (int k = NPT - 1; k >= 0; --k) {
+                const uint32_t m = meta[k];
+                const uint32_t w = m >> kWordShift;
+                const float    tLoop = *reinterpret_cast<const float*>(sTb + (m & 0x7cu));
+                const float    tFwd  = *reinterpret_cast<const float*>(sTb + ((m >> 5) & 0x7cu));
+                const float    tSkip = *reinterpret_cast<const float*>(sTb + ((m >> 10) & 0x7cu));
+                // word start (:271-290): from the newest book entry, or from scratch
+                const float uni  = sUni[w];
+                const float h0lm = last >= 0 ? __fadd_rn(uni, lastLm) : uni;
+                const float h0s  = __fadd_rn(lastScore, h0lm);
+                const bool  first = m & kFirst, second = m & kSecond;
+                // predecessors in the reference's order pre = sta-2, sta-1, sta (the first strictly smaller one wins)
+                float s1 = k >= 1 ? hs[k >= 1 ? k - 1 : 0] : pS1;
+                int   b1 = k >= 1 ? hb[k >= 1 ? k - 1 : 0] : pB1;
+                float s2 = k >= 2 ? hs[k >= 2 ? k - 2 : 0] : (k == 1 ? pS1 : pS2);
+                int   b2 = k >= 2 ? hb[k >= 2 ? k - 2 : 0] : (k == 1 ? pB1 : pB2);
+                s1 = first ? h0s : s1;
+                b1 = first ? last : b1;
+                s2 = second ? h0s : s2;
+                b2 = second ? last : b2;
+                const float c2 = __fadd_rn(s2, tSkip), c1 = __fadd_rn(s1, tFwd), c0 = __fadd_rn(hs[k], tLoop);
+                const bool  t2 = c2 < FLT_MAX;
+                float       bestS = t2 ? c2 : FLT_MAX;
+                int         bestB = t2 ? b2 : -1;
+                const bool  t1 = c1 < bestS;
+                bestS = t1 ? c1 : bestS;
+                bestB = t1 ? b1 : bestB;
+                const bool t0 = c0 < bestS;
+                bestS = t0 ? c0 : bestS;
+                bestB = t0 ? hb[k] : bestB;
+                const float e = *reinterpret_cast<const float*>(row + ((k & 1) ? emOff[k / 2] >> 16 : emOff[k / 2] & 0xffffu));
+                hs[k] = __fadd_rn(bestS, e);
+                hb[k] = bestB;
+                if (m & kLast)  // word end candidate (:400-404)
+                    sEnd[w] = make_float2(__fadd_rn(hs[k], sExit[w]), __int_as_float(bestB));
+            }
+            if (lane == 31)  // publish my last two states for the next warp's next frame
+                xch[(par ^ 1) * nWarps + warp] =
+                        make_float4(hs[NPT - 2], hs[NPT - 1], __int_as_float(hb[NPT - 2]), __int_as_float(hb[NPT - 1]));
         }
-        if (lane == 31)  // publish my last two states for the next warp's next frame
-            xch[(par ^ 1) * nWarps + warp] =
-                    make_float4(hs[NPT - 2], hs[NPT - 1], __int_as_float(hb[NPT - 2]), __int_as_float(hb[NPT - 1]));
         __syncthreads();
-        // per 32-word chunk: smallest candidate, its first lane, the second smallest
+        // per 32-word chunk: smallest candidate, the second smallest, and for the first word holding the smallest its
+        // index, lmScore and back pointer
         for (uint32_t c = warp; c < nChunks; c += nWarps) {
-            const uint32_t w   = c * 32 + lane;
-            const uint32_t key = w < p.W ? float_key(sEnd[w].x) : 0xffffffffu;
+            const uint32_t w  = c * 32 + lane;
+            float2         en = make_float2(FLT_MAX, __int_as_float(-1));
+            float          un = 0.0f;
+            if (w < p.W) {
+                en = sEnd[w];
+                un = sUni[w];
+            }
+            const uint32_t key = w < p.W ? float_key(en.x) : 0xffffffffu;
             const uint32_t k1  = __reduce_min_sync(0xffffffffu, key);
             const int      i1  = __ffs(__ballot_sync(0xffffffffu, key == k1)) - 1;
             const uint32_t k2  = __reduce_min_sync(0xffffffffu, lane == i1 ? 0xffffffffu : key);
-            if (lane == 0)
-                cInfo[c] = make_uint4(k1, k2, (uint32_t)i1, 0u);
+            if (lane == i1) {
+                const int   bk = __float_as_int(en.y);
+                const float lm = bk >= 0 ? __fadd_rn(un, sBkLm[bk]) : un;  // the hypothesis' lmScore
+                cInfo[c] = make_uint4(k1, k2, w, __float_as_uint(lm));
+                cBkp[c]  = bk;
+            }
         }
         cp_async_wait_all();  // next frame's score row has landed (made visible by the barriers below)
         __syncthreads();
         if (warp == 0) {
             float nbScore = FLT_MAX, nbLm = 0.0f;
-            int   nbWord = -1;
+            int   nbWord = -1, nbBkp = -1;
             // combine the chunks: lane-local over chunks lane, lane + 32, ..., then across lanes
-            uint32_t best1 = 0xffffffffu, best2 = 0xffffffffu, bestJ = 0;
-            for (uint32_t c = lane; c < nChunks; c += 32) {
+            uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+            int   bestBk = -1;
+            if ((uint32_t)lane < nChunks) {
+                best   = cInfo[lane];
+                bestBk = cBkp[lane];
+            }
+#pragma unroll 1
+            for (uint32_t c = lane + 32; c < nChunks; c += 32) {
                 const uint4 ci = cInfo[c];
-                if (ci.x < best1) {
-                    best2 = min(best1, ci.y);
-                    best1 = ci.x;
-                    bestJ = c * 32 + ci.z;
+                if (ci.x < best.x) {
+                    const uint32_t second = min(best.x, ci.y);
+                    best   = ci;
+                    best.y = second;
+                    bestBk = cBkp[c];
                 }
                 else
-                    best2 = min(best2, ci.x);
+                    best.y = min(best.y, ci.x);
             }
-            const uint32_t kM  = __reduce_min_sync(0xffffffffu, best1);
-            const int      lj  = __ffs(__ballot_sync(0xffffffffu, best1 == kM)) - 1;
-            const uint32_t kM2 = __reduce_min_sync(0xffffffffu, lane == lj ? best2 : best1);
+            const uint32_t kM  = __reduce_min_sync(0xffffffffu, best.x);
+            const int      lj  = __ffs(__ballot_sync(0xffffffffu, best.x == kM)) - 1;
+            const uint32_t kM2 = __reduce_min_sync(0xffffffffu, lane == lj ? best.y : best.x);
             const float    M = key_float(kM), M2 = key_float(kM2);
-            const float    slack = __fmul_rn(__fadd_rn(fabsf(M), __fadd_rn(p.maxAbsUni, maxAbsBkLm)), 4.76837158203125e-07f);
+            const float    slack = __fmul_rn(__fadd_rn(fabsf(M), __fadd_rn(p.maxAbsUni, sMaxLm)), 4.76837158203125e-07f);
             if (!p.forceScan && M2 > __fadd_rn(M, slack)) {
                 if (M < FLT_MAX) {  // the scan accepts the unique minimum last
-                    nbWord       = (int)__shfl_sync(0xffffffffu, bestJ, lj);
-                    const int bk = __float_as_int(sEnd[nbWord].y);
-                    nbLm         = bk >= 0 ? __fadd_rn(sUni[nbWord], sBkLm[bk]) : sUni[nbWord];
-                    nbScore      = __fsub_rn(M, nbLm);
+                    nbWord  = (int)__shfl_sync(0xffffffffu, best.z, lj);
+                    nbLm    = __uint_as_float(__shfl_sync(0xffffffffu, best.w, lj));
+                    nbBkp   = __shfl_sync(0xffffffffu, bestBk, lj);
+                    nbScore = __fsub_rn(M, nbLm);
                 }
             }
             else {
                 // the sequential scan over the words, replayed on the chunks that matter
+#pragma unroll 1
                 for (uint32_t cbase = 0; cbase < nChunks; cbase += 32) {
                     const uint32_t cc    = cbase + lane;
                     const float    cmin  = cc < nChunks ? key_float(cInfo[cc].x) : FLT_MAX;
@@ -470,9 +502,10 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
                         const uint32_t base = (cbase + cf) * 32;
                         const uint32_t w    = base + lane;
                         float          cand = FLT_MAX, lmw = 0.0f;
+                        int            bk   = -1;
                         if (w < p.W) {
                             const float2 en = sEnd[w];
-                            const int    bk = __float_as_int(en.y);
+                            bk   = __float_as_int(en.y);
                             cand = en.x;
                             lmw  = bk >= 0 ? __fadd_rn(sUni[w], sBkLm[bk]) : sUni[w];  // the hypothesis' lmScore
                         }
@@ -485,6 +518,7 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
                             const int   first    = __ffs(hits) - 1;
                             const float tmpScore = __shfl_sync(0xffffffffu, cand, first);
                             nbLm    = __shfl_sync(0xffffffffu, lmw, first);
+                            nbBkp   = __shfl_sync(0xffffffffu, bk, first);
                             nbScore = __fsub_rn(tmpScore, nbLm);
                             nbWord  = (int)(base + first);
                             todo    = first == 31 ? 0u : (0xffffffffu << (first + 1));
@@ -493,19 +527,17 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
                     }
                 }
             }
-            if (nbScore != FLT_MAX) {
-                maxAbsBkLm = fmaxf(maxAbsBkLm, fabsf(nbLm));
-                if (lane == 0) {
-                    const int b = sLast + 1;  // entries are only ever appended: the newest is the last
-                    p.bookScore[f0 + b] = nbScore;
-                    p.bookLm[f0 + b]    = nbLm;
-                    p.bookWord[f0 + b]  = nbWord;
-                    p.bookBkp[f0 + b]   = __float_as_int(sEnd[nbWord].y);
-                    p.bookTime[f0 + b]  = t;
-                    sBkLm[b]            = nbLm;
-                    sLast               = b;
-                    sLastScore          = nbScore;
-                    sLastLm             = nbLm;
+            if (nbScore != FLT_MAX && lane == 0) {
+                {
+                    const int b     = sLast + 1;  // entries are only ever appended: the newest is the last
+                    int4*     books = p.books + 2 * (f0 + b);
+                    books[0] = make_int4(__float_as_int(nbScore), __float_as_int(nbLm), nbWord, nbBkp);
+                    books[1] = make_int4(t, 0, 0, 0);
+                    sMaxLm   = fmaxf(sMaxLm, fabsf(nbLm));
+                    sBkLm[b]         = nbLm;
+                    sLast            = b;
+                    sLastScore       = nbScore;
+                    sLastLm          = nbLm;
                 }
             }
         }
@@ -526,8 +558,9 @@ struct rb_search {
     float                maxAbsUni = 0.0f;
     int                  npt = 0, regThreads = 0;  // states per thread / threads of the register-resident kernel, 0: per-word kernel
     uint32_t             maxEmis = 0;
-    rb::DevBuf<float>    dTdp, dUnigram, dHypScore, dHypLm, dBookScore, dBookLm, dEndScore, dScores;
-    rb::DevBuf<int>      dHypBkp, dBookWord, dBookBkp, dBookTime, dNBooks;
+    rb::DevBuf<float>    dTdp, dUnigram, dHypScore, dHypLm, dEndScore, dScores;
+    rb::DevBuf<int>      dHypBkp, dBooks, dNBooks;  // dBooks: 8 words per frame (two int4 per book entry)
+    std::vector<int>     hostBooks;
     rb::DevBuf<int64_t>  dFrameOff;
     // results of the last decode, on the host
     std::vector<int64_t> frameOff;
@@ -616,6 +649,8 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
                 if (atoi(e) * (uint32_t)kThreads >= nStates && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16))
                     h->npt = atoi(e);
             h->regThreads = (int)(((nStates + h->npt - 1) / h->npt + 31) / 32 * 32);
+            // one warp per 32-word chunk of the book keeping where that fits (warps without states skip the update)
+            h->regThreads = std::max(h->regThreads, (int)std::min<uint32_t>(kThreads, (lx->n_words + 31) / 32 * 32));
             h->maxEmis    = maxEmis;
             values.resize(kMaxValues, inf);
             if (h->dStateMeta.upload(meta.data(), meta.size(), h->stream) != RB_OK ||
@@ -666,11 +701,7 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
     RB_CHECK(h->dHypLm.reserve(stride * n_utt));
     RB_CHECK(h->dHypBkp.reserve(stride * n_utt));
     RB_CHECK(h->dEndScore.reserve((size_t)h->W * n_utt));
-    RB_CHECK(h->dBookScore.reserve((size_t)T));
-    RB_CHECK(h->dBookLm.reserve((size_t)T));
-    RB_CHECK(h->dBookWord.reserve((size_t)T));
-    RB_CHECK(h->dBookBkp.reserve((size_t)T));
-    RB_CHECK(h->dBookTime.reserve((size_t)T));
+    RB_CHECK(h->dBooks.reserve((size_t)T * 8));
     RB_CHECK(h->dNBooks.reserve((size_t)n_utt));
     RB_CHECK(h->dFrameOff.reserve((size_t)n_utt + 1));
     RB_CUDA(cudaMemcpyAsync(h->dFrameOff.p, h->frameOff.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, s));
@@ -690,22 +721,20 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
     p.hypScore   = h->dHypScore.p;
     p.hypLm      = h->dHypLm.p;
     p.hypBkp     = h->dHypBkp.p;
-    p.bookScore  = h->dBookScore.p;
-    p.bookLm     = h->dBookLm.p;
-    p.bookWord   = h->dBookWord.p;
-    p.bookBkp    = h->dBookBkp.p;
-    p.bookTime   = h->dBookTime.p;
+    p.books      = reinterpret_cast<int4*>(h->dBooks.p);
     p.nBooks     = h->dNBooks.p;
     p.endScore   = h->dEndScore.p;
     int64_t maxT = 0;
     for (int u = 0; u < n_utt; ++u)
         maxT = std::max(maxT, h->frameOff[u + 1] - h->frameOff[u]);
     const uint32_t rowFloats = ((uint32_t)n_emissions + 3) & ~3u;
-    const uint32_t nChunks   = (h->W + 31) / 32;
-    const size_t   smem2     = 128 + (size_t)(h->regThreads / 32) * 32 + (size_t)nChunks * 16 + (size_t)(h->W + (h->W & 1)) * 8 +
-                         (size_t)rowFloats * 8 + ((size_t)h->W * 2 + (size_t)maxT) * 4;
+    const SmemLayout lay(h->regThreads / 32, h->W, rowFloats, (uint32_t)maxT);
+    const size_t     smem2 = lay.total;
     if (h->npt && h->maxEmis < (uint32_t)n_emissions && smem2 <= h->dev.smem_optin - 1024) {
         SearchParams2 q;
+        q.lay       = lay;
+        q.nChunks   = (h->W + 31) / 32;
+        q.nStates   = h->nStates;
         q.stMeta    = h->dStateMeta.p;
         q.stEmOff   = h->dStateEmOff.p;
         q.values    = h->dValues.p;
@@ -719,11 +748,7 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
         q.scores    = d_scores;
         q.frameOff  = h->dFrameOff.p;
         q.nEmis     = n_emissions;
-        q.bookScore = h->dBookScore.p;
-        q.bookLm    = h->dBookLm.p;
-        q.bookWord  = h->dBookWord.p;
-        q.bookBkp   = h->dBookBkp.p;
-        q.bookTime  = h->dBookTime.p;
+        q.books     = reinterpret_cast<int4*>(h->dBooks.p);
         q.nBooks    = h->dNBooks.p;
         auto k = h->npt == 2 ? linear_search_reg_kernel<2>
                              : (h->npt == 4 ? linear_search_reg_kernel<4>
@@ -744,13 +769,19 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
     h->bookWord.resize(T);
     h->bookBkp.resize(T);
     h->bookTime.resize(T);
-    RB_CUDA(cudaMemcpyAsync(h->bookScore.data(), h->dBookScore.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
-    RB_CUDA(cudaMemcpyAsync(h->bookLm.data(), h->dBookLm.p, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
-    RB_CUDA(cudaMemcpyAsync(h->bookWord.data(), h->dBookWord.p, sizeof(int) * T, cudaMemcpyDeviceToHost, s));
-    RB_CUDA(cudaMemcpyAsync(h->bookBkp.data(), h->dBookBkp.p, sizeof(int) * T, cudaMemcpyDeviceToHost, s));
-    RB_CUDA(cudaMemcpyAsync(h->bookTime.data(), h->dBookTime.p, sizeof(int) * T, cudaMemcpyDeviceToHost, s));
+    h->hostBooks.resize((size_t)T * 8);
+    RB_CUDA(cudaMemcpyAsync(h->hostBooks.data(), h->dBooks.p, sizeof(int) * 8 * T, cudaMemcpyDeviceToHost, s));
     RB_CUDA(cudaMemcpyAsync(h->nBooks.data(), h->dNBooks.p, sizeof(int) * n_utt, cudaMemcpyDeviceToHost, s));
     RB_CUDA(cudaStreamSynchronize(s));
+    for (int u = 0; u < n_utt; ++u)
+        for (int64_t b = h->frameOff[u], e = b + h->nBooks[u]; b < e; ++b) {
+            const int* r = h->hostBooks.data() + b * 8;
+            memcpy(&h->bookScore[b], r, 4);
+            memcpy(&h->bookLm[b], r + 1, 4);
+            h->bookWord[b] = r[2];
+            h->bookBkp[b]  = r[3];
+            h->bookTime[b] = r[4];
+        }
     return RB_OK;
 }
 
