@@ -116,3 +116,138 @@ def write_mixture_set(path, ms):
         out.append(" " + " ".join([str(row.size)] + ["%s 1" % g32(v) for v in row]))
     with _open(path, "wb") as f:
         f.write(("\n".join(out) + "\n").encode("ascii"))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Math::Matrix / Math::Vector files: the Nn layer parameters, priors, LDA matrices, normalisation vectors.
+#
+# A file name may carry a format qualifier "bin:" or "xml:" (Core::FormatSet, src/Core/FormatSet.cc:21-49); without
+# one the Math formats default to XML (registered with isDefault = true, src/Math/Module.cc:26-40).
+#   bin  (Core::BinaryFormat, src/Core/FormatSet.hh:244-256; little endian, src/Core/BinaryStream.hh:65):
+#        matrix: u32 nRows, u32 nColumns, then elem_ = vector<Vector<T>>: u32 nRows, per row u32 nColumns + data
+#                (src/Math/Matrix.hh:560-575, src/Core/BinaryStream.hh:209-215, src/Math/Vector.hh:286-299)
+#        vector: u32 size + data
+#   xml  <matrix-f32 nRows=".." nColumns=".."> row after row, whitespace separated </matrix-f32>
+#        (src/Core/MatrixParser.hh:76-112, writer src/Math/Matrix.hh:642-647), <vector-f32 size=".."> (size optional,
+#        src/Core/VectorParser.hh:78-103); values are read with `istream >> T`, written in scientific notation.
+# ----------------------------------------------------------------------------------------------------------------
+import re
+import struct
+
+_TYPES = {"f32": np.float32, "f64": np.float64, "s32": np.int32, "u32": np.uint32}
+
+
+def split_qualifier(filename, default="xml"):
+    """("bin"|"xml"|..., path) of a FormatSet file name"""
+    filename = str(filename)
+    pos = filename.find(":")
+    return (default, filename) if pos < 0 else (filename[:pos], filename[pos + 1:])
+
+
+def _parse_values(text, dtype):
+    toks = text.split()
+    if dtype == np.float32:
+        return np.array([_f32(t.encode()) for t in toks], np.float32)  # single rounding, like `istream >> float`
+    if dtype == np.float64:
+        return np.array([float(t) for t in toks], np.float64)
+    return np.array([int(t) for t in toks], dtype)
+
+
+def _xml_element(data, kind):
+    m = re.search(rb"<(%s-([a-z0-9]+))\b([^>]*)>(.*?)</\1\s*>" % kind.encode(), data, re.S)
+    if not m:
+        raise ValueError("no <%s-*> element found" % kind)
+    atts = dict((k.decode(), v.decode()) for k, v in re.findall(rb'(\w+)\s*=\s*"([^"]*)"', m.group(3)))
+    tname = m.group(2).decode()
+    if tname not in _TYPES:
+        raise ValueError("unsupported element type %s-%s" % (kind, tname))
+    return _TYPES[tname], atts, m.group(4).decode()
+
+
+def read_matrix(filename, dtype=np.float32):
+    """Math::Matrix<T> from a `bin:` or `xml:` (default) file -> array [nRows, nColumns]"""
+    fmt, path = split_qualifier(filename)
+    with _open(path, "rb") as f:
+        data = f.read()
+    if fmt == "bin":
+        dt = np.dtype(dtype).newbyteorder("<")
+        n_rows, n_cols, n_vec = struct.unpack_from("<III", data, 0)
+        if n_vec != n_rows:
+            raise ValueError("%s: %d row vectors for a %d x %d matrix" % (path, n_vec, n_rows, n_cols))
+        out = np.empty((n_rows, n_cols), dtype)
+        pos = 12
+        for r in range(n_rows):
+            (n,) = struct.unpack_from("<I", data, pos)
+            if n != n_cols:
+                raise ValueError("%s: row %d has %d elements, expected %d" % (path, r, n, n_cols))
+            out[r] = np.frombuffer(data, dt, n, pos + 4)
+            pos += 4 + n * dt.itemsize
+        return out
+    if fmt != "xml":
+        raise ValueError("unknown matrix format '%s'" % fmt)
+    etype, atts, text = _xml_element(data, "matrix")
+    if "nRows" not in atts or "nColumns" not in atts:
+        raise ValueError("%s: nRows / nColumns attribute not given" % path)  # MatrixParser.hh:83-91
+    n_rows, n_cols = int(atts["nRows"]), int(atts["nColumns"])
+    vals = _parse_values(text, etype)
+    if vals.size != n_rows * n_cols:
+        raise ValueError("%s: %d elements for a %d x %d matrix" % (path, vals.size, n_rows, n_cols))
+    return vals.reshape(n_rows, n_cols).astype(dtype, copy=False)
+
+
+def read_vector(filename, dtype=np.float32):
+    fmt, path = split_qualifier(filename)
+    with _open(path, "rb") as f:
+        data = f.read()
+    if fmt == "bin":
+        (n,) = struct.unpack_from("<I", data, 0)
+        return np.frombuffer(data, np.dtype(dtype).newbyteorder("<"), n, 4).astype(dtype)
+    if fmt != "xml":
+        raise ValueError("unknown vector format '%s'" % fmt)
+    etype, atts, text = _xml_element(data, "vector")
+    vals = _parse_values(text, etype)
+    if "size" in atts and int(atts["size"]) != vals.size:
+        raise ValueError("%s: vector dimension mismatch: %s given and %d read" % (path, atts["size"], vals.size))
+    return vals.astype(dtype, copy=False)
+
+
+def _type_name(a):
+    for k, v in _TYPES.items():
+        if a.dtype == v:
+            return k
+    raise ValueError("unsupported dtype %s" % a.dtype)
+
+
+def _sci(a, precision):
+    fmt = "%%.%de" % precision if a.dtype.kind == "f" else "%d"
+    return " ".join(fmt % v for v in a)
+
+
+def write_matrix(filename, m, precision=20):
+    """the writer the Nn trainer uses (formats().write(filename, parameters, 20), src/Nn/LinearLayer.cc:284)"""
+    fmt, path = split_qualifier(filename)
+    m = np.ascontiguousarray(m)
+    with _open(path, "wb") as f:
+        if fmt == "bin":
+            f.write(struct.pack("<III", m.shape[0], m.shape[1], m.shape[0]))
+            for row in m:
+                f.write(struct.pack("<I", m.shape[1]) + row.astype(m.dtype.newbyteorder("<")).tobytes())
+        else:
+            t = _type_name(m)
+            f.write(('<?xml version="1.0" encoding="UTF-8"?>\n<matrix-%s nRows="%d" nColumns="%d">\n'
+                     % (t, m.shape[0], m.shape[1])).encode())
+            for row in m:
+                f.write((_sci(row, precision) + " \n").encode())
+            f.write(("</matrix-%s>\n" % t).encode())
+
+
+def write_vector(filename, v, precision=20):
+    fmt, path = split_qualifier(filename)
+    v = np.ascontiguousarray(v)
+    with _open(path, "wb") as f:
+        if fmt == "bin":
+            f.write(struct.pack("<I", v.size) + v.astype(v.dtype.newbyteorder("<")).tobytes())
+        else:
+            t = _type_name(v)
+            f.write(('<?xml version="1.0" encoding="UTF-8"?>\n<vector-%s size="%d">\n%s \n</vector-%s>\n'
+                     % (t, v.size, _sci(v, precision), t)).encode())

@@ -37,6 +37,26 @@ class NnScorer:
                                            C.byref(self._h)))
         self.n_inputs, self.n_outputs = self.dims[0], self.dims[-1]
 
+    @classmethod
+    def from_files(cls, layer_files, acts, prior_file=None, prior_scale=1.0, **kw):
+        """Build the scorer from the reference's per-layer parameter files (one Math::Matrix per layer, row = output
+        unit, column 0 = bias: LinearLayer::loadNetworkParameters / setParameters, src/Nn/LinearLayer.cc:219-237,
+        383-424) and its log-prior vector file (Prior::read, src/Nn/Prior.cc:216-228).  File names may carry the
+        "bin:" / "xml:" qualifier."""
+        from . import io
+        ws, bs = [], []
+        for f in layer_files:
+            w, b = parameters_from_matrix(io.read_matrix(f))
+            ws.append(w)
+            bs.append(b)
+        for l in range(1, len(ws)):
+            if ws[l].shape[1] != ws[l - 1].shape[0]:
+                raise capi.RasrB200Error(-1, "dimension mismatch: (parameter file vs. layer-dimension) %d vs. %d"
+                                         % (ws[l].shape[1], ws[l - 1].shape[0]))
+        dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+        prior = io.read_vector(prior_file) if prior_file else None
+        return cls(dims, acts, ws, bs, prior, prior_scale, **kw)
+
     def close(self):
         if getattr(self, "_h", None):
             capi.lib().rb_nn_destroy(self._h)

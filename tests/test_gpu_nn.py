@@ -133,3 +133,28 @@ def test_bf16_frames_are_independent():
     whole = sc.score(x)
     assert np.array_equal(whole[:7777], sc.score(x[:7777]))
     assert np.array_equal(whole[7777:], sc.score(x[7777:]))
+
+
+def test_scorer_from_reference_parameter_files(oracle, tmp_path):
+    """layer matrices and the prior written in the reference's file formats (bin and xml), loaded back, scored"""
+    from rasr_b200 import io as rio
+    rng = np.random.default_rng(31)
+    dims, acts = [24, 64, 40], ["sigmoid", "softmax"]
+    files = []
+    ws, bs = [], []
+    for l in range(2):
+        w = (rng.standard_normal((dims[l + 1], dims[l])) / np.sqrt(dims[l])).astype(np.float32)
+        b = (rng.standard_normal(dims[l + 1]) * 0.1).astype(np.float32)
+        name = ("bin:" if l == 0 else "xml:") + str(tmp_path / ("layer%d" % l))
+        rio.write_matrix(name, np.concatenate([b[:, None], w], axis=1))
+        files.append(name)
+        ws.append(w)
+        bs.append(b)
+    prior = np.log(rng.dirichlet(np.ones(dims[-1]))).astype(np.float32)
+    rio.write_vector(str(tmp_path / "prior.xml"), prior)
+    x = rng.standard_normal((50, dims[0])).astype(np.float32)
+    got = nn.NnScorer.from_files(files, acts, str(tmp_path / "prior.xml"), 0.7, precision="f32").score(x)
+    ref = nn.NnScorer(dims, acts, ws, bs, prior, 0.7, precision="f32").score(x)
+    assert np.array_equal(got, ref)
+    want = oracle.nn_scores(dims, acts, ws, bs, prior, 0.7, x)
+    assert np.allclose(got, want, rtol=1e-4, atol=1e-4)

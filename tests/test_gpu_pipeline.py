@@ -70,3 +70,26 @@ def test_audio_to_nn_scores_pipeline(oracle, diag):
     assert np.array_equal(s2, sc39.score(r["feats"]))
     with pytest.raises(Exception):
         pipeline.nn_score_utterances(fe, None, sc, samples, offs)  # 39-dim features into a 429-dim network
+
+
+def test_features_through_a_feature_cache(tmp_path):
+    """what a two-pass RASR setup does: the extraction run writes the features to a cache archive (one entry per
+    segment, timestamps included), the recognition run reads them back and scores them"""
+    from rasr_b200 import cache
+    samples, offs = synth.corpus(3, n_samples=8240)
+    fe = flow.FrontEnd()
+    r = fe.process(samples, offs)
+    fo = r["frame_offsets"]
+    with cache.FileArchive(tmp_path / "mfcc.cache", "w") as a:
+        for u in range(3):
+            sl = slice(int(fo[u]), int(fo[u + 1]))
+            cache.write_features(a, "corpus/rec/%d" % u, r["feats"][sl], np.stack([r["t_start"][sl], r["t_end"][sl]], 1),
+                                 {"datatype": "vector-f32", "sample-rate": "100"}, compress=(u == 1))
+    gmm = mm.GmmScorer(mm.MixtureSet.from_dict(synth.mixture_set()))
+    want = gmm.score(r["feats"])
+    with cache.FileArchive(tmp_path / "mfcc.cache") as a:
+        for u in range(3):
+            f, t, atts = cache.read_features(a, "corpus/rec/%d" % u)
+            sl = slice(int(fo[u]), int(fo[u + 1]))
+            assert np.array_equal(f, r["feats"][sl]) and np.array_equal(t[:, 0], r["t_start"][sl])
+            assert np.array_equal(gmm.score(f), want[sl])

@@ -77,3 +77,149 @@ def test_loaded_model_scores_like_the_in_memory_one(oracle, tmp_path):
     a = oracle.gmm_batch_float(oracle.MixtureSet(**msd), f)
     b = oracle.gmm_batch_float(oracle.MixtureSet(**rio.read_mixture_set(p)), f)
     assert np.array_equal(a, b)
+
+
+# ---- Math::Matrix / Math::Vector files (Nn layer parameters, priors) ------------------------------------------------
+
+def test_reads_hand_written_matrix_and_vector_xml(tmp_path):
+    """the layout of src/Core/MatrixParser.hh:76-112 / VectorParser.hh:78-103: attributes, row after row, line breaks
+    without meaning, optional size"""
+    p = tmp_path / "m.xml"
+    p.write_text('<?xml version="1.0" encoding="ISO-8859-1"?>\n<matrix-f32 nRows="2" nColumns="3">\n'
+                 "1 2.5\n-3e-1 4 5\n6.25e+00\n</matrix-f32>\n")
+    m = rio.read_matrix(str(p))
+    assert m.dtype == np.float32 and np.array_equal(m, np.array([[1, 2.5, -0.3], [4, 5, 6.25]], np.float32))
+    assert np.array_equal(rio.read_matrix("xml:" + str(p)), m)
+    v = tmp_path / "v.xml"
+    v.write_text('<vector-f32 size="3"> 0.1 0.2 0.3 </vector-f32>')
+    assert np.array_equal(rio.read_vector(str(v)), np.array([0.1, 0.2, 0.3], np.float32))
+    v.write_text("<vector-f64> 0.1 0.2 </vector-f64>")
+    assert np.array_equal(rio.read_vector(str(v), np.float64), np.array([0.1, 0.2]))
+    v.write_text('<vector-f32 size="4"> 0.1 0.2 0.3 </vector-f32>')
+    with pytest.raises(ValueError):
+        rio.read_vector(str(v))
+    p.write_text('<matrix-f32 nRows="2" nColumns="3"> 1 2 3 4 5 </matrix-f32>')
+    with pytest.raises(ValueError):
+        rio.read_matrix(str(p))
+    p.write_text('<matrix-f32 nRows="2"> 1 2 </matrix-f32>')
+    with pytest.raises(ValueError):
+        rio.read_matrix(str(p))
+
+
+def test_reads_hand_packed_binary_matrix(tmp_path):
+    """u32 nRows, u32 nColumns, u32 #row vectors, per row u32 size + little-endian data (src/Math/Matrix.hh:560-575)"""
+    import struct
+    p = tmp_path / "m.bin"
+    p.write_bytes(struct.pack("<III", 2, 2, 2) + struct.pack("<Iff", 2, 1.5, -2.0) + struct.pack("<Iff", 2, 0.25, 8.0))
+    assert np.array_equal(rio.read_matrix("bin:" + str(p)), np.array([[1.5, -2.0], [0.25, 8.0]], np.float32))
+    p.write_bytes(struct.pack("<III", 2, 2, 2) + struct.pack("<Iff", 2, 1.5, -2.0) + struct.pack("<Ifff", 3, 0, 0, 0))
+    with pytest.raises(ValueError):
+        rio.read_matrix("bin:" + str(p))
+
+
+@pytest.mark.parametrize("fmt", ["bin:", "xml:", ""])
+def test_matrix_and_vector_round_trip_bit_exact(tmp_path, fmt):
+    rng = np.random.default_rng(5)
+    m = (rng.standard_normal((7, 5)) * 10.0 ** rng.integers(-20, 20, (7, 5))).astype(np.float32)
+    v = rng.standard_normal(11).astype(np.float32)
+    rio.write_matrix(fmt + str(tmp_path / "m"), m)
+    rio.write_vector(fmt + str(tmp_path / "v"), v)
+    assert np.array_equal(rio.read_matrix(fmt + str(tmp_path / "m")), m)
+    assert np.array_equal(rio.read_vector(fmt + str(tmp_path / "v")), v)
+    d = rng.standard_normal((3, 4))
+    rio.write_matrix(fmt + str(tmp_path / "d"), d)
+    assert np.array_equal(rio.read_matrix(fmt + str(tmp_path / "d"), np.float64), d)
+
+
+def test_layer_parameter_files_follow_set_parameters(tmp_path):
+    """row = output unit, column 0 = bias, columns 1.. = weights (src/Nn/LinearLayer.cc:383-424)"""
+    from rasr_b200 import nn
+    param = np.arange(12, dtype=np.float32).reshape(3, 4)
+    rio.write_matrix("bin:" + str(tmp_path / "l0"), param)
+    w, b = nn.parameters_from_matrix(rio.read_matrix("bin:" + str(tmp_path / "l0")))
+    assert np.array_equal(b, [0, 4, 8]) and np.array_equal(w, [[1, 2, 3], [5, 6, 7], [9, 10, 11]])
+
+
+# ---- feature caches: Core::FileArchive + Flow cache streams ---------------------------------------------------------
+
+def _hand_packed_archive(path, with_table):
+    """bytes laid out by hand from the format comment of src/Core/FileArchive.cc:26-80"""
+    import struct
+    name = b"corpus/rec1/seg1"
+    vec = lambda v, t0, t1: struct.pack("<I", len(v)) + struct.pack("<%df" % len(v), *v) + struct.pack("<dd", t0, t1)
+    stream = (struct.pack("<I", 10) + b"vector-f32" + struct.pack("<I", 2) +
+              vec([1.0, 2.0, 3.0], 0.0, 0.025) + vec([4.0, 5.0, 6.0], 0.01, 0.035))
+    body = HEAD = b"SP_ARC1\0" + (b"\1" if with_table else b"\0")
+    body += struct.pack("<II", 0xAA55AA55, len(name)) + name
+    pos = len(body)
+    body += struct.pack("<III", len(stream), 0, 0) + stream + struct.pack("<I", 0x55AA55AA)
+    if with_table:
+        table = len(body)
+        body += struct.pack("<I", 1) + struct.pack("<I", len(name)) + name + struct.pack("<QII", pos, len(stream), 0)
+        holes = len(body)
+        body += struct.pack("<I", 0) + struct.pack("<QQ", holes, table)
+    path.write_bytes(body)
+
+
+@pytest.mark.parametrize("with_table", [True, False])
+def test_reads_hand_packed_feature_cache(tmp_path, with_table):
+    from rasr_b200 import cache
+    _hand_packed_archive(tmp_path / "f.cache", with_table)
+    with cache.FileArchive(tmp_path / "f.cache") as a:
+        assert a.names() == ["corpus/rec1/seg1"]
+        feats, times, atts = cache.read_features(a, "corpus/rec1/seg1")
+    assert feats.dtype == np.float32 and np.array_equal(feats, [[1, 2, 3], [4, 5, 6]])
+    assert np.array_equal(times, [[0.0, 0.025], [0.01, 0.035]]) and atts == {}
+
+
+@pytest.mark.parametrize("compress,gather", [(False, 0xFFFFFFFF), (True, 0xFFFFFFFF), (True, 3)])
+def test_feature_cache_round_trip(tmp_path, compress, gather):
+    import gzip as gz
+    from rasr_b200 import cache
+    rng = np.random.default_rng(8)
+    segs = {}
+    with cache.FileArchive(tmp_path / "d" / "f.cache", "w") as a:
+        for i, T in enumerate([17, 1, 40]):
+            f = rng.standard_normal((T, 39)).astype(np.float32)
+            t = np.stack([np.arange(T) * 0.01, np.arange(T) * 0.01 + 0.025], 1)
+            segs["c/r/s%d" % i] = (f, t)
+            cache.write_features(a, "c/r/s%d" % i, f, t, {"sample-rate": "100", "datatype": "vector-f32"},
+                                 gather=gather, compress=compress)
+        with pytest.raises(cache.ArchiveError):
+            a.write("c/r/s0", b"again")  # allow-overwrite is off
+    for strip_table in (False, True):
+        if strip_table:  # a writer that died before the table was written: flag 0 -> the reader scans
+            raw = bytearray((tmp_path / "d" / "f.cache").read_bytes())
+            raw[8] = 0
+            (tmp_path / "d" / "f.cache").write_bytes(bytes(raw))
+        with cache.FileArchive(tmp_path / "d" / "f.cache") as a:
+            assert sorted(a.names()) == sorted(list(segs) + [s + ".attribs" for s in segs])
+            for s, (f, t) in segs.items():
+                got, times, atts = cache.read_features(a, s)
+                assert np.array_equal(got, f) and np.array_equal(times, t)
+                assert atts == {"sample-rate": "100", "datatype": "vector-f32"}
+            if compress:  # stored entries are complete gzip members
+                pos, size, comp = a.files["c/r/s2"]
+                raw = (tmp_path / "d" / "f.cache").read_bytes()[pos + 12:pos + 12 + comp]
+                assert comp > 0 and len(gz.decompress(raw)) == size
+
+
+def test_overwrite_leaves_a_hole_that_readers_skip(tmp_path):
+    from rasr_b200 import cache
+    with cache.FileArchive(tmp_path / "a", "w", allow_overwrite=True) as a:
+        a.write("x", b"1111")
+        a.write("y", b"22")
+        a.write("x", b"333333")   # x is not the last entry: its old place becomes a hole
+        a.write("x", b"4")        # now it is the last one: the archive shrinks
+    for flag in (1, 0):
+        raw = bytearray((tmp_path / "a").read_bytes())
+        raw[8] = flag
+        (tmp_path / "a").write_bytes(bytes(raw))
+        with cache.FileArchive(tmp_path / "a") as a:
+            assert sorted(a.names()) == ["x", "y"] and a.read("x") == b"4" and a.read("y") == b"22"
+            assert len(a.holes) == 1
+    with pytest.raises(cache.ArchiveError):
+        cache.FileArchive(tmp_path / "missing")
+    (tmp_path / "junk").write_bytes(b"not an archive")
+    with pytest.raises(cache.ArchiveError):
+        cache.FileArchive(tmp_path / "junk")
