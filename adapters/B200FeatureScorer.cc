@@ -1,16 +1,21 @@
 #include "B200FeatureScorer.hh"
 
+#include <Math/Matrix.hh>
+#include <Math/Module.hh>
+#include <Math/Vector.hh>
 #include <Mm/Feature.hh>
 #include <Mm/GaussDensity.hh>
 #include <Mm/Mixture.hh>
+#include <cmath>
+#include <numeric>
 
 using namespace B200;
 
 const Core::ParameterInt   FeatureScorer::paramDevice("device", "CUDA device ordinal", 0, 0);
 const Core::ParameterInt   FeatureScorer::paramBufferSize("buffer-size", "frames buffered per dense scoring launch (default: the whole segment)", Core::Type<s32>::max, 1);
-const Core::ParameterBool  FeatureScorer::paramContraction("fma-contraction", "reproduce a CPU build with -ffp-contract=fast (gcc default) instead of a strict one", true);
-const Core::ParameterFloat FeatureScorer::paramMixtureWeightScale("mixture-weight-scale", "scale of the -log mixture weights (diagonal scorers)", 1.0);
-const Core::ParameterFloat FeatureScorer::paramGaussianScale("gaussian-scale", "scale of the Gaussian exponent (diagonal scorers)", 1.0);
+const Core::ParameterBool  GmmFeatureScorer::paramContraction("fma-contraction", "reproduce a CPU build with -ffp-contract=fast (gcc default) instead of a strict one", true);
+const Core::ParameterFloat GmmFeatureScorer::paramMixtureWeightScale("mixture-weight-scale", "scale of the -log mixture weights (diagonal scorers)", 1.0);
+const Core::ParameterFloat GmmFeatureScorer::paramGaussianScale("gaussian-scale", "scale of the Gaussian exponent (diagonal scorers)", 1.0);
 
 class FeatureScorer::ContextScorer : public Mm::FeatureScorer::ContextScorer {
 public:
@@ -28,16 +33,22 @@ private:
     u32                  segment_, frame_;
 };
 
-FeatureScorer::FeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> ms, rb_gmm_mode mode)
+FeatureScorer::FeatureScorer(const Core::Configuration& c)
         : Core::Component(c),
           Mm::FeatureScorer(c),
-          handle_(0),
-          nMixtures_(ms->nMixtures()),
-          dimension_(ms->dimension()),
+          nMixtures_(0),
+          dimension_(0),
           bufferSize_(paramBufferSize(c)),
           nScored_(0),
           nextFrame_(0),
-          segment_(0) {
+          segment_(0) {}
+
+GmmFeatureScorer::GmmFeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> ms, rb_gmm_mode mode)
+        : Core::Component(c),
+          FeatureScorer(c),
+          handle_(0) {
+    nMixtures_ = ms->nMixtures();
+    dimension_ = ms->dimension();
     // flatten Mm::MixtureSet (src/Mm/MixtureSet.hh:123-201) into the rb_mixture_set view
     std::vector<u32> mixOffsets(1, 0), mixDensity, densMean(ms->nDensities()), densCov(ms->nDensities());
     std::vector<f64> mixLogWeight;
@@ -72,8 +83,13 @@ FeatureScorer::FeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::M
         int(nMixtures_), int(ms->nDensities()), int(dimension_), int(paramDevice(c)));
 }
 
-FeatureScorer::~FeatureScorer() {
+GmmFeatureScorer::~GmmFeatureScorer() {
     rb_gmm_destroy(handle_);
+}
+
+void GmmFeatureScorer::scoreFrames(const f32* feats, u32 T, f32* scores) const {
+    if (rb_gmm_score(handle_, feats, T, scores, 0) != RB_OK)
+        criticalError("rasr_b200: %s", rb_last_error());
 }
 
 void FeatureScorer::getFeatureDescription(Mm::FeatureDescription& description) const {
@@ -114,9 +130,8 @@ Mm::FeatureScorer::Scorer FeatureScorer::getTimeIndexedScorer(u32 time) const {
 void FeatureScorer::scoreBufferedFrames() const {
     const u32 T = features_.size() / dimension_;
     scores_.resize(size_t(T) * nMixtures_);
-    if (rb_gmm_score(handle_, features_.data() + size_t(nScored_) * dimension_, T - nScored_,
-                     scores_.data() + size_t(nScored_) * nMixtures_, 0) != RB_OK)
-        criticalError("rasr_b200: %s", rb_last_error());
+    scoreFrames(features_.data() + size_t(nScored_) * dimension_, T - nScored_,
+                scores_.data() + size_t(nScored_) * nMixtures_);
     nScored_ = T;
 }
 
@@ -126,4 +141,100 @@ Mm::Score FeatureScorer::score(u32 segment, u32 frame, Mm::EmissionIndex e) cons
     if (frame >= nScored_)
         scoreBufferedFrames();
     return scores_[size_t(frame) * nMixtures_ + e];
+}
+
+// ---- Nn -------------------------------------------------------------------------------------------------------------
+
+const Core::ParameterStringVector NnFeatureScorer::paramParameterFiles("parameter-files", "parameter matrix file of every layer, bottom to top (the layers' parameters-old)", ",");
+const Core::ParameterString       NnFeatureScorer::paramHiddenActivation("hidden-activation", "activation of the hidden layers: sigmoid, rectified, tanh or linear", "sigmoid");
+const Core::ParameterString       NnFeatureScorer::paramPriorFile("prior-file", "log prior vector file; empty: estimate from the mixture weights", "");
+const Core::ParameterFloat        NnFeatureScorer::paramPrioriScale("priori-scale", "scaling of the logarithmized state priori probability", 1.0);
+const Core::ParameterBool         NnFeatureScorer::paramBf16("bf16", "bf16 operands with f32 accumulation on the tensor cores (false: f32 arithmetic)", true);
+
+NnFeatureScorer::NnFeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> ms)
+        : Core::Component(c),
+          FeatureScorer(c),
+          handle_(0) {
+    nMixtures_ = ms->nMixtures();
+    const std::vector<std::string> files = paramParameterFiles(c);
+    if (files.empty())
+        criticalError("b200-nn-batch-feature-scorer: no parameter-files given");
+    const std::string hidden = paramHiddenActivation(c);
+    int               hiddenAct;
+    if (hidden == "sigmoid")
+        hiddenAct = RB_ACT_SIGMOID;
+    else if (hidden == "rectified" || hidden == "relu")
+        hiddenAct = RB_ACT_RELU;
+    else if (hidden == "tanh")
+        hiddenAct = RB_ACT_TANH;
+    else if (hidden == "linear")
+        hiddenAct = RB_ACT_LINEAR;
+    else
+        criticalError("unknown hidden-activation '%s'", hidden.c_str());
+
+    // one Math::Matrix per layer: row = output unit, column 0 = bias, the others the weights of that unit
+    // (LinearLayer::setParameters, src/Nn/LinearLayer.cc:383-424); rb_nn_create takes weights[out][in] row-major
+    const int                     nLayers = files.size();
+    std::vector<int>              dims(nLayers + 1), acts(nLayers, hiddenAct);
+    std::vector<std::vector<f32>> weights(nLayers), biases(nLayers);
+    std::vector<const f32*>       wp(nLayers), bp(nLayers);
+    for (int l = 0; l < nLayers; ++l) {
+        Math::Matrix<f32> parameters;
+        log("reading parameter file ") << files[l] << " for layer " << l;
+        if (!Math::Module::instance().formats().read(files[l], parameters))
+            criticalError("failed to read parameter file '%s'", files[l].c_str());
+        if (parameters.nColumns() < 2)
+            criticalError("parameter file '%s' has no weight columns", files[l].c_str());
+        const u32 out = parameters.nRows(), in = parameters.nColumns() - 1;
+        if (l == 0)
+            dims[0] = in;
+        else if (u32(dims[l]) != in)
+            criticalError("dimension mismatch: (parameter file vs. layer-dimension) %d vs. %d", int(in), dims[l]);
+        dims[l + 1] = out;
+        weights[l].resize(size_t(out) * in);
+        biases[l].resize(out);
+        for (u32 r = 0; r < out; ++r) {
+            biases[l][r] = parameters[r][0];
+            for (u32 k = 0; k < in; ++k)
+                weights[l][size_t(r) * in + k] = parameters[r][k + 1];
+        }
+        wp[l] = weights[l].data();
+        bp[l] = biases[l].data();
+    }
+    acts[nLayers - 1] = RB_ACT_SOFTMAX;  // output layer must be linear+softmax; only its scores are computed
+    dimension_        = dims[0];
+    if (u32(dims[nLayers]) != nMixtures_)
+        criticalError("no one-to-one correspondence between network outputs (%d) and classes (%d)!", dims[nLayers],
+                      int(nMixtures_));
+
+    // log prior: from file, or relative mixture weight mass (Prior::setFromMixtureSet, src/Nn/Prior.cc:158-188)
+    std::vector<f32> logPrior(nMixtures_, 0.0f);
+    if (!paramPriorFile(c).empty()) {
+        Math::Vector<f32> priors;
+        if (!Math::Module::instance().formats().read(paramPriorFile(c), priors) || priors.size() != nMixtures_)
+            criticalError("failed to read a prior of dimension %d from '%s'", int(nMixtures_), paramPriorFile(c).c_str());
+        std::copy(priors.begin(), priors.end(), logPrior.begin());
+    }
+    else {
+        for (Mm::MixtureIndex m = 0; m < ms->nMixtures(); ++m)
+            for (size_t d = 0; d < ms->mixture(m)->nDensities(); ++d)
+                logPrior[m] += ms->mixture(m)->weight(d);
+        const f32 observationWeight = std::accumulate(logPrior.begin(), logPrior.end(), 0.0);
+        for (u32 m = 0; m < nMixtures_; ++m)
+            logPrior[m] = std::log(logPrior[m] / observationWeight);
+    }
+    if (rb_nn_create(nLayers, dims.data(), acts.data(), wp.data(), bp.data(), logPrior.data(), paramPrioriScale(c),
+                     paramBf16(c) ? RB_NN_BF16 : RB_NN_F32, paramDevice(c), &handle_) != RB_OK)
+        criticalError("rasr_b200: %s", rb_last_error());
+    log("b200 nn feature scorer: %d layers, %d inputs, %d outputs on device %d", nLayers, dims[0], dims[nLayers],
+        int(paramDevice(c)));
+}
+
+NnFeatureScorer::~NnFeatureScorer() {
+    rb_nn_destroy(handle_);
+}
+
+void NnFeatureScorer::scoreFrames(const f32* feats, u32 T, f32* scores) const {
+    if (rb_nn_score(handle_, feats, T, scores) != RB_OK)
+        criticalError("rasr_b200: %s", rb_last_error());
 }

@@ -6,7 +6,8 @@
  * src/Onnx/OnnxFeatureScorer.{hh,cc}: addFeature() collects the segment, the first flush()/score() runs ONE
  * dense rb_gmm_score over all buffered frames, ContextScorer::score(e) is then a lookup into the T x nMix
  * matrix.  Selected with  feature-scorer-type = b200-batch-float | b200-diagonal-maximum | b200-diagonal-sum
- * | b200-batch-tensor | b200-batch-int.
+ * | b200-batch-tensor | b200-batch-int (GmmFeatureScorer -> the rb_gmm calls)  or  b200-nn-batch-feature-scorer
+ * (NnFeatureScorer -> the rb_nn calls, the drop-in for src/Nn/BatchFeatureScorer.{hh,cc}).
  */
 #ifndef _B200_FEATURE_SCORER_HH
 #define _B200_FEATURE_SCORER_HH
@@ -20,16 +21,15 @@
 
 namespace B200 {
 
+/** Buffering half of the adapters: collects the segment, scores all frames not scored yet in one call of the
+ *  subclass, answers ContextScorer::score(e) from the dense matrix. */
 class FeatureScorer : public Mm::FeatureScorer {
 public:
-    static const Core::ParameterInt   paramDevice;              // CUDA ordinal
-    static const Core::ParameterInt   paramBufferSize;          // frames buffered before bufferFilled()
-    static const Core::ParameterBool  paramContraction;         // FMA contraction like the default CPU build
-    static const Core::ParameterFloat paramMixtureWeightScale;  // as Mm::GaussDiagonalMaximumFeatureScorer
-    static const Core::ParameterFloat paramGaussianScale;
+    static const Core::ParameterInt paramDevice;      // CUDA ordinal
+    static const Core::ParameterInt paramBufferSize;  // frames buffered before bufferFilled()
 
-    FeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> mixtureSet, rb_gmm_mode mode);
-    virtual ~FeatureScorer();
+    FeatureScorer(const Core::Configuration& c);
+    virtual ~FeatureScorer() {}
 
     virtual Mm::EmissionIndex nMixtures() const {
         return nMixtures_;
@@ -73,10 +73,15 @@ private:
     Mm::Score score(u32 segment, u32 frame, Mm::EmissionIndex e) const;
     void      scoreBufferedFrames() const;
 
-    rb_gmm*           handle_;
+protected:
+    /** scores [T x nMixtures_] of feats [T x dimension_], both row-major */
+    virtual void scoreFrames(const f32* feats, u32 T, f32* scores) const = 0;
+
     Mm::EmissionIndex nMixtures_;
     u32               dimension_;
     u32               bufferSize_;
+
+private:
     // all methods of the interface are const => the state is mutable (src/Mm/BatchFeatureScorer.hh:164-166)
     mutable std::vector<f32> features_;  // T x D row-major, the segment so far
     mutable std::vector<f32> scores_;    // T x nMix row-major, rows [0, nScored_)
@@ -85,11 +90,51 @@ private:
     mutable u32              segment_;    // guards delayed score() calls across reset()
 };
 
+class GmmFeatureScorer : public FeatureScorer {
+public:
+    static const Core::ParameterBool  paramContraction;         // FMA contraction like the default CPU build
+    static const Core::ParameterFloat paramMixtureWeightScale;  // as Mm::GaussDiagonalMaximumFeatureScorer
+    static const Core::ParameterFloat paramGaussianScale;
+
+    GmmFeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> mixtureSet, rb_gmm_mode mode);
+    virtual ~GmmFeatureScorer();
+
+protected:
+    virtual void scoreFrames(const f32* feats, u32 T, f32* scores) const;
+
+private:
+    rb_gmm* handle_;
+};
+
 template<rb_gmm_mode mode>
-class FeatureScorerOf : public FeatureScorer {
+class FeatureScorerOf : public GmmFeatureScorer {
 public:
     FeatureScorerOf(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> m)
-            : Core::Component(c), FeatureScorer(c, m, mode) {}
+            : Core::Component(c), GmmFeatureScorer(c, m, mode) {}
+};
+
+/** Feed-forward network scorer: score(e) = -(w_e.h + b_e - priori-scale * logprior_e), the top-layer softmax is not
+ *  evaluated (src/Nn/BatchFeatureScorer.cc:45-171, LinearAndActivationLayer.cc:154-160).  The network is given as
+ *  one parameter file per layer in the reference's Math::Matrix format (row = output unit, column 0 = bias,
+ *  src/Nn/LinearLayer.cc:219-237,383-424) plus the hidden activation; the prior comes from `prior-file` or, like
+ *  Prior::setFromMixtureSet (src/Nn/Prior.cc:158-188), from the mixture weights.  Network outputs map one-to-one to
+ *  the emission indices (ClassLabelWrapper without disregarded classes). */
+class NnFeatureScorer : public FeatureScorer {
+public:
+    static const Core::ParameterStringVector paramParameterFiles;  // "parameters-old" of the layers, bottom to top
+    static const Core::ParameterString       paramHiddenActivation;
+    static const Core::ParameterString       paramPriorFile;
+    static const Core::ParameterFloat        paramPrioriScale;
+    static const Core::ParameterBool         paramBf16;
+
+    NnFeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> mixtureSet);
+    virtual ~NnFeatureScorer();
+
+protected:
+    virtual void scoreFrames(const f32* feats, u32 T, f32* scores) const;
+
+private:
+    rb_nn* handle_;
 };
 
 }  // namespace B200
