@@ -133,6 +133,35 @@ int rb_frontend_process_dev(rb_frontend* h, const float* d_samples, const int64_
 int rb_frontend_set_debug(rb_frontend* h, int on);
 int rb_frontend_read_stages(rb_frontend* h, float* amplitude, float* fbank, float* cepstra);
 
+/* -------------------------------------------------------------------------------------
+ * signal-dc-detection in front of the MFCC chain (src/Signal/DcDetection.{hh,cc}; wired by
+ * src/Tools/FeatureExtraction/share/samples.flow:34-37): stretches of at least min_dc_length_s whose samples stay
+ * within max_dc_increment of the last non-DC sample are discarded, as are non-DC segments shorter than
+ * min_non_dc_segment_length_s.  Every kept run of samples is framed on its own (pre-emphasis and window restart
+ * at the gap, Preemphasis.cc:54-55, SlidingAlgorithmNode.hh:83-99) and starts at its own time; the derivative
+ * window runs across the runs of an utterance (the delay node ignores time stamps, src/Signal/Delay.cc:137-160).
+ * ------------------------------------------------------------------------------------- */
+typedef struct rb_dc_cfg {
+    double min_dc_length_s;             /* DcDetectionNode::paramMinDcLength,  DcDetection.cc:231-232 */
+    float  max_dc_increment;            /* paramMaxDcIncrement :234-235; 0: every sample is non-DC */
+    double min_non_dc_segment_length_s; /* paramMinNonDcSegmentLength :237-238 */
+    int    maximal_output_size;         /* paramMaximalOutputSize :240-241 (only shapes the accumulated start times) */
+} rb_dc_cfg;
+void rb_dc_default_cfg(rb_dc_cfg* cfg); /* the values samples.flow sets: .0125, 0.9, .026; 4096 */
+/* upper bound of the frames rb_frontend_process_dc can produce for these utterance lengths */
+long rb_frontend_dc_max_frames(const rb_frontend* h, const rb_dc_cfg* dc, const int64_t* offsets, int n_utt);
+/* like rb_frontend_process, but the frame counts depend on the data: feats/t_start/t_end have room for `capacity`
+ * frames (RB_ERR_INVALID if that is too small), frame_offsets [n_utt + 1] receives the frame range of every
+ * utterance. */
+int rb_frontend_process_dc(rb_frontend* h, const rb_dc_cfg* dc, const float* samples, const int64_t* offsets, int n_utt,
+                           float* feats, long capacity, int64_t* frame_offsets, double* t_start, double* t_end);
+/* the kept sample runs of the last rb_frontend_process_dc call: utterance, [begin, end) in the caller's buffer,
+ * start time relative to the utterance.  Any pointer may be NULL.  *sequential_path != 0: the input was not
+ * "equal to or an increment away from its predecessor" everywhere and the reference chain was replayed sample by
+ * sample.  Returns the number of runs. */
+long rb_frontend_dc_runs(const rb_frontend* h, int64_t* run_utt, int64_t* run_begin, int64_t* run_end,
+                         double* run_start, long capacity, int* sequential_path);
+
 /* =====================================================================================
  * GMM emission scorer behind Mm::FeatureScorer (src/Mm/FeatureScorer.hh:28-167)
  * ===================================================================================== */

@@ -133,9 +133,16 @@ struct WindowBuffer {
     WindowBuffer(unsigned L, unsigned S, double sr) : length(L), shift(S), sampleRate(sr), bufferStart(0), flushed(false) {}
 
     void put(const std::vector<float>& in, Time inStart) {
+        if (flushed) { /* needInit_ after the last flush: init() -> reset() (WindowBuffer.cc:45-48,117-118) */
+            flushed = false;
+            buffer.clear();
+        }
         if (buffer.empty())
             bufferStart = inStart;
         buffer.insert(buffer.end(), in.begin(), in.end());
+    }
+    Time endTime() const {
+        return bufferStart + (Time)buffer.size() / (Time)sampleRate;
     }
     void copyOut(Frame& out, unsigned n) {
         out.data.assign(buffer.begin(), buffer.begin() + n);
@@ -162,6 +169,96 @@ struct WindowBuffer {
         if (!flushed)
             advance();
         return true;
+    }
+};
+
+/* ------------------------------------------------------------------ DC detection
+ * Signal::DcDetection::{put,get,nextBlock,lastBlock,copyBlock,eraseBlock,flush} src/Signal/DcDetection.cc:89-226,
+ * isNonDC / isDcDetected src/Signal/DcDetection.hh:73-82; node parameters :231-241 (samples.flow:34-35 sets
+ * min-dc-length .0125, max-dc-increment 0.9, min-non-dc-segment-length .026).  Input packets are time-contiguous. */
+struct DcBlock {
+    std::vector<float> data;
+    Time               start;
+    long               firstSample; /* index of data[0] in the input stream (bookkeeping for the tests) */
+};
+
+struct DcDetection {
+    double            sampleRate;
+    float             maxDcIncrement;
+    unsigned          minDcLength, minNonDcSegmentLength, maximalOutputSize;
+    unsigned          nonDcLength, dcLength, nonDcSegmentLength;
+    std::deque<float> buffer;
+    Time              bufferStart;
+    long              consumed; /* input samples erased from the buffer so far */
+    DcDetection(double sr, double minDcS, float maxInc, double minNonDcS, unsigned maxOut)
+            : sampleRate(sr), maxDcIncrement(maxInc), minDcLength((unsigned)rint(minDcS * sr)),
+              minNonDcSegmentLength((unsigned)rint(minNonDcS * sr)), maximalOutputSize(maxOut), nonDcLength(1),
+              dcLength(0), nonDcSegmentLength(0), bufferStart(0), consumed(0) {}
+    bool isNonDC(float v) const {
+        return fabs(v - buffer[nonDcLength - 1]) >= maxDcIncrement;
+    }
+    bool isDcDetected() const {
+        return dcLength >= minDcLength;
+    }
+    void put(const std::vector<float>& in, Time inStart) {
+        if (buffer.empty())
+            bufferStart = inStart;
+        buffer.insert(buffer.end(), in.begin(), in.end());
+    }
+    bool nextBlock() {
+        while ((nonDcLength + dcLength) < buffer.size()) {
+            if (isNonDC(buffer[nonDcLength + dcLength])) {
+                if (isDcDetected())
+                    return true;
+                nonDcLength += dcLength; /* include the DC hypotheses */
+                dcLength = 0;
+                if (nonDcLength >= std::max(minNonDcSegmentLength, maximalOutputSize))
+                    return true;
+                nonDcLength++; /* include the new non-DC sample */
+            }
+            else
+                dcLength++;
+        }
+        return false;
+    }
+    bool lastBlock() {
+        if (buffer.empty())
+            return false;
+        if (isDcDetected())
+            return true;
+        nonDcLength += dcLength;
+        dcLength = 0;
+        return true;
+    }
+    bool flushBlock(DcBlock& out) {
+        bool result = false;
+        out.data.clear();
+        if ((nonDcSegmentLength += nonDcLength) >= minNonDcSegmentLength) { /* copyBlock */
+            out.data.assign(buffer.begin(), buffer.begin() + nonDcLength);
+            out.start       = bufferStart;
+            out.firstSample = consumed;
+            result          = true;
+        }
+        if (dcLength > 0)
+            nonDcSegmentLength = 0;
+        buffer.erase(buffer.begin(), buffer.begin() + nonDcLength + dcLength); /* eraseBlock */
+        consumed += nonDcLength + dcLength;
+        bufferStart += (Time)(nonDcLength + dcLength) / sampleRate;
+        nonDcLength = 1;
+        dcLength    = 0;
+        return result;
+    }
+    bool get(DcBlock& out) {
+        do {
+            if (!nextBlock())
+                return false;
+        } while (!flushBlock(out));
+        return true;
+    }
+    bool flush(DcBlock& out) {
+        if (!lastBlock())
+            return false;
+        return flushBlock(out);
     }
 };
 
@@ -508,9 +605,11 @@ extern "C" void orc_fft_real_packed(float* v, int n) {
     realForwardPacked(v, (unsigned)n);
 }
 
-extern "C" long orc_mfcc(const orc_frontend_cfg* cfg, const float* samples, long n_samples, long chunk, float* feats,
-                         double* t_start, double* t_end, float* spectrum, float* amplitude, float* fbank,
-                         float* cepstra) {
+namespace {
+long mfccImpl(const orc_frontend_cfg* cfg, const orc_dc_cfg* dcCfg, const float* samples, long n_samples, long chunk,
+              float* feats, double* t_start, double* t_end, float* spectrum, float* amplitude, float* fbank,
+              float* cepstra, long capacity, long* run_begin, long* run_end, double* run_start, long run_capacity,
+              long* n_runs) {
     if (!cfg || (!samples && n_samples > 0))
         return -1;
     const bool fuse = cfg->use_fma != 0;
@@ -531,31 +630,88 @@ extern "C" long orc_mfcc(const orc_frontend_cfg* cfg, const float* samples, long
     long               fed = 0;
     if (chunk <= 0)
         chunk = n_samples > 0 ? n_samples : 1;
-    bool eos = false;
-    while (true) {
-        Frame f;
-        if (wb.get(f)) {
-            frames.push_back(f);
-            continue;
+    if (!dcCfg) {
+        bool eos = false;
+        while (true) {
+            Frame f;
+            if (wb.get(f)) {
+                frames.push_back(f);
+                continue;
+            }
+            if (!eos && fed < n_samples) {
+                long               n = std::min(chunk, n_samples - fed);
+                std::vector<float> packet(samples + fed, samples + fed + n);
+                Time               start = (Time)fed / g.sampleRate;
+                pre.apply(packet);
+                wb.put(packet, start);
+                fed += n;
+                continue;
+            }
+            eos = true;
+            if (wb.flush(f)) {
+                frames.push_back(f);
+                continue;
+            }
+            break;
         }
-        if (!eos && fed < n_samples) {
+    }
+    else {
+        /* samples.flow: ... -> signal-dc-detection -> (mfcc.flow) pre-emphasis -> window.  The detector's blocks are
+         * time-contiguous while they belong to one non-DC segment; after a discarded DC stretch the next block
+         * starts later than the previous one ended: Preemphasis re-initialises (Preemphasis.cc:54-55) and the window
+         * node flushes like at end of stream before it accepts the block (SlidingAlgorithmNode.hh:83-99,
+         * WindowBuffer.cc:56-63, flush-before-gap = true Window.cc:116). */
+        DcDetection dc(g.sampleRate, dcCfg->min_dc_length_s, dcCfg->max_dc_increment,
+                       dcCfg->min_non_dc_segment_length_s, (unsigned)dcCfg->maximal_output_size);
+        Time        prevEnd = 0;
+        bool        first   = true;
+        long        nRuns   = 0;
+        auto drain = [&](bool flushAll) {
+            Frame f;
+            while (wb.get(f))
+                frames.push_back(f);
+            if (flushAll)
+                while (wb.flush(f))
+                    frames.push_back(f);
+        };
+        auto feed = [&](DcBlock& b) {
+            const bool gap = first || fabs(b.start - prevEnd) > 1e-9;
+            if (gap) {
+                drain(true);
+                pre.needInit = true;
+                if (run_begin && nRuns < run_capacity) {
+                    run_begin[nRuns] = b.firstSample;
+                    run_start[nRuns] = b.start;
+                }
+                ++nRuns;
+            }
+            if (run_end && nRuns <= run_capacity)
+                run_end[nRuns - 1] = b.firstSample + (long)b.data.size();
+            prevEnd = b.start + (Time)b.data.size() / g.sampleRate;
+            first   = false;
+            pre.apply(b.data);
+            wb.put(b.data, b.start);
+            drain(false);
+        };
+        DcBlock b;
+        while (fed < n_samples) {
             long               n = std::min(chunk, n_samples - fed);
             std::vector<float> packet(samples + fed, samples + fed + n);
-            Time               start = (Time)fed / g.sampleRate;
-            pre.apply(packet);
-            wb.put(packet, start);
+            dc.put(packet, (Time)fed / g.sampleRate);
             fed += n;
-            continue;
+            while (dc.get(b))
+                feed(b);
         }
-        eos = true;
-        if (wb.flush(f)) {
-            frames.push_back(f);
-            continue;
-        }
-        break;
+        if (dc.flush(b))
+            feed(b);
+        drain(true);
+        if (n_runs)
+            *n_runs = nRuns;
     }
 
     const long                      T = (long)frames.size();
+    if (capacity >= 0 && T > capacity)
+        return -3;
     std::vector<std::vector<float>> cep(T);
     std::vector<float>              amp, fbOut;
     for (long t = 0; t < T; ++t) {
@@ -608,6 +764,23 @@ extern "C" long orc_mfcc(const orc_frontend_cfg* cfg, const float* samples, long
             t_end[t] = e;
     }
     return T;
+}
+}  // namespace
+
+extern "C" long orc_mfcc(const orc_frontend_cfg* cfg, const float* samples, long n_samples, long chunk, float* feats,
+                         double* t_start, double* t_end, float* spectrum, float* amplitude, float* fbank,
+                         float* cepstra) {
+    return mfccImpl(cfg, 0, samples, n_samples, chunk, feats, t_start, t_end, spectrum, amplitude, fbank, cepstra, -1, 0,
+                    0, 0, 0, 0);
+}
+
+extern "C" long orc_mfcc_dc(const orc_frontend_cfg* cfg, const orc_dc_cfg* dc, const float* samples, long n_samples,
+                            long chunk, float* feats, double* t_start, double* t_end, long capacity, long* run_begin,
+                            long* run_end, double* run_start, long run_capacity, long* n_runs) {
+    if (!dc)
+        return -1;
+    return mfccImpl(cfg, dc, samples, n_samples, chunk, feats, t_start, t_end, 0, 0, 0, 0, capacity, run_begin, run_end,
+                    run_start, run_capacity, n_runs);
 }
 
 extern "C" const char* orc_version(void) {

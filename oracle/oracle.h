@@ -69,6 +69,19 @@ long orc_mfcc(const orc_frontend_cfg* cfg, const float* samples, long n_samples,
               float* feats, double* t_start, double* t_end, float* spectrum, float* amplitude,
               float* fbank, float* cepstra);
 
+/* signal-dc-detection (src/Signal/DcDetection.{hh,cc}) between the audio source and the MFCC chain, as wired in
+ * src/Tools/FeatureExtraction/share/samples.flow:34-37.  feats/t_start/t_end have room for `capacity` frames (-3 if
+ * that is too small); run_* receive the kept sample runs [begin, end) and their start times. */
+typedef struct orc_dc_cfg {
+    double min_dc_length_s;
+    float  max_dc_increment;
+    double min_non_dc_segment_length_s;
+    int    maximal_output_size;
+} orc_dc_cfg;
+long orc_mfcc_dc(const orc_frontend_cfg* cfg, const orc_dc_cfg* dc, const float* samples, long n_samples, long chunk,
+                 float* feats, double* t_start, double* t_end, long capacity, long* run_begin, long* run_end,
+                 double* run_start, long run_capacity, long* n_runs);
+
 /* in-place real FFT of `n` (power of two) f32 values in the packed layout of
  * Math::FastFourierTransform::transformReal (restatement). */
 void orc_fft_real_packed(float* v, int n);

@@ -140,6 +140,41 @@ def mfcc(cfg, samples, chunk=0, stages=False):
     return out
 
 
+class DcCfg(C.Structure):
+    _fields_ = [("min_dc_length_s", C.c_double), ("max_dc_increment", C.c_float),
+                ("min_non_dc_segment_length_s", C.c_double), ("maximal_output_size", C.c_int)]
+
+
+def dc_cfg(min_dc_length_s=0.0125, max_dc_increment=0.9, min_non_dc_segment_length_s=0.026, maximal_output_size=4096):
+    """parameters of signal-dc-detection as samples.flow:34-35 sets them (node defaults: .0125 / 0.9 / .02 / 4096)"""
+    return DcCfg(min_dc_length_s, max_dc_increment, min_non_dc_segment_length_s, maximal_output_size)
+
+
+def mfcc_dc(cfg, dc, samples, chunk=0):
+    """samples -> signal-dc-detection -> MFCC chain.  Returns feats, t_start, t_end and the kept sample runs
+    (begin, end, start time)."""
+    samples = np.ascontiguousarray(samples, np.float32)
+    g = geometry(cfg)
+    cap = samples.size // max(1, g.win_shift) + samples.size // 64 + 8
+    feats = np.zeros((cap, g.feat_dim), np.float32)
+    ts = np.zeros(cap, np.float64)
+    te = np.zeros(cap, np.float64)
+    rcap = samples.size // 8 + 2
+    rb, re = np.zeros(rcap, np.int64), np.zeros(rcap, np.int64)
+    rs = np.zeros(rcap, np.float64)
+    nr = C.c_long(0)
+    L = lib()
+    L.orc_mfcc_dc.restype = C.c_long
+    T = L.orc_mfcc_dc(C.byref(cfg), C.byref(dc), _p(samples, C.c_float), C.c_long(samples.size), C.c_long(chunk),
+                      _p(feats, C.c_float), _p(ts, C.c_double), _p(te, C.c_double), C.c_long(cap), _p(rb, C.c_long),
+                      _p(re, C.c_long), _p(rs, C.c_double), C.c_long(rcap), C.byref(nr))
+    if T < 0:
+        raise RuntimeError("orc_mfcc_dc failed: %d" % T)
+    n = nr.value
+    return dict(feats=feats[:T].copy(), t_start=ts[:T].copy(), t_end=te[:T].copy(), run_begin=rb[:n].copy(),
+                run_end=re[:n].copy(), run_start=rs[:n].copy())
+
+
 def fft_real_packed(v):
     v = np.ascontiguousarray(v, np.float32).copy()
     lib().orc_fft_real_packed(_p(v, C.c_float), C.c_int(v.size))

@@ -44,10 +44,18 @@ struct Tile {
 
 struct FeParams {
     const float*   samples;     // concatenated utterances
-    const int64_t* sampleOff;   // [U+1]
-    const int64_t* frameOff;    // [U+1]
+    // static features: segment u covers samples [sampleOff[u], sampleEnd[u]) and writes frames from frameOff[u] on.
+    // Plain calls: segments = utterances, sampleEnd = sampleOff + 1.  With DC detection: segments = kept sample runs.
+    const int64_t* sampleOff;
+    const int64_t* sampleEnd;
+    const int64_t* frameOff;
     const Tile*    tiles;
     int            nTiles;
+    // derivatives / concatenation run over whole utterances (the delay node does not look at time stamps):
+    // group g covers frames [groupFrameOff[g], groupFrameOff[g + 1]); same tables as above for plain calls
+    const int64_t* groupFrameOff;
+    const Tile*    groupTiles;
+    int            nGroupTiles;
     const float*   tables;      // blob, see TableLayout
     int            tableFloats;
     // geometry
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) mfcc_static_kernel(const FeParams p,
     for (int tileIdx = blockIdx.x; tileIdx < p.nTiles; tileIdx += gridDim.x) {
         const Tile    tile   = p.tiles[tileIdx];
         const int64_t uBeg   = p.sampleOff[tile.utt];
-        const int64_t uLen   = p.sampleOff[tile.utt + 1] - uBeg;
+        const int64_t uLen   = p.sampleEnd[tile.utt] - uBeg;
         const int64_t fOut   = p.frameOff[tile.utt] + tile.f0;
         // samples the tile touches, relative to the utterance: [s0 - 1, s1)
         const int64_t s0 = (int64_t)tile.f0 * p.S;
@@ -241,10 +249,10 @@ __global__ void __launch_bounds__(kThreads) mfcc_static_kernel(const FeParams p,
 
 // one thread per (frame, coefficient): static | delta | delta-delta
 __global__ void __launch_bounds__(256) mfcc_derivative_kernel(const FeParams p) {
-    for (int tileIdx = blockIdx.x; tileIdx < p.nTiles; tileIdx += gridDim.x) {
-        const Tile    tile = p.tiles[tileIdx];
-        const int64_t u0   = p.frameOff[tile.utt];
-        const int64_t nU   = p.frameOff[tile.utt + 1] - u0;
+    for (int tileIdx = blockIdx.x; tileIdx < p.nGroupTiles; tileIdx += gridDim.x) {
+        const Tile    tile = p.groupTiles[tileIdx];
+        const int64_t u0   = p.groupFrameOff[tile.utt];
+        const int64_t nU   = p.groupFrameOff[tile.utt + 1] - u0;
         const int     K    = p.nCep;
         for (int idx = threadIdx.x; idx < tile.nf * K; idx += blockDim.x) {
             const int     fi = idx / K, c = idx - fi * K;
@@ -332,6 +340,14 @@ struct rb_frontend {
     // device buffers
     rb::DevBuf<float>   dTables, dSamples, dCep, dFeats, dDbgAmp, dDbgFbank;
     rb::DevBuf<int16_t> dPcm;  // interleaved s16 input of rb_frontend_process_s16
+    // signal-dc-detection (rb_frontend_process_dc): flag bits, run table on the device, runs of the last call
+    rb::DevBuf<uint32_t> dDcBits;
+    rb::DevBuf<int64_t>  dDcOff, dDcRunBeg, dDcRunEnd;
+    rb::DevBuf<double>   dDcRunStart;
+    rb::DevBuf<int>      dDcCount;
+    std::vector<int64_t> dcRunUtt, dcRunBeg, dcRunEnd;
+    std::vector<double>  dcRunStart;
+    int                  dcSlowPath = 0;
     static constexpr int kSlots = 4;
     struct StageSlot {
         rb::PinnedBuf<char> host;
@@ -663,17 +679,275 @@ void timestamps(const rb_frontend* h, long nSamples, double start0, long T, doub
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// signal-dc-detection (src/Signal/DcDetection.{hh,cc}; wired in front of the MFCC chain by samples.flow:34-37).
+//
+// The reference walks the samples one by one: a sample is "non-DC" if it differs from the LAST non-DC sample by at
+// least max-dc-increment; a stretch of at least min-dc-length DC samples is discarded, non-DC segments shorter than
+// min-non-dc-segment-length as well, and what is kept leaves in blocks of at most max(min-non-dc-segment-length,
+// maximal-output-size) samples whose start times are accumulated block by block.
+//
+// The chain "last non-DC sample" is sequential, but when every sample either equals its predecessor or differs from
+// it by at least the increment -- always true for 16-bit audio, whose values are integers, and the increment 0.9 --
+// the reference sample always equals the previous sample (induction over the stream), so
+//     non-DC(i)  <=>  |x[i] - x[i-1]| >= increment.
+// dc_flags_kernel computes these flags as one bit per sample (and reports whether the premise holds);
+// dc_runs_kernel then replays the block logic per utterance with one warp that jumps from event to event -- the
+// next DC sample, the next non-DC sample, the next block cut -- by scanning 1024 flag bits per step.  If the premise
+// fails (arbitrary float input), dc_runs_sequential_kernel restates the reference literally, one thread per utterance.
+// Results (kept sample runs, their start times) are identical to the reference's in both cases.
+// ---------------------------------------------------------------------------------------------------------------
+struct DcParams {
+    const float*   x;
+    const int64_t* uOff;    // [nUtt + 1] sample ranges
+    int            nUtt;
+    float          inc;
+    uint32_t       minDc, minSeg, cut;  // samples; cut = max(minSeg, maximal-output-size)
+    double         sampleRate;
+    const uint32_t* bits;
+    const int64_t* runOff;  // [nUtt + 1] capacity ranges in the run arrays
+    int64_t*       runBeg;
+    int64_t*       runEnd;
+    double*        runStart;
+    int*           nRuns;   // [nUtt]
+};
+
+__global__ void __launch_bounds__(256) dc_flags_kernel(const float* __restrict__ x, int64_t n, float inc,
+                                                       const int64_t* __restrict__ uOff, int nUtt,
+                                                       uint32_t* __restrict__ bits, int* violation) {
+    const int     lane  = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x / 32);
+    for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * 1024; base < n; base += warps * 1024) {
+        uint32_t mine = 0;
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const int64_t i   = base + k * 32 + lane;
+            bool          nd  = false;
+            if (i < n) {
+                const float cur = x[i], prev = i > 0 ? x[i - 1] : cur;
+                nd = i == 0 || fabsf(cur - prev) >= inc;
+                if (!nd && cur != prev) {
+                    // premise broken unless i starts an utterance (its flag is never looked at)
+                    int lo = 0, hi = nUtt;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (uOff[mid] < i)
+                            lo = mid + 1;
+                        else
+                            hi = mid;
+                    }
+                    if (uOff[lo] != i)
+                        *violation = 1;
+                }
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, nd);
+            if (lane == k)
+                mine = word;
+        }
+        if (base + (int64_t)lane * 32 < n)
+            bits[base / 32 + lane] = mine;
+    }
+}
+
+struct DcRunWriter {
+    int64_t* beg;
+    int64_t* end;
+    double*  start;
+    int      cap, n;
+    int64_t  lastEnd;
+    uint32_t segLen, minSeg;
+    double   time, sampleRate;
+    // flushBlock = copyBlock + eraseBlock (DcDetection.cc:168-210)
+    __device__ void emit(int64_t b, uint32_t nonDc, uint32_t dc, bool write) {
+        segLen += nonDc;
+        if (segLen >= minSeg) {
+            if (n > 0 && lastEnd == b) {  // continues the previous block without a gap: same run
+                if (write && n <= cap)
+                    end[n - 1] = b + nonDc;
+            }
+            else {
+                if (write && n < cap) {
+                    beg[n]   = b;
+                    end[n]   = b + nonDc;
+                    start[n] = time;
+                }
+                ++n;
+            }
+            lastEnd = b + nonDc;
+        }
+        if (dc > 0)
+            segLen = 0;
+        time += (double)(nonDc + dc) / sampleRate;
+    }
+};
+
+// smallest i in [pos, end) whose flag equals `want`, else end; cooperative over the warp: 4096 flags per step
+// (one 16-byte load per lane; the flag buffer is padded so that the last load stays inside it)
+__device__ __forceinline__ int64_t dc_next_flag(const uint32_t* __restrict__ bits, int64_t pos, int64_t end, bool want) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t w = (pos >> 5) & ~(int64_t)3; w * 32 < end; w += 128) {
+        const int64_t wi = w + lane * 4;
+        uint32_t      v[4] = {0, 0, 0, 0};
+        if (wi * 32 < end) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(bits + wi);
+            v[0] = raw.x;
+            v[1] = raw.y;
+            v[2] = raw.z;
+            v[3] = raw.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t s0 = (wi + j) * 32;  // first sample of the word
+                v[j]             = want ? v[j] : ~v[j];
+                if (s0 + 32 <= pos || s0 >= end)
+                    v[j] = 0;
+                else {
+                    if (s0 < pos)
+                        v[j] &= 0xffffffffu << (pos - s0);
+                    if (end - s0 < 32)
+                        v[j] &= (1u << (end - s0)) - 1u;
+                }
+            }
+        }
+        const uint32_t any = __ballot_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3]) != 0);
+        if (any) {
+            const int first = __ffs(any) - 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t fv = __shfl_sync(0xffffffffu, v[j], first);
+                if (fv)
+                    return (w + first * 4 + j) * 32 + (__ffs(fv) - 1);
+            }
+        }
+    }
+    return end;
+}
+
+__global__ void __launch_bounds__(128) dc_runs_kernel(const DcParams p) {
+    const int u = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (u >= p.nUtt)
+        return;
+    const bool    write = (threadIdx.x & 31) == 0;
+    const int64_t uBeg = p.uOff[u], uEnd = p.uOff[u + 1];
+    DcRunWriter   out;
+    out.beg        = p.runBeg + p.runOff[u];
+    out.end        = p.runEnd + p.runOff[u];
+    out.start      = p.runStart + p.runOff[u];
+    out.cap        = (int)(p.runOff[u + 1] - p.runOff[u]);
+    out.n          = 0;
+    out.lastEnd    = -1;
+    out.segLen     = 0;
+    out.minSeg     = p.minSeg;
+    out.time       = 0.0;
+    out.sampleRate = p.sampleRate;
+    if (uEnd > uBeg) {
+        int64_t b   = uBeg;      // block start: the reference sample of the block (nonDcLength_ = 1)
+        int64_t pos = uBeg + 1;  // next sample to look at; pos - 1 is a non-DC sample
+        while (true) {
+            // [pos, z0): non-DC samples only -- the block is cut at the first one that is `cut` samples from its start
+            const int64_t z0 = dc_next_flag(p.bits, pos, uEnd, false);
+            while (true) {
+                const int64_t q = b + p.cut > pos ? b + p.cut : pos;
+                if (q >= z0)
+                    break;
+                out.emit(b, (uint32_t)(q - b), 0, write);
+                b   = q;
+                pos = q + 1;
+            }
+            if (z0 == uEnd) {  // end of stream: lastBlock()
+                out.emit(b, (uint32_t)(uEnd - b), 0, write);
+                break;
+            }
+            // [z0, z1): DC hypotheses behind the non-DC sample z0 - 1
+            const int64_t  z1 = dc_next_flag(p.bits, z0, uEnd, true);
+            const uint32_t dc = (uint32_t)(z1 - z0);
+            if (z1 == uEnd) {
+                if (dc >= p.minDc)
+                    out.emit(b, (uint32_t)(z0 - b), dc, write);
+                else
+                    out.emit(b, (uint32_t)(uEnd - b), 0, write);
+                break;
+            }
+            if (dc >= p.minDc) {  // DC detected: the hypotheses are discarded, z1 starts the next block
+                out.emit(b, (uint32_t)(z0 - b), dc, write);
+                b = z1;
+            }
+            else if ((uint32_t)(z1 - b) >= p.cut) {  // hypotheses absorbed; block full
+                out.emit(b, (uint32_t)(z1 - b), 0, write);
+                b = z1;
+            }
+            pos = z1 + 1;
+        }
+    }
+    if (write)
+        p.nRuns[u] = out.n;
+}
+
+// literal restatement of nextBlock / lastBlock (DcDetection.cc:133-166) on the samples themselves
+__global__ void __launch_bounds__(64) dc_runs_sequential_kernel(const DcParams p) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= p.nUtt)
+        return;
+    DcRunWriter out;
+    out.beg        = p.runBeg + p.runOff[u];
+    out.end        = p.runEnd + p.runOff[u];
+    out.start      = p.runStart + p.runOff[u];
+    out.cap        = (int)(p.runOff[u + 1] - p.runOff[u]);
+    out.n          = 0;
+    out.lastEnd    = -1;
+    out.segLen     = 0;
+    out.minSeg     = p.minSeg;
+    out.time       = 0.0;
+    out.sampleRate = p.sampleRate;
+    int64_t  b = p.uOff[u], n = p.uOff[u + 1] - b;
+    uint32_t nonDc = 1, dc = 0;
+    if (n > 0) {
+        float ref = p.x[b];
+        while ((int64_t)nonDc + dc < n) {
+            const float v = p.x[b + nonDc + dc];
+            if (fabsf(v - ref) >= p.inc) {
+                bool cutHere = dc >= p.minDc;
+                if (!cutHere) {
+                    nonDc += dc;
+                    dc = 0;
+                    cutHere = nonDc >= p.cut;
+                }
+                if (cutHere) {
+                    out.emit(b, nonDc, dc, true);
+                    b += nonDc + dc;
+                    n -= nonDc + dc;
+                    nonDc = 1;
+                    dc    = 0;
+                }
+                else
+                    ++nonDc;
+                ref = v;  // v is the last non-DC sample now (of the old block, or the first of the new one)
+            }
+            else
+                ++dc;
+        }
+        if (dc < p.minDc) {
+            nonDc += dc;
+            dc = 0;
+        }
+        out.emit(b, nonDc, dc, true);
+    }
+    p.nRuns[u] = out.n;
+}
+
 // One call = one staging slot: [sample offsets | frame offsets | tile table] built in pinned memory, sent with a
 // single H2D copy.  Slots form a ring guarded by events, so the call only enqueues work (no stream synchronise):
 // back-to-back calls keep the GPU queue full.
-int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, int nUtt, float* dFeats,
-               cudaStream_t s, int64_t* totalFramesOut) {
-    size_t nTiles = 0;
+// Segments [segBeg[i], segEnd[i]) of the sample buffer produce the static features; derivative windows run over
+// groups of consecutive segments (groupOff[g] .. groupOff[g + 1], segment indices).  groupOff == nullptr: every
+// segment is its own group (plain calls: segments = utterances).
+int run_segments(rb_frontend* h, const float* dSamples, const int64_t* segBeg, const int64_t* segEnd, int nSeg,
+                 const int64_t* groupOff, int nGroups, float* dFeats, cudaStream_t s, int64_t* totalFramesOut) {
+    size_t nTiles = 0, nGroupTiles = 0;
     {
         int64_t acc = 0;
-        for (int u = 0; u < nUtt; ++u) {
-            RB_REQUIRE(offsets[u + 1] >= offsets[u], "sample offsets not monotone at utterance %d", u);
-            const long T = frames_for(h, (long)(offsets[u + 1] - offsets[u]));
+        for (int u = 0; u < nSeg; ++u) {
+            RB_REQUIRE(segEnd[u] >= segBeg[u], "sample offsets not monotone at segment %d", u);
+            const long T = frames_for(h, (long)(segEnd[u] - segBeg[u]));
             acc += T;
             nTiles += (size_t)(T + kTileFrames - 1) / kTileFrames;
         }
@@ -681,47 +955,74 @@ int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, in
             *totalFramesOut = acc;
         if (acc == 0)
             return RB_OK;
+        if (groupOff)
+            for (int g = 0; g < nGroups; ++g) {
+                int64_t T = 0;
+                for (int64_t u = groupOff[g]; u < groupOff[g + 1]; ++u)
+                    T += frames_for(h, (long)(segEnd[u] - segBeg[u]));
+                nGroupTiles += (size_t)(T + kTileFrames - 1) / kTileFrames;
+            }
     }
-    RB_REQUIRE(nTiles < (size_t)1 << 31, "too many frames in one call");
+    RB_REQUIRE(nTiles < (size_t)1 << 31 && nGroupTiles < (size_t)1 << 31, "too many frames in one call");
     rb_frontend::StageSlot& slot = h->slots[h->nextSlot];
     h->nextSlot                  = (h->nextSlot + 1) % rb_frontend::kSlots;
     if (!slot.ev)
         RB_CUDA(cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
     else
         RB_CUDA(cudaEventSynchronize(slot.ev));  // the call that used this slot last has finished with it
-    const size_t offBytes = sizeof(int64_t) * (size_t)(nUtt + 1);
-    const size_t bytes    = 2 * offBytes + sizeof(Tile) * nTiles;
+    // [seg begin | seg end | seg frame offsets | group frame offsets | tiles | group tiles]
+    const size_t segBytes = sizeof(int64_t) * (size_t)(nSeg + 1);
+    const size_t grpBytes = groupOff ? sizeof(int64_t) * (size_t)(nGroups + 1) : 0;
+    const size_t bytes    = 3 * segBytes + grpBytes + sizeof(Tile) * (nTiles + nGroupTiles);
     RB_CHECK(slot.host.reserve(bytes));
     RB_CHECK(slot.dev.reserve(bytes));
-    int64_t* sOff  = reinterpret_cast<int64_t*>(slot.host.p);
-    int64_t* fOff  = reinterpret_cast<int64_t*>(slot.host.p + offBytes);
-    Tile*    tiles = reinterpret_cast<Tile*>(slot.host.p + 2 * offBytes);
-    sOff[0] = offsets[0];
-    fOff[0] = 0;
-    size_t ti = 0;
-    for (int u = 0; u < nUtt; ++u) {
-        sOff[u + 1]  = offsets[u + 1];
-        const long T = frames_for(h, (long)(offsets[u + 1] - offsets[u]));
-        fOff[u + 1]  = fOff[u] + T;
+    int64_t* sOff   = reinterpret_cast<int64_t*>(slot.host.p);
+    int64_t* sEnd   = reinterpret_cast<int64_t*>(slot.host.p + segBytes);
+    int64_t* fOff   = reinterpret_cast<int64_t*>(slot.host.p + 2 * segBytes);
+    int64_t* gOff   = reinterpret_cast<int64_t*>(slot.host.p + 3 * segBytes);
+    Tile*    tiles  = reinterpret_cast<Tile*>(slot.host.p + 3 * segBytes + grpBytes);
+    Tile*    gTiles = tiles + nTiles;
+    auto addTiles = [](Tile* out, size_t& ti, int u, long T) {
         for (long f0 = 0; f0 < T; f0 += kTileFrames) {
             Tile t;
             t.utt = u;
             t.f0  = (int)f0;
             t.nf  = (int)std::min<long>(kTileFrames, T - f0);
             t.pad = 0;
-            tiles[ti++] = t;
+            out[ti++] = t;
         }
+    };
+    fOff[0]   = 0;
+    size_t ti = 0;
+    for (int u = 0; u < nSeg; ++u) {
+        sOff[u]      = segBeg[u];
+        sEnd[u]      = segEnd[u];
+        const long T = frames_for(h, (long)(segEnd[u] - segBeg[u]));
+        fOff[u + 1]  = fOff[u] + T;
+        addTiles(tiles, ti, u, T);
     }
-    const int64_t total = fOff[nUtt];
+    sOff[nSeg] = sEnd[nSeg] = nSeg ? segEnd[nSeg - 1] : 0;
+    if (groupOff) {
+        size_t gi = 0;
+        for (int g = 0; g <= nGroups; ++g)
+            gOff[g] = fOff[groupOff[g]];
+        for (int g = 0; g < nGroups; ++g)
+            addTiles(gTiles, gi, g, (long)(gOff[g + 1] - gOff[g]));
+    }
+    const int64_t total = fOff[nSeg];
     RB_CHECK(h->dCep.reserve((size_t)total * h->cfg.n_cepstra));
     RB_CUDA(cudaMemcpyAsync(slot.dev.p, slot.host.p, bytes, cudaMemcpyHostToDevice, s));
 
     FeParams p;
     p.samples      = dSamples;
     p.sampleOff    = reinterpret_cast<const int64_t*>(slot.dev.p);
-    p.frameOff     = reinterpret_cast<const int64_t*>(slot.dev.p + offBytes);
-    p.tiles        = reinterpret_cast<const Tile*>(slot.dev.p + 2 * offBytes);
+    p.sampleEnd    = reinterpret_cast<const int64_t*>(slot.dev.p + segBytes);
+    p.frameOff     = reinterpret_cast<const int64_t*>(slot.dev.p + 2 * segBytes);
+    p.tiles        = reinterpret_cast<const Tile*>(slot.dev.p + 3 * segBytes + grpBytes);
     p.nTiles       = (int)nTiles;
+    p.groupFrameOff = groupOff ? reinterpret_cast<const int64_t*>(slot.dev.p + 3 * segBytes) : p.frameOff;
+    p.groupTiles    = groupOff ? p.tiles + nTiles : p.tiles;
+    p.nGroupTiles   = groupOff ? (int)nGroupTiles : (int)nTiles;
     p.tables       = h->dTables.p;
     p.tableFloats  = (int)h->blob.size();
     p.L            = h->L;
@@ -746,7 +1047,7 @@ int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, in
     p.feats        = dFeats;
     p.dbgAmp       = nullptr;
     p.dbgFbank     = nullptr;
-    p.totalSamples = offsets[nUtt];
+    p.totalSamples = nSeg ? segEnd[nSeg - 1] : 0;
     if (h->debug) {
         RB_CHECK(h->dDbgAmp.reserve((size_t)total * h->nBins));
         RB_CHECK(h->dDbgFbank.reserve((size_t)total * h->nFilters));
@@ -765,12 +1066,18 @@ int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, in
     }
     RB_LAUNCH_CHECK();
     if (h->cfg.derivatives) {
-        const int grid2 = (int)std::min<size_t>(nTiles, (size_t)h->dev.sm_count * 8);
+        const int grid2 = (int)std::min<size_t>((size_t)p.nGroupTiles, (size_t)h->dev.sm_count * 8);
         mfcc_derivative_kernel<<<grid2, 256, 0, s>>>(p);
         RB_LAUNCH_CHECK();
     }
     RB_CUDA(cudaEventRecord(slot.ev, s));
     return RB_OK;
+}
+
+// utterances [offsets[u], offsets[u + 1])
+int run_device(rb_frontend* h, const float* dSamples, const int64_t* offsets, int nUtt, float* dFeats,
+               cudaStream_t s, int64_t* totalFramesOut) {
+    return run_segments(h, dSamples, offsets, offsets + 1, nUtt, nullptr, nUtt, dFeats, s, totalFramesOut);
 }
 
 }  // namespace
@@ -1163,4 +1470,233 @@ cudaStream_t rb_frontend_stream(const rb_frontend* h) {
 }
 int rb_frontend_feat_dim(const rb_frontend* h) {
     return h->featDim;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// signal-dc-detection + front-end
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" void rb_dc_default_cfg(rb_dc_cfg* cfg) {
+    if (!cfg)
+        return;
+    // src/Tools/FeatureExtraction/share/samples.flow:34-35 (the node's own defaults differ only in .02 for the last)
+    cfg->min_dc_length_s             = 0.0125;
+    cfg->max_dc_increment            = 0.9f;
+    cfg->min_non_dc_segment_length_s = 0.026;
+    cfg->maximal_output_size         = 4096;
+}
+
+namespace {
+struct DcSizes {
+    uint32_t minDc, minSeg, cut;
+};
+int dc_sizes(const rb_frontend* h, const rb_dc_cfg* dc, DcSizes* out) {
+    RB_REQUIRE(dc->min_dc_length_s >= 0 && dc->min_non_dc_segment_length_s >= 0 && dc->max_dc_increment >= 0 &&
+                       dc->maximal_output_size >= 1,
+               "bad dc-detection parameters");
+    out->minDc  = (uint32_t)rint(dc->min_dc_length_s * h->sampleRate);  // DcDetection::init, DcDetection.cc:75-85
+    out->minSeg = (uint32_t)rint(dc->min_non_dc_segment_length_s * h->sampleRate);
+    out->cut    = std::max(out->minSeg, (uint32_t)dc->maximal_output_size);
+    return RB_OK;
+}
+// every kept run but the last of an utterance is followed by at least minDc discarded samples
+long dc_max_runs(const DcSizes& z, long n) {
+    return n <= 0 ? 0 : n / (long)std::max<uint32_t>(1, z.minDc + 1) + 1;
+}
+}  // namespace
+
+extern "C" long rb_frontend_dc_max_frames(const rb_frontend* h, const rb_dc_cfg* dc, const int64_t* offsets, int n_utt) {
+    if (!h || !dc || !offsets || n_utt < 0) {
+        rb::set_error("bad argument");
+        return RB_ERR_INVALID;
+    }
+    DcSizes z;
+    if (dc_sizes(h, dc, &z) != RB_OK)
+        return RB_ERR_INVALID;
+    long total = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        const long n = (long)(offsets[u + 1] - offsets[u]);
+        if (n > 0)  // a run of m samples gives at most m / S + 1 frames
+            total += n / h->S + dc_max_runs(z, n);
+    }
+    return total;
+}
+
+extern "C" int rb_frontend_process_dc(rb_frontend* h, const rb_dc_cfg* dc, const float* samples, const int64_t* offsets,
+                                      int n_utt, float* feats, long capacity, int64_t* frame_offsets, double* t_start,
+                                      double* t_end) {
+    RB_REQUIRE(h && dc && offsets && frame_offsets && n_utt >= 0 && capacity >= 0, "bad argument");
+    DcSizes z;
+    RB_CHECK(dc_sizes(h, dc, &z));
+    h->dcRunUtt.clear();
+    h->dcRunBeg.clear();
+    h->dcRunEnd.clear();
+    h->dcRunStart.clear();
+    frame_offsets[0] = 0;
+    if (n_utt == 0)
+        return RB_OK;
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    const int64_t base = offsets[0], nS = offsets[n_utt] - base;
+    RB_REQUIRE(nS >= 0, "negative sample count");
+    RB_REQUIRE(samples || nS == 0, "NULL sample buffer");
+    std::vector<int64_t> off(2 * (size_t)(n_utt + 1));  // [sample ranges | run capacity ranges]
+    int64_t*             rel    = off.data();
+    int64_t*             runOff = off.data() + n_utt + 1;
+    runOff[0]                   = 0;
+    for (int u = 0; u <= n_utt; ++u) {
+        rel[u] = offsets[u] - base;
+        RB_REQUIRE(u == 0 || rel[u] >= rel[u - 1], "sample offsets not monotone at utterance %d", u - 1);
+        if (u > 0)
+            runOff[u] = runOff[u - 1] + dc_max_runs(z, (long)(rel[u] - rel[u - 1]));
+    }
+    const size_t runCap = (size_t)runOff[n_utt];
+    cudaStream_t s      = h->stream;
+    RB_CHECK(h->dSamples.reserve((size_t)nS + 8));
+    RB_CHECK(h->dDcBits.reserve((size_t)(nS + 31) / 32 + 256));
+    RB_CHECK(h->dDcOff.upload(off.data(), off.size(), s));
+    RB_CHECK(h->dDcRunBeg.reserve(runCap));
+    RB_CHECK(h->dDcRunEnd.reserve(runCap));
+    RB_CHECK(h->dDcRunStart.reserve(runCap));
+    RB_CHECK(h->dDcCount.reserve((size_t)n_utt + 1));
+    if (nS > 0)
+        RB_CUDA(cudaMemcpyAsync(h->dSamples.p, samples + base, (size_t)nS * 4, cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaMemsetAsync(h->dDcCount.p, 0, sizeof(int) * ((size_t)n_utt + 1), s));
+    DcParams p;
+    p.x          = h->dSamples.p;
+    p.uOff       = h->dDcOff.p;
+    p.nUtt       = n_utt;
+    p.inc        = dc->max_dc_increment;
+    p.minDc      = z.minDc;
+    p.minSeg     = z.minSeg;
+    p.cut        = z.cut;
+    p.sampleRate = h->sampleRate;
+    p.bits       = h->dDcBits.p;
+    p.runOff     = h->dDcOff.p + n_utt + 1;
+    p.runBeg     = h->dDcRunBeg.p;
+    p.runEnd     = h->dDcRunEnd.p;
+    p.runStart   = h->dDcRunStart.p;
+    p.nRuns      = h->dDcCount.p;
+    int* dViolation = h->dDcCount.p + n_utt;
+    std::vector<int> counts((size_t)n_utt + 1, 0);
+    // a zero min-dc-length makes every non-DC sample a block of its own: only the literal restatement covers that
+    bool sequential = z.minDc == 0 || getenv("RB_DC_SEQUENTIAL") != nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (!sequential) {
+            if (nS > 0) {
+                const int grid = (int)std::min<int64_t>((nS + 8191) / 8192, (int64_t)h->dev.sm_count * 8);
+                dc_flags_kernel<<<grid, 256, 0, s>>>(h->dSamples.p, nS, p.inc, p.uOff, n_utt, h->dDcBits.p, dViolation);
+                RB_LAUNCH_CHECK();
+            }
+            dc_runs_kernel<<<(n_utt + 3) / 4, 128, 0, s>>>(p);
+        }
+        else
+            dc_runs_sequential_kernel<<<(n_utt + 63) / 64, 64, 0, s>>>(p);
+        RB_LAUNCH_CHECK();
+        RB_CUDA(cudaMemcpyAsync(counts.data(), h->dDcCount.p, sizeof(int) * counts.size(), cudaMemcpyDeviceToHost, s));
+        RB_CUDA(cudaStreamSynchronize(s));
+        if (sequential || counts[n_utt] == 0)
+            break;
+        sequential = true;  // the input is not "equal or an increment apart" everywhere: replay the reference chain
+    }
+    h->dcSlowPath = sequential;
+    // the run table comes back to the host: it shapes the launches that follow
+    std::vector<int64_t> rb(runCap), re(runCap);
+    std::vector<double>  rs(runCap);
+    if (runCap) {
+        RB_CUDA(cudaMemcpyAsync(rb.data(), h->dDcRunBeg.p, 8 * runCap, cudaMemcpyDeviceToHost, s));
+        RB_CUDA(cudaMemcpyAsync(re.data(), h->dDcRunEnd.p, 8 * runCap, cudaMemcpyDeviceToHost, s));
+        RB_CUDA(cudaMemcpyAsync(rs.data(), h->dDcRunStart.p, 8 * runCap, cudaMemcpyDeviceToHost, s));
+        RB_CUDA(cudaStreamSynchronize(s));
+    }
+    std::vector<int64_t> groupOff(1, 0);
+    for (int u = 0; u < n_utt; ++u) {
+        RB_REQUIRE(counts[u] <= runOff[u + 1] - runOff[u], "internal: run table of utterance %d overflowed", u);
+        long T = 0;
+        for (int r = 0; r < counts[u]; ++r) {
+            const size_t i = (size_t)runOff[u] + r;
+            h->dcRunUtt.push_back(u);
+            h->dcRunBeg.push_back(rb[i]);
+            h->dcRunEnd.push_back(re[i]);
+            h->dcRunStart.push_back(rs[i]);
+            T += frames_for(h, (long)(re[i] - rb[i]));
+        }
+        groupOff.push_back((int64_t)h->dcRunBeg.size());
+        frame_offsets[u + 1] = frame_offsets[u] + T;
+    }
+    const long total = (long)frame_offsets[n_utt];
+    if (total > capacity) {
+        rb::set_error("feature buffer holds %ld frames, %ld are needed (rb_frontend_dc_max_frames gives a bound)", capacity,
+                      total);
+        return RB_ERR_INVALID;
+    }
+    h->lastFrames = total;
+    if (total == 0)
+        return RB_OK;
+    RB_CHECK(h->dFeats.reserve((size_t)total * h->featDim));
+    const int nSeg = (int)h->dcRunBeg.size();
+    RB_CHECK(run_segments(h, h->dSamples.p, h->dcRunBeg.data(), h->dcRunEnd.data(), nSeg, groupOff.data(), n_utt,
+                          h->dFeats.p, s, nullptr));
+    if (feats)
+        RB_CUDA(cudaMemcpyAsync(feats, h->dFeats.p, (size_t)total * h->featDim * 4, cudaMemcpyDeviceToHost, s));
+    RB_CUDA(cudaStreamSynchronize(s));
+    if (t_start || t_end) {
+        // static frames: the window buffer restarts at every run with the run's start time (WindowBuffer.cc:56-59);
+        // the merged packets span the delay window, which runs across the runs of an utterance
+        std::vector<double> ws, we;
+        for (int u = 0; u < n_utt; ++u) {
+            ws.clear();
+            we.clear();
+            for (int64_t r = groupOff[u]; r < groupOff[u + 1]; ++r) {
+                const long n = (long)(h->dcRunEnd[r] - h->dcRunBeg[r]), T = frames_for(h, n);
+                double     cur = h->dcRunStart[r];
+                for (long t = 0; t < T; ++t) {
+                    const long len = std::min<long>(h->L, n - t * h->S);
+                    ws.push_back(cur);
+                    we.push_back(cur + (double)len / (double)h->sampleRate);
+                    cur += (double)h->S / (double)h->sampleRate;
+                }
+            }
+            const long T = (long)ws.size(), f0 = (long)frame_offsets[u];
+            for (long t = 0; t < T; ++t) {
+                double a = ws[t], b = we[t];
+                if (h->cfg.derivatives)
+                    for (int i = -2; i <= 2; ++i) {
+                        const long v = std::min<long>(std::max<long>(t + i, 0), T - 1);
+                        a            = std::min(a, ws[v]);
+                        b            = std::max(b, we[v]);
+                    }
+                if (t_start)
+                    t_start[f0 + t] = a;
+                if (t_end)
+                    t_end[f0 + t] = b;
+            }
+        }
+    }
+    // run positions are reported relative to the caller's buffer
+    for (auto& v : h->dcRunBeg)
+        v += base;
+    for (auto& v : h->dcRunEnd)
+        v += base;
+    return RB_OK;
+}
+
+extern "C" long rb_frontend_dc_runs(const rb_frontend* h, int64_t* run_utt, int64_t* run_begin, int64_t* run_end,
+                                    double* run_start, long capacity, int* sequential_path) {
+    if (!h) {
+        rb::set_error("NULL handle");
+        return RB_ERR_INVALID;
+    }
+    const long n = (long)h->dcRunBeg.size();
+    for (long i = 0; i < std::min(n, capacity); ++i) {
+        if (run_utt)
+            run_utt[i] = h->dcRunUtt[i];
+        if (run_begin)
+            run_begin[i] = h->dcRunBeg[i];
+        if (run_end)
+            run_end[i] = h->dcRunEnd[i];
+        if (run_start)
+            run_start[i] = h->dcRunStart[i];
+    }
+    if (sequential_path)
+        *sequential_path = h->dcSlowPath;
+    return n;
 }

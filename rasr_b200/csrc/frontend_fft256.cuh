@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kF256Threads, 2)
     for (int tileIdx = blockIdx.x; tileIdx < p.nTiles; tileIdx += gridDim.x) {
         const Tile    tile = p.tiles[tileIdx];
         const int64_t uBeg = p.sampleOff[tile.utt];
-        const int64_t uLen = p.sampleOff[tile.utt + 1] - uBeg;
+        const int64_t uLen = p.sampleEnd[tile.utt] - uBeg;
         const int64_t fOut = p.frameOff[tile.utt] + tile.f0;
         const int64_t s0   = (int64_t)tile.f0 * p.S;
         const int     span = (tile.nf - 1) * p.S + p.L;                    // samples the tile's frames cover

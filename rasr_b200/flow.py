@@ -104,6 +104,42 @@ class FrontEnd:
                 L.rb_frontend_set_debug(self._h, 0)
         return out
 
+    def process_dc(self, samples, offsets=None, dc=None, timestamps=True):
+        """signal-dc-detection (samples.flow:34-37) in front of the chain.  `dc`: capi.DcCfg or a dict of its fields
+        (default: the values samples.flow sets).  Returns dict(feats, frame_offsets, t_start, t_end, runs) with
+        runs = dict(utt, begin, end, start, sequential_path)."""
+        samples = np.ascontiguousarray(samples, np.float32)
+        if offsets is None:
+            offsets = np.array([0, samples.size], np.int64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        L = capi.lib()
+        cfg = capi.DcCfg()
+        L.rb_dc_default_cfg(C.byref(cfg))
+        if isinstance(dc, capi.DcCfg):
+            cfg = dc
+        elif dc:
+            for k, v in dc.items():
+                setattr(cfg, k, v)
+        n_utt = offsets.size - 1
+        cap = int(L.rb_frontend_dc_max_frames(self._h, C.byref(cfg), capi.ptr(offsets), n_utt))
+        if cap < 0:
+            capi.check(cap)
+        feats = np.zeros((cap, self.feat_dim), np.float32)
+        ts = np.zeros(cap, np.float64) if timestamps else None
+        te = np.zeros(cap, np.float64) if timestamps else None
+        fo = np.zeros(n_utt + 1, np.int64)
+        capi.check(L.rb_frontend_process_dc(self._h, C.byref(cfg), capi.ptr(samples), capi.ptr(offsets), n_utt,
+                                            capi.ptr(feats), cap, capi.ptr(fo), capi.ptr(ts), capi.ptr(te)))
+        T = int(fo[-1])
+        seq = C.c_int(0)
+        n = int(L.rb_frontend_dc_runs(self._h, None, None, None, None, 0, C.byref(seq)))
+        ru, rb, re = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        rs = np.zeros(n, np.float64)
+        L.rb_frontend_dc_runs(self._h, capi.ptr(ru), capi.ptr(rb), capi.ptr(re), capi.ptr(rs), n, None)
+        return dict(feats=feats[:T], frame_offsets=fo, t_start=ts[:T] if timestamps else None,
+                    t_end=te[:T] if timestamps else None,
+                    runs=dict(utt=ru, begin=rb, end=re, start=rs, sequential_path=bool(seq.value)))
+
     def process_s16(self, pcm, offsets=None, n_channels=1, track=0, timestamps=True, out=None):
         """16-bit PCM in (numpy int16 [frames] or [frames, n_channels] interleaved, or a pinned torch tensor);
         demultiplexed and converted on the device (samples.flow:13-18)."""
