@@ -10,6 +10,12 @@ const Core::ParameterFloat MfccNode::paramFilterWidth("filter-width", "mel filte
 const Core::ParameterInt   MfccNode::paramNrOutputs("nr-outputs", "number of cepstral coefficients", 13, 1);
 const Core::ParameterBool  MfccNode::paramDerivatives("derivatives", "append first and second order regression", true);
 const Core::ParameterInt   MfccNode::paramDevice("device", "CUDA device ordinal", 0, 0);
+// signal-dc-detection in front of the chain (src/Signal/DcDetection.cc:231-241; values of samples.flow:34-35)
+const Core::ParameterBool  MfccNode::paramDcDetection("dc-detection", "discard DC stretches of the input like signal-dc-detection", false);
+const Core::ParameterFloat MfccNode::paramMinDcLength("min-dc-length", "minimum length (in seconds) of DC necesseary for the decision", .0125, 0);
+const Core::ParameterFloat MfccNode::paramMaxDcIncrement("max-dc-increment", "interval with less variation taken as DC, 0 disables DC detection", 0.9, 0);
+const Core::ParameterFloat MfccNode::paramMinNonDcSegmentLength("min-non-dc-segment-length", "smaller segments (given in seconds) are discarded", .026, 0);
+const Core::ParameterInt   MfccNode::paramMaximalOutputSize("maximal-output-size", "maximal size of output", 4096, 1);
 
 MfccNode::MfccNode(const Core::Configuration& c)
         : Core::Component(c), Flow::SleeveNode(c), handle_(0), dirty_(true), segmentOpen_(false), nFrames_(0), nextFrame_(0), featDim_(0) {
@@ -22,6 +28,11 @@ MfccNode::MfccNode(const Core::Configuration& c)
     cfg_.n_cepstra         = paramNrOutputs(c);
     cfg_.derivatives       = paramDerivatives(c) ? 1 : 0;
     cfg_.device            = paramDevice(c);
+    dcDetection_                    = paramDcDetection(c);
+    dc_.min_dc_length_s             = paramMinDcLength(c);
+    dc_.max_dc_increment            = paramMaxDcIncrement(c);
+    dc_.min_non_dc_segment_length_s = paramMinNonDcSegmentLength(c);
+    dc_.maximal_output_size         = paramMaximalOutputSize(c);
 }
 
 MfccNode::~MfccNode() {
@@ -45,6 +56,16 @@ bool MfccNode::setParameter(const std::string& name, const std::string& value) {
         cfg_.derivatives = paramDerivatives(value) ? 1 : 0;
     else if (paramDevice.match(name))
         cfg_.device = paramDevice(value);
+    else if (paramDcDetection.match(name))
+        dcDetection_ = paramDcDetection(value);
+    else if (paramMinDcLength.match(name))
+        dc_.min_dc_length_s = paramMinDcLength(value);
+    else if (paramMaxDcIncrement.match(name))
+        dc_.max_dc_increment = paramMaxDcIncrement(value);
+    else if (paramMinNonDcSegmentLength.match(name))
+        dc_.min_non_dc_segment_length_s = paramMinNonDcSegmentLength(value);
+    else if (paramMaximalOutputSize.match(name))
+        dc_.maximal_output_size = paramMaximalOutputSize(value);
     else
         return false;
     dirty_ = true;
@@ -77,7 +98,7 @@ bool MfccNode::ensureHandle() {
         return true;
     rb_frontend_destroy(handle_);
     handle_ = 0;
-    if (rb_frontend_create(&cfg_, &handle_) != RB_OK) {
+    if (rb_frontend_create(&cfg_, &handle_) != RB_OK || rb_frontend_set_dc_detection(handle_, dcDetection_ ? &dc_ : 0) != RB_OK) {
         criticalError("rasr_b200: %s", rb_last_error());
         return false;
     }

@@ -30,6 +30,11 @@ public:
     static const Core::ParameterInt   paramNrOutputs;        // signal-cosine-transform nr-outputs
     static const Core::ParameterBool  paramDerivatives;      // append delta / delta-delta
     static const Core::ParameterInt   paramDevice;
+    static const Core::ParameterBool  paramDcDetection;           // signal-dc-detection in front of the chain
+    static const Core::ParameterFloat paramMinDcLength;           // its parameters, named as in DcDetection.cc:231-241
+    static const Core::ParameterFloat paramMaxDcIncrement;
+    static const Core::ParameterFloat paramMinNonDcSegmentLength;
+    static const Core::ParameterInt   paramMaximalOutputSize;
 
     static std::string filterName() {
         return "b200-mfcc";
@@ -46,6 +51,8 @@ private:
     void computeSegment();
 
     rb_frontend_cfg     cfg_;
+    rb_dc_cfg           dc_;
+    bool                dcDetection_;
     rb_frontend*        handle_;
     bool                dirty_;      // parameters changed since the handle was created
     bool                segmentOpen_;

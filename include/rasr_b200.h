@@ -155,6 +155,9 @@ long rb_frontend_dc_max_frames(const rb_frontend* h, const rb_dc_cfg* dc, const 
  * utterance. */
 int rb_frontend_process_dc(rb_frontend* h, const rb_dc_cfg* dc, const float* samples, const int64_t* offsets, int n_utt,
                            float* feats, long capacity, int64_t* frame_offsets, double* t_start, double* t_end);
+/* streaming interface (rb_frontend_push / finish / read): run the detector over the pushed samples at
+ * rb_frontend_finish; NULL switches it off again.  Start times continue from the start time of the first packet. */
+int rb_frontend_set_dc_detection(rb_frontend* h, const rb_dc_cfg* dc);
 /* the kept sample runs of the last rb_frontend_process_dc call: utterance, [begin, end) in the caller's buffer,
  * start time relative to the utterance.  Any pointer may be NULL.  *sequential_path != 0: the input was not
  * "equal to or an increment away from its predecessor" everywhere and the reference chain was replayed sample by

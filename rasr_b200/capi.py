@@ -27,7 +27,7 @@ SYMBOLS = [
     "rb_frontend_get_tables", "rb_frontend_nframes_for", "rb_frontend_reset", "rb_frontend_push",
     "rb_frontend_finish", "rb_frontend_nframes", "rb_frontend_read", "rb_frontend_count_frames",
     "rb_frontend_process", "rb_frontend_process_s16", "rb_frontend_process_dev", "rb_frontend_set_debug", "rb_frontend_read_stages",
-    "rb_dc_default_cfg", "rb_frontend_dc_max_frames", "rb_frontend_process_dc", "rb_frontend_dc_runs",
+    "rb_dc_default_cfg", "rb_frontend_dc_max_frames", "rb_frontend_process_dc", "rb_frontend_dc_runs", "rb_frontend_set_dc_detection",
     "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_s16", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
@@ -130,6 +130,7 @@ def lib():
     L.rb_frontend_dc_max_frames.restype = C.c_long
     L.rb_frontend_process_dc.argtypes = [vp, C.POINTER(DcCfg), vp, vp, C.c_int, vp, C.c_long, vp, vp, vp]
     L.rb_frontend_dc_runs.argtypes = [vp, vp, vp, vp, vp, C.c_long, vp]
+    L.rb_frontend_set_dc_detection.argtypes = [vp, C.POINTER(DcCfg)]
     L.rb_frontend_dc_runs.restype = C.c_long
     L.rb_frontend_set_debug.argtypes = [vp, C.c_int]
     L.rb_frontend_read_stages.argtypes = [vp, vp, vp, vp]

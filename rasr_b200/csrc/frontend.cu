@@ -348,6 +348,9 @@ struct rb_frontend {
     std::vector<int64_t> dcRunUtt, dcRunBeg, dcRunEnd;
     std::vector<double>  dcRunStart;
     int                  dcSlowPath = 0;
+    bool                 dcEnabled  = false;  // streaming API: rb_frontend_set_dc_detection
+    rb_dc_cfg            dcCfg{};
+    rb::DevBuf<double>   dDcUttStart;
     static constexpr int kSlots = 4;
     struct StageSlot {
         rb::PinnedBuf<char> host;
@@ -700,6 +703,7 @@ void timestamps(const rb_frontend* h, long nSamples, double start0, long T, doub
 struct DcParams {
     const float*   x;
     const int64_t* uOff;    // [nUtt + 1] sample ranges
+    const double*  uStart;  // [nUtt] start time of the utterances, or null (0)
     int            nUtt;
     float          inc;
     uint32_t       minDc, minSeg, cut;  // samples; cut = max(minSeg, maximal-output-size)
@@ -837,7 +841,7 @@ __global__ void __launch_bounds__(128) dc_runs_kernel(const DcParams p) {
     out.lastEnd    = -1;
     out.segLen     = 0;
     out.minSeg     = p.minSeg;
-    out.time       = 0.0;
+    out.time       = p.uStart ? p.uStart[u] : 0.0;
     out.sampleRate = p.sampleRate;
     if (uEnd > uBeg) {
         int64_t b   = uBeg;      // block start: the reference sample of the block (nonDcLength_ = 1)
@@ -896,7 +900,7 @@ __global__ void __launch_bounds__(64) dc_runs_sequential_kernel(const DcParams p
     out.lastEnd    = -1;
     out.segLen     = 0;
     out.minSeg     = p.minSeg;
-    out.time       = 0.0;
+    out.time       = p.uStart ? p.uStart[u] : 0.0;
     out.sampleRate = p.sampleRate;
     int64_t  b = p.uOff[u], n = p.uOff[u + 1] - b;
     uint32_t nonDc = 1, dc = 0;
@@ -1388,11 +1392,35 @@ extern "C" int rb_frontend_push(rb_frontend* h, const float* samples, long n, do
     return RB_OK;
 }
 
+namespace {
+int process_dc_impl(rb_frontend* h, const rb_dc_cfg* dc, const float* samples, const int64_t* offsets, int n_utt,
+                    float* feats, long capacity, int64_t* frame_offsets, double* t_start, double* t_end,
+                    const double* utt_start);
+}
+
 extern "C" int rb_frontend_finish(rb_frontend* h) {
     RB_REQUIRE(h != nullptr, "NULL handle");
     const long    n      = (long)h->pending.size();
-    const long    T      = frames_for(h, n);
     const int64_t off[2] = {0, n};
+    if (h->dcEnabled) {  // signal-dc-detection between the samples and the chain
+        const long cap = rb_frontend_dc_max_frames(h, &h->dcCfg, off, 1);
+        if (cap < 0)
+            return (int)cap;
+        h->lastFeats.assign((size_t)cap * h->featDim, 0.0f);
+        h->lastStart.assign(cap, 0.0);
+        h->lastEnd.assign(cap, 0.0);
+        int64_t fo[2] = {0, 0};
+        RB_CHECK(process_dc_impl(h, &h->dcCfg, h->pending.data(), off, 1, h->lastFeats.data(), cap, fo,
+                                 h->lastStart.data(), h->lastEnd.data(), &h->pendingStart));
+        h->lastFrames = (long)fo[1];
+        h->lastFeats.resize((size_t)fo[1] * h->featDim);
+        h->lastStart.resize(fo[1]);
+        h->lastEnd.resize(fo[1]);
+        h->pending.clear();
+        h->havePending = false;
+        return RB_OK;
+    }
+    const long T = frames_for(h, n);
     h->lastFeats.assign((size_t)T * h->featDim, 0.0f);
     h->lastStart.assign(T, 0.0);
     h->lastEnd.assign(T, 0.0);
@@ -1521,9 +1549,10 @@ extern "C" long rb_frontend_dc_max_frames(const rb_frontend* h, const rb_dc_cfg*
     return total;
 }
 
-extern "C" int rb_frontend_process_dc(rb_frontend* h, const rb_dc_cfg* dc, const float* samples, const int64_t* offsets,
-                                      int n_utt, float* feats, long capacity, int64_t* frame_offsets, double* t_start,
-                                      double* t_end) {
+namespace {
+int process_dc_impl(rb_frontend* h, const rb_dc_cfg* dc, const float* samples, const int64_t* offsets, int n_utt,
+                    float* feats, long capacity, int64_t* frame_offsets, double* t_start, double* t_end,
+                    const double* utt_start) {
     RB_REQUIRE(h && dc && offsets && frame_offsets && n_utt >= 0 && capacity >= 0, "bad argument");
     DcSizes z;
     RB_CHECK(dc_sizes(h, dc, &z));
@@ -1563,6 +1592,11 @@ extern "C" int rb_frontend_process_dc(rb_frontend* h, const rb_dc_cfg* dc, const
     DcParams p;
     p.x          = h->dSamples.p;
     p.uOff       = h->dDcOff.p;
+    p.uStart     = nullptr;
+    if (utt_start) {
+        RB_CHECK(h->dDcUttStart.upload(utt_start, (size_t)n_utt, s));
+        p.uStart = h->dDcUttStart.p;
+    }
     p.nUtt       = n_utt;
     p.inc        = dc->max_dc_increment;
     p.minDc      = z.minDc;
@@ -1676,6 +1710,24 @@ extern "C" int rb_frontend_process_dc(rb_frontend* h, const rb_dc_cfg* dc, const
         v += base;
     for (auto& v : h->dcRunEnd)
         v += base;
+    return RB_OK;
+}
+}  // namespace
+
+extern "C" int rb_frontend_process_dc(rb_frontend* h, const rb_dc_cfg* dc, const float* samples, const int64_t* offsets,
+                                      int n_utt, float* feats, long capacity, int64_t* frame_offsets, double* t_start,
+                                      double* t_end) {
+    return process_dc_impl(h, dc, samples, offsets, n_utt, feats, capacity, frame_offsets, t_start, t_end, nullptr);
+}
+
+extern "C" int rb_frontend_set_dc_detection(rb_frontend* h, const rb_dc_cfg* dc) {
+    RB_REQUIRE(h != nullptr, "NULL handle");
+    h->dcEnabled = dc != nullptr;
+    if (dc) {
+        DcSizes z;
+        RB_CHECK(dc_sizes(h, dc, &z));
+        h->dcCfg = *dc;
+    }
     return RB_OK;
 }
 

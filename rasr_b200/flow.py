@@ -165,6 +165,18 @@ class FrontEnd:
         capi.check(capi.lib().rb_frontend_process_dev(self._h, capi.ptr(d_samples), capi.ptr(offsets),
                                                       offsets.size - 1, capi.ptr(d_feats), capi.ptr(stream)))
 
+    def set_dc_detection(self, dc=None, enabled=True):
+        """streaming protocol: run signal-dc-detection over the pushed samples at finish()"""
+        L = capi.lib()
+        if not enabled:
+            capi.check(L.rb_frontend_set_dc_detection(self._h, None))
+            return
+        cfg = capi.DcCfg()
+        L.rb_dc_default_cfg(C.byref(cfg))
+        for k, v in (dc or {}).items():
+            setattr(cfg, k, v)
+        capi.check(L.rb_frontend_set_dc_detection(self._h, C.byref(cfg)))
+
     # streaming protocol
     def reset(self):
         capi.check(capi.lib().rb_frontend_reset(self._h))
@@ -191,6 +203,10 @@ class MfccNode:
               "maximum-input-size": ("fft_max_input", float), "filter-width": ("filter_width", float),
               "nr-outputs": ("n_cepstra", int), "derivatives": ("derivatives", lambda v: v in ("true", "1", "yes")),
               "device": ("device", int)}
+    # signal-dc-detection in front of the chain, parameter names of src/Signal/DcDetection.cc:231-241
+    DC_PARAMS = {"min-dc-length": ("min_dc_length_s", float), "max-dc-increment": ("max_dc_increment", float),
+                 "min-non-dc-segment-length": ("min_non_dc_segment_length_s", float),
+                 "maximal-output-size": ("maximal_output_size", int)}
 
     @staticmethod
     def filter_name():
@@ -198,6 +214,7 @@ class MfccNode:
 
     def __init__(self):
         self._kw = {}
+        self._dc, self._dc_on = {}, False
         self._fe = None
         self._out = []
         self._segment_open = False
@@ -205,6 +222,15 @@ class MfccNode:
 
     def set_parameter(self, name, value):
         """Returns False for unknown names, like Flow::AbstractNode::setParameter."""
+        if name == "dc-detection":
+            self._dc_on = value in ("true", "1", "yes")
+            self._fe = None
+            return True
+        if name in self.DC_PARAMS:
+            key, conv = self.DC_PARAMS[name]
+            self._dc[key] = conv(value)
+            self._fe = None
+            return True
         if name not in self.PARAMS:
             return False
         key, conv = self.PARAMS[name]
@@ -220,6 +246,7 @@ class MfccNode:
             return False
         sr = float(input_attributes["sample-rate"])
         self._fe = FrontEnd(sample_rate=sr, **self._kw)
+        self._fe.set_dc_detection(self._dc, self._dc_on)
         g = self._fe.geometry
         self.output_attributes = {"datatype": "vector-f32", "sample-rate": "%g" % (sr / g.win_shift),
                                   "frame-shift": "%g" % (g.win_shift / sr)}

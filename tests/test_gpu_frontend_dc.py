@@ -102,3 +102,28 @@ def test_capacity_is_checked():
     rc = capi.lib().rb_frontend_process_dc(fe.handle, C.byref(cfg), capi.ptr(x), capi.ptr(offs), 1, capi.ptr(feats), 10,
                                            capi.ptr(fo), None, None)
     assert rc == -1 and b"99 are needed" in capi.lib().rb_last_error()
+
+
+def test_flow_node_with_dc_detection(oracle):
+    """the Flow-node mirror (what adapters/B200MfccNode.cc does): packets with a start time in, dc-detection="true";
+    the start times of the runs continue from the first packet's start time like DcDetection::put (:105-108)"""
+    x = audio_with_plateaus(30000, 17)
+    node = flow.MfccNode()
+    assert node.set_parameter("dc-detection", "true") and node.set_parameter("min-dc-length", "0.0125")
+    assert node.configure({"sample-rate": "16000", "datatype": "vector-f32"})
+    t0 = 1.25
+    for a in range(0, x.size, 4000):
+        node.put(flow.Packet(x[a:a + 4000], t0 + a / 16000.0, t0 + min(a + 4000, x.size) / 16000.0))
+    node.put(flow.EOS)
+    out = []
+    while True:
+        p = node.work()
+        if p is flow.EOS:
+            break
+        out.append(p)
+    o = oracle.mfcc_dc(oracle.frontend_cfg(), oracle.dc_cfg(), x)
+    assert len(out) == o["feats"].shape[0] and len(o["run_begin"]) > 1
+    # the oracle entry starts at time 0: shifted times agree up to the rounding of the additions
+    assert np.allclose([p.start for p in out], t0 + o["t_start"], rtol=0, atol=1e-9)
+    assert np.allclose([p.end for p in out], t0 + o["t_end"], rtol=0, atol=1e-9)
+    assert rel_err(np.stack([p.data for p in out]), o["feats"]) < RTOL
