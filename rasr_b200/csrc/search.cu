@@ -244,23 +244,20 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
 constexpr uint32_t kFirst = 1u, kSecond = 2u, kLast = 1u << 17, kWordShift = 18, kMaxValues = 32;
 
 struct SmemLayout {  // byte offsets into the dynamic shared memory of the register-resident kernel
-    uint32_t xch, cInfo, end, rows, uni, exit, bkLm, cBkp, total;
+    uint32_t xch, end, rows, uni, exit, bkLm, total;
     SmemLayout(uint32_t nWarps, uint32_t W, uint32_t rowFloats, uint32_t maxT) {
-        const uint32_t nChunks = (W + 31) / 32;
-        uint32_t       o       = 128;
+        uint32_t o = 128;
         auto take = [&](uint32_t bytes) {
             const uint32_t at = o;
             o += (bytes + 15) & ~15u;
             return at;
         };
         xch   = take(2 * nWarps * 16);
-        cInfo = take(nChunks * 16);
         end   = take(W * 8);
         rows  = take(2 * rowFloats * 4);
         uni   = take(W * 4);
         exit  = take(W * 4);
         bkLm  = take(maxT * 4);
-        cBkp  = take(nChunks * 4);
         total = o;
     }
     SmemLayout() = default;
@@ -273,8 +270,9 @@ struct SearchParams2 {
     const float*    values;    // [32] distinct transition penalties
     const float*    unigram;   // [W]
     const float*    wordExit;  // [W] exit penalty of the word's last state
+    const uint32_t* warpWords; // [nWarps + 1] words whose last state lives in warp i: [warpWords[i], warpWords[i + 1])
     float           maxAbsUni;
-    uint32_t        W, nChunks, maxT, rowFloats, nStates;  // rowFloats: nEmis rounded up to 4
+    uint32_t        W, maxT, rowFloats, nStates;  // rowFloats: nEmis rounded up to 4
     int             forceScan;           // test hook: always replay the sequential scan
     const float*    scores;
     const int64_t*  frameOff;
@@ -304,19 +302,20 @@ __device__ __forceinline__ float key_float(uint32_t k) {
 template<int NPT>
 __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const SearchParams2 p) {
     extern __shared__ __align__(128) unsigned char smemReg[];
-    const uint32_t nThreads = blockDim.x, nWarps = nThreads / 32, nChunks = p.nChunks;
+    const uint32_t nThreads = blockDim.x, nWarps = nThreads / 32;
     // the carve-up is computed on the host (SmemLayout): one constant-bank operand per table address
     float*  sT    = reinterpret_cast<float*>(smemReg);                   // [32] penalty values, one per bank
     float4* xch   = reinterpret_cast<float4*>(smemReg + p.lay.xch);      // [2][nWarps] {s[n-2], s[n-1], b[n-2], b[n-1]} of lane 31
-    uint4*  cInfo = reinterpret_cast<uint4*>(smemReg + p.lay.cInfo);     // [nChunks] {min key, second key, word, lmScore}
     float2* sEnd  = reinterpret_cast<float2*>(smemReg + p.lay.end);      // [W] word end {candidate score, bkp}
     float*  rows  = reinterpret_cast<float*>(smemReg + p.lay.rows);      // [2][rowFloats], 16-byte aligned
     float*  sUni  = reinterpret_cast<float*>(smemReg + p.lay.uni);       // [W]
     float*  sExit = reinterpret_cast<float*>(smemReg + p.lay.exit);      // [W]
     float*  sBkLm = reinterpret_cast<float*>(smemReg + p.lay.bkLm);      // [maxT] lmScore of the book entries
-    int*    cBkp  = reinterpret_cast<int*>(smemReg + p.lay.cBkp);        // [nChunks] back pointer of the chunk's best word
-    __shared__ int   sLast;
-    __shared__ float sLastScore, sLastLm, sMaxLm;  // sMaxLm: bound on |lmScore| of the book entries so far
+    // per warp and frame parity: best word end of the warp's words {min key, second key, word, lmScore}, its bkp
+    __shared__ uint4 wInfo[2][32];
+    __shared__ int   wBkp[2][32];
+    __shared__ float sMaxLm[2];   // bound on |lmScore| of the book entries so far, by frame parity (written by thread 0)
+    __shared__ float sReplay[4];  // result of the sequential replay: score, lmScore, word, bkp
 
     const int     u  = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t f0 = p.frameOff[u];
@@ -340,8 +339,9 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
         sUni[i]  = p.unigram[i];
         sExit[i] = p.wordExit[i];
     }
-    // this thread's states
+    // this thread's states; the words whose LAST state lives in this warp are a contiguous range
     const uint32_t i0 = (uint32_t)tid * NPT;
+    const uint32_t wordA = p.warpWords[warp], wordB = p.warpWords[warp + 1];
     float    hs[NPT];
     int      hb[NPT];
     uint32_t meta[NPT], emOff[NPT / 2];
@@ -358,24 +358,27 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
         xch[warp]          = make_float4(FLT_MAX, FLT_MAX, __int_as_float(-1), __int_as_float(-1));
         xch[nWarps + warp] = make_float4(FLT_MAX, FLT_MAX, __int_as_float(-1), __int_as_float(-1));
     }
-    if (tid == 0) {
-        sLast      = -1;
-        sLastScore = 0.0f;
-        sLastLm    = 0.0f;
-        sMaxLm     = 0.0f;
-    }
+    if (tid == 0)
+        sMaxLm[0] = sMaxLm[1] = 0.0f;
+    // the newest book entry: every warp tracks it in registers (the book keeping below is evaluated by all warps)
+    int   last      = -1;
+    float lastScore = 0.0f, lastLm = 0.0f;  // 0 before the first entry
     cp_async_wait_all();
     __syncthreads();
     const unsigned char* sTb = reinterpret_cast<const unsigned char*>(sT);
+    // lmScore of a hypothesis that came from book entry bk (the newest entry is not read from shared memory: it was
+    // written after the last barrier)
+    auto lm_of = [&](uint32_t w, int bk) {
+        const float un = sUni[w];
+        return bk >= 0 ? __fadd_rn(un, bk == last ? lastLm : sBkLm[bk]) : un;
+    };
 
     for (int t = 1; t <= T; ++t) {
         const int par = t & 1;  // score row and boundary states of this frame are in buffer par
         if (t < T)
             prefetch_row(t + 1);
-        const unsigned char* row       = reinterpret_cast<const unsigned char*>(rows + par * p.rowFloats);
-        const int            last      = sLast;
-        const float          lastScore = sLastScore, lastLm = sLastLm;  // 0 before the first book entry
-        if ((uint32_t)(warp * 32 * NPT) < p.nStates) {  // warps behind the last state only take part in the book keeping
+        const unsigned char* row = reinterpret_cast<const unsigned char*>(rows + par * p.rowFloats);
+        {
             // previous-frame values of the two states left of my block
             float pS2 = __shfl_up_sync(0xffffffffu, hs[NPT - 2], 1), pS1 = __shfl_up_sync(0xffffffffu, hs[NPT - 1], 1);
             int   pB2 = __shfl_up_sync(0xffffffffu, hb[NPT - 2], 1), pB1 = __shfl_up_sync(0xffffffffu, hb[NPT - 1], 1);
@@ -427,57 +430,53 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
                 xch[(par ^ 1) * nWarps + warp] =
                         make_float4(hs[NPT - 2], hs[NPT - 1], __int_as_float(hb[NPT - 2]), __int_as_float(hb[NPT - 1]));
         }
-        __syncthreads();
-        // per 32-word chunk: smallest candidate, the second smallest, and for the first word holding the smallest its
-        // index, lmScore and back pointer
-        for (uint32_t c = warp; c < nChunks; c += nWarps) {
-            const uint32_t w  = c * 32 + lane;
-            float2         en = make_float2(FLT_MAX, __int_as_float(-1));
-            float          un = 0.0f;
-            if (w < p.W) {
-                en = sEnd[w];
-                un = sUni[w];
-            }
-            const uint32_t key = w < p.W ? float_key(en.x) : 0xffffffffu;
-            const uint32_t k1  = __reduce_min_sync(0xffffffffu, key);
-            const int      i1  = __ffs(__ballot_sync(0xffffffffu, key == k1)) - 1;
-            const uint32_t k2  = __reduce_min_sync(0xffffffffu, lane == i1 ? 0xffffffffu : key);
-            if (lane == i1) {
-                const int   bk = __float_as_int(en.y);
-                const float lm = bk >= 0 ? __fadd_rn(un, sBkLm[bk]) : un;  // the hypothesis' lmScore
-                cInfo[c] = make_uint4(k1, k2, w, __float_as_uint(lm));
-                cBkp[c]  = bk;
-            }
-        }
-        cp_async_wait_all();  // next frame's score row has landed (made visible by the barriers below)
-        __syncthreads();
-        if (warp == 0) {
-            float nbScore = FLT_MAX, nbLm = 0.0f;
-            int   nbWord = -1, nbBkp = -1;
-            // combine the chunks: lane-local over chunks lane, lane + 32, ..., then across lanes
-            uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
-            int   bestBk = -1;
-            if ((uint32_t)lane < nChunks) {
-                best   = cInfo[lane];
-                bestBk = cBkp[lane];
-            }
+        // best word end among this warp's words: smallest candidate, the first word holding it, the second smallest
+        __syncwarp();
+        {
+            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu, bw = 0;
+            int      bbk = -1;
 #pragma unroll 1
-            for (uint32_t c = lane + 32; c < nChunks; c += 32) {
-                const uint4 ci = cInfo[c];
-                if (ci.x < best.x) {
-                    const uint32_t second = min(best.x, ci.y);
-                    best   = ci;
-                    best.y = second;
-                    bestBk = cBkp[c];
+            for (uint32_t c = wordA; c < wordB; c += 32) {
+                const uint32_t w  = c + lane;
+                float2         en = make_float2(FLT_MAX, __int_as_float(-1));
+                if (w < wordB)
+                    en = sEnd[w];
+                const uint32_t key = w < wordB ? float_key(en.x) : 0xffffffffu;
+                const uint32_t m1  = __reduce_min_sync(0xffffffffu, key);
+                const int      i1  = __ffs(__ballot_sync(0xffffffffu, key == m1)) - 1;
+                const uint32_t m2  = __reduce_min_sync(0xffffffffu, lane == i1 ? 0xffffffffu : key);
+                const int      bk1 = __shfl_sync(0xffffffffu, __float_as_int(en.y), i1);
+                if (m1 < k1) {  // strictly smaller: later words only replace on a real improvement
+                    k2  = min(k1, m2);
+                    k1  = m1;
+                    bw  = c + i1;
+                    bbk = bk1;
                 }
                 else
-                    best.y = min(best.y, ci.x);
+                    k2 = min(k2, m1);
+            }
+            if (lane == 0) {
+                wInfo[par][warp] = make_uint4(k1, k2, bw, __float_as_uint(wordA < wordB ? lm_of(bw, bbk) : 0.0f));
+                wBkp[par][warp]  = bbk;
+            }
+        }
+        cp_async_wait_all();  // next frame's score row has landed (made visible by the barrier)
+        __syncthreads();      // the only barrier of a frame
+        // book keeping (:381-432), evaluated by every warp: combine the warps' best word ends
+        {
+            float nbScore = FLT_MAX, nbLm = 0.0f;
+            int   nbWord = -1, nbBkp = -1;
+            uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+            int   bestBk = -1;
+            if ((uint32_t)lane < nWarps) {
+                best   = wInfo[par][lane];
+                bestBk = wBkp[par][lane];
             }
             const uint32_t kM  = __reduce_min_sync(0xffffffffu, best.x);
             const int      lj  = __ffs(__ballot_sync(0xffffffffu, best.x == kM)) - 1;
             const uint32_t kM2 = __reduce_min_sync(0xffffffffu, lane == lj ? best.y : best.x);
             const float    M = key_float(kM), M2 = key_float(kM2);
-            const float    slack = __fmul_rn(__fadd_rn(fabsf(M), __fadd_rn(p.maxAbsUni, sMaxLm)), 4.76837158203125e-07f);
+            const float    slack = __fmul_rn(__fadd_rn(fabsf(M), __fadd_rn(p.maxAbsUni, sMaxLm[par])), 4.76837158203125e-07f);
             if (!p.forceScan && M2 > __fadd_rn(M, slack)) {
                 if (M < FLT_MAX) {  // the scan accepts the unique minimum last
                     nbWord  = (int)__shfl_sync(0xffffffffu, best.z, lj);
@@ -487,19 +486,10 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
                 }
             }
             else {
-                // the sequential scan over the words, replayed on the chunks that matter
+                // ties / near ties: warp 0 replays the sequential scan over the words, 32 at a time
+                if (warp == 0) {
 #pragma unroll 1
-                for (uint32_t cbase = 0; cbase < nChunks; cbase += 32) {
-                    const uint32_t cc    = cbase + lane;
-                    const float    cmin  = cc < nChunks ? key_float(cInfo[cc].x) : FLT_MAX;
-                    uint32_t       ctodo = 0xffffffffu;
-                    while (true) {
-                        const float    thr   = __fadd_rn(nbScore, nbLm);
-                        const uint32_t chits = __ballot_sync(0xffffffffu, cmin < thr) & ctodo;
-                        if (!chits)
-                            break;
-                        const int      cf   = __ffs(chits) - 1;  // next chunk (in word order) holding a word that beats thr
-                        const uint32_t base = (cbase + cf) * 32;
+                    for (uint32_t base = 0; base < p.W; base += 32) {
                         const uint32_t w    = base + lane;
                         float          cand = FLT_MAX, lmw = 0.0f;
                         int            bk   = -1;
@@ -507,44 +497,53 @@ __global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const Searc
                             const float2 en = sEnd[w];
                             bk   = __float_as_int(en.y);
                             cand = en.x;
-                            lmw  = bk >= 0 ? __fadd_rn(sUni[w], sBkLm[bk]) : sUni[w];  // the hypothesis' lmScore
+                            lmw  = lm_of(w, bk);
                         }
                         uint32_t todo = 0xffffffffu;
                         while (true) {
-                            const float    thr2 = __fadd_rn(nbScore, nbLm);
-                            const uint32_t hits = __ballot_sync(0xffffffffu, cand < thr2) & todo;
+                            const float    thr  = __fadd_rn(nbScore, nbLm);
+                            const uint32_t hits = __ballot_sync(0xffffffffu, cand < thr) & todo;
                             if (!hits)
                                 break;
-                            const int   first    = __ffs(hits) - 1;
+                            const int   first    = __ffs(hits) - 1;  // lowest word of the chunk that beats the current best
                             const float tmpScore = __shfl_sync(0xffffffffu, cand, first);
                             nbLm    = __shfl_sync(0xffffffffu, lmw, first);
                             nbBkp   = __shfl_sync(0xffffffffu, bk, first);
                             nbScore = __fsub_rn(tmpScore, nbLm);
                             nbWord  = (int)(base + first);
-                            todo    = first == 31 ? 0u : (0xffffffffu << (first + 1));
+                            todo    = first == 31 ? 0u : (0xffffffffu << (first + 1));  // words before it were rejected
                         }
-                        ctodo = cf == 31 ? 0u : (0xffffffffu << (cf + 1));  // earlier chunks were already passed
+                    }
+                    if (lane == 0) {
+                        sReplay[0] = nbScore;
+                        sReplay[1] = nbLm;
+                        sReplay[2] = __int_as_float(nbWord);
+                        sReplay[3] = __int_as_float(nbBkp);
                     }
                 }
+                __syncthreads();  // the condition is the same in every warp
+                nbScore = sReplay[0];
+                nbLm    = sReplay[1];
+                nbWord  = __float_as_int(sReplay[2]);
+                nbBkp   = __float_as_int(sReplay[3]);
             }
-            if (nbScore != FLT_MAX && lane == 0) {
-                {
-                    const int b     = sLast + 1;  // entries are only ever appended: the newest is the last
-                    int4*     books = p.books + 2 * (f0 + b);
+            if (nbScore != FLT_MAX) {
+                ++last;  // entries are only ever appended: the newest is the last
+                if (tid == 0) {
+                    int4* books = p.books + 2 * (f0 + last);
                     books[0] = make_int4(__float_as_int(nbScore), __float_as_int(nbLm), nbWord, nbBkp);
                     books[1] = make_int4(t, 0, 0, 0);
-                    sMaxLm   = fmaxf(sMaxLm, fabsf(nbLm));
-                    sBkLm[b]         = nbLm;
-                    sLast            = b;
-                    sLastScore       = nbScore;
-                    sLastLm          = nbLm;
+                    sBkLm[last] = nbLm;
                 }
+                lastScore = nbScore;
+                lastLm    = nbLm;
             }
+            if (tid == 0)  // read by every warp after the next barrier
+                sMaxLm[par ^ 1] = nbScore != FLT_MAX ? fmaxf(sMaxLm[par], fabsf(nbLm)) : sMaxLm[par];
         }
-        __syncthreads();
     }
     if (tid == 0)
-        p.nBooks[u] = sLast + 1;
+        p.nBooks[u] = last + 1;
 }
 
 }  // namespace
@@ -553,7 +552,7 @@ struct rb_search {
     rb::DeviceInfo dev;
     uint32_t       W = 0, nStates = 0, nModels = 0, entryModel = 0;
     cudaStream_t   stream = nullptr;
-    rb::DevBuf<uint32_t> dWordOff, dStateEmis, dStateTdp, dStateMeta, dStateEmOff;
+    rb::DevBuf<uint32_t> dWordOff, dStateEmis, dStateTdp, dStateMeta, dStateEmOff, dWarpWords;
     rb::DevBuf<float>    dValues, dWordExit;
     float                maxAbsUni = 0.0f;
     int                  npt = 0, regThreads = 0;  // states per thread / threads of the register-resident kernel, 0: per-word kernel
@@ -649,8 +648,24 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
                 if (atoi(e) * (uint32_t)kThreads >= nStates && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16))
                     h->npt = atoi(e);
             h->regThreads = (int)(((nStates + h->npt - 1) / h->npt + 31) / 32 * 32);
-            // one warp per 32-word chunk of the book keeping where that fits (warps without states skip the update)
-            h->regThreads = std::max(h->regThreads, (int)std::min<uint32_t>(kThreads, (lx->n_words + 31) / 32 * 32));
+            // words whose last state lives in warp i (contiguous: states are in lexicon order)
+            std::vector<uint32_t> warpWords(h->regThreads / 32 + 1, lx->n_words);
+            warpWords[0] = 0;
+            for (size_t i = 1; i < warpWords.size(); ++i) {  // first word whose last state is at or behind warp i
+                uint32_t lo = 0, hi = lx->n_words;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) / 2;
+                    if ((lx->word_offsets[mid + 1] - 1) / (32u * h->npt) < i)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                warpWords[i] = lo;
+            }
+            if (h->dWarpWords.upload(warpWords.data(), warpWords.size(), h->stream) != RB_OK) {
+                rb::set_error("lexicon upload failed");
+                return fail(RB_ERR_CUDA);
+            }
             h->maxEmis    = maxEmis;
             values.resize(kMaxValues, inf);
             if (h->dStateMeta.upload(meta.data(), meta.size(), h->stream) != RB_OK ||
@@ -730,10 +745,10 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
     const uint32_t rowFloats = ((uint32_t)n_emissions + 3) & ~3u;
     const SmemLayout lay(h->regThreads / 32, h->W, rowFloats, (uint32_t)maxT);
     const size_t     smem2 = lay.total;
-    if (h->npt && h->maxEmis < (uint32_t)n_emissions && smem2 <= h->dev.smem_optin - 1024) {
+    if (h->npt && h->maxEmis < (uint32_t)n_emissions && smem2 + 4096 <= h->dev.smem_optin) {
         SearchParams2 q;
         q.lay       = lay;
-        q.nChunks   = (h->W + 31) / 32;
+        q.warpWords = h->dWarpWords.p;
         q.nStates   = h->nStates;
         q.stMeta    = h->dStateMeta.p;
         q.stEmOff   = h->dStateEmOff.p;
