@@ -233,12 +233,15 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
 //  * The score row of the NEXT frame is copied to shared memory with cp.async while this frame is processed.
 //  * Book keeping (:381-432) is a sequential scan "accept w if cand_w < nbScore + nbLm; nbScore = cand_w - lm_w" whose
 //    threshold after accepting w is g_w = fl(fl(cand_w - lm_w) + lm_w), within 2^-24 (2|cand_w| + |lm_w|) of cand_w.
-//    Every warp reduces one 32-word chunk to (min, first lane of the min, second smallest) with REDUX; warp 0 combines
-//    them.  If the second smallest candidate exceeds the smallest M by more than 2^-21 (|M| + max|lm|), every word
-//    accepted before the first argmin j leaves a threshold above M, so j is accepted, and nothing after j beats g_j:
-//    the scan ends at j, and its result is written directly.  Otherwise (ties, near ties) warp 0 replays the scan:
-//    it walks the chunks in word order, opens only those whose minimum beats the current threshold (exists w: cand <
-//    thr  <=>  min cand < thr) and replays the reference's sequential acceptance test inside them.
+//    After its state update every warp reduces the words whose LAST state it owns (a contiguous range) with REDUX to
+//    (min, first word holding it, second smallest); after the one barrier of the frame EVERY warp combines the <= 32
+//    per-warp results and keeps the newest book entry in registers (thread 0 writes it out), so the next frame needs
+//    no second barrier.  If the second smallest candidate exceeds the smallest M by more than 2^-21 (|M| + max|lm|),
+//    every word accepted before the first argmin j leaves a threshold above M, so j is accepted, and nothing after j
+//    beats g_j: the scan ends at j, and its result is taken directly.  Otherwise (ties, near ties) warp 0 replays the
+//    scan, 32 words per ballot, and broadcasts the result.
+//  * What is written after the barrier and read before the next one is double-buffered by frame parity (exchange
+//    slots, per-warp results, the lm bound); the lmScore of the newest book entry comes from registers.
 // ------------------------------------------------------------------------------------------------------------------
 // meta: first | second << 1 | loop index << 2 | forward-in index << 7 | skip-in index << 12 | last << 17 | word << 18
 constexpr uint32_t kFirst = 1u, kSecond = 2u, kLast = 1u << 17, kWordShift = 18, kMaxValues = 32;
