@@ -339,6 +339,11 @@ int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_emissions, c
  * Book::score without LM, Book::lmScore); capacity = frames of the segment; returns the number of words or < 0 */
 long rb_search_traceback(const rb_search* h, int utt, uint32_t* words, int32_t* times, float* am_scores,
                          float* lm_scores);
+/* all segments of the last decode at once: word_offsets [n_utt + 1] receives prefix counts into the flat arrays
+ * (room for `capacity` words each, any may be NULL; total frames of the decode is always enough).  Returns the
+ * total number of words, < 0 on error. */
+long rb_search_traceback_all(const rb_search* h, int64_t* word_offsets, uint32_t* words, int32_t* times,
+                             float* am_scores, float* lm_scores, long capacity);
 
 /* =====================================================================================
  * Test hook: one bf16 tcgen05 GEMM  D[M x N] = A[M x K] * B[N x K]^T (+bias, activation),

@@ -355,9 +355,15 @@ struct rb_frontend {
     struct StageSlot {
         rb::PinnedBuf<char> host;
         rb::DevBuf<char>    dev;
-        cudaEvent_t         ev = nullptr;
+        cudaEvent_t         ev = nullptr, evUp = nullptr;
     } slots[kSlots];
     int nextSlot = 0;
+    // Host-buffer calls set this to their H2D stream: the tile tables are then uploaded on it, in line with the bulk
+    // sample copies.  Issued on the kernel stream the small copy only reaches the copy engine once the stream's
+    // dependencies have resolved -- by then the bulk copies of the NEXT slabs are queued in front of it, and the
+    // kernels of slab i wait for the transfers of slabs i+1.. (measured: 0.45 ms per call).
+    cudaStream_t uploadStream = nullptr;
+    rb::CopyStreams copy;  // streams / events of the host-buffer calls
     // streaming state
     std::vector<float> pending;
     double             pendingStart = 0;
@@ -375,6 +381,9 @@ struct rb_frontend {
                 cudaEventSynchronize(sl.ev);
                 cudaEventDestroy(sl.ev);
             }
+        for (StageSlot& sl : slots)
+            if (sl.evUp)
+                cudaEventDestroy(sl.evUp);
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -1015,7 +1024,15 @@ int run_segments(rb_frontend* h, const float* dSamples, const int64_t* segBeg, c
     }
     const int64_t total = fOff[nSeg];
     RB_CHECK(h->dCep.reserve((size_t)total * h->cfg.n_cepstra));
-    RB_CUDA(cudaMemcpyAsync(slot.dev.p, slot.host.p, bytes, cudaMemcpyHostToDevice, s));
+    if (h->uploadStream && h->uploadStream != s) {
+        if (!slot.evUp)
+            RB_CUDA(cudaEventCreateWithFlags(&slot.evUp, cudaEventDisableTiming));
+        RB_CUDA(cudaMemcpyAsync(slot.dev.p, slot.host.p, bytes, cudaMemcpyHostToDevice, h->uploadStream));
+        RB_CUDA(cudaEventRecord(slot.evUp, h->uploadStream));
+        RB_CUDA(cudaStreamWaitEvent(s, slot.evUp, 0));
+    }
+    else
+        RB_CUDA(cudaMemcpyAsync(slot.dev.p, slot.host.p, bytes, cudaMemcpyHostToDevice, s));
 
     FeParams p;
     p.samples      = dSamples;
@@ -1287,14 +1304,10 @@ int process_host(rb_frontend* h, const void* samplesRaw, int channels, int track
         if (u == n_utt || fo[u] - fo[cut.back()] >= target)
             cut.push_back(u);
     const int    nSlabs = (int)cut.size() - 1;
-    cudaStream_t sIn = nullptr, sOut = nullptr;
-    RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
-    RB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> evIn(nSlabs), evK(nSlabs);
-    for (int i = 0; i < nSlabs; ++i) {
-        cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming);
-    }
+    RB_CHECK(h->copy.ensure(2 * (size_t)nSlabs));
+    cudaStream_t sIn = h->copy.in, sOut = h->copy.out;
+    cudaEvent_t* evIn = h->copy.pool.data();
+    cudaEvent_t* evK  = h->copy.pool.data() + nSlabs;
     int rc = RB_OK;
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const int     u0 = cut[i], u1 = cut[i + 1];
@@ -1316,9 +1329,12 @@ int process_host(rb_frontend* h, const void* samplesRaw, int channels, int track
                     h->dPcm.p + sA * channels, h->dSamples.p + sA, n, channels, track);
             rb::count_launch();
         }
-        if (rc == RB_OK)
+        if (rc == RB_OK) {
+            h->uploadStream = sIn;
             rc = run_device(h, h->dSamples.p, rel.data() + u0, u1 - u0, h->dFeats.p + fA * h->featDim, h->stream,
                             nullptr);
+            h->uploadStream = nullptr;
+        }
         cudaEventRecord(evK[i], h->stream);
         cudaStreamWaitEvent(sOut, evK[i], 0);
         if (rc == RB_OK && feats && fB > fA &&
@@ -1328,12 +1344,6 @@ int process_host(rb_frontend* h, const void* samplesRaw, int channels, int track
     }
     const cudaError_t e1 = cudaStreamSynchronize(sIn), e2 = cudaStreamSynchronize(h->stream),
                       e3 = cudaStreamSynchronize(sOut);
-    for (int i = 0; i < nSlabs; ++i) {
-        cudaEventDestroy(evIn[i]);
-        cudaEventDestroy(evK[i]);
-    }
-    cudaStreamDestroy(sIn);
-    cudaStreamDestroy(sOut);
     if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
         rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != RB_OK)
@@ -1492,6 +1502,9 @@ int rb_frontend_convert_s16_dev(const rb_frontend* h, const int16_t* d_pcm, floa
 // accessors for pipeline.cu
 rb::DeviceInfo rb_frontend_device(const rb_frontend* h) {
     return h->dev;
+}
+void rb_frontend_set_upload_stream(rb_frontend* h, cudaStream_t s) {
+    h->uploadStream = s;
 }
 cudaStream_t rb_frontend_stream(const rb_frontend* h) {
     return h->stream;

@@ -6,6 +6,8 @@ struct rb_frontend;
 struct rb_gmm;
 
 cudaStream_t   rb_frontend_stream(const rb_frontend* h);
+// host-buffer pipelines: upload the per-call tile tables on this (H2D) stream; nullptr: on the kernel stream
+void           rb_frontend_set_upload_stream(rb_frontend* h, cudaStream_t s);
 rb::DeviceInfo rb_frontend_device(const rb_frontend* h);
 int            rb_frontend_feat_dim(const rb_frontend* h);
 int            rb_frontend_convert_s16_dev(const rb_frontend* h, const int16_t* d_pcm, float* d_out, long n, int channels,

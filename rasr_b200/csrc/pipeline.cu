@@ -8,6 +8,7 @@ namespace {
 struct Scratch {
     rb::DevBuf<float>   samples, feats, post, scores;
     rb::DevBuf<int16_t> pcm;
+    rb::CopyStreams     copy;
 };
 // one scratch set per front-end handle would be cleaner; pipelines are few, so key by handle
 Scratch& scratch_for(const rb_frontend* fe) {
@@ -72,21 +73,21 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
     // slab boundaries (utterance indices).  The call is bound by the D2H stream of the scores, so the first slabs are
     // small (the D2H stream starts early) and grow geometrically to ~16384 frames
     std::vector<int> cut(1, 0);
-    long             target = 2048;
+    long             target = 2048, targetMax = 16384;
+    if (const char* e = getenv("RB_PIPE_SLAB0"))  // experiments
+        target = std::max(1, atoi(e));
+    if (const char* e = getenv("RB_PIPE_SLABMAX"))
+        targetMax = std::max(1, atoi(e));
     for (int u = 1; u <= n_utt; ++u)
         if (u == n_utt || fo[u] - fo[cut.back()] >= target) {
             cut.push_back(u);
-            target = std::min<long>(2 * target, 16384);
+            target = std::min<long>(2 * target, targetMax);
         }
     const int    nSlabs = (int)cut.size() - 1;
-    cudaStream_t sIn = nullptr, sOut = nullptr;
-    RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
-    RB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> evIn(nSlabs), evK(nSlabs);
-    for (int i = 0; i < nSlabs; ++i) {
-        cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming);
-    }
+    RB_CHECK(sc.copy.ensure(2 * (size_t)nSlabs));
+    cudaStream_t sIn = sc.copy.in, sOut = sc.copy.out;
+    cudaEvent_t* evIn = sc.copy.pool.data();
+    cudaEvent_t* evK  = sc.copy.pool.data() + nSlabs;
     int rc = RB_OK;
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const int     u0 = cut[i], u1 = cut[i + 1];
@@ -108,9 +109,12 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
         if (rc == RB_OK && channels)
             rc = rb_frontend_convert_s16_dev(fe, sc.pcm.p + sA * channels, sc.samples.p + sA, (long)(sB - sA), channels,
                                              track, sK);
-        if (rc == RB_OK && fB > fA)
+        if (rc == RB_OK && fB > fA) {
+            rb_frontend_set_upload_stream(fe, sIn);
             rc = rb_pipeline_score_dev(fe, gmm, sc.samples.p, rel.data() + u0, u1 - u0, sc.feats.p + fA * D,
                                        sc.scores.p + fA * M, sK);
+            rb_frontend_set_upload_stream(fe, nullptr);
+        }
         cudaEventRecord(evK[i], sK);
         cudaStreamWaitEvent(sOut, evK[i], 0);
         if (rc == RB_OK && fB > fA) {
@@ -123,12 +127,6 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
         }
     }
     const cudaError_t e1 = cudaStreamSynchronize(sIn), e2 = cudaStreamSynchronize(sK), e3 = cudaStreamSynchronize(sOut);
-    for (int i = 0; i < nSlabs; ++i) {
-        cudaEventDestroy(evIn[i]);
-        cudaEventDestroy(evK[i]);
-    }
-    cudaStreamDestroy(sIn);
-    cudaStreamDestroy(sOut);
     if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
         rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != RB_OK)
@@ -215,15 +213,11 @@ extern "C" int rb_pipeline_nn_score(rb_frontend* fe, rb_postproc* pp, rb_nn* nn,
     RB_CHECK(sc.feats.reserve((size_t)T * D));
     RB_CHECK(sc.post.reserve((size_t)(pp ? T : 1) * Dp));
     RB_CHECK(sc.scores.reserve((size_t)2 * maxSlab * M));  // two slabs in flight: scoring of i, D2H of i-1
-    cudaStream_t sIn = nullptr, sOut = nullptr;
-    RB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
-    RB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> evIn(nSlabs), evK(nSlabs), evOut(nSlabs);
-    for (int i = 0; i < nSlabs; ++i) {
-        cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&evOut[i], cudaEventDisableTiming);
-    }
+    RB_CHECK(sc.copy.ensure(3 * (size_t)nSlabs));
+    cudaStream_t sIn = sc.copy.in, sOut = sc.copy.out;
+    cudaEvent_t* evIn  = sc.copy.pool.data();
+    cudaEvent_t* evK   = sc.copy.pool.data() + nSlabs;
+    cudaEvent_t* evOut = sc.copy.pool.data() + 2 * nSlabs;
     int rc = RB_OK;
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const int     u0 = cut[i], u1 = cut[i + 1];
@@ -236,9 +230,12 @@ extern "C" int rb_pipeline_nn_score(rb_frontend* fe, rb_postproc* pp, rb_nn* nn,
         cudaStreamWaitEvent(sK, evIn[i], 0);
         if (i >= 2)
             cudaStreamWaitEvent(sK, evOut[i - 2], 0);  // the score buffer of slab i-2 has been copied out
-        if (rc == RB_OK && fB > fA)
+        if (rc == RB_OK && fB > fA) {
+            rb_frontend_set_upload_stream(fe, sIn);
             rc = rb_pipeline_nn_score_dev(fe, pp, nn, sc.samples.p, rel.data() + u0, u1 - u0, sc.feats.p + fA * D,
                                           pp ? sc.post.p + fA * Dp : nullptr, dScores, sK);
+            rb_frontend_set_upload_stream(fe, nullptr);
+        }
         cudaEventRecord(evK[i], sK);
         cudaStreamWaitEvent(sOut, evK[i], 0);
         if (rc == RB_OK && fB > fA &&
@@ -248,13 +245,6 @@ extern "C" int rb_pipeline_nn_score(rb_frontend* fe, rb_postproc* pp, rb_nn* nn,
         cudaEventRecord(evOut[i], sOut);
     }
     const cudaError_t e1 = cudaStreamSynchronize(sIn), e2 = cudaStreamSynchronize(sK), e3 = cudaStreamSynchronize(sOut);
-    for (int i = 0; i < nSlabs; ++i) {
-        cudaEventDestroy(evIn[i]);
-        cudaEventDestroy(evK[i]);
-        cudaEventDestroy(evOut[i]);
-    }
-    cudaStreamDestroy(sIn);
-    cudaStreamDestroy(sOut);
     if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
         rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != RB_OK)

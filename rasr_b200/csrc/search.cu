@@ -842,3 +842,37 @@ extern "C" long rb_search_traceback(const rb_search* h, int utt, uint32_t* words
     }
     return n;
 }
+
+// every segment of the last decode in one call: word_offsets [n_utt + 1] are prefix counts into the flat arrays
+// (capacity entries each; any may be NULL).  Returns the total number of words, < 0 on error.
+extern "C" long rb_search_traceback_all(const rb_search* h, int64_t* word_offsets, uint32_t* words, int32_t* times,
+                                        float* am_scores, float* lm_scores, long capacity) {
+    if (!h || !word_offsets) {
+        rb::set_error("NULL argument");
+        return RB_ERR_INVALID;
+    }
+    const int n_utt  = (int)h->nBooks.size();
+    long      total  = 0;
+    word_offsets[0]  = 0;
+    std::vector<int> chain;
+    for (int u = 0; u < n_utt; ++u) {
+        const int64_t f0 = h->frameOff[u];
+        chain.clear();
+        for (int b = h->nBooks[u] - 1; b >= 0; b = h->bookBkp[f0 + b])
+            chain.push_back(b);
+        for (auto it = chain.rbegin(); it != chain.rend(); ++it, ++total) {
+            if (total >= capacity)
+                continue;
+            if (words)
+                words[total] = (uint32_t)h->bookWord[f0 + *it];
+            if (times)
+                times[total] = h->bookTime[f0 + *it];
+            if (am_scores)
+                am_scores[total] = h->bookScore[f0 + *it];
+            if (lm_scores)
+                lm_scores[total] = h->bookLm[f0 + *it];
+        }
+        word_offsets[u + 1] = total;
+    }
+    return total;
+}

@@ -40,7 +40,7 @@ class FrontEnd:
         self.feat_dim = g.feat_dim
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None:  # capi is None while the interpreter shuts down
             capi.lib().rb_frontend_destroy(self._h)
             self._h = None
 

@@ -73,7 +73,7 @@ class GmmScorer:
         self.dim = mixture_set.dim
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None:  # capi is None while the interpreter shuts down
             capi.lib().rb_gmm_destroy(self._h)
             self._h = None
 

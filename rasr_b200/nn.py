@@ -58,7 +58,7 @@ class NnScorer:
         return cls(dims, acts, ws, bs, prior, prior_scale, **kw)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None:  # capi is None while the interpreter shuts down
             capi.lib().rb_nn_destroy(self._h)
             self._h = None
 

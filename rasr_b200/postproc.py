@@ -35,7 +35,7 @@ class PostProcessor:
         self.dim_out = int(capi.lib().rb_postproc_dim_out(self._h))
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None:  # capi is None while the interpreter shuts down
             capi.lib().rb_postproc_destroy(self._h)
             self._h = None
 

@@ -28,23 +28,34 @@ class LinearSearch:
         self._fo = None
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None:  # capi is None while the interpreter shuts down
             capi.lib().rb_search_destroy(self._h)
             self._h = None
 
     __del__ = close
 
     def _result(self):
-        out = []
-        for u in range(self._fo.size - 1):
-            cap = max(1, int(self._fo[u + 1] - self._fo[u]))
-            words, times = np.zeros(cap, np.uint32), np.zeros(cap, np.int32)
-            am, lm = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
-            n = capi.lib().rb_search_traceback(self._h, u, capi.ptr(words), capi.ptr(times), capi.ptr(am), capi.ptr(lm))
-            if n < 0:
-                capi.check(int(n))
-            out.append(dict(words=words[:n], times=times[:n], am=am[:n], lm=lm[:n]))
-        return out
+        n_utt = self._fo.size - 1
+        cap = max(1, int(self._fo[-1] - self._fo[0]))
+        wo = np.zeros(n_utt + 1, np.int64)
+        words, times = np.zeros(cap, np.uint32), np.zeros(cap, np.int32)
+        am, lm = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        n = capi.lib().rb_search_traceback_all(self._h, capi.ptr(wo), capi.ptr(words), capi.ptr(times), capi.ptr(am),
+                                               capi.ptr(lm), cap)
+        if n < 0:
+            capi.check(int(n))
+        return [dict(words=words[wo[u]:wo[u + 1]], times=times[wo[u]:wo[u + 1]], am=am[wo[u]:wo[u + 1]],
+                     lm=lm[wo[u]:wo[u + 1]]) for u in range(n_utt)]
+
+    def traceback(self, utt):
+        """one segment of the last decode (rb_search_traceback)"""
+        cap = max(1, int(self._fo[utt + 1] - self._fo[utt]))
+        words, times = np.zeros(cap, np.uint32), np.zeros(cap, np.int32)
+        am, lm = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        n = capi.lib().rb_search_traceback(self._h, utt, capi.ptr(words), capi.ptr(times), capi.ptr(am), capi.ptr(lm))
+        if n < 0:
+            capi.check(int(n))
+        return dict(words=words[:n], times=times[:n], am=am[:n], lm=lm[:n])
 
     def decode(self, scores, frame_offsets=None):
         """Host score matrix [frames x n_emissions]; returns one traceback dict per segment."""

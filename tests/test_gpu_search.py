@@ -49,9 +49,11 @@ def test_segments_are_independent_and_ties_resolve_like_the_reference(oracle):
     rng = np.random.default_rng(9)
     fo = np.array([0, 37, 38, 180, 400], np.int64)
     scores = rng.integers(1, 6, (400, 64)).astype(np.float32)
-    got = search.LinearSearch(lex).decode(scores, fo)
+    ls = search.LinearSearch(lex)
+    got = ls.decode(scores, fo)
     for u in range(4):
         assert same(got[u], oracle.linear_search(lex, scores[fo[u]:fo[u + 1]])), u
+        assert same(ls.traceback(u), got[u])  # the per-segment entry point agrees with the all-at-once one
 
 
 def test_scores_from_the_gmm_scorer_on_device(oracle, diag):
