@@ -93,3 +93,30 @@ def test_features_through_a_feature_cache(tmp_path):
             sl = slice(int(fo[u]), int(fo[u + 1]))
             assert np.array_equal(f, r["feats"][sl]) and np.array_equal(t[:, 0], r["t_start"][sl])
             assert np.array_equal(gmm.score(f), want[sl])
+
+
+def test_c3_shard_at_full_size(oracle, diag):
+    """BASELINE config C3, one GPU's shard (125 utterances x 1000 frames): checked through size-independent properties --
+    every utterance's rows equal the rows of the same utterance processed alone (sharding / batching cannot change a
+    result), 16-bit PCM input equals f32 input, the scores of sampled utterances equal the oracle scorer on the GPU
+    features bit for bit and the oracle pipeline within tolerance"""
+    samples, offs = synth.corpus(125, n_samples=160240, seed0=3000)
+    fe = flow.FrontEnd()
+    msd = synth.mixture_set()
+    gmm = mm.GmmScorer(mm.MixtureSet.from_dict(msd))
+    scores, feats, fo = pipeline.score_utterances(fe, gmm, samples, offs, want_feats=True)
+    assert scores.shape == (125000, 256) and np.isfinite(scores).all()
+    s16, _ = pipeline.score_utterances(fe, gmm, samples.astype(np.int16), offs, pcm_channels=1)
+    assert np.array_equal(s16, scores)
+    oms = oracle.MixtureSet(**msd)
+    for u in (0, 57, 124):
+        a, b = int(offs[u]), int(offs[u + 1])
+        alone, f_alone, _ = pipeline.score_utterances(fe, gmm, samples[a:b], np.array([0, b - a], np.int64), want_feats=True)
+        sl = slice(int(fo[u]), int(fo[u + 1]))
+        assert np.array_equal(feats[sl], f_alone) and np.array_equal(scores[sl], alone), u
+        assert np.array_equal(scores[sl], oracle.gmm_batch_float(oms, feats[sl])), u
+    want = oracle.gmm_batch_float(oms, oracle.mfcc(oracle.frontend_cfg(), samples[offs[57]:offs[58]])["feats"])
+    sl = slice(int(fo[57]), int(fo[58]))
+    rel = np.abs(scores[sl] - want) / np.abs(want)
+    diag("pipeline_c3_full", max_rel=float(rel.max()), frames=int(scores.shape[0]))
+    assert rel.max() < 1e-4
