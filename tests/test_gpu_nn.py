@@ -158,3 +158,28 @@ def test_scorer_from_reference_parameter_files(oracle, tmp_path):
     assert np.array_equal(got, ref)
     want = oracle.nn_scores(dims, acts, ws, bs, prior, 0.7, x)
     assert np.allclose(got, want, rtol=1e-4, atol=1e-4)
+
+
+def test_c4_at_full_size(oracle, diag):
+    """BASELINE config C4 at the benchmarked size (429 -> 6 x 2048 -> 12000, 75776 frames on the device, 3.6 GB of
+    scores): sampled rows equal the same frames scored in a small batch bit for bit (tile scheduling cannot change a
+    result) and the bf16 oracle within its tolerance; every score is finite"""
+    import torch
+
+    net = synth.network()
+    T = 75776
+    x = synth.features(T, 429, seed=8, scale=1.0)
+    sc = nn.NnScorer(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, "bf16")
+    d_x = torch.from_numpy(x).cuda()
+    d_s = torch.empty((T, 12000), dtype=torch.float32, device="cuda")
+    sc.score_dev(d_x, T, d_s)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(d_s).all())
+    rows = np.concatenate([np.arange(0, 24), np.arange(37000, 37024), np.arange(T - 24, T)])
+    got = d_s[torch.from_numpy(rows).cuda()].cpu().numpy()
+    assert np.array_equal(got, sc.score(x[rows]))
+    want = oracle.nn_scores(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, x[rows[:24]],
+                            mode=oracle.NN_BF16)
+    e = scale_err(got[:24], want)
+    diag("nn_c4_full", err=e, frames=T)
+    assert e < 3e-3

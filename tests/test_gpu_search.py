@@ -93,3 +93,31 @@ def test_rejects_bad_lexicon():
     bad["entry_model"] = 9
     with pytest.raises(capi.RasrB200Error):
         search.LinearSearch(bad)
+
+
+def test_c5_shard_at_full_size(oracle, diag):
+    """BASELINE config C5, one GPU's shard (125 segments x 1000 frames, 1000-word lexicon): audio in, word sequences
+    out, scores never leave the device.  Sampled segments equal the oracle's LinearSearch on the same score rows, and
+    decoding a segment alone gives the same result as decoding it in the batch"""
+    import torch
+
+    from rasr_b200 import flow, pipeline
+
+    samples, offs = synth.corpus(125, n_samples=160240, seed0=3000)
+    fe = flow.FrontEnd()
+    gmm = mm.GmmScorer(mm.MixtureSet.from_dict(synth.mixture_set()))
+    lex = synth.lexicon(1000, 256)
+    ls = search.LinearSearch(lex)
+    fo = fe.count_frames(offs)
+    T = int(fo[-1])
+    d_samples = torch.from_numpy(samples).cuda()
+    d_feats = torch.empty((T, 39), dtype=torch.float32, device="cuda")
+    d_scores = torch.empty((T, 256), dtype=torch.float32, device="cuda")
+    pipeline.score_utterances_dev(fe, gmm, d_samples, offs, d_feats, d_scores)
+    got = ls.decode_dev(d_scores, 256, fo)
+    assert len(got) == 125 and all(len(g["words"]) > 0 for g in got)
+    for u in (0, 63, 124):
+        rows = d_scores[int(fo[u]):int(fo[u + 1])].cpu().numpy()
+        assert same(got[u], oracle.linear_search(lex, rows)), u
+        assert same(got[u], ls.decode(rows)[0]), u
+    diag("search_c5_full", frames=T, words=int(sum(len(g["words"]) for g in got)))
