@@ -171,6 +171,29 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(torch, index):
+    """One process per GPU, like `numactl --cpunodebind` in front of a RASR job: run this rank (and first-touch its pinned
+    host buffers) on the NUMA node its GPU hangs off.  With 8 ranks streaming scores to the host at once the PCIe
+    traffic otherwise crosses the socket interconnect.  Returns the node, or None if it cannot be determined."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,6 +221,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -487,9 +512,11 @@ def main():
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=float(e2e_ms.item()), api="host-buffer C-ABI call, pinned host memory"),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof)
+        line["config"]["host_numa_node"] = numa
         if variants:
             line["variants"] = variants
         if world == 1 and not args.no_cpu_baseline and wl == "gmm":
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core, not one NUMA node
             line["cpu_baseline"] = cpu_baseline_gmm()
         print(json.dumps(line), flush=True)
     if world > 1:
