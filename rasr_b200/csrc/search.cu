@@ -715,33 +715,10 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
     cudaStream_t s      = stream ? (cudaStream_t)stream : h->stream;
     const size_t stride = (size_t)h->nStates + h->W;
-    RB_CHECK(h->dHypScore.reserve(stride * n_utt));
-    RB_CHECK(h->dHypLm.reserve(stride * n_utt));
-    RB_CHECK(h->dHypBkp.reserve(stride * n_utt));
-    RB_CHECK(h->dEndScore.reserve((size_t)h->W * n_utt));
     RB_CHECK(h->dBooks.reserve((size_t)T * 8));
     RB_CHECK(h->dNBooks.reserve((size_t)n_utt));
     RB_CHECK(h->dFrameOff.reserve((size_t)n_utt + 1));
     RB_CUDA(cudaMemcpyAsync(h->dFrameOff.p, h->frameOff.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, s));
-    SearchParams p;
-    p.wordOff    = h->dWordOff.p;
-    p.stateEmis  = h->dStateEmis.p;
-    p.stateTdp   = h->dStateTdp.p;
-    p.tdp        = h->dTdp.p;
-    p.unigram    = h->dUnigram.p;
-    p.W          = h->W;
-    p.nStates    = h->nStates;
-    p.entryModel = h->entryModel;
-    p.nModels    = h->nModels;
-    p.scores     = d_scores;
-    p.frameOff   = h->dFrameOff.p;
-    p.nEmis      = n_emissions;
-    p.hypScore   = h->dHypScore.p;
-    p.hypLm      = h->dHypLm.p;
-    p.hypBkp     = h->dHypBkp.p;
-    p.books      = reinterpret_cast<int4*>(h->dBooks.p);
-    p.nBooks     = h->dNBooks.p;
-    p.endScore   = h->dEndScore.p;
     int64_t maxT = 0;
     for (int u = 0; u < n_utt; ++u)
         maxT = std::max(maxT, h->frameOff[u + 1] - h->frameOff[u]);
@@ -775,11 +752,35 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
         k<<<n_utt, h->regThreads, smem2, s>>>(q);
     }
     else {
-    const size_t smem = (stride * 3 + (size_t)h->W * 2 + (h->W + 1) + (size_t)h->nStates * 2) * 4;
-    p.useSmem         = smem <= h->dev.smem_optin - 1024 ? 1 : 0;
-    if (p.useSmem)
-        RB_CUDA(cudaFuncSetAttribute(linear_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    linear_search_kernel<<<n_utt, kThreads, p.useSmem ? smem : 0, s>>>(p);
+        // per-word kernel: hypotheses in global memory unless they fit into shared memory
+        RB_CHECK(h->dHypScore.reserve(stride * n_utt));
+        RB_CHECK(h->dHypLm.reserve(stride * n_utt));
+        RB_CHECK(h->dHypBkp.reserve(stride * n_utt));
+        RB_CHECK(h->dEndScore.reserve((size_t)h->W * n_utt));
+        SearchParams p;
+        p.wordOff    = h->dWordOff.p;
+        p.stateEmis  = h->dStateEmis.p;
+        p.stateTdp   = h->dStateTdp.p;
+        p.tdp        = h->dTdp.p;
+        p.unigram    = h->dUnigram.p;
+        p.W          = h->W;
+        p.nStates    = h->nStates;
+        p.entryModel = h->entryModel;
+        p.nModels    = h->nModels;
+        p.scores     = d_scores;
+        p.frameOff   = h->dFrameOff.p;
+        p.nEmis      = n_emissions;
+        p.hypScore   = h->dHypScore.p;
+        p.hypLm      = h->dHypLm.p;
+        p.hypBkp     = h->dHypBkp.p;
+        p.books      = reinterpret_cast<int4*>(h->dBooks.p);
+        p.nBooks     = h->dNBooks.p;
+        p.endScore   = h->dEndScore.p;
+        const size_t smem = (stride * 3 + (size_t)h->W * 2 + (h->W + 1) + (size_t)h->nStates * 2) * 4;
+        p.useSmem         = smem <= h->dev.smem_optin - 1024 ? 1 : 0;
+        if (p.useSmem)
+            RB_CUDA(cudaFuncSetAttribute(linear_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        linear_search_kernel<<<n_utt, kThreads, p.useSmem ? smem : 0, s>>>(p);
     }
     RB_LAUNCH_CHECK();
     h->bookScore.resize(T);
