@@ -324,14 +324,11 @@ def main():
             ls.decode_dev(d_scores, 256, fo, sptr, want_result=False)
 
         h_pcm = torch.from_numpy(samples_h.astype(np.int16)).pin_memory()
-        d_pcm_f = torch.empty(samples_h.size, dtype=torch.float32, device=dev)
 
         def e2e_fn():
-            # 16-bit PCM in, word sequences out: H2D of the audio, conversion, the three stages, tracebacks to the host
-            d_pcm_f.copy_(h_pcm.to(dev, non_blocking=True))
-            torch.cuda.current_stream().synchronize()
-            pipeline.score_utterances_dev(fe, scorer, d_pcm_f, offs, d_feats, d_scores, sptr)
-            return ls.decode_dev(d_scores, 256, fo, sptr)
+            # 16-bit PCM in, word sequences out (rb_pipeline_search): slab-pipelined H2D of the audio, conversion, the
+            # three stages, tracebacks to the host
+            return pipeline.search_utterances(fe, scorer, ls, h_pcm, offs, pcm_channels=1)
 
         h2d, d2h = samples_h.size * 2, T * 20
         units = T

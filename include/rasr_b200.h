@@ -344,6 +344,11 @@ long rb_search_traceback(const rb_search* h, int utt, uint32_t* words, int32_t* 
  * total number of words, < 0 on error. */
 long rb_search_traceback_all(const rb_search* h, int64_t* word_offsets, uint32_t* words, int32_t* times,
                              float* am_scores, float* lm_scores, long capacity);
+/* config C5 in one call: audio -> MFCC -> GMM scores -> LinearSearch.  samples: interleaved 16-bit PCM with
+ * n_channels >= 1 (track selects the channel), or f32 when n_channels == 0.  The score matrix stays on the device;
+ * results are read with rb_search_traceback / rb_search_traceback_all as after rb_search_decode. */
+int rb_pipeline_search(rb_frontend* fe, rb_gmm* gmm, rb_search* ls, const void* samples, int n_channels, int track,
+                       const int64_t* offsets, int n_utt);
 
 /* =====================================================================================
  * Test hook: one bf16 tcgen05 GEMM  D[M x N] = A[M x K] * B[N x K]^T (+bias, activation),

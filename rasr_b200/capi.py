@@ -32,7 +32,7 @@ SYMBOLS = [
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_s16", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
     "rb_pipeline_nn_score", "rb_pipeline_nn_score_dev",
-    "rb_search_create", "rb_search_destroy", "rb_search_decode", "rb_search_decode_dev", "rb_search_traceback", "rb_search_traceback_all",
+    "rb_search_create", "rb_search_destroy", "rb_search_decode", "rb_search_decode_dev", "rb_search_traceback", "rb_search_traceback_all", "rb_pipeline_search",
     "rb_postproc_create", "rb_postproc_destroy", "rb_postproc_dim_out", "rb_postproc_process", "rb_postproc_process_dev",
 ]
 
@@ -165,6 +165,7 @@ def lib():
     L.rb_search_traceback.restype = C.c_long
     L.rb_search_traceback_all.argtypes = [vp, vp, vp, vp, vp, vp, C.c_long]
     L.rb_search_traceback_all.restype = C.c_long
+    L.rb_pipeline_search.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int]
     L.rb_postproc_create.argtypes = [C.POINTER(PostprocCfg), C.c_int, C.POINTER(vp)]
     L.rb_postproc_destroy.argtypes = [vp]
     L.rb_postproc_destroy.restype = None

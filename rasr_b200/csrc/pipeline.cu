@@ -44,8 +44,10 @@ extern "C" int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* 
 // (640 B of samples in, 1 KB of scores out per frame).
 namespace {
 // samples: f32 mono (channels == 0) or interleaved s16 with `channels` channels of which `track` is used
+// scores == nullptr with keepOnDevice: the scores stay in the scratch buffer (*dScoresOut) for a consumer on the device
 int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, int channels, int track,
-                        const int64_t* offsets, int n_utt, float* scores, float* feats) {
+                        const int64_t* offsets, int n_utt, float* scores, float* feats, bool keepOnDevice = false,
+                        float** dScoresOut = nullptr, std::vector<int64_t>* frameOffOut = nullptr) {
     RB_REQUIRE(fe && gmm && offsets && n_utt >= 0, "bad argument");
     if (n_utt == 0)
         return RB_OK;
@@ -59,10 +61,12 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
     const long T = rb_frontend_count_frames(fe, rel.data(), n_utt, fo.data());
     if (T <= 0)
         return T == 0 ? RB_OK : RB_ERR_INVALID;
-    RB_REQUIRE(scores != nullptr, "NULL score buffer");
+    RB_REQUIRE(scores != nullptr || keepOnDevice, "NULL score buffer");
     RB_CUDA(cudaSetDevice(rb_frontend_device(fe).ordinal));
     Scratch&     sc = scratch_for(fe);
     const int    D = rb_frontend_feat_dim(fe), M = rb_gmm_n_mixtures(gmm);
+    if (frameOffOut)
+        *frameOffOut = fo;
     cudaStream_t sK = rb_frontend_stream(fe);
     RB_CHECK(sc.samples.reserve((size_t)nS + 8));
     RB_CHECK(sc.feats.reserve((size_t)T * D));
@@ -118,8 +122,8 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
         cudaEventRecord(evK[i], sK);
         cudaStreamWaitEvent(sOut, evK[i], 0);
         if (rc == RB_OK && fB > fA) {
-            if (cudaMemcpyAsync(scores + fA * M, sc.scores.p + fA * M, (size_t)(fB - fA) * M * 4,
-                                cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
+            if (scores && cudaMemcpyAsync(scores + fA * M, sc.scores.p + fA * M, (size_t)(fB - fA) * M * 4,
+                                          cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
                 rc = RB_ERR_CUDA;
             if (feats && cudaMemcpyAsync(feats + fA * D, sc.feats.p + fA * D, (size_t)(fB - fA) * D * 4,
                                          cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
@@ -136,9 +140,27 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
         rb::set_error("pipeline failed on the device: %s", cudaGetErrorString(e));
         return RB_ERR_CUDA;
     }
+    if (dScoresOut)
+        *dScoresOut = sc.scores.p;
     return RB_OK;
 }
 }  // namespace
+
+// audio -> MFCC -> GMM scores -> LinearSearch (config C5): only the audio goes to the device and only the word
+// sequences come back (rb_search_traceback / rb_search_traceback_all afterwards); the score matrix never leaves HBM
+extern "C" int rb_pipeline_search(rb_frontend* fe, rb_gmm* gmm, rb_search* ls, const void* samples, int n_channels,
+                                  int track, const int64_t* offsets, int n_utt) {
+    RB_REQUIRE(fe && gmm && ls && offsets && n_utt >= 0, "bad argument");
+    RB_REQUIRE(n_channels >= 0 && (n_channels == 0 || (track >= 0 && track < n_channels)), "track %d of %d channels",
+               track, n_channels);
+    float*               dScores = nullptr;
+    std::vector<int64_t> fo;
+    RB_CHECK(pipeline_score_host(fe, gmm, samples, n_channels, track, offsets, n_utt, nullptr, nullptr, true, &dScores,
+                                 &fo));
+    if (fo.empty())
+        fo.assign((size_t)n_utt + 1, 0);
+    return rb_search_decode_dev(ls, dScores, rb_gmm_n_mixtures(gmm), fo.data(), n_utt, rb_frontend_stream(fe));
+}
 
 extern "C" int rb_pipeline_score(rb_frontend* fe, rb_gmm* gmm, const float* samples, const int64_t* offsets, int n_utt,
                                  float* scores, float* feats) {

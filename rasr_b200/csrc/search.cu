@@ -303,7 +303,7 @@ __device__ __forceinline__ float key_float(uint32_t k) {
 }
 
 template<int NPT>
-__global__ void __launch_bounds__(kThreads) linear_search_reg_kernel(const SearchParams2 p) {
+__global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const SearchParams2 p) {
     extern __shared__ __align__(128) unsigned char smemReg[];
     const uint32_t nThreads = blockDim.x, nWarps = nThreads / 32;
     // the carve-up is computed on the host (SmemLayout): one constant-bank operand per table address

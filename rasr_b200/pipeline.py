@@ -30,6 +30,18 @@ def score_utterances(frontend, gmm, samples, offsets, want_feats=False, out=None
     return (scores, feats, fo) if want_feats else (scores, fo)
 
 
+def search_utterances(frontend, gmm, searcher, samples, offsets, pcm_channels=0, track=0, want_result=True):
+    """Config C5 in one call: host audio in (f32, or interleaved 16-bit PCM with pcm_channels > 0), one traceback dict
+    per segment out; features and scores never leave the device."""
+    if isinstance(samples, np.ndarray) or not hasattr(samples, "data_ptr"):
+        samples = np.ascontiguousarray(samples, np.int16 if pcm_channels else np.float32)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    capi.check(capi.lib().rb_pipeline_search(frontend.handle, gmm.handle, searcher.handle, capi.ptr(samples),
+                                             int(pcm_channels), int(track), capi.ptr(offsets), offsets.size - 1))
+    searcher._fo = frontend.count_frames(offsets)
+    return searcher._result() if want_result else None
+
+
 def score_utterances_dev(frontend, gmm, d_samples, offsets, d_feats, d_scores, stream=None):
     offsets = np.ascontiguousarray(offsets, np.int64)
     capi.check(capi.lib().rb_pipeline_score_dev(frontend.handle, gmm.handle, capi.ptr(d_samples), capi.ptr(offsets),

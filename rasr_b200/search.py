@@ -34,6 +34,10 @@ class LinearSearch:
 
     __del__ = close
 
+    @property
+    def handle(self):
+        return self._h
+
     def _result(self):
         n_utt = self._fo.size - 1
         cap = max(1, int(self._fo[-1] - self._fo[0]))

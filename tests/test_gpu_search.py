@@ -114,10 +114,14 @@ def test_c5_shard_at_full_size(oracle, diag):
     d_feats = torch.empty((T, 39), dtype=torch.float32, device="cuda")
     d_scores = torch.empty((T, 256), dtype=torch.float32, device="cuda")
     pipeline.score_utterances_dev(fe, gmm, d_samples, offs, d_feats, d_scores)
+    torch.cuda.synchronize()  # the scorer ran on the front-end's stream, the search runs on its own
     got = ls.decode_dev(d_scores, 256, fo)
     assert len(got) == 125 and all(len(g["words"]) > 0 for g in got)
     for u in (0, 63, 124):
         rows = d_scores[int(fo[u]):int(fo[u + 1])].cpu().numpy()
         assert same(got[u], oracle.linear_search(lex, rows)), u
         assert same(got[u], ls.decode(rows)[0]), u
+    # the one-call host entry point (16-bit PCM in, word sequences out) gives the same sequences
+    one = pipeline.search_utterances(fe, gmm, ls, samples.astype(np.int16), offs, pcm_channels=1)
+    assert len(one) == 125 and all(same(a, b) for a, b in zip(one, got))
     diag("search_c5_full", frames=T, words=int(sum(len(g["words"]) for g in got)))
