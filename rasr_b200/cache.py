@@ -1,4 +1,5 @@
-"""Feature caches of the reference: Core::FileArchive containers holding Flow data streams.
+"""Feature caches of the reference: Core::Archive containers (file, directory and bundle archives)
+holding Flow data streams.
 
 File archive (src/Core/FileArchive.cc:26-80 layout comment, code :166-560; all integers little endian,
 src/Core/BinaryStream.hh:65; strings are u32 length + bytes, src/Core/BinaryStream.cc:174-179):
@@ -238,6 +239,152 @@ class FileArchive:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class DirectoryArchive:
+    """src/Core/DirectoryArchive.cc: every entry is a plain file below the archive directory; a compressed entry is a
+    gzip file, recognised by its magic bytes, whose original size is its last four bytes (probe, :49-72).  The
+    reference does not scan the directory (:39-47): names() walks it here for convenience."""
+
+    def __init__(self, path, mode="r"):
+        self.path, self.mode = str(path), mode
+        if not os.path.isdir(self.path):
+            if mode != "w":
+                raise ArchiveError('Directory "%s" does not exist' % self.path)
+            os.makedirs(self.path, exist_ok=True)
+
+    def _file(self, name):
+        return os.path.join(self.path, name)
+
+    def names(self):
+        out = []
+        for root, _, files in os.walk(self.path):
+            out += [os.path.relpath(os.path.join(root, f), self.path) for f in files]
+        return sorted(out)
+
+    def __contains__(self, name):
+        return bool(name) and os.path.isfile(self._file(name))
+
+    def read(self, name):
+        if name not in self:
+            raise KeyError(name)
+        with open(self._file(name), "rb") as f:
+            data = f.read()
+        if data[:2] == b"\x1f\x8b" and len(data) >= 18:
+            return _gunzip_member(data, struct.unpack("<I", data[-4:])[0])
+        return data
+
+    def write(self, name, data, compress=False):
+        if self.mode != "w":
+            raise ArchiveError("archive is opened read-only")
+        if not name:
+            raise ArchiveError("empty entry name")
+        os.makedirs(os.path.dirname(self._file(name)) or self.path, exist_ok=True)
+        with open(self._file(name), "wb") as f:
+            f.write(_gzip_member(data) if compress else data)
+
+    def close(self):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class BundleArchive:
+    """src/Core/BundleArchive.cc: a text file (suffix .bundle) listing archives, one path per whitespace-separated
+    token; read-only.  The entry -> archive map is built from the members' file lists (createIndex, :125-137; a later
+    archive wins for a duplicate name) and cached next to the bundle as <bundle>.idx.gz in the reference's format
+    (writeIndex / readIndex, :139-172): number of archives, their paths, number of entries, "name index" lines."""
+
+    def __init__(self, path, write_index=True):
+        import gzip
+        self.path = str(path)
+        try:
+            with open(self.path) as f:
+                self.archives = f.read().split()
+        except OSError:
+            raise ArchiveError("cannot read bundle archive '%s'" % self.path)
+        self._open = {}
+        self.map = {}
+        idx = self.path + ".idx.gz"
+        if not self._read_index(idx):
+            self.map = {}
+            for i, a in enumerate(self.archives):
+                with open_archive(a) as ar:
+                    for n in ar.names():
+                        self.map[n] = i
+            if write_index:
+                try:
+                    with gzip.open(idx, "wt") as f:
+                        f.write("%d\n" % len(self.archives) + "".join(a + "\n" for a in self.archives))
+                        f.write("%d\n" % len(self.map) + "".join("%s %d\n" % kv for kv in self.map.items()))
+                except OSError:
+                    pass
+
+    def _read_index(self, idx):
+        import gzip
+        try:
+            with gzip.open(idx, "rt") as f:
+                toks = f.read().split()
+        except (OSError, EOFError):
+            return False
+        try:
+            n = int(toks[0])
+            if n != len(self.archives) or toks[1:1 + n] != self.archives:
+                return False
+            m = int(toks[1 + n])
+            rest = toks[2 + n:2 + n + 2 * m]
+            self.map = dict((rest[2 * i], int(rest[2 * i + 1])) for i in range(m))
+            return len(self.map) == m or m == len(rest) // 2
+        except (ValueError, IndexError):
+            return False
+
+    def names(self):
+        return list(self.map)
+
+    def __contains__(self, name):
+        return name in self.map
+
+    def read(self, name):
+        if name not in self.map:
+            raise KeyError(name)
+        i = self.map[name]
+        if i not in self._open:
+            self._open[i] = open_archive(self.archives[i])
+        return self._open[i].read(name)
+
+    def write(self, *a, **k):
+        raise ArchiveError("bundle archives are read-only")
+
+    def close(self):
+        for a in self._open.values():
+            a.close()
+        self._open = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def open_archive(path, mode="r", **kw):
+    """Archive::create / Archive::test (src/Core/Archive.cc:287-329): *.bundle -> bundle; an existing directory, or a
+    missing path ending in '/' -> directory archive; an existing file with the archive header, or a missing path ->
+    file archive."""
+    path = str(path)
+    if path.endswith(".bundle"):
+        return BundleArchive(path)
+    if os.path.isdir(path) or (not os.path.exists(path) and path.endswith("/")):
+        return DirectoryArchive(path, mode)
+    if os.path.isfile(path) and os.path.getsize(path) > 0:
+        with open(path, "rb") as f:
+            if f.read(8) != HEADER:
+                raise ArchiveError("unknown type of archive (requested path: '%s')." % path)
+    return FileArchive(path, mode, **kw)
 
 
 # ---- Flow cache ------------------------------------------------------------------------------------------------------

@@ -223,3 +223,39 @@ def test_overwrite_leaves_a_hole_that_readers_skip(tmp_path):
     (tmp_path / "junk").write_bytes(b"not an archive")
     with pytest.raises(cache.ArchiveError):
         cache.FileArchive(tmp_path / "junk")
+
+
+def test_directory_and_bundle_archives(tmp_path):
+    """the other two archive kinds (src/Core/DirectoryArchive.cc, BundleArchive.cc) and the type detection of
+    Archive::create: a feature cache split over a file archive and a directory archive, read through a bundle"""
+    import gzip as gz
+    from rasr_b200 import cache
+    rng = np.random.default_rng(3)
+    data = {}
+    with cache.open_archive(tmp_path / "part1.cache", "w") as a:
+        assert isinstance(a, cache.FileArchive)
+        for s in ("c/r/a", "c/r/b"):
+            data[s] = rng.standard_normal((9, 5)).astype(np.float32)
+            cache.write_features(a, s, data[s], np.zeros((9, 2)), {"sample-rate": "100"})
+    with cache.open_archive(str(tmp_path / "part2") + "/", "w") as a:
+        assert isinstance(a, cache.DirectoryArchive)
+        for s, comp in (("c/r/c", False), ("c/q/d", True)):
+            data[s] = rng.standard_normal((4, 5)).astype(np.float32)
+            cache.write_features(a, s, data[s], np.ones((4, 2)), compress=comp)
+    assert (tmp_path / "part2" / "c" / "r" / "c").is_file()          # entries are plain files ...
+    raw = (tmp_path / "part2" / "c" / "q" / "d").read_bytes()
+    assert raw[:2] == b"\x1f\x8b" and len(gz.decompress(raw)) == int.from_bytes(raw[-4:], "little")  # ... or gzip files
+    (tmp_path / "all.bundle").write_text("%s\n%s\n" % (tmp_path / "part1.cache", tmp_path / "part2"))
+    for _ in range(2):  # second pass goes through the cached index
+        with cache.open_archive(tmp_path / "all.bundle") as b:
+            assert isinstance(b, cache.BundleArchive) and set(data) <= set(b.names())
+            for s, f in data.items():
+                got, _, _ = cache.read_features(b, s)
+                assert np.array_equal(got, f)
+            with pytest.raises(cache.ArchiveError):
+                b.write("x", b"y")
+    idx = gz.open(str(tmp_path / "all.bundle") + ".idx.gz", "rt").read().split()
+    assert idx[0] == "2" and idx[1] == str(tmp_path / "part1.cache") and "c/q/d" in idx
+    (tmp_path / "junk.bin").write_bytes(b"something else")
+    with pytest.raises(cache.ArchiveError):
+        cache.open_archive(tmp_path / "junk.bin")
