@@ -43,6 +43,8 @@ def search_utterances(frontend, gmm, searcher, samples, offsets, pcm_channels=0,
 
 
 def score_utterances_dev(frontend, gmm, d_samples, offsets, d_feats, d_scores, stream=None):
+    """Device buffers; only enqueues.  stream=None means the FRONT-END handle's own stream (every handle owns one
+    non-blocking stream): pass one stream to all `*_dev` calls that feed each other, or synchronise between them."""
     offsets = np.ascontiguousarray(offsets, np.int64)
     capi.check(capi.lib().rb_pipeline_score_dev(frontend.handle, gmm.handle, capi.ptr(d_samples), capi.ptr(offsets),
                                                 offsets.size - 1, capi.ptr(d_feats), capi.ptr(d_scores),

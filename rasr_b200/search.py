@@ -71,6 +71,8 @@ class LinearSearch:
         return self._result()
 
     def decode_dev(self, d_scores, n_emissions, frame_offsets, stream=None, want_result=True):
+        """Score matrix on the device.  stream=None is this handle's own stream: the producer of `d_scores` must have
+        finished (or run on the stream passed here)."""
         self._fo = np.ascontiguousarray(frame_offsets, np.int64)
         capi.check(capi.lib().rb_search_decode_dev(self._h, capi.ptr(d_scores), int(n_emissions), capi.ptr(self._fo),
                                                    self._fo.size - 1, capi.ptr(stream)))
