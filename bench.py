@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "gmm-int", "frontend", "pipeline", "pipeline-nn", "pipeline-search", "nn"])
+    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "gmm-int", "gmm-presel", "frontend", "pipeline", "pipeline-nn", "pipeline-search", "nn"])
     ap.add_argument("--frames", type=int, default=0, help="override the frame count of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -238,11 +238,11 @@ def main():
 
     # ---------------- workload set-up: every rank owns its own shard (weak scaling, no collective)
     e2e_fn = None
-    if wl in ("gmm", "gmm-diag", "gmm-tensor", "gmm-int"):
+    if wl in ("gmm", "gmm-diag", "gmm-tensor", "gmm-int", "gmm-presel"):
         T = args.frames or C2["frames"]
         msd = synth.mixture_set()
         mode = {"gmm": "batch-float", "gmm-diag": "diagonal-maximum", "gmm-tensor": "batch-tensor",
-                "gmm-int": "batch-int"}[wl]
+                "gmm-int": "batch-int", "gmm-presel": "preselection-batch-float"}[wl]
         scorer = mm.GmmScorer(mm.MixtureSet.from_dict(msd), mode, device=local_rank)
         feats_h = synth.features(T, 39, seed=2024 + rank)
         d_in = [torch.from_numpy(feats_h).to(dev) for _ in range(R)]

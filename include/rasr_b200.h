@@ -203,7 +203,14 @@ typedef enum {
     /* Mm::BatchIntFeatureScorer / BatchUnrolledIntFeatureScorer ("batch-diagonal-maximum-int" / "-fast",
      * src/Mm/BatchFeatureScorer.cc:321-510, 581-650): means and features quantised to u8, s32 distances;
      * integer arithmetic on the tensor cores (IMMA), bit-identical scores */
-    RB_GMM_BATCH_INT = 4
+    RB_GMM_BATCH_INT = 4,
+    /* Mm::BatchPreselectionFloatFeatureScorer ("preselection-batch-float", src/Mm/BatchFeatureScorer.cc:257-315) with
+     * Mm::DensityClustering<f32, f32> (src/Mm/DensityClustering.{hh,cc,tcc}): the density means are clustered once
+     * (k-means, the reference's pseudo-random initialisation), per frame only the densities of the clusters nearest
+     * to the feature are scored, mixtures left without one get the back-off score.  Reproduces the reference's
+     * approximation (same clustering, same per-frame cluster choice, same scores); defaults as in
+     * DensityClustering.cc:20-34: 256 clusters, 32 selected, 5 iterations, back-off 40000. */
+    RB_GMM_BATCH_PRESELECT = 5
 } rb_gmm_mode;
 
 /* contraction: 1 = fused multiply-add where the reference's default build (gcc -O2 -march=native,
@@ -211,6 +218,11 @@ typedef enum {
 int  rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_weight_scale, float gaussian_scale,
                    int contraction, int device, rb_gmm** out);
 void rb_gmm_destroy(rb_gmm* h);
+/* RB_GMM_BATCH_PRESELECT only: rebuild the clustering with other parameters (density-clustering.clusters,
+ * .select-clusters, .iterations, .backoff-score) / read it back: cluster_of_density [n_densities] in mixture order,
+ * cluster_means [n_clusters * padded dimension] (padded = dim rounded up to 8); any pointer may be NULL */
+int  rb_gmm_configure_preselection(rb_gmm* h, int clusters, int select, int iterations, float backoff_score);
+int  rb_gmm_get_clustering(const rb_gmm* h, uint32_t* cluster_of_density, float* cluster_means, int* n_clusters);
 int  rb_gmm_n_mixtures(const rb_gmm* h);
 int  rb_gmm_dim(const rb_gmm* h);
 /* dense scoring of T frames against ALL mixtures: scores [T*n_mixtures] row-major,
@@ -354,6 +366,8 @@ int rb_pipeline_search(rb_frontend* fe, rb_gmm* gmm, rb_search* ls, const void* 
  * Test hook: one bf16 tcgen05 GEMM  D[M x N] = A[M x K] * B[N x K]^T (+bias, activation),
  * A/B f32 on the host, rounded to bf16 on the device.  Used by tests/ only.
  * ===================================================================================== */
+/* host-only test hook: the first n values of glibc's rand() after srand(seed), as restated for the clustering */
+void rb_test_glibc_rand(unsigned seed, int n, int* out);
 int rb_test_gemm_bf16(const float* a, const float* b, const float* bias, int M, int N, int K, int act,
                       float* d, int device);
 /* times `iters` launches of one GEMM variant (0: 128x256 tile, 1: 256x256 tile) on device-resident

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <set>
 #include <vector>
 
 namespace {
@@ -135,6 +136,115 @@ struct BatchFloat {
             }
         }
         free(x);
+    }
+
+    /* one density against one (scaled, padded) feature: the arithmetic of fillScoreCacheTpl :225-243 */
+    template<bool Fuse>
+    float densityScore(unsigned dns, const float* x) const {
+        const float* mean = means + (size_t)dns * padded;
+        __m128       s1   = _mm_load_ss(consts + dns);
+        __m128       s2   = _mm_setzero_ps();
+        for (unsigned d = 0; d < padded; d += 8) {
+            __m128 x1 = _mm_sub_ps(_mm_load_ps(mean + d), _mm_load_ps(x + d));
+            __m128 x2 = _mm_sub_ps(_mm_load_ps(mean + d + 4), _mm_load_ps(x + d + 4));
+            if (Fuse) {
+                s1 = _mm_fmadd_ps(x1, x1, s1);
+                s2 = _mm_fmadd_ps(x2, x2, s2);
+            }
+            else {
+                s1 = _mm_add_ps(s1, _mm_mul_ps(x1, x1));
+                s2 = _mm_add_ps(s2, _mm_mul_ps(x2, x2));
+            }
+        }
+        s1 = _mm_add_ps(s1, s2);
+        s2 = s1;
+        s1 = _mm_shuffle_ps(s1, s2, _MM_SHUFFLE(1, 0, 3, 2));
+        s1 = _mm_add_ps(s1, s2);
+        s2 = s1;
+        s1 = _mm_shuffle_ps(s1, s2, _MM_SHUFFLE(2, 3, 0, 1));
+        s1 = _mm_add_ps(s1, s2);
+        float r;
+        _mm_store_ss(&r, s1);
+        return r;
+    }
+};
+
+/* ------------------------------------------------------------------ Mm::DensityClustering<f32, f32>
+ * src/Mm/DensityClustering.{hh,cc,tcc}: k-means over the (scaled, padded) density means -- initializeClusters
+ * .tcc:62-75 (srand(1), rand() % nDensities, distinct densities), assignDensities :82-100, updateClusterMeans
+ * :103-123 (f64 sums), build :126-161; selectClusters :164-189 (std::sort by distance, the first `select`
+ * clusters are active); distances by Mm::unrolledVectorDistance src/Mm/Utilities.hh:254-296 (sequential
+ * score += df * df).  Parameters DensityClustering.cc:20-34: clusters 256, select-clusters 32, iterations 5,
+ * backoff-score 40000. */
+struct DensityClusteringF {
+    unsigned              nClusters, nSelected, dim, nDens;
+    bool                  fuse;
+    std::vector<float>    clusterMeans;
+    std::vector<unsigned> clusterOf;
+
+    float distance(const float* a, const float* b) const {
+        float score = 0;
+        for (unsigned d = 0; d < dim; ++d) {
+            float df = a[d] - b[d];
+            score    = fuse ? std::fmaf(df, df, score) : (score + df * df);
+        }
+        return score;
+    }
+    void build(const float* densities, unsigned dimension, unsigned nDensities, unsigned clusters, unsigned select,
+               unsigned iterations, bool useFma) {
+        dim       = dimension;
+        nDens     = nDensities;
+        nClusters = std::min(clusters, nDensities); /* DensityClusteringBase::init, .cc:52-56 */
+        nSelected = select;
+        fuse      = useFma;
+        clusterMeans.assign((size_t)nClusters * dim, 0.0f);
+        clusterOf.assign(nDens, 0);
+        std::set<unsigned> used;
+        srand(1);
+        for (unsigned c = 0; c < nClusters; ++c) {
+            unsigned pick = 0;
+            do {
+                pick = rand() % nDens;
+            } while (used.count(pick));
+            used.insert(pick);
+            std::copy(densities + (size_t)pick * dim, densities + (size_t)(pick + 1) * dim, clusterMeans.begin() + (size_t)c * dim);
+        }
+        for (unsigned it = 0; it < iterations; ++it) {
+            std::vector<std::vector<unsigned>> assigned(nClusters);
+            for (unsigned dns = 0; dns < nDens; ++dns) {
+                float    best = FLT_MAX;
+                unsigned bc   = 0;
+                for (unsigned c = 0; c < nClusters; ++c) {
+                    float dist = distance(&clusterMeans[(size_t)c * dim], densities + (size_t)dns * dim);
+                    if (dist < best) {
+                        best = dist;
+                        bc   = c;
+                    }
+                }
+                clusterOf[dns] = bc;
+                assigned[bc].push_back(dns);
+            }
+            for (unsigned c = 0; c < nClusters; ++c) {
+                if (assigned[c].empty())
+                    continue;
+                std::vector<double> sums(dim, 0.0);
+                for (unsigned a : assigned[c])
+                    for (unsigned d = 0; d < dim; ++d)
+                        sums[d] += densities[(size_t)a * dim + d];
+                for (unsigned d = 0; d < dim; ++d)
+                    clusterMeans[(size_t)c * dim + d] = sums[d] / (double)assigned[c].size();
+            }
+        }
+    }
+    void select(std::vector<char>& active, const float* feature) const {
+        std::vector<std::pair<float, unsigned>> byDistance(nClusters);
+        for (unsigned c = 0; c < nClusters; ++c)
+            byDistance[c] = std::make_pair(distance(feature, &clusterMeans[(size_t)c * dim]), c);
+        std::sort(byDistance.begin(), byDistance.end(),
+                  [](const std::pair<float, unsigned>& a, const std::pair<float, unsigned>& b) { return a.first < b.first; });
+        active.assign(nClusters, 0);
+        for (unsigned i = 0; i < nSelected && i < nClusters; ++i)
+            active[byDistance[i].second] = 1;
     }
 };
 
@@ -425,6 +535,53 @@ extern "C" int orc_gmm_batch_float(const orc_mixture_set* ms, const float* feats
         s.scoreFrames<true>(feats, 0, T, scores);
     else
         s.scoreFrames<false>(feats, 0, T, scores);
+    return 0;
+}
+
+/* Mm::BatchPreselectionFloatFeatureScorer src/Mm/BatchFeatureScorer.cc:257-315 ("preselection-batch-float"): only
+ * densities of the `select` clusters closest to the feature are scored; a mixture without one gets the back-off
+ * score.  cluster_of [n_densities] / cluster_means [n_clusters * padded] are optional outputs. */
+extern "C" int orc_gmm_preselect_float(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma,
+                                       int clusters, int select, int iterations, float backoff, uint32_t* cluster_of,
+                                       float* cluster_means, int* n_clusters) {
+    BatchFloat s;
+    int        rc = s.init(*ms);
+    if (rc)
+        return rc;
+    DensityClusteringF dc;
+    dc.build(s.means, s.padded, s.nDens, (unsigned)clusters, (unsigned)select, (unsigned)iterations, use_fma != 0);
+    if ((unsigned)select > dc.nClusters)
+        return -4; /* verify(nSelected_ <= nClusters_) */
+    if (cluster_of)
+        std::copy(dc.clusterOf.begin(), dc.clusterOf.end(), cluster_of);
+    if (cluster_means)
+        std::copy(dc.clusterMeans.begin(), dc.clusterMeans.end(), cluster_means);
+    if (n_clusters)
+        *n_clusters = (int)dc.nClusters;
+    float*            x = alignedFloats(s.padded);
+    std::vector<char> active;
+    for (long t = 0; t < T; ++t) {
+        std::memset(x, 0, sizeof(float) * s.padded);
+        for (unsigned d = 0; d < s.dim; ++d)
+            x[d] = feats[(size_t)t * s.dim + d] * s.isd[d];
+        dc.select(active, x);
+        for (unsigned m = 0; m < s.nMix; ++m) {
+            float best = FLT_MAX;
+            for (unsigned dns = s.offsets[m]; dns < s.offsets[m + 1]; ++dns) {
+                if (!active[dc.clusterOf[dns]])
+                    continue;
+                const float sc = use_fma ? s.densityScore<true>(dns, x) : s.densityScore<false>(dns, x);
+                if (sc < best) /* min_ps(best, sc) */
+                    best = sc;
+            }
+            if (best < FLT_MAX)
+                best *= 0.5;
+            if (best == FLT_MAX)
+                best = backoff;
+            scores[(size_t)t * s.nMix + m] = best;
+        }
+    }
+    free(x);
     return 0;
 }
 

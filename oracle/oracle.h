@@ -117,6 +117,12 @@ int orc_gmm_diag_sum(const orc_mixture_set* ms, float mixture_weight_scale, floa
 int orc_gmm_batch_int(const orc_mixture_set* ms, const float* feats, long T, float* scores, int n_threads);
 int orc_gmm_batch_int_model(const orc_mixture_set* ms, uint8_t* means, int32_t* consts, float* variance, float* scale,
                             int* padded);
+/* Mm::BatchPreselectionFloatFeatureScorer ("preselection-batch-float", src/Mm/BatchFeatureScorer.cc:257-315 with
+ * Mm::DensityClustering<f32, f32>): k-means clusters of the density means, only the densities of the `select`
+ * clusters nearest to the frame are scored, mixtures left without one get `backoff`. */
+int orc_gmm_preselect_float(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma,
+                            int clusters, int select, int iterations, float backoff, uint32_t* cluster_of,
+                            float* cluster_means, int* n_clusters);
 int orc_gmm_batch_float_mt(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma,
                            int n_threads);
 

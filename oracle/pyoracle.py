@@ -219,6 +219,24 @@ def gmm_batch_float(ms, feats, use_fma=True, threads=1):
     return scores
 
 
+def gmm_preselect_float(ms, feats, use_fma=True, clusters=256, select=32, iterations=5, backoff=40000.0):
+    """(scores, cluster index of every density, cluster means [n_clusters, padded])"""
+    feats = np.ascontiguousarray(feats, np.float32)
+    T = feats.shape[0]
+    scores = np.zeros((T, ms.n_mixtures), np.float32)
+    n_dens = int(ms.c.mix_offsets[ms.n_mixtures])
+    padded = (ms.dim + 7) // 8 * 8
+    cluster_of = np.zeros(n_dens, np.uint32)
+    means = np.zeros((clusters, padded), np.float32)
+    n = C.c_int(0)
+    rc = lib().orc_gmm_preselect_float(C.byref(ms.c), _p(feats, C.c_float), C.c_long(T), _p(scores, C.c_float),
+                                       int(use_fma), int(clusters), int(select), int(iterations), C.c_float(backoff),
+                                       _p(cluster_of, C.c_uint32), _p(means, C.c_float), C.byref(n))
+    if rc:
+        raise RuntimeError("orc_gmm_preselect_float failed: %d" % rc)
+    return scores, cluster_of, means[:n.value]
+
+
 def gmm_batch_int(ms, feats, threads=1):
     """Mm::BatchIntFeatureScorer ("batch-diagonal-maximum-int"): dense scores [T x nMix]."""
     feats = np.ascontiguousarray(feats, np.float32)

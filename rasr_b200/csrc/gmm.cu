@@ -520,6 +520,14 @@ int  rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cuda
 void rb_gmm_int_destroy(rb_gmm_int* h);
 int  rb_gmm_int_score(rb_gmm_int* h, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
 
+struct rb_gmm_presel;  // gmm_presel.cu
+int  rb_gmm_presel_create(const rb_mixture_set* ms, bool fuse, const rb::DeviceInfo& dev, cudaStream_t stream,
+                          rb_gmm_presel** out);
+void rb_gmm_presel_destroy(rb_gmm_presel* h);
+int  rb_gmm_presel_score(rb_gmm_presel* h, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
+int  rb_gmm_presel_configure(rb_gmm_presel* h, int clusters, int select, int iterations, float backoff, cudaStream_t s);
+void rb_gmm_presel_clustering(const rb_gmm_presel* h, uint32_t* cluster_of, float* cluster_means, int* n_clusters);
+
 struct rb_gmm_tensor;  // gmm_tensor.cu
 int  rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream,
                           rb_gmm_tensor** out);
@@ -561,12 +569,15 @@ struct rb_gmm {
     rb::PinnedBuf<float> hStage;
     rb_gmm_tensor*       tensor = nullptr;
     rb_gmm_int*          quantised = nullptr;
+    rb_gmm_presel*       presel    = nullptr;
 
     ~rb_gmm() {
         if (tensor)
             rb_gmm_tensor_destroy(tensor);
         if (quantised)
             rb_gmm_int_destroy(quantised);
+        if (presel)
+            rb_gmm_presel_destroy(presel);
         for (cudaEvent_t e : events)
             cudaEventDestroy(e);
         if (sIn)
@@ -812,7 +823,7 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
     RB_REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
     RB_CHECK(validate(ms));
-    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_BATCH_INT, "unknown gmm mode %d", mode);
+    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_BATCH_PRESELECT, "unknown gmm mode %d", mode);
     rb_gmm* h = new (std::nothrow) rb_gmm();
     if (!h) {
         rb::set_error("out of host memory");
@@ -838,6 +849,13 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
     std::vector<float> rows, isd;
     if (mode == RB_GMM_BATCH_INT) {
         rc = rb_gmm_int_create(ms, h->dev, h->stream, &h->quantised);
+        if (rc != RB_OK)
+            return fail(rc);
+        *out = h;
+        return RB_OK;
+    }
+    if (mode == RB_GMM_BATCH_PRESELECT) {
+        rc = rb_gmm_presel_create(ms, h->fuse, h->dev, h->stream, &h->presel);
         if (rc != RB_OK)
             return fail(rc);
         *out = h;
@@ -970,6 +988,10 @@ extern "C" int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* 
         RB_REQUIRE(d_best == nullptr, "Mm::BatchIntFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
         return rb_gmm_int_score(h->quantised, d_feats, T, d_scores, s);
     }
+    if (h->mode == RB_GMM_BATCH_PRESELECT) {
+        RB_REQUIRE(d_best == nullptr, "the preselection scorer does not report densities; use RB_GMM_DIAG_MAX");
+        return rb_gmm_presel_score(h->presel, d_feats, T, d_scores, s);
+    }
     if (h->mode == RB_GMM_BATCH_FLOAT)
         RB_REQUIRE(d_best == nullptr, "Mm::BatchFloatFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
     return launch_simt(h, d_feats, T, d_scores, d_best, s);
@@ -983,7 +1005,8 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     if (T == 0)
         return RB_OK;
     RB_REQUIRE(feats && scores, "NULL host buffer");
-    if (h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_BATCH_TENSOR || h->mode == RB_GMM_BATCH_INT)
+    if (h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_BATCH_TENSOR || h->mode == RB_GMM_BATCH_INT ||
+        h->mode == RB_GMM_BATCH_PRESELECT)
         RB_REQUIRE(best_density == nullptr, "this scorer mode does not report densities; use RB_GMM_DIAG_MAX");
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
     const size_t D = h->dim, M = h->nMix;
@@ -1044,5 +1067,18 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
         rb::set_error("gmm scoring failed on the device: %s", cudaGetErrorString(e));
         return RB_ERR_CUDA;
     }
+    return RB_OK;
+}
+
+// density preselection (RB_GMM_BATCH_PRESELECT): re-cluster with other parameters / read the clustering back
+extern "C" int rb_gmm_configure_preselection(rb_gmm* h, int clusters, int select, int iterations, float backoff_score) {
+    RB_REQUIRE(h && h->presel, "not a preselection scorer");
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    return rb_gmm_presel_configure(h->presel, clusters, select, iterations, backoff_score, h->stream);
+}
+
+extern "C" int rb_gmm_get_clustering(const rb_gmm* h, uint32_t* cluster_of_density, float* cluster_means, int* n_clusters) {
+    RB_REQUIRE(h && h->presel, "not a preselection scorer");
+    rb_gmm_presel_clustering(h->presel, cluster_of_density, cluster_means, n_clusters);
     return RB_OK;
 }

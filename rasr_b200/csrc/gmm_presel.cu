@@ -1,0 +1,388 @@
+// gmm_presel.cu -- Mm::BatchPreselectionFloatFeatureScorer ("preselection-batch-float",
+// src/Mm/BatchFeatureScorer.cc:257-315) with Mm::DensityClustering<f32, f32> (src/Mm/DensityClustering.{hh,cc,tcc}).
+//
+// The reference's CPU trick: cluster the density means once (k-means, 256 clusters), and per frame score only the
+// densities of the 32 clusters nearest to the feature vector; a mixture left without a scored density gets the
+// back-off score.  A GPU does not need the saving -- dense scoring is the fast path -- but a system tuned with this
+// scorer expects ITS scores, so the approximation is reproduced: same clustering (same pseudo-random initialisation,
+// same f32 distances and f64 centroid sums), same per-frame cluster choice, same per-density arithmetic and minimum.
+//
+//   host (create)           k-means on the scaled, padded means: restatement of initializeClusters / assignDensities /
+//                           updateClusterMeans; rand() is restated too (glibc's additive-feedback generator) so that
+//                           creating a scorer does not disturb the host program's random state
+//   presel_select_kernel    one warp per frame: f32 distances to all clusters (sequential sum over the padded
+//                           dimension like unrolledVectorDistance), then the `select` smallest by a radix select on the
+//                           distance bits -> one bit per cluster.  The reference sorts (distance, cluster) pairs by
+//                           distance only (std::sort, not stable): for exactly equal distances at the selection
+//                           boundary its choice is unspecified; here the lower cluster index wins.
+//   presel_score_kernel     one thread per (frame, mixture): the lane arithmetic of fillScoreCacheTpl (two 4-lane
+//                           accumulators over 8-dimension blocks, the constant first in lane 0, horizontal add) for the
+//                           densities whose cluster bit is set, minimum, x0.5, back-off.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <set>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+// glibc's rand() after srand(seed) (TYPE_3 additive feedback generator, r[i] = r[i-3] + r[i-31], output >> 1)
+struct GlibcRand {
+    std::vector<uint32_t> r;
+    size_t                k;
+    explicit GlibcRand(uint32_t seed) : r(34), k(0) {
+        r[0] = seed ? seed : 1;
+        for (int i = 1; i < 31; ++i) {
+            const int64_t hi = (int32_t)r[i - 1] / 127773, lo = (int32_t)r[i - 1] % 127773;
+            int64_t       w  = 16807 * lo - 2836 * hi;
+            if (w < 0)
+                w += 2147483647;
+            r[i] = (uint32_t)w;
+        }
+        for (int i = 31; i < 34; ++i)
+            r[i] = r[i - 31];
+        for (int i = 34; i < 344; ++i)
+            r.push_back(r[i - 31] + r[i - 3]);
+    }
+    int next() {
+        const size_t i = r.size();
+        r.push_back(r[i - 31] + r[i - 3]);
+        return (int)(r.back() >> 1);
+    }
+};
+
+struct PreselParams {
+    const float*   feats;      // [T * dim]
+    const float*   isd;        // [padded]
+    const float*   means;      // [nDens * padded] scaled means
+    const float*   consts;     // [nDens]
+    const uint32_t* offsets;   // [nMix + 1]
+    const uint8_t* clusterOf;  // [nDens]
+    const float*   clusterMeans;  // [nClusters * padded]
+    uint32_t*      active;     // [T * 8] one bit per cluster
+    float*         scores;     // [T * nMix]
+    long           T;
+    int            dim, padded, nMix, nClusters, nSelected, fuse;
+    float          backoff;
+};
+
+__device__ __forceinline__ float sq_acc(float df, float acc, bool fuse) {
+    return fuse ? __fmaf_rn(df, df, acc) : __fadd_rn(acc, __fmul_rn(df, df));
+}
+
+constexpr int kSelWarps = 8;
+
+// dynamic smem: cluster means [nClusters][padded + 1] | per warp: x [padded]
+__global__ void __launch_bounds__(kSelWarps * 32) presel_select_kernel(const PreselParams p) {
+    extern __shared__ float smem[];
+    const int stride = p.padded + 1;  // odd stride: lanes reading different clusters hit different banks
+    float*    cm     = smem;
+    float*    xs     = smem + (size_t)p.nClusters * stride + (threadIdx.x >> 5) * p.padded;
+    for (int i = threadIdx.x; i < p.nClusters * p.padded; i += blockDim.x)
+        cm[(i / p.padded) * stride + i % p.padded] = p.clusterMeans[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (long t = (long)blockIdx.x * kSelWarps + (threadIdx.x >> 5); t < p.T; t += (long)gridDim.x * kSelWarps) {
+        for (int d = lane; d < p.padded; d += 32)
+            xs[d] = d < p.dim ? __fmul_rn(p.feats[t * p.dim + d], p.isd[d]) : 0.0f;
+        __syncwarp();
+        // distances: cluster c = lane + 32 k
+        uint32_t key[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + 32 * k;
+            key[k]      = 0xffffffffu;
+            if (c < p.nClusters) {
+                float        score = 0.0f;
+                const float* m     = cm + c * stride;
+                for (int d = 0; d < p.padded; ++d)
+                    score = sq_acc(__fsub_rn(xs[d], m[d]), score, p.fuse);
+                key[k] = __float_as_uint(score);  // distances are >= 0: their bit patterns order like the values
+            }
+        }
+        // radix select of the nSelected-th smallest key
+        uint32_t prefix = 0, mask = 0;
+        int      remaining = p.nSelected;
+        for (int bit = 31; bit >= 0; --bit) {
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                cnt += ((key[k] & mask) == prefix && !((key[k] >> bit) & 1u) && lane + 32 * k < p.nClusters) ? 1 : 0;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (remaining > cnt) {
+                remaining -= cnt;
+                prefix |= 1u << bit;
+            }
+            mask |= 1u << bit;
+        }
+        // everything below the threshold, and the first `remaining` clusters (by index) that sit exactly on it
+        int before = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool     valid = lane + 32 * k < p.nClusters;
+            const uint32_t eq    = __ballot_sync(0xffffffffu, valid && key[k] == prefix);
+            const int      rank  = before + __popc(eq & ((1u << lane) - 1u));
+            const bool     sel   = valid && (key[k] < prefix || (key[k] == prefix && rank < remaining));
+            const uint32_t word  = __ballot_sync(0xffffffffu, sel);
+            if (lane == 0)
+                p.active[t * 8 + k] = word;
+            before += __popc(eq);
+        }
+        __syncwarp();
+    }
+}
+
+// block = one frame x up to 256 mixtures (x scaled once into shared memory)
+__global__ void __launch_bounds__(256) presel_score_kernel(const PreselParams p) {
+    __shared__ float    xs[128];
+    __shared__ uint32_t act[8];
+    for (long t = blockIdx.x; t < p.T; t += gridDim.x) {
+        __syncthreads();
+        for (int d = threadIdx.x; d < p.padded; d += blockDim.x)
+            xs[d] = d < p.dim ? __fmul_rn(p.feats[t * p.dim + d], p.isd[d]) : 0.0f;
+        if (threadIdx.x < 8)
+            act[threadIdx.x] = p.active[t * 8 + threadIdx.x];
+        __syncthreads();
+        for (int m = threadIdx.x; m < p.nMix; m += blockDim.x) {
+            float best = FLT_MAX;
+            for (uint32_t dns = p.offsets[m]; dns < p.offsets[m + 1]; ++dns) {
+                const uint32_t c = p.clusterOf[dns];
+                if (!((act[c >> 5] >> (c & 31)) & 1u))
+                    continue;
+                const float4* mu = reinterpret_cast<const float4*>(p.means + (size_t)dns * p.padded);
+                float a0 = p.consts[dns], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+                for (int d = 0; d < p.padded; d += 8) {
+                    const float4 u = mu[d >> 2], v = mu[(d >> 2) + 1];
+                    a0 = sq_acc(__fsub_rn(u.x, xs[d]), a0, p.fuse);
+                    a1 = sq_acc(__fsub_rn(u.y, xs[d + 1]), a1, p.fuse);
+                    a2 = sq_acc(__fsub_rn(u.z, xs[d + 2]), a2, p.fuse);
+                    a3 = sq_acc(__fsub_rn(u.w, xs[d + 3]), a3, p.fuse);
+                    b0 = sq_acc(__fsub_rn(v.x, xs[d + 4]), b0, p.fuse);
+                    b1 = sq_acc(__fsub_rn(v.y, xs[d + 5]), b1, p.fuse);
+                    b2 = sq_acc(__fsub_rn(v.z, xs[d + 6]), b2, p.fuse);
+                    b3 = sq_acc(__fsub_rn(v.w, xs[d + 7]), b3, p.fuse);
+                }
+                // s1 + s2, then the two shuffle-adds: lane 0 ends up with (v1 + v3) + (v0 + v2)
+                const float v0 = __fadd_rn(a0, b0), v1 = __fadd_rn(a1, b1), v2 = __fadd_rn(a2, b2), v3 = __fadd_rn(a3, b3);
+                const float sc = __fadd_rn(__fadd_rn(v3, v1), __fadd_rn(v2, v0));
+                best           = sc < best ? sc : best;  // _mm_min_ps(best, sc)
+            }
+            if (best < FLT_MAX)
+                best = __fmul_rn(best, 0.5f);
+            if (best == FLT_MAX)
+                best = p.backoff;
+            p.scores[t * p.nMix + m] = best;
+        }
+    }
+}
+
+}  // namespace
+
+struct rb_gmm_presel {
+    rb::DeviceInfo dev;
+    int            dim = 0, padded = 0, nMix = 0, nDens = 0, nClusters = 0, nSelected = 0;
+    bool           fuse = true;
+    float          backoff = 40000.0f;
+    std::vector<float>    isd, means, consts, clusterMeans;
+    std::vector<uint32_t> offsets, clusterOf;
+    rb::DevBuf<float>     dIsd, dMeans, dConsts, dClusterMeans;
+    rb::DevBuf<uint32_t>  dOffsets, dActive;
+    rb::DevBuf<uint8_t>   dClusterOf;
+};
+
+namespace {
+
+// Mm::unrolledVectorDistance<f32, f32> (src/Mm/Utilities.hh:254-296): sequential score += df * df
+float host_distance(const float* a, const float* b, int dim, bool fuse) {
+    float score = 0;
+    for (int d = 0; d < dim; ++d) {
+        const float df = a[d] - b[d];
+        if (fuse)
+            score = std::fmaf(df, df, score);
+        else {
+            volatile float sq = df * df;  // keep the product rounded on its own
+            score             = score + sq;
+        }
+    }
+    return score;
+}
+
+// DensityClustering::build (.tcc:126-161) with initializeClusters :62-75, assignDensities :82-100,
+// updateClusterMeans :103-123
+void build_clustering(rb_gmm_presel* h, int clusters, int iterations) {
+    const int dim = h->padded, nDens = h->nDens;
+    h->nClusters  = std::min(clusters, nDens);  // DensityClusteringBase::init, .cc:52-56
+    h->clusterMeans.assign((size_t)h->nClusters * dim, 0.0f);
+    h->clusterOf.assign(nDens, 0);
+    std::set<uint32_t> used;
+    GlibcRand          rng(1);
+    for (int c = 0; c < h->nClusters; ++c) {
+        uint32_t pick = 0;
+        do {
+            pick = (uint32_t)(rng.next() % nDens);
+        } while (used.count(pick));
+        used.insert(pick);
+        std::copy(h->means.begin() + (size_t)pick * dim, h->means.begin() + (size_t)(pick + 1) * dim,
+                  h->clusterMeans.begin() + (size_t)c * dim);
+    }
+    for (int it = 0; it < iterations; ++it) {
+        std::vector<std::vector<uint32_t>> assigned(h->nClusters);
+        for (int dns = 0; dns < nDens; ++dns) {
+            float best = FLT_MAX;
+            int   bc   = 0;
+            for (int c = 0; c < h->nClusters; ++c) {
+                const float dist = host_distance(&h->clusterMeans[(size_t)c * dim], &h->means[(size_t)dns * dim], dim, h->fuse);
+                if (dist < best) {
+                    best = dist;
+                    bc   = c;
+                }
+            }
+            h->clusterOf[dns] = (uint32_t)bc;
+            assigned[bc].push_back((uint32_t)dns);
+        }
+        for (int c = 0; c < h->nClusters; ++c) {
+            if (assigned[c].empty())
+                continue;
+            std::vector<double> sums(dim, 0.0);
+            for (uint32_t a : assigned[c])
+                for (int d = 0; d < dim; ++d)
+                    sums[d] += h->means[(size_t)a * dim + d];
+            for (int d = 0; d < dim; ++d)
+                h->clusterMeans[(size_t)c * dim + d] = (float)(sums[d] / (double)assigned[c].size());
+        }
+    }
+}
+
+int upload_clustering(rb_gmm_presel* h, cudaStream_t s) {
+    std::vector<uint8_t> c8(h->clusterOf.begin(), h->clusterOf.end());
+    RB_CHECK(h->dClusterOf.upload(c8.data(), c8.size(), s));
+    RB_CHECK(h->dClusterMeans.upload(h->clusterMeans, s));
+    RB_CUDA(cudaStreamSynchronize(s));
+    return RB_OK;
+}
+
+}  // namespace
+
+int rb_gmm_presel_configure(rb_gmm_presel* h, int clusters, int select, int iterations, float backoff, cudaStream_t s) {
+    RB_REQUIRE(clusters >= 1 && clusters <= 256 && select >= 1 && iterations >= 0, "bad preselection parameters");
+    build_clustering(h, clusters, iterations);
+    RB_REQUIRE(select <= h->nClusters, "select-clusters %d exceeds the %d clusters", select, h->nClusters);
+    h->nSelected = select;
+    h->backoff   = backoff;
+    return upload_clustering(h, s);
+}
+
+// model preparation = BatchFloatFeatureScorer::init (src/Mm/BatchFeatureScorer.cc:164-197)
+int rb_gmm_presel_create(const rb_mixture_set* ms, bool fuse, const rb::DeviceInfo& dev, cudaStream_t stream,
+                         rb_gmm_presel** out) {
+    *out = nullptr;
+    if (ms->n_covariances != 1) {
+        rb::set_error("feature scorer supports only globally pooled covariance");
+        return RB_ERR_UNSUPPORTED;
+    }
+    if (ms->dim > 120) {
+        rb::set_error("preselection scorer supports feature dimension <= 120 (got %u)", ms->dim);
+        return RB_ERR_UNSUPPORTED;
+    }
+    rb_gmm_presel* h = new (std::nothrow) rb_gmm_presel();
+    if (!h) {
+        rb::set_error("out of host memory");
+        return RB_ERR_NOMEM;
+    }
+    h->dev    = dev;
+    h->fuse   = fuse;
+    h->dim    = (int)ms->dim;
+    h->padded = (h->dim + 7) / 8 * 8;
+    h->nMix   = (int)ms->n_mixtures;
+    h->nDens  = (int)ms->mix_offsets[ms->n_mixtures];
+    h->isd.assign(h->padded, 0.0f);
+    double sumLog = 0;
+    for (int d = 0; d < h->dim; ++d) {
+        h->isd[d] = (float)1 / (float)std::sqrt(ms->variances[d]);
+        sumLog += std::log(std::fabs(ms->variances[d]));
+    }
+    const float logNormFactor = (float)((double)h->dim * std::log((double)2 * M_PI) + sumLog);
+    h->means.assign((size_t)h->nDens * h->padded, 0.0f);
+    h->consts.assign(h->nDens, 0.0f);
+    h->offsets.assign(ms->mix_offsets, ms->mix_offsets + ms->n_mixtures + 1);
+    for (uint32_t e = 0; e < (uint32_t)h->nDens; ++e) {
+        const uint32_t dns = ms->mix_density[e];
+        if (ms->dens_cov[dns] != 0) {
+            delete h;
+            rb::set_error("feature scorer supports only globally pooled covariance");
+            return RB_ERR_UNSUPPORTED;
+        }
+        const float* mu = ms->means + (size_t)ms->dens_mean[dns] * h->dim;
+        for (int d = 0; d < h->dim; ++d)
+            h->means[(size_t)e * h->padded + d] = mu[d] * h->isd[d];
+        h->consts[e] = (float)(logNormFactor - 2 * ms->mix_log_weight[e]);
+    }
+    int rc = h->dIsd.upload(h->isd, stream);
+    if (rc == RB_OK)
+        rc = h->dMeans.upload(h->means, stream);
+    if (rc == RB_OK)
+        rc = h->dConsts.upload(h->consts, stream);
+    if (rc == RB_OK)
+        rc = h->dOffsets.upload(h->offsets, stream);
+    if (rc == RB_OK)  // DensityClustering.cc:20-34: clusters 256, select-clusters 32, iterations 5, backoff-score 40000
+        rc = rb_gmm_presel_configure(h, 256, std::min(32, std::min(256, h->nDens)), 5, 40000.0f, stream);
+    if (rc != RB_OK) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return RB_OK;
+}
+
+void rb_gmm_presel_destroy(rb_gmm_presel* h) {
+    delete h;
+}
+
+int rb_gmm_presel_score(rb_gmm_presel* h, const float* dFeats, long T, float* dScores, cudaStream_t s) {
+    RB_CHECK(h->dActive.reserve((size_t)T * 8));
+    PreselParams p;
+    p.feats        = dFeats;
+    p.isd          = h->dIsd.p;
+    p.means        = h->dMeans.p;
+    p.consts       = h->dConsts.p;
+    p.offsets      = h->dOffsets.p;
+    p.clusterOf    = h->dClusterOf.p;
+    p.clusterMeans = h->dClusterMeans.p;
+    p.active       = h->dActive.p;
+    p.scores       = dScores;
+    p.T            = T;
+    p.dim          = h->dim;
+    p.padded       = h->padded;
+    p.nMix         = h->nMix;
+    p.nClusters    = h->nClusters;
+    p.nSelected    = h->nSelected;
+    p.fuse         = h->fuse ? 1 : 0;
+    p.backoff      = h->backoff;
+    const size_t smem = ((size_t)h->nClusters * (h->padded + 1) + (size_t)kSelWarps * h->padded) * 4;
+    RB_CUDA(cudaFuncSetAttribute(presel_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid1 = (int)std::min<long>((T + kSelWarps - 1) / kSelWarps, (long)h->dev.sm_count * 4);
+    presel_select_kernel<<<grid1, kSelWarps * 32, smem, s>>>(p);
+    RB_LAUNCH_CHECK();
+    const int grid2 = (int)std::min<long>(T, (long)h->dev.sm_count * 16);
+    presel_score_kernel<<<grid2, 256, 0, s>>>(p);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+void rb_gmm_presel_clustering(const rb_gmm_presel* h, uint32_t* cluster_of, float* cluster_means, int* n_clusters) {
+    if (cluster_of)
+        std::copy(h->clusterOf.begin(), h->clusterOf.end(), cluster_of);
+    if (cluster_means)
+        std::copy(h->clusterMeans.begin(), h->clusterMeans.end(), cluster_means);
+    if (n_clusters)
+        *n_clusters = h->nClusters;
+}
+
+// test hook (host only): the first n values of rand() after srand(seed), as restated above
+extern "C" void rb_test_glibc_rand(unsigned seed, int n, int* out) {
+    GlibcRand r(seed);
+    for (int i = 0; i < n; ++i)
+        out[i] = r.next();
+}

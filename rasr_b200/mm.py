@@ -57,7 +57,7 @@ class GmmScorer:
 
     MODES = {"batch-float": capi.GMM_BATCH_FLOAT, "diagonal-maximum": capi.GMM_DIAG_MAX,
              "diagonal-sum": capi.GMM_DIAG_SUM, "batch-tensor": capi.GMM_BATCH_TENSOR,
-             "batch-int": capi.GMM_BATCH_INT}
+             "batch-int": capi.GMM_BATCH_INT, "preselection-batch-float": capi.GMM_BATCH_PRESELECT}
 
     def __init__(self, mixture_set, mode="batch-float", mixture_weight_scale=1.0, gaussian_scale=1.0,
                  contraction=True, device=0):
@@ -82,6 +82,19 @@ class GmmScorer:
     @property
     def handle(self):
         return self._h
+
+    def configure_preselection(self, clusters=256, select=32, iterations=5, backoff_score=40000.0):
+        """density-clustering parameters of the preselection scorer (src/Mm/DensityClustering.cc:20-34)"""
+        capi.check(capi.lib().rb_gmm_configure_preselection(self._h, int(clusters), int(select), int(iterations),
+                                                            float(backoff_score)))
+
+    def clustering(self):
+        """(cluster index of every density in mixture order, cluster means [n_clusters, padded dim])"""
+        n_dens = int(self.mixture_set.mix_offsets[-1])
+        padded = (self.dim + 7) // 8 * 8
+        cluster_of, means, n = np.zeros(n_dens, np.uint32), np.zeros((256, padded), np.float32), C.c_int(0)
+        capi.check(capi.lib().rb_gmm_get_clustering(self._h, capi.ptr(cluster_of), capi.ptr(means), C.byref(n)))
+        return cluster_of, means[:n.value]
 
     def score(self, feats, want_density=False, out=None):
         """Host buffers (numpy, or pinned torch CPU tensors through their data_ptr)."""

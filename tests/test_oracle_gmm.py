@@ -218,3 +218,39 @@ def test_batch_int_ragged_and_empty(oracle):
     got = oracle.gmm_batch_int(ms, f)
     assert np.array_equal(got, int_scores_numpy(msd, f))
     assert np.all(got[:, 1] == np.float32(2147483647) / np.float32(oracle.gmm_batch_int_model(ms)["scale"]))
+
+
+# ---- density preselection ("preselection-batch-float") ---------------------------------------------------------------
+
+def test_glibc_rand_restatement_matches_libc():
+    """the clustering is initialised from rand() after srand(1) (src/Mm/DensityClustering.tcc:62-75); the library
+    restates glibc's generator instead of calling it (no side effect on the host program's random state)"""
+    import ctypes
+    from rasr_b200 import capi
+    libc = ctypes.CDLL(None)
+    for seed in (1, 2, 12345):
+        libc.srand(seed)
+        want = [libc.rand() for _ in range(1000)]
+        got = np.zeros(1000, np.int32)
+        capi.lib().rb_test_glibc_rand(seed, 1000, capi.ptr(got))
+        assert list(got) == want, seed
+
+
+def test_preselection_oracle_properties(oracle):
+    msd = synth.mixture_set()
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(300, 39)
+    full = oracle.gmm_batch_float(ms, f)
+    sc, cluster_of, means = oracle.gmm_preselect_float(ms, f)
+    assert means.shape == (256, 40) and cluster_of.max() < 256
+    hit = sc != np.float32(40000)
+    # a preselected score is the minimum over a subset of the densities: never below the full minimum, and equal to
+    # it whenever the best density's cluster was selected
+    assert (sc[hit] >= full[hit]).all() and (sc == full).mean() > 0.3 and (~hit).mean() < 0.2
+    # selecting every cluster is the plain batch scorer
+    assert np.array_equal(oracle.gmm_preselect_float(ms, f, select=256)[0], full)
+    # one cluster, one iteration: the cluster mean is the f64 mean of all scaled density means
+    _, c1, m1 = oracle.gmm_preselect_float(ms, f[:2], clusters=1, select=1, iterations=1)
+    isd = (1 / np.sqrt(msd["variances"][0].astype(np.float32))).astype(np.float32)
+    scaled = (msd["means"].astype(np.float32) * isd).astype(np.float32)
+    assert (c1 == 0).all() and np.array_equal(m1[0, :39], scaled.astype(np.float64).mean(0).astype(np.float32))
