@@ -15,6 +15,10 @@ const Core::ParameterInt   FeatureScorer::paramDevice("device", "CUDA device ord
 const Core::ParameterInt   FeatureScorer::paramBufferSize("buffer-size", "frames buffered per dense scoring launch (default: the whole segment)", Core::Type<s32>::max, 1);
 const Core::ParameterBool  GmmFeatureScorer::paramContraction("fma-contraction", "reproduce a CPU build with -ffp-contract=fast (gcc default) instead of a strict one", true);
 const Core::ParameterFloat GmmFeatureScorer::paramMixtureWeightScale("mixture-weight-scale", "scale of the -log mixture weights (diagonal scorers)", 1.0);
+const Core::ParameterInt   GmmFeatureScorer::paramClusters("clusters", "number of density clusters to build for density preselection", 256, 1, 256);
+const Core::ParameterInt   GmmFeatureScorer::paramSelectClusters("select-clusters", "number of clusters to select in density preselection", 32, 1, 256);
+const Core::ParameterInt   GmmFeatureScorer::paramClusteringIterations("iterations", "number of clustering iterations", 5);
+const Core::ParameterFloat GmmFeatureScorer::paramBackoffScore("backoff-score", "score used if no cluster is selected", 40000);
 const Core::ParameterFloat GmmFeatureScorer::paramGaussianScale("gaussian-scale", "scale of the Gaussian exponent (diagonal scorers)", 1.0);
 
 class FeatureScorer::ContextScorer : public Mm::FeatureScorer::ContextScorer {
@@ -79,6 +83,14 @@ GmmFeatureScorer::GmmFeatureScorer(const Core::Configuration& c, Core::Ref<const
     if (rb_gmm_create(&view, mode, paramMixtureWeightScale(c), paramGaussianScale(c), paramContraction(c),
                       paramDevice(c), &handle_) != RB_OK)
         criticalError("rasr_b200: %s", rb_last_error());
+    if (mode == RB_GMM_BATCH_PRESELECT) {
+        // the parameters of Mm::DensityClusteringBase under the same selection (src/Mm/BatchFeatureScorer.cc:262,
+        // src/Mm/DensityClustering.cc:20-34)
+        const Core::Configuration dc(c, "density-clustering");
+        if (rb_gmm_configure_preselection(handle_, paramClusters(dc), paramSelectClusters(dc), paramClusteringIterations(dc),
+                                          paramBackoffScore(dc)) != RB_OK)
+            criticalError("rasr_b200: %s", rb_last_error());
+    }
     log("b200 feature scorer: %d mixtures, %d densities, dimension %d on device %d",
         int(nMixtures_), int(ms->nDensities()), int(dimension_), int(paramDevice(c)));
 }
