@@ -15,9 +15,10 @@
 //                           distance bits -> one bit per cluster.  The reference sorts (distance, cluster) pairs by
 //                           distance only (std::sort, not stable): for exactly equal distances at the selection
 //                           boundary its choice is unspecified; here the lower cluster index wins.
-//   presel_score_kernel     one thread per (frame, mixture): the lane arithmetic of fillScoreCacheTpl (two 4-lane
-//                           accumulators over 8-dimension blocks, the constant first in lane 0, horizontal add) for the
-//                           densities whose cluster bit is set, minimum, x0.5, back-off.
+//   presel_score_kernel     one block per frame: the densities whose cluster bit is set are collected in a shared list
+//                           and scored by groups of 8 lanes with the lane arithmetic of fillScoreCacheTpl (two 4-lane
+//                           accumulators over 8-dimension blocks, the constant first in lane 0, horizontal add);
+//                           minimum per mixture by atomicMin on order-preserving keys, x0.5, back-off.
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -60,6 +61,7 @@ struct PreselParams {
     const float*   consts;     // [nDens]
     const uint32_t* offsets;   // [nMix + 1]
     const uint8_t* clusterOf;  // [nDens]
+    const uint32_t* densMix;   // [nDens] mixture of every density entry
     const float*   clusterMeans;  // [nClusters * padded]
     uint32_t*      active;     // [T * 8] one bit per cluster
     float*         scores;     // [T * nMix]
@@ -134,41 +136,73 @@ __global__ void __launch_bounds__(kSelWarps * 32) presel_select_kernel(const Pre
     }
 }
 
-// block = one frame x up to 256 mixtures (x scaled once into shared memory)
+// order-preserving map of f32 onto u32 (and back), so that the minimum over a mixture's scored densities can be taken
+// with an integer atomicMin: the minimum of a set does not depend on the order its elements arrive in
+__device__ __forceinline__ uint32_t presel_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float presel_unkey(uint32_t k) {
+    return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+
+constexpr int kListCap = 2048;  // densities looked at per round (8 per thread)
+
+// One block per frame.  Round by round, 2048 densities are tested against the frame's cluster bits and the active ones
+// collected in a shared list; the list is then scored by groups of 8 lanes -- lane j of a group owns accumulator lane
+// j of fillScoreCacheTpl's two 4-lane registers, so a group reads 32 contiguous bytes of the density row per
+// 8-dimension block -- and the horizontal adds are the reference's two shuffle-adds.
+// dynamic smem: best [nMix] keys
 __global__ void __launch_bounds__(256) presel_score_kernel(const PreselParams p) {
+    extern __shared__ uint32_t sBest[];
     __shared__ float    xs[128];
     __shared__ uint32_t act[8];
+    __shared__ uint32_t list[kListCap];
+    __shared__ int      count;
+    const int nDens = (int)p.offsets[p.nMix];
+    const int lane8 = threadIdx.x & 7, group = threadIdx.x >> 3;
     for (long t = blockIdx.x; t < p.T; t += gridDim.x) {
         __syncthreads();
         for (int d = threadIdx.x; d < p.padded; d += blockDim.x)
             xs[d] = d < p.dim ? __fmul_rn(p.feats[t * p.dim + d], p.isd[d]) : 0.0f;
         if (threadIdx.x < 8)
             act[threadIdx.x] = p.active[t * 8 + threadIdx.x];
+        for (int m = threadIdx.x; m < p.nMix; m += blockDim.x)
+            sBest[m] = presel_key(FLT_MAX);
+        for (int base = 0; base < nDens; base += kListCap) {
+            if (threadIdx.x == 0)
+                count = 0;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kListCap / 256; ++j) {
+                const int dns = base + j * 256 + threadIdx.x;
+                if (dns < nDens) {
+                    const uint32_t c = p.clusterOf[dns];
+                    if ((act[c >> 5] >> (c & 31)) & 1u)
+                        list[atomicAdd(&count, 1)] = (uint32_t)dns;
+                }
+            }
+            __syncthreads();
+            const int n = count;
+            for (int i0 = 0; i0 < n; i0 += 32) {  // warp-uniform trip count: the shuffles below need every lane
+                const int      i     = i0 + group;
+                const bool     valid = i < n;
+                const uint32_t dns   = list[valid ? i : 0];
+                const float*   mu    = p.means + (size_t)dns * p.padded + lane8;
+                float          acc   = lane8 == 0 ? p.consts[dns] : 0.0f;
+                for (int d = 0; d < p.padded; d += 8)
+                    acc = sq_acc(__fsub_rn(mu[d], xs[d + lane8]), acc, p.fuse);
+                // s1 + s2; s1 += shuffle(1,0,3,2); s1 += shuffle(2,3,0,1): lane 0 = (v1 + v3) + (v0 + v2)
+                float v = __fadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, 4, 8));
+                v       = __fadd_rn(__shfl_down_sync(0xffffffffu, v, 2, 8), v);
+                v       = __fadd_rn(__shfl_down_sync(0xffffffffu, v, 1, 8), v);
+                if (valid && lane8 == 0)
+                    atomicMin(&sBest[p.densMix[dns]], presel_key(v));
+            }
+        }
         __syncthreads();
         for (int m = threadIdx.x; m < p.nMix; m += blockDim.x) {
-            float best = FLT_MAX;
-            for (uint32_t dns = p.offsets[m]; dns < p.offsets[m + 1]; ++dns) {
-                const uint32_t c = p.clusterOf[dns];
-                if (!((act[c >> 5] >> (c & 31)) & 1u))
-                    continue;
-                const float4* mu = reinterpret_cast<const float4*>(p.means + (size_t)dns * p.padded);
-                float a0 = p.consts[dns], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
-                for (int d = 0; d < p.padded; d += 8) {
-                    const float4 u = mu[d >> 2], v = mu[(d >> 2) + 1];
-                    a0 = sq_acc(__fsub_rn(u.x, xs[d]), a0, p.fuse);
-                    a1 = sq_acc(__fsub_rn(u.y, xs[d + 1]), a1, p.fuse);
-                    a2 = sq_acc(__fsub_rn(u.z, xs[d + 2]), a2, p.fuse);
-                    a3 = sq_acc(__fsub_rn(u.w, xs[d + 3]), a3, p.fuse);
-                    b0 = sq_acc(__fsub_rn(v.x, xs[d + 4]), b0, p.fuse);
-                    b1 = sq_acc(__fsub_rn(v.y, xs[d + 5]), b1, p.fuse);
-                    b2 = sq_acc(__fsub_rn(v.z, xs[d + 6]), b2, p.fuse);
-                    b3 = sq_acc(__fsub_rn(v.w, xs[d + 7]), b3, p.fuse);
-                }
-                // s1 + s2, then the two shuffle-adds: lane 0 ends up with (v1 + v3) + (v0 + v2)
-                const float v0 = __fadd_rn(a0, b0), v1 = __fadd_rn(a1, b1), v2 = __fadd_rn(a2, b2), v3 = __fadd_rn(a3, b3);
-                const float sc = __fadd_rn(__fadd_rn(v3, v1), __fadd_rn(v2, v0));
-                best           = sc < best ? sc : best;  // _mm_min_ps(best, sc)
-            }
+            float best = presel_unkey(sBest[m]);
             if (best < FLT_MAX)
                 best = __fmul_rn(best, 0.5f);
             if (best == FLT_MAX)
@@ -188,7 +222,7 @@ struct rb_gmm_presel {
     std::vector<float>    isd, means, consts, clusterMeans;
     std::vector<uint32_t> offsets, clusterOf;
     rb::DevBuf<float>     dIsd, dMeans, dConsts, dClusterMeans;
-    rb::DevBuf<uint32_t>  dOffsets, dActive;
+    rb::DevBuf<uint32_t>  dOffsets, dActive, dDensMix;
     rb::DevBuf<uint8_t>   dClusterOf;
 };
 
@@ -326,6 +360,14 @@ int rb_gmm_presel_create(const rb_mixture_set* ms, bool fuse, const rb::DeviceIn
         rc = h->dConsts.upload(h->consts, stream);
     if (rc == RB_OK)
         rc = h->dOffsets.upload(h->offsets, stream);
+    std::vector<uint32_t> densMix(h->nDens);
+    for (int m = 0; m < h->nMix; ++m)
+        for (uint32_t e = h->offsets[m]; e < h->offsets[m + 1]; ++e)
+            densMix[e] = (uint32_t)m;
+    if (rc == RB_OK)
+        rc = h->dDensMix.upload(densMix, stream);
+    if (rc == RB_OK && cudaStreamSynchronize(stream) != cudaSuccess)
+        rc = RB_ERR_CUDA;
     if (rc == RB_OK)  // DensityClustering.cc:20-34: clusters 256, select-clusters 32, iterations 5, backoff-score 40000
         rc = rb_gmm_presel_configure(h, 256, std::min(32, std::min(256, h->nDens)), 5, 40000.0f, stream);
     if (rc != RB_OK) {
@@ -349,6 +391,7 @@ int rb_gmm_presel_score(rb_gmm_presel* h, const float* dFeats, long T, float* dS
     p.consts       = h->dConsts.p;
     p.offsets      = h->dOffsets.p;
     p.clusterOf    = h->dClusterOf.p;
+    p.densMix      = h->dDensMix.p;
     p.clusterMeans = h->dClusterMeans.p;
     p.active       = h->dActive.p;
     p.scores       = dScores;
@@ -365,8 +408,11 @@ int rb_gmm_presel_score(rb_gmm_presel* h, const float* dFeats, long T, float* dS
     const int grid1 = (int)std::min<long>((T + kSelWarps - 1) / kSelWarps, (long)h->dev.sm_count * 4);
     presel_select_kernel<<<grid1, kSelWarps * 32, smem, s>>>(p);
     RB_LAUNCH_CHECK();
+    const size_t smemBest = (size_t)h->nMix * 4;
+    RB_REQUIRE(smemBest + 12 * 1024 <= h->dev.smem_optin, "preselection scorer: %d mixtures do not fit", h->nMix);
+    RB_CUDA(cudaFuncSetAttribute(presel_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBest));
     const int grid2 = (int)std::min<long>(T, (long)h->dev.sm_count * 16);
-    presel_score_kernel<<<grid2, 256, 0, s>>>(p);
+    presel_score_kernel<<<grid2, 256, smemBest, s>>>(p);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
