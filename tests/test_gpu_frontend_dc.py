@@ -10,11 +10,11 @@ from tests.test_oracle_dc import audio_with_plateaus
 pytestmark = pytest.mark.gpu
 
 
-def check_against_oracle(oracle, fe, x, offs, r, dc=None):
+def check_against_oracle(oracle, fe, x, offs, r, dc=None, cfg=None):
     fo = r["frame_offsets"]
     k = 0
     for u in range(len(offs) - 1):
-        o = oracle.mfcc_dc(oracle.frontend_cfg(), oracle.dc_cfg(**(dc or {})), x[offs[u]:offs[u + 1]])
+        o = oracle.mfcc_dc(oracle.frontend_cfg(**(cfg or {})), oracle.dc_cfg(**(dc or {})), x[offs[u]:offs[u + 1]])
         n = len(o["run_begin"])
         sel = slice(k, k + n)
         assert list(r["runs"]["utt"][sel]) == [u] * n
@@ -127,3 +127,18 @@ def test_flow_node_with_dc_detection(oracle):
     assert np.allclose([p.start for p in out], t0 + o["t_start"], rtol=0, atol=1e-9)
     assert np.allclose([p.end for p in out], t0 + o["t_end"], rtol=0, atol=1e-9)
     assert rel_err(np.stack([p.data for p in out]), o["feats"]) < RTOL
+
+
+@pytest.mark.parametrize("kw", [dict(sample_rate=8000.0), dict(window_shift_s=0.005), dict(derivatives=0)])
+def test_other_front_end_geometries(oracle, kw):
+    """the generic front-end kernel (any geometry but the 512-point one) and other frame shifts also take the kept
+    runs as segments; min-dc-length etc. are given in seconds and follow the sample rate"""
+    x = audio_with_plateaus(30000, 23, n_plateaus=8)
+    fkw = dict(kw)
+    if "window_shift_s" in fkw:
+        fkw["window_shift"] = fkw.pop("window_shift_s")
+    if "derivatives" in fkw:
+        fkw["derivatives"] = bool(fkw["derivatives"])
+    fe = flow.FrontEnd(**fkw)
+    r = fe.process_dc(x)
+    check_against_oracle(oracle, fe, x, np.array([0, x.size], np.int64), r, cfg=kw)
