@@ -161,6 +161,7 @@ const Core::ParameterStringVector NnFeatureScorer::paramParameterFiles("paramete
 const Core::ParameterString       NnFeatureScorer::paramHiddenActivation("hidden-activation", "activation of the hidden layers: sigmoid, rectified, tanh or linear", "sigmoid");
 const Core::ParameterString       NnFeatureScorer::paramPriorFile("prior-file", "log prior vector file; empty: estimate from the mixture weights", "");
 const Core::ParameterFloat        NnFeatureScorer::paramPrioriScale("priori-scale", "scaling of the logarithmized state priori probability", 1.0);
+const Core::ParameterString       NnFeatureScorer::paramClassLabelFile("load-from-file", "class-labels: network-output-to-class-index mapping (Math::Vector<s32>, -1 = disregarded class)", "");
 const Core::ParameterBool         NnFeatureScorer::paramBf16("bf16", "bf16 operands with f32 accumulation on the tensor cores (false: f32 arithmetic)", true);
 
 NnFeatureScorer::NnFeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> ms)
@@ -215,28 +216,48 @@ NnFeatureScorer::NnFeatureScorer(const Core::Configuration& c, Core::Ref<const M
     }
     acts[nLayers - 1] = RB_ACT_SOFTMAX;  // output layer must be linear+softmax; only its scores are computed
     dimension_        = dims[0];
-    if (u32(dims[nLayers]) != nMixtures_)
+    // Nn::ClassLabelWrapper (src/Nn/ClassLabelWrapper.cc:33-100): emission class -> network output from the file
+    // the reference's wrapper saves (class-labels.load-from-file), else the identity
+    std::vector<s32> classToOutput;
+    const std::string labelFile = paramClassLabelFile(Core::Configuration(c, "class-labels"));
+    if (!labelFile.empty()) {
+        Math::Vector<s32> mapping;
+        if (!Math::Module::instance().formats().read(labelFile, mapping) || mapping.size() != nMixtures_)
+            criticalError("failed to read a mapping of %d classes from '%s'", int(nMixtures_), labelFile.c_str());
+        classToOutput.assign(mapping.begin(), mapping.end());
+    }
+    else if (u32(dims[nLayers]) != nMixtures_)
         criticalError("no one-to-one correspondence between network outputs (%d) and classes (%d)!", dims[nLayers],
                       int(nMixtures_));
 
-    // log prior: from file, or relative mixture weight mass (Prior::setFromMixtureSet, src/Nn/Prior.cc:158-188)
-    std::vector<f32> logPrior(nMixtures_, 0.0f);
+    // log prior per network output: from file, or relative mixture weight mass of the class mapped to the output
+    // (Prior::setFromMixtureSet, src/Nn/Prior.cc:158-188)
+    const u32        nOut = dims[nLayers];
+    std::vector<f32> logPrior(nOut, 0.0f);
     if (!paramPriorFile(c).empty()) {
         Math::Vector<f32> priors;
-        if (!Math::Module::instance().formats().read(paramPriorFile(c), priors) || priors.size() != nMixtures_)
-            criticalError("failed to read a prior of dimension %d from '%s'", int(nMixtures_), paramPriorFile(c).c_str());
+        if (!Math::Module::instance().formats().read(paramPriorFile(c), priors) || priors.size() != nOut)
+            criticalError("failed to read a prior of dimension %d from '%s'", int(nOut), paramPriorFile(c).c_str());
         std::copy(priors.begin(), priors.end(), logPrior.begin());
     }
     else {
-        for (Mm::MixtureIndex m = 0; m < ms->nMixtures(); ++m)
+        for (Mm::MixtureIndex m = 0; m < ms->nMixtures(); ++m) {
+            const s32 o = classToOutput.empty() ? s32(m) : classToOutput[m];
+            if (o < 0)
+                continue;
+            f32 mass = 0;
             for (size_t d = 0; d < ms->mixture(m)->nDensities(); ++d)
-                logPrior[m] += ms->mixture(m)->weight(d);
+                mass += ms->mixture(m)->weight(d);
+            logPrior[o] = mass;
+        }
         const f32 observationWeight = std::accumulate(logPrior.begin(), logPrior.end(), 0.0);
-        for (u32 m = 0; m < nMixtures_; ++m)
-            logPrior[m] = std::log(logPrior[m] / observationWeight);
+        for (u32 o = 0; o < nOut; ++o)
+            logPrior[o] = std::log(logPrior[o] / observationWeight);
     }
     if (rb_nn_create(nLayers, dims.data(), acts.data(), wp.data(), bp.data(), logPrior.data(), paramPrioriScale(c),
                      paramBf16(c) ? RB_NN_BF16 : RB_NN_F32, paramDevice(c), &handle_) != RB_OK)
+        criticalError("rasr_b200: %s", rb_last_error());
+    if (!classToOutput.empty() && rb_nn_set_class_mapping(handle_, classToOutput.size(), classToOutput.data()) != RB_OK)
         criticalError("rasr_b200: %s", rb_last_error());
     log("b200 nn feature scorer: %d layers, %d inputs, %d outputs on device %d", nLayers, dims[0], dims[nLayers],
         int(paramDevice(c)));

@@ -121,14 +121,16 @@ public:
  *  evaluated (src/Nn/BatchFeatureScorer.cc:45-171, LinearAndActivationLayer.cc:154-160).  The network is given as
  *  one parameter file per layer in the reference's Math::Matrix format (row = output unit, column 0 = bias,
  *  src/Nn/LinearLayer.cc:219-237,383-424) plus the hidden activation; the prior comes from `prior-file` or, like
- *  Prior::setFromMixtureSet (src/Nn/Prior.cc:158-188), from the mixture weights.  Network outputs map one-to-one to
- *  the emission indices (ClassLabelWrapper without disregarded classes). */
+ *  Prior::setFromMixtureSet (src/Nn/Prior.cc:158-188), from the mixture weights.  Emission classes map to network
+ *  outputs through the Nn::ClassLabelWrapper file (class-labels.load-from-file; disregarded classes score FLT_MAX,
+ *  src/Nn/BatchFeatureScorer.cc:163-169), else one-to-one. */
 class NnFeatureScorer : public FeatureScorer {
 public:
     static const Core::ParameterStringVector paramParameterFiles;  // "parameters-old" of the layers, bottom to top
     static const Core::ParameterString       paramHiddenActivation;
     static const Core::ParameterString       paramPriorFile;
     static const Core::ParameterFloat        paramPrioriScale;
+    static const Core::ParameterString       paramClassLabelFile;  // class-labels.load-from-file
     static const Core::ParameterBool         paramBf16;
 
     NnFeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> mixtureSet);

@@ -255,6 +255,12 @@ int  rb_nn_create(int n_layers, const int* dims, const int* act, const float* co
 void rb_nn_destroy(rb_nn* h);
 int  rb_nn_n_outputs(const rb_nn* h);
 int  rb_nn_n_inputs(const rb_nn* h);
+/* Nn::ClassLabelWrapper (src/Nn/ClassLabelWrapper.cc:57-100): class_to_output [n_classes] maps an emission class to a
+ * network output, -1 = disregarded class.  rb_nn_score[_dev] then writes [T * n_classes] scores, FLT_MAX for the
+ * disregarded classes (src/Nn/BatchFeatureScorer.cc:163-169); rb_nn_forward is not affected.  NULL removes the
+ * mapping.  rb_nn_n_emissions = n_classes, or the number of outputs without a mapping. */
+int  rb_nn_set_class_mapping(rb_nn* h, int n_classes, const int32_t* class_to_output);
+int  rb_nn_n_emissions(const rb_nn* h);
 /* scores [T*n_out]: score = -(w.h + b - prior_scale*log_prior), top-layer softmax NOT evaluated
  * (src/Nn/BatchFeatureScorer.cc:64,148-171) */
 int rb_nn_score(rb_nn* h, const float* feats, long T, float* scores);

@@ -30,7 +30,7 @@ SYMBOLS = [
     "rb_dc_default_cfg", "rb_frontend_dc_max_frames", "rb_frontend_process_dc", "rb_frontend_dc_runs", "rb_frontend_set_dc_detection",
     "rb_gmm_configure_preselection", "rb_gmm_get_clustering", "rb_test_glibc_rand",
     "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
-    "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_score", "rb_nn_score_dev",
+    "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_set_class_mapping", "rb_nn_n_emissions", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_s16", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
     "rb_pipeline_nn_score", "rb_pipeline_nn_score_dev",
     "rb_search_create", "rb_search_destroy", "rb_search_decode", "rb_search_decode_dev", "rb_search_traceback", "rb_search_traceback_all", "rb_pipeline_search",
@@ -152,6 +152,8 @@ def lib():
     L.rb_nn_destroy.restype = None
     L.rb_nn_n_outputs.argtypes = [vp]
     L.rb_nn_n_inputs.argtypes = [vp]
+    L.rb_nn_set_class_mapping.argtypes = [vp, C.c_int, vp]
+    L.rb_nn_n_emissions.argtypes = [vp]
     L.rb_nn_score.argtypes = [vp, vp, C.c_long, vp]
     L.rb_nn_score_dev.argtypes = [vp, vp, C.c_long, vp, vp]
     L.rb_nn_forward.argtypes = [vp, vp, C.c_long, vp]

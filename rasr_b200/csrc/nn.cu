@@ -282,6 +282,10 @@ struct rb_nn {
     rb::DevBuf<float> actFA, actFB;
     // host-pointer staging
     rb::DevBuf<float> dIn, dOut;
+    // optional Nn::ClassLabelWrapper mapping of the scores (rb_nn_set_class_mapping)
+    int               nClasses = 0;
+    rb::DevBuf<int>   dClassMap;
+    rb::DevBuf<float> dUnmapped;
 
     ~rb_nn() {
         for (NnLayer* l : layers)
@@ -376,11 +380,32 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
     return RB_OK;
 }
 
+// Nn::ClassLabelWrapper (src/Nn/ClassLabelWrapper.cc:57-100): emission class -> network output, -1 = disregarded class,
+// whose score is FLT_MAX (Nn::BatchFeatureScorer::ContextScorer::score, src/Nn/BatchFeatureScorer.cc:163-169)
+__global__ void __launch_bounds__(256) nn_map_classes_kernel(const float* __restrict__ in, int nOut, const int* __restrict__ map,
+                                                             int nClasses, long T, float* __restrict__ out) {
+    const long total = T * nClasses;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long t = i / nClasses;
+        const int  o = map[i - t * nClasses];
+        out[i]       = o >= 0 ? in[t * nOut + o] : FLT_MAX;
+    }
+}
+
 int run_dev(rb_nn* h, const float* dFeats, long T, float* dOut, bool scoreMode, cudaStream_t s) {
-    const int in = h->layers[0]->in, out = h->layers[h->nLayers - 1]->out;
+    const int  in = h->layers[0]->in, out = h->layers[h->nLayers - 1]->out;
+    const bool mapped = scoreMode && h->nClasses > 0;
+    if (mapped)
+        RB_CHECK(h->dUnmapped.reserve((size_t)std::min(h->chunk, T) * out));
     for (long a = 0; a < T; a += h->chunk) {
         const long n = std::min(h->chunk, T - a);
-        RB_CHECK(forward_chunk(h, dFeats + a * in, n, dOut + a * out, scoreMode, s));
+        RB_CHECK(forward_chunk(h, dFeats + a * in, n, mapped ? h->dUnmapped.p : dOut + a * out, scoreMode, s));
+        if (mapped) {
+            const long total = n * h->nClasses;
+            nn_map_classes_kernel<<<(int)std::min<long>((total + 255) / 256, (long)h->dev.sm_count * 16), 256, 0, s>>>(
+                    h->dUnmapped.p, out, h->dClassMap.p, h->nClasses, n, dOut + a * h->nClasses);
+            RB_LAUNCH_CHECK();
+        }
     }
     return RB_OK;
 }
@@ -392,7 +417,8 @@ int run_host(rb_nn* h, const float* feats, long T, float* outp, bool scoreMode) 
         return RB_OK;
     RB_REQUIRE(feats && outp, "NULL host buffer");
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
-    const size_t in = h->layers[0]->in, out = h->layers[h->nLayers - 1]->out;
+    const size_t in = h->layers[0]->in,
+                 out = scoreMode && h->nClasses > 0 ? (size_t)h->nClasses : (size_t)h->layers[h->nLayers - 1]->out;
     // bounded staging: the score matrix of a long segment (48 KB / frame for 12k senones) is streamed
     const long slab = std::min<long>(T, 4 * h->chunk);
     RB_CHECK(h->dIn.reserve((size_t)slab * in));
@@ -532,6 +558,27 @@ extern "C" void rb_nn_destroy(rb_nn* h) {
 
 extern "C" int rb_nn_n_outputs(const rb_nn* h) {
     return h ? h->layers[h->nLayers - 1]->out : 0;
+}
+
+extern "C" int rb_nn_n_emissions(const rb_nn* h) {
+    return h ? (h->nClasses > 0 ? h->nClasses : h->layers[h->nLayers - 1]->out) : 0;
+}
+
+extern "C" int rb_nn_set_class_mapping(rb_nn* h, int n_classes, const int32_t* class_to_output) {
+    RB_REQUIRE(h != nullptr, "nn handle is NULL");
+    if (!class_to_output || n_classes <= 0) {
+        h->nClasses = 0;
+        return RB_OK;
+    }
+    const int nOut = h->layers[h->nLayers - 1]->out;
+    for (int c = 0; c < n_classes; ++c)
+        RB_REQUIRE(class_to_output[c] >= -1 && class_to_output[c] < nOut, "class %d maps to output %d of %d", c,
+                   class_to_output[c], nOut);
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    RB_CHECK(h->dClassMap.upload(class_to_output, (size_t)n_classes, h->stream));
+    RB_CUDA(cudaStreamSynchronize(h->stream));
+    h->nClasses = n_classes;
+    return RB_OK;
 }
 
 extern "C" int rb_nn_n_inputs(const rb_nn* h) {

@@ -36,6 +36,7 @@ class NnScorer:
                                            float(prior_scale if lp is not None else 0.0), prec, device,
                                            C.byref(self._h)))
         self.n_inputs, self.n_outputs = self.dims[0], self.dims[-1]
+        self.n_emissions = self.n_outputs
 
     @classmethod
     def from_files(cls, layer_files, acts, prior_file=None, prior_scale=1.0, **kw):
@@ -57,6 +58,17 @@ class NnScorer:
         prior = io.read_vector(prior_file) if prior_file else None
         return cls(dims, acts, ws, bs, prior, prior_scale, **kw)
 
+    def set_class_mapping(self, class_to_output):
+        """Nn::ClassLabelWrapper: emission class -> network output, -1 = disregarded class (score FLT_MAX); None removes
+        the mapping.  Affects score() / score_dev() only."""
+        if class_to_output is None:
+            capi.check(capi.lib().rb_nn_set_class_mapping(self._h, 0, None))
+            self.n_emissions = self.n_outputs
+            return
+        m = np.ascontiguousarray(class_to_output, np.int32)
+        capi.check(capi.lib().rb_nn_set_class_mapping(self._h, int(m.size), capi.ptr(m)))
+        self.n_emissions = int(m.size)
+
     def close(self):
         if getattr(self, "_h", None) and capi is not None:  # capi is None while the interpreter shuts down
             capi.lib().rb_nn_destroy(self._h)
@@ -73,7 +85,7 @@ class NnScorer:
         if isinstance(feats, np.ndarray):
             feats = np.ascontiguousarray(feats, np.float32)
         T = int(feats.shape[0])
-        scores = out if out is not None else np.zeros((T, self.n_outputs), np.float32)
+        scores = out if out is not None else np.zeros((T, self.n_emissions), np.float32)
         capi.check(capi.lib().rb_nn_score(self._h, capi.ptr(feats), T, capi.ptr(scores)))
         return scores
 

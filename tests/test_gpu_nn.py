@@ -183,3 +183,34 @@ def test_c4_at_full_size(oracle, diag):
     e = scale_err(got[:24], want)
     diag("nn_c4_full", err=e, frames=T)
     assert e < 3e-3
+
+
+def test_class_label_mapping():
+    """Nn::ClassLabelWrapper: emission classes map to network outputs, disregarded classes score FLT_MAX
+    (src/Nn/ClassLabelWrapper.cc:57-100, src/Nn/BatchFeatureScorer.cc:163-169)"""
+    from rasr_b200 import capi
+    net = synth.network(dims=(45, 96, 70), seed=11)
+    x = synth.features(5000, 45, seed=12, scale=1.0)
+    sc = nn.NnScorer(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, "bf16")
+    plain = sc.score(x)
+    # 80 classes: what initMapping builds for disregard-classes = 3, 10, ..., the rest numbered consecutively
+    disregard = set(range(3, 80, 7))
+    mapping, nxt = [], 0
+    for c in range(80):
+        if c in disregard:
+            mapping.append(-1)
+        else:
+            mapping.append(nxt)
+            nxt += 1
+    assert nxt <= 70
+    sc.set_class_mapping(mapping)
+    got = sc.score(x)
+    assert got.shape == (5000, 80)
+    m = np.asarray(mapping)
+    assert np.array_equal(got[:, m >= 0], plain[:, m[m >= 0]])
+    assert (got[:, m < 0] == np.finfo(np.float32).max).all()
+    assert np.array_equal(sc.forward(x).shape, (5000, 70))   # the forward node is not mapped
+    sc.set_class_mapping(None)
+    assert np.array_equal(sc.score(x), plain)
+    with pytest.raises(capi.RasrB200Error):
+        sc.set_class_mapping([0, 70])
