@@ -10,6 +10,11 @@ const Core::ParameterFloat MfccNode::paramFilterWidth("filter-width", "mel filte
 const Core::ParameterInt   MfccNode::paramNrOutputs("nr-outputs", "number of cepstral coefficients", 13, 1);
 const Core::ParameterBool  MfccNode::paramDerivatives("derivatives", "append first and second order regression", true);
 const Core::ParameterInt   MfccNode::paramDevice("device", "CUDA device ordinal", 0, 0);
+// signal-window "type" (src/Signal/WindowFunction.cc:25-33); the Kaiser window (optional NR module) is not offered
+const Core::Choice          MfccNode::choiceWindowType("hamming", RB_WINDOW_HAMMING, "rectangular", RB_WINDOW_RECTANGULAR, "hanning", RB_WINDOW_HANNING,
+                                                        "periodic-hanning", RB_WINDOW_PERIODIC_HANNING, "bartlett", RB_WINDOW_BARTLETT,
+                                                        "blackman", RB_WINDOW_BLACKMAN, Core::Choice::endMark());
+const Core::ParameterChoice MfccNode::paramWindowType("window-type", &choiceWindowType, "type of window", RB_WINDOW_HAMMING);
 // signal-dc-detection in front of the chain (src/Signal/DcDetection.cc:231-241; values of samples.flow:34-35)
 const Core::ParameterBool  MfccNode::paramDcDetection("dc-detection", "discard DC stretches of the input like signal-dc-detection", false);
 const Core::ParameterFloat MfccNode::paramMinDcLength("min-dc-length", "minimum length (in seconds) of DC necesseary for the decision", .0125, 0);
@@ -28,6 +33,7 @@ MfccNode::MfccNode(const Core::Configuration& c)
     cfg_.n_cepstra         = paramNrOutputs(c);
     cfg_.derivatives       = paramDerivatives(c) ? 1 : 0;
     cfg_.device            = paramDevice(c);
+    cfg_.window_type       = paramWindowType(c);
     dcDetection_                    = paramDcDetection(c);
     dc_.min_dc_length_s             = paramMinDcLength(c);
     dc_.max_dc_increment            = paramMaxDcIncrement(c);
@@ -56,6 +62,8 @@ bool MfccNode::setParameter(const std::string& name, const std::string& value) {
         cfg_.derivatives = paramDerivatives(value) ? 1 : 0;
     else if (paramDevice.match(name))
         cfg_.device = paramDevice(value);
+    else if (paramWindowType.match(name))
+        cfg_.window_type = paramWindowType(value);
     else if (paramDcDetection.match(name))
         dcDetection_ = paramDcDetection(value);
     else if (paramMinDcLength.match(name))

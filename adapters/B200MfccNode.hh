@@ -30,6 +30,8 @@ public:
     static const Core::ParameterInt   paramNrOutputs;        // signal-cosine-transform nr-outputs
     static const Core::ParameterBool  paramDerivatives;      // append delta / delta-delta
     static const Core::ParameterInt   paramDevice;
+    static const Core::Choice          choiceWindowType;          // signal-window type
+    static const Core::ParameterChoice paramWindowType;
     static const Core::ParameterBool  paramDcDetection;           // signal-dc-detection in front of the chain
     static const Core::ParameterFloat paramMinDcLength;           // its parameters, named as in DcDetection.cc:231-241
     static const Core::ParameterFloat paramMaxDcIncrement;

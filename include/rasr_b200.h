@@ -71,7 +71,18 @@ typedef struct {
     int    n_cepstra;         /* signal-cosine-transform nr-outputs= */
     int    derivatives;       /* 0: static cepstra; 1: static || delta || delta-delta */
     int    device;            /* CUDA device ordinal */
+    int    window_type;       /* rb_window_type; signal-window "type" (src/Signal/WindowFunction.cc:25-33) */
 } rb_frontend_cfg;
+
+/* window functions of src/Signal/WindowFunction.cc:62-132; 0 = the default of the reference and of mfcc.flow */
+enum rb_window_type {
+    RB_WINDOW_HAMMING = 0,
+    RB_WINDOW_RECTANGULAR = 1,
+    RB_WINDOW_HANNING = 2,
+    RB_WINDOW_PERIODIC_HANNING = 3,
+    RB_WINDOW_BARTLETT = 4,
+    RB_WINDOW_BLACKMAN = 5
+};
 
 typedef struct {
     int win_length; /* samples */

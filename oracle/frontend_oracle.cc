@@ -263,15 +263,38 @@ struct DcDetection {
 };
 
 /* ------------------------------------------------------------------ window function
- * HammingWindowFunction::init src/Signal/WindowFunction.cc:92-101 */
-std::vector<float> hammingWindow(unsigned length) {
+ * {Rectangular,Bartlett,Hamming,Hanning,Blackman}WindowFunction::init src/Signal/WindowFunction.cc:62-132; type
+ * numbering: 0 hamming (the default), 1 rectangular, 2 hanning, 3 periodic-hanning, 4 bartlett, 5 blackman */
+std::vector<float> windowFunction(int type, unsigned length) {
     std::vector<float> w(length, 0.0f);
+    if (type == 1) {
+        std::fill(w.begin(), w.end(), 1.0f);
+        return w;
+    }
     if (length <= 1)
         return w;
+    if (type == 2 || type == 3) {
+        unsigned M = length - (type == 3 ? 0 : 1);
+        for (unsigned n = 0; n <= M / 2; ++n) {
+            w[n] = 0.5 - 0.5 * cos(2.0 * M_PI * n / M);
+            if (M - n < length)
+                w[M - n] = w[n];
+        }
+        return w;
+    }
     unsigned M = length - 1;
-    for (unsigned n = 0; n <= M / 2; ++n)
-        w[n] = w[M - n] = 0.54 - 0.46 * cos(2.0 * M_PI * n / M);
+    for (unsigned n = 0; n <= M / 2; ++n) {
+        if (type == 0)
+            w[n] = w[M - n] = 0.54 - 0.46 * cos(2.0 * M_PI * n / M);
+        else if (type == 4)
+            w[n] = w[M - n] = 2.0 * (float)n / (float)M;
+        else
+            w[n] = w[M - n] = 0.42 - 0.5 * cos(2.0 * M_PI * n / M) + 0.08 * cos(4.0 * M_PI * n / M);
+    }
     return w;
+}
+std::vector<float> hammingWindow(unsigned length) {
+    return windowFunction(0, length);
 }
 
 /* WindowFunction::work src/Signal/WindowFunction.hh:80-94 via Window::transform src/Signal/Window.cc:84-96 */
@@ -579,7 +602,7 @@ extern "C" int orc_frontend_tables(const orc_frontend_cfg* cfg, float* window, i
     MelFilterBank fb = buildMelFilterBank(g.fftOutRate, g.N / 2 + 1, cfg->filter_width);
     int           nb = g.N / 2 + 1;
     if (window) {
-        std::vector<float> w = hammingWindow(g.L);
+        std::vector<float> w = windowFunction(cfg->window_type, g.L);
         std::copy(w.begin(), w.end(), window);
     }
     for (size_t f = 0; f < fb.start.size(); ++f) {
@@ -620,7 +643,7 @@ long mfccImpl(const orc_frontend_cfg* cfg, const orc_dc_cfg* dcCfg, const float*
     MelFilterBank      fb     = buildMelFilterBank(g.fftOutRate, nBins, cfg->filter_width);
     const unsigned     K      = cfg->n_cepstra;
     std::vector<float> dct    = buildDct(K, (unsigned)fb.start.size());
-    std::vector<float> window = hammingWindow(g.L);
+    std::vector<float> window = windowFunction(cfg->window_type, g.L);
 
     /* --- the pull loop of SlidingAlgorithmNode::work (src/Signal/SlidingAlgorithmNode.hh:60-80):
      * try get(); if it fails pull one more pre-emphasised packet; at end of stream flush(). */

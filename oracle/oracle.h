@@ -39,6 +39,8 @@ typedef struct {
     int    derivatives;       /* 0: static cepstra only; 1: static || delta || delta-delta */
     int    use_fma;           /* 1: floating-point contraction as gcc -O2 -march=native does for the
                                  reference's default build; 0: every operation rounded separately */
+    int    window_type;       /* 0 hamming (default), 1 rectangular, 2 hanning, 3 periodic-hanning, 4 bartlett,
+                                 5 blackman (src/Signal/WindowFunction.cc:25-33,62-132) */
 } orc_frontend_cfg;
 
 typedef struct {

@@ -22,6 +22,9 @@ def build(ref=True):
         subprocess.check_call(["make", "-s", "-C", _HERE, "_ref"])
 
 
+WINDOW_TYPES = {"hamming": 0, "rectangular": 1, "hanning": 2, "periodic-hanning": 3, "bartlett": 4, "blackman": 5}
+
+
 class FrontendCfg(C.Structure):
     _fields_ = [
         ("sample_rate", C.c_double),
@@ -33,6 +36,7 @@ class FrontendCfg(C.Structure):
         ("n_cepstra", C.c_int),
         ("derivatives", C.c_int),
         ("use_fma", C.c_int),
+        ("window_type", C.c_int),
     ]
 
 
@@ -87,9 +91,9 @@ def _p(a, t):
 
 
 def frontend_cfg(sample_rate=16000.0, window_length_s=0.025, window_shift_s=0.01, fft_max_input_s=0.025,
-                 filter_width=268.258, alpha=1.0, n_cepstra=13, derivatives=True, use_fma=True):
+                 filter_width=268.258, alpha=1.0, n_cepstra=13, derivatives=True, use_fma=True, window_type="hamming"):
     return FrontendCfg(sample_rate, window_length_s, window_shift_s, fft_max_input_s, filter_width, alpha,
-                       n_cepstra, int(derivatives), int(use_fma))
+                       n_cepstra, int(derivatives), int(use_fma), WINDOW_TYPES[window_type])
 
 
 def geometry(cfg):

@@ -47,7 +47,10 @@ class RasrB200Error(RuntimeError):
 class FrontendCfg(C.Structure):
     _fields_ = [("sample_rate", C.c_double), ("window_length_s", C.c_double), ("window_shift_s", C.c_double),
                 ("fft_max_input_s", C.c_double), ("filter_width", C.c_double), ("preemphasis_alpha", C.c_float),
-                ("n_cepstra", C.c_int), ("derivatives", C.c_int), ("device", C.c_int)]
+                ("n_cepstra", C.c_int), ("derivatives", C.c_int), ("device", C.c_int), ("window_type", C.c_int)]
+
+
+WINDOW_TYPES = {"hamming": 0, "rectangular": 1, "hanning": 2, "periodic-hanning": 3, "bartlett": 4, "blackman": 5}
 
 
 class FrontendGeometry(C.Structure):

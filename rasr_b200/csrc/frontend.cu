@@ -486,12 +486,45 @@ int build_filterbank(rb_frontend* h) {
 }
 
 int build_tables(rb_frontend* h) {
-    // Hamming window, symmetric, M = L-1 (WindowFunction.cc:92-101)
+    // window functions of src/Signal/WindowFunction.cc:62-132 (f64 expressions narrowed to f32; symmetric fill)
     h->window.assign(h->L, 0.0f);
-    if (h->L > 1) {
-        const unsigned Mw = h->L - 1;
-        for (unsigned n = 0; n <= Mw / 2; ++n)
-            h->window[n] = h->window[Mw - n] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * n / Mw));
+    const unsigned size = (unsigned)h->L;
+    switch (h->cfg.window_type) {
+        case RB_WINDOW_RECTANGULAR:
+            std::fill(h->window.begin(), h->window.end(), 1.0f);
+            break;
+        case RB_WINDOW_HAMMING:
+        case RB_WINDOW_BARTLETT:
+        case RB_WINDOW_BLACKMAN:
+            if (size > 1) {
+                const unsigned Mw = size - 1;
+                for (unsigned n = 0; n <= Mw / 2; ++n) {
+                    double v;
+                    if (h->cfg.window_type == RB_WINDOW_HAMMING)
+                        v = 0.54 - 0.46 * cos(2.0 * M_PI * n / Mw);
+                    else if (h->cfg.window_type == RB_WINDOW_BARTLETT)
+                        v = 2.0 * (float)n / (float)Mw;
+                    else
+                        v = 0.42 - 0.5 * cos(2.0 * M_PI * n / Mw) + 0.08 * cos(4.0 * M_PI * n / Mw);
+                    h->window[n] = h->window[Mw - n] = (float)v;
+                }
+            }
+            break;
+        case RB_WINDOW_HANNING:
+        case RB_WINDOW_PERIODIC_HANNING:
+            if (size > 1) {
+                const unsigned Mw = size - (h->cfg.window_type == RB_WINDOW_PERIODIC_HANNING ? 0 : 1);
+                for (unsigned n = 0; n <= Mw / 2; ++n) {
+                    h->window[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / Mw));
+                    if (Mw - n < size)
+                        h->window[Mw - n] = h->window[n];
+                }
+            }
+            break;
+        default:
+            rb::set_error("unknown window type %d (the Kaiser window needs the reference's optional NR module)",
+                          h->cfg.window_type);
+            return RB_ERR_UNSUPPORTED;
     }
     RB_CHECK(build_filterbank(h));
     // DCT-II, even about N-1/2 (CosineTransform.cc:62-74)
@@ -1115,6 +1148,7 @@ extern "C" void rb_frontend_default_cfg(rb_frontend_cfg* cfg) {
     cfg->n_cepstra         = 13;
     cfg->derivatives       = 1;
     cfg->device            = 0;
+    cfg->window_type       = RB_WINDOW_HAMMING;
 }
 
 extern "C" int rb_frontend_create(const rb_frontend_cfg* cfg, rb_frontend** out) {

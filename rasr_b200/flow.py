@@ -28,10 +28,12 @@ class FrontEnd:
     """Thin RAII wrapper of rb_frontend_* (one handle = one node instance = one CUDA stream)."""
 
     def __init__(self, sample_rate=16000.0, window_length=0.025, window_shift=0.01, fft_max_input=0.025,
-                 filter_width=268.258, alpha=1.0, n_cepstra=13, derivatives=True, device=0):
+                 filter_width=268.258, alpha=1.0, n_cepstra=13, derivatives=True, device=0, window_type="hamming"):
         L = capi.lib()
+        if window_type not in capi.WINDOW_TYPES:
+            raise capi.RasrB200Error(-4, "unknown window type '%s'" % window_type)
         self.cfg = capi.FrontendCfg(sample_rate, window_length, window_shift, fft_max_input, filter_width, alpha,
-                                    n_cepstra, int(derivatives), device)
+                                    n_cepstra, int(derivatives), device, capi.WINDOW_TYPES[window_type])
         self._h = C.c_void_p()
         capi.check(L.rb_frontend_create(C.byref(self.cfg), C.byref(self._h)))
         g = capi.FrontendGeometry()
@@ -202,7 +204,7 @@ class MfccNode:
     PARAMS = {"alpha": ("alpha", float), "length": ("window_length", float), "shift": ("window_shift", float),
               "maximum-input-size": ("fft_max_input", float), "filter-width": ("filter_width", float),
               "nr-outputs": ("n_cepstra", int), "derivatives": ("derivatives", lambda v: v in ("true", "1", "yes")),
-              "device": ("device", int)}
+              "device": ("device", int), "window-type": ("window_type", str)}
     # signal-dc-detection in front of the chain, parameter names of src/Signal/DcDetection.cc:231-241
     DC_PARAMS = {"min-dc-length": ("min_dc_length_s", float), "max-dc-increment": ("max_dc_increment", float),
                  "min-non-dc-segment-length": ("min_non_dc_segment_length_s", float),

@@ -185,3 +185,24 @@ def test_s16_pcm_input_equals_float_input():
     assert np.array_equal(multi["feats"], want["feats"])
     with pytest.raises(Exception):
         fe.process_s16(pcm, offs, n_channels=3, track=3)
+
+
+@pytest.mark.parametrize("wt", ["rectangular", "hanning", "periodic-hanning", "bartlett", "blackman"])
+def test_other_window_types(oracle, wt):
+    """signal-window type= (src/Signal/WindowFunction.cc:25-33): the table is bit-identical to the oracle's, the
+    features follow at the front-end's tolerance"""
+    x = synth.utterance(20000, seed=14)
+    fe = flow.FrontEnd(window_type=wt)
+    ocfg = oracle.frontend_cfg(window_type=wt)
+    assert np.array_equal(fe.tables()["window"], oracle.tables(ocfg)["window"])
+    r, o = fe.process(x), oracle.mfcc(ocfg, x)
+    assert r["feats"].shape == o["feats"].shape and rel_err(r["feats"], o["feats"]) < RTOL
+    assert not np.array_equal(r["feats"], flow.FrontEnd().process(x)["feats"])
+    node = flow.MfccNode()
+    assert node.set_parameter("window-type", wt) and node.configure({"sample-rate": "16000"})
+
+
+def test_unknown_window_type_is_rejected():
+    from rasr_b200 import capi
+    with pytest.raises(capi.RasrB200Error):
+        flow.FrontEnd(window_type="kaiser")

@@ -159,3 +159,24 @@ def test_golden_fixture(oracle):
     r = oracle.mfcc(oracle.frontend_cfg(), x)
     assert np.array_equal(r["feats"], g["feats"])
     assert np.array_equal(r["t_start"], g["t_start"]) and np.array_equal(r["t_end"], g["t_end"])
+
+
+@pytest.mark.parametrize("wt", ["hamming", "rectangular", "hanning", "periodic-hanning", "bartlett", "blackman"])
+def test_window_functions(oracle, wt):
+    """the window types of src/Signal/WindowFunction.cc:62-132 against their textbook definitions (numpy, f64) and
+    the properties the reference's fill order implies"""
+    L = 400
+    w = oracle.tables(oracle.frontend_cfg(window_type=wt))["window"]
+    n = np.arange(L, dtype=np.float64)
+    want = {"hamming": 0.54 - 0.46 * np.cos(2 * np.pi * n / (L - 1)), "rectangular": np.ones(L),
+            "hanning": 0.5 - 0.5 * np.cos(2 * np.pi * n / (L - 1)), "periodic-hanning": 0.5 - 0.5 * np.cos(2 * np.pi * n / L),
+            "bartlett": 1 - np.abs(2 * n / (L - 1) - 1),
+            "blackman": 0.42 - 0.5 * np.cos(2 * np.pi * n / (L - 1)) + 0.08 * np.cos(4 * np.pi * n / (L - 1))}[wt]
+    assert w.dtype == np.float32 and w.shape == (L,)
+    assert np.abs(w - want).max() < 2e-7
+    if wt != "periodic-hanning":
+        assert np.array_equal(w, w[::-1])            # filled symmetrically, bit for bit
+    else:
+        assert np.array_equal(w[1:], w[1:][::-1]) and w[0] == 0.0 and w[L // 2] == 1.0
+    if wt in ("hanning", "bartlett"):
+        assert w[0] == 0.0 and w[-1] == 0.0
