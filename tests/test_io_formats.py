@@ -259,3 +259,39 @@ def test_directory_and_bundle_archives(tmp_path):
     (tmp_path / "junk.bin").write_bytes(b"something else")
     with pytest.raises(cache.ArchiveError):
         cache.open_archive(tmp_path / "junk.bin")
+
+
+def test_file_archive_against_a_dict_model(tmp_path):
+    """random sequences of writes and overwrites (some compressed, some entries later removed by overwriting): after
+    reopening -- through the info table and through the entry scan -- the archive holds exactly what a dict holds"""
+    from hypothesis import given, settings, strategies as st
+    from rasr_b200 import cache
+    names = st.sampled_from(["a", "b", "seg/1", "seg/2", "corpus/rec/long-name-0001", "x.attribs"])
+    ops = st.lists(st.tuples(names, st.binary(min_size=0, max_size=300), st.booleans()), min_size=1, max_size=25)
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None)
+    @given(ops)
+    def run(sequence):
+        counter[0] += 1
+        path = tmp_path / ("m%d.cache" % counter[0])
+        model = {}
+        with cache.FileArchive(path, "w", allow_overwrite=True) as a:
+            for name, data, comp in sequence:
+                a.write(name, data, compress=comp)
+                model[name] = data
+        for flag in (1, 0):
+            raw = bytearray(path.read_bytes())
+            raw[8] = flag
+            path.write_bytes(bytes(raw))
+            with cache.FileArchive(path) as a:
+                assert sorted(a.names()) == sorted(model)
+                for name, data in model.items():
+                    assert a.read(name) == data
+        # appending to an existing archive keeps what is there
+        with cache.FileArchive(path, "w", allow_overwrite=True) as a:
+            a.write("late", b"entry")
+        with cache.FileArchive(path) as a:
+            assert a.read("late") == b"entry" and all(a.read(n) == d for n, d in model.items())
+
+    run()
