@@ -129,6 +129,62 @@ def cpu_baseline_gmm(seconds=12.0):
                 sample="first %d of the 100000 C2 frames, all 256 mixtures, %d threads over frame ranges" % (n, cores))
 
 
+def cpu_baseline_frontend(seconds=10.0):
+    """Oracle port of the Flow MFCC chain (mfcc.flow + derivationWithRegression.flow), one utterance per task on all host
+    cores -- the reference's own model of parallelism (one process per corpus partition)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import pyoracle as o
+    from rasr_b200 import synth
+
+    o.build(ref=False)
+    cores = os.cpu_count() or 1
+    cfg = o.frontend_cfg()
+    utt = [synth.utterance(160240, seed=3000 + u) for u in range(cores)]
+    t = time.perf_counter()
+    o.mfcc(cfg, utt[0])
+    per_utt = time.perf_counter() - t
+    rounds = int(max(1, min(400, seconds / max(per_utt, 1e-3))))
+    with ThreadPoolExecutor(cores) as pool:  # the ctypes call releases the GIL
+        t = time.perf_counter()
+        frames = sum(r["feats"].shape[0] for _ in range(rounds) for r in pool.map(lambda x: o.mfcc(cfg, x), utt))
+        dt = time.perf_counter() - t
+    return dict(value=frames / dt, unit=UNIT, cores=cores, kind="port",
+                sample="%d utterances of 1000 frames (%d per core), one utterance per thread" % (rounds * cores, rounds))
+
+
+def cpu_baseline_nn(seconds=10.0):
+    """The reference's Nn CPU path is cblas_sgemm per layer (src/Math/Blas.hh:410-421) with whatever BLAS the system
+    has; here numpy's OpenBLAS sgemm on all host cores, whole-segment batches (the favourable case for the CPU), f32."""
+    from rasr_b200 import synth
+
+    cores = os.cpu_count() or 1
+    net = synth.network()
+    ws = [np.ascontiguousarray(w.T) for w in net["weights"]]
+
+    def forward(x):
+        h = x
+        for l, (w, b) in enumerate(zip(ws, net["biases"])):
+            h = h @ w + b
+            if l + 1 < len(ws):
+                h = np.maximum(h, 0.0, out=h) if net["acts"][l] in ("relu", "rectified") else 1.0 / (1.0 + np.exp(-h))
+        return -(h - net["log_prior"])
+
+    x = synth.features(2048, 429, seed=4, scale=1.0)
+    forward(x[:256])
+    t = time.perf_counter()
+    forward(x)
+    rate = x.shape[0] / (time.perf_counter() - t)
+    n = int(max(2048, min(65536, rate * seconds)))
+    x = synth.features(n, 429, seed=5, scale=1.0)
+    t = time.perf_counter()
+    for a in range(0, n, 4096):
+        forward(x[a:a + 4096])
+    dt = time.perf_counter() - t
+    return dict(value=n / dt, unit=UNIT, cores=cores, kind="port",
+                sample="%d frames in batches of 4096 through numpy / OpenBLAS sgemm (f32), all cores" % n)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -512,9 +568,10 @@ def main():
         line["config"]["host_numa_node"] = numa
         if variants:
             line["variants"] = variants
-        if world == 1 and not args.no_cpu_baseline and wl == "gmm":
+        if world == 1 and not args.no_cpu_baseline and wl in ("gmm", "frontend", "nn"):
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core, not one NUMA node
-            line["cpu_baseline"] = cpu_baseline_gmm()
+            line["cpu_baseline"] = {"gmm": cpu_baseline_gmm, "frontend": cpu_baseline_frontend,
+                                    "nn": cpu_baseline_nn}[wl]()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
