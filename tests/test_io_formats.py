@@ -295,3 +295,27 @@ def test_file_archive_against_a_dict_model(tmp_path):
             assert a.read("late") == b"entry" and all(a.read(n) == d for n, d in model.items())
 
     run()
+
+
+def test_matrix_formats_round_trip_any_finite_value(tmp_path):
+    """property: every finite f32 / f64 (denormals, signed zeros, extremes) survives both formats bit for bit -- the
+    xml writer prints 20 significant digits like formats().write(filename, parameters, 20)"""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+    counter = [0]
+
+    @settings(max_examples=30, deadline=None)
+    @given(hnp.arrays(np.float32, hnp.array_shapes(min_dims=2, max_dims=2, max_side=6),
+                      elements=st.floats(width=32, allow_nan=False, allow_infinity=False)),
+           hnp.arrays(np.float64, st.integers(0, 9), elements=st.floats(allow_nan=False, allow_infinity=False)))
+    def run(m, v):
+        counter[0] += 1
+        for fmt in ("bin:", "xml:"):
+            pm, pv = fmt + str(tmp_path / ("m%d" % counter[0])), fmt + str(tmp_path / ("v%d" % counter[0]))
+            rio.write_matrix(pm, m)
+            rio.write_vector(pv, v)
+            gm, gv = rio.read_matrix(pm), rio.read_vector(pv, np.float64)
+            assert gm.shape == m.shape and gm.tobytes() == m.tobytes()
+            assert gv.shape == v.shape and gv.tobytes() == v.tobytes()
+
+    run()
