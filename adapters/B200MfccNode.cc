@@ -10,10 +10,10 @@ const Core::ParameterFloat MfccNode::paramFilterWidth("filter-width", "mel filte
 const Core::ParameterInt   MfccNode::paramNrOutputs("nr-outputs", "number of cepstral coefficients", 13, 1);
 const Core::ParameterBool  MfccNode::paramDerivatives("derivatives", "append first and second order regression", true);
 const Core::ParameterInt   MfccNode::paramDevice("device", "CUDA device ordinal", 0, 0);
-// signal-window "type" (src/Signal/WindowFunction.cc:25-33); the Kaiser window (optional NR module) is not offered
+// signal-window "type" (src/Signal/WindowFunction.cc:25-33)
 const Core::Choice          MfccNode::choiceWindowType("hamming", RB_WINDOW_HAMMING, "rectangular", RB_WINDOW_RECTANGULAR, "hanning", RB_WINDOW_HANNING,
                                                         "periodic-hanning", RB_WINDOW_PERIODIC_HANNING, "bartlett", RB_WINDOW_BARTLETT,
-                                                        "blackman", RB_WINDOW_BLACKMAN, Core::Choice::endMark());
+                                                        "blackman", RB_WINDOW_BLACKMAN, "kaiser", RB_WINDOW_KAISER, Core::Choice::endMark());
 const Core::ParameterChoice MfccNode::paramWindowType("window-type", &choiceWindowType, "type of window", RB_WINDOW_HAMMING);
 // signal-dc-detection in front of the chain (src/Signal/DcDetection.cc:231-241; values of samples.flow:34-35)
 const Core::ParameterBool  MfccNode::paramDcDetection("dc-detection", "discard DC stretches of the input like signal-dc-detection", false);

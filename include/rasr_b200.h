@@ -81,7 +81,8 @@ enum rb_window_type {
     RB_WINDOW_HANNING = 2,
     RB_WINDOW_PERIODIC_HANNING = 3,
     RB_WINDOW_BARTLETT = 4,
-    RB_WINDOW_BLACKMAN = 5
+    RB_WINDOW_BLACKMAN = 5,
+    RB_WINDOW_KAISER = 6 /* beta = 0 as WindowFunction::create builds it (no node parameter sets beta): all ones */
 };
 
 typedef struct {

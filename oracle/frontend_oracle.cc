@@ -264,7 +264,23 @@ struct DcDetection {
 
 /* ------------------------------------------------------------------ window function
  * {Rectangular,Bartlett,Hamming,Hanning,Blackman}WindowFunction::init src/Signal/WindowFunction.cc:62-132; type
- * numbering: 0 hamming (the default), 1 rectangular, 2 hanning, 3 periodic-hanning, 4 bartlett, 5 blackman */
+ * numbering: 0 hamming (the default), 1 rectangular, 2 hanning, 3 periodic-hanning, 4 bartlett, 5 blackman,
+ * 6 kaiser (KaiserWindowFunction.cc:22-33 with Math::Nr::bessi0, src/Math/Nr/BesselFunctions.cc:22-37; beta is 0:
+ * WindowFunction::create constructs it with the default and nothing calls setBeta) */
+double nrBessi0(double x) {
+    double ax, ans, y;
+    if ((ax = fabs(x)) < 3.75) {
+        y = x / 3.75;
+        y *= y;
+        ans = 1.0 + y * (3.5156229 + y * (3.0899424 + y * (1.2067492 + y * (0.2659732 + y * (0.360768e-1 + y * 0.45813e-2)))));
+    }
+    else {
+        y   = 3.75 / ax;
+        ans = (exp(ax) / sqrt(ax)) *
+              (0.39894228 + y * (0.1328592e-1 + y * (0.225319e-2 + y * (-0.157565e-2 + y * (0.916281e-2 + y * (-0.2057706e-1 + y * (0.2635537e-1 + y * (-0.1647633e-1 + y * 0.392377e-2))))))));
+    }
+    return ans;
+}
 std::vector<float> windowFunction(int type, unsigned length) {
     std::vector<float> w(length, 0.0f);
     if (type == 1) {
@@ -283,6 +299,12 @@ std::vector<float> windowFunction(int type, unsigned length) {
         return w;
     }
     unsigned M = length - 1;
+    if (type == 6) {
+        const double beta = 0.0;
+        for (unsigned n = 0; n <= M / 2; ++n)
+            w[n] = w[M - n] = nrBessi0(beta * sqrt(1.0 - ((double)n / (M / 2.0) - 1.0) * ((double)n / (M / 2.0) - 1.0))) / nrBessi0(beta);
+        return w;
+    }
     for (unsigned n = 0; n <= M / 2; ++n) {
         if (type == 0)
             w[n] = w[M - n] = 0.54 - 0.46 * cos(2.0 * M_PI * n / M);

@@ -22,7 +22,7 @@ def build(ref=True):
         subprocess.check_call(["make", "-s", "-C", _HERE, "_ref"])
 
 
-WINDOW_TYPES = {"hamming": 0, "rectangular": 1, "hanning": 2, "periodic-hanning": 3, "bartlett": 4, "blackman": 5}
+WINDOW_TYPES = {"hamming": 0, "rectangular": 1, "hanning": 2, "periodic-hanning": 3, "bartlett": 4, "blackman": 5, "kaiser": 6}
 
 
 class FrontendCfg(C.Structure):

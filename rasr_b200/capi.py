@@ -50,7 +50,7 @@ class FrontendCfg(C.Structure):
                 ("n_cepstra", C.c_int), ("derivatives", C.c_int), ("device", C.c_int), ("window_type", C.c_int)]
 
 
-WINDOW_TYPES = {"hamming": 0, "rectangular": 1, "hanning": 2, "periodic-hanning": 3, "bartlett": 4, "blackman": 5}
+WINDOW_TYPES = {"hamming": 0, "rectangular": 1, "hanning": 2, "periodic-hanning": 3, "bartlett": 4, "blackman": 5, "kaiser": 6}
 
 
 class FrontendGeometry(C.Structure):

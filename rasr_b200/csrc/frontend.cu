@@ -521,9 +521,32 @@ int build_tables(rb_frontend* h) {
                 }
             }
             break;
+        case RB_WINDOW_KAISER:
+            // KaiserWindowFunction::init (src/Signal/KaiserWindowFunction.cc:22-33) with Math::Nr::bessi0
+            // (src/Math/Nr/BesselFunctions.cc:22-37).  WindowFunction::create builds it with beta = 0 and no node
+            // parameter reaches setBeta, so the window the reference produces is bessi0(0) / bessi0(0) everywhere
+            if (size > 1) {
+                const double   beta = 0.0;
+                const unsigned Mw   = size - 1;
+                auto bessi0 = [](double x) {
+                    const double ax = fabs(x);
+                    if (ax < 3.75) {
+                        double y = x / 3.75;
+                        y *= y;
+                        return 1.0 + y * (3.5156229 + y * (3.0899424 + y * (1.2067492 + y * (0.2659732 + y * (0.360768e-1 + y * 0.45813e-2)))));
+                    }
+                    const double y = 3.75 / ax;
+                    return (exp(ax) / sqrt(ax)) *
+                           (0.39894228 + y * (0.1328592e-1 + y * (0.225319e-2 + y * (-0.157565e-2 + y * (0.916281e-2 + y * (-0.2057706e-1 + y * (0.2635537e-1 + y * (-0.1647633e-1 + y * 0.392377e-2))))))));
+                };
+                for (unsigned n = 0; n <= Mw / 2; ++n) {
+                    const double u = (double)n / (Mw / 2.0) - 1.0;
+                    h->window[n] = h->window[Mw - n] = (float)(bessi0(beta * sqrt(1.0 - u * u)) / bessi0(beta));
+                }
+            }
+            break;
         default:
-            rb::set_error("unknown window type %d (the Kaiser window needs the reference's optional NR module)",
-                          h->cfg.window_type);
+            rb::set_error("unknown window type %d", h->cfg.window_type);
             return RB_ERR_UNSUPPORTED;
     }
     RB_CHECK(build_filterbank(h));

@@ -161,14 +161,15 @@ def test_golden_fixture(oracle):
     assert np.array_equal(r["t_start"], g["t_start"]) and np.array_equal(r["t_end"], g["t_end"])
 
 
-@pytest.mark.parametrize("wt", ["hamming", "rectangular", "hanning", "periodic-hanning", "bartlett", "blackman"])
+@pytest.mark.parametrize("wt", ["hamming", "rectangular", "hanning", "periodic-hanning", "bartlett", "blackman", "kaiser"])
 def test_window_functions(oracle, wt):
     """the window types of src/Signal/WindowFunction.cc:62-132 against their textbook definitions (numpy, f64) and
     the properties the reference's fill order implies"""
     L = 400
     w = oracle.tables(oracle.frontend_cfg(window_type=wt))["window"]
     n = np.arange(L, dtype=np.float64)
-    want = {"hamming": 0.54 - 0.46 * np.cos(2 * np.pi * n / (L - 1)), "rectangular": np.ones(L),
+    # kaiser: WindowFunction::create builds it with beta = 0 and nothing sets beta: I0(0) / I0(0) = 1 everywhere
+    want = {"hamming": 0.54 - 0.46 * np.cos(2 * np.pi * n / (L - 1)), "rectangular": np.ones(L), "kaiser": np.kaiser(L, 0.0),
             "hanning": 0.5 - 0.5 * np.cos(2 * np.pi * n / (L - 1)), "periodic-hanning": 0.5 - 0.5 * np.cos(2 * np.pi * n / L),
             "bartlett": 1 - np.abs(2 * n / (L - 1) - 1),
             "blackman": 0.42 - 0.5 * np.cos(2 * np.pi * n / (L - 1)) + 0.08 * np.cos(4 * np.pi * n / (L - 1))}[wt]
