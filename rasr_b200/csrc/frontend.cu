@@ -1265,6 +1265,7 @@ extern "C" void rb_frontend_destroy(rb_frontend* h) {
     if (!h)
         return;
     cudaSetDevice(h->dev.ordinal);
+    rb_pipeline_forget(h);  // scratch buffers of the rb_pipeline_* calls that used this handle
     delete h;
 }
 

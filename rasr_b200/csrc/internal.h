@@ -6,6 +6,8 @@ struct rb_frontend;
 struct rb_gmm;
 
 cudaStream_t   rb_frontend_stream(const rb_frontend* h);
+// pipeline.cu: drop the per-handle scratch buffers of the host-buffer pipelines (rb_frontend_destroy calls it)
+void           rb_pipeline_forget(const rb_frontend* fe);
 // host-buffer pipelines: upload the per-call tile tables on this (H2D) stream; nullptr: on the kernel stream
 void           rb_frontend_set_upload_stream(rb_frontend* h, cudaStream_t s);
 rb::DeviceInfo rb_frontend_device(const rb_frontend* h);

@@ -10,9 +10,13 @@ struct Scratch {
     rb::DevBuf<int16_t> pcm;
     rb::CopyStreams     copy;
 };
-// one scratch set per front-end handle would be cleaner; pipelines are few, so key by handle
-Scratch& scratch_for(const rb_frontend* fe) {
+// one scratch set per front-end handle (and calling thread), released when the handle is destroyed
+std::vector<std::pair<const rb_frontend*, Scratch*>>& scratch_table() {
     static thread_local std::vector<std::pair<const rb_frontend*, Scratch*>> table;
+    return table;
+}
+Scratch& scratch_for(const rb_frontend* fe) {
+    auto& table = scratch_table();
     for (auto& e : table)
         if (e.first == fe)
             return *e.second;
@@ -20,6 +24,17 @@ Scratch& scratch_for(const rb_frontend* fe) {
     return *table.back().second;
 }
 }  // namespace
+
+// called by rb_frontend_destroy: the device buffers and copy streams of the pipelines that used this handle go with it
+void rb_pipeline_forget(const rb_frontend* fe) {
+    auto& table = scratch_table();
+    for (size_t i = 0; i < table.size(); ++i)
+        if (table[i].first == fe) {
+            delete table[i].second;
+            table.erase(table.begin() + i);
+            return;
+        }
+}
 
 extern "C" int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, const int64_t* offsets,
                                      int n_utt, float* d_feats, float* d_scores, void* stream) {
