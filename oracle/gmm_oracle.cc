@@ -9,6 +9,7 @@
  * (gcc -O2 -march=native, -ffp-contract=fast) applies to `s += x * x`.
  */
 #include "oracle.h"
+#include "std_sort_restated.h"
 
 #include <immintrin.h>
 
@@ -582,6 +583,115 @@ extern "C" int orc_gmm_preselect_float(const orc_mixture_set* ms, const float* f
         }
     }
     free(x);
+    return 0;
+}
+
+/* ---- test hooks for oracle/std_sort_restated.h: sort (key, index) pairs by key only, with the real std::sort and with
+ * the restatement; the resulting index permutations must be identical */
+extern "C" void orc_sort_pairs(const int32_t* keys, int n, int32_t* perm, int restated) {
+    std::vector<std::pair<int32_t, int32_t>> v(n);
+    for (int i = 0; i < n; ++i)
+        v[i] = std::make_pair(keys[i], i);
+    auto less = [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first < b.first; };
+    if (restated)
+        stdsort::sort(v.data(), v.data() + n, less);
+    else
+        std::sort(v.begin(), v.end(), less);
+    for (int i = 0; i < n; ++i)
+        perm[i] = v[i].second;
+}
+
+/* Mm::BatchPreselectionIntFeatureScorer ("preselection-batch-int", src/Mm/BatchFeatureScorer.cc:514-577) with
+ * Mm::DensityClustering<u8, s32>: like the float variant on the quantised means and features -- s32 distances
+ * (unrolledVectorDistance<u8, s32>), cluster means truncated back to u8 (the f64 centroid is assigned to a u8),
+ * no back-off score: a mixture without a selected density scores (f32)INT_MAX / scale.  The cluster choice uses the
+ * real std::sort (ties!).  cluster_of [n_densities] is an optional output. */
+extern "C" int orc_gmm_preselect_int(const orc_mixture_set* ms, const float* feats, long T, float* scores, int clusters,
+                                     int select, int iterations, uint32_t* cluster_of, int restated_sort) {
+    BatchInt s;
+    int      rc = s.init(*ms);
+    if (rc)
+        return rc;
+    const unsigned dim = s.padded, nDens = s.nDens, nClusters = std::min<unsigned>((unsigned)clusters, nDens);
+    if ((unsigned)select > nClusters)
+        return -4;
+    auto distance = [dim](const uint8_t* a, const uint8_t* b) {
+        int32_t score = 0;
+        for (unsigned d = 0; d < dim; ++d) {
+            int32_t df = (int32_t)a[d] - (int32_t)b[d];
+            score += df * df;
+        }
+        return score;
+    };
+    std::vector<uint8_t>  clusterMeans((size_t)nClusters * dim);
+    std::vector<unsigned> clusterOf(nDens, 0);
+    std::set<unsigned>    used;
+    srand(1);
+    for (unsigned c = 0; c < nClusters; ++c) {
+        unsigned pick = 0;
+        do {
+            pick = rand() % nDens;
+        } while (used.count(pick));
+        used.insert(pick);
+        std::memcpy(&clusterMeans[(size_t)c * dim], s.means + (size_t)pick * dim, dim);
+    }
+    for (int it = 0; it < iterations; ++it) {
+        std::vector<std::vector<unsigned>> assigned(nClusters);
+        for (unsigned dns = 0; dns < nDens; ++dns) {
+            int32_t  best = 2147483647;
+            unsigned bc   = 0;
+            for (unsigned c = 0; c < nClusters; ++c) {
+                int32_t dist = distance(&clusterMeans[(size_t)c * dim], s.means + (size_t)dns * dim);
+                if (dist < best) {
+                    best = dist;
+                    bc   = c;
+                }
+            }
+            clusterOf[dns] = bc;
+            assigned[bc].push_back(dns);
+        }
+        for (unsigned c = 0; c < nClusters; ++c) {
+            if (assigned[c].empty())
+                continue;
+            std::vector<double> sums(dim, 0.0);
+            for (unsigned a : assigned[c])
+                for (unsigned d = 0; d < dim; ++d)
+                    sums[d] += s.means[(size_t)a * dim + d];
+            for (unsigned d = 0; d < dim; ++d)
+                clusterMeans[(size_t)c * dim + d] = (uint8_t)(sums[d] / (double)assigned[c].size());
+        }
+    }
+    if (cluster_of)
+        std::copy(clusterOf.begin(), clusterOf.end(), cluster_of);
+    std::vector<uint8_t>                     x(dim);
+    std::vector<std::pair<int32_t, unsigned>> byDistance(nClusters);
+    std::vector<char>                        active(nClusters);
+    auto less = [](const std::pair<int32_t, unsigned>& a, const std::pair<int32_t, unsigned>& b) { return a.first < b.first; };
+    for (long t = 0; t < T; ++t) {
+        std::fill(x.begin(), x.end(), 0);
+        for (unsigned d = 0; d < s.dim; ++d)
+            x[d] = BatchInt::quantize(feats[(size_t)t * s.dim + d] * s.variance[d]);
+        for (unsigned c = 0; c < nClusters; ++c)
+            byDistance[c] = std::make_pair(distance(x.data(), &clusterMeans[(size_t)c * dim]), c);
+        if (restated_sort)
+            stdsort::sort(byDistance.data(), byDistance.data() + nClusters, less);
+        else
+            std::sort(byDistance.begin(), byDistance.end(), less);
+        std::fill(active.begin(), active.end(), 0);
+        for (unsigned i = 0; i < (unsigned)select; ++i)
+            active[byDistance[i].second] = 1;
+        for (unsigned m = 0; m < s.nMix; ++m) {
+            int32_t best = 2147483647;
+            for (unsigned dns = s.offsets[m]; dns < s.offsets[m + 1]; ++dns) {
+                if (!active[clusterOf[dns]])
+                    continue;
+                int32_t tmp = distance(s.means + (size_t)dns * dim, x.data()) + s.consts[dns];
+                if (tmp < best)
+                    best = tmp;
+            }
+            scores[(size_t)t * s.nMix + m] = static_cast<float>(best) / s.scale_;
+        }
+    }
     return 0;
 }
 

@@ -125,6 +125,13 @@ int orc_gmm_batch_int_model(const orc_mixture_set* ms, uint8_t* means, int32_t* 
 int orc_gmm_preselect_float(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma,
                             int clusters, int select, int iterations, float backoff, uint32_t* cluster_of,
                             float* cluster_means, int* n_clusters);
+/* Mm::BatchPreselectionIntFeatureScorer ("preselection-batch-int", src/Mm/BatchFeatureScorer.cc:514-577).  Checker for
+ * a kernel that is not built yet: restated_sort != 0 picks the clusters with oracle/std_sort_restated.h
+ * instead of std::sort -- the two must agree. */
+int orc_gmm_preselect_int(const orc_mixture_set* ms, const float* feats, long T, float* scores, int clusters, int select,
+                          int iterations, uint32_t* cluster_of, int restated_sort);
+/* (key, index) pairs sorted by key only: index permutation of std::sort (restated = 0) / of the restatement */
+void orc_sort_pairs(const int32_t* keys, int n, int32_t* perm, int restated);
 int orc_gmm_batch_float_mt(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma,
                            int n_threads);
 

@@ -241,6 +241,26 @@ def gmm_preselect_float(ms, feats, use_fma=True, clusters=256, select=32, iterat
     return scores, cluster_of, means[:n.value]
 
 
+def gmm_preselect_int(ms, feats, clusters=256, select=32, iterations=5, restated_sort=False):
+    feats = np.ascontiguousarray(feats, np.float32)
+    T = feats.shape[0]
+    scores = np.zeros((T, ms.n_mixtures), np.float32)
+    cluster_of = np.zeros(int(ms.c.mix_offsets[ms.n_mixtures]), np.uint32)
+    rc = lib().orc_gmm_preselect_int(C.byref(ms.c), _p(feats, C.c_float), C.c_long(T), _p(scores, C.c_float),
+                                     int(clusters), int(select), int(iterations), _p(cluster_of, C.c_uint32),
+                                     int(restated_sort))
+    if rc:
+        raise RuntimeError("orc_gmm_preselect_int failed: %d" % rc)
+    return scores, cluster_of
+
+
+def sort_pairs(keys, restated):
+    keys = np.ascontiguousarray(keys, np.int32)
+    perm = np.zeros(keys.size, np.int32)
+    lib().orc_sort_pairs(_p(keys, C.c_int32), int(keys.size), _p(perm, C.c_int32), int(restated))
+    return perm
+
+
 def gmm_batch_int(ms, feats, threads=1):
     """Mm::BatchIntFeatureScorer ("batch-diagonal-maximum-int"): dense scores [T x nMix]."""
     feats = np.ascontiguousarray(feats, np.float32)

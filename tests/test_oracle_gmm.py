@@ -254,3 +254,43 @@ def test_preselection_oracle_properties(oracle):
     isd = (1 / np.sqrt(msd["variances"][0].astype(np.float32))).astype(np.float32)
     scaled = (msd["means"].astype(np.float32) * isd).astype(np.float32)
     assert (c1 == 0).all() and np.array_equal(m1[0, :39], scaled.astype(np.float64).mean(0).astype(np.float32))
+
+
+def test_std_sort_restatement_matches_libstdcxx(oracle):
+    """oracle/std_sort_restated.h against the real std::sort on (key, index) pairs compared by key only: with ties
+    the resulting index permutation is whatever introsort does, and the restatement has to do the same
+    (Mm::DensityClustering::selectClusters, src/Mm/DensityClustering.tcc:164-189)"""
+    rng = np.random.default_rng(5)
+    cases = [np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(16, np.int32), np.zeros(17, np.int32),
+             np.zeros(256, np.int32), np.arange(300, dtype=np.int32), np.arange(300, dtype=np.int32)[::-1],
+             np.repeat(np.arange(8, dtype=np.int32), 40)]
+    for n in (2, 15, 16, 17, 33, 100, 256, 1000, 4097):
+        for hi in (2, 5, 50, 1 << 30):
+            cases.append(rng.integers(0, hi, n).astype(np.int32))
+    # organ-pipe and sawtooth inputs drive introsort towards its depth limit (heap sort branch)
+    cases.append(np.concatenate([np.arange(2000), np.arange(2000)[::-1]]).astype(np.int32))
+    cases.append((np.arange(5000) % 7).astype(np.int32))
+    for k in cases:
+        want, got = oracle.sort_pairs(k, False), oracle.sort_pairs(k, True)
+        assert np.array_equal(want, got), (k.size, k[:8])
+        assert np.array_equal(np.sort(want), np.arange(k.size)) and (np.diff(k[want]) >= 0).all()
+
+
+def test_preselection_int_oracle_properties(oracle):
+    """Mm::BatchPreselectionIntFeatureScorer (src/Mm/BatchFeatureScorer.cc:514-577): subset minimum of the int scorer"""
+    msd = synth.mixture_set()
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(200, 39)
+    full = oracle.gmm_batch_int(ms, f)
+    sc, cluster_of = oracle.gmm_preselect_int(ms, f)
+    none = np.float32(2147483647) / np.float32(oracle.gmm_batch_int_model(ms)["scale"])
+    hit = sc != none
+    assert cluster_of.max() < 256 and (~hit).mean() < 0.3
+    assert (sc[hit] >= full[hit]).all() and (sc == full).mean() > 0.3
+    # selecting every cluster is the plain int scorer
+    assert np.array_equal(oracle.gmm_preselect_int(ms, f, select=256)[0], full)
+    # the restated sort picks the same clusters as std::sort, ties included (few clusters, coarse u8 distances)
+    for clusters, select in ((256, 32), (64, 8), (16, 3)):
+        a = oracle.gmm_preselect_int(ms, f, clusters=clusters, select=select, restated_sort=False)
+        b = oracle.gmm_preselect_int(ms, f, clusters=clusters, select=select, restated_sort=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
