@@ -222,7 +222,13 @@ typedef enum {
      * to the feature are scored, mixtures left without one get the back-off score.  Reproduces the reference's
      * approximation (same clustering, same per-frame cluster choice, same scores); defaults as in
      * DensityClustering.cc:20-34: 256 clusters, 32 selected, 5 iterations, back-off 40000. */
-    RB_GMM_BATCH_PRESELECT = 5
+    RB_GMM_BATCH_PRESELECT = 5,
+    /* Mm::BatchPreselectionIntFeatureScorer ("preselection-batch-int", src/Mm/BatchFeatureScorer.cc:514-577) with
+     * Mm::DensityClustering<u8, s32>: the same scheme on the u8 model of RB_GMM_BATCH_INT -- s32 distances, centroids
+     * truncated to u8, no back-off score (a mixture without a scored density gets (f32)INT_MAX / scale).  Equal
+     * distances at the selection boundary are resolved like the reference's std::sort (libstdc++ introsort restated,
+     * rasr_b200/csrc/introsort.cuh): bit-identical scores. */
+    RB_GMM_BATCH_PRESELECT_INT = 6
 } rb_gmm_mode;
 
 /* contraction: 1 = fused multiply-add where the reference's default build (gcc -O2 -march=native,
@@ -230,9 +236,11 @@ typedef enum {
 int  rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_weight_scale, float gaussian_scale,
                    int contraction, int device, rb_gmm** out);
 void rb_gmm_destroy(rb_gmm* h);
-/* RB_GMM_BATCH_PRESELECT only: rebuild the clustering with other parameters (density-clustering.clusters,
- * .select-clusters, .iterations, .backoff-score) / read it back: cluster_of_density [n_densities] in mixture order,
- * cluster_means [n_clusters * padded dimension] (padded = dim rounded up to 8); any pointer may be NULL */
+/* RB_GMM_BATCH_PRESELECT / _PRESELECT_INT only: rebuild the clustering with other parameters
+ * (density-clustering.clusters, .select-clusters, .iterations, .backoff-score; the int variant ignores the back-off
+ * score) / read it back: cluster_of_density [n_densities] in mixture order, cluster_means [n_clusters * padded
+ * dimension] (padded = dim rounded up to 8; int variant: rounded up to 16, the u8 centroids as f32); any pointer may
+ * be NULL */
 int  rb_gmm_configure_preselection(rb_gmm* h, int clusters, int select, int iterations, float backoff_score);
 int  rb_gmm_get_clustering(const rb_gmm* h, uint32_t* cluster_of_density, float* cluster_means, int* n_clusters);
 int  rb_gmm_n_mixtures(const rb_gmm* h);
@@ -386,6 +394,9 @@ int rb_pipeline_search(rb_frontend* fe, rb_gmm* gmm, rb_search* ls, const void* 
  * ===================================================================================== */
 /* host-only test hook: the first n values of glibc's rand() after srand(seed), as restated for the clustering */
 void rb_test_glibc_rand(unsigned seed, int n, int* out);
+/* test hook (host only): (key, index) pairs sorted by key only with csrc/introsort.cuh, the restatement of libstdc++'s
+ * std::sort behind RB_GMM_BATCH_PRESELECT_INT; perm [n] = the index order */
+void rb_test_introsort(const int* keys, int n, int* perm);
 int rb_test_gemm_bf16(const float* a, const float* b, const float* bias, int M, int N, int K, int act,
                       float* d, int device);
 /* times `iters` launches of one GEMM variant (0: 128x256 tile, 1: 256x256 tile) on device-resident

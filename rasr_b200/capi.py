@@ -17,6 +17,7 @@ STATUS = {0: "RB_OK", -1: "RB_ERR_INVALID", -2: "RB_ERR_NO_DEVICE", -3: "RB_ERR_
           -5: "RB_ERR_STATE", -6: "RB_ERR_NOMEM"}
 
 GMM_BATCH_FLOAT, GMM_DIAG_MAX, GMM_DIAG_SUM, GMM_BATCH_TENSOR, GMM_BATCH_INT, GMM_BATCH_PRESELECT = 0, 1, 2, 3, 4, 5
+GMM_BATCH_PRESELECT_INT = 6
 ACT = {"linear": 0, "sigmoid": 1, "relu": 2, "rectified": 2, "softmax": 3, "tanh": 4}
 NN_F32, NN_BF16 = 0, 1
 
@@ -28,7 +29,7 @@ SYMBOLS = [
     "rb_frontend_finish", "rb_frontend_nframes", "rb_frontend_read", "rb_frontend_count_frames",
     "rb_frontend_process", "rb_frontend_process_s16", "rb_frontend_process_dev", "rb_frontend_set_debug", "rb_frontend_read_stages",
     "rb_dc_default_cfg", "rb_frontend_dc_max_frames", "rb_frontend_process_dc", "rb_frontend_dc_runs", "rb_frontend_set_dc_detection",
-    "rb_gmm_configure_preselection", "rb_gmm_get_clustering", "rb_test_glibc_rand",
+    "rb_gmm_configure_preselection", "rb_gmm_get_clustering", "rb_test_glibc_rand", "rb_test_introsort",
     "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_set_class_mapping", "rb_nn_n_emissions", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_s16", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
@@ -146,6 +147,8 @@ def lib():
     L.rb_gmm_get_clustering.argtypes = [vp, vp, vp, vp]
     L.rb_test_glibc_rand.argtypes = [C.c_uint, C.c_int, vp]
     L.rb_test_glibc_rand.restype = None
+    L.rb_test_introsort.argtypes = [vp, C.c_int, vp]
+    L.rb_test_introsort.restype = None
     L.rb_gmm_n_mixtures.argtypes = [vp]
     L.rb_gmm_dim.argtypes = [vp]
     L.rb_gmm_score.argtypes = [vp, vp, C.c_long, vp, vp]

@@ -528,6 +528,15 @@ int  rb_gmm_presel_score(rb_gmm_presel* h, const float* d_feats, long T, float* 
 int  rb_gmm_presel_configure(rb_gmm_presel* h, int clusters, int select, int iterations, float backoff, cudaStream_t s);
 void rb_gmm_presel_clustering(const rb_gmm_presel* h, uint32_t* cluster_of, float* cluster_means, int* n_clusters);
 
+struct rb_gmm_presel_int;  // gmm_presel_int.cu
+int  rb_gmm_presel_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream,
+                              rb_gmm_presel_int** out);
+void rb_gmm_presel_int_destroy(rb_gmm_presel_int* h);
+int  rb_gmm_presel_int_score(rb_gmm_presel_int* h, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
+int  rb_gmm_presel_int_configure(rb_gmm_presel_int* h, int clusters, int select, int iterations, cudaStream_t s);
+void rb_gmm_presel_int_clustering(const rb_gmm_presel_int* h, uint32_t* cluster_of, float* cluster_means,
+                                  int* n_clusters);
+
 struct rb_gmm_tensor;  // gmm_tensor.cu
 int  rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream,
                           rb_gmm_tensor** out);
@@ -570,6 +579,7 @@ struct rb_gmm {
     rb_gmm_tensor*       tensor = nullptr;
     rb_gmm_int*          quantised = nullptr;
     rb_gmm_presel*       presel    = nullptr;
+    rb_gmm_presel_int*   preselInt = nullptr;
 
     ~rb_gmm() {
         if (tensor)
@@ -578,6 +588,8 @@ struct rb_gmm {
             rb_gmm_int_destroy(quantised);
         if (presel)
             rb_gmm_presel_destroy(presel);
+        if (preselInt)
+            rb_gmm_presel_int_destroy(preselInt);
         for (cudaEvent_t e : events)
             cudaEventDestroy(e);
         if (sIn)
@@ -823,7 +835,7 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
     RB_REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
     RB_CHECK(validate(ms));
-    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_BATCH_PRESELECT, "unknown gmm mode %d", mode);
+    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_BATCH_PRESELECT_INT, "unknown gmm mode %d", mode);
     rb_gmm* h = new (std::nothrow) rb_gmm();
     if (!h) {
         rb::set_error("out of host memory");
@@ -856,6 +868,13 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
     }
     if (mode == RB_GMM_BATCH_PRESELECT) {
         rc = rb_gmm_presel_create(ms, h->fuse, h->dev, h->stream, &h->presel);
+        if (rc != RB_OK)
+            return fail(rc);
+        *out = h;
+        return RB_OK;
+    }
+    if (mode == RB_GMM_BATCH_PRESELECT_INT) {
+        rc = rb_gmm_presel_int_create(ms, h->dev, h->stream, &h->preselInt);
         if (rc != RB_OK)
             return fail(rc);
         *out = h;
@@ -992,6 +1011,10 @@ extern "C" int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* 
         RB_REQUIRE(d_best == nullptr, "the preselection scorer does not report densities; use RB_GMM_DIAG_MAX");
         return rb_gmm_presel_score(h->presel, d_feats, T, d_scores, s);
     }
+    if (h->mode == RB_GMM_BATCH_PRESELECT_INT) {
+        RB_REQUIRE(d_best == nullptr, "the preselection scorer does not report densities; use RB_GMM_DIAG_MAX");
+        return rb_gmm_presel_int_score(h->preselInt, d_feats, T, d_scores, s);
+    }
     if (h->mode == RB_GMM_BATCH_FLOAT)
         RB_REQUIRE(d_best == nullptr, "Mm::BatchFloatFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
     return launch_simt(h, d_feats, T, d_scores, d_best, s);
@@ -1006,7 +1029,7 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
         return RB_OK;
     RB_REQUIRE(feats && scores, "NULL host buffer");
     if (h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_BATCH_TENSOR || h->mode == RB_GMM_BATCH_INT ||
-        h->mode == RB_GMM_BATCH_PRESELECT)
+        h->mode == RB_GMM_BATCH_PRESELECT || h->mode == RB_GMM_BATCH_PRESELECT_INT)
         RB_REQUIRE(best_density == nullptr, "this scorer mode does not report densities; use RB_GMM_DIAG_MAX");
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
     const size_t D = h->dim, M = h->nMix;
@@ -1072,13 +1095,19 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
 
 // density preselection (RB_GMM_BATCH_PRESELECT): re-cluster with other parameters / read the clustering back
 extern "C" int rb_gmm_configure_preselection(rb_gmm* h, int clusters, int select, int iterations, float backoff_score) {
-    RB_REQUIRE(h && h->presel, "not a preselection scorer");
+    RB_REQUIRE(h && (h->presel || h->preselInt), "not a preselection scorer");
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    if (h->preselInt)  // the int variant has no back-off score
+        return rb_gmm_presel_int_configure(h->preselInt, clusters, select, iterations, h->stream);
     return rb_gmm_presel_configure(h->presel, clusters, select, iterations, backoff_score, h->stream);
 }
 
 extern "C" int rb_gmm_get_clustering(const rb_gmm* h, uint32_t* cluster_of_density, float* cluster_means, int* n_clusters) {
-    RB_REQUIRE(h && h->presel, "not a preselection scorer");
+    RB_REQUIRE(h && (h->presel || h->preselInt), "not a preselection scorer");
+    if (h->preselInt) {
+        rb_gmm_presel_int_clustering(h->preselInt, cluster_of_density, cluster_means, n_clusters);
+        return RB_OK;
+    }
     rb_gmm_presel_clustering(h->presel, cluster_of_density, cluster_means, n_clusters);
     return RB_OK;
 }

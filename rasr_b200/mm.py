@@ -57,7 +57,8 @@ class GmmScorer:
 
     MODES = {"batch-float": capi.GMM_BATCH_FLOAT, "diagonal-maximum": capi.GMM_DIAG_MAX,
              "diagonal-sum": capi.GMM_DIAG_SUM, "batch-tensor": capi.GMM_BATCH_TENSOR,
-             "batch-int": capi.GMM_BATCH_INT, "preselection-batch-float": capi.GMM_BATCH_PRESELECT}
+             "batch-int": capi.GMM_BATCH_INT, "preselection-batch-float": capi.GMM_BATCH_PRESELECT,
+             "preselection-batch-int": capi.GMM_BATCH_PRESELECT_INT}
 
     def __init__(self, mixture_set, mode="batch-float", mixture_weight_scale=1.0, gaussian_scale=1.0,
                  contraction=True, device=0):
@@ -91,7 +92,7 @@ class GmmScorer:
     def clustering(self):
         """(cluster index of every density in mixture order, cluster means [n_clusters, padded dim])"""
         n_dens = int(self.mixture_set.mix_offsets[-1])
-        padded = (self.dim + 7) // 8 * 8
+        padded = (self.dim + 15) // 16 * 16 if self.mode == capi.GMM_BATCH_PRESELECT_INT else (self.dim + 7) // 8 * 8
         cluster_of, means, n = np.zeros(n_dens, np.uint32), np.zeros((256, padded), np.float32), C.c_int(0)
         capi.check(capi.lib().rb_gmm_get_clustering(self._h, capi.ptr(cluster_of), capi.ptr(means), C.byref(n)))
         return cluster_of, means[:n.value]

@@ -270,9 +270,16 @@ def test_std_sort_restatement_matches_libstdcxx(oracle):
     # organ-pipe and sawtooth inputs drive introsort towards its depth limit (heap sort branch)
     cases.append(np.concatenate([np.arange(2000), np.arange(2000)[::-1]]).astype(np.int32))
     cases.append((np.arange(5000) % 7).astype(np.int32))
+    from rasr_b200 import capi
     for k in cases:
+        k = np.ascontiguousarray(k)
         want, got = oracle.sort_pairs(k, False), oracle.sort_pairs(k, True)
         assert np.array_equal(want, got), (k.size, k[:8])
+        # the library's own restatement (rasr_b200/csrc/introsort.cuh, host instantiation of the code the
+        # preselection kernel runs per frame)
+        dev = np.zeros(k.size, np.int32)
+        capi.lib().rb_test_introsort(capi.ptr(k), int(k.size), capi.ptr(dev))
+        assert np.array_equal(want, dev), (k.size, k[:8])
         assert np.array_equal(np.sort(want), np.arange(k.size)) and (np.diff(k[want]) >= 0).all()
 
 
