@@ -256,7 +256,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "gmm-int", "gmm-presel", "frontend", "pipeline", "pipeline-nn", "pipeline-search", "nn"])
+    ap.add_argument("--workload", default="gmm", choices=["gmm", "gmm-diag", "gmm-tensor", "gmm-int", "gmm-presel", "gmm-presel-int", "frontend", "pipeline", "pipeline-nn", "pipeline-search", "nn"])
     ap.add_argument("--frames", type=int, default=0, help="override the frame count of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -294,11 +294,12 @@ def main():
 
     # ---------------- workload set-up: every rank owns its own shard (weak scaling, no collective)
     e2e_fn = None
-    if wl in ("gmm", "gmm-diag", "gmm-tensor", "gmm-int", "gmm-presel"):
+    if wl in ("gmm", "gmm-diag", "gmm-tensor", "gmm-int", "gmm-presel", "gmm-presel-int"):
         T = args.frames or C2["frames"]
         msd = synth.mixture_set()
         mode = {"gmm": "batch-float", "gmm-diag": "diagonal-maximum", "gmm-tensor": "batch-tensor",
-                "gmm-int": "batch-int", "gmm-presel": "preselection-batch-float"}[wl]
+                "gmm-int": "batch-int", "gmm-presel": "preselection-batch-float",
+                "gmm-presel-int": "preselection-batch-int"}[wl]
         scorer = mm.GmmScorer(mm.MixtureSet.from_dict(msd), mode, device=local_rank)
         feats_h = synth.features(T, 39, seed=2024 + rank)
         d_in = [torch.from_numpy(feats_h).to(dev) for _ in range(R)]
@@ -317,7 +318,7 @@ def main():
         units = T
         workload = "C2: GMM FeatureScorer (%s), 39-dim, 4096 densities / 256 mixtures, %d frames per GPU" % (mode, T)
         algo_bytes = ALGO_BYTES_PER_FRAME["gmm"] * T
-        bound, dtype = "hbm", "f32"
+        bound, dtype = "hbm", ("u8/s32" if wl in ("gmm-int", "gmm-presel-int") else "f32")
     elif wl in ("frontend", "pipeline"):
         n_utt = 125
         if args.frames:

@@ -12,11 +12,15 @@
 // frame runs it on the frame's pairs in shared memory.
 //
 //   presel_int_select_kernel   one warp per frame: quantise the feature (also stored for the score kernel), s32
-//                              distances to all clusters (lanes over clusters, 4 dimensions per dp4a), lane 0 sorts,
-//                              the first `select` clusters become one bit each
-//   presel_int_score_kernel    one block per frame: every thread tests densities against the cluster bits and scores
-//                              the active ones (dp4a on |m - x| bytes), minimum per mixture by atomicMin in shared
-//                              memory, (f32)best / scale_ with a correctly rounded division
+//                              distances to all clusters (lanes over clusters, 4 dimensions per dp4a), then a radix
+//                              select of the `select`-th smallest distance d*.  Clusters nearer than d* are in, farther
+//                              ones are out whatever the sort does; only when more clusters sit exactly at d* than
+//                              there are places left does the permutation matter, and only then lane 0 runs the
+//                              introsort.  One bit per selected cluster.
+//   presel_int_score_kernel    one block per frame.  The densities are stored cluster by cluster (the clustering is
+//                              static), so the block walks the selected clusters' rows only: a warp per cluster, a
+//                              lane per density (dp4a on |m - x| bytes), minimum per mixture by atomicMin in shared
+//                              memory (a minimum does not depend on the order), (f32)best / scale_ correctly rounded
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -31,10 +35,11 @@ namespace {
 struct PreselIntParams {
     const float*    feats;         // [T * dim]
     const float*    variance;      // [dim] inverse standard deviation * quantisation scale
+    // densities in cluster order (all densities of cluster 0, then of cluster 1, ...)
     const uint32_t* means;         // [nDens * words] u8 means, 4 per word, zero padded
     const int*      consts;        // [nDens]
-    const uint8_t*  clusterOf;     // [nDens]
-    const uint32_t* densMix;       // [nDens]
+    const uint32_t* densMix;       // [nDens] mixture of the density
+    const uint32_t* clusterStart;  // [nClusters + 1] first row of every cluster
     const uint32_t* clusterMeans;  // [nClusters * words]
     uint32_t*       xq;            // [T * words] quantised features
     uint32_t*       active;        // [T * 8]
@@ -102,20 +107,57 @@ __global__ void __launch_bounds__(kSelWarps * 32) presel_int_select_kernel(const
         if (lane < 8)
             bits[warp][lane] = 0;
         __syncwarp();
-        for (int c = lane; c < p.nClusters; c += 32) {
-            const uint32_t* m = cm + c * rowStride;
-            int             dist = 0;
-            for (int w = 0; w < p.words; ++w)
-                dist = sq_diff4(xs[w], m[w], dist);
-            pairs[c] = DistCluster{dist, (uint32_t)c};
+        uint32_t key[8];  // cluster lane + 32 k
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + 32 * k;
+            key[k]      = 0xffffffffu;
+            if (c < p.nClusters) {
+                const uint32_t* m    = cm + c * rowStride;
+                int             dist = 0;
+                for (int w = 0; w < p.words; ++w)
+                    dist = sq_diff4(xs[w], m[w], dist);
+                key[k]   = (uint32_t)dist;  // < 2^24: at most 128 dimensions of at most 255^2
+                pairs[c] = DistCluster{dist, (uint32_t)c};
+            }
         }
-        __syncwarp();
-        if (lane == 0)
-            rb::introsort::sort<18>(pairs, pairs + p.nClusters, ByDistance());
-        __syncwarp();
-        for (int i = lane; i < p.nSelected; i += 32) {
-            const uint32_t c = pairs[i].cluster;
-            atomicOr(&bits[warp][c >> 5], 1u << (c & 31));
+        // radix select of the nSelected-th smallest distance
+        uint32_t prefix = 0, mask = 0xff000000u;
+        int      remaining = p.nSelected;
+        for (int bit = 23; bit >= 0; --bit) {
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                cnt += ((key[k] & mask) == prefix && !((key[k] >> bit) & 1u)) ? 1 : 0;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (remaining > cnt) {
+                remaining -= cnt;
+                prefix |= 1u << bit;
+            }
+            mask |= 1u << bit;
+        }
+        int atBoundary = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            atBoundary += key[k] == prefix ? 1 : 0;
+        atBoundary = __reduce_add_sync(0xffffffffu, atBoundary);
+        if (atBoundary == remaining) {  // warp-uniform: every cluster at the boundary distance is selected
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t word = __ballot_sync(0xffffffffu, key[k] <= prefix);
+                if (lane == 0)
+                    bits[warp][k] = word;
+            }
+        }
+        else {  // more candidates at the boundary than places: the reference's sort decides
+            __syncwarp();
+            if (lane == 0)
+                rb::introsort::sort<18>(pairs, pairs + p.nClusters, ByDistance());
+            __syncwarp();
+            for (int i = lane; i < p.nSelected; i += 32) {
+                const uint32_t c = pairs[i].cluster;
+                atomicOr(&bits[warp][c >> 5], 1u << (c & 31));
+            }
         }
         __syncwarp();
         if (lane < 8)
@@ -129,6 +171,8 @@ __global__ void __launch_bounds__(256) presel_int_score_kernel(const PreselIntPa
     extern __shared__ int sBest[];
     __shared__ uint32_t xs[32];
     __shared__ uint32_t act[8];
+    __shared__ uint32_t sel[256];  // the selected clusters, ascending
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long t = blockIdx.x; t < p.T; t += gridDim.x) {
         __syncthreads();
         if (threadIdx.x < p.words)
@@ -138,20 +182,35 @@ __global__ void __launch_bounds__(256) presel_int_score_kernel(const PreselIntPa
         for (int m = threadIdx.x; m < p.nMix; m += blockDim.x)
             sBest[m] = INT_MAX;
         __syncthreads();
-        for (int dns = threadIdx.x; dns < p.nDens; dns += blockDim.x) {
-            const uint32_t c = p.clusterOf[dns];
-            if (!((act[c >> 5] >> (c & 31)) & 1u))
-                continue;
-            const uint32_t* mu   = p.means + (size_t)dns * p.words;
-            int             dist = 0;
-            for (int w = 0; w < p.words; w += 4) {  // words is a multiple of 4 (dimension padded to 16)
-                const uint4 v = *reinterpret_cast<const uint4*>(mu + w);
-                dist          = sq_diff4(v.x, xs[w], dist);
-                dist          = sq_diff4(v.y, xs[w + 1], dist);
-                dist          = sq_diff4(v.z, xs[w + 2], dist);
-                dist          = sq_diff4(v.w, xs[w + 3], dist);
+        {  // thread c owns cluster c: its place in the list = number of selected clusters below it
+            const uint32_t word = act[warp];
+            if ((word >> lane) & 1u) {
+                int pos = __popc(word & ((1u << lane) - 1u));
+                for (int k = 0; k < warp; ++k)
+                    pos += __popc(act[k]);
+                sel[pos] = (uint32_t)threadIdx.x;
             }
-            atomicMin(&sBest[p.densMix[dns]], dist + p.consts[dns]);
+        }
+        int nSel = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            nSel += __popc(act[k]);
+        __syncthreads();
+        for (int j = warp; j < nSel; j += 8) {
+            const uint32_t c   = sel[j];
+            const int      end = (int)p.clusterStart[c + 1];
+            for (int row = (int)p.clusterStart[c] + lane; row < end; row += 32) {
+                const uint32_t* mu   = p.means + (size_t)row * p.words;
+                int             dist = 0;
+                for (int w = 0; w < p.words; w += 4) {  // words is a multiple of 4 (dimension padded to 16)
+                    const uint4 v = *reinterpret_cast<const uint4*>(mu + w);
+                    dist          = sq_diff4(v.x, xs[w], dist);
+                    dist          = sq_diff4(v.y, xs[w + 1], dist);
+                    dist          = sq_diff4(v.z, xs[w + 2], dist);
+                    dist          = sq_diff4(v.w, xs[w + 3], dist);
+                }
+                atomicMin(&sBest[p.densMix[row]], dist + p.consts[row]);
+            }
         }
         __syncthreads();
         for (int m = threadIdx.x; m < p.nMix; m += blockDim.x)
@@ -204,12 +263,12 @@ struct rb_gmm_presel_int {
     rb::DeviceInfo dev;
     int            dim = 0, padded = 0, nMix = 0, nDens = 0, nClusters = 0, nSelected = 0;
     float          scale = 1.0f;
-    std::vector<uint8_t>  means, clusterMeans;  // [nDens * padded], [nClusters * padded]
-    std::vector<uint32_t> clusterOf;
+    std::vector<uint8_t>  means, clusterMeans;  // [nDens * padded] in mixture order, [nClusters * padded]
+    std::vector<int>      consts;               // [nDens] in mixture order
+    std::vector<uint32_t> densMix, clusterOf;   // [nDens] in mixture order
     rb::DevBuf<float>     dVariance;
-    rb::DevBuf<uint32_t>  dMeans, dClusterMeans, dDensMix, dXq, dActive;
+    rb::DevBuf<uint32_t>  dMeans, dClusterMeans, dDensMix, dClusterStart, dXq, dActive;  // dMeans.. in cluster order
     rb::DevBuf<int>       dConsts;
-    rb::DevBuf<uint8_t>   dClusterOf;
 };
 
 namespace {
@@ -266,8 +325,25 @@ int rb_gmm_presel_int_configure(rb_gmm_presel_int* h, int clusters, int select, 
                std::min(clusters, h->nDens));
     build_clustering(h, clusters, iterations);
     h->nSelected = select;
-    std::vector<uint8_t> c8(h->clusterOf.begin(), h->clusterOf.end());
-    RB_CHECK(h->dClusterOf.upload(c8.data(), c8.size(), s));
+    // the device copy of the model, cluster by cluster (within a cluster: mixture order)
+    std::vector<uint32_t> start(h->nClusters + 1, 0), mix(h->nDens);
+    for (int e = 0; e < h->nDens; ++e)
+        ++start[h->clusterOf[e] + 1];
+    for (int c = 0; c < h->nClusters; ++c)
+        start[c + 1] += start[c];
+    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+    std::vector<uint8_t>  rows(h->means.size());
+    std::vector<int>      consts(h->nDens);
+    for (int e = 0; e < h->nDens; ++e) {
+        const uint32_t row = fill[h->clusterOf[e]]++;
+        std::memcpy(&rows[(size_t)row * h->padded], &h->means[(size_t)e * h->padded], h->padded);
+        consts[row] = h->consts[e];
+        mix[row]    = h->densMix[e];
+    }
+    RB_CHECK(h->dMeans.upload(reinterpret_cast<const uint32_t*>(rows.data()), rows.size() / 4, s));
+    RB_CHECK(h->dConsts.upload(consts, s));
+    RB_CHECK(h->dDensMix.upload(mix, s));
+    RB_CHECK(h->dClusterStart.upload(start, s));
     RB_CHECK(h->dClusterMeans.upload(reinterpret_cast<const uint32_t*>(h->clusterMeans.data()),
                                      h->clusterMeans.size() / 4, s));
     RB_CUDA(cudaStreamSynchronize(s));
@@ -327,8 +403,8 @@ int rb_gmm_presel_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev
     const float logNormFactor = logNorm * scaleSquared;
 
     h->means.assign((size_t)h->nDens * h->padded, 0);
-    std::vector<int>      consts(h->nDens, 0);
-    std::vector<uint32_t> densMix(h->nDens, 0);
+    h->consts.assign(h->nDens, 0);
+    h->densMix.assign(h->nDens, 0);
     for (uint32_t m = 0; m < ms->n_mixtures; ++m) {
         for (uint32_t e = ms->mix_offsets[m]; e < ms->mix_offsets[m + 1]; ++e) {
             const uint32_t dns = ms->mix_density[e];
@@ -340,17 +416,11 @@ int rb_gmm_presel_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev
             const float* mu = ms->means + (size_t)ms->dens_mean[dns] * D;
             for (unsigned d = 0; d < D; ++d)
                 h->means[(size_t)e * h->padded + d] = quantize_u8_host(mu[d] * variance[d]);
-            consts[e]  = (int)((double)logNormFactor - (double)h->scale * ms->mix_log_weight[e]);
-            densMix[e] = m;
+            h->consts[e]  = (int)((double)logNormFactor - (double)h->scale * ms->mix_log_weight[e]);
+            h->densMix[e] = m;
         }
     }
     int rc = h->dVariance.upload(variance, stream);
-    if (rc == RB_OK)
-        rc = h->dMeans.upload(reinterpret_cast<const uint32_t*>(h->means.data()), h->means.size() / 4, stream);
-    if (rc == RB_OK)
-        rc = h->dConsts.upload(consts, stream);
-    if (rc == RB_OK)
-        rc = h->dDensMix.upload(densMix, stream);
     if (rc == RB_OK && cudaStreamSynchronize(stream) != cudaSuccess) {
         rb::set_error("int preselection model upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = RB_ERR_CUDA;
@@ -378,8 +448,8 @@ int rb_gmm_presel_int_score(rb_gmm_presel_int* h, const float* dFeats, long T, f
     p.variance     = h->dVariance.p;
     p.means        = h->dMeans.p;
     p.consts       = h->dConsts.p;
-    p.clusterOf    = h->dClusterOf.p;
     p.densMix      = h->dDensMix.p;
+    p.clusterStart = h->dClusterStart.p;
     p.clusterMeans = h->dClusterMeans.p;
     p.xq           = h->dXq.p;
     p.active       = h->dActive.p;
