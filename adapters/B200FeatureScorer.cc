@@ -83,7 +83,7 @@ GmmFeatureScorer::GmmFeatureScorer(const Core::Configuration& c, Core::Ref<const
     if (rb_gmm_create(&view, mode, paramMixtureWeightScale(c), paramGaussianScale(c), paramContraction(c),
                       paramDevice(c), &handle_) != RB_OK)
         criticalError("rasr_b200: %s", rb_last_error());
-    if (mode == RB_GMM_BATCH_PRESELECT) {
+    if (mode == RB_GMM_BATCH_PRESELECT || mode == RB_GMM_BATCH_PRESELECT_INT) {  // the int variant ignores the back-off score
         // the parameters of Mm::DensityClusteringBase under the same selection (src/Mm/BatchFeatureScorer.cc:262,
         // src/Mm/DensityClustering.cc:20-34)
         const Core::Configuration dc(c, "density-clustering");
