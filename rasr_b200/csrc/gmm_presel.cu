@@ -13,8 +13,10 @@
 //   presel_select_kernel    one warp per frame: f32 distances to all clusters (sequential sum over the padded
 //                           dimension like unrolledVectorDistance), then the `select` smallest by a radix select on the
 //                           distance bits -> one bit per cluster.  The reference sorts (distance, cluster) pairs by
-//                           distance only (std::sort, not stable): for exactly equal distances at the selection
-//                           boundary its choice is unspecified; here the lower cluster index wins.
+//                           distance only (std::sort, not stable): when more clusters sit exactly at the boundary
+//                           distance than there are places left (duplicate centroids, for instance), which of them
+//                           survive is decided by libstdc++'s introsort -- lane 0 then runs introsort.cuh on the
+//                           frame's pairs, as in gmm_presel_int.cu.
 //   presel_score_kernel     one block per frame: the densities whose cluster bit is set are collected in a shared list
 //                           and scored by groups of 8 lanes with the lane arithmetic of fillScoreCacheTpl (two 4-lane
 //                           accumulators over 8-dimension blocks, the constant first in lane 0, horizontal add);
@@ -26,6 +28,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "introsort.cuh"
 
 namespace {
 
@@ -76,12 +79,29 @@ __device__ __forceinline__ float sq_acc(float df, float acc, bool fuse) {
 
 constexpr int kSelWarps = 8;
 
-// dynamic smem: cluster means [nClusters][padded + 1] | per warp: x [padded]
+struct DistCluster {  // std::pair<f32 distance, u32 cluster>; distances are >= 0, their bit patterns order like the values
+    uint32_t distBits;
+    uint32_t cluster;
+};
+struct ByDistance {
+    __host__ __device__ __forceinline__ bool operator()(const DistCluster& a, const DistCluster& b) const {
+        return a.distBits < b.distBits;
+    }
+};
+
+// float offset of the (distance, cluster) pairs in the select kernel's dynamic shared memory (8-byte aligned)
+__host__ __device__ __forceinline__ size_t presel_pairs_offset(int nClusters, int padded) {
+    return ((size_t)nClusters * (padded + 1) + (size_t)kSelWarps * padded + 1) & ~(size_t)1;
+}
+
+// dynamic smem: cluster means [nClusters][padded + 1] | per warp: x [padded] | per warp: pairs [256]
 __global__ void __launch_bounds__(kSelWarps * 32) presel_select_kernel(const PreselParams p) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(8) float smem[];
     const int stride = p.padded + 1;  // odd stride: lanes reading different clusters hit different banks
     float*    cm     = smem;
     float*    xs     = smem + (size_t)p.nClusters * stride + (threadIdx.x >> 5) * p.padded;
+    DistCluster* pairs =
+            reinterpret_cast<DistCluster*>(smem + presel_pairs_offset(p.nClusters, p.padded)) + (threadIdx.x >> 5) * 256;
     for (int i = threadIdx.x; i < p.nClusters * p.padded; i += blockDim.x)
         cm[(i / p.padded) * stride + i % p.padded] = p.clusterMeans[i];
     __syncthreads();
@@ -101,7 +121,8 @@ __global__ void __launch_bounds__(kSelWarps * 32) presel_select_kernel(const Pre
                 const float* m     = cm + c * stride;
                 for (int d = 0; d < p.padded; ++d)
                     score = sq_acc(__fsub_rn(xs[d], m[d]), score, p.fuse);
-                key[k] = __float_as_uint(score);  // distances are >= 0: their bit patterns order like the values
+                key[k]   = __float_as_uint(score);  // distances are >= 0: their bit patterns order like the values
+                pairs[c] = DistCluster{key[k], (uint32_t)c};
             }
         }
         // radix select of the nSelected-th smallest key
@@ -119,18 +140,30 @@ __global__ void __launch_bounds__(kSelWarps * 32) presel_select_kernel(const Pre
             }
             mask |= 1u << bit;
         }
-        // everything below the threshold, and the first `remaining` clusters (by index) that sit exactly on it
-        int before = 0;
+        int atBoundary = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const bool     valid = lane + 32 * k < p.nClusters;
-            const uint32_t eq    = __ballot_sync(0xffffffffu, valid && key[k] == prefix);
-            const int      rank  = before + __popc(eq & ((1u << lane) - 1u));
-            const bool     sel   = valid && (key[k] < prefix || (key[k] == prefix && rank < remaining));
-            const uint32_t word  = __ballot_sync(0xffffffffu, sel);
-            if (lane == 0)
-                p.active[t * 8 + k] = word;
-            before += __popc(eq);
+        for (int k = 0; k < 8; ++k)
+            atBoundary += (lane + 32 * k < p.nClusters && key[k] == prefix) ? 1 : 0;
+        atBoundary = __reduce_add_sync(0xffffffffu, atBoundary);
+        if (atBoundary == remaining) {  // warp-uniform: everything up to the boundary distance is selected
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t word = __ballot_sync(0xffffffffu, lane + 32 * k < p.nClusters && key[k] <= prefix);
+                if (lane == 0)
+                    p.active[t * 8 + k] = word;
+            }
+        }
+        else {  // more candidates at the boundary distance than places: the reference's sort decides
+            __syncwarp();
+            if (lane == 0) {
+                rb::introsort::sort<18>(pairs, pairs + p.nClusters, ByDistance());
+                uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < p.nSelected; ++i)
+                    words[pairs[i].cluster >> 5] |= 1u << (pairs[i].cluster & 31);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    p.active[t * 8 + k] = words[k];
+            }
         }
         __syncwarp();
     }
@@ -403,7 +436,7 @@ int rb_gmm_presel_score(rb_gmm_presel* h, const float* dFeats, long T, float* dS
     p.nSelected    = h->nSelected;
     p.fuse         = h->fuse ? 1 : 0;
     p.backoff      = h->backoff;
-    const size_t smem = ((size_t)h->nClusters * (h->padded + 1) + (size_t)kSelWarps * h->padded) * 4;
+    const size_t smem = presel_pairs_offset(h->nClusters, h->padded) * 4 + (size_t)kSelWarps * 256 * sizeof(DistCluster);
     RB_CUDA(cudaFuncSetAttribute(presel_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid1 = (int)std::min<long>((T + kSelWarps - 1) / kSelWarps, (long)h->dev.sm_count * 4);
     presel_select_kernel<<<grid1, kSelWarps * 32, smem, s>>>(p);

@@ -102,3 +102,19 @@ def test_rejects_bad_parameters():
         sc.configure_preselection(clusters=4, select=5)
     with pytest.raises(capi.RasrB200Error):
         sc.configure_preselection(clusters=300, select=5)
+
+
+@pytest.mark.parametrize("contraction", [True, False])
+def test_float_variant_duplicate_means_tie_like_std_sort(oracle, contraction):
+    """RB_GMM_BATCH_PRESELECT (float): densities sharing four means give duplicate centroids, hence exactly equal f32
+    distances around the selection boundary; the choice among them follows the reference's std::sort"""
+    msd = synth.mixture_set(dim=12, n_mixtures=40, densities_per_mixture=8, seed=3)
+    msd["means"] = np.repeat(msd["means"][:4], (msd["means"].shape[0] + 3) // 4, axis=0)[:msd["means"].shape[0]].copy()
+    oms, gms = both(oracle, msd)
+    f = synth.features(200, 12, seed=4)
+    want, cl, means = oracle.gmm_preselect_float(oms, f, use_fma=contraction, clusters=100, select=13)
+    sc = mm.GmmScorer(gms, "preselection-batch-float", contraction=contraction)
+    sc.configure_preselection(100, 13, 5)
+    got_cl, got_means = sc.clustering()
+    assert np.array_equal(got_cl, cl) and np.array_equal(got_means, means)
+    assert np.array_equal(sc.score(f), want)
