@@ -75,16 +75,13 @@ def test_full_size_on_the_device(oracle, diag):
     d_out = torch.empty((T, 256), dtype=torch.float32, device="cuda")
     sc.score_dev(d_in, T, d_out)
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    sc.score_dev(d_in, T, d_out, stream=torch.cuda.current_stream().cuda_stream)
-    ev[1].record()
+    sc.score_dev(d_in, T, d_out)  # a second call on the handle's own stream (timings: bench.py --workload ...)
     torch.cuda.synchronize()
     got = d_out.cpu().numpy()
     idx = np.random.default_rng(0).choice(T, 1500, replace=False)
     idx.sort()
     want = oracle.gmm_preselect_float(oms, f[idx])[0]
-    diag("gmm_presel_100k", ms=ev[0].elapsed_time(ev[1]), n_diff=int((got[idx] != want).sum()))
+    diag("gmm_presel_100k", n_diff=int((got[idx] != want).sum()))
     assert np.array_equal(got[idx], want) and np.isfinite(got).all()
 
 
