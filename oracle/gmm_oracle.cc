@@ -601,6 +601,38 @@ extern "C" void orc_sort_pairs(const int32_t* keys, int n, int32_t* perm, int re
         perm[i] = v[i].second;
 }
 
+extern "C" long orc_sort_heap_calls(void) {
+    return stdsort::heapSortCalls();
+}
+
+/* An input that drives THIS library's std::sort into its depth limit (the heap sort branch), built with McIlroy's
+ * adversary ("A Killer Adversary for Quicksort", 1999): the comparison freezes the values of undecided ("gas")
+ * elements as late as possible, always making the pivot candidate the smallest remaining one.  keys [n] receives a
+ * permutation of 0..n-1. */
+extern "C" void orc_sort_killer(int n, int32_t* keys) {
+    std::vector<int32_t> val(n, n); /* n = gas */
+    std::vector<int32_t> idx(n);
+    for (int i = 0; i < n; ++i)
+        idx[i] = i;
+    int32_t nsolid = 0, candidate = 0;
+    const int32_t gas = n;
+    std::sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) {
+        if (val[x] == gas && val[y] == gas) {
+            if (x == candidate)
+                val[x] = nsolid++;
+            else
+                val[y] = nsolid++;
+        }
+        if (val[x] == gas)
+            candidate = x;
+        else if (val[y] == gas)
+            candidate = y;
+        return val[x] < val[y];
+    });
+    for (int i = 0; i < n; ++i)
+        keys[i] = val[i] == gas ? nsolid++ : val[i];
+}
+
 /* Mm::BatchPreselectionIntFeatureScorer ("preselection-batch-int", src/Mm/BatchFeatureScorer.cc:514-577) with
  * Mm::DensityClustering<u8, s32>: like the float variant on the quantised means and features -- s32 distances
  * (unrolledVectorDistance<u8, s32>), cluster means truncated back to u8 (the f64 centroid is assigned to a u8),

@@ -132,6 +132,9 @@ int orc_gmm_preselect_int(const orc_mixture_set* ms, const float* feats, long T,
                           int iterations, uint32_t* cluster_of, int restated_sort);
 /* (key, index) pairs sorted by key only: index permutation of std::sort (restated = 0) / of the restatement */
 void orc_sort_pairs(const int32_t* keys, int n, int32_t* perm, int restated);
+/* number of times the restatement fell back to heap sort so far; an adversarial input (McIlroy) for this std::sort */
+long orc_sort_heap_calls(void);
+void orc_sort_killer(int n, int32_t* keys);
 int orc_gmm_batch_float_mt(const orc_mixture_set* ms, const float* feats, long T, float* scores, int use_fma,
                            int n_threads);
 

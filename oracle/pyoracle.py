@@ -261,6 +261,17 @@ def sort_pairs(keys, restated):
     return perm
 
 
+def sort_heap_calls():
+    lib().orc_sort_heap_calls.restype = C.c_long
+    return int(lib().orc_sort_heap_calls())
+
+
+def sort_killer(n):
+    keys = np.zeros(n, np.int32)
+    lib().orc_sort_killer(int(n), _p(keys, C.c_int32))
+    return keys
+
+
 def gmm_batch_int(ms, feats, threads=1):
     """Mm::BatchIntFeatureScorer ("batch-diagonal-maximum-int"): dense scores [T x nMix]."""
     feats = np.ascontiguousarray(feats, np.float32)

@@ -17,6 +17,12 @@ namespace stdsort {
 
 const int kThreshold = 16; /* _S_threshold */
 
+/* test statistic: how often the depth limit was hit (the tests want to see this branch taken) */
+inline long& heapSortCalls() {
+    static long calls = 0;
+    return calls;
+}
+
 template<class T, class Less>
 inline void adjustHeap(T* first, long holeIndex, long len, T value, Less comp) {
     const long topIndex    = holeIndex;
@@ -46,6 +52,7 @@ inline void adjustHeap(T* first, long holeIndex, long len, T value, Less comp) {
 /* __partial_sort(first, last, last) = __heap_select (only make_heap when middle == last) + __sort_heap */
 template<class T, class Less>
 inline void heapSort(T* first, T* last, Less comp) {
+    ++heapSortCalls();
     const long len = last - first;
     if (len >= 2) {
         long parent = (len - 2) / 2;

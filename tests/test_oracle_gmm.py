@@ -270,7 +270,14 @@ def test_std_sort_restatement_matches_libstdcxx(oracle):
     # organ-pipe and sawtooth inputs drive introsort towards its depth limit (heap sort branch)
     cases.append(np.concatenate([np.arange(2000), np.arange(2000)[::-1]]).astype(np.int32))
     cases.append((np.arange(5000) % 7).astype(np.int32))
+    # McIlroy's adversary against this libstdc++: quadratic partitioning, so the depth limit (heap sort) is reached
+    for n in (200, 256, 3000):
+        killer = oracle.sort_killer(n)
+        assert np.array_equal(np.sort(killer), np.arange(n))
+        cases.append(killer)
+        cases.append((killer // 3).astype(np.int32))  # the same shape with ties
     from rasr_b200 import capi
+    heap_before = oracle.sort_heap_calls()
     for k in cases:
         k = np.ascontiguousarray(k)
         want, got = oracle.sort_pairs(k, False), oracle.sort_pairs(k, True)
@@ -281,6 +288,7 @@ def test_std_sort_restatement_matches_libstdcxx(oracle):
         capi.lib().rb_test_introsort(capi.ptr(k), int(k.size), capi.ptr(dev))
         assert np.array_equal(want, dev), (k.size, k[:8])
         assert np.array_equal(np.sort(want), np.arange(k.size)) and (np.diff(k[want]) >= 0).all()
+    assert oracle.sort_heap_calls() > heap_before, "no case reached the heap sort branch"
 
 
 def test_preselection_int_oracle_properties(oracle):
