@@ -309,3 +309,28 @@ def test_preselection_int_oracle_properties(oracle):
         a = oracle.gmm_preselect_int(ms, f, clusters=clusters, select=select, restated_sort=False)
         b = oracle.gmm_preselect_int(ms, f, clusters=clusters, select=select, restated_sort=True)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_std_sort_restatements_property(oracle):
+    """random sizes and key ranges (few distinct keys = many ties): std::sort, the oracle's restatement and the
+    library's introsort.cuh produce the same permutation"""
+    from hypothesis import given, settings, strategies as st
+    from rasr_b200 import capi
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, 700), st.sampled_from([1, 2, 3, 7, 40, 1000, 1 << 30]), st.integers(0, 2 ** 32 - 1),
+           st.sampled_from(["random", "sorted", "reversed", "sawtooth"]))
+    def check(n, hi, seed, shape):
+        k = np.random.default_rng(seed).integers(0, hi, n).astype(np.int32)
+        if shape == "sorted":
+            k.sort()
+        elif shape == "reversed":
+            k = np.ascontiguousarray(np.sort(k)[::-1])
+        elif shape == "sawtooth":
+            k = np.ascontiguousarray(np.concatenate([np.sort(k[: n // 2]), np.sort(k[n // 2:])]))
+        want = oracle.sort_pairs(k, False)
+        lib = np.zeros(n, np.int32)
+        capi.lib().rb_test_introsort(capi.ptr(k), int(n), capi.ptr(lib))
+        assert np.array_equal(want, oracle.sort_pairs(k, True)) and np.array_equal(want, lib)
+
+    check()
