@@ -42,6 +42,12 @@ def main():
     mx, mb = o.gmm_diag_max(ms, f)
     sm, sb = o.gmm_diag_sum(ms, f)
     np.savez_compressed(os.path.join(HERE, "gmm_ragged.npz"), batch=batch, max=mx, max_best=mb, sum=sm, sum_best=sb)
+    # 4. the quantised and the density-preselection scorers on the same ragged model (few clusters: contested ties)
+    sel_f, cl_f, means_f = o.gmm_preselect_float(ms, f, clusters=16, select=4)
+    sel_i, cl_i = o.gmm_preselect_int(ms, f, clusters=16, select=4)
+    np.savez_compressed(os.path.join(HERE, "gmm_ragged_int_presel.npz"), int=o.gmm_batch_int(ms, f), presel_float=sel_f,
+                        presel_float_cluster_of=cl_f, presel_float_means=means_f, presel_int=sel_i,
+                        presel_int_cluster_of=cl_i)
     print("golden fixtures written to", HERE)
 
 
