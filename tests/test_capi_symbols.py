@@ -73,3 +73,14 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn), errors="replace").read()
                 hit = re.search(r"(from|import)\s+oracle|liboracle|pyoracle|oracle\.h|\borc_[a-z]", text)
                 assert hit is None, (os.path.join(dirpath, fn), hit.group(0))
+
+
+def test_scorer_mode_constants_match_the_header():
+    """rb_gmm_mode in include/rasr_b200.h against the Python mirror (capi.GMM_*) and the reference's scorer names"""
+    from rasr_b200 import mm
+    text = open(os.path.join(ROOT, "include", "rasr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    enum = dict((k, int(v)) for k, v in re.findall(r"\b(RB_GMM_[A-Z_]+)\s*=\s*(\d+)", text))
+    assert enum == {"RB_" + k: getattr(capi, k) for k in dir(capi) if k.startswith("GMM_")}
+    assert sorted(mm.GmmScorer.MODES.values()) == sorted(enum.values())
+    assert mm.GmmScorer.MODES["preselection-batch-int"] == enum["RB_GMM_BATCH_PRESELECT_INT"]
