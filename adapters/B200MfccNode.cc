@@ -95,8 +95,11 @@ bool MfccNode::configure() {
     }
     if (!ensureHandle())
         return false;
-    // what the chain window -> ... -> cosine-transform leaves in the attributes
+    // what the chain window -> ... -> cosine-transform leaves in the attributes: the window node adds "frame-shift"
+    // (src/Signal/Window.cc:166), the FFT and filter-bank nodes rewrite "sample-rate" and the cosine transform finally
+    // sets it to 1 (src/Signal/CosineTransform.cc:208); the regression / concat mergers keep both
     a->set("frame-shift", cfg_.window_shift_s);
+    a->set("sample-rate", 1);
     a->set("datatype", Flow::Vector<f32>::type()->name());
     return putOutputAttributes(0, a);
 }

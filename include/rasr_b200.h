@@ -336,7 +336,8 @@ int rb_pipeline_score_s16(rb_frontend* fe, rb_gmm* gmm, const int16_t* samples, 
 int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, const int64_t* offsets, int n_utt,
                           float* d_feats, float* d_scores, void* stream);
 
-/* audio -> MFCC -> (rb_postproc, may be NULL) -> Nn scores (config C4 fed from audio).  scores [frames * n_outputs];
+/* audio -> MFCC -> (rb_postproc, may be NULL) -> Nn scores (config C4 fed from audio).  scores [frames *
+ * rb_nn_n_emissions(nn)] (= n_classes with a class mapping, else the number of outputs);
  * the device variant needs d_feats [frames * feat_dim] and, with a post-processor, d_post [frames * dim_out]. */
 int rb_pipeline_nn_score(rb_frontend* fe, rb_postproc* pp, rb_nn* nn, const float* samples, const int64_t* offsets,
                          int n_utt, float* scores);

@@ -629,6 +629,9 @@ int validate(const rb_mixture_set* ms) {
     for (uint32_t e = 0; e < nEntries; ++e) {
         const uint32_t d = ms->mix_density[e];
         RB_REQUIRE(d < ms->n_densities, "mixture entry %u refers to density %u >= %u", e, d, ms->n_densities);
+    }
+    // every density, referenced by a mixture or not: the quantisation scale and the clusterings walk all of them
+    for (uint32_t d = 0; d < ms->n_densities; ++d) {
         RB_REQUIRE(ms->dens_mean[d] < ms->n_means, "density %u refers to mean %u >= %u", d, ms->dens_mean[d],
                    ms->n_means);
         RB_REQUIRE(ms->dens_cov[d] < ms->n_covariances, "density %u refers to covariance %u >= %u", d,

@@ -233,7 +233,9 @@ extern "C" int rb_pipeline_nn_score(rb_frontend* fe, rb_postproc* pp, rb_nn* nn,
     RB_REQUIRE(scores != nullptr, "NULL score buffer");
     RB_CUDA(cudaSetDevice(rb_frontend_device(fe).ordinal));
     Scratch&     sc = scratch_for(fe);
-    const int    D = rb_frontend_feat_dim(fe), Dp = pp ? rb_postproc_dim_out(pp) : D, M = rb_nn_n_outputs(nn);
+    // rb_nn_score_dev writes [T x n_emissions] rows: the class count once a class mapping is active (which may exceed the
+    // number of network outputs when classes are disregarded), else the number of outputs
+    const int    D = rb_frontend_feat_dim(fe), Dp = pp ? rb_postproc_dim_out(pp) : D, M = rb_nn_n_emissions(nn);
     cudaStream_t sK = rb_frontend_stream(fe);
     // slabs of whole utterances, ~16384 frames each: the f32 score slab (48 KB per frame for 12k senones) is what
     // bounds the size, and its D2H copy is what bounds the call

@@ -624,6 +624,7 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
         uint32_t       maxEmis = 0;
         for (uint32_t s = 0; s < nStates; ++s)
             maxEmis = std::max(maxEmis, lx->state_emission[s]);
+        h->maxEmis = maxEmis;  // kept for every lexicon: decode checks it against the width of the score rows
         fits = fits && maxEmis < 16384 && nStates <= (uint32_t)kThreads * 16;
         const float*          tdp = lx->tdp;
         const uint32_t        em  = lx->entry_model;
@@ -669,7 +670,6 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
                 rb::set_error("lexicon upload failed");
                 return fail(RB_ERR_CUDA);
             }
-            h->maxEmis    = maxEmis;
             values.resize(kMaxValues, inf);
             if (h->dStateMeta.upload(meta.data(), meta.size(), h->stream) != RB_OK ||
                 h->dStateEmOff.upload(reinterpret_cast<const uint32_t*>(emOff.data()), emOff.size() / 2, h->stream) != RB_OK ||
@@ -704,6 +704,9 @@ extern "C" void rb_search_destroy(rb_search* h) {
 extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_emissions, const int64_t* frame_offsets,
                                     int n_utt, void* stream) {
     RB_REQUIRE(h && frame_offsets && n_utt >= 0 && n_emissions >= 1, "bad argument");
+    // require(emissionScores->nEmissions() >= acousticModel_->nEmissions()), src/Search/LinearSearch.cc:235
+    RB_REQUIRE(h->nStates == 0 || h->maxEmis < (uint32_t)n_emissions,
+               "the lexicon refers to emission %u, the score rows have %d emissions", h->maxEmis, n_emissions);
     h->frameOff.assign(frame_offsets, frame_offsets + n_utt + 1);
     const int64_t base = frame_offsets[0], T = frame_offsets[n_utt] - base;
     for (auto& f : h->frameOff)
@@ -725,7 +728,7 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
     const uint32_t rowFloats = ((uint32_t)n_emissions + 3) & ~3u;
     const SmemLayout lay(h->regThreads / 32, h->W, rowFloats, (uint32_t)maxT);
     const size_t     smem2 = lay.total;
-    if (h->npt && h->maxEmis < (uint32_t)n_emissions && smem2 + 4096 <= h->dev.smem_optin) {
+    if (h->npt && smem2 + 4096 <= h->dev.smem_optin) {
         SearchParams2 q;
         q.lay       = lay;
         q.warpWords = h->dWarpWords.p;

@@ -249,10 +249,15 @@ class MfccNode:
         sr = float(input_attributes["sample-rate"])
         self._fe = FrontEnd(sample_rate=sr, **self._kw)
         self._fe.set_dc_detection(self._dc, self._dc_on)
-        g = self._fe.geometry
-        self.output_attributes = {"datatype": "vector-f32", "sample-rate": "%g" % (sr / g.win_shift),
-                                  "frame-shift": "%g" % (g.win_shift / sr)}
+        self.output_attributes = self.output_attributes_for(self._kw.get("window_shift", 0.01))
         return True
+
+    @staticmethod
+    def output_attributes_for(window_shift_s):
+        """What the replaced chain leaves in the attributes: the window node adds "frame-shift" = its shift parameter
+        (src/Signal/Window.cc:166), the cosine transform sets "sample-rate" to 1 (src/Signal/CosineTransform.cc:208);
+        values travel as text with 6 significant digits (src/Flow/Attributes.hh:104-113)."""
+        return {"datatype": "vector-f32", "sample-rate": "1", "frame-shift": "%g" % window_shift_s}
 
     def put(self, packet):
         """Input side of work(): a Packet of samples, or EOS."""

@@ -52,13 +52,14 @@ def score_utterances_dev(frontend, gmm, d_samples, offsets, d_feats, d_scores, s
 
 
 def nn_score_utterances(frontend, postproc, nn, samples, offsets, out=None):
-    """audio -> MFCC -> post-processing (may be None) -> Nn scores; host buffers in, [total_frames x n_outputs] out."""
+    """audio -> MFCC -> post-processing (may be None) -> Nn scores; host buffers in, [total_frames x n_emissions] out
+    (n_emissions = the class count of an active class mapping, else the number of network outputs)."""
     if isinstance(samples, np.ndarray) or not hasattr(samples, "data_ptr"):
         samples = np.ascontiguousarray(samples, np.float32)
     offsets = np.ascontiguousarray(offsets, np.int64)
     fo = frontend.count_frames(offsets)
     T = int(fo[-1])
-    scores = out if out is not None else np.zeros((T, nn.n_outputs), np.float32)
+    scores = out if out is not None else np.zeros((T, nn.n_emissions), np.float32)
     capi.check(capi.lib().rb_pipeline_nn_score(frontend.handle, postproc.handle if postproc else None, nn.handle,
                                                capi.ptr(samples), capi.ptr(offsets), offsets.size - 1,
                                                capi.ptr(scores)))

@@ -72,6 +72,30 @@ def test_audio_to_nn_scores_pipeline(oracle, diag):
         pipeline.nn_score_utterances(fe, None, sc, samples, offs)  # 39-dim features into a 429-dim network
 
 
+def test_audio_to_nn_scores_with_disregarded_classes():
+    """a class mapping with -1 entries makes the score rows wider than the network output (n_classes > n_outputs):
+    the one-call pipeline must size its slabs and the host stride by the class count.  More than one slab (> 16384
+    frames) so the second slab's offset is exercised too."""
+    from rasr_b200 import nn
+
+    samples, offs = synth.corpus(9, n_samples=320240)  # 9 x 2001 frames -> two slabs
+    fe = flow.FrontEnd()
+    net = synth.network(dims=(39, 64, 40), seed=5)
+    sc = nn.NnScorer(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, "bf16")
+    rng = np.random.default_rng(11)
+    mapping = np.full(57, -1, np.int32)
+    mapping[rng.permutation(57)[:40]] = rng.permutation(40).astype(np.int32)
+    sc.set_class_mapping(mapping)
+    assert sc.n_emissions == 57 and sc.n_outputs == 40
+    scores, fo = pipeline.nn_score_utterances(fe, None, sc, samples, offs)
+    assert scores.shape == (int(fo[-1]), 57) and int(fo[-1]) > 16384
+    r = fe.process(samples, offs)
+    want = sc.score(r["feats"])
+    assert np.array_equal(scores, want)
+    assert (scores[:, mapping < 0] == np.finfo(np.float32).max).all()
+    assert (scores[:, mapping >= 0] < 1e30).all()
+
+
 def test_features_through_a_feature_cache(tmp_path):
     """what a two-pass RASR setup does: the extraction run writes the features to a cache archive (one entry per
     segment, timestamps included), the recognition run reads them back and scores them"""

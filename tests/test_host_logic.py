@@ -72,6 +72,12 @@ def test_mfcc_node_parameters():
     assert not node.configure({"datatype": "vector-s16", "sample-rate": "16000"})
     with pytest.raises(capi.RasrB200Error):
         node.put(flow.EOS)  # used before a successful configure()
+    # the attributes the replaced chain leaves: "sample-rate" 1 (src/Signal/CosineTransform.cc:208), "frame-shift" =
+    # the window node's shift parameter (src/Signal/Window.cc:166), as text
+    assert flow.MfccNode.output_attributes_for(0.01) == {"datatype": "vector-f32", "sample-rate": "1",
+                                                         "frame-shift": "0.01"}
+    src = open(os.path.join(os.path.dirname(__file__), "..", "adapters", "B200MfccNode.cc")).read()
+    assert 'a->set("sample-rate", 1);' in src and 'a->set("frame-shift", cfg_.window_shift_s);' in src
 
 
 def test_partition_is_balanced_and_complete():
