@@ -1,0 +1,189 @@
+"""ctypes binding of oracle/_ref/librasr_ref*.so: the REFERENCE's own object code (Core, Flow, Math, Signal, Mm
+translation units compiled from /root/reference by oracle/refbuild/Makefile) behind the C entry points of
+oracle/refbuild/ref_host.cc.
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, tests/golden/make_golden.py and bench.py's cpu_baseline /
+--impl reference legs.  The product package rasr_b200 never imports this module.
+
+Two variants, both loadable in one process (each library binds its own symbols, -Bsymbolic / -fno-gnu-unique):
+`native=False` = every operation rounded separately, `native=True` = gcc's default FMA contraction, what the
+reference's own -march=native build does.  The adapters (libb200_adapters.so) resolve against the native variant.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REFBUILD = os.path.join(_HERE, "refbuild")
+REFERENCE = "/root/reference"
+FLOW_SHARE = os.path.join(REFERENCE, "src", "Tools", "FeatureExtraction", "share")
+
+_libs = {}
+
+
+def path(native=False):
+    return os.path.join(_HERE, "_ref", "librasr_ref_native.so" if native else "librasr_ref.so")
+
+
+def available(native=False):
+    return os.path.exists(path(native))
+
+
+def build():
+    """Compile the reference's sources from where they lie (needs /root/reference; a few minutes the first time)."""
+    if not os.path.isdir(os.path.join(REFERENCE, "src", "Mm")):
+        raise RuntimeError("the reference checkout is not present on this host")
+    subprocess.check_call(["make", "-s", "-j%d" % (os.cpu_count() or 4), "-C", _REFBUILD, "all"])
+
+
+def lib(native=False, log_file=None):
+    native = bool(native)
+    if native in _libs:
+        return _libs[native]
+    if not available(native):
+        build()
+    # the native variant is loaded globally: libb200_adapters.so resolves the RASR symbols against it
+    L = C.CDLL(path(native), mode=C.RTLD_GLOBAL if native else C.RTLD_LOCAL)
+    L.ref_last_error.restype = C.c_char_p
+    L.ref_flow_create.restype = C.c_void_p
+    L.ref_flow_run.restype = C.c_long
+    L.ref_mm_create.restype = C.c_void_p
+    L.ref_init(log_file.encode() if log_file else None)
+    # the reference's own .flow files are found through this path when a network names them as a filter; on a host
+    # without the reference checkout (the GPU box) only self-contained networks can be built
+    L.ref_config_set(b"*.network-file-path", FLOW_SHARE.encode())
+    _libs[native] = L
+    return L
+
+
+_adapters = None
+
+
+def load_adapters():
+    """Load oracle/_ref/libb200_adapters.so (adapters/*.cc compiled against the reference's headers) into the
+    reference host and run INIT_MODULE(B200): afterwards the reference's Flow registry knows the filter "b200-mfcc" and
+    its Mm factory the "b200-*" feature scorers, both forwarding to librasr_b200.so."""
+    global _adapters
+    L = lib(native=True)
+    if _adapters is None:
+        p = os.path.join(_HERE, "_ref", "libb200_adapters.so")
+        if not os.path.exists(p):
+            build()
+        _adapters = C.CDLL(p, mode=C.RTLD_GLOBAL)
+        _adapters.b200_adapters_register()
+    return L
+
+
+def config_set(name, value, native=False):
+    """A resource of the reference's global Core::Configuration, e.g. ("*.density-clustering.clusters", "64")."""
+    lib(native).ref_config_set(name.encode(), str(value).encode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# the values src/Tools/FeatureExtraction/share/mfcc.flow:8-34 and samples.flow:34-35 fix, as the text they carry there
+CHAIN_DEFAULTS = {"block-size": 4096, "alpha": "1.00", "window-type": "hamming", "shift": ".01", "length": "0.025",
+                  "maximum-input-size": "0.025", "filter-width": "268.258", "nr-cepstrum-coefficients": 13}
+DC_DEFAULTS = {"min-dc-length": ".0125", "max-dc-increment": "0.9", "min-non-dc-segment-length": ".026",
+               "maximal-output-size": 4096}
+
+
+def chain_parameters(dc=False, **overrides):
+    """Parameters of mfcc_chain_plain.flow / mfcc_chain_dc.flow / b200_mfcc.flow; keyword names with '_' for '-'."""
+    p = dict(CHAIN_DEFAULTS)
+    if dc:
+        p.update(DC_DEFAULTS)
+    p.update({k.replace("_", "-"): v for k, v in overrides.items()})
+    return p
+
+
+class FlowNetwork:
+    """A Flow::Network built by the reference's NetworkParser from `flow_file` (relative names: oracle/refbuild/flows)."""
+
+    def __init__(self, flow_file="mfcc_derivatives.flow", parameters=None, native=False, selection="flow"):
+        self._L = lib(native)
+        if not os.path.isabs(flow_file):
+            flow_file = os.path.join(_REFBUILD, "flows", flow_file)
+        self._h = self._L.ref_flow_create(flow_file.encode(), selection.encode())
+        if not self._h:
+            raise RuntimeError("ref_flow_create: %s" % self._L.ref_last_error().decode())
+        for k, v in (parameters or {}).items():
+            if self._L.ref_flow_set_parameter(C.c_void_p(self._h), k.encode(), str(v).encode()) != 0:
+                raise RuntimeError("network has no parameter %s" % k)
+
+    def run(self, samples, port="features", sample_rate=16000.0, start_time=0.0, capacity=None):
+        """One segment through the network; returns dict(feats [T x dim], t_start, t_end, sizes)."""
+        samples = np.ascontiguousarray(samples, np.float32)
+        cap = int(capacity if capacity is not None else samples.size // 16 + 64)
+        dim = C.c_int(0)
+        # first pass counts packets and finds their width
+        n = self._L.ref_flow_run(C.c_void_p(self._h), port.encode(), _p(samples), C.c_long(samples.size),
+                                 C.c_double(sample_rate), C.c_double(start_time), None, C.c_long(0), 0, None, None,
+                                 C.byref(dim), None)
+        if n < 0:
+            raise RuntimeError("ref_flow_run: %s" % self._L.ref_last_error().decode())
+        cap, d = int(n), max(1, dim.value)
+        feats = np.zeros((cap, d), np.float32)
+        ts, te = np.zeros(cap, np.float64), np.zeros(cap, np.float64)
+        sizes = np.zeros(cap, np.int32)
+        n2 = self._L.ref_flow_run(C.c_void_p(self._h), port.encode(), _p(samples), C.c_long(samples.size),
+                                  C.c_double(sample_rate), C.c_double(start_time), _p(feats), C.c_long(cap), d,
+                                  _p(ts), _p(te), C.byref(dim), _p(sizes))
+        if n2 != n:
+            raise RuntimeError("the network produced %d packets on the second pass, %d on the first" % (n2, n))
+        return dict(feats=feats, t_start=ts, t_end=te, sizes=sizes)
+
+    def attribute(self, port, name):
+        buf = C.create_string_buffer(256)
+        if self._L.ref_flow_get_attribute(C.c_void_p(self._h), port.encode(), name.encode(), buf, 256) < 0:
+            raise RuntimeError("no output port %s" % port)
+        return buf.value.decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ref_flow_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class FeatureScorer:
+    """An Mm::FeatureScorer created by the reference's own factory (`scorer_type` = the value of feature-scorer-type,
+    src/Mm/Module.cc:83-105; "diagonal-sum" instantiates the unregistered GaussDiagonalSumFeatureScorer).  `ms` is an
+    oracle.pyoracle.MixtureSet (same C layout).  `config`: resources below the scorer's selection, e.g.
+    {"density-clustering.clusters": 64, "buffer-size": 4}."""
+
+    def __init__(self, ms, scorer_type, config=None, native=False, selection=None):
+        self._L = lib(native)
+        FeatureScorer._count = getattr(FeatureScorer, "_count", 0) + 1
+        sel = selection or "feature-scorer-%d" % FeatureScorer._count
+        for k, v in (config or {}).items():
+            self._L.ref_config_set(("*.%s.%s" % (sel, k)).encode(), str(v).encode())
+        self._ms = ms
+        self._h = self._L.ref_mm_create(C.byref(ms.c), scorer_type.encode(), sel.encode())
+        if not self._h:
+            raise RuntimeError("ref_mm_create: %s" % self._L.ref_last_error().decode())
+        self.n_mixtures = int(self._L.ref_mm_n_mixtures(C.c_void_p(self._h)))
+
+    def score(self, feats, want_best=False):
+        feats = np.ascontiguousarray(feats, np.float32)
+        T = feats.shape[0]
+        scores = np.zeros((T, self.n_mixtures), np.float32)
+        best = np.zeros((T, self.n_mixtures), np.uint32) if want_best else None
+        rc = self._L.ref_mm_score(C.c_void_p(self._h), _p(feats), C.c_long(T), _p(scores), _p(best))
+        if rc:
+            raise RuntimeError("ref_mm_score failed (%d)" % rc)
+        return (scores, best) if want_best else scores
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ref_mm_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        self.close()
