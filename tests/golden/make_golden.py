@@ -1,8 +1,14 @@
-"""Regenerates the committed golden fixtures from the CPU oracle (and, for the FFT, from the
-reference's own object code in oracle/_ref).  Run from the repo root:  python tests/golden/make_golden.py
+"""Regenerates the committed golden fixtures FROM THE REFERENCE'S OWN OBJECT CODE (oracle/_ref/librasr_ref*.so: the
+reference's Core / Flow / Math / Signal / Mm sources compiled from /root/reference, see oracle/refbuild/Makefile):
+the MFCC features come out of a Flow::Network that the reference's NetworkParser builds from the reference's own
+mfcc.flow + derivationWithRegression.flow, the scores out of feature scorers made by the reference's Mm factory.
+Nothing in these files was computed by the oracle restatement or by the CUDA engine.
 
-The fixtures pin the oracle against silent drift and travel to the GPU box, where /root/reference
-does not exist."""
+Run from the repo root, in the build container (needs /root/reference):  python tests/golden/make_golden.py
+
+"strict" = -ffp-contract=off (every operation rounded separately), "native" = gcc's default contraction with FMA
+available, i.e. the reference's default -march=native build.  The fixtures travel to the GPU box, where
+/root/reference does not exist; tests/test_oracle_*.py pin the oracle to them, tests/test_gpu_*.py the CUDA path."""
 import ctypes as C
 import os
 import sys
@@ -11,43 +17,98 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import pyoracle as o  # noqa: E402
-from rasr_b200 import synth  # noqa: E402
+from oracle import pyoracle as o  # noqa: E402  (only MixtureSet: the C layout shared with the reference shim)
+from oracle import pyref  # noqa: E402
+from rasr_b200 import io, synth  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCE = "reference object code (oracle/_ref/librasr_ref.so = strict, librasr_ref_native.so = native)"
+
+
+def scorers(ms, f, names, config=None):
+    out = {}
+    for name in names:
+        for native in (False, True):
+            key = "%s/%s" % (name, "native" if native else "strict")
+            sc = pyref.FeatureScorer(ms, name, config, native=native)
+            if name.startswith("diagonal"):
+                out[key], out[key + "/best"] = sc.score(f, want_best=True)
+            else:
+                out[key] = sc.score(f)
+    return out
 
 
 def main():
     o.build(ref=True)
-    # 1. MFCC+derivatives of a 2 s C1-style utterance
-    n, seed = 32000, 1234
-    r = o.mfcc(o.frontend_cfg(), synth.utterance(n, seed))
-    np.savez_compressed(os.path.join(HERE, "mfcc_c1_2s.npz"), n_samples=n, seed=seed, feats=r["feats"],
-                        t_start=r["t_start"], t_end=r["t_end"])
-    # 2. FFT vectors produced by the REFERENCE's object code (strict build)
+    pyref.build()
+    # 1. BASELINE config C1: the 10 s utterance through the reference's own flow files, 999 x 39
+    n, seed = 160000, 1234
+    x = synth.utterance(n, seed)
+    P = {"nr-cepstrum-coefficients": 13, "block-size": 4096}
+    d = dict(n_samples=n, seed=seed, source=SOURCE)
+    for native in (False, True):
+        net = pyref.FlowNetwork("mfcc_derivatives.flow", P, native=native)
+        r, c = net.run(x), net.run(x, port="cepstra")
+        tag = "native" if native else "strict"
+        d.update({"feats_" + tag: r["feats"], "cepstra_" + tag: c["feats"]})
+        d.update(t_start=r["t_start"], t_end=r["t_end"], cepstra_t_start=c["t_start"], cepstra_t_end=c["t_end"])
+    np.savez_compressed(os.path.join(HERE, "ref_mfcc_c1.npz"), **d)
+    # 1b. every stage of a short utterance (the self-contained chain: same nodes as mfcc.flow)
+    n2, seed2 = 8240, 77
+    x2 = synth.utterance(n2, seed2)
+    net = pyref.FlowNetwork("mfcc_chain_plain.flow", pyref.chain_parameters())
+    d = dict(n_samples=n2, seed=seed2, source=SOURCE)
+    for port in ("frames", "spectrum", "amplitude", "filterbank", "cepstra", "features"):
+        d[port] = net.run(x2, port=port)["feats"]
+    np.savez_compressed(os.path.join(HERE, "ref_mfcc_stages.npz"), **d)
+    # 1c. signal-dc-detection in front of the chain
+    x3 = synth.utterance(40000, seed=9)
+    x3[5000:9000] = x3[4999]
+    x3[15000:15300] = 7.0
+    x3[20000:20250] = -3.0
+    r = pyref.FlowNetwork("mfcc_chain_dc.flow", pyref.chain_parameters(dc=True)).run(x3)
+    np.savez_compressed(os.path.join(HERE, "ref_mfcc_dc.npz"), samples=x3.astype(np.int16), feats=r["feats"],
+                        t_start=r["t_start"], t_end=r["t_end"], source=SOURCE)
+    # 2. FFT vectors of the reference's FFT translation unit alone (strict build)
     ref = o.ref_fft(native=False)
-    if ref is not None:
-        rng = np.random.default_rng(99)
-        x = (rng.standard_normal((8, 512)) * 3000).astype(np.float32)
-        x[:, 400:] = 0
-        y = x.copy()
-        for row in y:
-            ref.ref_fft_transform_real(row.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(512))
-        np.savez_compressed(os.path.join(HERE, "fft512_reference.npz"), x=x, y=y)
-    # 3. GMM scores of a small ragged model (all three scorers)
-    msd = synth.ragged_mixture_set(dim=39, n_covariances=1)
-    ms = o.MixtureSet(**msd)
+    rng = np.random.default_rng(99)
+    xf = (rng.standard_normal((8, 512)) * 3000).astype(np.float32)
+    xf[:, 400:] = 0
+    y = xf.copy()
+    for row in y:
+        ref.ref_fft_transform_real(row.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(512))
+    np.savez_compressed(os.path.join(HERE, "fft512_reference.npz"), x=xf, y=y)
+    # 3. BASELINE config C2's model (39 dims, 4096 densities, 256 mixtures), the first 96 of its 100 000 frames
+    ms = o.MixtureSet(**synth.mixture_set())
+    f = synth.features(100000, 39)[:96]
+    names = ["batch-diagonal-maximum-float", "batch-diagonal-maximum-int", "preselection-batch-float",
+             "preselection-batch-int", "diagonal-maximum", "diagonal-sum"]
+    np.savez_compressed(os.path.join(HERE, "ref_gmm_c2.npz"), n_frames=96, source=SOURCE, **scorers(ms, f, names))
+    # 4. a small ragged model (mixtures of unequal size sharing densities out of order); few clusters: contested ties
+    ms = o.MixtureSet(**synth.ragged_mixture_set(dim=39, n_covariances=1))
     f = synth.features(64, 39, seed=5)
-    batch = o.gmm_batch_float(ms, f)
-    mx, mb = o.gmm_diag_max(ms, f)
-    sm, sb = o.gmm_diag_sum(ms, f)
-    np.savez_compressed(os.path.join(HERE, "gmm_ragged.npz"), batch=batch, max=mx, max_best=mb, sum=sm, sum_best=sb)
-    # 4. the quantised and the density-preselection scorers on the same ragged model (few clusters: contested ties)
-    sel_f, cl_f, means_f = o.gmm_preselect_float(ms, f, clusters=16, select=4)
-    sel_i, cl_i = o.gmm_preselect_int(ms, f, clusters=16, select=4)
-    np.savez_compressed(os.path.join(HERE, "gmm_ragged_int_presel.npz"), int=o.gmm_batch_int(ms, f), presel_float=sel_f,
-                        presel_float_cluster_of=cl_f, presel_float_means=means_f, presel_int=sel_i,
-                        presel_int_cluster_of=cl_i)
+    cfg = {"density-clustering.clusters": 16, "density-clustering.select-clusters": 4}
+    d = scorers(ms, f, ["batch-diagonal-maximum-float", "batch-diagonal-maximum-int", "diagonal-maximum", "diagonal-sum"])
+    d.update(scorers(ms, f, ["preselection-batch-float", "preselection-batch-int"], cfg))
+    np.savez_compressed(os.path.join(HERE, "ref_gmm_ragged.npz"), source=SOURCE, **d)
+    # 4b. several covariances (diagonal scorers only)
+    ms = o.MixtureSet(**synth.ragged_mixture_set(dim=24, n_covariances=3, seed=11))
+    f = synth.features(64, 24, seed=6)
+    np.savez_compressed(os.path.join(HERE, "ref_gmm_ragged_3cov.npz"), source=SOURCE,
+                        **scorers(ms, f, ["diagonal-maximum", "diagonal-sum"]))
+    # 5. post-processing: signal-normalization -> sequence concatenation -> matrix multiplication (lda.flow wiring)
+    ff = synth.features(300, 13, seed=5)
+    M = np.random.default_rng(3).standard_normal((20, 65)).astype(np.float32)
+    path = "bin:/tmp/make_golden_lda.bin"
+    io.write_matrix(path, M)
+    d = dict(source=SOURCE, matrix=M)
+    for kind, length, right in (("mean-and-variance", "infinite", "infinite"), ("mean", 51, 25)):
+        net = pyref.FlowNetwork("postproc_chain.flow", {"block-size": 13, "norm-type": kind, "norm-length": length,
+                                                         "norm-right": right, "splice-length": 5, "splice-right": 2,
+                                                         "matrix-file": path})
+        for port in ("normalized", "spliced", "projected"):
+            d["%s/%s/%s" % (kind, length, port)] = net.run(ff.reshape(-1), port=port, sample_rate=1300.0)["feats"]
+    np.savez_compressed(os.path.join(HERE, "ref_postproc.npz"), **d)
     print("golden fixtures written to", HERE)
 
 

@@ -62,14 +62,6 @@ def test_c1_utterance_stage_by_stage(oracle, diag):
     assert np.array_equal(r["feats"][:, :13], r["cepstra"])
 
 
-def test_golden_fixture(oracle):
-    g = np.load(os.path.join(GOLDEN, "mfcc_c1_2s.npz"))
-    x = synth.utterance(int(g["n_samples"]), int(g["seed"]))
-    r = flow.FrontEnd().process(x)
-    assert np.array_equal(r["t_start"], g["t_start"]) and np.array_equal(r["t_end"], g["t_end"])
-    assert rel_err(r["feats"], g["feats"]) < RTOL
-
-
 @pytest.mark.parametrize("n", [1, 2, 3, 160, 399, 400, 401, 560, 561, 1000, 5119, 5120, 5121, 5361])
 def test_short_and_boundary_lengths(oracle, n):
     """Frame count / short last frame / tile boundaries (32 frames = 5120 samples of shift)."""

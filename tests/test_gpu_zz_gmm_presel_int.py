@@ -117,21 +117,3 @@ def test_float_variant_duplicate_means_tie_like_std_sort(oracle, contraction):
     assert np.array_equal(sc.score(f), want)
 
 
-def test_golden_fixture_ragged_model():
-    """committed fixture tests/golden/gmm_ragged_int_presel.npz (mixtures of unequal size sharing densities out of
-    order, 16 clusters / 4 selected): quantised scorer and both preselection scorers, bit for bit"""
-    import os
-
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gmm_ragged_int_presel.npz"))
-    gms = mm.MixtureSet.from_dict(synth.ragged_mixture_set(dim=39, n_covariances=1))
-    f = synth.features(64, 39, seed=5)
-    assert np.array_equal(mm.GmmScorer(gms, "batch-int").score(f), g["int"])
-    sc = mm.GmmScorer(gms, "preselection-batch-float")
-    sc.configure_preselection(16, 4, 5)
-    cl, means = sc.clustering()
-    assert np.array_equal(cl, g["presel_float_cluster_of"]) and np.array_equal(means, g["presel_float_means"])
-    assert np.array_equal(sc.score(f), g["presel_float"])
-    sc = mm.GmmScorer(gms, "preselection-batch-int")
-    sc.configure_preselection(16, 4, 5)
-    assert np.array_equal(sc.clustering()[0], g["presel_int_cluster_of"])
-    assert np.array_equal(sc.score(f), g["presel_int"])

@@ -1,0 +1,166 @@
+"""The RASR-side adapters (adapters/*.cc) EXECUTED: compiled against the reference's headers, linked against the
+reference's own object code (oracle/_ref/librasr_ref_native.so = its Core / Flow / Math / Signal / Mm sources) and
+loaded into that host next to librasr_b200.so.  After INIT_MODULE(B200)
+
+  * the reference's Flow::NetworkParser builds a network whose only processing node is the adapter "b200-mfcc"
+    (oracle/refbuild/flows/b200_mfcc.flow) and Flow::Network::getData pulls its packets -- compared with the packets of
+    the network made of the reference's own nodes (mfcc_chain_*.flow: same nodes and links as mfcc.flow +
+    derivationWithRegression.flow) in the same process;
+  * the reference's Mm::FeatureScorerFactory creates "b200-*" feature scorers from an Mm::MixtureSet, and the
+    recognizer's buffered call protocol (src/Speech/Recognizer.cc:271-281,197-205, replayed by ref_host.cc) reads every
+    emission score through Mm::FeatureScorer::ContextScorer::score -- compared with the reference's own scorers fed the
+    same MixtureSet object.
+
+Nothing here goes through the Python mirror of the interfaces: the call stack is reference code -> adapter -> C ABI ->
+CUDA kernels."""
+import os
+
+import numpy as np
+import pytest
+
+from rasr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import pyref
+
+    need = [pyref.path(True), os.path.join(ROOT, "oracle", "_ref", "libb200_adapters.so")]
+    missing = [p for p in need if not os.path.exists(p)]
+    if missing and not os.path.isdir(pyref.REFERENCE):
+        pytest.fail("%s missing: build them where the reference checkout is (python __graft_entry__.py)" % missing)
+    pyref.load_adapters()
+    return pyref
+
+
+@pytest.fixture(scope="module")
+def oms():
+    from oracle import pyoracle  # only for the C layout of the mixture set handed to the reference
+
+    return pyoracle
+
+
+def dim_err(got, want):
+    scale = np.sqrt(np.mean(want.astype(np.float64) ** 2, axis=0))
+    return float((np.abs(got.astype(np.float64) - want) / scale).max())
+
+
+def adapter_parameters(ref, dc=False, **kw):
+    p = ref.chain_parameters(dc=True, **kw)
+    p.update({"derivatives": "true", "dc-detection": "true" if dc else "false"})
+    return p
+
+
+def test_mfcc_node_in_a_network_built_by_the_reference(ref, diag):
+    """C1: the 10 s utterance.  Same number of packets, identical f64 time stamps, features within 1e-4; the attributes
+    the adapter publishes equal what the reference's chain leaves."""
+    x = synth.utterance(160000)
+    theirs = ref.FlowNetwork("mfcc_chain_plain.flow", ref.chain_parameters(), native=True)
+    ours = ref.FlowNetwork("b200_mfcc.flow", adapter_parameters(ref), native=True)
+    a, b = theirs.run(x), ours.run(x)
+    assert a["feats"].shape == b["feats"].shape == (999, 39)
+    assert np.array_equal(a["t_start"], b["t_start"]) and np.array_equal(a["t_end"], b["t_end"])
+    err = dim_err(b["feats"], a["feats"])
+    diag("adapter_mfcc_node_c1", err=err)
+    assert err < RTOL
+    for name in ("sample-rate", "frame-shift", "datatype"):
+        assert ours.attribute("features", name) == theirs.attribute("features", name), name
+    # a second and third segment through the same node instance: state reset at EOS, new start time, other packet size
+    for seed, n, t0 in ((5, 12345, 3.25), (6, 401, 100.0)):
+        y = synth.utterance(n, seed=seed)
+        a, b = theirs.run(y, start_time=t0), ours.run(y, start_time=t0)
+        assert a["feats"].shape == b["feats"].shape
+        assert np.array_equal(a["t_start"], b["t_start"]) and np.array_equal(a["t_end"], b["t_end"])
+        assert dim_err(b["feats"], a["feats"]) < RTOL
+
+
+@pytest.mark.parametrize("kw", [dict(block_size=160), dict(alpha="0.97", nr_cepstrum_coefficients=16),
+                                dict(window_type="hanning", shift=".005", length=".02")])
+def test_mfcc_node_parameters_reach_the_engine(ref, kw):
+    x = synth.utterance(20000, seed=21)
+    a = ref.FlowNetwork("mfcc_chain_plain.flow", ref.chain_parameters(**kw), native=True).run(x)
+    b = ref.FlowNetwork("b200_mfcc.flow", adapter_parameters(ref, **kw), native=True).run(x)
+    assert a["feats"].shape == b["feats"].shape
+    assert np.array_equal(a["t_start"], b["t_start"]) and np.array_equal(a["t_end"], b["t_end"])
+    assert dim_err(b["feats"], a["feats"]) < RTOL
+
+
+def test_mfcc_node_with_dc_detection(ref):
+    x = synth.utterance(40000, seed=9)
+    x[5000:9000] = x[4999]
+    x[15000:15300] = 7.0
+    a = ref.FlowNetwork("mfcc_chain_dc.flow", ref.chain_parameters(dc=True), native=True).run(x)
+    b = ref.FlowNetwork("b200_mfcc.flow", adapter_parameters(ref, dc=True), native=True).run(x)
+    assert a["feats"].shape == b["feats"].shape and a["feats"].shape[0] < 249
+    assert np.array_equal(a["t_start"], b["t_start"]) and np.array_equal(a["t_end"], b["t_end"])
+    assert dim_err(b["feats"], a["feats"]) < RTOL
+
+
+PAIRS = [("batch-diagonal-maximum-float", "b200-batch-float"), ("batch-diagonal-maximum-int", "b200-batch-int"),
+         ("preselection-batch-float", "b200-preselection-batch-float"),
+         ("preselection-batch-int", "b200-preselection-batch-int")]
+
+
+@pytest.mark.parametrize("theirs,ours", PAIRS, ids=[p[1] for p in PAIRS])
+def test_scorers_from_the_references_factory_bit_identical(ref, oms, theirs, ours):
+    """C2's model, 600 frames: the reference's scorer and the adapter, both created by Mm::Module's factory from the
+    same MixtureSet, both read through ContextScorer::score under the recognizer's protocol: identical bits"""
+    ms = oms.MixtureSet(**synth.mixture_set())
+    f = synth.features(600, 39, seed=31)
+    a = ref.FeatureScorer(ms, theirs, native=True).score(f)
+    b = ref.FeatureScorer(ms, ours, native=True).score(f)
+    assert a.shape == b.shape == (600, 256)
+    assert np.array_equal(a, b), "%d of %d scores differ" % ((a != b).sum(), a.size)
+
+
+def test_strict_variant_and_preselection_resources(ref, oms):
+    """fma-contraction=false (the adapter's resource) against the reference's strict build; density-clustering.* resources
+    travel through the reference's own configuration to both scorers"""
+    ms = oms.MixtureSet(**synth.mixture_set(n_mixtures=32))
+    f = synth.features(300, 39, seed=32)
+    a = ref.FeatureScorer(ms, "batch-diagonal-maximum-float", native=False).score(f)
+    b = ref.FeatureScorer(ms, "b200-batch-float", {"fma-contraction": "false"}, native=True).score(f)
+    assert np.array_equal(a, b)
+    cfg = {"density-clustering.clusters": 64, "density-clustering.select-clusters": 8,
+           "density-clustering.iterations": 3, "density-clustering.backoff-score": 777.0}
+    for theirs, ours in PAIRS[2:]:
+        a = ref.FeatureScorer(ms, theirs, cfg, native=True).score(f)
+        b = ref.FeatureScorer(ms, ours, cfg, native=True).score(f)
+        assert np.array_equal(a, b), ours
+
+
+def test_diagonal_scorers_from_the_references_factory(ref, oms, diag):
+    ms = oms.MixtureSet(**synth.ragged_mixture_set(dim=24, n_covariances=3, seed=11))
+    f = synth.features(200, 24, seed=33)
+    a = ref.FeatureScorer(ms, "diagonal-maximum", native=False).score(f)
+    b = ref.FeatureScorer(ms, "b200-diagonal-maximum", {"fma-contraction": "false"}, native=True).score(f)
+    assert np.array_equal(a, b)
+    s = ref.FeatureScorer(ms, "diagonal-sum", native=False).score(f)
+    t = ref.FeatureScorer(ms, "b200-diagonal-sum", {"fma-contraction": "false"}, native=True).score(f)
+    rel = float((np.abs(s - t) / np.abs(s)).max())
+    diag("adapter_diag_sum", rel=rel)
+    assert rel < 1e-6
+    c = ref.FeatureScorer(ms, "b200-diagonal-maximum", native=True).score(f)
+    assert float((np.abs(c - a) / np.abs(a)).max()) < 1e-6  # contracted variant: an ulp or two
+
+
+def test_tensor_mode_through_the_adapter(ref, oms):
+    ms = oms.MixtureSet(**synth.mixture_set(n_mixtures=64))
+    f = synth.features(512, 39, seed=34)
+    a = ref.FeatureScorer(ms, "batch-diagonal-maximum-float", native=True).score(f)
+    b = ref.FeatureScorer(ms, "b200-batch-tensor", native=True).score(f)
+    assert float((np.abs(a - b) / np.abs(a)).max()) < RTOL
+
+
+@pytest.mark.parametrize("buffer_size", [1, 5, 1000])
+def test_adapter_buffer_sizes(ref, oms, buffer_size):
+    """bufferFilled() / flush() protocol of the adapter for small, odd and larger-than-segment buffers"""
+    ms = oms.MixtureSet(**synth.mixture_set(n_mixtures=16))
+    f = synth.features(77, 39, seed=35)
+    a = ref.FeatureScorer(ms, "batch-diagonal-maximum-float", native=True).score(f)
+    b = ref.FeatureScorer(ms, "b200-batch-float", {"buffer-size": buffer_size}, native=True).score(f)
+    assert np.array_equal(a, b)

@@ -151,16 +151,6 @@ def test_fma_variant_is_close(oracle):
     assert np.abs(a - b).max() < 1e-4
 
 
-def test_golden_fixture(oracle):
-    """Committed output of the restatement on a short C1-style utterance (tests/golden/make_golden.py)."""
-    path = os.path.join(GOLDEN, "mfcc_c1_2s.npz")
-    g = np.load(path)
-    x = synth.utterance(int(g["n_samples"]), int(g["seed"]))
-    r = oracle.mfcc(oracle.frontend_cfg(), x)
-    assert np.array_equal(r["feats"], g["feats"])
-    assert np.array_equal(r["t_start"], g["t_start"]) and np.array_equal(r["t_end"], g["t_end"])
-
-
 @pytest.mark.parametrize("wt", ["hamming", "rectangular", "hanning", "periodic-hanning", "bartlett", "blackman", "kaiser"])
 def test_window_functions(oracle, wt):
     """the window types of src/Signal/WindowFunction.cc:62-132 against their textbook definitions (numpy, f64) and

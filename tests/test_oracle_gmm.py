@@ -113,17 +113,6 @@ def test_scales(oracle):
     assert s1.shape == a.shape
 
 
-def test_golden_fixture(oracle):
-    g = np.load(os.path.join(GOLDEN, "gmm_ragged.npz"))
-    ms = oracle.MixtureSet(**synth.ragged_mixture_set(dim=39, n_covariances=1))
-    f = synth.features(64, 39, seed=5)
-    assert np.array_equal(oracle.gmm_batch_float(ms, f), g["batch"])
-    mx, mb = oracle.gmm_diag_max(ms, f)
-    assert np.array_equal(mx, g["max"]) and np.array_equal(mb, g["max_best"])
-    sm, sb = oracle.gmm_diag_sum(ms, f)
-    assert np.array_equal(sm, g["sum"]) and np.array_equal(sb, g["sum_best"])
-
-
 # ---------------------------------------------------------------- Mm::BatchIntFeatureScorer (a12)
 
 def int_model_numpy(msd):
@@ -336,16 +325,3 @@ def test_std_sort_restatements_property(oracle):
     check()
 
 
-def test_golden_fixture_int_and_preselection(oracle):
-    """tests/golden/gmm_ragged_int_presel.npz (make_golden.py, item 4): the quantised scorer and both preselection
-    scorers on the ragged model, 16 clusters / 4 selected"""
-    g = np.load(os.path.join(GOLDEN, "gmm_ragged_int_presel.npz"))
-    ms = oracle.MixtureSet(**synth.ragged_mixture_set(dim=39, n_covariances=1))
-    f = synth.features(64, 39, seed=5)
-    assert np.array_equal(oracle.gmm_batch_int(ms, f), g["int"])
-    sc, cl, means = oracle.gmm_preselect_float(ms, f, clusters=16, select=4)
-    assert np.array_equal(sc, g["presel_float"]) and np.array_equal(cl, g["presel_float_cluster_of"])
-    assert np.array_equal(means, g["presel_float_means"])
-    for restated in (False, True):
-        sc, cl = oracle.gmm_preselect_int(ms, f, clusters=16, select=4, restated_sort=restated)
-        assert np.array_equal(sc, g["presel_int"]) and np.array_equal(cl, g["presel_int_cluster_of"])
