@@ -119,13 +119,13 @@ void FeatureScorer::addFeature(const Mm::FeatureVector& f) const {
     require(!bufferFilled());
     if (f.size() != dimension_)
         criticalError("feature has dimension %zu, mixture set expects %d", f.size(), int(dimension_));
-    features_.insert(features_.end(), f.begin(), f.end());
+    features_.append(f.data(), f.data() + f.size());
 }
 
 Mm::FeatureScorer::Scorer FeatureScorer::getScorer(const Mm::FeatureVector& f) const {
     if (f.size() != dimension_)
         criticalError("feature has dimension %zu, mixture set expects %d", f.size(), int(dimension_));
-    features_.insert(features_.end(), f.begin(), f.end());
+    features_.append(f.data(), f.data() + f.size());
     return flush();
 }
 

@@ -17,6 +17,7 @@
 #include <Mm/MixtureSet.hh>
 #include <vector>
 
+#include "B200HostBuffer.hh"
 #include "rasr_b200.h"
 
 namespace B200 {
@@ -83,8 +84,9 @@ protected:
 
 private:
     // all methods of the interface are const => the state is mutable (src/Mm/BatchFeatureScorer.hh:164-166)
-    mutable std::vector<f32> features_;  // T x D row-major, the segment so far
-    mutable std::vector<f32> scores_;    // T x nMix row-major, rows [0, nScored_)
+    // page-locked (B200HostBuffer.hh): the library's slab pipeline copies from / into these at the PCIe rate
+    mutable HostBuffer features_;  // T x D row-major, the segment so far
+    mutable HostBuffer scores_;    // T x nMix row-major, rows [0, nScored_)
     mutable u32              nScored_;
     mutable u32              nextFrame_;  // oldest frame that has no scorer yet
     mutable u32              segment_;    // guards delayed score() calls across reset()

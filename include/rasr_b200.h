@@ -49,6 +49,20 @@ int rb_device_count(void);
 /* kernels launched by this library since load (all handles, all threads) */
 uint64_t rb_launch_count(void);
 
+/* -------------------------------------------------------------------------------------
+ * Page-locked host memory.  Every host-buffer entry point below (rb_frontend_process*, rb_gmm_score, rb_nn_score,
+ * rb_pipeline_*) accepts any host pointer, but only from page-locked memory do the copies run asynchronously at the
+ * PCIe rate and overlap with the kernels (pageable memory is staged by the driver, every copy synchronous).  The
+ * adapters keep the buffered segment -- the reference's `std::vector<f32>` feature / score buffers, e.g.
+ * src/Mm/BatchFeatureScorer.hh:164-166, src/Nn/BatchFeatureScorer.hh -- in memory from rb_host_alloc; a host that
+ * cannot move its buffers registers them in place.
+ * ------------------------------------------------------------------------------------- */
+int  rb_host_alloc(size_t bytes, void** out); /* cudaHostAlloc, usable from every device */
+void rb_host_free(void* p);
+int  rb_host_register(void* p, size_t bytes); /* page-lock an existing allocation in place */
+int  rb_host_unregister(void* p);
+int  rb_host_is_pinned(const void* p);        /* 1: page-locked, 0: pageable / unknown */
+
 /* =====================================================================================
  * Front-end: the Flow network of src/Tools/FeatureExtraction/share/mfcc.flow:8-34
  *   signal-preemphasis -> signal-window (hamming) -> signal-real-fast-fourier-transform ->

@@ -24,6 +24,7 @@ NN_F32, NN_BF16 = 0, 1
 # every symbol include/rasr_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "rb_last_error", "rb_version", "rb_device_count", "rb_launch_count",
+    "rb_host_alloc", "rb_host_free", "rb_host_register", "rb_host_unregister", "rb_host_is_pinned",
     "rb_frontend_default_cfg", "rb_frontend_create", "rb_frontend_destroy", "rb_frontend_get_geometry",
     "rb_frontend_get_tables", "rb_frontend_nframes_for", "rb_frontend_reset", "rb_frontend_push",
     "rb_frontend_finish", "rb_frontend_nframes", "rb_frontend_read", "rb_frontend_count_frames",
@@ -118,6 +119,12 @@ def lib():
     L.rb_frontend_get_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rb_frontend_nframes_for.argtypes = [vp, C.c_long]
     L.rb_frontend_nframes_for.restype = C.c_long
+    L.rb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.rb_host_free.argtypes = [vp]
+    L.rb_host_free.restype = None
+    L.rb_host_register.argtypes = [vp, C.c_size_t]
+    L.rb_host_unregister.argtypes = [vp]
+    L.rb_host_is_pinned.argtypes = [vp]
     L.rb_frontend_reset.argtypes = [vp]
     L.rb_frontend_push.argtypes = [vp, vp, C.c_long, C.c_double]
     L.rb_frontend_finish.argtypes = [vp]
@@ -207,6 +214,37 @@ def ptr(a):
     if hasattr(a, "data_ptr"):
         return C.c_void_p(a.data_ptr())
     raise TypeError("cannot take the address of %r" % type(a))
+
+
+class _PinnedBlock:
+    """Owns one rb_host_alloc allocation; freed when the last numpy view of it goes away."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().rb_host_alloc(max(1, int(nbytes)), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and C is not None and _lib is not None:
+            _lib.rb_host_free(self.ptr)
+            self.ptr = None
+
+
+def host_empty(shape, dtype=np.float32):
+    """numpy array in page-locked host memory from rb_host_alloc (what the adapters keep their feature / score buffers
+    in): copies to and from it run asynchronously at the PCIe rate."""
+    dtype = np.dtype(dtype)
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(v) for v in shape)
+    n = int(np.prod(shape)) if shape else 1
+    block = _PinnedBlock(n * dtype.itemsize)
+    buf = (C.c_char * max(1, n * dtype.itemsize)).from_address(block.ptr.value)
+    a = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    buf._block = block  # the ctypes buffer is the numpy array's base: the block lives as long as any view of it
+    return a
+
+
+def host_is_pinned(a):
+    return bool(lib().rb_host_is_pinned(ptr(a)))
 
 
 def device_count():

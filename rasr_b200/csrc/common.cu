@@ -78,3 +78,62 @@ extern "C" int rb_device_count(void) {
 extern "C" uint64_t rb_launch_count(void) {
     return rb::g_launches.load();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// page-locked host memory for the caller's feature / score / sample buffers (the host-buffer entry points accept any
+// host pointer; from pageable memory every cudaMemcpyAsync is staged by the driver and synchronous)
+extern "C" int rb_host_alloc(size_t bytes, void** out) {
+    RB_REQUIRE(out != nullptr, "NULL output pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        rb::set_error("no CUDA device available; librasr_b200 has no CPU path");
+        return RB_ERR_NO_DEVICE;
+    }
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        rb::set_error("cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return RB_ERR_NOMEM;
+    }
+    return RB_OK;
+}
+
+extern "C" void rb_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess)
+        cudaGetLastError();
+}
+
+extern "C" int rb_host_register(void* p, size_t bytes) {
+    RB_REQUIRE(p != nullptr && bytes > 0, "bad argument");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        rb::set_error("cudaHostRegister of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? RB_ERR_NOMEM : RB_ERR_CUDA;
+    }
+    return RB_OK;
+}
+
+extern "C" int rb_host_unregister(void* p) {
+    RB_REQUIRE(p != nullptr, "bad argument");
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        rb::set_error("cudaHostUnregister failed: %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
+    return RB_OK;
+}
+
+// 1: page-locked (rb_host_alloc / rb_host_register / cudaHostAlloc), 0: pageable or unknown
+extern "C" int rb_host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}

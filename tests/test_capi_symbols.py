@@ -71,7 +71,7 @@ def test_product_package_never_imports_the_oracle():
         for fn in files:
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cc", "Makefile")):
                 text = open(os.path.join(dirpath, fn), errors="replace").read()
-                hit = re.search(r"(from|import)\s+oracle|liboracle|pyoracle|oracle\.h|\borc_[a-z]", text)
+                hit = re.search(r"(from|import)\s+oracle|liboracle|pyoracle|pyref|librasr_ref|oracle\.h|\borc_[a-z]|\bref_(mm|flow)_", text)
                 assert hit is None, (os.path.join(dirpath, fn), hit.group(0))
 
 
