@@ -1,4 +1,5 @@
 #include "B200FeatureScorer.hh"
+#include "B200NnNetwork.hh"
 
 #include <Math/Matrix.hh>
 #include <Math/Module.hh>
@@ -164,11 +165,7 @@ const Core::ParameterFloat        NnFeatureScorer::paramPrioriScale("priori-scal
 const Core::ParameterString       NnFeatureScorer::paramClassLabelFile("load-from-file", "class-labels: network-output-to-class-index mapping (Math::Vector<s32>, -1 = disregarded class)", "");
 const Core::ParameterBool         NnFeatureScorer::paramBf16("bf16", "bf16 operands with f32 accumulation on the tensor cores (false: f32 arithmetic)", true);
 
-NnFeatureScorer::NnFeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> ms)
-        : Core::Component(c),
-          FeatureScorer(c),
-          handle_(0) {
-    nMixtures_ = ms->nMixtures();
+void NnFeatureScorer::readParameterFiles(const Core::Configuration& c, NnNetwork& net) const {
     const std::vector<std::string> files = paramParameterFiles(c);
     if (files.empty())
         criticalError("b200-nn-batch-feature-scorer: no parameter-files given");
@@ -187,10 +184,14 @@ NnFeatureScorer::NnFeatureScorer(const Core::Configuration& c, Core::Ref<const M
 
     // one Math::Matrix per layer: row = output unit, column 0 = bias, the others the weights of that unit
     // (LinearLayer::setParameters, src/Nn/LinearLayer.cc:383-424); rb_nn_create takes weights[out][in] row-major
-    const int                     nLayers = files.size();
-    std::vector<int>              dims(nLayers + 1), acts(nLayers, hiddenAct);
-    std::vector<std::vector<f32>> weights(nLayers), biases(nLayers);
-    std::vector<const f32*>       wp(nLayers), bp(nLayers);
+    const int nLayers = files.size();
+    net.dims.assign(nLayers + 1, 0);
+    net.acts.assign(nLayers, hiddenAct);
+    net.weights.resize(nLayers);
+    net.biases.resize(nLayers);
+    std::vector<int>&              dims    = net.dims;
+    std::vector<std::vector<f32>>& weights = net.weights;
+    std::vector<std::vector<f32>>& biases  = net.biases;
     for (int l = 0; l < nLayers; ++l) {
         Math::Matrix<f32> parameters;
         log("reading parameter file ") << files[l] << " for layer " << l;
@@ -211,10 +212,29 @@ NnFeatureScorer::NnFeatureScorer(const Core::Configuration& c, Core::Ref<const M
             for (u32 k = 0; k < in; ++k)
                 weights[l][size_t(r) * in + k] = parameters[r][k + 1];
         }
-        wp[l] = weights[l].data();
-        bp[l] = biases[l].data();
     }
-    acts[nLayers - 1] = RB_ACT_SOFTMAX;  // output layer must be linear+softmax; only its scores are computed
+}
+
+NnFeatureScorer::NnFeatureScorer(const Core::Configuration& c, Core::Ref<const Mm::MixtureSet> ms)
+        : Core::Component(c),
+          FeatureScorer(c),
+          handle_(0) {
+    nMixtures_ = ms->nMixtures();
+    // the network: the reference's own configuration keys (neural-network.links, <layer>.layer-type, parameters-old ...,
+    // B200NnNetwork.hh) as Nn::BatchFeatureScorer reads them through Nn::NeuralNetwork (src/Nn/BatchFeatureScorer.cc:58-67),
+    // or -- for set-ups without a layer description -- an explicit list of parameter files
+    NnNetwork net;
+    if (NnNetwork::configured(c)) {
+        if (!net.read(*this, c))
+            return;
+        if (!net.topIsLinearAndSoftmax)
+            criticalError("output layer must be of type 'linear+softmax'");
+    }
+    else
+        readParameterFiles(c, net);
+    const int         nLayers = net.nLayers();
+    std::vector<int>& dims    = net.dims;
+    net.acts[nLayers - 1]     = RB_ACT_SOFTMAX;  // only the scores of the output layer are computed
     dimension_        = dims[0];
     // Nn::ClassLabelWrapper (src/Nn/ClassLabelWrapper.cc:33-100): emission class -> network output from the file
     // the reference's wrapper saves (class-labels.load-from-file), else the identity
@@ -254,9 +274,9 @@ NnFeatureScorer::NnFeatureScorer(const Core::Configuration& c, Core::Ref<const M
         for (u32 o = 0; o < nOut; ++o)
             logPrior[o] = std::log(logPrior[o] / observationWeight);
     }
-    if (rb_nn_create(nLayers, dims.data(), acts.data(), wp.data(), bp.data(), logPrior.data(), paramPrioriScale(c),
-                     paramBf16(c) ? RB_NN_BF16 : RB_NN_F32, paramDevice(c), &handle_) != RB_OK)
-        criticalError("rasr_b200: %s", rb_last_error());
+    handle_ = net.create(*this, logPrior, paramPrioriScale(c), paramBf16(c), paramDevice(c));
+    if (!handle_)
+        return;
     if (!classToOutput.empty() && rb_nn_set_class_mapping(handle_, classToOutput.size(), classToOutput.data()) != RB_OK)
         criticalError("rasr_b200: %s", rb_last_error());
     log("b200 nn feature scorer: %d layers, %d inputs, %d outputs on device %d", nLayers, dims[0], dims[nLayers],

@@ -120,9 +120,11 @@ public:
 };
 
 /** Feed-forward network scorer: score(e) = -(w_e.h + b_e - priori-scale * logprior_e), the top-layer softmax is not
- *  evaluated (src/Nn/BatchFeatureScorer.cc:45-171, LinearAndActivationLayer.cc:154-160).  The network is given as
- *  one parameter file per layer in the reference's Math::Matrix format (row = output unit, column 0 = bias,
- *  src/Nn/LinearLayer.cc:219-237,383-424) plus the hidden activation; the prior comes from `prior-file` or, like
+ *  evaluated (src/Nn/BatchFeatureScorer.cc:45-171, LinearAndActivationLayer.cc:154-160).  The network is described
+ *  by the reference's own configuration keys (neural-network.links, <layer>.layer-type / dimension-* / links,
+ *  parameters-old: see B200NnNetwork.hh), so a configuration written for nn-batch-feature-scorer works unchanged;
+ *  without a layer description the legacy `parameter-files` list (one Math::Matrix per layer, row = output unit,
+ *  column 0 = bias, src/Nn/LinearLayer.cc:383-424) plus `hidden-activation` is used.  The prior comes from `prior-file` or, like
  *  Prior::setFromMixtureSet (src/Nn/Prior.cc:158-188), from the mixture weights.  Emission classes map to network
  *  outputs through the Nn::ClassLabelWrapper file (class-labels.load-from-file; disregarded classes score FLT_MAX,
  *  src/Nn/BatchFeatureScorer.cc:163-169), else one-to-one. */
@@ -142,6 +144,8 @@ protected:
     virtual void scoreFrames(const f32* feats, u32 T, f32* scores) const;
 
 private:
+    void readParameterFiles(const Core::Configuration& c, struct NnNetwork& net) const;
+
     rb_nn* handle_;
 };
 

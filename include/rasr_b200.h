@@ -126,6 +126,11 @@ int rb_frontend_get_tables(const rb_frontend* h, float* window, int* fb_start, i
 /* frames the window node emits for one segment of n samples (WindowBuffer get/flush protocol,
  * src/Signal/WindowBuffer.cc:50-126, flush-all=false) */
 long rb_frontend_nframes_for(const rb_frontend* h, long n_samples);
+/* Timestamp (src/Flow/Timestamp.hh:39-44) of every packet the chain emits for a segment of n_samples samples whose first
+ * sample is at start_time: start accumulated by repeated += shift / sample rate as WindowBuffer does
+ * (src/Signal/WindowBuffer.cc:94), merged over the regression window when derivatives are on
+ * (src/Flow/Merger.hh:79-101).  t_start / t_end [frames] may be NULL; returns the number of frames.  Host only. */
+long rb_frontend_timestamps(const rb_frontend* h, long n_samples, double start_time, double* t_start, double* t_end);
 
 /* --- streaming protocol = what Flow::Node::work() sees (src/Signal/SlidingAlgorithmNode.hh:60-80):
  * packets of samples arrive in time order; on the EOS sentinel the segment is computed. */

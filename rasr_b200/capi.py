@@ -26,7 +26,7 @@ SYMBOLS = [
     "rb_last_error", "rb_version", "rb_device_count", "rb_launch_count",
     "rb_host_alloc", "rb_host_free", "rb_host_register", "rb_host_unregister", "rb_host_is_pinned",
     "rb_frontend_default_cfg", "rb_frontend_create", "rb_frontend_destroy", "rb_frontend_get_geometry",
-    "rb_frontend_get_tables", "rb_frontend_nframes_for", "rb_frontend_reset", "rb_frontend_push",
+    "rb_frontend_get_tables", "rb_frontend_nframes_for", "rb_frontend_timestamps", "rb_frontend_reset", "rb_frontend_push",
     "rb_frontend_finish", "rb_frontend_nframes", "rb_frontend_read", "rb_frontend_count_frames",
     "rb_frontend_process", "rb_frontend_process_s16", "rb_frontend_process_dev", "rb_frontend_set_debug", "rb_frontend_read_stages",
     "rb_dc_default_cfg", "rb_frontend_dc_max_frames", "rb_frontend_process_dc", "rb_frontend_dc_runs", "rb_frontend_set_dc_detection",
@@ -125,6 +125,8 @@ def lib():
     L.rb_host_register.argtypes = [vp, C.c_size_t]
     L.rb_host_unregister.argtypes = [vp]
     L.rb_host_is_pinned.argtypes = [vp]
+    L.rb_frontend_timestamps.argtypes = [vp, C.c_long, C.c_double, vp, vp]
+    L.rb_frontend_timestamps.restype = C.c_long
     L.rb_frontend_reset.argtypes = [vp]
     L.rb_frontend_push.argtypes = [vp, vp, C.c_long, C.c_double]
     L.rb_frontend_finish.argtypes = [vp]

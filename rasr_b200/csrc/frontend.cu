@@ -1307,6 +1307,16 @@ extern "C" long rb_frontend_nframes_for(const rb_frontend* h, long n_samples) {
     return h ? frames_for(h, n_samples) : 0;
 }
 
+extern "C" long rb_frontend_timestamps(const rb_frontend* h, long n_samples, double start_time, double* t_start,
+                                       double* t_end) {
+    if (!h || n_samples < 0)
+        return -1;
+    const long T = frames_for(h, n_samples);
+    if (T > 0)
+        timestamps(h, n_samples, start_time, T, t_start, t_end);
+    return T;
+}
+
 extern "C" long rb_frontend_count_frames(const rb_frontend* h, const int64_t* offsets, int n_utt,
                                          int64_t* frame_offsets) {
     if (!h || !offsets || n_utt < 0)
