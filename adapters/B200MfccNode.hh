@@ -48,7 +48,7 @@ public:
     virtual bool configure();
     virtual bool work(Flow::PortId p);
 
-private:
+protected:  // b200-audio-feature-scorer (B200Nodes.hh) builds on this node
     bool ensureHandle();
     void computeSegment();
 

@@ -6,6 +6,7 @@
 
 #include "B200FeatureScorer.hh"
 #include "B200MfccNode.hh"
+#include "B200Nodes.hh"
 
 namespace B200 {
 
@@ -21,6 +22,9 @@ Module_::Module_() {
     f->registerFeatureScorer<FeatureScorerOf<RB_GMM_BATCH_PRESELECT_INT>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 7, "b200-preselection-batch-int");
     f->registerFeatureScorer<NnFeatureScorer, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 5, "b200-nn-batch-feature-scorer");
     Flow::Registry::instance().registerFilter<MfccNode>();
+    Flow::Registry::instance().registerFilter<NnForwardNode>();
+    Flow::Registry::instance().registerFilter<PostprocessingNode>();
+    Flow::Registry::instance().registerFilter<AudioScorerNode>();
 }
 
 }  // namespace B200

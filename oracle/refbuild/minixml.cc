@@ -374,4 +374,8 @@ int xmlSAX2GetColumnNumber(void* ctx) {
 xmlParserInputPtr resolveEntity(void*, const xmlChar*, const xmlChar*) {
     return 0;
 }
+xmlDictPtr xmlDictCreate(void) {
+    return 0;
+}
+void xmlDictFree(xmlDictPtr) {}
 }

@@ -157,6 +157,7 @@ const char* ref_last_error() {
 
 /* creates the application object and registers the flow filters; log_file = NULL: /dev/null */
 int ref_init(const char* log_file);
+void ref_register_nn();
 
 int ref_init(const char* log_file) {
     if (app)
@@ -177,6 +178,7 @@ int ref_init(const char* log_file) {
     INIT_MODULE(Flow);
     INIT_MODULE(Signal);
     INIT_MODULE(Mm);
+    ref_register_nn();  // neural-network-forward, nn-batch-feature-scorer ... (ref_nn.cc, as src/Nn/Module.cc:100-115)
     Flow::Registry::instance().registerFilter<SampleSourceNode>();
     return 0;
 }

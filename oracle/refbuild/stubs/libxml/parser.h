@@ -71,6 +71,9 @@ const xmlChar* xmlSAX2GetSystemId(void* ctx);
 int  xmlSAX2GetLineNumber(void* ctx);
 int  xmlSAX2GetColumnNumber(void* ctx);
 xmlParserInputPtr resolveEntity(void* ctx, const xmlChar* publicId, const xmlChar* systemId);
+/* src/Math/Random.cc:31-37 creates and frees a dictionary once to initialise libxml2's random seed */
+xmlDictPtr xmlDictCreate(void);
+void       xmlDictFree(xmlDictPtr dict);
 #ifdef __cplusplus
 }
 #endif

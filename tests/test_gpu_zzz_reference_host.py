@@ -164,3 +164,121 @@ def test_adapter_buffer_sizes(ref, oms, buffer_size):
     a = ref.FeatureScorer(ms, "batch-diagonal-maximum-float", native=True).score(f)
     b = ref.FeatureScorer(ms, "b200-batch-float", {"buffer-size": buffer_size}, native=True).score(f)
     assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the other adapters: Nn scorer and forward node configured with the REFERENCE's keys, post-processing node, and the
+# fused audio -> scores node -- each against the reference's own component in the same process
+
+from tests.helpers_nn import NN_FLOW, nn_files  # noqa: E402  (same configuration / file helpers as the CPU suite)
+from rasr_b200 import io  # noqa: E402
+
+
+@pytest.mark.parametrize("hidden", ["sigmoid", "relu"])
+def test_nn_scorer_reads_the_references_configuration(ref, oms, tmp_path, diag, hidden):
+    """b200-nn-batch-feature-scorer given exactly the configuration of nn-batch-feature-scorer (neural-network.links,
+    layer-type, dimension-*, parameters-old, prior-file, priori-scale): f32 path within 1e-5, bf16 path within the stated
+    bf16 tolerance (2e-3 of scale; bf16 cannot meet 1e-4 against f32 sgemm)"""
+    net = synth.network(dims=(45, 96, 64, 40), hidden=hidden, seed=3)
+    cfg = nn_files(tmp_path, net, hidden)
+    io.write_vector("xml:" + str(tmp_path / "prior.xml"), net["log_prior"])
+    cfg.update({"prior-file": "xml:" + str(tmp_path / "prior.xml"), "priori-scale": 0.7})
+    ms = oms.MixtureSet(**synth.mixture_set(dim=45, n_mixtures=40, densities_per_mixture=1))
+    x = synth.features(333, 45, seed=9, scale=1.0)
+    want = ref.FeatureScorer(ms, "nn-batch-feature-scorer", cfg, native=True).score(x)
+    f32 = ref.FeatureScorer(ms, "b200-nn-batch-feature-scorer", dict(cfg, bf16="false"), native=True).score(x)
+    bf16 = ref.FeatureScorer(ms, "b200-nn-batch-feature-scorer", cfg, native=True).score(x)
+    scale = np.abs(want).max()
+    e32, e16 = float(np.abs(f32 - want).max() / scale), float(np.abs(bf16 - want).max() / scale)
+    diag("adapter_nn_scorer_" + hidden, f32=e32, bf16=e16)
+    assert e32 < 1e-5 and e16 < 2e-3
+
+
+def test_nn_forward_node_against_the_references_node(ref, tmp_path, diag):
+    net = synth.network(dims=(45, 96, 40), hidden="sigmoid", seed=6)
+    cfg = nn_files(tmp_path, net, "sigmoid")
+    io.write_vector("xml:" + str(tmp_path / "prior.xml"), net["log_prior"])
+    cfg.update({"prior-file": "xml:" + str(tmp_path / "prior.xml"), "priori-scale": 0.5})
+    out = {}
+    for sel, filt in (("nnref", "neural-network-forward"), ("nnb200", "b200-neural-network-forward")):
+        for k, v in cfg.items():
+            ref.config_set("*.%s.nn.%s" % (sel, k), v, native=True)
+        ref.config_set("*.%s.nn.bf16" % sel, "false", native=True)
+        (tmp_path / (sel + ".flow")).write_text(NN_FLOW % filt)
+        x = synth.features(200, 45, seed=12, scale=1.0)
+        out[sel] = ref.FlowNetwork(str(tmp_path / (sel + ".flow")), {"block-size": 45}, native=True,
+                                   selection=sel).run(x.reshape(-1), sample_rate=4500.0)
+    a, b = out["nnref"], out["nnb200"]
+    assert a["feats"].shape == b["feats"].shape == (200, 40)
+    err = float(np.abs(a["feats"] - b["feats"]).max())
+    diag("adapter_nn_forward_node", err=err)
+    assert err < 1e-6  # posteriors (softmax, prior removed from the bias), f32 path
+    # the adapter carries the input packet's time stamps (the reference emits [1, 1]: see tests/test_ref_parity.py)
+    assert np.allclose(b["t_start"], np.arange(200) * 0.01) and np.allclose(b["t_end"], (np.arange(200) + 1) * 0.01)
+
+
+POSTPROC_FLOW = """<?xml version="1.0" encoding="ISO-8859-1"?>
+<network name="network">
+  <out name="projected"/>
+  <param name="block-size"/>
+  <param name="norm-type"/> <param name="norm-length"/> <param name="norm-right"/>
+  <param name="splice-length"/> <param name="splice-right"/> <param name="matrix-file"/>
+  <node name="source" filter="ref-sample-source" block-size="$(block-size)"/>
+  <node name="post" filter="b200-feature-postprocessing" normalization-type="$(norm-type)"
+        normalization-length="$(norm-length)" normalization-right="$(norm-right)" window-max-size="$(splice-length)"
+        window-right="$(splice-right)" matrix-file="$(matrix-file)" fma-contraction="false"/>
+  <link from="source" to="post"/>
+  <link from="post" to="network:projected"/>
+</network>
+"""
+
+
+@pytest.mark.parametrize("kind,length,right", [("mean-and-variance", "infinite", "infinite"), ("mean", 51, 25)])
+def test_postprocessing_node_against_the_references_nodes(ref, tmp_path, kind, length, right):
+    """one node instead of signal-normalization -> sequence concatenation -> matrix multiplication: identical bits and
+    identical time stamps (strict arithmetic on both sides)"""
+    f = synth.features(300, 13, seed=5)
+    M = np.random.default_rng(3).standard_normal((20, 65)).astype(np.float32)
+    path = "bin:%s" % (tmp_path / "lda.bin")
+    io.write_matrix(path, M)
+    P = {"block-size": 13, "norm-type": kind, "norm-length": length, "norm-right": right, "splice-length": 5,
+         "splice-right": 2, "matrix-file": path}
+    (tmp_path / "post.flow").write_text(POSTPROC_FLOW)
+    a = ref.FlowNetwork("postproc_chain.flow", P, native=True).run(f.reshape(-1), port="projected", sample_rate=1300.0)
+    b = ref.FlowNetwork(str(tmp_path / "post.flow"), P, native=True).run(f.reshape(-1), port="projected", sample_rate=1300.0)
+    assert a["feats"].shape == b["feats"].shape == (300, 20)
+    # the native reference build contracts the matrix product; the strict comparison is in the golden test
+    assert np.abs(a["feats"] - b["feats"]).max() / np.abs(a["feats"]).max() < 1e-6
+    assert np.array_equal(a["t_start"], b["t_start"]) and np.array_equal(a["t_end"], b["t_end"])
+
+
+AUDIO_FLOW = """<?xml version="1.0" encoding="ISO-8859-1"?>
+<network name="network">
+  <out name="scores"/>
+  <param name="block-size"/>
+  <node name="source" filter="ref-sample-source" block-size="$(block-size)"/>
+  <node name="scorer" filter="b200-audio-feature-scorer"/>
+  <link from="source" to="scorer"/>
+  <link from="scorer" to="network:scores"/>
+</network>
+"""
+
+
+def test_audio_to_scores_node(ref, oms, tmp_path, diag):
+    """b200-audio-feature-scorer: samples in, +log scores out, features never leave the device.  Against the reference's
+    own chain: its MFCC network, then its batch scorer on those features, negated as Speech::FeatureScorerNode does.
+    The mixture set travels as a text file (.pms) written by rasr_b200.io and read by the reference's MixtureSetReader."""
+    msd = synth.mixture_set(n_mixtures=48)
+    io.write_mixture_set(str(tmp_path / "model.pms"), msd)
+    ref.config_set("*.audioflow.scorer.mixture-set.file", str(tmp_path / "model.pms"), native=True)
+    ref.config_set("*.audioflow.scorer.feature-scorer.feature-scorer-type", "batch-diagonal-maximum-float", native=True)
+    (tmp_path / "audio.flow").write_text(AUDIO_FLOW)
+    x = synth.utterance(48240, seed=41)
+    got = ref.FlowNetwork(str(tmp_path / "audio.flow"), {"block-size": 4096}, native=True, selection="audioflow").run(x, port="scores")
+    feats = ref.FlowNetwork("mfcc_chain_plain.flow", ref.chain_parameters(), native=True).run(x)
+    want = -ref.FeatureScorer(oms.MixtureSet(**msd), "batch-diagonal-maximum-float", native=True).score(feats["feats"])
+    assert got["feats"].shape == want.shape == (300, 48)
+    assert np.array_equal(got["t_start"], feats["t_start"]) and np.array_equal(got["t_end"], feats["t_end"])
+    rel = float((np.abs(got["feats"] - want) / np.abs(want)).max())
+    diag("adapter_audio_scorer_node", rel=rel)
+    assert rel < RTOL

@@ -15,6 +15,7 @@ import numpy as np
 import pytest
 
 from rasr_b200 import io, synth
+from tests.helpers_nn import NN_FLOW, nn_files
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -338,3 +339,66 @@ def test_buffer_size_does_not_change_scores(ref, oracle, buffer_size):
     f = synth.features(50, 39, seed=2)
     got = ref.FeatureScorer(ms, "batch-diagonal-maximum-float", {"buffer-size": buffer_size}).score(f)
     assert np.array_equal(got, oracle.gmm_batch_float(ms, f, use_fma=False))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# legacy Nn module (rows a15-a17): the reference's own Nn::BatchFeatureScorer and neural-network-forward node, configured
+# with the reference's keys, parameter / prior files written by rasr_b200.io (row f3) -- against the oracle's f32 path.
+# The BLAS below the reference is the plain-loop stand-in (oracle/refbuild/miniblas.cc), sequential f32 accumulation.
+
+@pytest.mark.parametrize("hidden", ["sigmoid", "relu", "tanh"])
+def test_nn_batch_feature_scorer(ref, oracle, tmp_path, hidden):
+    net = synth.network(dims=(20, 32, 24, 16), hidden=hidden, seed=3)
+    cfg = nn_files(tmp_path, net, hidden)
+    io.write_vector("xml:" + str(tmp_path / "prior.xml"), net["log_prior"])
+    cfg.update({"prior-file": "xml:" + str(tmp_path / "prior.xml"), "priori-scale": 0.7, "buffer-size": 8})
+    ms = oracle.MixtureSet(**synth.mixture_set(dim=20, n_mixtures=16, densities_per_mixture=1))
+    x = synth.features(37, 20, seed=9, scale=1.0)
+    got = ref.FeatureScorer(ms, "nn-batch-feature-scorer", cfg).score(x)
+    want = oracle.nn_scores(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 0.7, x,
+                            mode=oracle.NN_F32)
+    assert got.shape == (37, 16)
+    if hidden == "tanh":  # tanh of libm vs the oracle's formulation: an ulp
+        assert np.abs(got - want).max() / np.abs(want).max() < 1e-6
+    else:
+        assert np.array_equal(got, want)
+
+
+def test_nn_prior_from_mixture_weights(ref, oracle, tmp_path):
+    """without a prior file the prior is the relative mixture-weight mass of each class (Prior::setFromMixtureSet,
+    src/Nn/Prior.cc:158-188)"""
+    net = synth.network(dims=(12, 16, 8), hidden="sigmoid", seed=5)
+    cfg = nn_files(tmp_path, net, "sigmoid")
+    msd = synth.ragged_mixture_set(dim=12, sizes=(1, 3, 2, 5, 1, 4, 2, 2), seed=4)
+    # linear weights (not normalised per mixture) so that the classes carry different mass
+    rng = np.random.default_rng(1)
+    msd["mix_log_weight"] = np.log(rng.uniform(0.1, 2.0, msd["mix_log_weight"].size))
+    ms = oracle.MixtureSet(**msd)
+    x = synth.features(20, 12, seed=10, scale=1.0)
+    got = ref.FeatureScorer(ms, "nn-batch-feature-scorer", cfg).score(x)
+    mass = np.array([np.exp(msd["mix_log_weight"][a:b]).astype(np.float32).sum(dtype=np.float32)
+                     for a, b in zip(msd["mix_offsets"][:-1], msd["mix_offsets"][1:])], np.float32)
+    log_prior = np.log(mass / mass.sum(dtype=np.float32))
+    want = oracle.nn_scores(net["dims"], net["acts"], net["weights"], net["biases"], log_prior, 1.0, x, mode=oracle.NN_F32)
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
+
+
+def test_neural_network_forward_node(ref, oracle, tmp_path):
+    """the reference's neural-network-forward Flow node (src/Nn/NeuralNetworkForwardNode.cc): softmax output, one packet
+    per input packet with its time stamp, buffer size irrelevant"""
+    net = synth.network(dims=(20, 32, 16), hidden="sigmoid", seed=6)
+    cfg = nn_files(tmp_path, net, "sigmoid")
+    for k, v in cfg.items():
+        ref.config_set("*.nnflow.nn." + k, v)
+    ref.config_set("*.nnflow.nn.buffer-size", 7)
+    (tmp_path / "nn.flow").write_text(NN_FLOW % "neural-network-forward")
+    x = synth.features(45, 20, seed=12, scale=1.0)
+    r = ref.FlowNetwork(str(tmp_path / "nn.flow"), {"block-size": 20}, selection="nnflow").run(x.reshape(-1), sample_rate=2000.0)
+    want = oracle.nn_forward(net["dims"], net["acts"], net["weights"], net["biases"], x, mode=oracle.NN_F32)
+    assert r["feats"].shape == want.shape
+    assert np.abs(r["feats"] - want).max() < 1e-6 and np.allclose(r["feats"].sum(axis=1), 1.0, atol=1e-5)
+    # NeuralNetworkForwardNode::putNextFeature (src/Nn/NeuralNetworkForwardNode.cc:171) means to copy the input packet's
+    # time stamp, but its `cond ? aggregateBuffer_[i] : featureBuffer_[i]` mixes two DataPtr types, which only convert
+    # to each other through bool: every output packet of the reference carries the time stamp [1, 1].  The adapter
+    # (b200-neural-network-forward) carries the input packet's time stamp, as the statement intends.
+    assert np.array_equal(r["t_start"], np.ones(45)) and np.array_equal(r["t_end"], np.ones(45))
