@@ -651,6 +651,118 @@ class Bench:
             roofline=dict(bound="hbm", achieved=gbs, peak=self.peaks["hbm"], unit="GB/s", frac=gbs / self.peaks["hbm"]))}
 
 
+    # ---------------- north_star: "allgather of the score matrix only where a single decoder rank consumes all frames".
+    # C3 shard per rank (125 utterances x 1000 frames x 256 scores = 128 MB), gathered into every rank's window (all-gather)
+    # or into rank 0's (gather): the engine's own exchange over NVLink peer memory (push kernel; scorer epilogue storing
+    # straight into the consumer's HBM) next to NCCL on the same buffers.  Device-timed, max over ranks.
+    def gather_variants(self, steps, warmup):
+        torch, dev, sptr, world, rank = self.torch, self.dev, self.sptr, self.world, self.rank
+        from rasr_b200 import comm, flow, mm, pipeline, synth
+
+        n_utt = 125
+        samples_h, offs = synth.corpus(n_utt, n_samples=160240, seed0=3000 + 1000 * rank)
+        fe = flow.FrontEnd(device=self.local_rank)
+        scorer = mm.GmmScorer(mm.MixtureSet.from_dict(synth.mixture_set()), device=self.local_rank)
+        T = int(fe.count_frames(offs)[-1])
+        row_offsets = np.arange(world + 1, dtype=np.int64) * T
+        ex = comm.ScoreExchange(world, rank, self.local_rank, row_offsets, 256, comm.torch_exchange(self.dist), nccl=True)
+        d_samples = torch.from_numpy(samples_h).to(dev)
+        d_feats = torch.empty((T, 39), dtype=torch.float32, device=dev)
+        d_local = torch.empty((T, 256), dtype=torch.float32, device=dev)
+        own = ex.target(rank)
+        shard_bytes = T * 256 * 4
+
+        def timed(fn):
+            for _ in range(warmup):
+                fn()
+            self.barrier()
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(self.stream)
+            for _ in range(steps):
+                fn()
+            ev[1].record(self.stream)
+            self.barrier()
+            return self.max_over_ranks(ev[0].elapsed_time(ev[1]) / steps)
+
+        def score(out):
+            pipeline.score_utterances_dev(fe, scorer, d_samples, offs, d_feats, out, sptr)
+
+        def v_compute():
+            score(d_local)
+
+        def v_p2p():
+            ex.gather(d_local, -1, "p2p", sptr)
+            ex.barrier(sptr)
+
+        def v_nccl():
+            ex.gather(own, -1, "nccl", sptr)
+
+        def v_step_p2p():
+            score(own)
+            ex.gather(own, -1, "p2p", sptr)
+            ex.barrier(sptr)
+
+        def v_step_nccl():
+            score(own)
+            ex.gather(own, -1, "nccl", sptr)
+
+        # the all-gather pipelined behind the scorer: the shard is scored in 5 slabs of whole utterances into this
+        # rank's own window, every finished slab is pushed to the peers from a second stream while the next one is
+        # being scored; only the last slab's push is exposed
+        side = torch.cuda.Stream(device=dev)
+        fo = fe.count_frames(offs)
+        cuts = [n_utt * k // 5 for k in range(6)]
+        sample_pos = [int(offs[c]) for c in cuts]
+        slab_ev = [torch.cuda.Event() for _ in range(5)]
+        done_ev = torch.cuda.Event()
+        row0 = int(row_offsets[rank])
+
+        def v_step_p2p_slabs():
+            for k in range(5):
+                u0, u1 = cuts[k], cuts[k + 1]
+                f0, f1 = int(fo[u0]), int(fo[u1])
+                pipeline.score_utterances_dev(fe, scorer, d_samples[sample_pos[k]:], offs[u0:u1 + 1] - offs[u0],
+                                              d_feats[f0:], own + f0 * 1024, sptr)
+                slab_ev[k].record(self.stream)
+                side.wait_event(slab_ev[k])
+                ex.push_rows(own + f0 * 1024, row0 + f0, f1 - f0, -1, side.cuda_stream)
+            done_ev.record(side)
+            self.stream.wait_event(done_ev)
+            ex.barrier(sptr)
+
+        def v_step_fused_root():
+            score(ex.target(0))
+            ex.barrier(sptr)
+
+        def v_step_push_root():
+            score(d_local)
+            ex.gather(d_local, 0, "p2p", sptr)
+            ex.barrier(sptr)
+
+        out = dict(shard_bytes=shard_bytes, gathered_bytes=shard_bytes * world, frames_per_rank=T,
+                   nccl_version=comm.nccl_version(),
+                   note="ms per step, CUDA events on the launching stream, max over ranks; GB/s = bytes arriving in ONE "
+                        "rank's window per second ((world-1) shards for the all-gathers and for the root of the gathers)")
+        t_compute = timed(v_compute)
+        out["compute_only_ms"] = t_compute
+        arriving = shard_bytes * (world - 1)
+        for name, fn, with_compute in (("allgather_p2p", v_p2p, False), ("allgather_nccl", v_nccl, False),
+                                       ("step_allgather_p2p", v_step_p2p, True), ("step_allgather_nccl", v_step_nccl, True),
+                                       ("step_allgather_p2p_5_slabs_overlapped", v_step_p2p_slabs, True),
+                                       ("step_gather_root0_fused_epilogue", v_step_fused_root, True),
+                                       ("step_gather_root0_push", v_step_push_root, True)):
+            ms = timed(fn)
+            d = dict(ms=ms)
+            if with_compute:
+                d["frames_per_s"] = T * world / (ms * 1e-3)
+                d["exposed_exchange_ms"] = ms - t_compute
+            else:
+                d["gbs_in_per_rank"] = arriving / (ms * 1e-3) / 1e9
+            out[name] = d
+        ex.close()
+        return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -661,6 +773,8 @@ def main():
                     help="all (default): the C2 headline plus C3 / C4 / C5 under 'workloads'; else that workload alone")
     ap.add_argument("--frames", type=int, default=0, help="override the frame count of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1: add the score exchange (own NVLink push / fused epilogue vs NCCL) under 'gather'")
     ap.add_argument("--cpu-seconds", type=float, default=0.0, help="reference arm: CPU seconds per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -681,7 +795,8 @@ def main():
     numa = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     sampler = ClockSampler(local_rank)
     sampler.start()
     b = Bench(args, torch, dist, rank, local_rank, world, sampler)
@@ -713,6 +828,12 @@ def main():
             extra[key] = me
             del we
         line["workloads"] = extra
+    if world > 1 and (args.gather or args.workload == "all"):
+        torch.cuda.empty_cache()
+        try:
+            line["gather"] = b.gather_variants(max(3, min(args.steps, 10)), 3)
+        except Exception as e:  # noqa: BLE001 -- e.g. no peer access on this box: reported, the scoring numbers stand
+            line["gather"] = dict(unavailable=str(e)[:300])
     sampler.stop()
 
     if rank == 0:
@@ -722,6 +843,8 @@ def main():
                                     "nn": cpu_baseline_nn}[head]()
         print(json.dumps(line), flush=True)
     if world > 1:
+        if isinstance(line.get("gather"), dict) and "unavailable" in line["gather"]:
+            os._exit(0)  # the device context may be gone (trapped barrier): do not wait for a collective teardown
         dist.destroy_process_group()
 
 

@@ -409,6 +409,57 @@ int rb_pipeline_search(rb_frontend* fe, rb_gmm* gmm, rb_search* ls, const void* 
                        const int64_t* offsets, int n_utt);
 
 /* =====================================================================================
+ * Exchange of the score matrix between the GPUs of one box.  The reference has no collective: its only
+ * parallelism is N independent processes over corpus partitions (src/Bliss/CorpusDescription.cc:173-180,482-491).  This
+ * serves the one case where a single decoder rank consumes the frames of every shard: the rows
+ * [row_offsets[r], row_offsets[r+1]) of the gathered matrix [row_offsets[world] x row_len] f32 come from rank r.
+ * One process per GPU; the processes exchange two small byte strings through whatever the host has (MPI,
+ * torch.distributed, files) -- the library has no transport of its own.
+ *   rb_comm_create              on every rank (selects `device`)
+ *   rb_comm_window_alloc        the window = this rank's copy of the gathered matrix in HBM; `handle`
+ *                               [RB_COMM_HANDLE_BYTES] is what the peers need to map it
+ *   rb_comm_window_attach       handles [world * RB_COMM_HANDLE_BYTES] in rank order: maps every peer's window (CUDA IPC;
+ *                               RB_ERR_UNSUPPORTED without peer access)
+ *   rb_comm_window_ptr          device pointer of rank `peer`'s window in THIS process: passing
+ *                               (float*)ptr + row_offsets[rank] * row_len as d_scores to rb_gmm_score_dev /
+ *                               rb_pipeline_score_dev / rb_nn_score_dev makes the scorer's epilogue store straight into
+ *                               the consumer's HBM over NVLink (compute and transfer fused, no local copy)
+ *   rb_comm_gather_scores_dev   root < 0: all-gather, else gather to `root`.  RB_COMM_P2P: one kernel of 128-bit loads
+ *                               and NVLink stores into the peers' windows (skips the local copy when d_send already is
+ *                               this rank's slice of its own window); RB_COMM_NCCL: ncclAllGather (equal shards) or
+ *                               grouped in-place ncclBroadcasts (unequal shards; no padding, no staging copy).  Only
+ *                               enqueues on `stream` (NULL: the communicator's own).
+ *   rb_comm_barrier_dev         device-side barrier of all ranks on `stream`: once it has passed, everything the peers
+ *                               stored into this rank's window before THEIR barrier is visible to the kernels enqueued
+ *                               behind it (needed after P2P stores; also call it before a window is overwritten).  A
+ *                               peer that never arrives traps the kernel after ~10 s instead of hanging the GPU.
+ *   rb_comm_nccl_unique_id      rank 0 creates the id [RB_COMM_ID_BYTES], the host distributes it,
+ *   rb_comm_nccl_init           every rank joins (collective).  libnccl.so.2 is resolved at run time.
+ * ===================================================================================== */
+typedef struct rb_comm rb_comm;
+#define RB_COMM_HANDLE_BYTES 64
+#define RB_COMM_ID_BYTES 128
+enum { RB_COMM_P2P = 0, RB_COMM_NCCL = 1 };
+
+int  rb_comm_create(int world, int rank, int device, rb_comm** out);
+void rb_comm_destroy(rb_comm* c);
+int  rb_comm_world(const rb_comm* c);
+int  rb_comm_rank(const rb_comm* c);
+int  rb_comm_window_alloc(rb_comm* c, size_t bytes, void** d_window, void* handle);
+int  rb_comm_window_attach(rb_comm* c, const void* handles);
+int  rb_comm_window_ptr(const rb_comm* c, int peer, void** d_ptr);
+int  rb_comm_gather_scores_dev(rb_comm* c, const float* d_send, const int64_t* row_offsets, int row_len, int root,
+                               int transport, void* stream);
+/* P2P push of a row range: rows [first_row, first_row + n_rows) of the gathered matrix, read from d_send, go to `root`
+ * (or to every rank, root < 0).  Lets the host pipeline the exchange slab by slab behind the scorer (second stream). */
+int  rb_comm_push_rows_dev(rb_comm* c, const float* d_send, int64_t first_row, int64_t n_rows, int row_len, int root,
+                           void* stream);
+int  rb_comm_barrier_dev(rb_comm* c, void* stream);
+int  rb_comm_nccl_unique_id(void* id);
+int  rb_comm_nccl_init(rb_comm* c, const void* id);
+int  rb_comm_nccl_version(void); /* e.g. 22809; 0 when libnccl.so.2 cannot be loaded */
+
+/* =====================================================================================
  * Test hook: one bf16 tcgen05 GEMM  D[M x N] = A[M x K] * B[N x K]^T (+bias, activation),
  * A/B f32 on the host, rounded to bf16 on the device.  Used by tests/ only.
  * ===================================================================================== */

@@ -37,7 +37,12 @@ SYMBOLS = [
     "rb_pipeline_nn_score", "rb_pipeline_nn_score_dev",
     "rb_search_create", "rb_search_destroy", "rb_search_decode", "rb_search_decode_dev", "rb_search_traceback", "rb_search_traceback_all", "rb_pipeline_search",
     "rb_postproc_create", "rb_postproc_destroy", "rb_postproc_dim_out", "rb_postproc_process", "rb_postproc_process_dev",
+    "rb_comm_create", "rb_comm_destroy", "rb_comm_world", "rb_comm_rank", "rb_comm_window_alloc", "rb_comm_window_attach",
+    "rb_comm_window_ptr", "rb_comm_gather_scores_dev", "rb_comm_push_rows_dev", "rb_comm_barrier_dev", "rb_comm_nccl_unique_id", "rb_comm_nccl_init",
+    "rb_comm_nccl_version",
 ]
+COMM_P2P, COMM_NCCL = 0, 1
+COMM_HANDLE_BYTES, COMM_ID_BYTES = 64, 128
 
 
 class RasrB200Error(RuntimeError):
@@ -194,6 +199,19 @@ def lib():
     L.rb_postproc_dim_out.argtypes = [vp]
     L.rb_postproc_process.argtypes = [vp, vp, vp, C.c_int, vp]
     L.rb_postproc_process_dev.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+    L.rb_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.rb_comm_destroy.argtypes = [vp]
+    L.rb_comm_destroy.restype = None
+    L.rb_comm_world.argtypes = [vp]
+    L.rb_comm_rank.argtypes = [vp]
+    L.rb_comm_window_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), vp]
+    L.rb_comm_window_attach.argtypes = [vp, vp]
+    L.rb_comm_window_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.rb_comm_gather_scores_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.rb_comm_push_rows_dev.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, vp]
+    L.rb_comm_barrier_dev.argtypes = [vp, vp]
+    L.rb_comm_nccl_unique_id.argtypes = [vp]
+    L.rb_comm_nccl_init.argtypes = [vp, vp]
     L.rb_test_gemm_bf16.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.rb_test_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int]
     _lib = L

@@ -88,18 +88,30 @@ def partition(lengths, world_size):
     return [np.array(sorted(p), np.int64) for p in parts]
 
 
-def gather_scores(local_scores, dist, group=None):
-    """All-gather of the per-rank score slabs (equal-padded) for a single decoder rank.
-    `local_scores` is a torch tensor [T_r x M] on this rank's device; returns the list of slabs."""
+def gather_scores(local_scores, dist, group=None, out=None):
+    """All-gather of the per-rank score slabs through torch.distributed (the library baseline; the engine's own exchange
+    is rasr_b200.comm.ScoreExchange over NVLink peer memory).  Shards may differ in length: every rank's rows are
+    broadcast in place into one preallocated matrix -- no padding, no staging copy.  `local_scores` is a torch tensor
+    [T_r x M] on this rank's device; returns the list of per-rank views of the gathered matrix (`out` if given)."""
     import torch
 
-    world = dist.get_world_size(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = torch.tensor([local_scores.shape[0]], dtype=torch.int64, device=local_scores.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    tmax = int(max(int(c.item()) for c in counts))
-    padded = torch.zeros((tmax, local_scores.shape[1]), dtype=local_scores.dtype, device=local_scores.device)
-    padded[:local_scores.shape[0]] = local_scores
-    slabs = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(slabs, padded, group=group)
-    return [s[:int(c.item())] for s, c in zip(slabs, counts)]
+    counts = torch.zeros(world, dtype=torch.int64, device=local_scores.device)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    counts = [int(c) for c in counts.tolist()]
+    total, M = sum(counts), local_scores.shape[1]
+    if out is None:
+        out = torch.empty((total, M), dtype=local_scores.dtype, device=local_scores.device)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    views = [out[int(offs[r]):int(offs[r + 1])] for r in range(world)]
+    if views[rank].data_ptr() != local_scores.data_ptr():
+        views[rank].copy_(local_scores)
+    if len(set(counts)) == 1 and total:
+        dist.all_gather_into_tensor(out, views[rank], group=group)
+    else:
+        work = [dist.broadcast(views[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group,
+                               async_op=True) for r in range(world) if counts[r]]
+        for wk in work:
+            wk.wait()
+    return views
