@@ -255,6 +255,144 @@ __global__ void __launch_bounds__(kThreads, (NB <= 5) ? (FPT == 1 ? 3 : (FPT == 
 }
 
 // ------------------------------------------------------------------------------------------
+// BATCH_FLOAT, second half of the exact two-pass scorer.  gmm_tensor.cu's screening pass left, for
+// every (frame, mixture), the set of densities that can still win -- one bit per density, almost always a single bit --
+// in the score matrix itself.  Here only those densities are evaluated, in the reference's operation order (the same
+// lanes, fused multiply-adds and add tree as gmm_batch_kernel above), and the word is overwritten with the score.
+//   * a CTA keeps the rows of one mixture group in shared memory for its whole life (one bulk copy) and strides over
+//     blocks of 256 frames; a thread owns one frame, its scaled feature vector (read coalesced from the transposed
+//     copy the screening pass wrote) stays in registers as packed f32x2 pairs;
+//   * per mixture a lane picks ITS candidate row (per-lane LDS.128 addresses), candidates in ascending density order
+//     with the reference's `min_ps` operand order, so a frame whose set is "every density" (non-finite input) replays
+//     the reference loop exactly.
+// ------------------------------------------------------------------------------------------
+struct RefineParams {
+    const float* rows;      // [nRows * refine_pitch(NB)], mixture order
+    const int*   grp_row;   // [G+1]
+    const int*   grp_mix;   // [G+1]
+    const int*   mix_row;   // [nMix+1] first row of every mixture
+    const float* xT;        // [NB*8 x pitch] scaled features, transposed
+    long         pitch;
+    const uint32_t* words;  // [nMix / 4][pitch][4] candidate sets (EpiGmmScreen, gmm_tensor.cu)
+    float*       scores;    // [T * nMix]
+    long         T;
+    int          nMix, nGroups, nFrameBlocks;
+};
+
+// refinement rows: [ mu' (NB*8) | c | 0 ] = NB*8 + 2 floats = an ODD number (4 NB + 1) of 8-byte words, so that the 16
+// lanes of an LDS.64 phase that pick 16 different rows of a mixture hit 16 different bank pairs and the per-lane gather
+// runs at the full shared-memory rate (with the 176-byte rows of the direct kernel, rows j and j + 8 collide and the
+// gather cost 2.2 wavefronts per phase: 291 us per 100k frames).
+__host__ __device__ constexpr int refine_pitch(int nb) {
+    return nb * 8 + 2;
+}
+
+template<int NB, bool FUSE>
+__device__ __forceinline__ float batch_row_score(const float* row, const uint64_t (&x)[NB * 4]) {
+    const uint64_t* r    = reinterpret_cast<const uint64_t*>(row);
+    uint64_t        a[4] = {r[NB * 4], 0ull, 0ull, 0ull};  // (c, 0): constant first, lane 0 of the first accumulator
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t d = sub2(r[4 * b + j], x[4 * b + j]);
+            a[j]             = FUSE ? fma2(d, d, a[j]) : sqadd2(d, a[j]);
+        }
+    }
+    const uint64_t q = add2(add2(a[0], a[2]), add2(a[1], a[3]));
+    return __fadd_rn(lo2(q), hi2(q));
+}
+
+template<int NB, bool FUSE>
+__global__ void __launch_bounds__(kThreads, 3) gmm_refine_kernel(const RefineParams p) {
+    constexpr int ROWF = refine_pitch(NB);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int g    = blockIdx.x % p.nGroups;
+    const int row0 = p.grp_row[g], row1 = p.grp_row[g + 1];
+    const int mix0 = p.grp_mix[g], mix1 = p.grp_mix[g + 1];
+    // shared memory: [ mbarrier | first row offset of every mixture of the group | the group's rows ]
+    uint64_t*      bar    = reinterpret_cast<uint64_t*>(smem_raw);
+    int*           first  = reinterpret_cast<int*>(smem_raw + 16);
+    unsigned char* region = smem_raw + 16 + (((size_t)(mix1 - mix0) * sizeof(int) + 15) & ~(size_t)15);
+    // a row is 8-byte aligned only: the bulk copy starts at the 16-byte boundary below the first row and ends at the
+    // one above the last (the device buffer carries a spare row for the overhang)
+    const size_t   gBegin = (size_t)row0 * ROWF * 4, gEnd = (size_t)row1 * ROWF * 4;
+    const size_t   cBegin = gBegin & ~(size_t)15, cEnd = (gEnd + 15) & ~(size_t)15;
+    const float*   rows   = reinterpret_cast<const float*>(region + (gBegin - cBegin));
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    for (int m = tid; m < mix1 - mix0; m += kThreads)
+        first[m] = (p.mix_row[mix0 + m] - row0) * ROWF;
+    __syncthreads();
+    if (tid == 0) {
+        const size_t total = cEnd - cBegin;
+        mbar_expect_tx(bar, (uint32_t)total);
+        for (size_t off = 0; off < total; off += 65536) {
+            const uint32_t bytes = (uint32_t)(total - off < 65536 ? total - off : 65536);
+            bulk_g2s(region + off, reinterpret_cast<const unsigned char*>(p.rows) + cBegin + off, bytes, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+
+    const int member   = blockIdx.x / p.nGroups;
+    const int nMembers = ((int)gridDim.x - g + p.nGroups - 1) / p.nGroups;
+    for (int fb = member; fb < p.nFrameBlocks; fb += nMembers) {
+        const long t  = (long)fb * kThreads + tid;
+        const long tc = t < p.T ? t : p.T - 1;
+        uint64_t   x[NB * 4];
+#pragma unroll
+        for (int i = 0; i < NB * 4; ++i)
+            x[i] = pack2(__ldg(p.xT + (size_t)(2 * i) * p.pitch + tc), __ldg(p.xT + (size_t)(2 * i + 1) * p.pitch + tc));
+        const uint4* w   = reinterpret_cast<const uint4*>(p.words) + tc;  // + (m4 / 4) * pitch
+        float*       out = p.scores + (size_t)tc * p.nMix;
+        uint4        mk  = t < p.T ? __ldg(w + (size_t)(mix0 >> 2) * p.pitch) : make_uint4(0u, 0u, 0u, 0u);
+        for (int m4 = mix0; m4 < mix1; m4 += 4) {
+            const uint32_t sets[4] = {mk.x, mk.y, mk.z, mk.w};
+            if (m4 + 4 < mix1 && t < p.T)  // the next quad's sets are on their way while this one is evaluated
+                mk = __ldg(w + (size_t)((m4 + 4) >> 2) * p.pitch);
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float* base = rows + first[m4 - mix0 + q];
+                uint32_t     set  = sets[q];
+                float        best = FLT_MAX;
+                while (set) {
+                    const int j = __ffs((int)set) - 1;
+                    set &= set - 1;
+                    const float rs = batch_row_score<NB, FUSE>(base + j * ROWF, x);
+                    best           = best < rs ? best : rs;
+                }
+                o[q] = best < FLT_MAX ? __fmul_rn(best, 0.5f) : best;
+            }
+            if (t < p.T)
+                *reinterpret_cast<float4*>(out + m4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+typedef void (*GmmRefineKernel)(const RefineParams);
+template<int N>
+GmmRefineKernel pick_refine(bool fuse) {
+    return fuse ? gmm_refine_kernel<N, true> : gmm_refine_kernel<N, false>;
+}
+GmmRefineKernel refine_kernel_for(int nb, bool fuse) {
+    switch (nb) {
+        case 1: return pick_refine<1>(fuse);
+        case 2: return pick_refine<2>(fuse);
+        case 3: return pick_refine<3>(fuse);
+        case 4: return pick_refine<4>(fuse);
+        case 5: return pick_refine<5>(fuse);
+        case 6: return pick_refine<6>(fuse);
+        case 7: return pick_refine<7>(fuse);
+        case 8: return pick_refine<8>(fuse);
+    }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
 // DIAG_MAX / DIAG_SUM: row = [ mu (NQ*4) | isd (NQ*4) | -2 log w * scale | logNorm | flags | 0 ]
 // distance(): 4 SSE lanes over the first (dim & ~3) dims, hadd, then the tail dims sequentially
 // (src/Mm/GaussDiagonalMaximumFeatureScorer.cc:144-233, SSE3 branch)
@@ -542,6 +680,10 @@ int  rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, c
                           rb_gmm_tensor** out);
 void rb_gmm_tensor_destroy(rb_gmm_tensor* t);
 int  rb_gmm_tensor_score(rb_gmm_tensor* t, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
+bool rb_gmm_tensor_screenable(const rb_gmm_tensor* t);
+long rb_gmm_tensor_chunk(const rb_gmm_tensor* t);
+int  rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* d_feats, long n, const uint32_t** words, const float** xT,
+                          long* pitch, cudaStream_t stream);
 
 struct rb_gmm {
     rb::DeviceInfo dev;
@@ -575,8 +717,15 @@ struct rb_gmm {
     rb::DevBuf<int>      dGrpRow, dGrpMix;
     rb::DevBuf<float>    dFeats, dScores;  // staging for the host-pointer entry point
     rb::DevBuf<uint32_t> dBest;
-    rb::PinnedBuf<float> hStage;
     rb_gmm_tensor*       tensor = nullptr;
+    // BATCH_FLOAT on large batches: tensor-core screening + exact evaluation of the surviving densities (same bits as
+    // the direct kernel).  refGroups = 0: not available for this model.
+    GmmRefineKernel      refine = nullptr;
+    int                  refGroups = 0, refSlots = 0;
+    size_t               refSmem = 0;
+    long                 exactMinFrames = 2048;
+    rb::DevBuf<int>      dMixRow;
+    rb::DevBuf<float>    dRefRows;
     rb_gmm_int*          quantised = nullptr;
     rb_gmm_presel*       presel    = nullptr;
     rb_gmm_presel_int*   preselInt = nullptr;
@@ -831,6 +980,106 @@ int launch_simt(rb_gmm* h, const float* dFeats, long T, float* dScores, uint32_t
     return RB_OK;
 }
 
+
+// BATCH_FLOAT: can large batches take the screening + refinement route?  Needs what the tensor scorer needs (no empty
+// mixture, at most 256 densities per mixture), at most 32 densities per mixture (one bit each), a mixture count that is
+// a multiple of 4 (16-byte words), finite parameters, and a mixture grouping whose rows fit shared memory.  When it does
+// not apply the direct kernel serves every call (same scores, only slower).  RB_GMM_EXACT=0 switches the route off.
+int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsHost) {
+    const char* env = getenv("RB_GMM_EXACT");
+    if (env && atoi(env) == 0)
+        return RB_OK;
+    if (env && atoi(env) > 1)
+        h->exactMinFrames = 1;  // tests: every call takes the two-pass route
+    if (h->nMix % 4 != 0)
+        return RB_OK;
+    for (uint32_t m = 0; m < ms->n_mixtures; ++m) {
+        const uint32_t n = ms->mix_offsets[m + 1] - ms->mix_offsets[m];
+        if (n == 0 || n > 32)
+            return RB_OK;
+    }
+    h->refine = refine_kernel_for(h->nUnits, h->fuse);
+    if (!h->refine)
+        return RB_OK;
+    rb_gmm_tensor* t = nullptr;
+    if (rb_gmm_tensor_create(ms, h->dev, h->stream, &t) != RB_OK || !rb_gmm_tensor_screenable(t)) {
+        if (t)
+            rb_gmm_tensor_destroy(t);
+        return RB_OK;  // e.g. non-finite parameters: the direct kernel reproduces the reference on those too
+    }
+    // fewest groups whose rows fit 48 KB (3-4 CTAs per SM); else up to 200 KB at lower occupancy
+    const int        pitch = refine_pitch(h->nUnits);
+    std::vector<int> mixRow(h->nMix + 1, 0);
+    for (int m = 0; m < h->nMix; ++m)
+        mixRow[m + 1] = mixRow[m] + h->rowsOfMixture[m];
+    int    pickG = 0;
+    size_t pickSmem = 0;
+    for (size_t budget : {(size_t)49 * 1024, (size_t)100 * 1024, (size_t)200 * 1024}) {
+        for (int G = 1; G <= kMaxGroups && !pickG; ++G) {
+            std::vector<int> grpRow, grpMix;
+            make_groups(h, G, grpRow, grpMix);
+            size_t need = 0;
+            for (size_t g = 0; g + 1 < grpRow.size(); ++g)
+                need = std::max(need, 16 + rb::round_up(sizeof(int) * (size_t)(grpMix[g + 1] - grpMix[g]), 16) +
+                                              rb::round_up(sizeof(float) * (size_t)(grpRow[g + 1] - grpRow[g]) * pitch, 16) + 32);
+            if (need <= budget) {
+                pickG    = G;
+                pickSmem = need;
+            }
+        }
+        if (pickG)
+            break;
+    }
+    int occ = 0;
+    if (!pickG ||
+        cudaFuncSetAttribute(h->refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pickSmem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->refine, kThreads, pickSmem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        rb_gmm_tensor_destroy(t);
+        return RB_OK;
+    }
+    // the rows again at the refinement pitch (+ one spare row for the 16-byte overhang of the bulk copy)
+    std::vector<float> rrows((size_t)(h->nRows + 1) * pitch, 0.0f);
+    for (int r = 0; r < h->nRows; ++r) {
+        const float* src = rowsHost + (size_t)r * h->rowf;
+        std::copy(src, src + h->nUnits * 8 + 1, rrows.begin() + (size_t)r * pitch);
+    }
+    if (h->dRefRows.upload(rrows, h->stream) != RB_OK || h->dMixRow.upload(mixRow, h->stream) != RB_OK ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        rb_gmm_tensor_destroy(t);
+        return RB_ERR_CUDA;
+    }
+    h->tensor    = t;
+    h->refGroups = pickG;
+    h->refSmem   = pickSmem;
+    h->refSlots  = h->dev.sm_count * occ;
+    return RB_OK;
+}
+
+int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores, cudaStream_t s) {
+    const long chunk = rb_gmm_tensor_chunk(h->tensor);
+    for (long a = 0; a < T; a += chunk) {
+        const long   n = std::min(chunk, T - a);
+        RefineParams p;
+        RB_CHECK(rb_gmm_tensor_screen(h->tensor, dFeats + (size_t)a * h->dim, n, &p.words, &p.xT, &p.pitch, s));
+        p.scores       = dScores + (size_t)a * h->nMix;
+        const int G    = h->refGroups;
+        p.rows         = h->dRefRows.p;
+        p.grp_row      = h->dGrpRow.p + (size_t)G * kGroupStride;
+        p.grp_mix      = h->dGrpMix.p + (size_t)G * kGroupStride;
+        p.mix_row      = h->dMixRow.p;
+        p.T            = n;
+        p.nMix         = h->nMix;
+        p.nGroups      = h->groupsOf[G];
+        p.nFrameBlocks = (int)((n + kThreads - 1) / kThreads);
+        const long items = (long)p.nGroups * p.nFrameBlocks;
+        const int  grid  = (int)std::max<long>(p.nGroups, std::min<long>(items, h->refSlots));
+        h->refine<<<grid, kThreads, h->refSmem, s>>>(p);
+        RB_LAUNCH_CHECK();
+    }
+    return RB_OK;
+}
+
 }  // namespace
 
 extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_weight_scale, float gaussian_scale,
@@ -974,6 +1223,11 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         if (rc != RB_OK)
             return fail(rc);
     }
+    if (mode == RB_GMM_BATCH_FLOAT) {
+        rc = setup_exact_two_pass(h, ms, rows.data());
+        if (rc != RB_OK)
+            return fail(rc);
+    }
     *out = h;
     return RB_OK;
 }
@@ -1018,8 +1272,11 @@ extern "C" int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* 
         RB_REQUIRE(d_best == nullptr, "the preselection scorer does not report densities; use RB_GMM_DIAG_MAX");
         return rb_gmm_presel_int_score(h->preselInt, d_feats, T, d_scores, s);
     }
-    if (h->mode == RB_GMM_BATCH_FLOAT)
+    if (h->mode == RB_GMM_BATCH_FLOAT) {
         RB_REQUIRE(d_best == nullptr, "Mm::BatchFloatFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
+        if (h->refGroups > 0 && T >= h->exactMinFrames && ((uintptr_t)d_scores % 16) == 0)
+            return launch_exact_two_pass(h, d_feats, T, d_scores, s);
+    }
     return launch_simt(h, d_feats, T, d_scores, d_best, s);
 }
 

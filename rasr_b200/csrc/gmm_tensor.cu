@@ -137,6 +137,105 @@ struct EpiGmmMin {
     }
 };
 
+// ---- screening epilogue (exact batch-float scoring) ------------------------------
+// Instead of the minimum itself, every (frame, mixture) gets the SET of densities whose approximate score lies within
+// thr[frame] of the smallest one -- one bit per density of the mixture (mixtures of at most 32 densities).  thr bounds
+// twice the error of the split-precision product plus twice the rounding error of the reference's own f32 sum, so the
+// density that wins in the reference's arithmetic is always in the set; gmm_refine_kernel (gmm.cu) then evaluates
+// only those densities in the reference's operation order.  thr = +inf (frame with non-finite or out-of-range
+// values): every density is a candidate.  The words go where the scores will be (same buffer, overwritten in place).
+template<int SEG>
+struct EpiGmmScreen {
+    const uint32_t* endMask;
+    const int*      mixStart;
+    const float*    thr;    // [T] in accumulator units
+    uint32_t*       masks;  // [nMix / 4][pitch][4]: the words of mixtures 4q .. 4q+3 of frame t form one uint4 at (q, t) --
+                            // both this epilogue (lane = frame) and gmm_refine_kernel (thread = frame) access it coalesced
+    long            pitch;
+    int             nMix;
+    static constexpr bool kUniform = SEG > 0;
+    struct State {
+        float    best, thr;
+        uint32_t mask;
+        int      pos;
+    };
+    __device__ __forceinline__ uint32_t* word(int row, int mix) const {
+        return masks + (((size_t)(mix >> 2) * (size_t)pitch + (size_t)row) << 2) + (mix & 3);
+    }
+    __device__ void begin(State& st, int row) const {
+        st.best = FLT_MAX;
+        st.thr  = __ldg(thr + row);
+        st.mask = 0;
+        st.pos  = 0;
+    }
+    __device__ void emit64(const State& st, int row, int col0, const float (&v)[64]) const {
+        constexpr int S  = SEG > 0 ? SEG : 32;
+        constexpr int NO = 64 / S;
+        const int     m0 = col0 / S;
+        if (m0 >= nMix)
+            return;
+        constexpr uint32_t kAll = S == 32 ? 0xffffffffu : ((1u << (S & 31)) - 1u);
+        const bool         all  = !(st.thr < FLT_MAX);
+        uint32_t           out[NO];
+#pragma unroll
+        for (int g = 0; g < NO; ++g) {
+            const float lim = tree_min<S>(v + g * S) + st.thr;
+            uint32_t    mk  = 0;
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                mk |= v[g * S + j] <= lim ? (1u << j) : 0u;
+            out[g] = (all || mk == 0) ? kAll : mk;
+        }
+        // nMix % 4 == 0 (a condition of the exact route), so whole quads are always inside the matrix
+        if constexpr (NO == 2)
+            *reinterpret_cast<uint2*>(word(row, m0)) = make_uint2(out[0], out[1]);
+        else {
+#pragma unroll
+            for (int g = 0; g < NO; g += 4)
+                if (m0 + g < nMix)
+                    *reinterpret_cast<uint4*>(word(row, m0 + g)) = make_uint4(out[g], out[g + 1], out[g + 2], out[g + 3]);
+        }
+    }
+    // ragged mixtures: one pass over the columns.  A density enters the set if it lies within thr of the running
+    // minimum; the set is emptied when a new minimum undercuts the old one by more than thr (nothing seen before can
+    // then be within thr of the final minimum).  The result is a superset of the exact candidate set.
+    __device__ void chunk(State& st, int row, int col0, const float (&v)[32]) const {
+        if (SEG > 0)
+            return;
+        const int      c    = col0 >> 5;
+        const uint32_t ends = __ldg(endMask + c);
+        int            mix  = __ldg(mixStart + c);
+        if ((col0 & (rbgemm::BN - 1)) == 0) {
+            st.best = FLT_MAX;
+            st.mask = 0;
+            st.pos  = 0;
+        }
+        const bool all = !(st.thr < FLT_MAX);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float    x   = v[j];
+            const uint32_t bit = 1u << (st.pos & 31);
+            if (x < st.best - st.thr) {
+                st.mask = bit;
+                st.best = x;
+            }
+            else if (x <= st.best + st.thr) {
+                st.mask |= bit;
+                st.best = fminf(st.best, x);
+            }
+            ++st.pos;
+            if ((ends >> j) & 1u) {
+                const uint32_t full = st.pos >= 32 ? 0xffffffffu : ((1u << st.pos) - 1u);
+                *word(row, mix) = (all || st.mask == 0) ? full : st.mask;
+                ++mix;
+                st.best = FLT_MAX;
+                st.mask = 0;
+                st.pos  = 0;
+            }
+        }
+    }
+};
+
 // ---- features -> split fp16 A operand + |x|^2 -------------------------------------------------
 // row layout [ xh(dp) | xh(dp) | xl(dp) | 1 1 1 0... ] padded to kPad halves.  8 lanes per frame, a
 // lane owns 8 consecutive dims and writes whole 16-byte chunks (dp <= 64).
@@ -144,7 +243,9 @@ __global__ void __launch_bounds__(256) gmm_split_features_kernel(const float* __
                                                                  const float* __restrict__ isd,
                                                                  const float* __restrict__ centre, long T, int dim,
                                                                  int dp, int kPad, float scale, __half* __restrict__ A,
-                                                                 float* __restrict__ xnorm) {
+                                                                 float* __restrict__ xnorm, float* __restrict__ thr,
+                                                                 float thrA, float thrB, float* __restrict__ xT,
+                                                                 long pitch) {
     const int  sub = threadIdx.x & 7;  // lane within the frame group
     const long g0  = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 3;
     const long nG  = ((long)gridDim.x * blockDim.x) >> 3;
@@ -153,14 +254,20 @@ __global__ void __launch_bounds__(256) gmm_split_features_kernel(const float* __
         const long t   = t0 < T ? t0 : T - 1;
         float      acc = 0.0f;
         uint32_t   hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+        int        bad = 0;  // non-finite or outside the fp16 range: the screening must not trust this frame
         if (sub < nChunk) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int d = sub * 8 + j;
-                float     x = 0.0f;
-                if (d < dim)
-                    x = __fsub_rn(__fmul_rn(__ldg(feats + (size_t)t * dim + d), __ldg(isd + d)), __ldg(centre + d));
+                float     x = 0.0f, xr = 0.0f;
+                if (d < dim) {
+                    xr = __fmul_rn(__ldg(feats + (size_t)t * dim + d), __ldg(isd + d));  // the reference's scaled feature
+                    x  = __fsub_rn(xr, __ldg(centre + d));
+                }
+                if (xT && t0 < T)
+                    xT[(size_t)d * pitch + t] = xr;
                 acc      = __fmaf_rn(x, x, acc);
+                bad |= !(fabsf(x * scale) <= 60000.0f);
                 float xs = fminf(fmaxf(x * scale, -60000.0f), 60000.0f);
                 const __half h = __float2half_rn(xs);
                 const __half l = __float2half_rn(xs - __half2float(h));
@@ -171,6 +278,9 @@ __global__ void __launch_bounds__(256) gmm_split_features_kernel(const float* __
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 1);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 2);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 4);
         if (t0 < T) {
             uint4* row = reinterpret_cast<uint4*>(A + (size_t)t * kPad);
             if (sub < nChunk) {
@@ -182,8 +292,11 @@ __global__ void __launch_bounds__(256) gmm_split_features_kernel(const float* __
             // tail chunks: three ones (0x3C00) then zeros
             for (int c = 3 * nChunk + sub; c < (kPad >> 3); c += 8)
                 row[c] = c == 3 * nChunk ? make_uint4(0x3C003C00u, 0x00003C00u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-            if (sub == 0)
+            if (sub == 0) {
                 xnorm[t] = acc;
+                if (thr)
+                    thr[t] = (bad || !(acc < FLT_MAX)) ? __int_as_float(0x7f800000) : __fmaf_rn(acc, thrA, thrB);
+            }
         }
     }
 }
@@ -391,9 +504,14 @@ struct rb_gmm_tensor {
     rb::DeviceInfo dev;
     int            dim = 0, dp = 0, kPad = 0, nMix = 0, nCols = 0, seg = 0;
     float          scale = 1.0f;
-    long           chunk = 262144;  // frames per GEMM launch (64 MB of fp16 A operand, L2-resident)
+    long           chunk = 262144;  // frames per GEMM launch at most (64 MB of fp16 A operand)
+    long           cap   = 0;       // frames the per-call buffers below hold (grown on demand up to chunk)
+    // screening (exact batch-float scoring): thr = thrA * |x|^2 + thrB in accumulator units, see rb_gmm_tensor_create
+    bool           screenable = false;
+    float          thrA = 0.0f, thrB = 0.0f;
     rb::DevBuf<__half>   dB, dA;
-    rb::DevBuf<float>    dIsd, dCentre, dXnorm;
+    rb::DevBuf<float>    dIsd, dCentre, dXnorm, dThr, dXT;
+    rb::DevBuf<uint32_t> dWords;  // candidate sets of the screening pass, [nMix / 4][cap][4]
     rb::DevBuf<uint32_t> dEndMask;
     rb::DevBuf<int>      dMixStart;
     CUtensorMap          mapA, mapB;
@@ -427,6 +545,18 @@ int launch_kernel(rb_gmm_tensor* t, long T, const Epi& epi, cudaStream_t s) {
     return RB_OK;
 }
 
+template<class Epi>
+int launch_epi(rb_gmm_tensor* t, long T, const Epi& epi, cudaStream_t s) {
+    switch (t->kPad / rbgemm::BK) {
+        case 1: return launch_kernel<Epi, 1, 2>(t, T, epi, s);
+        case 2: return launch_kernel<Epi, 2, 2>(t, T, epi, s);
+        case 3: return launch_kernel<Epi, 3, 1>(t, T, epi, s);
+        case 4: return launch_kernel<Epi, 4, 1>(t, T, epi, s);
+    }
+    rb::set_error("unsupported K padding %d", t->kPad);
+    return RB_ERR_UNSUPPORTED;
+}
+
 template<int SEG>
 int launch_seg(rb_gmm_tensor* t, long T, float* dScores, cudaStream_t s) {
     EpiGmmMin<SEG> epi;
@@ -436,14 +566,37 @@ int launch_seg(rb_gmm_tensor* t, long T, float* dScores, cudaStream_t s) {
     epi.scores   = dScores;
     epi.nMix     = t->nMix;
     epi.invS2    = 1.0f / (t->scale * t->scale);
-    switch (t->kPad / rbgemm::BK) {
-        case 1: return launch_kernel<EpiGmmMin<SEG>, 1, 2>(t, T, epi, s);
-        case 2: return launch_kernel<EpiGmmMin<SEG>, 2, 2>(t, T, epi, s);
-        case 3: return launch_kernel<EpiGmmMin<SEG>, 3, 1>(t, T, epi, s);
-        case 4: return launch_kernel<EpiGmmMin<SEG>, 4, 1>(t, T, epi, s);
+    return launch_epi(t, T, epi, s);
+}
+
+template<int SEG>
+int launch_screen(rb_gmm_tensor* t, long T, cudaStream_t s) {
+    EpiGmmScreen<SEG> epi;
+    epi.endMask  = t->dEndMask.p;
+    epi.mixStart = t->dMixStart.p;
+    epi.thr      = t->dThr.p;
+    epi.masks    = t->dWords.p;
+    epi.pitch    = t->cap;
+    epi.nMix     = t->nMix;
+    return launch_epi(t, T, epi, s);
+}
+
+// per-call buffers for up to min(T, chunk) frames; the TMA map of the A operand follows the allocation
+int ensure_capacity(rb_gmm_tensor* t, long T, bool screen) {
+    const long need = std::min(T, t->chunk);
+    if (need > t->cap) {
+        const long cap = std::max(need, t->cap);
+        RB_CHECK(t->dA.reserve((size_t)cap * t->kPad));
+        RB_CHECK(t->dXnorm.reserve((size_t)cap));
+        RB_CHECK(rbgemm::make_map(&t->mapA, t->dA.p, (uint64_t)cap, (uint64_t)t->kPad, (uint64_t)t->kPad, rbgemm::BM, false));
+        t->cap = cap;
     }
-    rb::set_error("unsupported K padding %d", t->kPad);
-    return RB_ERR_UNSUPPORTED;
+    if (screen) {
+        RB_CHECK(t->dThr.reserve((size_t)t->cap));
+        RB_CHECK(t->dXT.reserve((size_t)t->cap * t->dp));
+        RB_CHECK(t->dWords.reserve((size_t)t->cap * t->nMix));
+    }
+    return RB_OK;
 }
 
 }  // namespace
@@ -590,15 +743,52 @@ int rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cu
         t->dCentre.upload(centre, stream) != RB_OK || t->dEndMask.upload(endMask, stream) != RB_OK ||
         t->dMixStart.upload(mixStart, stream) != RB_OK)
         return fail(RB_ERR_CUDA);
-    if (t->dA.reserve((size_t)t->chunk * kPad) != RB_OK || t->dXnorm.reserve((size_t)t->chunk) != RB_OK)
-        return fail(RB_ERR_NOMEM);
+    {
+        // Screening threshold.  With Q = |xc|^2 + |mu_c|^2 + |c + |mu_c|^2| (centred, scaled values)
+        //   - the reference's own f32 sum (<= 5 fused accumulations + 3 adds per lane, differences rounded once) is
+        //     within 11 u (|c| + |x - mu|^2) <= 33 u Q of the exact value, u = 2^-24;
+        //   - the split-precision product misses the exact cross term by the centring roundings (4 u Q), the fp16
+        //     representation of both operands and the dropped lo * lo products (3 * 2^-22 Q, plus 2^-25 per element
+        //     where a low part falls into the fp16 subnormal range), the residual of the three-term constant
+        //     (measured below) and the tensor core's f32 accumulation over K / 16 steps (taken as <= 2^-20 Q).
+        // A density can win in the reference's arithmetic only if its approximate score is within twice the sum of the
+        // two of the approximate minimum: <= 2^-17 Q.  kappa = 2^-16 doubles that again; tests/test_gpu_gmm_exact.py
+        // measures the actual error of the product (~2^-22 Q) on the device.
+        double qmu = 0, resid = 0;
+        bool   finite = std::isfinite((double)logNorm);
+        uint32_t nMax = 0;
+        for (uint32_t m = 0; m < ms->n_mixtures; ++m)
+            nMax = std::max(nMax, ms->mix_offsets[m + 1] - ms->mix_offsets[m]);
+        for (uint32_t e = 0; e < nEntries; ++e) {
+            double n2 = 0;
+            for (unsigned d = 0; d < D; ++d) {
+                const double v = mu[(size_t)e * D + d];
+                n2 += v * v;
+                finite = finite && std::isfinite(v);
+            }
+            finite = finite && std::isfinite(cc[e]);
+            qmu    = std::max(qmu, n2 + std::fabs(cc[e]));
+        }
+        for (int col = 0; col < t->nCols; ++col) {
+            const uint32_t e = colEntry[col];
+            if (e == 0xffffffffu)
+                continue;
+            const __half* row = B.data() + (size_t)col * kPad;
+            const double  got = ((double)__half2float(row[3 * dp]) + (double)__half2float(row[3 * dp + 1]) +
+                                (double)__half2float(row[3 * dp + 2])) / ((double)scale * (double)scale);
+            resid = std::max(resid, std::fabs(got - cc[e]));
+        }
+        const double kappa = std::ldexp(1.0, -16) + std::ldexp(1.0, -21) * std::sqrt((double)dp) / (double)scale;
+        const double s2    = (double)scale * (double)scale;
+        t->thrA       = (float)(s2 * kappa);
+        t->thrB       = (float)(s2 * (kappa * (qmu + 2.0) + 2.0 * resid) * 1.0001);
+        t->screenable = finite && nMax <= 32 && std::isfinite(t->thrA) && std::isfinite(t->thrB) && t->thrA > 0;
+    }
     if (cudaStreamSynchronize(stream) != cudaSuccess) {
         rb::set_error("tensor GMM model upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(RB_ERR_CUDA);
     }
     int rc = rbgemm::make_map(&t->mapB, t->dB.p, (uint64_t)t->nCols, (uint64_t)kPad, (uint64_t)kPad, rbgemm::BN, false);
-    if (rc == RB_OK)
-        rc = rbgemm::make_map(&t->mapA, t->dA.p, (uint64_t)t->chunk, (uint64_t)kPad, (uint64_t)kPad, rbgemm::BM, false);
     if (rc != RB_OK)
         return fail(rc);
     *out = t;
@@ -609,12 +799,43 @@ void rb_gmm_tensor_destroy(rb_gmm_tensor* t) {
     delete t;
 }
 
+bool rb_gmm_tensor_screenable(const rb_gmm_tensor* t) {
+    return t && t->screenable;
+}
+long rb_gmm_tensor_chunk(const rb_gmm_tensor* t) {
+    return t->chunk;
+}
+
+// Exact batch-float scoring, first half: for n <= chunk frames compute the candidate-density words (*words, laid out
+// [nMix / 4][pitch][4]) and the reference's scaled features, transposed ([dp x pitch], x' = fl(feat * isd)) (*xT).
+int rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* dFeats, long n, const uint32_t** words, const float** xT,
+                         long* pitch, cudaStream_t s) {
+    RB_REQUIRE(t->screenable, "this mixture set cannot be screened");
+    RB_REQUIRE(n >= 1 && n <= t->chunk, "bad frame count for one screening pass");
+    RB_CHECK(ensure_capacity(t, n, true));
+    const int blocks = (int)std::min<long>((n + 31) / 32, (long)t->dev.sm_count * 16);
+    gmm_split_features_kernel<<<blocks, 256, 0, s>>>(dFeats, t->dIsd.p, t->dCentre.p, n, t->dim, t->dp, t->kPad, t->scale,
+                                                     t->dA.p, t->dXnorm.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p, t->cap);
+    RB_LAUNCH_CHECK();
+    *xT    = t->dXT.p;
+    *words = t->dWords.p;
+    *pitch = t->cap;
+    switch (t->seg) {
+        case 8: return launch_screen<8>(t, n, s);
+        case 16: return launch_screen<16>(t, n, s);
+        case 32: return launch_screen<32>(t, n, s);
+        default: return launch_screen<0>(t, n, s);
+    }
+}
+
 int rb_gmm_tensor_score(rb_gmm_tensor* t, const float* dFeats, long T, float* dScores, cudaStream_t s) {
+    RB_CHECK(ensure_capacity(t, T, false));
     for (long a = 0; a < T; a += t->chunk) {
         const long n      = std::min(t->chunk, T - a);
         const int  blocks = (int)std::min<long>((n + 31) / 32, (long)t->dev.sm_count * 16);
         gmm_split_features_kernel<<<blocks, 256, 0, s>>>(dFeats + (size_t)a * t->dim, t->dIsd.p, t->dCentre.p, n,
-                                                         t->dim, t->dp, t->kPad, t->scale, t->dA.p, t->dXnorm.p);
+                                                         t->dim, t->dp, t->kPad, t->scale, t->dA.p, t->dXnorm.p,
+                                                         nullptr, 0.0f, 0.0f, nullptr, 0);
         RB_LAUNCH_CHECK();
         float* out = dScores + (size_t)a * t->nMix;
         int    rc;
