@@ -402,7 +402,7 @@ class Bench:
             w["e2e"] = lambda: scorer.score(h_in, out=h_out)
             p_out = np.empty((T, 256), np.float32)
             w["e2e_pageable"] = lambda: scorer.score(feats_h, out=p_out)
-            w.update(h2d=T * 39 * 4, d2h=T * 256 * 4, units=T, algo_bytes=ALGO_BYTES_PER_FRAME["gmm"] * T, bound="hbm",
+            w.update(scorer=scorer, h2d=T * 39 * 4, d2h=T * 256 * 4, units=T, algo_bytes=ALGO_BYTES_PER_FRAME["gmm"] * T, bound="hbm",
                      dtype="u8/s32" if wl in ("gmm-int", "gmm-presel-int") else "f32",
                      workload=C2_WORKLOAD.replace("batch-float", mode).replace("100000", str(T)),
                      keep=(scorer, d_in, d_out, msd))
@@ -605,13 +605,26 @@ class Bench:
             achieved = w["algo_bytes"] / (dev_ms * 1e-3) / 1e9
             roof = dict(bound="hbm", achieved=achieved, peak=peaks["hbm"], unit="GB/s", frac=achieved / peaks["hbm"],
                         traffic=None, peak_source=peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)")
-            if wl in GMM_WORKLOADS:
-                sm_mhz = clocks.get("sm_mhz") or 1965.0
-                # CUDA-core ceiling of the reference-order arithmetic: sub + fma per (frame, density, dim)
-                fp32_ceiling = 148 * 128 * sm_mhz * 1e6 / (2 * 39 * 4096)
-                roof["fp32_alu"] = dict(ceiling_frames_per_s=fp32_ceiling, frac=(units / (dev_ms * 1e-3)) / fp32_ceiling,
-                                        note="direct-form GMM is FP32-issue bound: 2 FMA-pipe ops per "
-                                             "(frame,density,dim) at the sampled SM clock")
+            if wl == "gmm" and w.get("scorer") is not None:
+                # the exact route is three kernels per step: live CUDA-event durations of each (rb_gmm_set_timing)
+                sc, d_in, d_out = w["scorer"], w["keep"][1], w["keep"][2]
+                sc.set_timing(True)
+                parts = []
+                for i in range(5):
+                    sc.score_dev(d_in[i % self.R], units, d_out[i % self.R], None, self.sptr)
+                    t3 = sc.timing()
+                    if t3:
+                        parts.append(t3)
+                sc.set_timing(False)
+                if parts:
+                    k = np.mean(np.asarray(parts), axis=0)
+                    roof["kernels_ms"] = {"gmm_split_features_kernel": float(k[0]),
+                                          "gmm_tensor_kernel<EpiGmmScreen>": float(k[1]),
+                                          "gmm_refine_kernel": float(k[2])}
+                    roof["dominant_kernel"] = "gmm_refine_kernel"
+                    roof["note"] = ("exact batch-float route = operand split + tcgen05 screening + exact refinement; "
+                                    "achieved = algorithmic bytes of the step / step time; the refinement is bound by "
+                                    "shared-memory wavefronts (per-lane row gathers), the screening by tcgen05.ld")
         else:
             achieved = NN_FLOP_PER_FRAME * units / (dev_ms * 1e-3) / 1e12
             roof = dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
@@ -625,31 +638,50 @@ class Bench:
                     config=dict(workload=w["workload"], wall_ms_per_step=wall_ms), e2e=e2e, gpu_launches=int(launches),
                     clocks=clocks, roofline=roof, dev_ms=dev_ms)
 
-    # the tensor-core formulation of the C2 scorer (RB_GMM_BATCH_TENSOR, 1e-4 relative instead of bit-identical), timed the
-    # same way on the same buffers and reported beside the headline as "variants"
-    def tensor_variant(self, w, steps, warmup):
+    # other formulations of the C2 scorer, timed the same way on the same buffers and reported beside the headline:
+    #   batch-tensor        RB_GMM_BATCH_TENSOR, 1e-4 relative instead of bit-identical
+    #   batch-float-direct  the single direct-form kernel (RB_GMM_EXACT=0), what batches below 2048 frames and models
+    #                       the screening does not cover run on; FP32-issue bound
+    def gmm_variants(self, w, steps, warmup):
         torch, stream = self.torch, self.stream
         from rasr_b200 import mm
 
         scorer, d_in, d_out, msd = w["keep"]
         T, R = w["units"], self.R
-        tscorer = mm.GmmScorer(mm.MixtureSet.from_dict(msd), "batch-tensor", device=self.local_rank)
-        for i in range(warmup):
-            tscorer.score_dev(d_in[i % R], T, d_out[i % R], None, self.sptr)
-        self.barrier()
-        tev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        tev[0].record(stream)
-        for i in range(steps):
-            tscorer.score_dev(d_in[i % R], T, d_out[i % R], None, self.sptr)
-        tev[1].record(stream)
-        self.barrier()
-        tms = self.max_over_ranks(tev[0].elapsed_time(tev[1]) / steps)
-        gbs = w["algo_bytes"] / (tms * 1e-3) / 1e9
-        return {"batch-tensor": dict(
-            value=T * self.world / (tms * 1e-3), unit=UNIT, ms_per_step=tms, dtype="f16x3 split operands, f32 accumulate",
-            parity="<= 1e-4 relative to the reference scores (tests/test_gpu_gmm_tensor.py)",
-            roofline=dict(bound="hbm", achieved=gbs, peak=self.peaks["hbm"], unit="GB/s", frac=gbs / self.peaks["hbm"]))}
-
+        out = {}
+        for name in ("batch-tensor", "batch-float-direct"):
+            if name == "batch-float-direct":
+                os.environ["RB_GMM_EXACT"] = "0"
+            try:
+                vs = mm.GmmScorer(mm.MixtureSet.from_dict(msd), name.replace("-direct", ""), device=self.local_rank)
+            finally:
+                os.environ.pop("RB_GMM_EXACT", None)
+            for i in range(warmup):
+                vs.score_dev(d_in[i % R], T, d_out[i % R], None, self.sptr)
+            self.barrier()
+            tev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            tev[0].record(stream)
+            for i in range(steps):
+                vs.score_dev(d_in[i % R], T, d_out[i % R], None, self.sptr)
+            tev[1].record(stream)
+            self.barrier()
+            tms = self.max_over_ranks(tev[0].elapsed_time(tev[1]) / steps)
+            gbs = w["algo_bytes"] / (tms * 1e-3) / 1e9
+            d = dict(value=T * self.world / (tms * 1e-3), unit=UNIT, ms_per_step=tms,
+                     roofline=dict(bound="hbm", achieved=gbs, peak=self.peaks["hbm"], unit="GB/s", frac=gbs / self.peaks["hbm"]))
+            if name == "batch-tensor":
+                d.update(dtype="f16x3 split operands, f32 accumulate",
+                         parity="<= 1e-4 relative to the reference scores (tests/test_gpu_gmm_tensor.py)")
+            else:
+                fp32_ceiling = 148 * 128 * 1965.0e6 / (2 * 39 * 4096)
+                d.update(dtype="f32", parity="bit-identical (tests/test_gpu_gmm.py)",
+                         fp32_alu=dict(ceiling_frames_per_s=fp32_ceiling, frac=(T / (tms * 1e-3)) / fp32_ceiling,
+                                       note="direct form: sub + fma per (frame, density, dim) on 148 x 128 lanes at "
+                                            "1965 MHz; scripts/micro/fp32_rate.cu measures 0.90 of that for a dependent "
+                                            "FADD2 -> FFMA2 stream"))
+            out[name] = d
+            del vs
+        return out
 
     # ---------------- north_star: "allgather of the score matrix only where a single decoder rank consumes all frames".
     # C3 shard per rank (125 utterances x 1000 frames x 256 scores = 128 MB), gathered into every rank's window (all-gather)
@@ -804,7 +836,7 @@ def main():
     head = "gmm" if args.workload == "all" else args.workload
     w = b.setup(head, args.frames)
     m = b.measure(w, args.steps, args.warmup)
-    variants = b.tensor_variant(w, args.steps, args.warmup) if head == "gmm" else None
+    variants = b.gmm_variants(w, args.steps, args.warmup) if head == "gmm" else None
     line = dict(metric=METRIC, value=m["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=m["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype=m["dtype"],
                 data="synthetic",

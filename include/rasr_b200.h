@@ -272,6 +272,12 @@ int  rb_gmm_dim(const rb_gmm* h);
 int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores, uint32_t* best_density);
 int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* d_scores, uint32_t* d_best_density,
                      void* stream);
+/* measurement hook (bench.py): RB_GMM_BATCH_FLOAT scores batches of >= 2048 frames in three kernels (operand split,
+ * tensor-core screening of the candidate densities, exact evaluation of the candidates); with timing on, CUDA events
+ * bracket them on the launching stream and rb_gmm_get_timing returns their durations of the last such call
+ * (ms3 = split, screen, refine; waits for the call; RB_ERR_STATE if the last calls took the single direct kernel) */
+int rb_gmm_set_timing(rb_gmm* h, int on);
+int rb_gmm_get_timing(rb_gmm* h, float* ms3);
 
 /* =====================================================================================
  * Legacy Nn feed-forward scorer (src/Nn/BatchFeatureScorer.cc:45-171, src/Nn/NeuralNetwork.cc:313-425)

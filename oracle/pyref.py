@@ -115,11 +115,22 @@ class FlowNetwork:
             if self._L.ref_flow_set_parameter(C.c_void_p(self._h), k.encode(), str(v).encode()) != 0:
                 raise RuntimeError("network has no parameter %s" % k)
 
-    def run(self, samples, port="features", sample_rate=16000.0, start_time=0.0, capacity=None):
-        """One segment through the network; returns dict(feats [T x dim], t_start, t_end, sizes)."""
+    def run(self, samples, port="features", sample_rate=16000.0, start_time=0.0, capacity=None, width=None):
+        """One segment through the network; returns dict(feats [T x dim], t_start, t_end, sizes).  The segment is pulled
+        twice (count, then fill) unless `width` (the packet size) is given: networks with side effects -- a cache node
+        that writes what passes through -- must be run once."""
         samples = np.ascontiguousarray(samples, np.float32)
         cap = int(capacity if capacity is not None else samples.size // 16 + 64)
         dim = C.c_int(0)
+        if width is not None:
+            feats = np.zeros((cap, int(width)), np.float32)
+            ts, te, sizes = np.zeros(cap, np.float64), np.zeros(cap, np.float64), np.zeros(cap, np.int32)
+            n = self._L.ref_flow_run(C.c_void_p(self._h), port.encode(), _p(samples), C.c_long(samples.size),
+                                     C.c_double(sample_rate), C.c_double(start_time), _p(feats), C.c_long(cap),
+                                     int(width), _p(ts), _p(te), C.byref(dim), _p(sizes))
+            if n < 0 or n > cap or dim.value > int(width):
+                raise RuntimeError("ref_flow_run: %s" % (self._L.ref_last_error().decode() or "capacity / width too small"))
+            return dict(feats=feats[:n], t_start=ts[:n], t_end=te[:n], sizes=sizes[:n])
         # first pass counts packets and finds their width
         n = self._L.ref_flow_run(C.c_void_p(self._h), port.encode(), _p(samples), C.c_long(samples.size),
                                  C.c_double(sample_rate), C.c_double(start_time), None, C.c_long(0), 0, None, None,
@@ -136,6 +147,10 @@ class FlowNetwork:
         if n2 != n:
             raise RuntimeError("the network produced %d packets on the second pass, %d on the first" % (n2, n))
         return dict(feats=feats, t_start=ts, t_end=te, sizes=sizes)
+
+    def set_parameter(self, name, value):
+        if self._L.ref_flow_set_parameter(C.c_void_p(self._h), name.encode(), str(value).encode()) != 0:
+            raise RuntimeError("network has no parameter %s" % name)
 
     def attribute(self, port, name):
         buf = C.create_string_buffer(256)
@@ -187,3 +202,77 @@ class FeatureScorer:
 
     def __del__(self):
         self.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's own readers / writers of its model files (oracle/refbuild/ref_io.cc)
+def _io(native=False):
+    L = lib(native)
+    L.ref_mm_load.restype = C.c_void_p
+    return L
+
+
+def write_mixture_text(ms, path, precision=6, native=False):
+    """Mm::Module_::writeMixtureSet (text; `ms` is an oracle.pyoracle.MixtureSet)"""
+    if _io(native).ref_mm_write_text(C.byref(ms.c), str(path).encode(), int(precision)) != 0:
+        raise RuntimeError("the reference could not write %s" % path)
+
+
+def write_mixture_estimator(ms, feats, mix_of_frame, path, native=False):
+    """Viterbi accumulation of the frames on `ms` (frame t -> mixture mix_of_frame[t], density chosen by the reference's
+    diagonal-maximum scorer), accumulators written by Mm::Module_::writeMixtureSetEstimator"""
+    feats = np.ascontiguousarray(feats, np.float32)
+    mof = np.ascontiguousarray(mix_of_frame, np.uint32)
+    if _io(native).ref_mm_write_estimator(C.byref(ms.c), _p(feats), C.c_long(feats.shape[0]), _p(mof),
+                                          str(path).encode()) != 0:
+        raise RuntimeError("the reference could not write %s" % path)
+
+
+def read_mixture_file(path, native=False):
+    """Mm::Module_::readMixtureSet -> dict in the layout of rasr_b200.io.read_mixture_set"""
+    L = _io(native)
+    h = L.ref_mm_load(str(path).encode(), None)
+    if not h:
+        raise RuntimeError("the reference could not read %s" % path)
+    h = C.c_void_p(h)
+    sizes = np.zeros(6, np.uint32)
+    L.ref_mm_sizes(h, _p(sizes))
+    dim, n_mix, n_dns, n_mean, n_cov, n_ent = (int(v) for v in sizes)
+    out = dict(dim=dim, mix_offsets=np.zeros(n_mix + 1, np.uint32), mix_density=np.zeros(n_ent, np.uint32),
+               mix_log_weight=np.zeros(n_ent, np.float64), dens_mean=np.zeros(n_dns, np.uint32),
+               dens_cov=np.zeros(n_dns, np.uint32), means=np.zeros((n_mean, dim), np.float32),
+               variances=np.zeros((n_cov, dim), np.float32))
+    L.ref_mm_dump(h, _p(out["mix_offsets"]), _p(out["mix_density"]), _p(out["mix_log_weight"]), _p(out["dens_mean"]),
+                  _p(out["dens_cov"]), _p(out["means"]), _p(out["variances"]))
+    L.ref_mm_unload(h)
+    return out
+
+
+def write_matrix(filename, m, native=False):
+    m = np.ascontiguousarray(m, np.float32)
+    if _io(native).ref_math_write_matrix(str(filename).encode(), m.shape[0], m.shape[1], _p(m)) != 0:
+        raise RuntimeError("the reference could not write %s" % filename)
+
+
+def read_matrix(filename, native=False):
+    L, r, c = _io(native), C.c_int(0), C.c_int(0)
+    if L.ref_math_read_matrix(str(filename).encode(), C.byref(r), C.byref(c), None, C.c_long(0)) != 0:
+        raise RuntimeError("the reference could not read %s" % filename)
+    out = np.zeros((r.value, c.value), np.float32)
+    L.ref_math_read_matrix(str(filename).encode(), C.byref(r), C.byref(c), _p(out), C.c_long(out.size))
+    return out
+
+
+def write_vector(filename, v, native=False):
+    v = np.ascontiguousarray(v, np.float32)
+    if _io(native).ref_math_write_vector(str(filename).encode(), v.size, _p(v)) != 0:
+        raise RuntimeError("the reference could not write %s" % filename)
+
+
+def read_vector(filename, native=False):
+    L, n = _io(native), C.c_int(0)
+    if L.ref_math_read_vector(str(filename).encode(), C.byref(n), None, C.c_long(0)) != 0:
+        raise RuntimeError("the reference could not read %s" % filename)
+    out = np.zeros(n.value, np.float32)
+    L.ref_math_read_vector(str(filename).encode(), C.byref(n), _p(out), C.c_long(out.size))
+    return out

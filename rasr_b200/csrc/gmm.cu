@@ -683,7 +683,7 @@ int  rb_gmm_tensor_score(rb_gmm_tensor* t, const float* d_feats, long T, float* 
 bool rb_gmm_tensor_screenable(const rb_gmm_tensor* t);
 long rb_gmm_tensor_chunk(const rb_gmm_tensor* t);
 int  rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* d_feats, long n, const uint32_t** words, const float** xT,
-                          long* pitch, cudaStream_t stream);
+                          long* pitch, cudaStream_t stream, cudaEvent_t after_split);
 
 struct rb_gmm {
     rb::DeviceInfo dev;
@@ -726,6 +726,8 @@ struct rb_gmm {
     long                 exactMinFrames = 2048;
     rb::DevBuf<int>      dMixRow;
     rb::DevBuf<float>    dRefRows;
+    cudaEvent_t          tev[4] = {nullptr, nullptr, nullptr, nullptr};  // rb_gmm_set_timing: around the three kernels
+    bool                 timed = false;
     rb_gmm_int*          quantised = nullptr;
     rb_gmm_presel*       presel    = nullptr;
     rb_gmm_presel_int*   preselInt = nullptr;
@@ -741,6 +743,9 @@ struct rb_gmm {
             rb_gmm_presel_int_destroy(preselInt);
         for (cudaEvent_t e : events)
             cudaEventDestroy(e);
+        for (cudaEvent_t e : tev)
+            if (e)
+                cudaEventDestroy(e);
         if (sIn)
             cudaStreamDestroy(sIn);
         if (sOut)
@@ -1061,7 +1066,13 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
     for (long a = 0; a < T; a += chunk) {
         const long   n = std::min(chunk, T - a);
         RefineParams p;
-        RB_CHECK(rb_gmm_tensor_screen(h->tensor, dFeats + (size_t)a * h->dim, n, &p.words, &p.xT, &p.pitch, s));
+        const bool   timing = h->tev[0] != nullptr && a == 0;  // the first chunk of the call is the one that is timed
+        if (timing)
+            cudaEventRecord(h->tev[0], s);
+        RB_CHECK(rb_gmm_tensor_screen(h->tensor, dFeats + (size_t)a * h->dim, n, &p.words, &p.xT, &p.pitch, s,
+                                      timing ? h->tev[1] : nullptr));
+        if (timing)
+            cudaEventRecord(h->tev[2], s);
         p.scores       = dScores + (size_t)a * h->nMix;
         const int G    = h->refGroups;
         p.rows         = h->dRefRows.p;
@@ -1076,6 +1087,10 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
         const int  grid  = (int)std::max<long>(p.nGroups, std::min<long>(items, h->refSlots));
         h->refine<<<grid, kThreads, h->refSmem, s>>>(p);
         RB_LAUNCH_CHECK();
+        if (timing) {
+            cudaEventRecord(h->tev[3], s);
+            h->timed = true;
+        }
     }
     return RB_OK;
 }
@@ -1350,6 +1365,36 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
         rb::set_error("gmm scoring failed on the device: %s", cudaGetErrorString(e));
         return RB_ERR_CUDA;
     }
+    return RB_OK;
+}
+
+// Measurement hook for bench.py's roofline: events around the three kernels of the exact two-pass route (first chunk of
+// a call).  rb_gmm_get_timing waits for the last timed call and returns its split / screen / refine durations in ms;
+// RB_ERR_STATE if the last calls took the direct kernel.
+extern "C" int rb_gmm_set_timing(rb_gmm* h, int on) {
+    RB_REQUIRE(h != nullptr, "gmm handle is NULL");
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    for (cudaEvent_t& e : h->tev) {
+        if (on && !e)
+            RB_CUDA(cudaEventCreate(&e));
+        if (!on && e) {
+            cudaEventDestroy(e);
+            e = nullptr;
+        }
+    }
+    h->timed = false;
+    return RB_OK;
+}
+
+extern "C" int rb_gmm_get_timing(rb_gmm* h, float* ms3) {
+    RB_REQUIRE(h && ms3, "NULL argument");
+    if (!h->tev[0] || !h->timed) {
+        rb::set_error("no timed two-pass call on this handle");
+        return RB_ERR_STATE;
+    }
+    RB_CUDA(cudaEventSynchronize(h->tev[3]));
+    for (int i = 0; i < 3; ++i)
+        RB_CUDA(cudaEventElapsedTime(ms3 + i, h->tev[i], h->tev[i + 1]));
     return RB_OK;
 }
 

@@ -809,7 +809,7 @@ long rb_gmm_tensor_chunk(const rb_gmm_tensor* t) {
 // Exact batch-float scoring, first half: for n <= chunk frames compute the candidate-density words (*words, laid out
 // [nMix / 4][pitch][4]) and the reference's scaled features, transposed ([dp x pitch], x' = fl(feat * isd)) (*xT).
 int rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* dFeats, long n, const uint32_t** words, const float** xT,
-                         long* pitch, cudaStream_t s) {
+                         long* pitch, cudaStream_t s, cudaEvent_t afterSplit) {
     RB_REQUIRE(t->screenable, "this mixture set cannot be screened");
     RB_REQUIRE(n >= 1 && n <= t->chunk, "bad frame count for one screening pass");
     RB_CHECK(ensure_capacity(t, n, true));
@@ -817,6 +817,8 @@ int rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* dFeats, long n, const ui
     gmm_split_features_kernel<<<blocks, 256, 0, s>>>(dFeats, t->dIsd.p, t->dCentre.p, n, t->dim, t->dp, t->kPad, t->scale,
                                                      t->dA.p, t->dXnorm.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p, t->cap);
     RB_LAUNCH_CHECK();
+    if (afterSplit)
+        cudaEventRecord(afterSplit, s);
     *xT    = t->dXT.p;
     *words = t->dWords.p;
     *pitch = t->cap;

@@ -16,6 +16,7 @@ no meaning; f32 fields are parsed as f32 (strtof), weights as f64.  Files ending
 import ctypes
 import gzip
 import io
+import struct
 
 import numpy as np
 
@@ -116,6 +117,146 @@ def write_mixture_set(path, ms):
         out.append(" " + " ".join([str(row.size)] + ["%s 1" % g32(v) for v in row]))
     with _open(path, "wb") as f:
         f.write(("\n".join(out) + "\n").encode("ascii"))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Mixture-set accumulator files -- what the reference reads for every mixture file name that does not end in .pms or
+# .gz (the `.mix` files of a trained system): MixtureSetReader falls back to MixtureSetEstimatorReader
+# (src/Mm/MixtureSetReader.hh:108-121), which loads the ACCUMULATORS of the last training iteration and estimates the
+# mixture set from them.  (`MixtureSet::read(Core::BinaryInputStream&)` itself is a stub that raises "reading of
+# binary mixture sets is not supported in this version", src/Mm/MixtureSet.cc:219-222.)
+#
+# Layout (little endian; AbstractMixtureSetEstimator::read, src/Mm/AbstractMixtureSetEstimator.cc:404-478):
+#   char magic[8] = "MIXSET\0\0", u32 version, u32 dimension
+#   u32 nMeans,       per mean:       u32 size, f64 sum[size],         weight      (VectorAccumulator.hh:80-95)
+#   u32 nCovariances, per covariance: u32 size, f64 sumOfSquares[size], weight
+#   u32 nDensities,   per density:    u32 meanIndex, u32 covarianceIndex            (GaussDensityEstimator.cc:46-56)
+#   u32 nMixtures,    per mixture:    u32 nDensities, per entry u32 densityIndex, weight   (MixtureEstimator.cc:140-160)
+#   weight = f64 for version > 0, u32 count for version 0
+# Estimation (AbstractMixtureSetEstimator::estimate :305-338 with the parameter defaults of :25-58):
+#   - a mixture without observations is an error; per mixture, densities whose weight is below
+#     max(minimum-observation-weight = 5, total * minimum-relative-weight = 0) are dropped, except the heaviest one
+#     (MixtureEstimator.cc:64-79);
+#   - densities, means and covariances are renumbered in the order the mixtures refer to them (:804-817);
+#   - mixture weights: log(weight), normalised with logExpNorm (Mixture.cc:63-74, Utilities.hh:43-51);
+#   - mean = sum / weight (f64, narrowed to f32; GaussDensityEstimator.cc:148-157);
+#   - variance = (sumOfSquares - SUM_means sum_m^2 / weight_m) / weight over ALL means that shared the covariance before
+#     densities were dropped (:201-229), then clipped from below at minimum-variance (0: off).
+# ----------------------------------------------------------------------------------------------------------------
+def read_mixture_estimator(path, min_observation_weight=5.0, min_relative_weight=0.0, min_variance=0.0,
+                           normalize_mixture_weights=True):
+    """-> mixture-set dict (keys as read_mixture_set) estimated from an accumulator file"""
+    with _open(path, "rb") as f:
+        data = f.read()
+    if data[:8].rstrip(b"\0") != b"MIXSET":
+        raise ValueError('%s: mixture set estimator file with magic "%s" could not be read, "MIXSET" expected'
+                         % (path, data[:8].rstrip(b"\0").decode("ascii", "replace")))
+    pos = 8
+
+    def take(fmt):
+        nonlocal pos
+        v = struct.unpack_from("<" + fmt, data, pos)
+        pos += struct.calcsize("<" + fmt)
+        return v if len(v) > 1 else v[0]
+
+    version, dim = take("II")
+    weight_fmt = "d" if version > 0 else "I"
+
+    def accumulators():
+        out = []
+        for _ in range(take("I")):
+            n = take("I")
+            sums = np.frombuffer(data, "<f8", n, pos).astype(np.float64)
+            skip(8 * n)
+            out.append((sums, float(take(weight_fmt))))
+        return out
+
+    def skip(n):
+        nonlocal pos
+        pos += n
+
+    mean_acc = accumulators()
+    cov_acc = accumulators()
+    dens = [take("II") for _ in range(take("I"))]
+    mixtures = []
+    for _ in range(take("I")):
+        entries = []
+        for _ in range(take("I")):
+            d = take("I")
+            entries.append([d, float(take(weight_fmt))])
+        mixtures.append(entries)
+    if pos > len(data):
+        raise ValueError("%s: error reading mixture set estimator (file too short)" % path)
+
+    # means per covariance BEFORE densities are dropped (CovarianceToMeanSetMap over every density a mixture refers to)
+    cov_means = {}
+    for entries in mixtures:
+        for d, _ in entries:
+            cov_means.setdefault(dens[d][1], set()).add(dens[d][0])
+    for m, entries in enumerate(mixtures):
+        total = sum(w for _, w in entries)
+        if total == 0:
+            raise ValueError("%s: mixture %d has zero weight" % (path, m))
+        min_w = max(min_observation_weight, total * min_relative_weight)
+        heaviest = max(range(len(entries)), key=lambda i: (entries[i][1], -i))  # first maximum
+        keep_id = id(entries[heaviest])
+        mixtures[m] = [e for e in entries if e[1] >= min_w or id(e) == keep_id]
+    # renumber in order of first reference
+    d_map, m_map, c_map = {}, {}, {}
+    for entries in mixtures:
+        for d, _ in entries:
+            m_map.setdefault(dens[d][0], len(m_map))
+            c_map.setdefault(dens[d][1], len(c_map))
+            d_map.setdefault(d, len(d_map))
+    offs, mix_density, logw = [0], [], []
+    wmin = -np.finfo(np.float64).max  # Core::Type<f64>::min
+    for entries in mixtures:
+        lw = np.array([np.log(w) if w > 0 else wmin for _, w in entries], np.float64)
+        if normalize_mixture_weights and lw.size:
+            k = int(np.argmax(lw))
+            acc = 0.0
+            for i, v in enumerate(lw):
+                if i != k:
+                    acc += np.exp(v - lw[k])
+            lw = lw - (np.log1p(acc) + lw[k])
+        mix_density += [d_map[d] for d, _ in entries]
+        logw += list(lw)
+        offs.append(len(mix_density))
+    dens_mean = np.zeros(len(d_map), np.uint32)
+    dens_cov = np.zeros(len(d_map), np.uint32)
+    for d, i in d_map.items():
+        dens_mean[i], dens_cov[i] = m_map[dens[d][0]], c_map[dens[d][1]]
+    means = np.zeros((len(m_map), dim), np.float32)
+    for old, i in m_map.items():
+        sums, w = mean_acc[old]
+        if w != 0:
+            means[i] = (sums / w).astype(np.float32)
+    variances = np.zeros((len(c_map), dim), np.float32)
+    for old, i in c_map.items():
+        sq, w = cov_acc[old]
+        if w == 0:
+            continue
+        mean_sq = np.zeros(dim, np.float64)
+        for mo in sorted(cov_means[old]):  # the reference walks a std::set ordered by address = creation order
+            ms, mw = mean_acc[mo]
+            if mw > 0:
+                mean_sq += ms * ms / mw
+        v = ((sq - mean_sq) / w).astype(np.float32)
+        if min_variance != 0:
+            v = np.maximum(v, np.float32(min_variance))
+        variances[i] = v
+    return dict(dim=int(dim), mix_offsets=np.asarray(offs, np.uint32), mix_density=np.asarray(mix_density, np.uint32),
+                mix_log_weight=np.asarray(logw, np.float64), dens_mean=dens_mean, dens_cov=dens_cov, means=means,
+                variances=variances)
+
+
+def read_mixture_file(path, **estimator_parameters):
+    """What Mm::Module_::readMixtureSet does with a file name (src/Mm/MixtureSetReader.cc:27-34, .hh:108-121): text
+    reader for *.pms and *.gz, the accumulator reader + estimation for everything else."""
+    ext = "." + str(path).rsplit(".", 1)[-1] if "." in str(path) else ""
+    if ext in (".pms", ".gz"):
+        return read_mixture_set(path)
+    return read_mixture_estimator(path, **estimator_parameters)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -34,10 +34,12 @@ class MixtureSet:
 
     @classmethod
     def read(cls, path):
-        """Load a mixture text file (".pms" / ".pms.gz", doc/file_formats/mixture_file.rst) -- rasr_b200.io"""
+        """Load a mixture file the way Mm::Module_::readMixtureSet does: text (".pms" / ".gz",
+        doc/file_formats/mixture_file.rst) or, for any other name (".mix"), the accumulator file of the last training
+        iteration, estimated on the fly -- rasr_b200.io"""
         from . import io as rio
 
-        return cls(**rio.read_mixture_set(path))
+        return cls(**rio.read_mixture_file(path))
 
     @property
     def n_mixtures(self):
@@ -106,6 +108,18 @@ class GmmScorer:
         best = np.zeros((T, self.n_mixtures), np.uint32) if want_density else None
         capi.check(capi.lib().rb_gmm_score(self._h, capi.ptr(feats), T, capi.ptr(scores), capi.ptr(best)))
         return (scores, best) if want_density else scores
+
+    def set_timing(self, on=True):
+        capi.check(capi.lib().rb_gmm_set_timing(self._h, int(on)))
+
+    def timing(self):
+        """(split, screen, refine) ms of the last timed two-pass call, or None if the direct kernel served it"""
+        ms = np.zeros(3, np.float32)
+        rc = capi.lib().rb_gmm_get_timing(self._h, capi.ptr(ms))
+        if rc == -5:
+            return None
+        capi.check(rc)
+        return [float(v) for v in ms]
 
     def score_dev(self, d_feats, T, d_scores, d_best=None, stream=None):
         capi.check(capi.lib().rb_gmm_score_dev(self._h, capi.ptr(d_feats), int(T), capi.ptr(d_scores),
