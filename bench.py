@@ -365,6 +365,9 @@ class Bench:
         self.peaks = measured_peaks()
 
     def barrier(self):
+        # drain the device first: the library's own exchange (rb_comm_*: NCCL on a second communicator, spin barriers)
+        # must never be in flight together with torch's NCCL barrier
+        self.torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
@@ -862,10 +865,26 @@ def main():
         line["workloads"] = extra
     if world > 1 and (args.gather or args.workload == "all"):
         torch.cuda.empty_cache()
+        # the scoring numbers above stand whatever happens here: if the exchange does not come back (a peer that cannot
+        # be mapped, a collective that never completes) every rank gives up after 90 s, rank 0 prints the line without it
+        finished = threading.Event()
+
+        def give_up():
+            if not finished.is_set():
+                line["gather"] = dict(unavailable="the score exchange did not finish within 90 s")
+                if rank == 0:
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+
+        watchdog = threading.Timer(90.0, give_up)
+        watchdog.daemon = True
+        watchdog.start()
         try:
             line["gather"] = b.gather_variants(max(3, min(args.steps, 10)), 3)
         except Exception as e:  # noqa: BLE001 -- e.g. no peer access on this box: reported, the scoring numbers stand
             line["gather"] = dict(unavailable=str(e)[:300])
+        finished.set()
+        watchdog.cancel()
     sampler.stop()
 
     if rank == 0:
