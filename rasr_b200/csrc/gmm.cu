@@ -24,10 +24,12 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 
 namespace {
 
 using namespace rbdev;
+using namespace rbf32x2;
 
 constexpr int kThreads        = 256;
 constexpr int kFramesPerThr   = 2;
@@ -50,46 +52,6 @@ struct GmmParams {
     int             nFrameBlocks;
     int             vec4;  // 1: nMix % 4 == 0 and scores 16-byte aligned -> float4 stores
 };
-
-// packed pairs of f32 in one 64-bit register pair (sm_100 FADD2 / FMUL2 / FFMA2)
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float lo2(uint64_t v) {
-    return __uint_as_float((uint32_t)v);
-}
-__device__ __forceinline__ float hi2(uint64_t v) {
-    return __uint_as_float((uint32_t)(v >> 32));
-}
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
-// strict (non-contracted) a + d*d per lane.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the
-// explicit rounding modifiers, so the product is formed with scalar FMULs whose .rn is honoured.
-__device__ __forceinline__ uint64_t sqadd2(uint64_t d, uint64_t a) {
-    const float dl = lo2(d), dh = hi2(d);
-    return pack2(__fadd_rn(lo2(a), __fmul_rn(dl, dl)), __fadd_rn(hi2(a), __fmul_rn(dh, dh)));
-}
 
 __device__ __forceinline__ float sq_acc(float d, float a, bool fuse) {
     return fuse ? __fmaf_rn(d, d, a) : __fadd_rn(a, __fmul_rn(d, d));
@@ -279,29 +241,9 @@ struct RefineParams {
     int          nMix, nGroups, nFrameBlocks;
 };
 
-// refinement rows: [ mu' (NB*8) | c | 0 ] = NB*8 + 2 floats = an ODD number (4 NB + 1) of 8-byte words, so that the 16
-// lanes of an LDS.64 phase that pick 16 different rows of a mixture hit 16 different bank pairs and the per-lane gather
-// runs at the full shared-memory rate (with the 176-byte rows of the direct kernel, rows j and j + 8 collide and the
-// gather cost 2.2 wavefronts per phase: 291 us per 100k frames).
-__host__ __device__ constexpr int refine_pitch(int nb) {
-    return nb * 8 + 2;
-}
-
-template<int NB, bool FUSE>
-__device__ __forceinline__ float batch_row_score(const float* row, const uint64_t (&x)[NB * 4]) {
-    const uint64_t* r    = reinterpret_cast<const uint64_t*>(row);
-    uint64_t        a[4] = {r[NB * 4], 0ull, 0ull, 0ull};  // (c, 0): constant first, lane 0 of the first accumulator
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint64_t d = sub2(r[4 * b + j], x[4 * b + j]);
-            a[j]             = FUSE ? fma2(d, d, a[j]) : sqadd2(d, a[j]);
-        }
-    }
-    const uint64_t q = add2(add2(a[0], a[2]), add2(a[1], a[3]));
-    return __fadd_rn(lo2(q), hi2(q));
-}
+constexpr int kStageQuads = 4;                    // mixtures staged per flush = 16
+constexpr int kStagePitch = kStageQuads * 4 + 4;  // floats per frame row of the staging tile (80 B: conflict-free STS.128)
+constexpr int kStageBytes = (kThreads / 32) * 32 * kStagePitch * 4;
 
 template<int NB, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 3) gmm_refine_kernel(const RefineParams p) {
@@ -319,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 3) gmm_refine_kernel(const RefinePar
     const size_t   gBegin = (size_t)row0 * ROWF * 4, gEnd = (size_t)row1 * ROWF * 4;
     const size_t   cBegin = gBegin & ~(size_t)15, cEnd = (gEnd + 15) & ~(size_t)15;
     const float*   rows   = reinterpret_cast<const float*>(region + (gBegin - cBegin));
+    float*         stage  = reinterpret_cast<float*>(region + (((gEnd - cBegin) + 47) & ~(size_t)15));  // after the rows
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -346,9 +289,10 @@ __global__ void __launch_bounds__(kThreads, 3) gmm_refine_kernel(const RefinePar
 #pragma unroll
         for (int i = 0; i < NB * 4; ++i)
             x[i] = pack2(__ldg(p.xT + (size_t)(2 * i) * p.pitch + tc), __ldg(p.xT + (size_t)(2 * i + 1) * p.pitch + tc));
-        const uint4* w   = reinterpret_cast<const uint4*>(p.words) + tc;  // + (m4 / 4) * pitch
-        float*       out = p.scores + (size_t)tc * p.nMix;
-        uint4        mk  = t < p.T ? __ldg(w + (size_t)(mix0 >> 2) * p.pitch) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4* w  = reinterpret_cast<const uint4*>(p.words) + tc;  // + (m4 / 4) * pitch
+        uint4        mk = t < p.T ? __ldg(w + (size_t)(mix0 >> 2) * p.pitch) : make_uint4(0u, 0u, 0u, 0u);
+        const long   warpFrame0 = (long)fb * kThreads + (tid & ~31);
+        int          staged = 0;  // quads waiting in this warp's staging tile
         for (int m4 = mix0; m4 < mix1; m4 += 4) {
             const uint32_t sets[4] = {mk.x, mk.y, mk.z, mk.w};
             if (m4 + 4 < mix1 && t < p.T)  // the next quad's sets are on their way while this one is evaluated
@@ -367,8 +311,26 @@ __global__ void __launch_bounds__(kThreads, 3) gmm_refine_kernel(const RefinePar
                 }
                 o[q] = best < FLT_MAX ? __fmul_rn(best, 0.5f) : best;
             }
-            if (t < p.T)
-                *reinterpret_cast<float4*>(out + m4) = make_float4(o[0], o[1], o[2], o[3]);
+            // Scores leave through a per-warp staging tile [32 frames][kStageQuads quads]: a thread's own 16 bytes per
+            // quad would be a store instruction touching 32 different lines, 1 KB apart; after the transpose four lanes
+            // share a frame and an instruction writes 64 contiguous bytes into each of 8 rows (a quarter of the LSU
+            // wavefronts, whole sectors -- which is also what a peer's window behind NVLink wants to see).
+            float* mine = stage + (tid >> 5) * (32 * kStagePitch);
+            *reinterpret_cast<float4*>(mine + (tid & 31) * kStagePitch + staged * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            ++staged;
+            if (staged == kStageQuads || m4 + 4 >= mix1) {
+                __syncwarp();
+                const int mFirst = m4 + 4 - staged * 4;
+                for (int k = tid & 31; k < 32 * staged; k += 32) {
+                    const int  r = k / staged, c = k - r * staged;
+                    const long tf = warpFrame0 + r;
+                    if (tf < p.T)
+                        *reinterpret_cast<float4*>(p.scores + (size_t)tf * p.nMix + mFirst + c * 4) =
+                                *reinterpret_cast<const float4*>(mine + r * kStagePitch + c * 4);
+                }
+                __syncwarp();
+                staged = 0;
+            }
         }
     }
 }
@@ -1019,14 +981,15 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
         mixRow[m + 1] = mixRow[m] + h->rowsOfMixture[m];
     int    pickG = 0;
     size_t pickSmem = 0;
-    for (size_t budget : {(size_t)49 * 1024, (size_t)100 * 1024, (size_t)200 * 1024}) {
+    for (size_t budget : {(size_t)72 * 1024, (size_t)110 * 1024, (size_t)200 * 1024}) {
         for (int G = 1; G <= kMaxGroups && !pickG; ++G) {
             std::vector<int> grpRow, grpMix;
             make_groups(h, G, grpRow, grpMix);
             size_t need = 0;
             for (size_t g = 0; g + 1 < grpRow.size(); ++g)
                 need = std::max(need, 16 + rb::round_up(sizeof(int) * (size_t)(grpMix[g + 1] - grpMix[g]), 16) +
-                                              rb::round_up(sizeof(float) * (size_t)(grpRow[g + 1] - grpRow[g]) * pitch, 16) + 32);
+                                              rb::round_up(sizeof(float) * (size_t)(grpRow[g + 1] - grpRow[g]) * pitch, 16) + 64 +
+                                              kStageBytes);
             if (need <= budget) {
                 pickG    = G;
                 pickSmem = need;

@@ -179,11 +179,15 @@ struct EpiGmmScreen {
         uint32_t           out[NO];
 #pragma unroll
         for (int g = 0; g < NO; ++g) {
+            // v <= lim  <=>  lim - v >= 0  <=>  the sign bit of (lim - v) is clear (the difference of equal values is
+            // +0).  The subtraction runs on the FMA pipe, one funnel shift per column collects the sign bits: the
+            // epilogue warps are bound by the half-rate ALU pipe, where compare + select + or cost three slots.
             const float lim = tree_min<S>(v + g * S) + st.thr;
             uint32_t    mk  = 0;
 #pragma unroll
-            for (int j = 0; j < S; ++j)
-                mk |= v[g * S + j] <= lim ? (1u << j) : 0u;
+            for (int j = S - 1; j >= 0; --j)
+                mk = __funnelshift_l(__float_as_uint(__fsub_rn(lim, v[g * S + j])), mk, 1);
+            mk     = ~mk & kAll;
             out[g] = (all || mk == 0) ? kAll : mk;
         }
         // nMix % 4 == 0 (a condition of the exact route), so whole quads are always inside the matrix
