@@ -55,10 +55,11 @@ def test_c2_shape_equals_oracle_and_direct_kernel(oracle, diag, contraction):
     assert np.array_equal(bits(two), bits(want))
 
 
-@pytest.mark.parametrize("dpm", [8, 32])
-def test_other_uniform_mixture_sizes(oracle, dpm):
-    msd = synth.mixture_set(dim=39, n_mixtures=64, densities_per_mixture=dpm, seed=dpm)
-    f = synth.features(3000, 39, seed=dpm)
+@pytest.mark.parametrize("dpm,dim", [(8, 39), (32, 39), (16, 26), (8, 32), (32, 30)])
+def test_other_uniform_mixture_sizes(oracle, dpm, dim):
+    """8 / 16 / 32 densities per mixture; 68 mixtures: the model's last 256-column block is only partly filled"""
+    msd = synth.mixture_set(dim=dim, n_mixtures=68, densities_per_mixture=dpm, seed=dpm + dim)
+    f = synth.features(3000, dim, seed=dpm)
     want = oracle.gmm_batch_float(oracle.MixtureSet(**msd), f, threads=8)
     assert np.array_equal(bits(scorer(msd, "two-pass").score(f)), bits(want))
 
