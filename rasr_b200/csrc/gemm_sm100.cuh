@@ -4,11 +4,14 @@
 //   * operands are staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a 4-stage ring,
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128x256x16), accumulators
 //     live in TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps the MMAs of i+1),
-//   * four epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per call) and
-//     hand 32 consecutive columns of one row to the epilogue functor (bias / activation / min ...),
+//   * eight epilogue warps (two per TMEM lane quarter, 128 accumulator columns each) read the accumulator with
+//     tcgen05.ld (32 lanes x 32 columns per call) and hand 32 consecutive columns of one row to the epilogue functor
+//     (bias / activation ...).  With four warps -- one per scheduler, nothing to hide its latencies behind -- the
+//     epilogue of a 128 x 256 tile took ~7.7 us: longer than the MMAs of a K = 448 tile (2.7 us), so the Nn input
+//     layer ran at 561 TFLOP/s, and the f32 score layer's epilogue stuck out from under its MMAs too,
 //   * persistent grid (one CTA per SM), tiles ordered n-fastest so the A tile of a frame block is
 //     re-read from L2, never from HBM.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..7 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue.
 #pragma once
 
 #include <cuda.h>
@@ -25,7 +28,7 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES     = BM * BK * 2;
 constexpr int B_BYTES     = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS     = 256;
+constexpr int THREADS     = 384;  // 4 control warps + 8 epilogue warps
 constexpr int TMEM_COLS   = 512;
 constexpr int SMEM_BYTES  = STAGES * STAGE_BYTES + 256 + 1024;  // ring + barriers + alignment slack
 constexpr int OUT_STAGE_BYTES = 4 * 2 * 32 * 32 * 4;             // TMA-store epilogue: 4 warps x 2 boxes of 32 x 32 f32
@@ -121,8 +124,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 //   struct State;                                   per-thread state that lives across the chunks of one tile row
 //   __device__ void begin(State&, int row) const;   once per (tile, row)
 //   __device__ void chunk(State&, int row, int col0, const float (&v)[32]) const;   columns col0..col0+31
-// row < M is guaranteed by the caller; columns may exceed N -- the functor masks them.  Chunks of a
-// row arrive in increasing column order.
+// row < M is guaranteed by the caller; columns may exceed N -- the functor masks them.  The two column halves of a
+// tile row are handled by different warps: a functor must not carry state from chunk to chunk.
 // Epilogues with  static constexpr bool kTmaStore = true  provide  transform(col0, v, o)  instead of chunk():
 // the kernel stages each 32 x 32 f32 block in (128-byte swizzled) shared memory and hands it to the TMA unit, which
 // writes whole lines and clips at the matrix edges; the LSU never sees the row-strided stores that otherwise make a
@@ -131,6 +134,10 @@ template<class Epi, bool TMA_STORE = false>
 __global__ void __launch_bounds__(THREADS, 1)
         gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOut, int M, int N, int K, uint32_t idesc, const Epi epi) {
+    // epilogue warps: eight (two per TMEM lane quarter) for the register epilogues; the TMA-store variant keeps four --
+    // its staging boxes would cost a ring stage, and with three stages the score layer lost more (721 -> 790 us per
+    // 18944 frames) than the second set of warps gave
+    constexpr int EPI_WARPS = TMA_STORE ? 4 : 8;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw   = smem_u32(smem_dyn);
     const uint32_t pad   = (1024u - (raw & 1023u)) & 1023u;
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -211,11 +218,13 @@ __global__ void __launch_bounds__(THREADS, 1)
             }
         }
     }
-    else if (warp >= 4) {
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
+    else if (warp >= 4 && warp < 4 + EPI_WARPS) {
+        const int q = warp & 3;          // TMEM lane quarter this warp may read
+        const int h = (warp - 4) >> 2;   // eight warps: which half of the tile's columns
+        constexpr int CPW = BN / 32 / (EPI_WARPS / 4);  // 32-column chunks per warp
         uint32_t  tc = 0;
         // TMA-store staging: two 4 KB boxes per epilogue warp behind the operand ring (1024-byte aligned)
-        const uint32_t outStage = sbase + STAGES * STAGE_BYTES + 1024 + q * 2 * 4096;
+        const uint32_t outStage = sbase + STAGES * STAGE_BYTES + 1024 + (warp - 4) * 2 * 4096;
         for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++tc) {
             const int      mb = tile / nNB, nb = tile - mb * nNB;
             const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             if (row < M)
                 epi.begin(st, row);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c += 2) {  // two TMEM loads in flight per wait
+            for (int c = h * CPW; c < (h + 1) * CPW; c += 2) {  // two TMEM loads in flight per wait
                 float          v0[32], v1[32];
                 const uint32_t ta = tmemBase + ((uint32_t)(q * 32) << 16) + a * BN + c * 32;
                 tmem_ld32_issue(ta, v0);
