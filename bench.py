@@ -676,12 +676,18 @@ class Bench:
                 d.update(dtype="f16x3 split operands, f32 accumulate",
                          parity="<= 1e-4 relative to the reference scores (tests/test_gpu_gmm_tensor.py)")
             else:
-                fp32_ceiling = 148 * 128 * 1965.0e6 / (2 * 39 * 4096)
+                # FP32 peak: measured with scripts/micro/fp32_rate.cu (profiles/fp32_peak.json) -- a dependent
+                # FADD2 -> FFMA2 stream, the instruction pair this kernel is made of, sustains 115 of the nominal 128
+                # lane-FMAs per clock and SM
+                ppath = os.path.join(ROOT, "profiles", "fp32_peak.json")
+                lanes = json.load(open(ppath))["fadd2_ffma2_pairs"] if os.path.exists(ppath) else 128.0
+                fp32_ceiling = 148 * lanes * 1965.0e6 / (2 * 39 * 4096)
                 d.update(dtype="f32", parity="bit-identical (tests/test_gpu_gmm.py)",
                          fp32_alu=dict(ceiling_frames_per_s=fp32_ceiling, frac=(T / (tms * 1e-3)) / fp32_ceiling,
-                                       note="direct form: sub + fma per (frame, density, dim) on 148 x 128 lanes at "
-                                            "1965 MHz; scripts/micro/fp32_rate.cu measures 0.90 of that for a dependent "
-                                            "FADD2 -> FFMA2 stream"))
+                                       lane_fma_per_clk_per_sm=lanes, nominal_lane_fma_per_clk_per_sm=128.0,
+                                       peak_source="measured (profiles/fp32_peak.json, scripts/micro/fp32_rate.cu)"
+                                       if os.path.exists(ppath) else "nominal",
+                                       note="direct form: sub + fma per (frame, density, dim) on 148 SMs at 1965 MHz"))
             out[name] = d
             del vs
         return out
