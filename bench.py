@@ -775,6 +775,12 @@ class Bench:
             score(ex.target(0))
             ex.barrier(sptr)
 
+        fan = ex.targets()
+
+        def v_step_fused_allgather():
+            pipeline.score_utterances_fanout_dev(fe, scorer, d_samples, offs, d_feats, fan, sptr)
+            ex.barrier(sptr)
+
         def v_step_push_root():
             score(d_local)
             ex.gather(d_local, 0, "p2p", sptr)
@@ -790,6 +796,7 @@ class Bench:
         for name, fn, with_compute in (("allgather_p2p", v_p2p, False), ("allgather_nccl", v_nccl, False),
                                        ("step_allgather_p2p", v_step_p2p, True), ("step_allgather_nccl", v_step_nccl, True),
                                        ("step_allgather_p2p_5_slabs_overlapped", v_step_p2p_slabs, True),
+                                       ("step_allgather_fused_epilogue", v_step_fused_allgather, True),
                                        ("step_gather_root0_fused_epilogue", v_step_fused_root, True),
                                        ("step_gather_root0_push", v_step_push_root, True)):
             ms = timed(fn)

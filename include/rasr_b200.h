@@ -272,6 +272,11 @@ int  rb_gmm_dim(const rb_gmm* h);
 int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores, uint32_t* best_density);
 int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* d_scores, uint32_t* d_best_density,
                      void* stream);
+/* the same scores into n_dst (1..16) destinations at once, row for row: d_dst[k] [T * n_mixtures] may lie in the HBM of
+ * another GPU of the box (rb_comm_window_ptr) -- the all-gather of the score matrix fused into the scorer.  The exact
+ * route of RB_GMM_BATCH_FLOAT stores to every destination from its last kernel (64 contiguous bytes per frame and store
+ * instruction, crossing NVLink while the kernel is still computing); the other modes copy the finished matrix. */
+int rb_gmm_score_fanout_dev(rb_gmm* h, const float* d_feats, long T, int n_dst, float* const* d_dst, void* stream);
 /* measurement hook (bench.py): RB_GMM_BATCH_FLOAT scores batches of >= 2048 frames in three kernels (operand split,
  * tensor-core screening of the candidate densities, exact evaluation of the candidates); with timing on, CUDA events
  * bracket them on the launching stream and rb_gmm_get_timing returns their durations of the last such call
@@ -361,6 +366,10 @@ int rb_pipeline_score_s16(rb_frontend* fe, rb_gmm* gmm, const int16_t* samples, 
 int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, const int64_t* offsets, int n_utt,
                           float* d_feats, float* d_scores, void* stream);
 
+/* rb_pipeline_score_dev with the scores fanned out to n_dst destinations (rb_gmm_score_fanout_dev) */
+int rb_pipeline_score_fanout_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, const int64_t* offsets, int n_utt,
+                                 float* d_feats, int n_dst, float* const* d_dst, void* stream);
+
 /* audio -> MFCC -> (rb_postproc, may be NULL) -> Nn scores (config C4 fed from audio).  scores [frames *
  * rb_nn_n_emissions(nn)] (= n_classes with a class mapping, else the number of outputs);
  * the device variant needs d_feats [frames * feat_dim] and, with a post-processor, d_post [frames * dim_out]. */
@@ -430,6 +439,8 @@ int rb_pipeline_search(rb_frontend* fe, rb_gmm* gmm, rb_search* ls, const void* 
  *                               (float*)ptr + row_offsets[rank] * row_len as d_scores to rb_gmm_score_dev /
  *                               rb_pipeline_score_dev / rb_nn_score_dev makes the scorer's epilogue store straight into
  *                               the consumer's HBM over NVLink (compute and transfer fused, no local copy)
+ *                               (rb_gmm_score_fanout_dev / rb_pipeline_score_fanout_dev take one such pointer per rank: the
+ *                               all-gather fused into the scorer)
  *   rb_comm_gather_scores_dev   root < 0: all-gather, else gather to `root`.  RB_COMM_P2P: one kernel of 128-bit loads
  *                               and NVLink stores into the peers' windows (skips the local copy when d_send already is
  *                               this rank's slice of its own window); RB_COMM_NCCL: ncclAllGather (equal shards) or

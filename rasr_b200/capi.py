@@ -31,7 +31,7 @@ SYMBOLS = [
     "rb_frontend_process", "rb_frontend_process_s16", "rb_frontend_process_dev", "rb_frontend_set_debug", "rb_frontend_read_stages",
     "rb_dc_default_cfg", "rb_frontend_dc_max_frames", "rb_frontend_process_dc", "rb_frontend_dc_runs", "rb_frontend_set_dc_detection",
     "rb_gmm_configure_preselection", "rb_gmm_get_clustering", "rb_test_glibc_rand", "rb_test_introsort",
-    "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_set_timing", "rb_gmm_get_timing", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
+    "rb_gmm_create", "rb_gmm_destroy", "rb_gmm_set_timing", "rb_gmm_get_timing", "rb_gmm_score_fanout_dev", "rb_pipeline_score_fanout_dev", "rb_gmm_n_mixtures", "rb_gmm_dim", "rb_gmm_score", "rb_gmm_score_dev",
     "rb_nn_create", "rb_nn_destroy", "rb_nn_n_outputs", "rb_nn_n_inputs", "rb_nn_set_class_mapping", "rb_nn_n_emissions", "rb_nn_score", "rb_nn_score_dev",
     "rb_nn_forward", "rb_nn_forward_dev", "rb_pipeline_score", "rb_pipeline_score_s16", "rb_pipeline_score_dev", "rb_test_gemm_bf16", "rb_test_gemm_bench",
     "rb_pipeline_nn_score", "rb_pipeline_nn_score_dev",
@@ -165,6 +165,8 @@ def lib():
     L.rb_test_introsort.restype = None
     L.rb_gmm_n_mixtures.argtypes = [vp]
     L.rb_gmm_dim.argtypes = [vp]
+    L.rb_gmm_score_fanout_dev.argtypes = [vp, vp, C.c_long, C.c_int, vp, vp]
+    L.rb_pipeline_score_fanout_dev.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp]
     L.rb_gmm_set_timing.argtypes = [vp, C.c_int]
     L.rb_gmm_get_timing.argtypes = [vp, vp]
     L.rb_gmm_score.argtypes = [vp, vp, C.c_long, vp, vp]

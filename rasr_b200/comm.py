@@ -87,6 +87,13 @@ class ScoreExchange:
         and the scores are stored over NVLink as they are computed"""
         return self.peer_window(peer) + int(self.row_offsets[self.rank]) * self.row_len * 4
 
+    def targets(self, root=-1):
+        """this rank's rows in the window of `root`, or (root < 0) of every rank, own window first: the destination list
+        of rb_gmm_score_fanout_dev / rb_pipeline_score_fanout_dev"""
+        if root >= 0:
+            return [self.target(root)]
+        return [self.target(self.rank)] + [self.target(r) for r in range(self.world) if r != self.rank]
+
     @property
     def my_rows(self):
         return int(self.row_offsets[self.rank + 1] - self.row_offsets[self.rank])

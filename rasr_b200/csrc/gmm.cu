@@ -237,6 +237,8 @@ struct RefineParams {
     long         pitch;
     const uint32_t* words;  // [nMix / 4][pitch][4] candidate sets (EpiGmmScreen, gmm_tensor.cu)
     float*       scores;    // [T * nMix]
+    float*       extra[15]; // further destinations that receive the same rows (peer windows, rb_gmm_score_fanout_dev)
+    int          nExtra;
     long         T;
     int          nMix, nGroups, nFrameBlocks;
 };
@@ -324,9 +326,13 @@ __global__ void __launch_bounds__(kThreads, 3) gmm_refine_kernel(const RefinePar
                 for (int k = tid & 31; k < 32 * staged; k += 32) {
                     const int  r = k / staged, c = k - r * staged;
                     const long tf = warpFrame0 + r;
-                    if (tf < p.T)
-                        *reinterpret_cast<float4*>(p.scores + (size_t)tf * p.nMix + mFirst + c * 4) =
-                                *reinterpret_cast<const float4*>(mine + r * kStagePitch + c * 4);
+                    if (tf < p.T) {
+                        const float4 val = *reinterpret_cast<const float4*>(mine + r * kStagePitch + c * 4);
+                        const size_t at  = (size_t)tf * p.nMix + mFirst + c * 4;
+                        *reinterpret_cast<float4*>(p.scores + at) = val;
+                        for (int e = 0; e < p.nExtra; ++e)  // the same 64 contiguous bytes per frame into every peer's window
+                            *reinterpret_cast<float4*>(p.extra[e] + at) = val;
+                    }
                 }
                 __syncwarp();
                 staged = 0;
@@ -1024,7 +1030,8 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
     return RB_OK;
 }
 
-int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores, cudaStream_t s) {
+int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores, float* const* extra, int nExtra,
+                          cudaStream_t s) {
     const long chunk = rb_gmm_tensor_chunk(h->tensor);
     for (long a = 0; a < T; a += chunk) {
         const long   n = std::min(chunk, T - a);
@@ -1037,6 +1044,9 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
         if (timing)
             cudaEventRecord(h->tev[2], s);
         p.scores       = dScores + (size_t)a * h->nMix;
+        p.nExtra       = nExtra;
+        for (int e = 0; e < nExtra; ++e)
+            p.extra[e] = extra[e] + (size_t)a * h->nMix;
         const int G    = h->refGroups;
         p.rows         = h->dRefRows.p;
         p.grp_row      = h->dGrpRow.p + (size_t)G * kGroupStride;
@@ -1225,6 +1235,36 @@ extern "C" int rb_gmm_dim(const rb_gmm* h) {
     return h ? h->dim : 0;
 }
 
+namespace {
+// scores into d_scores and, row for row, into the nExtra further destinations (windows of peer GPUs): the exact two-pass
+// route stores them from the refinement kernel itself, every other route copies the finished matrix
+int score_dev_impl(rb_gmm* h, const float* d_feats, long T, float* d_scores, float* const* extra, int nExtra,
+                   uint32_t* d_best, cudaStream_t s) {
+    if (h->mode == RB_GMM_BATCH_FLOAT && h->refGroups > 0 && T >= h->exactMinFrames && ((uintptr_t)d_scores % 16) == 0) {
+        bool aligned = true;
+        for (int e = 0; e < nExtra; ++e)
+            aligned = aligned && ((uintptr_t)extra[e] % 16) == 0;
+        if (aligned)
+            return launch_exact_two_pass(h, d_feats, T, d_scores, extra, nExtra, s);
+    }
+    int rc;
+    if (h->mode == RB_GMM_BATCH_TENSOR)
+        rc = rb_gmm_tensor_score(h->tensor, d_feats, T, d_scores, s);
+    else if (h->mode == RB_GMM_BATCH_INT)
+        rc = rb_gmm_int_score(h->quantised, d_feats, T, d_scores, s);
+    else if (h->mode == RB_GMM_BATCH_PRESELECT)
+        rc = rb_gmm_presel_score(h->presel, d_feats, T, d_scores, s);
+    else if (h->mode == RB_GMM_BATCH_PRESELECT_INT)
+        rc = rb_gmm_presel_int_score(h->preselInt, d_feats, T, d_scores, s);
+    else
+        rc = launch_simt(h, d_feats, T, d_scores, d_best, s);
+    RB_CHECK(rc);
+    for (int e = 0; e < nExtra; ++e)
+        RB_CUDA(cudaMemcpyAsync(extra[e], d_scores, (size_t)T * h->nMix * sizeof(float), cudaMemcpyDefault, s));
+    return RB_OK;
+}
+}  // namespace
+
 extern "C" int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* d_scores, uint32_t* d_best,
                                 void* stream) {
     RB_REQUIRE(h != nullptr, "gmm handle is NULL");
@@ -1234,28 +1274,24 @@ extern "C" int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* 
     RB_REQUIRE(d_feats && d_scores, "NULL device buffer");
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-    if (h->mode == RB_GMM_BATCH_TENSOR) {
-        RB_REQUIRE(d_best == nullptr, "best-density output is not available in tensor mode");
-        return rb_gmm_tensor_score(h->tensor, d_feats, T, d_scores, s);
-    }
-    if (h->mode == RB_GMM_BATCH_INT) {
-        RB_REQUIRE(d_best == nullptr, "Mm::BatchIntFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
-        return rb_gmm_int_score(h->quantised, d_feats, T, d_scores, s);
-    }
-    if (h->mode == RB_GMM_BATCH_PRESELECT) {
-        RB_REQUIRE(d_best == nullptr, "the preselection scorer does not report densities; use RB_GMM_DIAG_MAX");
-        return rb_gmm_presel_score(h->presel, d_feats, T, d_scores, s);
-    }
-    if (h->mode == RB_GMM_BATCH_PRESELECT_INT) {
-        RB_REQUIRE(d_best == nullptr, "the preselection scorer does not report densities; use RB_GMM_DIAG_MAX");
-        return rb_gmm_presel_int_score(h->preselInt, d_feats, T, d_scores, s);
-    }
-    if (h->mode == RB_GMM_BATCH_FLOAT) {
-        RB_REQUIRE(d_best == nullptr, "Mm::BatchFloatFeatureScorer does not report densities; use RB_GMM_DIAG_MAX");
-        if (h->refGroups > 0 && T >= h->exactMinFrames && ((uintptr_t)d_scores % 16) == 0)
-            return launch_exact_two_pass(h, d_feats, T, d_scores, s);
-    }
-    return launch_simt(h, d_feats, T, d_scores, d_best, s);
+    if (h->mode != RB_GMM_DIAG_MAX && h->mode != RB_GMM_DIAG_SUM)
+        RB_REQUIRE(d_best == nullptr, "this scorer mode does not report densities; use RB_GMM_DIAG_MAX");
+    return score_dev_impl(h, d_feats, T, d_scores, nullptr, 0, d_best, s);
+}
+
+extern "C" int rb_gmm_score_fanout_dev(rb_gmm* h, const float* d_feats, long T, int n_dst, float* const* d_dst,
+                                       void* stream) {
+    RB_REQUIRE(h != nullptr, "gmm handle is NULL");
+    RB_REQUIRE(T >= 0, "negative frame count");
+    RB_REQUIRE(n_dst >= 1 && n_dst <= 16 && d_dst, "between 1 and 16 destinations");
+    if (T == 0)
+        return RB_OK;
+    RB_REQUIRE(d_feats != nullptr, "NULL device buffer");
+    for (int e = 0; e < n_dst; ++e)
+        RB_REQUIRE(d_dst[e] != nullptr, "destination %d is NULL", e);
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    return score_dev_impl(h, d_feats, T, d_dst[0], d_dst + 1, n_dst - 1, nullptr, s);
 }
 
 // Host-pointer entry point: frames are cut into slabs; H2D of slab i+1, scoring of slab i and D2H of

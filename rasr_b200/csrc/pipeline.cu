@@ -54,6 +54,24 @@ extern "C" int rb_pipeline_score_dev(rb_frontend* fe, rb_gmm* gmm, const float* 
     return RB_OK;
 }
 
+extern "C" int rb_pipeline_score_fanout_dev(rb_frontend* fe, rb_gmm* gmm, const float* d_samples, const int64_t* offsets,
+                                            int n_utt, float* d_feats, int n_dst, float* const* d_dst, void* stream) {
+    RB_REQUIRE(fe && gmm && offsets && n_utt >= 0, "bad argument");
+    RB_REQUIRE(rb_frontend_feat_dim(fe) == rb_gmm_dim(gmm), "front-end emits %d-dim features, mixture set expects %d",
+               rb_frontend_feat_dim(fe), rb_gmm_dim(gmm));
+    if (n_utt == 0)
+        return RB_OK;
+    const long T = rb_frontend_count_frames(fe, offsets, n_utt, nullptr);
+    RB_REQUIRE(T >= 0, "bad offsets");
+    if (T == 0)
+        return RB_OK;
+    RB_REQUIRE(d_samples && d_feats && d_dst && n_dst >= 1, "NULL device buffer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : rb_frontend_stream(fe);
+    RB_CHECK(rb_frontend_process_dev(fe, d_samples, offsets, n_utt, d_feats, s));
+    RB_CHECK(rb_gmm_score_fanout_dev(gmm, d_feats, T, n_dst, d_dst, s));
+    return RB_OK;
+}
+
 // Host-pointer entry point: the utterances are cut into slabs (whole utterances, ~8 per call); H2D of slab i+1,
 // front-end + scoring of slab i and D2H of slab i-1 overlap on three streams.  PCIe is the end-to-end bound
 // (640 B of samples in, 1 KB of scores out per frame).

@@ -109,6 +109,12 @@ class GmmScorer:
         capi.check(capi.lib().rb_gmm_score(self._h, capi.ptr(feats), T, capi.ptr(scores), capi.ptr(best)))
         return (scores, best) if want_density else scores
 
+    def score_fanout_dev(self, d_feats, T, dsts, stream=None):
+        """the same scores into every destination of `dsts` (device addresses, e.g. ScoreExchange.targets())"""
+        arr = (C.c_void_p * len(dsts))(*[capi.ptr(d).value for d in dsts])
+        capi.check(capi.lib().rb_gmm_score_fanout_dev(self._h, capi.ptr(d_feats), int(T), len(dsts), arr,
+                                                      capi.ptr(stream)))
+
     def set_timing(self, on=True):
         capi.check(capi.lib().rb_gmm_set_timing(self._h, int(on)))
 

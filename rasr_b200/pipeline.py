@@ -51,6 +51,19 @@ def score_utterances_dev(frontend, gmm, d_samples, offsets, d_feats, d_scores, s
                                                 capi.ptr(stream)))
 
 
+def score_utterances_fanout_dev(frontend, gmm, d_samples, offsets, d_feats, dsts, stream=None):
+    """score_utterances_dev with the scores stored into every destination of `dsts` (device addresses: this rank's rows
+    in the windows of the GPUs that need them, rasr_b200.comm.ScoreExchange.targets()) -- the exchange fused into the
+    scorer's last kernel"""
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    import ctypes as C
+
+    arr = (C.c_void_p * len(dsts))(*[capi.ptr(d).value for d in dsts])
+    capi.check(capi.lib().rb_pipeline_score_fanout_dev(frontend.handle, gmm.handle, capi.ptr(d_samples), capi.ptr(offsets),
+                                                       offsets.size - 1, capi.ptr(d_feats), len(dsts), arr,
+                                                       capi.ptr(stream)))
+
+
 def nn_score_utterances(frontend, postproc, nn, samples, offsets, out=None):
     """audio -> MFCC -> post-processing (may be None) -> Nn scores; host buffers in, [total_frames x n_emissions] out
     (n_emissions = the class count of an active class mapping, else the number of network outputs)."""

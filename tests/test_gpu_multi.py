@@ -116,6 +116,31 @@ def _worker(rank, port, q):
         res["inplace_allgather"] = bool(np.array_equal(win.cpu().numpy(), ref))
         dist.barrier()
 
+        # 5a. the all-gather fused into the scorer: its last kernel stores every row into both windows
+        win.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        big = synth.features(6000, 39, seed=78)          # large enough for the screening + refinement route
+        offs2 = np.array([0, 2500, 6000], np.int64)
+        ex2 = comm.ScoreExchange(WORLD, rank, rank, offs2, M, comm.torch_exchange(dist))
+        mine2 = torch.from_numpy(big[offs2[rank]:offs2[rank + 1]]).to(dev)
+        scorer.score_fanout_dev(mine2, int(offs2[rank + 1] - offs2[rank]), ex2.targets(), sp)
+        ex2.barrier(sp)
+        stream.synchronize()
+        ref2 = o.gmm_batch_float(o.MixtureSet(**msd), big, threads=4)
+        res["fused_allgather"] = bool(np.array_equal(ex2.window(torch).cpu().numpy(), ref2))
+        # ... and a mode without a fused store path (copies of the finished matrix)
+        tscorer = mm.GmmScorer(mm.MixtureSet.from_dict(msd), "batch-int", device=rank)
+        single = torch.empty((int(offs2[-1]), M), dtype=torch.float32, device=dev)
+        tscorer.score_dev(torch.from_numpy(big).to(dev), int(offs2[-1]), single, None, sp)
+        dist.barrier()
+        tscorer.score_fanout_dev(mine2, int(offs2[rank + 1] - offs2[rank]), ex2.targets(), sp)
+        ex2.barrier(sp)
+        stream.synchronize()
+        res["fanout_by_copy"] = bool(torch.equal(ex2.window(torch), single))
+        dist.barrier()
+        ex2.close()
+
         # 5b. row-range pushes (the slab-pipelined exchange): two halves of the shard, the second to rank 0 only
         win.zero_()
         torch.cuda.synchronize()
@@ -170,8 +195,8 @@ def test_score_exchange_two_ranks(oracle, diag):
         r = res[rank]
         assert "error" not in r, r.get("error")
         diag("score_exchange_rank%d" % rank, **r)
-        for key in ("allgather_p2p", "gather_root1", "allgather_nccl", "fused_scorer", "inplace_allgather", "push_rows",
-                    "rejects_overflow"):
+        for key in ("allgather_p2p", "gather_root1", "allgather_nccl", "fused_scorer", "inplace_allgather", "fused_allgather", "fanout_by_copy",
+                    "push_rows", "rejects_overflow"):
             assert r[key] is True, (rank, key)
         assert r["nccl_version"] >= 20000
 

@@ -131,3 +131,24 @@ def test_gather_scores_gloo_world2():
     for rank, sizes, s in res:
         assert sum(sizes) == 26
         assert s == pytest.approx(total)
+
+
+def test_score_exchange_fails_loudly_without_a_device():
+    """rb_comm_* has no CPU path either: creating a communicator without an sm_100 device is RB_ERR_NO_DEVICE, bad
+    world / rank arguments are RB_ERR_INVALID before any device is touched"""
+    import ctypes as C
+
+    from rasr_b200 import capi, comm
+
+    L = capi.lib()
+    h = C.c_void_p()
+    assert L.rb_comm_create(0, 0, 0, C.byref(h)) == -1
+    assert L.rb_comm_create(4, 4, 0, C.byref(h)) == -1
+    assert L.rb_comm_create(17, 0, 0, C.byref(h)) == -1
+    with pytest.raises(ValueError):
+        comm.ScoreExchange(2, 0, 0, [0, 5], 8)  # row_offsets must have world + 1 entries
+    if capi.device_count() == 0:
+        assert L.rb_comm_create(2, 0, 0, C.byref(h)) == -2
+        with pytest.raises(capi.RasrB200Error) as e:
+            comm.ScoreExchange(1, 0, 0, [0, 5], 8)
+        assert e.value.status == -2
