@@ -347,6 +347,21 @@ def bind_to_gpu_numa_node(torch, index):
         return None
 
 
+class stdout_to_stderr:
+    """fd-level redirect: libraries that print to stdout (NCCL's version banner at communicator creation) must not get
+    in front of the one JSON line this program owes its caller"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class Bench:
     """Set-up and timing of one workload on this rank's GPU."""
 
@@ -706,7 +721,8 @@ class Bench:
         scorer = mm.GmmScorer(mm.MixtureSet.from_dict(synth.mixture_set()), device=self.local_rank)
         T = int(fe.count_frames(offs)[-1])
         row_offsets = np.arange(world + 1, dtype=np.int64) * T
-        ex = comm.ScoreExchange(world, rank, self.local_rank, row_offsets, 256, comm.torch_exchange(self.dist), nccl=True)
+        with stdout_to_stderr():
+            ex = comm.ScoreExchange(world, rank, self.local_rank, row_offsets, 256, comm.torch_exchange(self.dist), nccl=True)
         d_samples = torch.from_numpy(samples_h).to(dev)
         d_feats = torch.empty((T, 39), dtype=torch.float32, device=dev)
         d_local = torch.empty((T, 256), dtype=torch.float32, device=dev)
