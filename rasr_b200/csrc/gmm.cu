@@ -649,6 +649,7 @@ int  rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, c
 void rb_gmm_tensor_destroy(rb_gmm_tensor* t);
 int  rb_gmm_tensor_score(rb_gmm_tensor* t, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
 bool rb_gmm_tensor_screenable(const rb_gmm_tensor* t);
+int  rb_gmm_tensor_reserve(rb_gmm_tensor* t, long frames, bool screen);
 long rb_gmm_tensor_chunk(const rb_gmm_tensor* t);
 int  rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* d_feats, long n, const uint32_t** words, const float** xT,
                           long* pitch, cudaStream_t stream, cudaEvent_t after_split);
@@ -1330,6 +1331,12 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     }
     cudaStream_t sIn = h->sIn, sOut = h->sOut;
     int          rc = RB_OK;
+    if (h->tensor) {  // the largest slab's scratch once, before the pipeline starts
+        long largest = 0;
+        for (int i = 0; i < nSlabs; ++i)
+            largest = std::max(largest, cut[i + 1] - cut[i]);
+        RB_CHECK(rb_gmm_tensor_reserve(h->tensor, largest, h->mode == RB_GMM_BATCH_FLOAT));
+    }
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const long  a = cut[i], n = cut[i + 1] - cut[i];
         cudaEvent_t evIn = h->events[2 * i], evK = h->events[2 * i + 1];

@@ -803,6 +803,12 @@ void rb_gmm_tensor_destroy(rb_gmm_tensor* t) {
     delete t;
 }
 
+// size the per-call buffers once for calls of up to `frames` frames (a host-buffer call that scores slab after slab must
+// not reallocate -- cudaFree synchronises the device -- in the middle of its copy / compute pipeline)
+int rb_gmm_tensor_reserve(rb_gmm_tensor* t, long frames, bool screen) {
+    return ensure_capacity(t, frames, screen);
+}
+
 bool rb_gmm_tensor_screenable(const rb_gmm_tensor* t) {
     return t && t->screenable;
 }
