@@ -1,7 +1,164 @@
 // common.cu -- error plumbing, device selection and the library-level entry points.
 #include "common.cuh"
 
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
 namespace rb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// worker pool of the host stager (see common.cuh).  Created on first use, never destroyed: the threads sleep on a
+// condition variable and die with the process (a static destructor could race with them at exit).
+namespace {
+struct CopyJob {
+    cudaEvent_t       ev;
+    const void*       src;
+    void*             dst;
+    size_t            bytes;
+    std::atomic<int>* busy;
+    std::atomic<int>* failed;
+    int               device;
+};
+struct CopyPool {
+    std::mutex              m;
+    std::condition_variable cv;
+    std::deque<CopyJob>     q;
+    CopyPool() {
+        unsigned n = std::thread::hardware_concurrency();
+        n          = n >= 16 ? 4 : (n >= 4 ? 2 : 1);
+        if (const char* e = getenv("RB_COPY_THREADS"))
+            n = (unsigned)std::max(1, atoi(e));
+        for (unsigned i = 0; i < n; ++i)
+            std::thread([this] { run(); }).detach();
+    }
+    void run() {
+        int dev = -1;
+        for (;;) {
+            CopyJob j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return !q.empty(); });
+                j = q.front();
+                q.pop_front();
+            }
+            if (j.device >= 0 && j.device != dev) {
+                cudaSetDevice(j.device);
+                dev = j.device;
+            }
+            if (j.ev && cudaEventSynchronize(j.ev) != cudaSuccess) {
+                cudaGetLastError();
+                j.failed->store(1);
+            }
+            else
+                std::memcpy(j.dst, j.src, j.bytes);
+            if (j.ev)
+                j.busy->store(0, std::memory_order_release);
+            else
+                j.busy->fetch_sub(1, std::memory_order_release);  // plain copy: one part of a parallel_memcpy done
+        }
+    }
+    // urgent: input copies gate the GPU's work and overtake the queued output copies
+    void submit(const CopyJob& j, bool urgent = false) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            if (urgent)
+                q.push_front(j);
+            else
+                q.push_back(j);
+        }
+        cv.notify_one();
+    }
+};
+CopyPool& copy_pool() {
+    static CopyPool* p = new CopyPool();  // intentionally leaked
+    return *p;
+}
+}  // namespace
+
+// host-to-host copy split over the pool's workers and the calling thread (a single core of the GPU boxes' hosts copies
+// ~9 GB/s; pageable features have to reach page-locked memory faster than that to keep up with the DMA)
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t kPart = (size_t)1 << 20;
+    if (bytes < 4 * kPart) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const int        parts = 4;
+    const size_t     step  = round_up((bytes + parts - 1) / parts, 4096);
+    std::atomic<int> pending{0};
+    std::atomic<int> failed{0};
+    for (int i = 1; i < parts; ++i) {
+        const size_t off = (size_t)i * step;
+        if (off >= bytes)
+            break;
+        pending.fetch_add(1);
+        copy_pool().submit(CopyJob{nullptr, (const unsigned char*)src + off, (unsigned char*)dst + off,
+                                   std::min(step, bytes - off), &pending, &failed, -1},
+                           true);
+    }
+    std::memcpy(dst, src, std::min(step, bytes));
+    while (pending.load(std::memory_order_acquire))
+        std::this_thread::yield();
+}
+
+HostStager::~HostStager() {
+    drain();
+    for (cudaEvent_t e : done)
+        cudaEventDestroy(e);
+    delete[] busy;
+}
+
+int HostStager::ensure(size_t slot_bytes, int slots, int dev) {
+    if (slot_bytes <= slotBytes && slots <= nSlots)
+        return RB_OK;
+    RB_CHECK(drain());
+    slot_bytes = std::max(slot_bytes, slotBytes);
+    slots      = std::max(slots, nSlots);
+    RB_CHECK(ring.reserve(slot_bytes * (size_t)slots));
+    while ((int)done.size() < slots) {
+        cudaEvent_t e = nullptr;
+        RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        done.push_back(e);
+    }
+    delete[] busy;
+    busy = new std::atomic<int>[slots];
+    for (int i = 0; i < slots; ++i)
+        busy[i].store(0);
+    slotBytes = slot_bytes;
+    nSlots    = slots;
+    next      = 0;
+    device    = dev;
+    return RB_OK;
+}
+
+int HostStager::d2h(void* dst, const void* d_src, size_t bytes, cudaStream_t s) {
+    for (size_t off = 0; off < bytes; off += slotBytes) {
+        const size_t n = std::min(slotBytes, bytes - off);
+        const int    k = next;
+        next           = (next + 1) % nSlots;
+        while (busy[k].load(std::memory_order_acquire))  // the worker is still copying this slot's previous content out
+            std::this_thread::yield();
+        unsigned char* slot = ring.p + (size_t)k * slotBytes;
+        RB_CUDA(cudaMemcpyAsync(slot, (const unsigned char*)d_src + off, n, cudaMemcpyDeviceToHost, s));
+        RB_CUDA(cudaEventRecord(done[k], s));
+        busy[k].store(1, std::memory_order_release);
+        copy_pool().submit(CopyJob{done[k], slot, (unsigned char*)dst + off, n, &busy[k], &failed, device});
+    }
+    return RB_OK;
+}
+
+int HostStager::drain() {
+    for (int k = 0; k < nSlots; ++k)
+        while (busy && busy[k].load(std::memory_order_acquire))
+            std::this_thread::yield();
+    if (failed.exchange(0)) {
+        set_error("a device-to-host copy into the staging ring failed");
+        return RB_ERR_CUDA;
+    }
+    return RB_OK;
+}
 
 static thread_local char t_error[1024] = "";
 

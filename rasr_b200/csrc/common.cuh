@@ -172,6 +172,32 @@ inline size_t round_up(size_t v, size_t m) {
     return (v + m - 1) / m * m;
 }
 
+// host-to-host copy on several cores (the stager's worker pool + the calling thread)
+void parallel_memcpy(void* dst, const void* src, size_t bytes);
+
+// D2H into PAGEABLE caller memory.  cudaMemcpyAsync to pageable memory is staged by the driver and blocks the calling
+// thread until the copy is done, so the H2D / kernel / D2H slab pipeline of a host-buffer call degenerates to one step
+// after the other (C2: 14.9 M frames/s against 50.8 M from page-locked buffers).  The stager keeps the pipeline
+// asynchronous: the DMA goes into a ring of page-locked slots, and a small process-wide pool of worker threads waits
+// for each slot's event and copies it on into the caller's buffer while the next slabs are in flight.
+struct HostStager {
+    PinnedBuf<unsigned char> ring;
+    size_t                   slotBytes = 0;
+    int                      nSlots = 0, next = 0, device = 0;
+    std::vector<cudaEvent_t> done;       // DMA into the slot has completed
+    std::atomic<int>*        busy = nullptr;  // per slot: 1 while a worker still has to copy it out
+    HostStager() {}
+    HostStager(const HostStager&)            = delete;
+    HostStager& operator=(const HostStager&) = delete;
+    ~HostStager();
+    int ensure(size_t slot_bytes, int slots, int dev);
+    // enqueue: device -> slot(s) on stream s, then slot -> dst by a worker.  Returns once everything is enqueued.
+    int d2h(void* dst, const void* d_src, size_t bytes, cudaStream_t s);
+    // block until every enqueued copy has reached the caller's buffer; RB_ERR_CUDA if a DMA failed
+    int drain();
+    std::atomic<int> failed{0};
+};
+
 }  // namespace rb
 
 // ---------------------------------------------------------------- device-side PTX wrappers

@@ -695,6 +695,8 @@ struct rb_gmm {
     long                 exactMinFrames = 2048;
     rb::DevBuf<int>      dMixRow;
     rb::DevBuf<float>    dRefRows;
+    rb::HostStager       stager;  // host-buffer calls with pageable score buffers
+    rb::PinnedBuf<float> hFeats;  // ... and pageable feature buffers: copied here by several cores, then DMA
     cudaEvent_t          tev[4] = {nullptr, nullptr, nullptr, nullptr};  // rb_gmm_set_timing: around the three kernels
     bool                 timed = false;
     rb_gmm_int*          quantised = nullptr;
@@ -1331,6 +1333,13 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     }
     cudaStream_t sIn = h->sIn, sOut = h->sOut;
     int          rc = RB_OK;
+    // pageable score buffer: through the page-locked staging ring + worker threads (common.cuh HostStager)
+    const bool staged = !rb_host_is_pinned(scores) && getenv("RB_NO_HOST_STAGER") == nullptr;
+    if (staged)
+        RB_CHECK(h->stager.ensure((size_t)4 << 20, 8, h->dev.ordinal));
+    const bool stagedIn = !rb_host_is_pinned(feats) && getenv("RB_NO_HOST_STAGER") == nullptr && (size_t)T * D * 4 >= ((size_t)4 << 20);
+    if (stagedIn)
+        RB_CHECK(h->hFeats.reserve((size_t)T * D));
     if (h->tensor) {  // the largest slab's scratch once, before the pipeline starts
         long largest = 0;
         for (int i = 0; i < nSlabs; ++i)
@@ -1340,8 +1349,12 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const long  a = cut[i], n = cut[i + 1] - cut[i];
         cudaEvent_t evIn = h->events[2 * i], evK = h->events[2 * i + 1];
-        if (cudaMemcpyAsync(h->dFeats.p + a * D, feats + a * D, (size_t)n * D * 4, cudaMemcpyHostToDevice, sIn) !=
-            cudaSuccess)
+        const float* src = feats + a * D;
+        if (stagedIn) {  // (the staging area holds the whole call: no slot has to be waited for)
+            rb::parallel_memcpy(h->hFeats.p + a * D, src, (size_t)n * D * 4);
+            src = h->hFeats.p + a * D;
+        }
+        if (cudaMemcpyAsync(h->dFeats.p + a * D, src, (size_t)n * D * 4, cudaMemcpyHostToDevice, sIn) != cudaSuccess)
             rc = RB_ERR_CUDA;
         cudaEventRecord(evIn, sIn);
         cudaStreamWaitEvent(h->stream, evIn, 0);
@@ -1350,9 +1363,11 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
                                   best_density ? h->dBest.p + a * M : nullptr, h->stream);
         cudaEventRecord(evK, h->stream);
         cudaStreamWaitEvent(sOut, evK, 0);
-        if (rc == RB_OK &&
-            cudaMemcpyAsync(scores + a * M, h->dScores.p + a * M, (size_t)n * M * 4, cudaMemcpyDeviceToHost, sOut) !=
-                    cudaSuccess)
+        if (rc == RB_OK && staged)
+            rc = h->stager.d2h(scores + a * M, h->dScores.p + a * M, (size_t)n * M * 4, sOut);
+        else if (rc == RB_OK &&
+                 cudaMemcpyAsync(scores + a * M, h->dScores.p + a * M, (size_t)n * M * 4, cudaMemcpyDeviceToHost, sOut) !=
+                         cudaSuccess)
             rc = RB_ERR_CUDA;
         if (rc == RB_OK && best_density &&
             cudaMemcpyAsync(best_density + a * M, h->dBest.p + a * M, (size_t)n * M * 4, cudaMemcpyDeviceToHost,
@@ -1362,6 +1377,11 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     cudaError_t e1 = cudaStreamSynchronize(sIn);
     cudaError_t e2 = cudaStreamSynchronize(h->stream);
     cudaError_t e3 = cudaStreamSynchronize(sOut);
+    if (staged) {  // the workers' copies into the caller's buffer
+        const int rs = h->stager.drain();
+        if (rc == RB_OK)
+            rc = rs;
+    }
     if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
         rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != RB_OK)

@@ -9,6 +9,8 @@ struct Scratch {
     rb::DevBuf<float>   samples, feats, post, scores;
     rb::DevBuf<int16_t> pcm;
     rb::CopyStreams     copy;
+    rb::HostStager      stager;  // pageable result buffers (common.cuh)
+    rb::PinnedBuf<unsigned char> hIn;  // pageable sample buffers: copied here by several cores, then DMA
 };
 // one scratch set per front-end handle (and calling thread), released when the handle is destroyed
 std::vector<std::pair<const rb_frontend*, Scratch*>>& scratch_table() {
@@ -126,6 +128,16 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
     cudaEvent_t* evIn = sc.copy.pool.data();
     cudaEvent_t* evK  = sc.copy.pool.data() + nSlabs;
     int rc = RB_OK;
+    // pageable result buffers go through the page-locked staging ring + worker threads (common.cuh HostStager)
+    const bool stagedScores = scores && !rb_host_is_pinned(scores) && getenv("RB_NO_HOST_STAGER") == nullptr;
+    const bool stagedFeats  = feats && !rb_host_is_pinned(feats) && getenv("RB_NO_HOST_STAGER") == nullptr;
+    if (stagedScores || stagedFeats)
+        RB_CHECK(sc.stager.ensure((size_t)4 << 20, 8, rb_frontend_device(fe).ordinal));
+    const size_t sampleBytes = channels ? (size_t)channels * 2 : 4;
+    const bool   stagedIn = nS * sampleBytes >= ((size_t)4 << 20) && !rb_host_is_pinned(samplesRaw) &&
+                          getenv("RB_NO_HOST_STAGER") == nullptr;
+    if (stagedIn)
+        RB_CHECK(sc.hIn.reserve((size_t)nS * sampleBytes));
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const int     u0 = cut[i], u1 = cut[i + 1];
         // the aligned bulk copies of the front-end may read up to 3 samples before a slab's first utterance:
@@ -133,12 +145,14 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
         const int64_t sA = rel[u0], sB = rel[u1];
         const int64_t fA = fo[u0], fB = fo[u1];
         if (sB > sA) {
-            const cudaError_t e =
-                    channels ? cudaMemcpyAsync(sc.pcm.p + sA * channels, pcm + (base + sA) * channels,
-                                               (size_t)(sB - sA) * channels * 2, cudaMemcpyHostToDevice, sIn)
-                             : cudaMemcpyAsync(sc.samples.p + sA, samples + base + sA, (size_t)(sB - sA) * 4,
-                                               cudaMemcpyHostToDevice, sIn);
-            if (e != cudaSuccess)
+            const void*  src   = channels ? (const void*)(pcm + (base + sA) * channels) : (const void*)(samples + base + sA);
+            const size_t bytes = (size_t)(sB - sA) * sampleBytes;
+            if (stagedIn) {  // (the staging area holds the whole call: no slot has to be waited for)
+                rb::parallel_memcpy(sc.hIn.p + (size_t)sA * sampleBytes, src, bytes);
+                src = sc.hIn.p + (size_t)sA * sampleBytes;
+            }
+            void* dst = channels ? (void*)(sc.pcm.p + sA * channels) : (void*)(sc.samples.p + sA);
+            if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sIn) != cudaSuccess)
                 rc = RB_ERR_CUDA;
         }
         cudaEventRecord(evIn[i], sIn);
@@ -155,15 +169,25 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
         cudaEventRecord(evK[i], sK);
         cudaStreamWaitEvent(sOut, evK[i], 0);
         if (rc == RB_OK && fB > fA) {
-            if (scores && cudaMemcpyAsync(scores + fA * M, sc.scores.p + fA * M, (size_t)(fB - fA) * M * 4,
-                                          cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
+            if (stagedScores)
+                rc = sc.stager.d2h(scores + fA * M, sc.scores.p + fA * M, (size_t)(fB - fA) * M * 4, sOut);
+            else if (scores && cudaMemcpyAsync(scores + fA * M, sc.scores.p + fA * M, (size_t)(fB - fA) * M * 4,
+                                               cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
                 rc = RB_ERR_CUDA;
-            if (feats && cudaMemcpyAsync(feats + fA * D, sc.feats.p + fA * D, (size_t)(fB - fA) * D * 4,
-                                         cudaMemcpyDeviceToHost, sOut) != cudaSuccess)
+            if (rc == RB_OK && stagedFeats)
+                rc = sc.stager.d2h(feats + fA * D, sc.feats.p + fA * D, (size_t)(fB - fA) * D * 4, sOut);
+            else if (rc == RB_OK && feats &&
+                     cudaMemcpyAsync(feats + fA * D, sc.feats.p + fA * D, (size_t)(fB - fA) * D * 4, cudaMemcpyDeviceToHost,
+                                     sOut) != cudaSuccess)
                 rc = RB_ERR_CUDA;
         }
     }
     const cudaError_t e1 = cudaStreamSynchronize(sIn), e2 = cudaStreamSynchronize(sK), e3 = cudaStreamSynchronize(sOut);
+    if (stagedScores || stagedFeats) {
+        const int rs = sc.stager.drain();
+        if (rc == RB_OK)
+            rc = rs;
+    }
     if (rc == RB_ERR_CUDA && rb::get_error()[0] == 0)
         rb::set_error("asynchronous copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc != RB_OK)
