@@ -487,7 +487,7 @@ void rb_test_glibc_rand(unsigned seed, int n, int* out);
 void rb_test_introsort(const int* keys, int n, int* perm);
 int rb_test_gemm_bf16(const float* a, const float* b, const float* bias, int M, int N, int K, int act,
                       float* d, int device);
-/* times `iters` launches of one GEMM variant (0: 128x256 tile, 1: 256x256 tile) on device-resident
+/* times `iters` launches of the GEMM (variant 0: 128x256 tile; other values are rejected) on device-resident
  * operands with the bf16 hidden-layer epilogue; *ms_per_iter from CUDA events.  Used by scripts/ only. */
 int rb_test_gemm_bench(int M, int N, int K, int variant, int iters, float* ms_per_iter, int device);
 

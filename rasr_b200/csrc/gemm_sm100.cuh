@@ -289,140 +289,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// 256 x 256 CTA tile: two 128-row accumulators (TMEM columns 0-255 and 256-511) share every B stage,
-// which cuts the L2->SM operand traffic per MAC by a third against the 128 x 256 kernel above (64 KB per
-// 4.2 M MACs instead of 48 KB per 2.1 M).  Large-K GEMMs on this chip are bound by that traffic, not by
-// the tensor pipe, so this is the kernel the Nn layers use.  TMEM is single-buffered here (all 512
-// columns hold the tile), so the epilogue (8 warps) is exposed once per tile: < 10 % at K = 2048.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue.
-constexpr int MT2_BM          = 256;
-constexpr int MT2_STAGES      = 3;
-constexpr int MT2_A_BYTES     = MT2_BM * BK * 2;
-constexpr int MT2_STAGE_BYTES = MT2_A_BYTES + B_BYTES;
-constexpr int MT2_THREADS     = 384;
-constexpr int MT2_SMEM_BYTES  = MT2_STAGES * MT2_STAGE_BYTES + 256 + 1024;
-
-template<class Epi>
-__global__ void __launch_bounds__(MT2_THREADS, 1)
-        gemm16_mt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
-                          int N, int K, uint32_t idesc, const Epi epi) {
-    extern __shared__ unsigned char smem_dyn[];
-    const uint32_t raw   = smem_u32(smem_dyn);
-    const uint32_t pad   = (1024u - (raw & 1023u)) & 1023u;
-    unsigned char* base  = smem_dyn + pad;
-    const uint32_t sbase = raw + pad;
-    uint64_t* full       = reinterpret_cast<uint64_t*>(base + MT2_STAGES * MT2_STAGE_BYTES);
-    uint64_t* empty      = full + MT2_STAGES;
-    uint64_t* tfull      = empty + MT2_STAGES;
-    uint64_t* tempty     = tfull + 1;
-    uint32_t* tmemPtr    = reinterpret_cast<uint32_t*>(tempty + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nMB = (M + MT2_BM - 1) / MT2_BM, nNB = (N + BN - 1) / BN, nTiles = nMB * nNB, nKB = K / BK;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < MT2_STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(tfull, 1);
-        mbar_init(tempty, 8);
-        mbar_fence_init();
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemPtr)),
-                     "r"((uint32_t)TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmemBase = *tmemPtr;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-                const int mb = tile / nNB, nb = tile - mb * nNB;
-                for (int kb = 0; kb < nKB; ++kb, ++it) {
-                    const uint32_t s = it % MT2_STAGES, ph = (it / MT2_STAGES) & 1u;
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    mbar_expect_tx(&full[s], MT2_STAGE_BYTES);
-                    tma_load_2d(sbase + s * MT2_STAGE_BYTES, &tmA, kb * BK, mb * MT2_BM, &full[s]);
-                    tma_load_2d(sbase + s * MT2_STAGE_BYTES + MT2_A_BYTES, &tmB, kb * BK, nb * BN, &full[s]);
-                }
-            }
-        }
-    }
-    else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t it = 0, tc = 0;
-            for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++tc) {
-                mbar_wait(tempty, (tc & 1u) ^ 1u);  // the epilogue has drained the previous tile
-                tc_fence_after();
-                for (int kb = 0; kb < nKB; ++kb, ++it) {
-                    const uint32_t s = it % MT2_STAGES, ph = (it / MT2_STAGES) & 1u;
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after();
-                    const uint64_t a0 = smem_desc(sbase + s * MT2_STAGE_BYTES);
-                    const uint64_t a1 = smem_desc(sbase + s * MT2_STAGE_BYTES + A_BYTES);
-                    const uint64_t bd = smem_desc(sbase + s * MT2_STAGE_BYTES + MT2_A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        tc_mma(tmemBase, a0 + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-                        tc_mma(tmemBase + BN, a1 + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-                    }
-                    tc_commit(&empty[s]);
-                }
-                tc_commit(tfull);
-            }
-        }
-    }
-    else if (warp >= 4) {
-        const int q = warp & 3;         // TMEM lane quarter
-        const int h = (warp - 4) >> 2;  // which accumulator / row half
-        uint32_t  tc = 0;
-        for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++tc) {
-            const int mb = tile / nNB, nb = tile - mb * nNB;
-            mbar_wait(tfull, tc & 1u);
-            tc_fence_after();
-            const int row = mb * MT2_BM + h * 128 + q * 32 + lane;
-            typename Epi::State st;
-            if (row < M)
-                epi.begin(st, row);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; c += 2) {  // two TMEM loads in flight per wait
-                float          v0[32], v1[32];
-                const uint32_t ta = tmemBase + ((uint32_t)(q * 32) << 16) + h * BN + c * 32;
-                tmem_ld32_issue(ta, v0);
-                tmem_ld32_issue(ta + 32, v1);
-                tmem_ld_wait();
-                if (row < M) {
-                    epi.chunk(st, row, nb * BN + c * 32, v0);
-                    epi.chunk(st, row, nb * BN + c * 32 + 32, v1);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(tempty);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)TMEM_COLS)
-                     : "memory");
-    }
-}
-
 // ---------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -460,21 +326,6 @@ inline int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
         return RB_ERR_CUDA;
     }
-    return RB_OK;
-}
-
-// A map must have been built with boxRows = MT2_BM
-template<class Epi>
-int launch_mt2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int fmt, const Epi& epi,
-               int smCount, cudaStream_t s) {
-    RB_CUDA(cudaFuncSetAttribute(gemm16_mt2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT2_SMEM_BYTES));
-    RB_REQUIRE(K % BK == 0 && K > 0, "GEMM K=%d must be a positive multiple of %d", K, BK);
-    const int nTiles = ((M + MT2_BM - 1) / MT2_BM) * ((N + BN - 1) / BN);
-    int       grid   = std::min(nTiles, smCount);
-    if (const char* e = getenv("RB_GEMM_GRID"))  // experiments: fewer CTAs than SMs
-        grid = std::max(1, std::min(grid, atoi(e)));
-    gemm16_mt2_kernel<Epi><<<grid, MT2_THREADS, MT2_SMEM_BYTES, s>>>(tmA, tmB, M, N, K, instr_desc(fmt), epi);
-    RB_LAUNCH_CHECK();
     return RB_OK;
 }
 

@@ -273,11 +273,9 @@ struct rb_nn {
     std::vector<NnLayer*> layers;
     cudaStream_t         stream = nullptr;
     long                 chunk = 18944;  // frames per pass: 74 row blocks of 256 -> whole waves on 148 SMs
-    std::vector<CUtensorMap> mapIn128;  // the same inputs with 128-row boxes (double-buffered 128 x 256 kernel)
-    bool                 doubleBuffered = true;
-    // bf16 path: ping-pong activation buffers [chunk x maxKPad] and their TMA maps per layer input
+    // bf16 path: ping-pong activation buffers [chunk x maxKPad] and their TMA maps (128-row boxes) per layer input
+    std::vector<CUtensorMap>  mapIn128;
     rb::DevBuf<__nv_bfloat16> actA, actB;
-    std::vector<CUtensorMap>  mapIn;  // map of the input activation of layer l
     // f32 path
     rb::DevBuf<float> actFA, actFB;
     // host-pointer staging
@@ -320,12 +318,8 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
                 epi.ldo  = h->layers[l + 1]->kPad;
                 epi.N    = ly->out;
                 epi.act  = ly->act;
-                if (h->doubleBuffered)
-                    RB_CHECK(rbgemm::launch(h->mapIn128[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
-                                            h->dev.sm_count, s));
-                else
-                    RB_CHECK(rbgemm::launch_mt2(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16,
-                                                epi, h->dev.sm_count, s));
+                RB_CHECK(rbgemm::launch(h->mapIn128[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
+                                        h->dev.sm_count, s));
                 std::swap(cur, nxt);
             }
             else {
@@ -338,7 +332,7 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
                 epi.sign = scoreMode ? -1.0f : 1.0f;
                 // the 128 x 256 kernel double-buffers its accumulator in TMEM: the epilogue of tile i (here 48 KB of
                 // f32 scores per frame) overlaps the MMAs of tile i+1
-                const bool tmaStore = h->doubleBuffered && (ly->out % 4) == 0 && ((uintptr_t)dOut % 16) == 0 &&
+                const bool tmaStore = (ly->out % 4) == 0 && ((uintptr_t)dOut % 16) == 0 &&
                                       getenv("RB_NN_NO_TMA_STORE") == nullptr;
                 if (tmaStore) {  // wide f32 rows: whole-line stores by the TMA unit instead of row-strided STG
                     CUtensorMap mapOut;
@@ -346,12 +340,9 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
                     RB_CHECK(rbgemm::launch_tma_store(h->mapIn128[l], ly->mapW, mapOut, (int)T, ly->out, ly->kPad,
                                                       rbgemm::FMT_BF16, epi, h->dev.sm_count, s));
                 }
-                else if (h->doubleBuffered)
+                else
                     RB_CHECK(rbgemm::launch(h->mapIn128[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
                                             h->dev.sm_count, s));
-                else
-                    RB_CHECK(rbgemm::launch_mt2(h->mapIn[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16,
-                                                epi, h->dev.sm_count, s));
             }
         }
     }
@@ -470,7 +461,7 @@ extern "C" int rb_nn_create(int n_layers, const int* dims, const int* act, const
     }
     h->precision = precision;
     h->nLayers   = n_layers;
-    h->chunk     = (long)rbgemm::MT2_BM * std::max(1, h->dev.sm_count / 2);
+    h->chunk     = 256L * std::max(1, h->dev.sm_count / 2);  // 18944 frames on 148 SMs: whole waves of 128-row tiles
     int maxKPad = 0, maxDim = 0;
     for (int l = 0; l < n_layers; ++l) {
         NnLayer* ly = new NnLayer();
@@ -526,20 +517,14 @@ extern "C" int rb_nn_create(int n_layers, const int* dims, const int* act, const
         cudaMemset(h->actB.p, 0, (size_t)h->chunk * maxKPad * 2);
         // padding columns of the first layer's input are written by the converter; hidden activations
         // are written up to the next layer's kPad by the epilogue
-        h->mapIn.resize(n_layers);
         h->mapIn128.resize(n_layers);
         for (int l = 0; l < n_layers; ++l) {
             const __nv_bfloat16* buf = (l % 2 == 0) ? h->actA.p : h->actB.p;
-            rc = rbgemm::make_map(&h->mapIn[l], buf, (uint64_t)h->chunk, (uint64_t)h->layers[l]->kPad,
-                                  (uint64_t)h->layers[l]->kPad, rbgemm::MT2_BM, true);
-            if (rc == RB_OK)
-                rc = rbgemm::make_map(&h->mapIn128[l], buf, (uint64_t)h->chunk, (uint64_t)h->layers[l]->kPad,
-                                      (uint64_t)h->layers[l]->kPad, rbgemm::BM, true);
+            rc = rbgemm::make_map(&h->mapIn128[l], buf, (uint64_t)h->chunk, (uint64_t)h->layers[l]->kPad,
+                                  (uint64_t)h->layers[l]->kPad, rbgemm::BM, true);
             if (rc != RB_OK)
                 return fail(rc);
         }
-        if (const char* e = getenv("RB_NN_MT2"))  // experiments: the 256 x 256 single-buffered kernel
-            h->doubleBuffered = atoi(e) == 0;
     }
     else {
         if (h->actFA.reserve((size_t)h->chunk * maxDim) != RB_OK || h->actFB.reserve((size_t)h->chunk * maxDim) != RB_OK)
@@ -634,8 +619,7 @@ extern "C" int rb_test_gemm_bf16(const float* a, const float* b, const float* bi
         convert_pad_bf16_kernel<<<256, 256, 0, s>>>(dB32.p, dB.p, N, K, kPad);
         rb::count_launch(2);
         CUtensorMap mA, mB;
-        const bool  mt2 = M >= rbgemm::MT2_BM;  // both kernels are exercised by the parity tests
-        if ((rc = rbgemm::make_map(&mA, dA.p, M, kPad, kPad, mt2 ? rbgemm::MT2_BM : rbgemm::BM, true)) != RB_OK) break;
+        if ((rc = rbgemm::make_map(&mA, dA.p, M, kPad, kPad, rbgemm::BM, true)) != RB_OK) break;
         if ((rc = rbgemm::make_map(&mB, dB.p, N, kPad, kPad, rbgemm::BN, true)) != RB_OK) break;
         EpiFinalF32 epi;
         epi.bias = bias ? dBias.p : nullptr;
@@ -644,8 +628,7 @@ extern "C" int rb_test_gemm_bf16(const float* a, const float* b, const float* bi
         epi.N    = N;
         epi.act  = act;
         epi.sign = 1.0f;
-        rc = mt2 ? rbgemm::launch_mt2(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s)
-                 : rbgemm::launch(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s);
+        rc = rbgemm::launch(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s);
         if (rc != RB_OK) break;
         cudaError_t e = cudaMemcpyAsync(d, dD.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess)
@@ -676,8 +659,8 @@ extern "C" int rb_test_gemm_bench(int M, int N, int K, int variant, int iters, f
     RB_CUDA(cudaMemset(dB.p, 0x3c, (size_t)N * kPad * 2));
     RB_CUDA(cudaMemset(dBias.p, 0, (size_t)N * 4));
     CUtensorMap mA, mB;
-    const bool  mt2 = variant == 1;
-    RB_CHECK(rbgemm::make_map(&mA, dA.p, M, kPad, kPad, mt2 ? rbgemm::MT2_BM : rbgemm::BM, true));
+    RB_REQUIRE(variant == 0, "GEMM variant %d does not exist (0: 128 x 256 tile, double-buffered TMEM)", variant);
+    RB_CHECK(rbgemm::make_map(&mA, dA.p, M, kPad, kPad, rbgemm::BM, true));
     RB_CHECK(rbgemm::make_map(&mB, dB.p, N, kPad, kPad, rbgemm::BN, true));
     EpiHiddenBf16 epi;
     epi.bias = dBias.p;
@@ -694,8 +677,7 @@ extern "C" int rb_test_gemm_bench(int M, int N, int K, int variant, int iters, f
     for (int i = 0; i < iters + 2 && rc == RB_OK; ++i) {
         if (i == 2)
             cudaEventRecord(e0, s);
-        rc = mt2 ? rbgemm::launch_mt2(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s)
-                 : rbgemm::launch(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s);
+        rc = rbgemm::launch(mA, mB, M, N, kPad, rbgemm::FMT_BF16, epi, dev.sm_count, s);
     }
     cudaEventRecord(e1, s);
     cudaError_t e = cudaStreamSynchronize(s);
