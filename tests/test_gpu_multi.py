@@ -141,6 +141,29 @@ def _worker(rank, port, q):
         dist.barrier()
         ex2.close()
 
+        # 5c. the Nn scorer's TMA-store epilogue writing its shard straight into rank 1's window
+        from rasr_b200 import nn as rnn
+        net = synth.network(dims=(429, 256, 512), seed=1)
+        xs = synth.features(300 + 200, 429, seed=2, scale=1.0)
+        offs3 = np.array([0, 300, 500], np.int64)
+        ex3 = comm.ScoreExchange(WORLD, rank, rank, offs3, 512, comm.torch_exchange(dist))
+        sc3 = rnn.NnScorer(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 1.0, "bf16", device=rank)
+        whole = torch.empty((500, 512), dtype=torch.float32, device=dev)
+        sc3.score_dev(torch.from_numpy(xs).to(dev), 500, whole, sp)
+        ex3.window(torch).zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        part = torch.from_numpy(xs[offs3[rank]:offs3[rank + 1]]).to(dev)
+        sc3.score_dev(part, int(offs3[rank + 1] - offs3[rank]), ex3.target(1), sp)
+        ex3.barrier(sp)
+        stream.synchronize()
+        if rank == 1:
+            res["nn_fused_gather"] = bool(torch.equal(ex3.window(torch), whole))
+        else:
+            res["nn_fused_gather"] = bool((ex3.window(torch) == 0).all())
+        dist.barrier()
+        ex3.close()
+
         # 5b. row-range pushes (the slab-pipelined exchange): two halves of the shard, the second to rank 0 only
         win.zero_()
         torch.cuda.synchronize()
@@ -195,7 +218,7 @@ def test_score_exchange_two_ranks(oracle, diag):
         r = res[rank]
         assert "error" not in r, r.get("error")
         diag("score_exchange_rank%d" % rank, **r)
-        for key in ("allgather_p2p", "gather_root1", "allgather_nccl", "fused_scorer", "inplace_allgather", "fused_allgather", "fanout_by_copy",
+        for key in ("allgather_p2p", "gather_root1", "allgather_nccl", "fused_scorer", "inplace_allgather", "fused_allgather", "fanout_by_copy", "nn_fused_gather",
                     "push_rows", "rejects_overflow"):
             assert r[key] is True, (rank, key)
         assert r["nccl_version"] >= 20000
