@@ -20,6 +20,11 @@
 //     accumulators sums dims 8b+j / 8b+4+j, constant added first in lane 0, same horizontal
 //     add tree), so BATCH_FLOAT scores are bit-identical to the CPU path, contraction on or off.
 //   * the kernel is FP32-ALU bound (2 issue slots per (frame,density,dim)); see DESIGN.md.
+//
+// BATCH_FLOAT on batches of >= 2048 frames does not run that kernel: the reference's result for a mixture is a minimum,
+// so gmm_tensor.cu screens the densities that can win with a split-precision tcgen05 product and gmm_refine_kernel
+// (below) evaluates only those, in the reference's operation order -- same bits, a sixteenth of the FP32 work
+// (rb_gmm_score_fanout_dev stores the result into several GPUs' windows at once).
 #include <cfloat>
 #include <cmath>
 

@@ -15,6 +15,11 @@
 // keeps |x|^2 and the cross term small, so the cancellation in the expanded form costs < 1e-6
 // relative on realistic data.  Scores agree with the reference within 1e-4 relative (north_star
 // tolerance; measured ~1e-6), but are not bit-identical -- RB_GMM_BATCH_FLOAT is.
+//
+// The same product also serves RB_GMM_BATCH_FLOAT (the exact scorer) on large batches: with the EpiGmmScreen epilogue
+// the kernel does not emit the minimum but, per (frame, mixture), the set of densities within a proven error bound of
+// it; gmm_refine_kernel (gmm.cu) evaluates those in the reference's operation order (rb_gmm_tensor_screen below,
+// DESIGN.md 4.1b).
 #include <cfloat>
 #include <cmath>
 
