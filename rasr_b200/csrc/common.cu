@@ -4,6 +4,7 @@
 #include <condition_variable>
 #include <deque>
 #include <mutex>
+#include <pthread.h>
 #include <thread>
 
 namespace rb {
@@ -71,9 +72,24 @@ struct CopyPool {
         cv.notify_one();
     }
 };
-CopyPool& copy_pool() {
-    static CopyPool* p = new CopyPool();  // intentionally leaked
-    return *p;
+// One pool per process, intentionally leaked.  A forked child inherits the pointer but not the threads: the atfork
+// handler drops the pointer so that the child builds its own pool on first use.
+CopyPool*  g_pool = nullptr;
+std::mutex g_poolMutex;
+CopyPool&  copy_pool() {
+    std::lock_guard<std::mutex> lk(g_poolMutex);
+    if (!g_pool) {
+        static bool hooked = false;
+        if (!hooked) {
+            pthread_atfork(nullptr, nullptr, [] {
+                g_pool = nullptr;
+                new (&g_poolMutex) std::mutex();
+            });
+            hooked = true;
+        }
+        g_pool = new CopyPool();
+    }
+    return *g_pool;
 }
 }  // namespace
 

@@ -244,6 +244,8 @@ struct RefineParams {
     float*       scores;    // [T * nMix]
     float*       extra[15]; // further destinations that receive the same rows (peer windows, rb_gmm_score_fanout_dev)
     int          nExtra;
+    uint32_t*    best;      // DIAG_MAX: [T * nMix] index of the winning density within its mixture, or null
+    int          dim;       // DIAG_MAX: feature dimension (tail dims are summed sequentially)
     long         T;
     int          nMix, nGroups, nFrameBlocks;
 };
@@ -361,6 +363,168 @@ GmmRefineKernel refine_kernel_for(int nb, bool fuse) {
         case 6: return pick_refine<6>(fuse);
         case 7: return pick_refine<7>(fuse);
         case 8: return pick_refine<8>(fuse);
+    }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// DIAG_MAX, second half of the exact two-pass scorer: as gmm_refine_kernel, for Mm::GaussDiagonalMaximumFeatureScorer.
+// Refinement rows [ mu (4 NQ) | 1/sigma (4 NQ) | w | logNorm ] = 8 NQ + 2 floats (an odd number of 8-byte words).  The
+// arithmetic is gmm_diag_kernel's for one frame: packed f32x2 over the full quads in the reference's SSE lane order,
+// the horizontal add, the tail dimensions sequentially, then the f64 sum of the three f32 terms compared against the
+// f32 running best (calculateScoreAndDensity :130-137).  That comparison is order dependent (the best is narrowed to
+// f32 after every update), so the candidates are walked in ascending density order: a density outside the candidate
+// set can only hold the best before the first candidate is seen, and never after (its score exceeds every
+// candidate's by more than the narrowing error), so the final (score, density) pair is the reference's.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int refine_diag_pitch(int nq) {
+    return nq * 8 + 2;
+}
+
+template<int NQ, bool FUSE>
+__global__ void __launch_bounds__(kThreads, 2) gmm_refine_diag_kernel(const RefineParams p) {
+    constexpr int ROWF = refine_diag_pitch(NQ);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int g    = blockIdx.x % p.nGroups;
+    const int row0 = p.grp_row[g], row1 = p.grp_row[g + 1];
+    const int mix0 = p.grp_mix[g], mix1 = p.grp_mix[g + 1];
+    uint64_t*      bar    = reinterpret_cast<uint64_t*>(smem_raw);
+    int*           first  = reinterpret_cast<int*>(smem_raw + 16);
+    unsigned char* region = smem_raw + 16 + (((size_t)(mix1 - mix0) * sizeof(int) + 15) & ~(size_t)15);
+    const size_t   gBegin = (size_t)row0 * ROWF * 4, gEnd = (size_t)row1 * ROWF * 4;
+    const size_t   cBegin = gBegin & ~(size_t)15, cEnd = (gEnd + 15) & ~(size_t)15;
+    const float*   rows   = reinterpret_cast<const float*>(region + (gBegin - cBegin));
+    float*         stage  = reinterpret_cast<float*>(region + (((gEnd - cBegin) + 47) & ~(size_t)15));
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    for (int m = tid; m < mix1 - mix0; m += kThreads)
+        first[m] = (p.mix_row[mix0 + m] - row0) * ROWF;
+    __syncthreads();
+    if (tid == 0) {
+        const size_t total = cEnd - cBegin;
+        mbar_expect_tx(bar, (uint32_t)total);
+        for (size_t off = 0; off < total; off += 65536) {
+            const uint32_t bytes = (uint32_t)(total - off < 65536 ? total - off : 65536);
+            bulk_g2s(region + off, reinterpret_cast<const unsigned char*>(p.rows) + cBegin + off, bytes, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+
+    const int nFullQ = p.dim >> 2, nTail = p.dim & 3;
+    const int member   = blockIdx.x / p.nGroups;
+    const int nMembers = ((int)gridDim.x - g + p.nGroups - 1) / p.nGroups;
+    for (int fb = member; fb < p.nFrameBlocks; fb += nMembers) {
+        const long t  = (long)fb * kThreads + tid;
+        const long tc = t < p.T ? t : p.T - 1;
+        uint64_t   xp[NQ * 2];
+        float      xt[4];  // scalar copies of the last quad for the tail dimensions
+#pragma unroll
+        for (int i = 0; i < NQ * 2; ++i) {
+            const float a = __ldg(p.xT + (size_t)(2 * i) * p.pitch + tc), b = __ldg(p.xT + (size_t)(2 * i + 1) * p.pitch + tc);
+            xp[i] = pack2(a, b);
+            if (i >= NQ * 2 - 2) {
+                xt[2 * (i - (NQ * 2 - 2))]     = a;
+                xt[2 * (i - (NQ * 2 - 2)) + 1] = b;
+            }
+        }
+        const uint4* w  = reinterpret_cast<const uint4*>(p.words) + tc;
+        uint4        mk = t < p.T ? __ldg(w + (size_t)(mix0 >> 2) * p.pitch) : make_uint4(0u, 0u, 0u, 0u);
+        const long   warpFrame0 = (long)fb * kThreads + (tid & ~31);
+        int          staged = 0;
+        for (int m4 = mix0; m4 < mix1; m4 += 4) {
+            const uint32_t sets[4] = {mk.x, mk.y, mk.z, mk.w};
+            if (m4 + 4 < mix1 && t < p.T)
+                mk = __ldg(w + (size_t)((m4 + 4) >> 2) * p.pitch);
+            float    o[4];
+            uint32_t ob[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float* base = rows + first[m4 - mix0 + q];
+                uint32_t     set  = sets[q];
+                float        best = FLT_MAX;
+                uint32_t     bd   = 0xffffffffu;
+                while (set) {
+                    const int j = __ffs((int)set) - 1;
+                    set &= set - 1;
+                    const uint64_t* r    = reinterpret_cast<const uint64_t*>(base + j * ROWF);
+                    uint64_t        s[2] = {0ull, 0ull};
+#pragma unroll
+                    for (int qd = 0; qd < NQ; ++qd) {
+                        if (qd < nFullQ) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint64_t e = mul2(sub2(r[2 * qd + h], xp[2 * qd + h]), r[2 * NQ + 2 * qd + h]);
+                                s[h]             = FUSE ? fma2(e, e, s[h]) : sqadd2(e, s[h]);
+                            }
+                        }
+                    }
+                    float d = __fadd_rn(0.0f, __fadd_rn(__fadd_rn(lo2(s[0]), hi2(s[0])), __fadd_rn(lo2(s[1]), hi2(s[1]))));
+                    if (nTail) {
+                        const uint64_t ma = r[2 * NQ - 2], mb = r[2 * NQ - 1], va = r[4 * NQ - 2], vb = r[4 * NQ - 1];
+                        const float    mt[4] = {lo2(ma), hi2(ma), lo2(mb), hi2(mb)};
+                        const float    vt[4] = {lo2(va), hi2(va), lo2(vb), hi2(vb)};
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (k < nTail) {
+                                const float e = __fmul_rn(__fsub_rn(mt[k], xt[k]), vt[k]);
+                                d             = sq_acc(e, d, FUSE);
+                            }
+                    }
+                    const uint64_t tail = r[4 * NQ];  // (w, logNorm)
+                    const double   sc   = ((double)lo2(tail) + (double)hi2(tail)) + (double)d;
+                    if ((double)best > sc) {
+                        best = (float)sc;
+                        bd   = (uint32_t)j;
+                    }
+                }
+                o[q]  = __fmul_rn(0.5f, best);
+                ob[q] = bd;
+            }
+            if (p.best && t < p.T)
+                *reinterpret_cast<uint4*>(p.best + (size_t)t * p.nMix + m4) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+            float* mine = stage + (tid >> 5) * (32 * kStagePitch);
+            *reinterpret_cast<float4*>(mine + (tid & 31) * kStagePitch + staged * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            ++staged;
+            if (staged == kStageQuads || m4 + 4 >= mix1) {
+                __syncwarp();
+                const int mFirst = m4 + 4 - staged * 4;
+                for (int k = tid & 31; k < 32 * staged; k += 32) {
+                    const int  r = k / staged, c = k - r * staged;
+                    const long tf = warpFrame0 + r;
+                    if (tf < p.T) {
+                        const float4 val = *reinterpret_cast<const float4*>(mine + r * kStagePitch + c * 4);
+                        const size_t at  = (size_t)tf * p.nMix + mFirst + c * 4;
+                        *reinterpret_cast<float4*>(p.scores + at) = val;
+                        for (int e = 0; e < p.nExtra; ++e)
+                            *reinterpret_cast<float4*>(p.extra[e] + at) = val;
+                    }
+                }
+                __syncwarp();
+                staged = 0;
+            }
+        }
+    }
+}
+
+template<int N>
+GmmRefineKernel pick_refine_diag(bool fuse) {
+    return fuse ? gmm_refine_diag_kernel<N, true> : gmm_refine_diag_kernel<N, false>;
+}
+GmmRefineKernel refine_diag_kernel_for(int nq, bool fuse) {
+    switch (nq) {
+        case 1: return pick_refine_diag<1>(fuse);
+        case 2: return pick_refine_diag<2>(fuse);
+        case 3: return pick_refine_diag<3>(fuse);
+        case 4: return pick_refine_diag<4>(fuse);
+        case 5: return pick_refine_diag<5>(fuse);
+        case 6: return pick_refine_diag<6>(fuse);
+        case 7: return pick_refine_diag<7>(fuse);
+        case 8: return pick_refine_diag<8>(fuse);
+        case 9: return pick_refine_diag<9>(fuse);
+        case 10: return pick_refine_diag<10>(fuse);
     }
     return nullptr;
 }
@@ -655,6 +819,8 @@ void rb_gmm_tensor_destroy(rb_gmm_tensor* t);
 int  rb_gmm_tensor_score(rb_gmm_tensor* t, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
 bool rb_gmm_tensor_screenable(const rb_gmm_tensor* t);
 int  rb_gmm_tensor_reserve(rb_gmm_tensor* t, long frames, bool screen);
+int  rb_gmm_tensor_create_diag(const rb_mixture_set* ms, const float* rows, int rowf, int nq, const rb::DeviceInfo& dev,
+                               cudaStream_t stream, rb_gmm_tensor** out);
 long rb_gmm_tensor_chunk(const rb_gmm_tensor* t);
 int  rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* d_feats, long n, const uint32_t** words, const float** xT,
                           long* pitch, cudaStream_t stream, cudaEvent_t after_split);
@@ -966,7 +1132,7 @@ int launch_simt(rb_gmm* h, const float* dFeats, long T, float* dScores, uint32_t
 // mixture, at most 256 densities per mixture), at most 32 densities per mixture (one bit each), a mixture count that is
 // a multiple of 4 (16-byte words), finite parameters, and a mixture grouping whose rows fit shared memory.  When it does
 // not apply the direct kernel serves every call (same scores, only slower).  RB_GMM_EXACT=0 switches the route off.
-int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsHost) {
+int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsHost, bool diag) {
     const char* env = getenv("RB_GMM_EXACT");
     if (env && atoi(env) == 0)
         return RB_OK;
@@ -979,17 +1145,20 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
         if (n == 0 || n > 32)
             return RB_OK;
     }
-    h->refine = refine_kernel_for(h->nUnits, h->fuse);
+    h->refine = diag ? refine_diag_kernel_for(h->nUnits, h->fuse) : refine_kernel_for(h->nUnits, h->fuse);
     if (!h->refine)
         return RB_OK;
     rb_gmm_tensor* t = nullptr;
-    if (rb_gmm_tensor_create(ms, h->dev, h->stream, &t) != RB_OK || !rb_gmm_tensor_screenable(t)) {
+    const int      made = diag ? rb_gmm_tensor_create_diag(ms, rowsHost, h->rowf, h->nUnits, h->dev, h->stream, &t)
+                               : rb_gmm_tensor_create(ms, h->dev, h->stream, &t);
+    if (made != RB_OK || !rb_gmm_tensor_screenable(t)) {
         if (t)
             rb_gmm_tensor_destroy(t);
         return RB_OK;  // e.g. non-finite parameters: the direct kernel reproduces the reference on those too
     }
     // fewest groups whose rows fit 48 KB (3-4 CTAs per SM); else up to 200 KB at lower occupancy
-    const int        pitch = refine_pitch(h->nUnits);
+    const int        pitch = diag ? refine_diag_pitch(h->nUnits) : refine_pitch(h->nUnits);
+    const int        used  = diag ? h->nUnits * 8 + 2 : h->nUnits * 8 + 1;  // leading floats of a direct-kernel row
     std::vector<int> mixRow(h->nMix + 1, 0);
     for (int m = 0; m < h->nMix; ++m)
         mixRow[m + 1] = mixRow[m] + h->rowsOfMixture[m];
@@ -1024,7 +1193,7 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
     std::vector<float> rrows((size_t)(h->nRows + 1) * pitch, 0.0f);
     for (int r = 0; r < h->nRows; ++r) {
         const float* src = rowsHost + (size_t)r * h->rowf;
-        std::copy(src, src + h->nUnits * 8 + 1, rrows.begin() + (size_t)r * pitch);
+        std::copy(src, src + used, rrows.begin() + (size_t)r * pitch);
     }
     if (h->dRefRows.upload(rrows, h->stream) != RB_OK || h->dMixRow.upload(mixRow, h->stream) != RB_OK ||
         cudaStreamSynchronize(h->stream) != cudaSuccess) {
@@ -1039,7 +1208,7 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
 }
 
 int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores, float* const* extra, int nExtra,
-                          cudaStream_t s) {
+                          uint32_t* dBest, cudaStream_t s) {
     const long chunk = rb_gmm_tensor_chunk(h->tensor);
     for (long a = 0; a < T; a += chunk) {
         const long   n = std::min(chunk, T - a);
@@ -1055,6 +1224,8 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
         p.nExtra       = nExtra;
         for (int e = 0; e < nExtra; ++e)
             p.extra[e] = extra[e] + (size_t)a * h->nMix;
+        p.best         = dBest ? dBest + (size_t)a * h->nMix : nullptr;
+        p.dim          = h->dim;
         const int G    = h->refGroups;
         p.rows         = h->dRefRows.p;
         p.grp_row      = h->dGrpRow.p + (size_t)G * kGroupStride;
@@ -1219,8 +1390,13 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         if (rc != RB_OK)
             return fail(rc);
     }
+    if (mode == RB_GMM_DIAG_MAX) {
+        rc = setup_exact_two_pass(h, ms, rows.data(), true);
+        if (rc != RB_OK)
+            return fail(rc);
+    }
     if (mode == RB_GMM_BATCH_FLOAT) {
-        rc = setup_exact_two_pass(h, ms, rows.data());
+        rc = setup_exact_two_pass(h, ms, rows.data(), false);
         if (rc != RB_OK)
             return fail(rc);
     }
@@ -1248,12 +1424,13 @@ namespace {
 // route stores them from the refinement kernel itself, every other route copies the finished matrix
 int score_dev_impl(rb_gmm* h, const float* d_feats, long T, float* d_scores, float* const* extra, int nExtra,
                    uint32_t* d_best, cudaStream_t s) {
-    if (h->mode == RB_GMM_BATCH_FLOAT && h->refGroups > 0 && T >= h->exactMinFrames && ((uintptr_t)d_scores % 16) == 0) {
+    if ((h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_DIAG_MAX) && h->refGroups > 0 && T >= h->exactMinFrames &&
+        ((uintptr_t)d_scores % 16) == 0 && ((uintptr_t)d_best % 16) == 0) {
         bool aligned = true;
         for (int e = 0; e < nExtra; ++e)
             aligned = aligned && ((uintptr_t)extra[e] % 16) == 0;
         if (aligned)
-            return launch_exact_two_pass(h, d_feats, T, d_scores, extra, nExtra, s);
+            return launch_exact_two_pass(h, d_feats, T, d_scores, extra, nExtra, d_best, s);
     }
     int rc;
     if (h->mode == RB_GMM_BATCH_TENSOR)
@@ -1349,7 +1526,7 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
         long largest = 0;
         for (int i = 0; i < nSlabs; ++i)
             largest = std::max(largest, cut[i + 1] - cut[i]);
-        RB_CHECK(rb_gmm_tensor_reserve(h->tensor, largest, h->mode == RB_GMM_BATCH_FLOAT));
+        RB_CHECK(rb_gmm_tensor_reserve(h->tensor, largest, h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_DIAG_MAX));
     }
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const long  a = cut[i], n = cut[i + 1] - cut[i];

@@ -310,6 +310,77 @@ __global__ void __launch_bounds__(256) gmm_split_features_kernel(const float* __
     }
 }
 
+// ---- diagonal scorers (per-density covariance): features -> split fp16 A operand + threshold -------------------------
+//   dist_k(x) = sum_d v_kd^2 (x_d - mu_kd)^2 = sum_d  xc_d^2 v_kd^2  -  2 xc_d (v_kd^2 mu_c,kd)  +  v_kd^2 mu_c,kd^2
+// (xc, mu_c centred on the mean of all means).  A row = [ X2h | X2h | X2l | X1h | X1h | X1l | 1 1 1 0.. ] with X2 = xc^2,
+// X1 = xc; B row = [ V2h | V2l | V2h | Mh | Ml | Mh | c1 c2 c3 ] with V2 = v^2, M = -2 v^2 mu_c (built on the host).
+// vmax2[d] = the largest v_kd^2 of any density: qx = sum_d vmax2_d xc_d^2 bounds the feature's share of every density's
+// distance and sets the frame's screening threshold.  xT receives the RAW feature (the reference subtracts it from the
+// unscaled mean, src/Mm/GaussDiagonalMaximumFeatureScorer.cc:144-233).
+__global__ void __launch_bounds__(256) gmm_split_features_diag_kernel(const float* __restrict__ feats,
+                                                                      const float* __restrict__ centre,
+                                                                      const float* __restrict__ vmax2, long T, int dim,
+                                                                      int dp, int kPad, __half* __restrict__ A,
+                                                                      float* __restrict__ thr, float thrA, float thrB,
+                                                                      float* __restrict__ xT, long pitch) {
+    const int  sub = threadIdx.x & 7;
+    const long g0  = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 3;
+    const long nG  = ((long)gridDim.x * blockDim.x) >> 3;
+    const int  nChunk = dp >> 3;
+    for (long t0 = g0; t0 < ((T + 3) & ~3L); t0 += nG) {
+        const long t   = t0 < T ? t0 : T - 1;
+        float      qx  = 0.0f;
+        uint32_t   h2[4] = {0, 0, 0, 0}, l2[4] = {0, 0, 0, 0}, h1[4] = {0, 0, 0, 0}, l1[4] = {0, 0, 0, 0};
+        int        bad = 0;
+        if (sub < nChunk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d = sub * 8 + j;
+                float     xr = 0.0f, x = 0.0f, w = 0.0f;
+                if (d < dim) {
+                    xr = __ldg(feats + (size_t)t * dim + d);
+                    x  = __fsub_rn(xr, __ldg(centre + d));
+                    w  = __ldg(vmax2 + d);
+                }
+                if (xT && t0 < T)
+                    xT[(size_t)d * pitch + t] = xr;
+                const float x2 = __fmul_rn(x, x);
+                qx             = __fmaf_rn(x2, w, qx);
+                bad |= !(x2 <= 57600.0f);
+                const float  c2 = fminf(x2, 60000.0f), c1 = fminf(fmaxf(x, -60000.0f), 60000.0f);
+                const __half a  = __float2half_rn(c2), b = __float2half_rn(c2 - __half2float(a));
+                const __half c  = __float2half_rn(c1), e = __float2half_rn(c1 - __half2float(c));
+                h2[j >> 1] |= (uint32_t)__half_as_ushort(a) << ((j & 1) * 16);
+                l2[j >> 1] |= (uint32_t)__half_as_ushort(b) << ((j & 1) * 16);
+                h1[j >> 1] |= (uint32_t)__half_as_ushort(c) << ((j & 1) * 16);
+                l1[j >> 1] |= (uint32_t)__half_as_ushort(e) << ((j & 1) * 16);
+            }
+        }
+        qx += __shfl_xor_sync(0xffffffffu, qx, 1);
+        qx += __shfl_xor_sync(0xffffffffu, qx, 2);
+        qx += __shfl_xor_sync(0xffffffffu, qx, 4);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 1);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 2);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 4);
+        if (t0 < T) {
+            uint4* row = reinterpret_cast<uint4*>(A + (size_t)t * kPad);
+            if (sub < nChunk) {
+                const uint4 a2 = make_uint4(h2[0], h2[1], h2[2], h2[3]), a1 = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+                row[sub]              = a2;
+                row[nChunk + sub]     = a2;
+                row[2 * nChunk + sub] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+                row[3 * nChunk + sub] = a1;
+                row[4 * nChunk + sub] = a1;
+                row[5 * nChunk + sub] = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+            }
+            for (int c = 6 * nChunk + sub; c < (kPad >> 3); c += 8)
+                row[c] = c == 6 * nChunk ? make_uint4(0x3C003C00u, 0x00003C00u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+            if (sub == 0)
+                thr[t] = (bad || !(qx < FLT_MAX)) ? __int_as_float(0x7f800000) : __fmaf_rn(qx, thrA, thrB);
+        }
+    }
+}
+
 // ---- B-stationary tcgen05 kernel ------------------------------------------------------------------
 // The model slice of NBRES column blocks (256 densities x K each) is loaded into shared memory ONCE per
 // CTA; only the 128-frame A tiles stream through a TMA ring.  Streaming both operands per tile (the
@@ -521,6 +592,8 @@ struct rb_gmm_tensor {
     rb::DevBuf<__half>   dB, dA;
     rb::DevBuf<float>    dIsd, dCentre, dXnorm, dThr, dXT;
     rb::DevBuf<uint32_t> dWords;  // candidate sets of the screening pass, [nMix / 4][cap][4]
+    bool                 diag = false;   // operands of the diagonal scorers (rb_gmm_tensor_create_diag)
+    rb::DevBuf<float>    dVmax2;
     rb::DevBuf<uint32_t> dEndMask;
     rb::DevBuf<int>      dMixStart;
     CUtensorMap          mapA, mapB;
@@ -804,6 +877,162 @@ int rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cu
     return RB_OK;
 }
 
+// Operands of the screening pass for the DIAGONAL scorers (per-density covariance, Mm::GaussDiagonalMaximumFeatureScorer).
+// `rows` are the rows gmm.cu built for its direct kernel, one per mixture entry in mixture order:
+// [ mu (4 nq) | isd (4 nq) | w | logNorm | flags | 0 ], score = w + logNorm + sum_d ((mu_d - x_d) isd_d)^2.
+int rb_gmm_tensor_create_diag(const rb_mixture_set* ms, const float* rows, int rowf, int nq, const rb::DeviceInfo& dev,
+                              cudaStream_t stream, rb_gmm_tensor** out) {
+    *out = nullptr;
+    const unsigned D  = ms->dim;
+    const int      dp = (int)rb::round_up(D, 8);
+    const int      kPad = (int)rb::round_up((size_t)6 * dp + 3, 64);
+    if (kPad > 4 * rbgemm::BK) {
+        rb::set_error("diagonal screening supports at most 40 dimensions (got %u)", D);
+        return RB_ERR_UNSUPPORTED;
+    }
+    const uint32_t n0 = ms->mix_offsets[1] - ms->mix_offsets[0];
+    bool           uniform = true;
+    for (uint32_t m = 0; m < ms->n_mixtures; ++m) {
+        const uint32_t n = ms->mix_offsets[m + 1] - ms->mix_offsets[m];
+        if (n == 0 || n > 32) {
+            rb::set_error("diagonal screening needs 1..32 densities per mixture (mixture %u has %u)", m, n);
+            return RB_ERR_UNSUPPORTED;
+        }
+        uniform = uniform && n == n0;
+    }
+    rb_gmm_tensor* t = new (std::nothrow) rb_gmm_tensor();
+    if (!t) {
+        rb::set_error("out of host memory");
+        return RB_ERR_NOMEM;
+    }
+    auto fail = [&](int code) {
+        delete t;
+        return code;
+    };
+    t->dev  = dev;
+    t->dim  = (int)D;
+    t->dp   = dp;
+    t->kPad = kPad;
+    t->nMix = (int)ms->n_mixtures;
+    t->seg  = (uniform && (n0 == 8 || n0 == 16 || n0 == 32)) ? (int)n0 : 0;
+    t->diag = true;
+    std::vector<uint32_t> colEntry, colEnd;
+    for (uint32_t m = 0; m < ms->n_mixtures; ++m) {
+        const uint32_t e0 = ms->mix_offsets[m], n = ms->mix_offsets[m + 1] - e0;
+        if (colEntry.size() % rbgemm::BN + n > (size_t)rbgemm::BN)
+            while (colEntry.size() % rbgemm::BN) {
+                colEntry.push_back(0xffffffffu);
+                colEnd.push_back(0);
+            }
+        for (uint32_t i = 0; i < n; ++i) {
+            colEntry.push_back(e0 + i);
+            colEnd.push_back(i + 1 == n);
+        }
+    }
+    while (colEntry.size() % rbgemm::BN) {
+        colEntry.push_back(0xffffffffu);
+        colEnd.push_back(0);
+    }
+    t->nCols = (int)colEntry.size();
+    const uint32_t nEntries = ms->mix_offsets[ms->n_mixtures];
+    // centre = mean of all means (f32, the value the feature kernel subtracts)
+    std::vector<double> centre64(D, 0.0);
+    for (uint32_t e = 0; e < nEntries; ++e)
+        for (unsigned d = 0; d < D; ++d)
+            centre64[d] += rows[(size_t)e * rowf + d];
+    std::vector<float> centre(dp, 0.0f), vmax2(dp, 0.0f);
+    for (unsigned d = 0; d < D; ++d)
+        centre[d] = (float)(centre64[d] / std::max<uint32_t>(nEntries, 1));
+    // per entry: V2 = v^2, M = -2 v^2 mu_c, constant = w + logNorm + sum v^2 mu_c^2 (f64)
+    std::vector<double> v2((size_t)nEntries * D), mm((size_t)nEntries * D), cc(nEntries);
+    double              maxAbs = 0, maxC = 0, qmu = 0;
+    bool                finite = true;
+    for (uint32_t e = 0; e < nEntries; ++e) {
+        const float* row = rows + (size_t)e * rowf;
+        double       acc = 0;
+        for (unsigned d = 0; d < D; ++d) {
+            const double v   = (double)row[4 * nq + d];
+            const float  muc = row[d] - centre[d];  // f32, like the feature's centring
+            const double a = v * v, b = a * (double)muc;
+            v2[(size_t)e * D + d] = a;
+            mm[(size_t)e * D + d] = -2.0 * b;
+            acc += b * (double)muc;
+            maxAbs   = std::max(maxAbs, std::max(a, std::fabs(2.0 * b)));
+            vmax2[d] = std::max(vmax2[d], (float)(a * (1.0 + 1e-6)));
+            finite   = finite && std::isfinite(a) && std::isfinite(b);
+        }
+        cc[e]  = (double)row[8 * nq] + (double)row[8 * nq + 1] + acc;
+        finite = finite && std::isfinite(cc[e]);
+        maxC   = std::max(maxC, std::fabs(cc[e]));
+        qmu    = std::max(qmu, acc + std::fabs(cc[e]));
+    }
+    float scale = 1.0f;
+    while ((maxAbs * scale > 16384.0 || maxC * scale > 32768.0) && scale > 1e-12f)
+        scale *= 0.5f;
+    while (maxAbs * scale < 64.0 && maxC * scale < 128.0 && scale < 1e12f && maxAbs > 0)  // keep the low halves normal
+        scale *= 2.0f;
+    t->scale = scale;
+    std::vector<__half> B((size_t)t->nCols * kPad, __float2half_rn(0.0f));
+    double              resid = 0;
+    for (int col = 0; col < t->nCols; ++col) {
+        const uint32_t e = colEntry[col];
+        if (e == 0xffffffffu)
+            continue;
+        __half* row = B.data() + (size_t)col * kPad;
+        for (unsigned d = 0; d < D; ++d) {
+            const float  a = (float)(v2[(size_t)e * D + d] * scale), b = (float)(mm[(size_t)e * D + d] * scale);
+            const __half ah = __float2half_rn(a), al = __float2half_rn(a - __half2float(ah));
+            const __half bh = __float2half_rn(b), bl = __float2half_rn(b - __half2float(bh));
+            row[d]          = ah;
+            row[dp + d]     = al;
+            row[2 * dp + d] = ah;
+            row[3 * dp + d] = bh;
+            row[4 * dp + d] = bl;
+            row[5 * dp + d] = bh;
+        }
+        double r = cc[e] * (double)scale, got = 0;
+        for (int j = 0; j < 3; ++j) {
+            const __half h  = __float2half_rn((float)r);
+            row[6 * dp + j] = h;
+            r -= (double)__half2float(h);
+            got += (double)__half2float(h);
+        }
+        resid = std::max(resid, std::fabs(got / (double)scale - cc[e]));
+    }
+    const int             nChunks = t->nCols / 32;
+    std::vector<uint32_t> endMask(nChunks, 0);
+    std::vector<int>      mixStart(nChunks, 0);
+    int                   mix = 0;
+    for (int c = 0; c < nChunks; ++c) {
+        mixStart[c] = mix;
+        for (int j = 0; j < 32; ++j)
+            if (colEnd[c * 32 + j]) {
+                endMask[c] |= 1u << j;
+                ++mix;
+            }
+    }
+    // Threshold: the bound of the batch scorer with the two product groups of the expansion, sixteen
+    // K steps and the reference's longer rounding chain (difference, scaling by 1/sigma, up to 10 accumulations per
+    // lane, the f64 sum narrowed to f32): twice the sum of all terms stays below 2^-16 Q, kappa = 2^-15.
+    const double kappa = std::ldexp(1.0, -15) + std::ldexp(1.0, -20) * std::sqrt((double)dp) / (double)scale;
+    t->thrA       = (float)((double)scale * kappa);
+    t->thrB       = (float)((double)scale * (kappa * (qmu + 2.0) + 2.0 * resid) * 1.0001);
+    t->screenable = finite && std::isfinite(t->thrA) && std::isfinite(t->thrB) && t->thrA > 0;
+    if (t->dB.upload(B.data(), B.size(), stream) != RB_OK || t->dCentre.upload(centre, stream) != RB_OK ||
+        t->dVmax2.upload(vmax2, stream) != RB_OK || t->dEndMask.upload(endMask, stream) != RB_OK ||
+        t->dMixStart.upload(mixStart, stream) != RB_OK)
+        return fail(RB_ERR_CUDA);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) {
+        rb::set_error("tensor GMM model upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(RB_ERR_CUDA);
+    }
+    const int rc = rbgemm::make_map(&t->mapB, t->dB.p, (uint64_t)t->nCols, (uint64_t)kPad, (uint64_t)kPad, rbgemm::BN, false);
+    if (rc != RB_OK)
+        return fail(rc);
+    *out = t;
+    return RB_OK;
+}
+
 void rb_gmm_tensor_destroy(rb_gmm_tensor* t) {
     delete t;
 }
@@ -829,8 +1058,13 @@ int rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* dFeats, long n, const ui
     RB_REQUIRE(n >= 1 && n <= t->chunk, "bad frame count for one screening pass");
     RB_CHECK(ensure_capacity(t, n, true));
     const int blocks = (int)std::min<long>((n + 31) / 32, (long)t->dev.sm_count * 16);
-    gmm_split_features_kernel<<<blocks, 256, 0, s>>>(dFeats, t->dIsd.p, t->dCentre.p, n, t->dim, t->dp, t->kPad, t->scale,
-                                                     t->dA.p, t->dXnorm.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p, t->cap);
+    if (t->diag)
+        gmm_split_features_diag_kernel<<<blocks, 256, 0, s>>>(dFeats, t->dCentre.p, t->dVmax2.p, n, t->dim, t->dp, t->kPad,
+                                                              t->dA.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p, t->cap);
+    else
+        gmm_split_features_kernel<<<blocks, 256, 0, s>>>(dFeats, t->dIsd.p, t->dCentre.p, n, t->dim, t->dp, t->kPad, t->scale,
+                                                         t->dA.p, t->dXnorm.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p,
+                                                         t->cap);
     RB_LAUNCH_CHECK();
     if (afterSplit)
         cudaEventRecord(afterSplit, s);

@@ -178,3 +178,84 @@ def test_full_c2_batch_equals_direct_kernel(diag):
     n_diff = int((bits(one) != bits(two)).sum())
     diag("gmm_exact_full_c2", n_diff=n_diff, total=one.size)
     assert n_diff == 0
+
+
+# ---- RB_GMM_DIAG_MAX (Mm::GaussDiagonalMaximumFeatureScorer, per-density covariance, best density reported) through the
+# ---- same screening + refinement route: scores AND density indices must be the direct kernel's and the oracle's
+def diag_scorer(msd, route, contraction=True):
+    return scorer(msd, route, contraction, mode="diagonal-maximum")
+
+
+@pytest.mark.parametrize("contraction", [True, False])
+@pytest.mark.parametrize("n_cov", [1, 3])
+def test_diag_max_c2_shape(oracle, diag, contraction, n_cov):
+    msd = synth.mixture_set(n_covariances=n_cov)
+    f = synth.features(5000, 39, seed=17)
+    want, want_b = oracle.gmm_diag_max(oracle.MixtureSet(**msd), f, use_fma=contraction)
+    two, two_b = diag_scorer(msd, "two-pass", contraction).score(f, want_density=True)
+    one, one_b = diag_scorer(msd, "direct", contraction).score(f, want_density=True)
+    diag("gmm_exact_diag_c2", contraction=contraction, n_cov=n_cov, n_diff=int((bits(two) != bits(want)).sum()),
+         n_diff_idx=int((two_b != want_b).sum()), total=two.size)
+    assert np.array_equal(bits(one), bits(want)) and np.array_equal(one_b, want_b)
+    assert np.array_equal(bits(two), bits(want)) and np.array_equal(two_b, want_b)
+    # without the index output
+    assert np.array_equal(bits(diag_scorer(msd, "two-pass", contraction).score(f)), bits(want))
+
+
+@pytest.mark.parametrize("dim", [2, 7, 8, 13, 24, 33, 40])
+def test_diag_max_dimensions_and_scales(oracle, dim):
+    """tail dimensions (dim % 4 != 0) are summed sequentially in the reference; mixture-weight and Gaussian scales"""
+    msd = synth.mixture_set(dim=dim, n_mixtures=12, densities_per_mixture=16, seed=dim, n_covariances=2)
+    f = synth.features(2500, dim, seed=dim)
+    want, want_b = oracle.gmm_diag_max(oracle.MixtureSet(**msd), f, mixture_weight_scale=0.7, gaussian_scale=1.3)
+    old = os.environ.get("RB_GMM_EXACT")
+    os.environ["RB_GMM_EXACT"] = "2"
+    try:
+        sc = mm.GmmScorer(mm.MixtureSet.from_dict(msd), "diagonal-maximum", mixture_weight_scale=0.7, gaussian_scale=1.3)
+    finally:
+        if old is None:
+            del os.environ["RB_GMM_EXACT"]
+        else:
+            os.environ["RB_GMM_EXACT"] = old
+    got, got_b = sc.score(f, want_density=True)
+    assert np.array_equal(bits(got), bits(want)) and np.array_equal(got_b, want_b)
+
+
+def test_diag_max_ragged_ties_and_non_finite(oracle):
+    rng = np.random.default_rng(11)
+    sizes = [int(s) for s in rng.integers(1, 33, 24)]
+    msd = ragged_set(39, sizes, 4)
+    msd["variances"] = rng.uniform(0.3, 3.0, (4, 39)).astype(np.float32)
+    msd["dens_cov"] = rng.integers(0, 4, len(msd["dens_cov"])).astype(np.uint32)
+    means = msd["means"].reshape(-1, 39)
+    # duplicate densities inside the first mixtures: exact ties decided by the reference's order of comparison
+    offs = msd["mix_offsets"]
+    for m in range(len(sizes)):
+        if sizes[m] >= 3:
+            d0, d1, d2 = (int(msd["mix_density"][offs[m] + i]) for i in range(3))
+            means[msd["dens_mean"][d1]] = means[msd["dens_mean"][d0]]
+            msd["dens_cov"][d1] = msd["dens_cov"][d0]
+            msd["mix_log_weight"][offs[m] + 1] = msd["mix_log_weight"][offs[m]]
+            means[msd["dens_mean"][d2]] = means[msd["dens_mean"][d0]] + np.float32(1e-6)
+    f = synth.features(3000, 39, seed=9)
+    f[3, 2] = np.nan
+    f[4, :] = np.inf
+    f[5, 7] = 1.0e5
+    f[6, :] = 300.0
+    one, one_b = diag_scorer(msd, "direct").score(f, want_density=True)
+    two, two_b = diag_scorer(msd, "two-pass").score(f, want_density=True)
+    assert np.array_equal(bits(one), bits(two)) and np.array_equal(one_b, two_b)
+    ok = np.ones(3000, bool)
+    ok[3:7] = False
+    want, want_b = oracle.gmm_diag_max(oracle.MixtureSet(**msd), f[ok])
+    assert np.array_equal(bits(two[ok]), bits(want)) and np.array_equal(two_b[ok], want_b)
+
+
+def test_diag_max_full_size_equals_direct_kernel(diag):
+    msd = synth.mixture_set(n_covariances=2)
+    f = synth.features(100000, 39, seed=5)
+    one, one_b = diag_scorer(msd, "direct").score(f, want_density=True)
+    two, two_b = mm.GmmScorer(mm.MixtureSet.from_dict(msd), "diagonal-maximum").score(f, want_density=True)
+    n_diff, n_idx = int((bits(one) != bits(two)).sum()), int((one_b != two_b).sum())
+    diag("gmm_exact_diag_full", n_diff=n_diff, n_diff_idx=n_idx, total=one.size)
+    assert n_diff == 0 and n_idx == 0
