@@ -660,6 +660,7 @@ class Bench:
     #   batch-tensor        RB_GMM_BATCH_TENSOR, 1e-4 relative instead of bit-identical
     #   batch-float-direct  the single direct-form kernel (RB_GMM_EXACT=0), what batches below 2048 frames and models
     #                       the screening does not cover run on; FP32-issue bound
+    #   diagonal-maximum    RASR's default scorer (per-density covariance, best density), exact, same route
     def gmm_variants(self, w, steps, warmup):
         torch, stream = self.torch, self.stream
         from rasr_b200 import mm
@@ -667,7 +668,7 @@ class Bench:
         scorer, d_in, d_out, msd = w["keep"]
         T, R = w["units"], self.R
         out = {}
-        for name in ("batch-tensor", "batch-float-direct"):
+        for name in ("batch-tensor", "batch-float-direct", "diagonal-maximum"):
             if name == "batch-float-direct":
                 os.environ["RB_GMM_EXACT"] = "0"
             try:
@@ -690,6 +691,10 @@ class Bench:
             if name == "batch-tensor":
                 d.update(dtype="f16x3 split operands, f32 accumulate",
                          parity="<= 1e-4 relative to the reference scores (tests/test_gpu_gmm_tensor.py)")
+            elif name == "diagonal-maximum":
+                d.update(dtype="f32", parity="scores and best-density indices bit-identical (tests/test_gpu_gmm_exact.py)",
+                         note="Mm::GaussDiagonalMaximumFeatureScorer (per-density covariance) on the same model, through "
+                              "the screening + refinement route")
             else:
                 # FP32 peak: measured with scripts/micro/fp32_rate.cu (profiles/fp32_peak.json) -- a dependent
                 # FADD2 -> FFMA2 stream, the instruction pair this kernel is made of, sustains 115 of the nominal 128
