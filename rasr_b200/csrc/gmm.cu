@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "f32x2.cuh"
+#include "internal.h"
 
 namespace {
 
@@ -1479,6 +1480,13 @@ extern "C" int rb_gmm_score_fanout_dev(rb_gmm* h, const float* d_feats, long T, 
     return score_dev_impl(h, d_feats, T, d_dst[0], d_dst + 1, n_dst - 1, nullptr, s);
 }
 
+int rb_gmm_reserve(rb_gmm* h, long frames) {
+    if (!h || !h->tensor || frames <= 0)
+        return RB_OK;
+    RB_CUDA(cudaSetDevice(h->dev.ordinal));
+    return rb_gmm_tensor_reserve(h->tensor, frames, h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_DIAG_MAX);
+}
+
 // Host-pointer entry point: frames are cut into slabs; H2D of slab i+1, scoring of slab i and D2H of
 // slab i-1 overlap on three streams (PCIe is the end-to-end bound: 1 KB of scores per frame).
 extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores, uint32_t* best_density) {
@@ -1522,11 +1530,11 @@ extern "C" int rb_gmm_score(rb_gmm* h, const float* feats, long T, float* scores
     const bool stagedIn = !rb_host_is_pinned(feats) && getenv("RB_NO_HOST_STAGER") == nullptr && (size_t)T * D * 4 >= ((size_t)4 << 20);
     if (stagedIn)
         RB_CHECK(h->hFeats.reserve((size_t)T * D));
-    if (h->tensor) {  // the largest slab's scratch once, before the pipeline starts
+    {  // the largest slab's scratch once, before the pipeline starts
         long largest = 0;
         for (int i = 0; i < nSlabs; ++i)
             largest = std::max(largest, cut[i + 1] - cut[i]);
-        RB_CHECK(rb_gmm_tensor_reserve(h->tensor, largest, h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_DIAG_MAX));
+        RB_CHECK(rb_gmm_reserve(h, largest));
     }
     for (int i = 0; i < nSlabs && rc == RB_OK; ++i) {
         const long  a = cut[i], n = cut[i + 1] - cut[i];

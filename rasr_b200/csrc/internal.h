@@ -14,3 +14,5 @@ rb::DeviceInfo rb_frontend_device(const rb_frontend* h);
 int            rb_frontend_feat_dim(const rb_frontend* h);
 int            rb_frontend_convert_s16_dev(const rb_frontend* h, const int16_t* d_pcm, float* d_out, long n, int channels,
                                            int track, cudaStream_t s);
+// gmm.cu: size the scorer's per-call scratch for calls of up to `frames` frames before a slab pipeline starts
+int            rb_gmm_reserve(rb_gmm* h, long frames);

@@ -123,6 +123,12 @@ int pipeline_score_host(rb_frontend* fe, rb_gmm* gmm, const void* samplesRaw, in
             target = std::min<long>(2 * target, targetMax);
         }
     const int    nSlabs = (int)cut.size() - 1;
+    {  // the scorer's scratch for the largest slab once, before the pipeline starts (a reallocation synchronises the device)
+        long largest = 0;
+        for (int i = 0; i < nSlabs; ++i)
+            largest = std::max<long>(largest, fo[cut[i + 1]] - fo[cut[i]]);
+        RB_CHECK(rb_gmm_reserve(gmm, largest));
+    }
     RB_CHECK(sc.copy.ensure(2 * (size_t)nSlabs));
     cudaStream_t sIn = sc.copy.in, sOut = sc.copy.out;
     cudaEvent_t* evIn = sc.copy.pool.data();
