@@ -1,7 +1,9 @@
 /*
  * frontend_oracle.cc -- CPU restatement of the reference's MFCC Flow pipeline.
  *
- * TEST INFRASTRUCTURE ONLY (see oracle.h).  Each block names the reference lines it follows.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  Each block names the reference lines it follows.  PARITY PINNED: bit for
+ * bit against Flow networks built by the reference's own NetworkParser from its own .flow files (oracle/_ref,
+ * tests/test_ref_parity.py: every stage, 14 boundary lengths, packet sizes, sample rates, window types, DC detection).
  * The network restated is src/Tools/FeatureExtraction/share/mfcc.flow:8-34 followed by
  * derivationWithRegression.flow:7-27 and a generic-vector-f32-concat of static|delta|delta-delta.
  *

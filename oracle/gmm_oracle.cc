@@ -1,9 +1,11 @@
 /*
  * gmm_oracle.cc -- CPU restatement of the reference's diagonal-covariance GMM feature scorers.
  *
- * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED by reference tests: the reference has no
- * unit test for any Mm scorer; the restatement follows the cited lines, including accumulation
- * order and the f32/f64 mixing.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY PINNED: the reference has no unit test for any Mm
+ * scorer, so its own scorers -- src/Mm compiled into oracle/_ref, created by Mm::Module's factory --
+ * are the check: every function here equals them bit for bit (tests/test_ref_parity.py: C2 model,
+ * ragged / multi-covariance models, preselection parameters, tied distances, buffer sizes).  The
+ * restatement follows the cited lines, including accumulation order and the f32/f64 mixing.
  *
  * Build with -ffp-contract=off.  use_fma selects the contraction the reference's default build
  * (gcc -O2 -march=native, -ffp-contract=fast) applies to `s += x * x`.

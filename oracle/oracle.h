@@ -7,14 +7,20 @@
  * legs may load it; the product (rasr_b200/) never links or calls anything in oracle/.
  *
  * Every function names the reference file:line it follows (paths relative to the
- * reference checkout).  Parity status:
- *   - Nn layers:   pinned by the reference's own unit-test vectors
- *                  (src/Test/Nn_LinearAndActivationLayer.cc:79-179, src/Test/Nn_NeuralNetwork.cc:37-120)
- *   - FFT:         pinned against the reference's own TU src/Math/FastFourierTransform.cc compiled
- *                  from where it lies into oracle/_ref (see oracle/Makefile)
- *   - everything else (pre-emphasis, framing, window, amplitude, filterbank, log, DCT,
- *     regression, all Mm scorers): PARITY UNPINNED by reference tests (none exist); the
- *     restatement follows the cited source lines and is checked by self-derived KATs.
+ * reference checkout).  Parity status: PINNED to the reference's own object code.  The reference has
+ * no unit tests for this path (only the Nn layer vectors of src/Test/Nn_*.cc, which are used too), so
+ * 129 of its translation units (Core, Flow, Math, Mc, Mm, Nn, Signal) are compiled from where they lie
+ * into oracle/_ref/librasr_ref{,_native}.so (oracle/refbuild/Makefile) and driven the way RASR's tools
+ * drive them (ref_host.cc, ref_nn.cc, ref_io.cc):
+ *   - front-end (pre-emphasis, framing / flush / time stamps, window, FFT, amplitude, filter bank, log,
+ *     DCT, delay / regression / concat, DC detection), normalisation / splice / matrix nodes: bit for bit
+ *     against Flow networks the reference's NetworkParser builds from its own .flow files;
+ *   - all Mm scorers (batch-float, int, unrolled int, both preselection scorers, diagonal max / sum):
+ *     bit for bit against scorers made by Mm::Module's factory, read through the recognizer's protocol;
+ *   - Nn batch scorer and neural-network-forward node: against the reference's own, same configuration;
+ *   (tests/test_ref_parity.py; fixtures made by that object code: tests/golden/ref_*.npz, ref_io/)
+ *   - NOT covered by reference object code: Search::LinearSearch (needs Am / Lm / Bliss / Fsa); its
+ *     restatement is pinned by a literal Python transcription of feed / bookKeeping only.
  */
 #ifndef RASR_ORACLE_H
 #define RASR_ORACLE_H

@@ -6,8 +6,10 @@
  *   signal-matrix-multiplication-f32                     src/Signal/MatrixMult.hh, src/Math/Matrix.hh:487-494,
  *                                                         src/Math/Vector.hh:95-101
  *
- * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED by reference tests (none exist for these nodes); the
- * restatement follows the cited lines including the f32 / f64 mixing and the update order of the running sums.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY PINNED to the reference's own nodes (src/Signal compiled into
+ * oracle/_ref, wired by its NetworkParser from oracle/refbuild/flows/postproc_chain.flow): bit for bit over the window / length /
+ * output-point combinations of tests/test_ref_parity.py.  The restatement follows the cited lines including the f32 / f64
+ * mixing and the update order of the running sums.
  * Build with -ffp-contract=off; use_fma selects the contraction the reference's default build applies.
  */
 #include "oracle.h"

@@ -7,7 +7,9 @@
  *   getCurrentBestSentence        src/Search/LinearSearch.cc:438-468
  *   transition types              src/Am/TransitionModel.hh:32-37 (loop 0, forward 1, skip 2, exit 3)
  *
- * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED by reference tests (the reference has none for Search).
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED: the reference has no test for Search, and LinearSearch.cc
+ * does not compile into oracle/_ref without the Am / Lm / Bliss / Fsa stack; pinned by a literal Python transcription
+ * of feed / bookKeeping only (tests/test_oracle_search.py).
  * What is restated is the arithmetic of feed / bookKeeping on a lexicon given as flat arrays (every pronunciation a
  * regular word, single-word recognition off, unigram scores precomputed as LinearSearch does: isUnigram() is always
  * true, :434-436); the Bliss lexicon, the Am model lookup and the lattice / history plumbing are not.
