@@ -276,3 +276,175 @@ def read_vector(filename, native=False):
     out = np.zeros(n.value, np.float32)
     L.ref_math_read_vector(str(filename).encode(), C.byref(n), _p(out), C.c_long(out.size))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Search::LinearSearch (oracle/_ref/librasr_ref_search.so, oracle/refbuild/ref_search.cc)
+
+_search = None
+TDP_MODELS = ("entry-m1", "entry-m2", "silence", "state-0", "state-1")  # src/Am/TransitionModel.hh:72-78
+TDP_TYPES = ("loop", "forward", "skip", "exit")                         # src/Am/TransitionModel.hh:32-37
+
+
+def search_path():
+    return os.path.join(_HERE, "_ref", "librasr_ref_search.so")
+
+
+def search_lib():
+    global _search
+    if _search is None:
+        if not os.path.exists(search_path()):
+            build()
+        # self-contained (its own copy of the strict objects and its own application object / configuration)
+        S = C.CDLL(search_path(), mode=C.RTLD_LOCAL)
+        S.ref_last_error.restype = C.c_char_p
+        S.ref_init(None)
+        S.ref_search_create.restype = C.c_void_p
+        for f in ("ref_search_order", "ref_search_states", "ref_search_run"):
+            getattr(S, f).restype = C.c_long
+        _search = S
+    return _search
+
+
+def write_lexicon(path, n_phonemes, words, silence=True, silence_first=False):
+    """A Bliss lexicon file: context-independent phonemes p0..p<n-1> (+ "si"), one lemma "w<k>" per entry of
+    `words` (each a list of phoneme numbers, or a list of such lists = several pronunciations), optionally the
+    special lemma "silence" (no syntactic token, empty evaluation sequence: an irregular word)."""
+    sil = ('  <lemma special="silence"><orth>[SILENCE]</orth><phon>si</phon><synt/><eval/></lemma>\n'
+           if silence else "")
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0" encoding="UTF-8"?>\n<lexicon>\n  <phoneme-inventory>\n')
+        for k in range(n_phonemes):
+            f.write("    <phoneme><symbol>p%d</symbol><variation>none</variation></phoneme>\n" % k)
+        # always in the inventory: LinearSearch verifies that the acoustic model knows a silence phoneme
+        f.write("    <phoneme><symbol>si</symbol><variation>none</variation></phoneme>\n")
+        f.write("  </phoneme-inventory>\n")
+        if silence_first:
+            f.write(sil)
+        for k, prons in enumerate(words):
+            if len(prons) and not isinstance(prons[0], (list, tuple)):
+                prons = [prons]
+            f.write("  <lemma><orth>w%d</orth>" % k)
+            for p in prons:
+                f.write("<phon>%s</phon>" % " ".join("p%d" % q for q in p))
+            f.write("</lemma>\n")
+        if not silence_first:
+            f.write(sil)
+        f.write("</lexicon>\n")
+
+
+class LinearSearch:
+    """The reference's Search::LinearSearch over a lexicon file, a (phoneme, state) -> emission table, transition
+    scores tdp[model][type] (models in TDP_MODELS order) and unscaled unigram scores; everything else is read by
+    the reference's own classes from its configuration."""
+    _count = 0
+
+    def __init__(self, lexicon_file, emission_of, silence_emission, n_emissions, tdp, unigram, states_per_phone=3,
+                 state_repetitions=1, lm_scale=1.0, tdp_scale=1.0, pronunciation_scale=0.0, single_word=False,
+                 scratch_dir="/tmp"):
+        S = search_lib()
+        LinearSearch._count += 1
+        sel = "search-%d-%d" % (os.getpid(), LinearSearch._count)
+        put = lambda k, v: S.ref_config_set(("*.%s.%s" % (sel, k)).encode(), str(v).encode())
+        put("lexicon.file", lexicon_file)
+        put("acoustic-model.hmm.states-per-phone", states_per_phone)
+        put("acoustic-model.hmm.state-repetitions", state_repetitions)
+        put("acoustic-model.state-tying.type", "lookup")
+        put("acoustic-model.state-tying.file", os.path.join(scratch_dir, sel + ".tying"))
+        put("acoustic-model.tdp.scale", repr(float(tdp_scale)))
+        tdp = np.asarray(tdp, np.float32).reshape(len(TDP_MODELS), len(TDP_TYPES))
+        for m, model in enumerate(TDP_MODELS):
+            for t, typ in enumerate(TDP_TYPES):
+                v = float(tdp[m, t])
+                put("acoustic-model.tdp.%s.%s" % (model, typ), "infinity" if np.isinf(v) else repr(v))
+        # the reference's default is true (src/Search/LinearSearch.cc:26-30)
+        put("recognizer.single-word-recognition", "true" if single_word else "false")
+        put("lm.scale", repr(float(lm_scale)))
+        put("pronunciation-scale", repr(float(pronunciation_scale)))
+        self._emis = np.ascontiguousarray(emission_of, np.int32)
+        self._uni = np.ascontiguousarray(unigram, np.float32)
+        self.n_emissions = int(n_emissions)
+        self._S = S
+        self._h = S.ref_search_create(sel.encode(), _p(self._emis), int(states_per_phone), int(silence_emission),
+                                      self.n_emissions, _p(self._uni), int(self._uni.size))
+        if not self._h:
+            raise RuntimeError("reference LinearSearch could not be set up: %s" % S.ref_last_error().decode())
+        self._h = C.c_void_p(self._h)
+
+    def order(self):
+        """word number of every lemma pronunciation in the order LinearSearch visits them (-1: silence)"""
+        n = self._S.ref_search_order(self._h, None, C.c_long(0))
+        out = np.empty(n, np.int32)
+        self._S.ref_search_order(self._h, _p(out), C.c_long(n))
+        return out
+
+    def states(self, i, capacity=256):
+        """(emission, transition model) of every state of pronunciation i, as LinearSearch derives them"""
+        e = np.empty(capacity, np.int32)
+        m = np.empty(capacity, np.int32)
+        n = self._S.ref_search_states(self._h, C.c_long(i), _p(e), _p(m), C.c_long(capacity))
+        if n < 0 or n > capacity:
+            raise RuntimeError("ref_search_states(%d) -> %d" % (i, n))
+        return e[:n].copy(), m[:n].copy()
+
+    def tdps(self):
+        out = np.empty((len(TDP_MODELS), len(TDP_TYPES)), np.float32)
+        self._S.ref_search_tdps(self._h, _p(out))
+        return out
+
+    def run(self, scores):
+        scores = np.ascontiguousarray(scores, np.float32)
+        T = scores.shape[0]
+        assert scores.shape[1] == self.n_emissions
+        cap = max(T, 1)
+        words, times = np.empty(cap, np.int32), np.empty(cap, np.int32)
+        am, lm = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        fin = np.zeros(2, np.float32)
+        n = self._S.ref_search_run(self._h, _p(scores), C.c_long(T), self.n_emissions, _p(words), _p(times), _p(am),
+                                   _p(lm), C.c_long(cap), _p(fin))
+        return words[:n].copy(), times[:n].copy(), am[:n].copy(), lm[:n].copy(), fin
+
+    def close(self):
+        if self._h:
+            self._S.ref_search_destroy(self._h)
+            self._h = None
+
+
+def flat_lexicon(words, emission_of, silence_emission, tdp, unigram, states_per_phone=3, state_repetitions=1,
+                 silence=True, silence_first=False, lm_scale=1.0, tdp_scale=1.0):
+    """The flat-array form (oracle.h orc_lexicon / rb_lexicon) of what write_lexicon + LinearSearch describe, derived
+    HERE from the rules of src/Search/LinearSearch.cc:32-84,472-480 -- tests compare it with what the reference's own
+    objects hand out (LinearSearch.order / states / tdps).  Rows of `word` give the word number of every flat entry
+    (-1 = silence)."""
+    F = np.float32
+    emission_of = np.asarray(emission_of, np.int64).reshape(-1, states_per_phone)
+    entries = []  # (word number, [phonemes] or None for silence)
+    for k, prons in enumerate(words):
+        if len(prons) and not isinstance(prons[0], (list, tuple)):
+            prons = [prons]
+        entries += [(k, list(p)) for p in prons]
+    sil = [(-1, None)] if silence else []
+    entries = sil + entries if silence_first else entries + sil
+    offs, emis, model, uni, word = [0], [], [], [], []
+    for k, p in entries:
+        if p is None:
+            emis.append(silence_emission)
+            model.append(2)  # TransitionModel::silence
+            uni.append(F(0))
+        else:
+            for ph in p:
+                for a in range(states_per_phone):
+                    for b in range(state_repetitions):
+                        emis.append(int(emission_of[ph, a]))
+                        model.append(3 + b)  # phone0 + b
+            uni.append(F(F(lm_scale) * F(unigram[k])))
+        offs.append(len(emis))
+        word.append(k)
+    fmax = np.finfo(np.float32).max
+    t = np.asarray(tdp, np.float32).reshape(5, 4)
+    with np.errstate(over="ignore", invalid="ignore"):
+        t = np.clip(F(tdp_scale) * t, -fmax, fmax).astype(np.float32)  # StateTransitionModel::load: scale * value, Core::clip
+    t[0, 0] = t[1, 0] = fmax                                           # TransitionModel::correct(): entry loops forbidden
+    return dict(word_offsets=np.asarray(offs, np.uint32), state_emission=np.asarray(emis, np.uint32),
+                state_tdp_model=np.asarray(model, np.uint32), tdp=t, entry_model=0,
+                unigram=np.asarray(uni, np.float32), word=np.asarray(word, np.int32))
