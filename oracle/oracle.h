@@ -184,6 +184,8 @@ typedef struct {
     const float*    tdp;             /* [n_models * 4]: loop, forward, skip, exit */
     uint32_t        entry_model;     /* Am::TransitionModel::entryM1 */
     const float*    unigram;         /* [n_words] LM score of entering the word */
+    const uint8_t*  word_regular;    /* [n_words] Pronunciation::isRegularWord (1) or not (silence, noise); NULL = all regular */
+    int32_t         single_word;     /* LinearSearch "single-word-recognition" (reference default: on) */
 } orc_lexicon;
 long orc_linear_search(const orc_lexicon* lx, const float* scores, long T, int n_emissions, uint32_t* words,
                        int32_t* times, float* am, float* lm);

@@ -360,7 +360,7 @@ class LexiconC(C.Structure):
     _fields_ = [("n_words", C.c_uint32), ("word_offsets", C.POINTER(C.c_uint32)),
                 ("state_emission", C.POINTER(C.c_uint32)), ("state_tdp_model", C.POINTER(C.c_uint32)),
                 ("n_models", C.c_uint32), ("tdp", C.POINTER(C.c_float)), ("entry_model", C.c_uint32),
-                ("unigram", C.POINTER(C.c_float))]
+                ("unigram", C.POINTER(C.c_float)), ("word_regular", C.POINTER(C.c_uint8)), ("single_word", C.c_int32)]
 
 
 def linear_search(lex, scores):
@@ -371,9 +371,13 @@ def linear_search(lex, scores):
              state_tdp_model=np.ascontiguousarray(lex["state_tdp_model"], np.uint32),
              tdp=np.ascontiguousarray(lex["tdp"], np.float32).reshape(-1, 4),
              unigram=np.ascontiguousarray(lex["unigram"], np.float32))
+    reg = lex.get("word_regular")
+    if reg is not None:
+        reg = np.ascontiguousarray(reg, np.uint8)
     c = LexiconC(a["word_offsets"].size - 1, _p(a["word_offsets"], C.c_uint32), _p(a["state_emission"], C.c_uint32),
                  _p(a["state_tdp_model"], C.c_uint32), a["tdp"].shape[0], _p(a["tdp"], C.c_float),
-                 int(lex["entry_model"]), _p(a["unigram"], C.c_float))
+                 int(lex["entry_model"]), _p(a["unigram"], C.c_float),
+                 _p(reg, C.c_uint8) if reg is not None else None, int(bool(lex.get("single_word", False))))
     scores = np.ascontiguousarray(scores, np.float32)
     T = scores.shape[0]
     words, times = np.zeros(max(T, 1), np.uint32), np.zeros(max(T, 1), np.int32)

@@ -306,10 +306,11 @@ def search_lib():
     return _search
 
 
-def write_lexicon(path, n_phonemes, words, silence=True, silence_first=False):
+def write_lexicon(path, n_phonemes, words, silence=True, silence_first=False, irregular=()):
     """A Bliss lexicon file: context-independent phonemes p0..p<n-1> (+ "si"), one lemma "w<k>" per entry of
     `words` (each a list of phoneme numbers, or a list of such lists = several pronunciations), optionally the
-    special lemma "silence" (no syntactic token, empty evaluation sequence: an irregular word)."""
+    special lemma "silence" (no syntactic token, empty evaluation sequence: an irregular word).  Lemmata whose number
+    is in `irregular` keep their syntactic token (LM score) but get an empty evaluation sequence (noise words)."""
     sil = ('  <lemma special="silence"><orth>[SILENCE]</orth><phon>si</phon><synt/><eval/></lemma>\n'
            if silence else "")
     with open(path, "w") as f:
@@ -327,7 +328,7 @@ def write_lexicon(path, n_phonemes, words, silence=True, silence_first=False):
             f.write("  <lemma><orth>w%d</orth>" % k)
             for p in prons:
                 f.write("<phon>%s</phon>" % " ".join("p%d" % q for q in p))
-            f.write("</lemma>\n")
+            f.write("<eval/></lemma>\n" if k in irregular else "</lemma>\n")
         if not silence_first:
             f.write(sil)
         f.write("</lexicon>\n")
@@ -411,7 +412,7 @@ class LinearSearch:
 
 
 def flat_lexicon(words, emission_of, silence_emission, tdp, unigram, states_per_phone=3, state_repetitions=1,
-                 silence=True, silence_first=False, lm_scale=1.0, tdp_scale=1.0):
+                 silence=True, silence_first=False, lm_scale=1.0, tdp_scale=1.0, single_word=False, irregular=()):
     """The flat-array form (oracle.h orc_lexicon / rb_lexicon) of what write_lexicon + LinearSearch describe, derived
     HERE from the rules of src/Search/LinearSearch.cc:32-84,472-480 -- tests compare it with what the reference's own
     objects hand out (LinearSearch.order / states / tdps).  Rows of `word` give the word number of every flat entry
@@ -447,4 +448,6 @@ def flat_lexicon(words, emission_of, silence_emission, tdp, unigram, states_per_
     t[0, 0] = t[1, 0] = fmax                                           # TransitionModel::correct(): entry loops forbidden
     return dict(word_offsets=np.asarray(offs, np.uint32), state_emission=np.asarray(emis, np.uint32),
                 state_tdp_model=np.asarray(model, np.uint32), tdp=t, entry_model=0,
-                unigram=np.asarray(uni, np.float32), word=np.asarray(word, np.int32))
+                unigram=np.asarray(uni, np.float32), word=np.asarray(word, np.int32),
+                word_regular=np.asarray([k >= 0 and k not in irregular for k in word], np.uint8),
+                single_word=bool(single_word))

@@ -7,12 +7,19 @@
  *   getCurrentBestSentence        src/Search/LinearSearch.cc:438-468
  *   transition types              src/Am/TransitionModel.hh:32-37 (loop 0, forward 1, skip 2, exit 3)
  *
- * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED: the reference has no test for Search, and LinearSearch.cc
- * does not compile into oracle/_ref without the Am / Lm / Bliss / Fsa stack; pinned by a literal Python transcription
- * of feed / bookKeeping only (tests/test_oracle_search.py).
- * What is restated is the arithmetic of feed / bookKeeping on a lexicon given as flat arrays (every pronunciation a
- * regular word, single-word recognition off, unigram scores precomputed as LinearSearch does: isUnigram() is always
- * true, :434-436); the Bliss lexicon, the Am model lookup and the lattice / history plumbing are not.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY PINNED to the reference's own object code: LinearSearch.cc with
+ * the Bliss lexicon parser, the Am state / transition / tying models and the Lm scaling wrapper compiled from where
+ * they lie into oracle/_ref/librasr_ref_search.so (oracle/refbuild/ref_search.cc), compared bit for bit on words,
+ * end frames and both scores in tests/test_ref_search.py -- with single-word recognition on (the reference's
+ * default, :26-30) and off; a literal Python transcription of feed / bookKeeping is the second pin
+ * (tests/test_oracle_search.py).
+ * What is restated is the arithmetic of feed / bookKeeping on a lexicon given as flat arrays (unigram scores
+ * precomputed as LinearSearch does: isUnigram() is always true, :434-436); the Bliss lexicon, the Am model lookup
+ * and the lattice / history plumbing are not.
+ * Single-word recognition (:248-258, 355-370, 390-395, 479-485): an irregular pronunciation (silence, noise) gets a
+ * second "irregular chain" entry right behind it; a second book records the best sequence of irregular words only;
+ * a regular word may only start from that book once the main book's newest entry already contains a regular word,
+ * so every sentence is  irregular* regular irregular*.
  */
 #include "oracle.h"
 
@@ -20,13 +27,19 @@
 #include <vector>
 
 namespace {
+/* back pointers name an entry of either book: >= 0 the main book, <= -2 entry (-2 - bkp) of the irregular book */
 struct Book {
     float score, lmScore;
     int   word, bkp, time;
+    bool  hadRegularWord;
 };
 struct Hypo {
     float score, lmScore;
     int   bkp;
+};
+struct Entry {  /* one WordPronunciationState */
+    uint32_t word;
+    bool     regular, chain;
 };
 }  // namespace
 
@@ -34,26 +47,60 @@ struct Hypo {
  * the word end), am (Book::score: without LM), lm (Book::lmScore).  Returns the number of words, < 0 on error. */
 extern "C" long orc_linear_search(const orc_lexicon* lx, const float* scores, long T, int n_emissions, uint32_t* words,
                                   int32_t* times, float* am, float* lm) {
-    const uint32_t W = lx->n_words;
-    std::vector<std::vector<Hypo>> hyp(W);
-    for (uint32_t w = 0; w < W; ++w) {
+    const bool         single = lx->single_word != 0;
+    std::vector<Entry> entries; /* addPronunciations, :472-487 */
+    for (uint32_t w = 0; w < lx->n_words; ++w) {
+        const bool regular = !lx->word_regular || lx->word_regular[w];
+        entries.push_back(Entry{w, regular, false});
+        if (single && !regular)
+            entries.push_back(Entry{w, regular, true});
+    }
+    const size_t                   E = entries.size();
+    std::vector<std::vector<Hypo>> hyp(E);
+    for (size_t e = 0; e < E; ++e) {
+        const uint32_t w = entries[e].word;
         const uint32_t S = lx->word_offsets[w + 1] - lx->word_offsets[w];
         if (S == 0)
             return -1;
-        hyp[w].assign(S + 1, Hypo{FLT_MAX, 0.0f, -1}); /* WordPronunciationState::restart */
+        hyp[e].assign(S + 1, Hypo{FLT_MAX, 0.0f, -1}); /* WordPronunciationState::restart */
     }
-    std::vector<Book> book;
+    std::vector<Book> book, irregularBook;
+    auto              entry_of = [&](int bkp) -> const Book& { return bkp >= 0 ? book[bkp] : irregularBook[-2 - bkp]; };
     std::vector<Hypo> tmp;
+    /* bookKeeping (:381-432) */
+    auto keep = [&](Book& nb, bool irregular, long t) {
+        for (size_t e = 0; e < E; ++e) {
+            const uint32_t w = entries[e].word;
+            const Hypo&    h = hyp[e].back();
+            if (irregular && entries[e].regular)
+                continue;
+            if (irregular && h.bkp != -1 && entry_of(h.bkp).hadRegularWord)
+                continue;
+            const uint32_t model    = lx->state_tdp_model[lx->word_offsets[w + 1] - 1];
+            const float    tmpScore = h.score + lx->tdp[model * 4 + 3];
+            if (tmpScore < nb.score + nb.lmScore) {
+                nb.score          = tmpScore - h.lmScore;
+                nb.lmScore        = h.lmScore;
+                nb.bkp            = h.bkp;
+                nb.word           = (int)w;
+                nb.time           = (int)t;
+                nb.hadRegularWord = entries[e].regular ? true : (h.bkp != -1 ? entry_of(h.bkp).hadRegularWord : false);
+            }
+        }
+    };
     for (long t = 1; t <= T; ++t) {
         const float* sc = scores + (size_t)(t - 1) * n_emissions;
-        for (uint32_t w = 0; w < W; ++w) {
-            std::vector<Hypo>& h    = hyp[w];
-            const uint32_t     s0   = lx->word_offsets[w];
-            const int          last = book.empty() ? -1 : (int)book.size() - 1;
-            h[0].bkp                = last;
-            if (last >= 0) {
-                h[0].lmScore = lx->unigram[w] + book[last].lmScore;
-                h[0].score   = book[last].score;
+        for (size_t e = 0; e < E; ++e) {
+            const uint32_t     w  = entries[e].word;
+            std::vector<Hypo>& h  = hyp[e];
+            const uint32_t     s0 = lx->word_offsets[w];
+            int                last = book.empty() ? -1 : (int)book.size() - 1;
+            if ((single && last >= 0 && book[last].hadRegularWord && entries[e].regular) || entries[e].chain)
+                last = irregularBook.empty() ? -1 : -2 - ((int)irregularBook.size() - 1); /* :248-258 */
+            h[0].bkp = last;
+            if (last != -1) {
+                h[0].lmScore = lx->unigram[w] + entry_of(last).lmScore;
+                h[0].score   = entry_of(last).score;
             }
             else {
                 h[0].lmScore = lx->unigram[w];
@@ -80,32 +127,27 @@ extern "C" long orc_linear_search(const orc_lexicon* lx, const float* scores, lo
                 h[sta].lmScore = tmp[sta].lmScore;
             }
         }
-        Book nb{FLT_MAX, 0.0f, -1, -1, 0};
-        for (uint32_t w = 0; w < W; ++w) { /* bookKeeping */
-            const Hypo&    h     = hyp[w].back();
-            const uint32_t model = lx->state_tdp_model[lx->word_offsets[w + 1] - 1];
-            const float    tmpScore = h.score + lx->tdp[model * 4 + 3];
-            if (tmpScore < nb.score + nb.lmScore) {
-                nb.score   = tmpScore - h.lmScore;
-                nb.lmScore = h.lmScore;
-                nb.bkp     = h.bkp;
-                nb.word    = (int)w;
-                nb.time    = (int)t;
-            }
-        }
+        Book nb{FLT_MAX, 0.0f, -1, -1, 0, false};
+        keep(nb, false, t);
         if (nb.score != FLT_MAX)
             book.push_back(nb);
+        if (single) { /* :355-370 */
+            Book ib{FLT_MAX, 0.0f, -1, -1, 0, false};
+            keep(ib, true, t);
+            if (ib.score != FLT_MAX)
+                irregularBook.push_back(ib);
+        }
     }
-    /* getCurrentBestSentence: follow the back pointers from the last book entry */
-    std::vector<int> chain;
-    for (int b = book.empty() ? -1 : (int)book.size() - 1; b >= 0; b = book[b].bkp)
-        chain.push_back(b);
+    /* getCurrentBestSentence: follow the back pointers from the last entry of the main book */
+    std::vector<const Book*> chain;
+    for (int b = book.empty() ? -1 : (int)book.size() - 1; b != -1; b = entry_of(b).bkp)
+        chain.push_back(&entry_of(b));
     long n = 0;
     for (auto it = chain.rbegin(); it != chain.rend(); ++it, ++n) {
-        words[n] = (uint32_t)book[*it].word;
-        times[n] = book[*it].time;
-        am[n]    = book[*it].score;
-        lm[n]    = book[*it].lmScore;
+        words[n] = (uint32_t)(*it)->word;
+        times[n] = (*it)->time;
+        am[n]    = (*it)->score;
+        lm[n]    = (*it)->lmScore;
     }
     return n;
 }

@@ -21,7 +21,8 @@ TDP_DEFAULT = np.array([[INF, 0.0, 3.0, 0.0], [INF, 0.0, 3.0, 0.0], [0.7, 0.7, I
 
 
 def make_case(tmp_path, n_words, n_phonemes, n_emissions, seed, P=3, R=1, silence=True, silence_first=False,
-              lm_scale=1.0, tdp_scale=1.0, tdp=TDP_DEFAULT, multi=False, duplicates=0, max_len=4, grid=False):
+              lm_scale=1.0, tdp_scale=1.0, tdp=TDP_DEFAULT, multi=False, duplicates=0, max_len=4, grid=False,
+              single_word=False, irregular=()):
     rng = np.random.default_rng(seed)
     words = []
     for k in range(n_words):
@@ -38,12 +39,12 @@ def make_case(tmp_path, n_words, n_phonemes, n_emissions, seed, P=3, R=1, silenc
         unigram = (np.round(unigram * 2) / 2).astype(np.float32)
     unigram = np.concatenate([unigram, unigram[:duplicates]])
     lex_file = str(tmp_path / ("lexicon_%d.xml" % seed))
-    pyref.write_lexicon(lex_file, n_phonemes, words, silence=silence, silence_first=silence_first)
-    kw = dict(states_per_phone=P, state_repetitions=R, lm_scale=lm_scale, tdp_scale=tdp_scale)
+    pyref.write_lexicon(lex_file, n_phonemes, words, silence=silence, silence_first=silence_first, irregular=irregular)
+    kw = dict(states_per_phone=P, state_repetitions=R, lm_scale=lm_scale, tdp_scale=tdp_scale, single_word=single_word)
     ref = pyref.LinearSearch(lex_file, emission_of, n_emissions - 1, n_emissions, tdp, unigram,
                              scratch_dir=str(tmp_path), **kw)
     flat = pyref.flat_lexicon(words, emission_of, n_emissions - 1, tdp, unigram, silence=silence,
-                              silence_first=silence_first, **kw)
+                              silence_first=silence_first, irregular=irregular, **kw)
     return ref, flat
 
 
@@ -65,6 +66,8 @@ def check_run(oracle, ref, flat, scores):
     assert np.array_equal(got["am"], am) and np.array_equal(got["lm"], lm)
     if len(words):
         assert fin[0] == am[-1] and fin[1] == lm[-1]  # closing item: last book entry + sentence end score (0 here)
+    if flat["single_word"]:
+        assert int(flat["word_regular"][got["words"]].sum()) <= 1
     return words
 
 
@@ -81,6 +84,17 @@ CASES = [
     (64, 20, 128, 300, 8, dict(R=2, max_len=6)),
     (12, 6, 20, 2, 9, {}),      # shorter than most words: few or no book entries
     (5, 3, 10, 1, 10, dict(P=1)),
+    # single-word recognition, the reference's default: irregular* regular irregular*
+    (7, 5, 16, 60, 11, dict(single_word=True)),
+    (40, 12, 64, 150, 12, dict(single_word=True, R=2)),
+    (25, 8, 32, 90, 13, dict(single_word=True, P=1, silence_first=True)),
+    (30, 10, 48, 200, 14, dict(single_word=True, P=2, R=2, lm_scale=12.5, tdp_scale=0.75)),
+    (20, 6, 32, 80, 15, dict(single_word=True, silence=False)),   # no irregular word at all
+    (16, 4, 24, 70, 16, dict(single_word=True, duplicates=5, multi=True)),
+    (12, 6, 20, 2, 17, dict(single_word=True)),
+    (30, 8, 40, 160, 18, dict(single_word=True, irregular=(0, 7, 8, 29))),   # noise words besides silence
+    (30, 8, 40, 160, 19, dict(single_word=False, irregular=(0, 7, 8, 29))),  # the flag is inert without the mode
+    (10, 4, 16, 120, 20, dict(single_word=True, irregular=tuple(range(10)))),  # nothing but irregular words
 ]
 
 
@@ -97,12 +111,14 @@ def test_oracle_matches_reference_linear_search(oracle, tmp_path, n_words, n_pho
         ref.close()
 
 
-def test_ties_resolve_to_the_first_pronunciation(oracle, tmp_path):
+@pytest.mark.parametrize("single_word", [False, True])
+def test_ties_resolve_to_the_first_pronunciation(oracle, tmp_path, single_word):
     """Scores, transition and LM scores on a coarse grid (multiples of 0.5, exact in float32) make equal path scores
     common, and six lemmata repeat earlier ones: both sides must keep the first of equals (strict < in feed and
     bookKeeping, src/Search/LinearSearch.cc:321,405)."""
     tdp = np.array([[INF, 0, 1, 0], [INF, 0, 1, 0], [0.5, 0.5, INF, 1], [1, 0, 2, 0], [1, 0, 2, 0]], np.float32)
-    ref, flat = make_case(tmp_path, 12, 3, 6, 21, P=1, R=1, tdp=tdp, duplicates=6, max_len=2, grid=True)
+    ref, flat = make_case(tmp_path, 12, 3, 6, 21, P=1, R=1, tdp=tdp, duplicates=6, max_len=2, grid=True,
+                          single_word=single_word, irregular=(2, 5) if single_word else ())
     try:
         check_flat(ref, flat)
         rng = np.random.default_rng(5)
