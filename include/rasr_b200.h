@@ -384,8 +384,9 @@ int rb_pipeline_nn_score_dev(rb_frontend* fe, rb_postproc* pp, rb_nn* nn, const 
  * all pronunciations with a unigram LM and one book-keeping entry per frame (src/Search/LinearSearch.cc:233-432) --
  * fed from the dense score matrix the scorers above leave on the device, instead of two virtual calls per HMM state
  * and frame (emissionScores->score(mixture), :346).  The lexicon is passed as flat arrays (what LinearSearch builds
- * from Bliss::Lexicon + Am::AcousticModel in setModelCombination): every pronunciation is a regular word, single-word
- * recognition off.
+ * from Bliss::Lexicon + Am::AcousticModel in setModelCombination).  Both modes of the reference are implemented:
+ * continuous recognition and single-word recognition (its default) with irregular words (silence, noise) around
+ * the one regular word.
  * ===================================================================================== */
 
 typedef struct rb_search rb_search;
@@ -399,6 +400,10 @@ typedef struct {
     const float*    tdp;             /* [n_models * 4]: loop, forward, skip, exit (src/Am/TransitionModel.hh:32-37) */
     uint32_t        entry_model;     /* Am::TransitionModel::entryM1 */
     const float*    unigram;         /* [n_words] WordPronunciationState::unigramScore */
+    const uint8_t*  word_regular;    /* [n_words] Pronunciation::isRegularWord (src/Search/LinearSearch.cc:86-96): 0 for
+                                        silence / noise lemmata (empty evaluation sequence); NULL = every word regular */
+    int32_t         single_word;     /* the recognizer's "single-word-recognition" (:26-30; the reference's default is
+                                        true): sentences are irregular* regular irregular*.  0 = continuous recognition */
 } rb_lexicon;
 
 int  rb_search_create(const rb_lexicon* lx, int device, rb_search** out);

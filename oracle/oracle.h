@@ -19,8 +19,10 @@
  *     bit for bit against scorers made by Mm::Module's factory, read through the recognizer's protocol;
  *   - Nn batch scorer and neural-network-forward node: against the reference's own, same configuration;
  *   (tests/test_ref_parity.py; fixtures made by that object code: tests/golden/ref_*.npz, ref_io/)
- *   - NOT covered by reference object code: Search::LinearSearch (needs Am / Lm / Bliss / Fsa); its
- *     restatement is pinned by a literal Python transcription of feed / bookKeeping only.
+ *   - Search::LinearSearch (continuous and single-word recognition): bit for bit against the reference's own
+ *     LinearSearch, compiled with the Bliss / Am / Lm / Fsa units it needs into oracle/_ref/librasr_ref_search.so
+ *     and fed from a lexicon file and the reference's configuration (ref_search.cc, tests/test_ref_search.py,
+ *     fixture tests/golden/ref_search.npz).
  */
 #ifndef RASR_ORACLE_H
 #define RASR_ORACLE_H

@@ -81,7 +81,7 @@ class LexiconC(C.Structure):
     _fields_ = [("n_words", C.c_uint32), ("word_offsets", C.POINTER(C.c_uint32)),
                 ("state_emission", C.POINTER(C.c_uint32)), ("state_tdp_model", C.POINTER(C.c_uint32)),
                 ("n_models", C.c_uint32), ("tdp", C.POINTER(C.c_float)), ("entry_model", C.c_uint32),
-                ("unigram", C.POINTER(C.c_float))]
+                ("unigram", C.POINTER(C.c_float)), ("word_regular", C.POINTER(C.c_uint8)), ("single_word", C.c_int32)]
 
 
 class MixtureSetC(C.Structure):

@@ -52,7 +52,21 @@ struct SearchParams {
     // word-end candidates of the current frame, per segment [W]
     float* endScore;
     int    useSmem;  // hypotheses, lexicon tables and word-end candidates of the segment live in shared memory
+    // single-word recognition (:248-258, 355-370, 390-395): the "words" above are then the ENTRIES of the search
+    // (an irregular pronunciation is followed by its irregular-chain copy)
+    int             single;
+    const uint8_t*  flags;      // [W] bit 0: regular word, bit 1: irregular-chain entry
+    const uint32_t* entryWord;  // [W] word of the caller's lexicon, written into the book
+    const uint32_t* irrList;    // [nIrr] the entries that are not regular words, ascending
+    uint32_t        nIrr;
+    int4*           irrBooks;   // the second book: best sequences of irregular words only; same layout as books
+    int*            nIrrBooks;  // [U]
 };
+
+// back pointers name an entry of either book: >= 0 the main book, <= -2 entry (-2 - bkp) of the irregular book
+__device__ __forceinline__ int irr_ref(int i) {
+    return -2 - i;
+}
 
 __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchParams p) {
     const int      u      = blockIdx.x;
@@ -95,8 +109,12 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
         unigram   = sUni;
     }
     int4*          books  = p.books + 2 * f0;
+    int4*          irrBooks = p.single ? p.irrBooks + 2 * f0 : nullptr;
     __shared__ int   sLast;                  // index of the newest book entry, -1 if none
     __shared__ float sLastScore, sLastLm;
+    __shared__ int   sLastHad;               // Book::hadRegularWord of the newest entry
+    __shared__ int   sIrr;                   // newest entry of the irregular book, -1 if none
+    __shared__ float sIrrScore, sIrrLm;
     __shared__ float sTdp[64 * 4];           // transition models (when there are at most 64)
     if (p.nModels <= 64) {
         for (uint32_t i = threadIdx.x; i < p.nModels * 4; i += kThreads)
@@ -114,21 +132,38 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
         sLast      = -1;
         sLastScore = 0.0f;
         sLastLm    = 0.0f;
+        sLastHad   = 0;
+        sIrr       = -1;
+        sIrrScore  = 0.0f;
+        sIrrLm     = 0.0f;
     }
     __syncthreads();
+    // Book::hadRegularWord of the entry a back pointer names (entries of the irregular book never have one, :368)
+    auto had_regular = [&](int bkp) { return bkp >= 0 ? books[2 * bkp + 1].y : 0; };
 
     for (int t = 1; t <= T; ++t) {
         const float* sc   = p.scores + (size_t)(f0 + t - 1) * p.nEmis;
-        const int    last = sLast;
-        const float  lastScore = sLastScore, lastLm = sLastLm;
+        const int    mainLast = sLast, mainHad = sLastHad, irrLast = sIrr;
+        const float  mainScore = sLastScore, mainLm = sLastLm, irrScore = sIrrScore, irrLm = sIrrLm;
         for (uint32_t w = threadIdx.x; w < p.W; w += kThreads) {
             const uint32_t s0 = wordOff[w], S = wordOff[w + 1] - s0;
             float*         ws = hs + s0 + w;  // [0..S]
             float*         wl = hl + s0 + w;
             int*           wb = hb + s0 + w;
-            // word start (:271-290): from the newest book entry, or from scratch
+            // word start (:248-290): from the newest book entry, or from scratch; in single-word recognition a
+            // regular word behind a regular word, and every irregular-chain entry, starts from the irregular book
+            int   last      = mainLast;
+            float lastScore = mainScore, lastLm = mainLm;
+            if (p.single) {
+                const uint32_t fl = p.flags[w];
+                if ((mainLast >= 0 && mainHad && (fl & 1u)) || (fl & 2u)) {
+                    last      = irrLast >= 0 ? irr_ref(irrLast) : -1;
+                    lastScore = irrScore;
+                    lastLm    = irrLm;
+                }
+            }
             float h0lm, h0s;
-            if (last >= 0) {
+            if (last != -1) {
                 h0lm = __fadd_rn(unigram[w], lastLm);
                 h0s  = lastScore;
             }
@@ -175,42 +210,81 @@ __global__ void __launch_bounds__(kThreads) linear_search_kernel(const SearchPar
         // book keeping (:381-432): sequential scan over the words, replayed by warp 0
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x;
-            float     nbScore = FLT_MAX, nbLm = 0.0f;
-            int       nbWord = -1, nbBkp = -1;
-            for (uint32_t base = 0; base < p.W; base += 32) {
-                const uint32_t w   = base + lane;
-                const float    cand = w < p.W ? es[w] : FLT_MAX;
-                uint32_t       todo = 0xffffffffu;
-                while (true) {
-                    const float    thr  = __fadd_rn(nbScore, nbLm);
-                    const uint32_t hits = __ballot_sync(0xffffffffu, w < p.W && cand < thr) & todo;
-                    if (!hits)
-                        break;
-                    const int      first = __ffs(hits) - 1;  // lowest word of the chunk that beats the current best
-                    const uint32_t ww    = base + first;
-                    const uint32_t s0 = wordOff[ww], S = wordOff[ww + 1] - s0;
-                    const float    tmpScore = __shfl_sync(0xffffffffu, cand, first);
-                    const float    lmw = hl[s0 + ww + S];
-                    nbScore = __fsub_rn(tmpScore, lmw);
-                    nbLm    = lmw;
-                    nbBkp   = hb[s0 + ww + S];
-                    nbWord  = (int)ww;
-                    todo    = first == 31 ? 0u : (0xffffffffu << (first + 1));  // words before it were already rejected
+            float     nbScore, nbLm;
+            int       nbWord, nbBkp;
+            // irregular = false: over all entries.  irregular = true (:390-395): over the entries that are not regular
+            // words and whose history holds no regular word either
+            auto scan = [&](bool irregular) {
+                nbScore = FLT_MAX;
+                nbLm    = 0.0f;
+                nbWord  = -1;
+                nbBkp   = -1;
+                const uint32_t n = irregular ? p.nIrr : p.W;
+                for (uint32_t base = 0; base < n; base += 32) {
+                    const uint32_t i  = base + lane;
+                    uint32_t       w  = i;
+                    bool           ok = i < n;
+                    if (irregular && ok) {
+                        w                 = p.irrList[i];
+                        const uint32_t s0 = wordOff[w], S = wordOff[w + 1] - s0;
+                        ok                = !had_regular(hb[s0 + w + S]);
+                    }
+                    const float    cand = ok ? es[w] : FLT_MAX;
+                    uint32_t       todo = 0xffffffffu;
+                    while (true) {
+                        const float    thr  = __fadd_rn(nbScore, nbLm);
+                        const uint32_t hits = __ballot_sync(0xffffffffu, ok && cand < thr) & todo;
+                        if (!hits)
+                            break;
+                        const int      first = __ffs(hits) - 1;  // lowest entry of the chunk that beats the current best
+                        const uint32_t ww    = __shfl_sync(0xffffffffu, w, first);
+                        const uint32_t s0 = wordOff[ww], S = wordOff[ww + 1] - s0;
+                        const float    tmpScore = __shfl_sync(0xffffffffu, cand, first);
+                        const float    lmw = hl[s0 + ww + S];
+                        nbScore = __fsub_rn(tmpScore, lmw);
+                        nbLm    = lmw;
+                        nbBkp   = hb[s0 + ww + S];
+                        nbWord  = (int)ww;
+                        todo    = first == 31 ? 0u : (0xffffffffu << (first + 1));  // entries before it were already rejected
+                    }
+                }
+            };
+            scan(false);
+            const float mScore = nbScore, mLm = nbLm;
+            const int   mWord = nbWord, mBkp = nbBkp;
+            if (p.single) {
+                scan(true);
+                if (lane == 0 && nbScore != FLT_MAX) {
+                    const int b = sIrr + 1;
+                    irrBooks[2 * b]     = make_int4(__float_as_int(nbScore), __float_as_int(nbLm), (int)p.entryWord[nbWord], nbBkp);
+                    irrBooks[2 * b + 1] = make_int4(t, 0, 0, 0);
+                    sIrr      = b;
+                    sIrrScore = nbScore;
+                    sIrrLm    = nbLm;
                 }
             }
-            if (lane == 0 && nbScore != FLT_MAX) {
+            if (lane == 0 && mScore != FLT_MAX) {
                 const int b = sLast + 1;  // entries are only ever appended: the newest is the last
-                books[2 * b]     = make_int4(__float_as_int(nbScore), __float_as_int(nbLm), nbWord, nbBkp);
-                books[2 * b + 1] = make_int4(t, 0, 0, 0);
+                int       had = 0, word = mWord;
+                if (p.single) {
+                    had  = (p.flags[mWord] & 1u) ? 1 : had_regular(mBkp);
+                    word = (int)p.entryWord[mWord];
+                }
+                books[2 * b]     = make_int4(__float_as_int(mScore), __float_as_int(mLm), word, mBkp);
+                books[2 * b + 1] = make_int4(t, had, 0, 0);
                 sLast       = b;
-                sLastScore  = nbScore;
-                sLastLm     = nbLm;
+                sLastScore  = mScore;
+                sLastLm     = mLm;
+                sLastHad    = had;
             }
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         p.nBooks[u] = sLast + 1;
+        if (p.single)
+            p.nIrrBooks[u] = sIrr + 1;
+    }
 }
 
 
@@ -563,11 +637,21 @@ struct rb_search {
     rb::DevBuf<float>    dTdp, dUnigram, dHypScore, dHypLm, dEndScore, dScores;
     rb::DevBuf<int>      dHypBkp, dBooks, dNBooks;  // dBooks: 8 words per frame (two int4 per book entry)
     std::vector<int>     hostBooks;
+    // single-word recognition: W / nStates count the ENTRIES of the search (irregular words twice)
+    bool                  single = false;
+    uint32_t              nIrr   = 0;
+    rb::DevBuf<uint8_t>   dFlags;
+    rb::DevBuf<uint32_t>  dEntryWord, dIrrList;
+    rb::DevBuf<int>       dIrrBooks, dNIrrBooks;
+    std::vector<int>      hostIrrBooks, nIrrBooks;
     rb::DevBuf<int64_t>  dFrameOff;
     // results of the last decode, on the host
     std::vector<int64_t> frameOff;
-    std::vector<float>   bookScore, bookLm;
-    std::vector<int>     bookWord, bookBkp, bookTime, nBooks;
+    std::vector<int>     nBooks;
+    // the record a back pointer names (>= 0: main book, <= -2: entry -2 - bkp of the irregular book) in segment f0
+    const int* record(int64_t f0, int ref) const {
+        return ref >= 0 ? hostBooks.data() + (f0 + ref) * 8 : hostIrrBooks.data() + (f0 + (-2 - ref)) * 8;
+    }
     ~rb_search() {
         if (stream)
             cudaStreamDestroy(stream);
@@ -591,6 +675,37 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
         rb::set_error("out of host memory");
         return RB_ERR_NOMEM;
     }
+    // single-word recognition: the search runs over ENTRIES -- every pronunciation, an irregular one followed by its
+    // irregular-chain copy (addPronunciations, :472-487); the tables below are those of the entries
+    std::vector<uint32_t> eOff, eEmis, eTdp, eWord, irrList;
+    std::vector<float>    eUni;
+    std::vector<uint8_t>  eFlags;
+    rb_lexicon            entries = *lx;
+    if (lx->single_word) {
+        eOff.push_back(0);
+        for (uint32_t w = 0; w < lx->n_words; ++w) {
+            const bool regular = !lx->word_regular || lx->word_regular[w];
+            for (int copy = 0; copy < (regular ? 1 : 2); ++copy) {
+                if (!regular)
+                    irrList.push_back((uint32_t)eWord.size());
+                eWord.push_back(w);
+                eFlags.push_back((uint8_t)((regular ? 1 : 0) | (copy ? 2 : 0)));
+                eUni.push_back(lx->unigram[w]);
+                eEmis.insert(eEmis.end(), lx->state_emission + lx->word_offsets[w], lx->state_emission + lx->word_offsets[w + 1]);
+                eTdp.insert(eTdp.end(), lx->state_tdp_model + lx->word_offsets[w], lx->state_tdp_model + lx->word_offsets[w + 1]);
+                eOff.push_back((uint32_t)eEmis.size());
+            }
+        }
+        entries.n_words         = (uint32_t)eWord.size();
+        entries.word_offsets    = eOff.data();
+        entries.state_emission  = eEmis.data();
+        entries.state_tdp_model = eTdp.data();
+        entries.unigram         = eUni.data();
+        lx                      = &entries;
+        h->single               = true;
+        h->nIrr                 = (uint32_t)irrList.size();
+    }
+    const uint32_t nStatesAll = lx->word_offsets[lx->n_words];
     auto fail = [&](int code) {
         delete h;
         return code;
@@ -603,14 +718,15 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
         return fail(RB_ERR_CUDA);
     }
     h->W          = lx->n_words;
-    h->nStates    = nStates;
+    h->nStates    = nStatesAll;
     h->nModels    = lx->n_models;
     h->entryModel = lx->entry_model;
     // register-resident kernel: per-state descriptor and the table of distinct transition penalties
     {
         const float           inf = std::numeric_limits<float>::infinity();
         std::vector<float>    values;
-        bool                  fits = lx->n_words <= (1u << (32 - kWordShift));
+        // (single-word recognition runs on the per-word kernel: two books and a choice of predecessor per entry)
+        bool                  fits = lx->n_words <= (1u << (32 - kWordShift)) && !h->single;
         auto valueOf = [&](float v) -> uint32_t {
             for (size_t i = 0; i < values.size(); ++i)
                 if (memcmp(&values[i], &v, 4) == 0)
@@ -622,7 +738,7 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
         };
         const uint32_t infIdx  = valueOf(inf);
         uint32_t       maxEmis = 0;
-        for (uint32_t s = 0; s < nStates; ++s)
+        for (uint32_t s = 0; s < nStatesAll; ++s)
             maxEmis = std::max(maxEmis, lx->state_emission[s]);
         h->maxEmis = maxEmis;  // kept for every lexicon: decode checks it against the width of the score rows
         fits = fits && maxEmis < 16384 && nStates <= (uint32_t)kThreads * 16;
@@ -680,9 +796,15 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
             }
         }
     }
+    if (h->single && (h->dFlags.upload(eFlags.data(), eFlags.size(), h->stream) != RB_OK ||
+                      h->dEntryWord.upload(eWord.data(), eWord.size(), h->stream) != RB_OK ||
+                      h->dIrrList.upload(irrList.data(), std::max<size_t>(irrList.size(), 1), h->stream) != RB_OK)) {
+        rb::set_error("lexicon upload failed");
+        return fail(RB_ERR_CUDA);
+    }
     if (h->dWordOff.upload(lx->word_offsets, lx->n_words + 1, h->stream) != RB_OK ||
-        h->dStateEmis.upload(lx->state_emission, nStates, h->stream) != RB_OK ||
-        h->dStateTdp.upload(lx->state_tdp_model, nStates, h->stream) != RB_OK ||
+        h->dStateEmis.upload(lx->state_emission, nStatesAll, h->stream) != RB_OK ||
+        h->dStateTdp.upload(lx->state_tdp_model, nStatesAll, h->stream) != RB_OK ||
         h->dTdp.upload(lx->tdp, (size_t)lx->n_models * 4, h->stream) != RB_OK ||
         h->dUnigram.upload(lx->unigram, lx->n_words, h->stream) != RB_OK ||
         cudaStreamSynchronize(h->stream) != cudaSuccess) {
@@ -779,6 +901,19 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
         p.books      = reinterpret_cast<int4*>(h->dBooks.p);
         p.nBooks     = h->dNBooks.p;
         p.endScore   = h->dEndScore.p;
+        p.single     = h->single ? 1 : 0;
+        p.flags      = h->dFlags.p;
+        p.entryWord  = h->dEntryWord.p;
+        p.irrList    = h->dIrrList.p;
+        p.nIrr       = h->nIrr;
+        p.irrBooks   = nullptr;
+        p.nIrrBooks  = nullptr;
+        if (h->single) {
+            RB_CHECK(h->dIrrBooks.reserve((size_t)T * 8));
+            RB_CHECK(h->dNIrrBooks.reserve((size_t)n_utt));
+            p.irrBooks  = reinterpret_cast<int4*>(h->dIrrBooks.p);
+            p.nIrrBooks = h->dNIrrBooks.p;
+        }
         const size_t smem = (stride * 3 + (size_t)h->W * 2 + (h->W + 1) + (size_t)h->nStates * 2) * 4;
         p.useSmem         = smem <= h->dev.smem_optin - 1024 ? 1 : 0;
         if (p.useSmem)
@@ -786,24 +921,16 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
         linear_search_kernel<<<n_utt, kThreads, p.useSmem ? smem : 0, s>>>(p);
     }
     RB_LAUNCH_CHECK();
-    h->bookScore.resize(T);
-    h->bookLm.resize(T);
-    h->bookWord.resize(T);
-    h->bookBkp.resize(T);
-    h->bookTime.resize(T);
     h->hostBooks.resize((size_t)T * 8);
     RB_CUDA(cudaMemcpyAsync(h->hostBooks.data(), h->dBooks.p, sizeof(int) * 8 * T, cudaMemcpyDeviceToHost, s));
     RB_CUDA(cudaMemcpyAsync(h->nBooks.data(), h->dNBooks.p, sizeof(int) * n_utt, cudaMemcpyDeviceToHost, s));
+    if (h->single) {
+        h->hostIrrBooks.resize((size_t)T * 8);
+        h->nIrrBooks.assign(n_utt, 0);
+        RB_CUDA(cudaMemcpyAsync(h->hostIrrBooks.data(), h->dIrrBooks.p, sizeof(int) * 8 * T, cudaMemcpyDeviceToHost, s));
+        RB_CUDA(cudaMemcpyAsync(h->nIrrBooks.data(), h->dNIrrBooks.p, sizeof(int) * n_utt, cudaMemcpyDeviceToHost, s));
+    }
     RB_CUDA(cudaStreamSynchronize(s));
-    for (int u = 0; u < n_utt; ++u)
-        for (int64_t b = h->frameOff[u], e = b + h->nBooks[u]; b < e; ++b) {
-            const int* r = h->hostBooks.data() + b * 8;
-            memcpy(&h->bookScore[b], r, 4);
-            memcpy(&h->bookLm[b], r + 1, 4);
-            h->bookWord[b] = r[2];
-            h->bookBkp[b]  = r[3];
-            h->bookTime[b] = r[4];
-        }
     return RB_OK;
 }
 
@@ -829,20 +956,21 @@ extern "C" long rb_search_traceback(const rb_search* h, int utt, uint32_t* words
         rb::set_error("no such segment in the last decode");
         return RB_ERR_INVALID;
     }
-    const int64_t    f0 = h->frameOff[utt];
-    std::vector<int> chain;
-    for (int b = h->nBooks[utt] - 1; b >= 0; b = h->bookBkp[f0 + b])
-        chain.push_back(b);
+    const int64_t           f0 = h->frameOff[utt];
+    std::vector<const int*> chain;  // records {score, lmScore, word, bkp, time, hadRegularWord, -, -}
+    for (int b = h->nBooks[utt] - 1; b != -1; b = h->record(f0, b)[3])
+        chain.push_back(h->record(f0, b));
     long n = 0;
     for (auto it = chain.rbegin(); it != chain.rend(); ++it, ++n) {
+        const int* r = *it;
         if (words)
-            words[n] = (uint32_t)h->bookWord[f0 + *it];
+            words[n] = (uint32_t)r[2];
         if (times)
-            times[n] = h->bookTime[f0 + *it];
+            times[n] = r[4];
         if (am_scores)
-            am_scores[n] = h->bookScore[f0 + *it];
+            memcpy(&am_scores[n], r, 4);
         if (lm_scores)
-            lm_scores[n] = h->bookLm[f0 + *it];
+            memcpy(&lm_scores[n], r + 1, 4);
     }
     return n;
 }
@@ -858,23 +986,24 @@ extern "C" long rb_search_traceback_all(const rb_search* h, int64_t* word_offset
     const int n_utt  = (int)h->nBooks.size();
     long      total  = 0;
     word_offsets[0]  = 0;
-    std::vector<int> chain;
+    std::vector<const int*> chain;
     for (int u = 0; u < n_utt; ++u) {
         const int64_t f0 = h->frameOff[u];
         chain.clear();
-        for (int b = h->nBooks[u] - 1; b >= 0; b = h->bookBkp[f0 + b])
-            chain.push_back(b);
+        for (int b = h->nBooks[u] - 1; b != -1; b = h->record(f0, b)[3])
+            chain.push_back(h->record(f0, b));
         for (auto it = chain.rbegin(); it != chain.rend(); ++it, ++total) {
             if (total >= capacity)
                 continue;
+            const int* r = *it;
             if (words)
-                words[total] = (uint32_t)h->bookWord[f0 + *it];
+                words[total] = (uint32_t)r[2];
             if (times)
-                times[total] = h->bookTime[f0 + *it];
+                times[total] = r[4];
             if (am_scores)
-                am_scores[total] = h->bookScore[f0 + *it];
+                memcpy(&am_scores[total], r, 4);
             if (lm_scores)
-                lm_scores[total] = h->bookLm[f0 + *it];
+                memcpy(&lm_scores[total], r + 1, 4);
         }
         word_offsets[u + 1] = total;
     }

@@ -10,7 +10,9 @@ from . import capi
 
 class LinearSearch:
     """lexicon: dict(word_offsets, state_emission, state_tdp_model, tdp [n_models x 4: loop, forward, skip, exit],
-    entry_model, unigram) -- see rasr_b200.synth.lexicon."""
+    entry_model, unigram[, word_regular, single_word]) -- see rasr_b200.synth.lexicon.  single_word = the
+    recognizer's "single-word-recognition" (the reference's default is true; here it must be asked for), word_regular
+    marks the lemmata with a non-empty evaluation sequence (0: silence / noise)."""
 
     def __init__(self, lexicon, device=0):
         self._a = dict(word_offsets=np.ascontiguousarray(lexicon["word_offsets"], np.uint32),
@@ -19,10 +21,16 @@ class LinearSearch:
                        tdp=np.ascontiguousarray(lexicon["tdp"], np.float32).reshape(-1, 4),
                        unigram=np.ascontiguousarray(lexicon["unigram"], np.float32))
         a = self._a
+        if lexicon.get("word_regular") is not None:
+            a["word_regular"] = np.ascontiguousarray(lexicon["word_regular"], np.uint8)
+            if a["word_regular"].size != a["unigram"].size:
+                raise ValueError("word_regular needs one flag per word")
         P = lambda x, t: x.ctypes.data_as(C.POINTER(t))
         c = capi.LexiconC(a["word_offsets"].size - 1, P(a["word_offsets"], C.c_uint32),
                           P(a["state_emission"], C.c_uint32), P(a["state_tdp_model"], C.c_uint32), a["tdp"].shape[0],
-                          P(a["tdp"], C.c_float), int(lexicon["entry_model"]), P(a["unigram"], C.c_float))
+                          P(a["tdp"], C.c_float), int(lexicon["entry_model"]), P(a["unigram"], C.c_float),
+                          P(a["word_regular"], C.c_uint8) if "word_regular" in a else None,
+                          int(bool(lexicon.get("single_word", False))))
         self._h = C.c_void_p()
         capi.check(capi.lib().rb_search_create(C.byref(c), int(device), C.byref(self._h)))
         self._fo = None

@@ -51,3 +51,18 @@ def diag():
 
     yield report
     f.close()
+
+
+@pytest.fixture(scope="session")
+def reference_search_golden():
+    """tests/golden/ref_search.npz: tracebacks of the reference's own LinearSearch (tests/golden/make_golden_search.py)"""
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_search.npz"))
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/")
+        cases.setdefault(name, {})[field] = z[key]
+    for c in cases.values():
+        c["entry_model"] = 0
+        c["single_word"] = bool(c["single_word"])
+    return cases

@@ -41,6 +41,66 @@ def test_kernel_variants_bit_exact(oracle, monkeypatch, n_words, min_s, max_s, e
         assert same(got[u], oracle.linear_search(lex, scores[fo[u]:fo[u + 1]])), u
 
 
+def irregular_lexicon(n_words, n_emis, seed, n_irregular, min_states=3, max_states=12):
+    """synth.lexicon with a one-state silence-like word in front and n_irregular noise words spread over the lexicon"""
+    lex = synth.lexicon(n_words, n_emis, min_states=min_states, max_states=max_states, seed=seed)
+    rng = np.random.default_rng(seed + 1000)
+    reg = np.ones(n_words, np.uint8)
+    reg[rng.choice(n_words, n_irregular, replace=False)] = 0
+    # silence: one state on the silence-like transition model, no LM score, irregular
+    lex["word_offsets"] = np.concatenate([[0], lex["word_offsets"] + 1]).astype(np.uint32)
+    lex["state_emission"] = np.concatenate([[n_emis - 1], lex["state_emission"]]).astype(np.uint32)
+    lex["state_tdp_model"] = np.concatenate([[2], lex["state_tdp_model"]]).astype(np.uint32)
+    lex["unigram"] = np.concatenate([[0.0], lex["unigram"]]).astype(np.float32)
+    lex["word_regular"] = np.concatenate([[0], reg]).astype(np.uint8)
+    lex["single_word"] = True
+    return lex
+
+
+@pytest.mark.parametrize("n_words,n_irr,min_s,max_s,quantised", [(60, 3, 3, 12, False), (700, 9, 3, 12, False),
+                                                                 (2100, 20, 3, 12, False), (300, 40, 1, 3, True),
+                                                                 (50, 50, 2, 5, True)])
+def test_single_word_recognition_bit_exact(oracle, n_words, n_irr, min_s, max_s, quantised):
+    """the recognizer's default mode (src/Search/LinearSearch.cc:26-30): a second book of irregular-only sequences,
+    irregular-chain entries, regular words restricted to one per sentence; lexicons held in shared memory and (2100
+    words) in global memory; quantised scores make ties in both book-keeping scans"""
+    lex = irregular_lexicon(n_words, 64, 31, n_irr, min_s, max_s)
+    rng = np.random.default_rng(31)
+    fo = np.array([0, 150, 151, 260], np.int64)
+    if quantised:
+        lex["unigram"] = np.round(lex["unigram"] * 2) / 2
+        scores = rng.integers(1, 6, (260, 64)).astype(np.float32)
+    else:
+        scores = (rng.random((260, 64)) * 25 + 2).astype(np.float32)
+    ls = search.LinearSearch(lex)
+    got = ls.decode(scores, fo)
+    for u in range(3):
+        want = oracle.linear_search(lex, scores[fo[u]:fo[u + 1]])
+        assert same(got[u], want), u
+        assert int(lex["word_regular"][want["words"]].sum()) <= 1
+        assert same(ls.traceback(u), got[u])
+    # the same lexicon in continuous mode: the flags are inert
+    lex["single_word"] = False
+    got = search.LinearSearch(lex).decode(scores, fo)
+    for u in range(3):
+        assert same(got[u], oracle.linear_search(lex, scores[fo[u]:fo[u + 1]])), u
+
+
+@pytest.mark.parametrize("name", ["continuous", "continuous_scaled", "single_word", "single_word_noise", "single_word_ties"])
+@pytest.mark.parametrize("env", [None, "RB_SEARCH_PER_WORD"])
+def test_reference_golden(monkeypatch, reference_search_golden, name, env):
+    """tracebacks written by the reference's own LinearSearch object code (tests/golden/make_golden_search.py)"""
+    if env:
+        monkeypatch.setenv(env, "1")
+    c = reference_search_golden[name]
+    got = search.LinearSearch(c).decode(c["scores"], c["frame_offsets"])
+    ro = c["result_offsets"]
+    for u in range(ro.size - 1):
+        a, b = int(ro[u]), int(ro[u + 1])
+        want = dict(words=c["words"][a:b], times=c["times"][a:b], am=c["am"][a:b], lm=c["lm"][a:b])
+        assert same(got[u], want), (name, u)
+
+
 def test_segments_are_independent_and_ties_resolve_like_the_reference(oracle):
     """several segments of different length in one call; quantised scores create exact ties between predecessors and
     between word ends, which must resolve as in the reference (first predecessor / first word in lexicon order)"""

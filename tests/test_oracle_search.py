@@ -103,3 +103,14 @@ def test_forced_path_kat(oracle):
     assert list(r["words"]) == [1, 0] and list(r["times"]) == [2, 4]
     assert r["am"][0] == np.float32(2.0) and r["lm"][0] == np.float32(0.25)
     assert r["am"][1] == np.float32(4.0) and r["lm"][1] == np.float32(0.75)
+
+
+@pytest.mark.parametrize("name", ["continuous", "continuous_scaled", "single_word", "single_word_noise", "single_word_ties"])
+def test_oracle_reproduces_reference_golden(oracle, reference_search_golden, name):
+    c = reference_search_golden[name]
+    fo, ro = c["frame_offsets"], c["result_offsets"]
+    for u in range(fo.size - 1):
+        got = oracle.linear_search(c, c["scores"][fo[u]:fo[u + 1]])
+        a, b = int(ro[u]), int(ro[u + 1])
+        assert np.array_equal(got["words"], c["words"][a:b]) and np.array_equal(got["times"], c["times"][a:b])
+        assert np.array_equal(got["am"], c["am"][a:b]) and np.array_equal(got["lm"], c["lm"][a:b])
