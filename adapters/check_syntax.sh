@@ -6,7 +6,7 @@
 REF=${1:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
 rc=0
-for f in B200FeatureScorer.cc B200MfccNode.cc B200NnNetwork.cc B200Nodes.cc Module.cc; do
+for f in B200FeatureScorer.cc B200MfccNode.cc B200NnNetwork.cc B200Nodes.cc B200LinearSearch.cc Module.cc; do
   g++ -fsyntax-only -std=gnu++20 -funsigned-char -I"$HERE/stubs" -I"$REF/src" -I"$HERE/../include" "$HERE/$f" || rc=1
 done
 exit $rc

@@ -290,20 +290,42 @@ def search_path():
     return os.path.join(_HERE, "_ref", "librasr_ref_search.so")
 
 
-def search_lib():
+def search_lib(global_scope=False):
+    """global_scope: needed before load_search_adapter() -- the adapter library resolves its RASR symbols (and the
+    inline statics of the reference's headers) against this library; do that in a process of its own, never next
+    to load_adapters()."""
     global _search
     if _search is None:
         if not os.path.exists(search_path()):
             build()
         # self-contained (its own copy of the strict objects and its own application object / configuration)
-        S = C.CDLL(search_path(), mode=C.RTLD_LOCAL)
+        S = C.CDLL(search_path(), mode=C.RTLD_GLOBAL if global_scope else C.RTLD_LOCAL)
         S.ref_last_error.restype = C.c_char_p
         S.ref_init(None)
         S.ref_search_create.restype = C.c_void_p
-        for f in ("ref_search_order", "ref_search_states", "ref_search_run"):
+        for f in ("ref_search_order", "ref_search_states", "ref_search_run", "ref_search_items"):
             getattr(S, f).restype = C.c_long
         _search = S
     return _search
+
+
+_search_adapter = None
+
+
+def load_search_adapter():
+    """oracle/_ref/libb200_search_adapter.so: adapters/B200LinearSearch.cc compiled against the reference's headers;
+    afterwards LinearSearch(..., adapter=True) drives it through the Search::SearchAlgorithm interface."""
+    global _search_adapter
+    if _search_adapter is None:
+        if _search is not None:
+            raise RuntimeError("load_search_adapter() must come before the first use of the search library")
+        S = search_lib(global_scope=True)
+        p = os.path.join(_HERE, "_ref", "libb200_search_adapter.so")
+        if not os.path.exists(p):
+            build()
+        _search_adapter = C.CDLL(p, mode=C.RTLD_GLOBAL)
+        _search_adapter.b200_search_adapter_register()
+    return _search_adapter
 
 
 def write_lexicon(path, n_phonemes, words, silence=True, silence_first=False, irregular=()):
@@ -342,7 +364,7 @@ class LinearSearch:
 
     def __init__(self, lexicon_file, emission_of, silence_emission, n_emissions, tdp, unigram, states_per_phone=3,
                  state_repetitions=1, lm_scale=1.0, tdp_scale=1.0, pronunciation_scale=0.0, single_word=False,
-                 scratch_dir="/tmp"):
+                 scratch_dir="/tmp", adapter=False):
         S = search_lib()
         LinearSearch._count += 1
         sel = "search-%d-%d" % (os.getpid(), LinearSearch._count)
@@ -367,7 +389,7 @@ class LinearSearch:
         self.n_emissions = int(n_emissions)
         self._S = S
         self._h = S.ref_search_create(sel.encode(), _p(self._emis), int(states_per_phone), int(silence_emission),
-                                      self.n_emissions, _p(self._uni), int(self._uni.size))
+                                      self.n_emissions, _p(self._uni), int(self._uni.size), int(bool(adapter)))
         if not self._h:
             raise RuntimeError("reference LinearSearch could not be set up: %s" % S.ref_last_error().decode())
         self._h = C.c_void_p(self._h)
@@ -404,6 +426,13 @@ class LinearSearch:
         n = self._S.ref_search_run(self._h, _p(scores), C.c_long(T), self.n_emissions, _p(words), _p(times), _p(am),
                                    _p(lm), C.c_long(cap), _p(fin))
         return words[:n].copy(), times[:n].copy(), am[:n].copy(), lm[:n].copy(), fin
+
+    def items(self, capacity=4096):
+        """every item of getCurrentBestSentence after run(): (word or -2, time, acoustic, lm) arrays"""
+        w, t = np.empty(capacity, np.int32), np.empty(capacity, np.int32)
+        a, l = np.empty(capacity, np.float32), np.empty(capacity, np.float32)
+        n = self._S.ref_search_items(self._h, _p(w), _p(t), _p(a), _p(l), C.c_long(capacity))
+        return w[:n].copy(), t[:n].copy(), a[:n].copy(), l[:n].copy()
 
     def close(self):
         if self._h:

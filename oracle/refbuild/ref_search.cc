@@ -241,12 +241,17 @@ public:
     }
 };
 
+// an alternative Search::SearchAlgorithm to drive instead of the reference's (the adapter of adapters/B200LinearSearch.cc
+// registers itself here when oracle/_ref/libb200_search_adapter.so is loaded)
+typedef Search::SearchAlgorithm* (*SearchFactory)(const Core::Configuration&);
+SearchFactory alternativeFactory = 0;
+
 struct SearchHandle {
     Core::Configuration                 config;
     Bliss::LexiconRef                   lexicon;
     Core::Ref<TableAcousticModel>       am;
     Core::Ref<Lm::ScaledLanguageModel>  lm;
-    Search::LinearSearch*               search = 0;
+    Search::SearchAlgorithm*            search = 0;
     std::vector<int32_t>                order;  // lemma-pronunciation order of the lexicon, as word numbers
 };
 
@@ -261,8 +266,13 @@ extern "C" {
  *   <sel>.lm.scale, <sel>.pronunciation-scale
  * emission_of[k * states_per_phone + s]: emission of state s of phoneme p<k>; silence_emission: of "si".
  * unigram[k]: unscaled LM score of the syntactic token w<k>. */
+void ref_search_set_factory(void* factory) {
+    alternativeFactory = (SearchFactory)factory;
+}
+
+/* alternative = 0: the reference's Search::LinearSearch; 1: the algorithm of ref_search_set_factory */
 void* ref_search_create(const char* selection, const int32_t* emission_of, int states_per_phone,
-                        int silence_emission, int n_emissions, const float* unigram, int n_unigram) {
+                        int silence_emission, int n_emissions, const float* unigram, int n_unigram, int alternative) {
     ref_init(0);
     SearchHandle* h = new SearchHandle();
     h->config       = Core::Configuration(Core::Application::us()->getConfiguration(), selection ? selection : "search");
@@ -276,7 +286,12 @@ void* ref_search_create(const char* selection, const int32_t* emission_of, int s
     Core::Configuration      lmc(h->config, "lm");
     Core::Ref<Lm::LanguageModel> table(new TableLm(lmc, h->lexicon, unigram, n_unigram));
     h->lm     = Core::ref(new Lm::LanguageModelScaling(lmc, table));
-    h->search = new Search::LinearSearch(Core::Configuration(h->config, "recognizer"));
+    if (alternative && !alternativeFactory) {
+        delete h;
+        return 0;
+    }
+    h->search = alternative ? alternativeFactory(Core::Configuration(h->config, "recognizer"))
+                            : new Search::LinearSearch(Core::Configuration(h->config, "recognizer"));
     Speech::ModelCombination mc(h->config, h->lexicon, h->am, h->lm);
     if (!h->search->setModelCombination(mc)) {
         delete h->search;
@@ -336,6 +351,21 @@ void ref_search_tdps(void* handle, float* out) {
     for (int t = 0; t < 5; ++t)
         for (int k = 0; k < 4; ++k)
             out[t * 4 + k] = (*h->am->stateTransition(t))[k];
+}
+
+/* every item of the traceback as getCurrentBestSentence returns it (after ref_search_run): word number (-2 for the
+ * items without a pronunciation), time, acoustic and lm score */
+long ref_search_items(void* handle, int32_t* words, int32_t* times, float* am, float* lm, long capacity) {
+    SearchHandle*     h = (SearchHandle*)handle;
+    Search::Traceback tb;
+    h->search->getCurrentBestSentence(tb);
+    for (size_t i = 0; i < tb.size() && (long)i < capacity; ++i) {
+        words[i] = tb[i].pronunciation ? indexOfSymbol(tb[i].pronunciation->lemma()->preferredOrthographicForm().str()) : -2;
+        times[i] = (int32_t)tb[i].time;
+        am[i]    = tb[i].score.acoustic;
+        lm[i]    = tb[i].score.lm;
+    }
+    return (long)tb.size();
 }
 
 /* restart, feed every row of scores [T x n_emissions], getCurrentBestSentence.  Outputs (capacity each): the

@@ -1,0 +1,16 @@
+/*
+ * search_adapter_register.cc -- makes the Search::SearchAlgorithm adapter (adapters/B200LinearSearch.cc) known to the
+ * test host of ref_search.cc; a RASR checkout adds one case to Search::Module_::createRecognizer instead
+ * (src/Search/Module.cc:88-110).  TEST INFRASTRUCTURE ONLY; contains no reference code.
+ */
+#include "../../adapters/B200LinearSearch.hh"
+
+extern "C" void ref_search_set_factory(void* factory);
+
+static Search::SearchAlgorithm* makeB200LinearSearch(const Core::Configuration& c) {
+    return new B200::LinearSearch(c);
+}
+
+extern "C" void b200_search_adapter_register() {
+    ref_search_set_factory((void*)&makeB200LinearSearch);
+}

@@ -282,3 +282,27 @@ def test_audio_to_scores_node(ref, oms, tmp_path, diag):
     rel = float((np.abs(got["feats"] - want) / np.abs(want)).max())
     diag("adapter_audio_scorer_node", rel=rel)
     assert rel < RTOL
+
+
+def test_linear_search_adapter_next_to_the_reference_search(diag):
+    """adapters/B200LinearSearch.cc (Search::SearchAlgorithm over rb_search_*) and the reference's own
+    Search::LinearSearch, both set up by the reference's lexicon parser / acoustic model parts / LM scaling from one
+    lexicon file and fed the same scorer objects: every traceback item bit-identical, continuous and single-word
+    recognition.  In a process of its own (tests/search_adapter_host.py): the search host is a second copy of the
+    reference's object code and must not share a symbol scope with the one the tests above loaded."""
+    import json
+    import subprocess
+    import sys
+
+    from oracle import pyref
+    need = [pyref.search_path(), os.path.join(ROOT, "oracle", "_ref", "libb200_search_adapter.so")]
+    missing = [p for p in need if not os.path.exists(p)]
+    if missing and not os.path.isdir(pyref.REFERENCE):
+        pytest.fail("%s missing: build them where the reference checkout is (python __graft_entry__.py)" % missing)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "search_adapter_host.py")], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["ok"], out
+    assert set(out["items"]) == {"continuous", "continuous_scaled", "single_word", "single_word_noise", "single_word_ties"}
+    diag("search_adapter_in_reference_host", **{k: int(v) for k, v in out["items"].items()})
