@@ -1,6 +1,6 @@
 /*
  * B200::LinearSearch -- Search::SearchAlgorithm adapter that forwards to the score consumer of librasr_b200.so
- * (rb_search_*, include/rasr_b200.h): the drop-in for Search::LinearSearch (src/Search/LinearSearch.{hh,cc}).
+ * (the rb_search calls of include/rasr_b200.h): the drop-in for Search::LinearSearch (src/Search/LinearSearch.{hh,cc}).
  *
  * Written against the RASR headers (src/Search/Search.hh:39-150); compiled inside a RASR checkout.
  * setModelCombination() flattens lexicon + acoustic model + language model into the arrays of rb_lexicon the way
