@@ -476,6 +476,38 @@ class Bench:
             # three stages, tracebacks to the host
             w["e2e"] = lambda: pipeline.search_utterances(fe, scorer, ls, h_pcm, offs, pcm_channels=1)
             w["e2e_pageable"] = lambda: pipeline.search_utterances(fe, scorer, ls, pcm, offs, pcm_channels=1)
+
+            def search_alone():
+                """the search kernel by itself on the resident score matrix: continuous recognition (the lexicon
+                above) and the recognizer's default single-word recognition (the same words + a silence word, 2 %
+                of the words irregular)"""
+                lex = synth.lexicon(1000, 256)
+                rs = np.random.default_rng(5)
+                single = dict(lex, single_word=True)
+                single["word_offsets"] = np.concatenate([[0], lex["word_offsets"] + 1]).astype(np.uint32)
+                single["state_emission"] = np.concatenate([[255], lex["state_emission"]]).astype(np.uint32)
+                single["state_tdp_model"] = np.concatenate([[2], lex["state_tdp_model"]]).astype(np.uint32)
+                single["unigram"] = np.concatenate([[0.0], lex["unigram"]]).astype(np.float32)
+                reg = np.ones(1001, np.uint8)
+                reg[0] = 0
+                reg[1 + rs.choice(1000, 20, replace=False)] = 0
+                single["word_regular"] = reg
+                out = {}
+                for name, obj in (("continuous", ls), ("single_word", search.LinearSearch(single, device=local_rank))):
+                    for _ in range(2):
+                        obj.decode_dev(d_scores, 256, fo, sptr, want_result=False)
+                    tev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    tev[0].record(self.stream)
+                    for _ in range(5):
+                        obj.decode_dev(d_scores, 256, fo, sptr, want_result=False)
+                    tev[1].record(self.stream)
+                    torch.cuda.synchronize()
+                    ms = tev[0].elapsed_time(tev[1]) / 5
+                    out[name] = dict(ms=ms, us_per_frame_and_segment=ms * 1e3 / 1000.0,
+                                     frames_per_s=T / (ms * 1e-3))
+                return out
+
+            w["post"] = ("search_kernel_alone", search_alone)
             w.update(step=step, h2d=samples_h.size * 2, d2h=T * 20, units=T, algo_bytes=ALGO_BYTES_PER_FRAME["pipeline"] * T,
                      bound="hbm", dtype="f32", keep=(fe, scorer, ls, d_samples, d_feats, d_scores),
                      workload="C5: audio -> MFCC -> GMM scores -> LinearSearch (1000 words), %d utterances x 1000 frames "
@@ -652,9 +684,12 @@ class Bench:
         if os.path.exists(tpath):
             roof["traffic"] = json.load(open(tpath)).get(wl)  # dram bytes per launch (ncu, profiles/)
             roof["algorithmic_bytes"] = int(w["algo_bytes"])
-        return dict(value=value, unit=UNIT, ms_per_step=ms_per_step, steps=steps, warmup=warmup, dtype=w["dtype"],
-                    config=dict(workload=w["workload"], wall_ms_per_step=wall_ms), e2e=e2e, gpu_launches=int(launches),
-                    clocks=clocks, roofline=roof, dev_ms=dev_ms)
+        res = dict(value=value, unit=UNIT, ms_per_step=ms_per_step, steps=steps, warmup=warmup, dtype=w["dtype"],
+                   config=dict(workload=w["workload"], wall_ms_per_step=wall_ms), e2e=e2e, gpu_launches=int(launches),
+                   clocks=clocks, roofline=roof, dev_ms=dev_ms)
+        if w.get("post"):
+            res[w["post"][0]] = w["post"][1]()
+        return res
 
     # other formulations of the C2 scorer, timed the same way on the same buffers and reported beside the headline:
     #   batch-tensor        RB_GMM_BATCH_TENSOR, 1e-4 relative instead of bit-identical
@@ -883,6 +918,8 @@ def main():
                 e2e=m["e2e"], gpu_launches=m["gpu_launches"], clocks=m["clocks"], roofline=m["roofline"])
     if variants:
         line["variants"] = variants
+    if "search_kernel_alone" in m:
+        line["search_kernel_alone"] = m["search_kernel_alone"]
     del w
 
     # ---------------- the other BASELINE configs (C3, C4, C5) in the same driver-run record

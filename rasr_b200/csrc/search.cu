@@ -322,7 +322,10 @@ constexpr uint32_t kFirst = 1u, kSecond = 2u, kLast = 1u << 17, kWordShift = 18,
 
 struct SmemLayout {  // byte offsets into the dynamic shared memory of the register-resident kernel
     uint32_t xch, end, rows, uni, exit, bkLm, total;
-    SmemLayout(uint32_t nWarps, uint32_t W, uint32_t rowFloats, uint32_t maxT) {
+    uint32_t flags, irrSlot, irrEnd, irrList, irrLm, bkHad;  // single-word recognition only
+    uint32_t endBuffers;  // 2: the word ends are double-buffered by frame parity (any warp may read them after the barrier)
+    SmemLayout(uint32_t nWarps, uint32_t W, uint32_t rowFloats, uint32_t maxT, bool single = false, uint32_t nIrr = 0,
+               uint32_t endBuf = 1) {
         uint32_t o = 128;
         auto take = [&](uint32_t bytes) {
             const uint32_t at = o;
@@ -330,11 +333,21 @@ struct SmemLayout {  // byte offsets into the dynamic shared memory of the regis
             return at;
         };
         xch   = take(2 * nWarps * 16);
-        end   = take(W * 8);
+        endBuffers = endBuf;
+        end   = take(W * 8 * endBuf);
         rows  = take(2 * rowFloats * 4);
         uni   = take(W * 4);
         exit  = take(W * 4);
         bkLm  = take(maxT * 4);
+        flags = irrSlot = irrEnd = irrList = irrLm = bkHad = 0;
+        if (single) {
+            flags   = take(W);
+            irrSlot = take(W * 2);
+            irrEnd  = take(2 * (nIrr + 1) * 8);
+            irrList = take((nIrr + 1) * 4);
+            irrLm   = take(maxT * 4);
+            bkHad   = take(maxT);
+        }
         total = o;
     }
     SmemLayout() = default;
@@ -350,12 +363,19 @@ struct SearchParams2 {
     const uint32_t* warpWords; // [nWarps + 1] words whose last state lives in warp i: [warpWords[i], warpWords[i + 1])
     float           maxAbsUni;
     uint32_t        W, maxT, rowFloats, nStates;  // rowFloats: nEmis rounded up to 4
-    int             forceScan;           // test hook: always replay the sequential scan
+    int             forceScan;           // test hook: 1 = never take the unique-minimum shortcut, 2 = and use the warp-0 replay
     const float*    scores;
     const int64_t*  frameOff;
     int             nEmis;
     int4*           books;
     int*            nBooks;
+    // single-word recognition (the "words" are then the entries of the search, see SearchParams)
+    const uint8_t*  flags;
+    const uint32_t* entryWord;
+    const uint32_t* irrList;
+    uint32_t        nIrr;
+    int4*           irrBooks;
+    int*            nIrrBooks;
 };
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* g) {
@@ -376,7 +396,11 @@ __device__ __forceinline__ float key_float(uint32_t k) {
     return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
 }
 
-template<int NPT>
+//  * SINGLE (single-word recognition, :248-258, 355-370, 390-395): every warp also tracks the newest entry of the
+//    irregular book in registers; a word start picks its predecessor book by the entry's flags; the word ends of the
+//    (few) irregular entries are mirrored into a slot array double-buffered by frame parity, over which every warp
+//    replays the second, irregular-only book-keeping scan exactly after the frame's barrier.
+template<int NPT, bool SINGLE>
 __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const SearchParams2 p) {
     extern __shared__ __align__(128) unsigned char smemReg[];
     const uint32_t nThreads = blockDim.x, nWarps = nThreads / 32;
@@ -388,6 +412,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
     float*  sUni  = reinterpret_cast<float*>(smemReg + p.lay.uni);       // [W]
     float*  sExit = reinterpret_cast<float*>(smemReg + p.lay.exit);      // [W]
     float*  sBkLm = reinterpret_cast<float*>(smemReg + p.lay.bkLm);      // [maxT] lmScore of the book entries
+    uint8_t*  sFlags   = smemReg + p.lay.flags;                               // [W] bit 0 regular, bit 1 irregular chain
+    uint16_t* sIrrSlot = reinterpret_cast<uint16_t*>(smemReg + p.lay.irrSlot);  // [W] position in irrList, 0xffff: regular
+    float2*   sIrrEnd  = reinterpret_cast<float2*>(smemReg + p.lay.irrEnd);   // [2][nIrr + 1] word ends of the irregular entries
+    uint32_t* sIrrList = reinterpret_cast<uint32_t*>(smemReg + p.lay.irrList);  // [nIrr]
+    float*    sIrrLm   = reinterpret_cast<float*>(smemReg + p.lay.irrLm);     // [maxT] lmScore of the irregular book's entries
+    uint8_t*  sBkHad   = smemReg + p.lay.bkHad;                               // [maxT] Book::hadRegularWord
     // per warp and frame parity: best word end of the warp's words {min key, second key, word, lmScore}, its bkp
     __shared__ uint4 wInfo[2][32];
     __shared__ int   wBkp[2][32];
@@ -415,6 +445,18 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
     for (uint32_t i = tid; i < p.W; i += nThreads) {
         sUni[i]  = p.unigram[i];
         sExit[i] = p.wordExit[i];
+        if (SINGLE) {
+            sFlags[i]   = p.flags[i];
+            sIrrSlot[i] = 0xffffu;
+        }
+    }
+    if (SINGLE) {
+        __syncthreads();
+        for (uint32_t i = tid; i < p.nIrr; i += nThreads) {
+            const uint32_t w = p.irrList[i];
+            sIrrList[i] = w;
+            sIrrSlot[w] = (uint16_t)i;
+        }
     }
     // this thread's states; the words whose LAST state lives in this warp are a contiguous range
     const uint32_t i0 = (uint32_t)tid * NPT;
@@ -440,21 +482,32 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
     // the newest book entry: every warp tracks it in registers (the book keeping below is evaluated by all warps)
     int   last      = -1;
     float lastScore = 0.0f, lastLm = 0.0f;  // 0 before the first entry
+    int   lastHad   = 0;                    // Book::hadRegularWord of the newest entry
+    int   irrLast   = -1;                   // the newest entry of the irregular book
+    float irrScore = 0.0f, irrLm = 0.0f;
     cp_async_wait_all();
     __syncthreads();
     const unsigned char* sTb = reinterpret_cast<const unsigned char*>(sT);
     // lmScore of a hypothesis that came from book entry bk (the newest entry is not read from shared memory: it was
-    // written after the last barrier)
+    // written after the last barrier); bk <= -2 names entry -2 - bk of the irregular book
     auto lm_of = [&](uint32_t w, int bk) {
         const float un = sUni[w];
+        if (SINGLE && bk <= -2)
+            return __fadd_rn(un, -2 - bk == irrLast ? irrLm : sIrrLm[-2 - bk]);
         return bk >= 0 ? __fadd_rn(un, bk == last ? lastLm : sBkLm[bk]) : un;
     };
+    auto had_of = [&](int bk) -> int { return bk >= 0 ? (bk == last ? lastHad : (int)sBkHad[bk]) : 0; };
 
     for (int t = 1; t <= T; ++t) {
         const int par = t & 1;  // score row and boundary states of this frame are in buffer par
         if (t < T)
             prefetch_row(t + 1);
         const unsigned char* row = reinterpret_cast<const unsigned char*>(rows + par * p.rowFloats);
+        float2* sEndT = sEnd + (p.lay.endBuffers == 2 ? par * p.W : 0u);  // this frame's word ends
+        // single-word recognition, uniform over the frame: the flag bits that send a word start to the irregular book
+        // (bit 1: irregular-chain entry; bit 0: regular word, once the main book's newest entry holds a regular word)
+        const uint32_t irrSelect = 2u | ((last >= 0 && lastHad) ? 1u : 0u);
+        const int      irrRef    = irrLast >= 0 ? -2 - irrLast : -1;
         {
             // previous-frame values of the two states left of my block
             float pS2 = __shfl_up_sync(0xffffffffu, hs[NPT - 2], 1), pS1 = __shfl_up_sync(0xffffffffu, hs[NPT - 1], 1);
@@ -473,10 +526,21 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
                 const float    tLoop = *reinterpret_cast<const float*>(sTb + (m & 0x7cu));
                 const float    tFwd  = *reinterpret_cast<const float*>(sTb + ((m >> 5) & 0x7cu));
                 const float    tSkip = *reinterpret_cast<const float*>(sTb + ((m >> 10) & 0x7cu));
-                // word start (:271-290): from the newest book entry, or from scratch
-                const float uni  = sUni[w];
-                const float h0lm = last >= 0 ? __fadd_rn(uni, lastLm) : uni;
-                const float h0s  = __fadd_rn(lastScore, h0lm);
+                // word start (:248-290): from the newest book entry, or from scratch; in single-word recognition a
+                // regular word behind a regular word, and every irregular-chain entry, starts from the irregular book
+                const float uni = sUni[w];
+                int         from = last;
+                float       fromScore = lastScore, fromLm = lastLm;
+                // byte offset of the state's emission in the score row; its two low bits carry the entry's flags
+                const uint32_t eo = (k & 1) ? emOff[k / 2] >> 16 : emOff[k / 2] & 0xffffu;
+                if (SINGLE) {
+                    const bool useIrr = (eo & irrSelect) != 0;  // chain entry, or regular word behind a regular word
+                    from      = useIrr ? irrRef : last;
+                    fromScore = useIrr ? irrScore : lastScore;
+                    fromLm    = useIrr ? irrLm : lastLm;
+                }
+                const float h0lm = from != -1 ? __fadd_rn(uni, fromLm) : uni;
+                const float h0s  = __fadd_rn(fromScore, h0lm);
                 const bool  first = m & kFirst, second = m & kSecond;
                 // predecessors in the reference's order pre = sta-2, sta-1, sta (the first strictly smaller one wins)
                 float s1 = k >= 1 ? hs[k >= 1 ? k - 1 : 0] : pS1;
@@ -484,9 +548,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
                 float s2 = k >= 2 ? hs[k >= 2 ? k - 2 : 0] : (k == 1 ? pS1 : pS2);
                 int   b2 = k >= 2 ? hb[k >= 2 ? k - 2 : 0] : (k == 1 ? pB1 : pB2);
                 s1 = first ? h0s : s1;
-                b1 = first ? last : b1;
+                b1 = first ? from : b1;
                 s2 = second ? h0s : s2;
-                b2 = second ? last : b2;
+                b2 = second ? from : b2;
                 const float c2 = __fadd_rn(s2, tSkip), c1 = __fadd_rn(s1, tFwd), c0 = __fadd_rn(hs[k], tLoop);
                 const bool  t2 = c2 < FLT_MAX;
                 float       bestS = t2 ? c2 : FLT_MAX;
@@ -497,11 +561,15 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
                 const bool t0 = c0 < bestS;
                 bestS = t0 ? c0 : bestS;
                 bestB = t0 ? hb[k] : bestB;
-                const float e = *reinterpret_cast<const float*>(row + ((k & 1) ? emOff[k / 2] >> 16 : emOff[k / 2] & 0xffffu));
+                const float e = *reinterpret_cast<const float*>(row + (SINGLE ? eo & 0xfffcu : eo));
                 hs[k] = __fadd_rn(bestS, e);
                 hb[k] = bestB;
-                if (m & kLast)  // word end candidate (:400-404)
-                    sEnd[w] = make_float2(__fadd_rn(hs[k], sExit[w]), __int_as_float(bestB));
+                if (m & kLast) {  // word end candidate (:400-404)
+                    const float2 en = make_float2(__fadd_rn(hs[k], sExit[w]), __int_as_float(bestB));
+                    sEndT[w] = en;
+                    if (SINGLE && !(eo & 1u))  // an irregular entry: mirror its word end into its slot
+                        sIrrEnd[par * (p.nIrr + 1) + sIrrSlot[w]] = en;
+                }
             }
             if (lane == 31)  // publish my last two states for the next warp's next frame
                 xch[(par ^ 1) * nWarps + warp] =
@@ -517,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
                 const uint32_t w  = c + lane;
                 float2         en = make_float2(FLT_MAX, __int_as_float(-1));
                 if (w < wordB)
-                    en = sEnd[w];
+                    en = sEndT[w];
                 const uint32_t key = w < wordB ? float_key(en.x) : 0xffffffffu;
                 const uint32_t m1  = __reduce_min_sync(0xffffffffu, key);
                 const int      i1  = __ffs(__ballot_sync(0xffffffffu, key == m1)) - 1;
@@ -551,9 +619,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
             }
             const uint32_t kM  = __reduce_min_sync(0xffffffffu, best.x);
             const int      lj  = __ffs(__ballot_sync(0xffffffffu, best.x == kM)) - 1;
-            const uint32_t kM2 = __reduce_min_sync(0xffffffffu, lane == lj ? best.y : best.x);
-            const float    M = key_float(kM), M2 = key_float(kM2);
+            const uint32_t kMo = __reduce_min_sync(0xffffffffu, lane == lj ? 0xffffffffu : best.x);  // best of the other warps
+            const uint32_t kM2 = min(kMo, __shfl_sync(0xffffffffu, best.y, lj));
+            const float    M = key_float(kM), M2 = key_float(kM2), Mo = key_float(kMo);
             const float    slack = __fmul_rn(__fadd_rn(fabsf(M), __fadd_rn(p.maxAbsUni, sMaxLm[par])), 4.76837158203125e-07f);
+            // the words of warps [first, ...) selected by warpMask, exactly as the reference scans them
+            uint32_t warpMask = 0u;
             if (!p.forceScan && M2 > __fadd_rn(M, slack)) {
                 if (M < FLT_MAX) {  // the scan accepts the unique minimum last
                     nbWord  = (int)__shfl_sync(0xffffffffu, best.z, lj);
@@ -562,8 +633,64 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
                     nbScore = __fsub_rn(M, nbLm);
                 }
             }
-            else {
-                // ties / near ties: warp 0 replays the sequential scan over the words, 32 at a time
+            else if (p.lay.endBuffers == 2 && p.forceScan < 2) {
+                // Ties / near ties.  If every word OUTSIDE warp lj's range of n words is above M + K slack, K = n / 4 + 2,
+                // the scan over that range alone, started from scratch, ends in the reference's state.  The reference
+                // enters the range with a threshold t_in > M + K slack - e (only far words were accepted; e <= slack / 4
+                // bounds the rounding of g_w above).  While the two scans disagree, a word accepted by one of them only
+                // was rejected by the lower threshold, so the lower of the two thresholds falls by at most e per word
+                // and stays above M + e over the n words; a word accepted by both makes them identical from there on,
+                // and the first word holding M is such a word.  Behind the range the threshold is at most M + e and no
+                // far word beats it.  (Typical: an irregular word and its irregular-chain copy with equal scores.)
+                const float nLj = (float)(p.warpWords[lj + 1] - p.warpWords[lj]);
+                const float far = __fmul_rn(slack, __fadd_rn(__fmul_rn(nLj, 0.25f), 2.0f));
+                warpMask = (p.forceScan < 1 && Mo > __fadd_rn(M, far)) ? (1u << lj) : 0xffffffffu;
+            }
+            if (warpMask) {
+                // ties / near ties: the sequential scan, exactly, by EVERY warp and without a second barrier (the word
+                // ends are double-buffered).  A warp's words can only be accepted if its smallest candidate beats the
+                // running threshold (cand >= min >= thr rejects them all and leaves the threshold as it is), so the
+                // scan visits only the "record-breaking" warps in order -- a handful -- and replays their words.
+                const float myMin = (uint32_t)lane < nWarps ? key_float(best.x) : FLT_MAX;  // warps without words: NaN
+                uint32_t    nextWarps = warpMask;
+                while (true) {
+                    const float    thr0  = __fadd_rn(nbScore, nbLm);
+                    const uint32_t hitsW = __ballot_sync(0xffffffffu, myMin < thr0) & nextWarps;
+                    if (!hitsW)
+                        break;
+                    const int wi = __ffs(hitsW) - 1;
+                    nextWarps    = wi == 31 ? 0u : (0xffffffffu << (wi + 1));
+                    const uint32_t a = p.warpWords[wi], b = p.warpWords[wi + 1];
+#pragma unroll 1
+                    for (uint32_t base = a; base < b; base += 32) {
+                        const uint32_t w    = base + lane;
+                        float          cand = FLT_MAX, lmw = 0.0f;
+                        int            bk   = -1;
+                        if (w < b) {
+                            const float2 en = sEndT[w];
+                            bk   = __float_as_int(en.y);
+                            cand = en.x;
+                            lmw  = lm_of(w, bk);
+                        }
+                        uint32_t todo = 0xffffffffu;
+                        while (true) {
+                            const float    thr  = __fadd_rn(nbScore, nbLm);
+                            const uint32_t hits = __ballot_sync(0xffffffffu, cand < thr) & todo;
+                            if (!hits)
+                                break;
+                            const int   first    = __ffs(hits) - 1;
+                            const float tmpScore = __shfl_sync(0xffffffffu, cand, first);
+                            nbLm    = __shfl_sync(0xffffffffu, lmw, first);
+                            nbBkp   = __shfl_sync(0xffffffffu, bk, first);
+                            nbScore = __fsub_rn(tmpScore, nbLm);
+                            nbWord  = (int)(base + first);
+                            todo    = first == 31 ? 0u : (0xffffffffu << (first + 1));
+                        }
+                    }
+                }
+            }
+            else if (p.forceScan || !(M2 > __fadd_rn(M, slack))) {
+                // (lexicons whose word ends do not fit twice) warp 0 replays the sequential scan over the words, 32 at a time
                 if (warp == 0) {
 #pragma unroll 1
                     for (uint32_t base = 0; base < p.W; base += 32) {
@@ -571,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
                         float          cand = FLT_MAX, lmw = 0.0f;
                         int            bk   = -1;
                         if (w < p.W) {
-                            const float2 en = sEnd[w];
+                            const float2 en = sEndT[w];
                             bk   = __float_as_int(en.y);
                             cand = en.x;
                             lmw  = lm_of(w, bk);
@@ -604,23 +731,85 @@ __global__ void __launch_bounds__(kThreads, 1) linear_search_reg_kernel(const Se
                 nbWord  = __float_as_int(sReplay[2]);
                 nbBkp   = __float_as_int(sReplay[3]);
             }
+            // the second book (:355-370): the exact scan over the irregular entries whose history holds no regular
+            // word, replayed by every warp (they all keep the newest entries in registers); evaluated on the state
+            // BEFORE the main book's new entry is appended, like the reference (both scans see this frame's hypotheses)
+            float ibScore = FLT_MAX, ibLm = 0.0f;
+            int   ibWord = -1, ibBkp = -1;
+            if (SINGLE) {
+#pragma unroll 1
+                for (uint32_t base = 0; base < p.nIrr; base += 32) {
+                    const uint32_t i    = base + lane;
+                    float          cand = FLT_MAX, lmw = 0.0f;
+                    int            bk   = -1;
+                    uint32_t       w    = 0;
+                    if (i < p.nIrr) {
+                        const float2 en = sIrrEnd[par * (p.nIrr + 1) + i];
+                        w  = sIrrList[i];
+                        bk = __float_as_int(en.y);
+                        if (!had_of(bk)) {
+                            cand = en.x;
+                            lmw  = lm_of(w, bk);
+                        }
+                    }
+                    uint32_t todo = 0xffffffffu;
+                    while (true) {
+                        const float    thr  = __fadd_rn(ibScore, ibLm);
+                        const uint32_t hits = __ballot_sync(0xffffffffu, cand < thr) & todo;
+                        if (!hits)
+                            break;
+                        const int   first    = __ffs(hits) - 1;
+                        const float tmpScore = __shfl_sync(0xffffffffu, cand, first);
+                        ibLm    = __shfl_sync(0xffffffffu, lmw, first);
+                        ibBkp   = __shfl_sync(0xffffffffu, bk, first);
+                        ibWord  = (int)__shfl_sync(0xffffffffu, w, first);
+                        ibScore = __fsub_rn(tmpScore, ibLm);
+                        todo    = first == 31 ? 0u : (0xffffffffu << (first + 1));
+                    }
+                }
+            }
             if (nbScore != FLT_MAX) {
+                int had = 0;
+                if (SINGLE)
+                    had = (sFlags[nbWord] & 1u) ? 1 : had_of(nbBkp);  // before `last` moves on
                 ++last;  // entries are only ever appended: the newest is the last
                 if (tid == 0) {
                     int4* books = p.books + 2 * (f0 + last);
-                    books[0] = make_int4(__float_as_int(nbScore), __float_as_int(nbLm), nbWord, nbBkp);
-                    books[1] = make_int4(t, 0, 0, 0);
+                    books[0] = make_int4(__float_as_int(nbScore), __float_as_int(nbLm),
+                                         SINGLE ? (int)p.entryWord[nbWord] : nbWord, nbBkp);
+                    books[1] = make_int4(t, had, 0, 0);
                     sBkLm[last] = nbLm;
+                    if (SINGLE)
+                        sBkHad[last] = (uint8_t)had;
                 }
                 lastScore = nbScore;
                 lastLm    = nbLm;
+                lastHad   = had;
             }
-            if (tid == 0)  // read by every warp after the next barrier
-                sMaxLm[par ^ 1] = nbScore != FLT_MAX ? fmaxf(sMaxLm[par], fabsf(nbLm)) : sMaxLm[par];
+            if (SINGLE && ibScore != FLT_MAX) {
+                ++irrLast;
+                if (tid == 0) {
+                    int4* books = p.irrBooks + 2 * (f0 + irrLast);
+                    books[0] = make_int4(__float_as_int(ibScore), __float_as_int(ibLm), (int)p.entryWord[ibWord], ibBkp);
+                    books[1] = make_int4(t, 0, 0, 0);
+                    sIrrLm[irrLast] = ibLm;
+                }
+                irrScore = ibScore;
+                irrLm    = ibLm;
+            }
+            if (tid == 0) {  // read by every warp after the next barrier
+                float m = nbScore != FLT_MAX ? fmaxf(sMaxLm[par], fabsf(nbLm)) : sMaxLm[par];
+                if (SINGLE && ibScore != FLT_MAX)
+                    m = fmaxf(m, fabsf(ibLm));
+                sMaxLm[par ^ 1] = m;
+            }
         }
     }
-    if (tid == 0)
+    if (tid == 0) {
         p.nBooks[u] = last + 1;
+        if (SINGLE)
+            p.nIrrBooks[u] = irrLast + 1;
+    }
 }
 
 }  // namespace
@@ -704,8 +893,10 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
         lx                      = &entries;
         h->single               = true;
         h->nIrr                 = (uint32_t)irrList.size();
+        if (irrList.empty())
+            irrList.push_back(0);  // never read (nIrr = 0); keeps the table uploads uniform
     }
-    const uint32_t nStatesAll = lx->word_offsets[lx->n_words];
+    const uint32_t nStatesAll = lx->word_offsets[lx->n_words];  // of the entries, from here on
     auto fail = [&](int code) {
         delete h;
         return code;
@@ -725,8 +916,7 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
     {
         const float           inf = std::numeric_limits<float>::infinity();
         std::vector<float>    values;
-        // (single-word recognition runs on the per-word kernel: two books and a choice of predecessor per entry)
-        bool                  fits = lx->n_words <= (1u << (32 - kWordShift)) && !h->single;
+        bool                  fits = lx->n_words <= (1u << (32 - kWordShift)) && h->nIrr <= 1024;
         auto valueOf = [&](float v) -> uint32_t {
             for (size_t i = 0; i < values.size(); ++i)
                 if (memcmp(&values[i], &v, 4) == 0)
@@ -741,7 +931,7 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
         for (uint32_t s = 0; s < nStatesAll; ++s)
             maxEmis = std::max(maxEmis, lx->state_emission[s]);
         h->maxEmis = maxEmis;  // kept for every lexicon: decode checks it against the width of the score rows
-        fits = fits && maxEmis < 16384 && nStates <= (uint32_t)kThreads * 16;
+        fits = fits && maxEmis < 16384 && nStatesAll <= (uint32_t)kThreads * 16;
         const float*          tdp = lx->tdp;
         const uint32_t        em  = lx->entry_model;
         const uint32_t*       mo  = lx->state_tdp_model;
@@ -756,18 +946,18 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
                 const uint32_t oSkip = j == 0 ? infIdx : valueOf(j == 1 ? tdp[em * 4 + 2] : tdp[mo[i - 2] * 4 + 2]);
                 meta[i]  = (j == 0 ? kFirst : 0u) | (j == 1 ? kSecond : 0u) | oLoop << 2 | oFwd << 7 | oSkip << 12 |
                            (i + 1 == lx->word_offsets[w + 1] ? kLast : 0u) | (w << kWordShift);
-                emOff[i] = (uint16_t)(lx->state_emission[i] * 4);
+                emOff[i] = (uint16_t)(lx->state_emission[i] * 4 | (h->single ? eFlags[w] : 0));
             }
             wordExit[w]  = tdp[mo[lx->word_offsets[w + 1] - 1] * 4 + 3];
             h->maxAbsUni = std::max(h->maxAbsUni, std::fabs(lx->unigram[w]));
         }
         if (fits && getenv("RB_SEARCH_PER_WORD") == nullptr) {
             // few states per thread while that still fills the SM's four schedulers with several warps each
-            h->npt = nStates <= 512 * 2 ? 2 : (nStates <= (uint32_t)kThreads * 4 ? 4 : (nStates <= (uint32_t)kThreads * 8 ? 8 : 16));
+            h->npt = nStatesAll <= 512 * 2 ? 2 : (nStatesAll <= (uint32_t)kThreads * 4 ? 4 : (nStatesAll <= (uint32_t)kThreads * 8 ? 8 : 16));
             if (const char* e = getenv("RB_SEARCH_NPT"))
-                if (atoi(e) * (uint32_t)kThreads >= nStates && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16))
+                if (atoi(e) * (uint32_t)kThreads >= nStatesAll && (atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16))
                     h->npt = atoi(e);
-            h->regThreads = (int)(((nStates + h->npt - 1) / h->npt + 31) / 32 * 32);
+            h->regThreads = (int)(((nStatesAll + h->npt - 1) / h->npt + 31) / 32 * 32);
             // words whose last state lives in warp i (contiguous: states are in lexicon order)
             std::vector<uint32_t> warpWords(h->regThreads / 32 + 1, lx->n_words);
             warpWords[0] = 0;
@@ -798,7 +988,7 @@ extern "C" int rb_search_create(const rb_lexicon* lx, int device, rb_search** ou
     }
     if (h->single && (h->dFlags.upload(eFlags.data(), eFlags.size(), h->stream) != RB_OK ||
                       h->dEntryWord.upload(eWord.data(), eWord.size(), h->stream) != RB_OK ||
-                      h->dIrrList.upload(irrList.data(), std::max<size_t>(irrList.size(), 1), h->stream) != RB_OK)) {
+                      h->dIrrList.upload(irrList.data(), irrList.size(), h->stream) != RB_OK)) {
         rb::set_error("lexicon upload failed");
         return fail(RB_ERR_CUDA);
     }
@@ -848,8 +1038,10 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
     for (int u = 0; u < n_utt; ++u)
         maxT = std::max(maxT, h->frameOff[u + 1] - h->frameOff[u]);
     const uint32_t rowFloats = ((uint32_t)n_emissions + 3) & ~3u;
-    const SmemLayout lay(h->regThreads / 32, h->W, rowFloats, (uint32_t)maxT);
-    const size_t     smem2 = lay.total;
+    SmemLayout lay(h->regThreads / 32, h->W, rowFloats, (uint32_t)maxT, h->single, h->nIrr, 2);
+    if (lay.total + 4096 > h->dev.smem_optin)
+        lay = SmemLayout(h->regThreads / 32, h->W, rowFloats, (uint32_t)maxT, h->single, h->nIrr, 1);
+    const size_t smem2 = lay.total;
     if (h->npt && smem2 + 4096 <= h->dev.smem_optin) {
         SearchParams2 q;
         q.lay       = lay;
@@ -864,15 +1056,31 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
         q.W         = h->W;
         q.maxT      = (uint32_t)maxT;
         q.rowFloats = rowFloats;
-        q.forceScan = getenv("RB_SEARCH_FORCE_SCAN") != nullptr;
+        q.forceScan = getenv("RB_SEARCH_FORCE_SCAN") ? std::max(1, atoi(getenv("RB_SEARCH_FORCE_SCAN"))) : 0;
         q.scores    = d_scores;
         q.frameOff  = h->dFrameOff.p;
         q.nEmis     = n_emissions;
         q.books     = reinterpret_cast<int4*>(h->dBooks.p);
         q.nBooks    = h->dNBooks.p;
-        auto k = h->npt == 2 ? linear_search_reg_kernel<2>
-                             : (h->npt == 4 ? linear_search_reg_kernel<4>
-                                            : (h->npt == 8 ? linear_search_reg_kernel<8> : linear_search_reg_kernel<16>));
+        q.flags     = h->dFlags.p;
+        q.entryWord = h->dEntryWord.p;
+        q.irrList   = h->dIrrList.p;
+        q.nIrr      = h->nIrr;
+        q.irrBooks  = nullptr;
+        q.nIrrBooks = nullptr;
+        if (h->single) {
+            RB_CHECK(h->dIrrBooks.reserve((size_t)T * 8));
+            RB_CHECK(h->dNIrrBooks.reserve((size_t)n_utt));
+            q.irrBooks  = reinterpret_cast<int4*>(h->dIrrBooks.p);
+            q.nIrrBooks = h->dNIrrBooks.p;
+        }
+        auto pick = [&](auto one, auto two, auto three, auto four) {
+            return h->npt == 2 ? one : (h->npt == 4 ? two : (h->npt == 8 ? three : four));
+        };
+        auto k = h->single ? pick(linear_search_reg_kernel<2, true>, linear_search_reg_kernel<4, true>,
+                                  linear_search_reg_kernel<8, true>, linear_search_reg_kernel<16, true>)
+                           : pick(linear_search_reg_kernel<2, false>, linear_search_reg_kernel<4, false>,
+                                  linear_search_reg_kernel<8, false>, linear_search_reg_kernel<16, false>);
         RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         k<<<n_utt, h->regThreads, smem2, s>>>(q);
     }

@@ -25,11 +25,13 @@ def test_linear_search_bit_exact(oracle, n_words, n_emis, T, seed):
 
 @pytest.mark.parametrize("n_words,min_s,max_s,env", [(2100, 3, 12, None), (300, 1, 3, None), (90, 2, 5, None),
                                                      (700, 3, 12, "RB_SEARCH_PER_WORD"), (300, 1, 3, "RB_SEARCH_PER_WORD"),
-                                                     (700, 3, 12, "RB_SEARCH_FORCE_SCAN"), (1200, 3, 9, "RB_SEARCH_NPT=16")])
+                                                     (700, 3, 12, "RB_SEARCH_FORCE_SCAN"), (700, 3, 12, "RB_SEARCH_FORCE_SCAN=2"),
+                                                     (1200, 3, 9, "RB_SEARCH_NPT=16")])
 def test_kernel_variants_bit_exact(oracle, monkeypatch, n_words, min_s, max_s, env):
     """the register-resident kernel at 2, 4, 8 and 16 states per thread, words of one and two states (the entry
     hypothesis is both predecessors), its book keeping forced onto the sequential replay, and the per-word kernel that
-    serves lexicons the register kernel does not fit"""
+    serves lexicons the register kernel does not fit; FORCE_SCAN = never the unique-minimum shortcut (1: the scan over
+    the record-breaking warps by every warp, 2: the warp-0 replay behind a second barrier)"""
     if env:
         monkeypatch.setenv(*(env.split("=") if "=" in env else (env, "1")))
     lex = synth.lexicon(n_words, 64, min_states=min_s, max_states=max_s, seed=21)
@@ -60,10 +62,14 @@ def irregular_lexicon(n_words, n_emis, seed, n_irregular, min_states=3, max_stat
 @pytest.mark.parametrize("n_words,n_irr,min_s,max_s,quantised", [(60, 3, 3, 12, False), (700, 9, 3, 12, False),
                                                                  (2100, 20, 3, 12, False), (300, 40, 1, 3, True),
                                                                  (50, 50, 2, 5, True)])
-def test_single_word_recognition_bit_exact(oracle, n_words, n_irr, min_s, max_s, quantised):
+@pytest.mark.parametrize("env", [None, "RB_SEARCH_PER_WORD", "RB_SEARCH_FORCE_SCAN", "RB_SEARCH_FORCE_SCAN=2"])
+def test_single_word_recognition_bit_exact(oracle, monkeypatch, n_words, n_irr, min_s, max_s, quantised, env):
     """the recognizer's default mode (src/Search/LinearSearch.cc:26-30): a second book of irregular-only sequences,
     irregular-chain entries, regular words restricted to one per sentence; lexicons held in shared memory and (2100
-    words) in global memory; quantised scores make ties in both book-keeping scans"""
+    words) in global memory; quantised scores make ties in both book-keeping scans; on the register-resident kernel
+    (irregular word ends mirrored into slots, second scan replayed by every warp) and on the per-word kernel"""
+    if env:
+        monkeypatch.setenv(*(env.split("=") if "=" in env else (env, "1")))
     lex = irregular_lexicon(n_words, 64, 31, n_irr, min_s, max_s)
     rng = np.random.default_rng(31)
     fo = np.array([0, 150, 151, 260], np.int64)
