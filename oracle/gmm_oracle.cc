@@ -490,6 +490,116 @@ struct BatchInt {
     }
 };
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Mm::SimdGaussDiagonalMaximumFeatureScorer ("SIMD-diagonal-maximum", src/Mm/SimdFeatureScorer.{hh,cc} +
+ * src/Mm/IntelOptimization.{hh,cc}): u8-quantised means and features like the batch-int scorer, but with one
+ * quantised copy of the feature vector PER COVARIANCE (each scaled by that covariance's 1/sqrt(var)), the constant of
+ * a density truncated from f32, the best density kept, and the score 0.5 * int / scaling^2 evaluated in double.
+ *   init / getScaling / quantizationScalingFactor   SimdFeatureScorer.cc:62-135
+ *   buildMixtureTable / createDensityElement        SimdFeatureScorer.cc:79-104, IntelOptimization.cc:39-49
+ *   multiplyAndQuantize / quantize                  IntelOptimization.cc:51-69, Utilities.hh:190-202
+ *   calculateScoreAndDensity / quantizedScore       SimdFeatureScorer.cc:137-176
+ *   distance                                        the code SSE2CodeGenerator.cc emits: sum_d (m_d - x_d)^2 in s32
+ * (The reference's cmake build generates 32-bit code on x86-64 and crashes in this scorer; oracle/refbuild compiles
+ * the generator with -DPROC_x86_64, as the reference's old Makefiles did, to run it.) */
+struct SimdDiagMax {
+    unsigned                          dim, nMix, nCov;
+    std::vector<std::vector<float>>   isd;     /* [cov][dim] 1/sqrt(var) * scaling */
+    std::vector<unsigned>             offsets; /* [nMix + 1] */
+    std::vector<uint8_t>              means;   /* [nDens][dim] */
+    std::vector<int32_t>              consts;
+    std::vector<unsigned>             cov;
+    float                             scalingSquared;
+
+    int init(const orc_mixture_set& ms) {
+        dim  = ms.dim;
+        nMix = ms.n_mixtures;
+        nCov = ms.n_covariances;
+        isd.assign(nCov, std::vector<float>(dim));
+        std::vector<float> logNorm(nCov);
+        for (unsigned c = 0; c < nCov; ++c) {
+            const float* var = ms.variances + (size_t)c * dim;
+            for (unsigned d = 0; d < dim; ++d) {
+                if (!(var[d] > 0))
+                    return -2; /* require(checkDiagonal(diagonal)) */
+                isd[c][d] = inverseSquareRoot(var[d]);
+            }
+            logNorm[c] = (float)gaussLogNormFactor(var, dim); /* Score logNormalizationFactor_ */
+        }
+        /* getScaling(): range of mean / sqrt(var) over ALL densities of the set */
+        float minMean = FLT_MAX, maxMean = -FLT_MAX; /* Core::Type<f32>::max, ::min = -FLT_MAX */
+        for (unsigned i = 0; i < ms.n_densities; ++i) {
+            const float* mu = ms.means + (size_t)ms.dens_mean[i] * dim;
+            const float* sd = isd[ms.dens_cov[i]].data();
+            for (unsigned d = 0; d < dim; ++d) {
+                const float divided = mu[d] * sd[d];
+                minMean             = std::min(minMean, divided);
+                maxMean             = std::max(maxMean, divided);
+            }
+        }
+        const float intervalSize = 2 * std::max(std::fabs(minMean), std::fabs(maxMean));
+        const float scaling      = (float)255 / (1.25 * intervalSize);
+        scalingSquared           = scaling * scaling;
+        for (unsigned c = 0; c < nCov; ++c) { /* CovarianceFeatureScorerElement::scale */
+            for (unsigned d = 0; d < dim; ++d)
+                isd[c][d] = isd[c][d] * scaling;
+            logNorm[c] *= scaling * scaling;
+        }
+        offsets.assign(nMix + 1, 0);
+        for (unsigned m = 0; m < nMix; ++m)
+            offsets[m + 1] = offsets[m] + (ms.mix_offsets[m + 1] - ms.mix_offsets[m]);
+        means.assign((size_t)offsets[nMix] * dim, 0);
+        consts.assign(offsets[nMix], 0);
+        cov.assign(offsets[nMix], 0);
+        for (unsigned m = 0; m < nMix; ++m) {
+            unsigned k = offsets[m];
+            for (unsigned e = ms.mix_offsets[m]; e < ms.mix_offsets[m + 1]; ++e, ++k) {
+                const unsigned dns = ms.mix_density[e];
+                const unsigned c   = ms.dens_cov[dns];
+                const float*   mu  = ms.means + (size_t)ms.dens_mean[dns] * dim;
+                cov[k]             = c;
+                for (unsigned d = 0; d < dim; ++d)
+                    means[(size_t)k * dim + d] = BatchInt::quantize(mu[d] * isd[c][d]);
+                /* Weight (f64) = f32 * -2 * f64; passed as Score (f32); (s32)(f32 + f32) */
+                const double scaledMinus2LogWeight = scalingSquared * -2 * ms.mix_log_weight[e];
+                consts[k] = (int32_t)((float)scaledMinus2LogWeight + logNorm[c]);
+            }
+        }
+        return 0;
+    }
+
+    void scoreFrames(const float* feats, long t0, long t1, float* scores, uint32_t* best) const {
+        std::vector<uint8_t> x((size_t)nCov * dim);
+        for (long t = t0; t < t1; ++t) {
+            const float* f = feats + (size_t)t * dim;
+            for (unsigned c = 0; c < nCov; ++c)
+                for (unsigned d = 0; d < dim; ++d)
+                    x[(size_t)c * dim + d] = BatchInt::quantize(f[d] * isd[c][d]);
+            for (unsigned m = 0; m < nMix; ++m) {
+                int      minScore = 2147483647;
+                uint32_t bestDns  = 0xffffffffu;
+                for (unsigned k = offsets[m]; k < offsets[m + 1]; ++k) {
+                    const uint8_t* mean = means.data() + (size_t)k * dim;
+                    const uint8_t* xq   = x.data() + (size_t)cov[k] * dim;
+                    int            dist = 0;
+                    for (unsigned d = 0; d < dim; ++d) {
+                        const int df = (int)mean[d] - (int)xq[d];
+                        dist += df * df;
+                    }
+                    const int score = consts[k] + dist;
+                    if (score < minScore) {
+                        minScore = score;
+                        bestDns  = k - offsets[m];
+                    }
+                }
+                scores[(size_t)t * nMix + m] = (float)(0.5 * minScore / scalingSquared);
+                if (best)
+                    best[(size_t)t * nMix + m] = bestDns;
+            }
+        }
+    }
+};
+
 }  // namespace
 
 extern "C" int orc_gmm_batch_int(const orc_mixture_set* ms, const float* feats, long T, float* scores, int n_threads) {
@@ -506,6 +616,44 @@ extern "C" int orc_gmm_batch_int(const orc_mixture_set* ms, const float* feats, 
     }
     for (auto& th : pool)
         th.join();
+    return 0;
+}
+
+/* scores [T * n_mixtures], best (optional) [T * n_mixtures] density-in-mixture indices */
+extern "C" int orc_gmm_simd_diag_max(const orc_mixture_set* ms, const float* feats, long T, float* scores, uint32_t* best,
+                                     int n_threads) {
+    SimdDiagMax s;
+    int         rc = s.init(*ms);
+    if (rc)
+        return rc;
+    if (n_threads < 1)
+        n_threads = 1;
+    std::vector<std::thread> pool;
+    for (int i = 0; i < n_threads; ++i) {
+        long a = T * i / n_threads, b = T * (i + 1) / n_threads;
+        pool.emplace_back([&s, feats, scores, best, a, b]() { s.scoreFrames(feats, a, b, scores, best); });
+    }
+    for (auto& th : pool)
+        th.join();
+    return 0;
+}
+
+/* the quantised model (for known-answer tests and the CUDA side's checks): means [n_dens * dim], consts [n_dens],
+ * isd [n_cov * dim] (scaled), scaling^2 */
+extern "C" int orc_gmm_simd_model(const orc_mixture_set* ms, uint8_t* means, int32_t* consts, float* isd, float* scaling_squared) {
+    SimdDiagMax s;
+    int         rc = s.init(*ms);
+    if (rc)
+        return rc;
+    if (means)
+        std::memcpy(means, s.means.data(), s.means.size());
+    if (consts)
+        std::memcpy(consts, s.consts.data(), sizeof(int32_t) * s.consts.size());
+    if (isd)
+        for (unsigned c = 0; c < s.nCov; ++c)
+            std::memcpy(isd + (size_t)c * s.dim, s.isd[c].data(), sizeof(float) * s.dim);
+    if (scaling_squared)
+        *scaling_squared = s.scalingSquared;
     return 0;
 }
 

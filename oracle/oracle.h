@@ -125,6 +125,10 @@ int orc_gmm_diag_sum(const orc_mixture_set* ms, float mixture_weight_scale, floa
  * processes over corpus partitions; threads over frame ranges are the same thing for a dense scorer) */
 /* Mm::BatchIntFeatureScorer (u8-quantised means / features, s32 distances; src/Mm/BatchFeatureScorer.cc:321-510) */
 int orc_gmm_batch_int(const orc_mixture_set* ms, const float* feats, long T, float* scores, int n_threads);
+/* Mm::SimdGaussDiagonalMaximumFeatureScorer ("SIMD-diagonal-maximum"): u8-quantised, one quantised feature vector
+ * per covariance, best density-in-mixture index (optional) */
+int orc_gmm_simd_diag_max(const orc_mixture_set* ms, const float* feats, long T, float* scores, uint32_t* best, int n_threads);
+int orc_gmm_simd_model(const orc_mixture_set* ms, uint8_t* means, int32_t* consts, float* isd, float* scaling_squared);
 int orc_gmm_batch_int_model(const orc_mixture_set* ms, uint8_t* means, int32_t* consts, float* variance, float* scale,
                             int* padded);
 /* Mm::BatchPreselectionFloatFeatureScorer ("preselection-batch-float", src/Mm/BatchFeatureScorer.cc:257-315 with

@@ -283,6 +283,19 @@ def gmm_batch_int(ms, feats, threads=1):
     return scores
 
 
+def gmm_simd_diag_max(ms, feats, threads=1, want_best=False):
+    """Mm::SimdGaussDiagonalMaximumFeatureScorer over all mixtures; optionally the best density-in-mixture indices"""
+    feats = np.ascontiguousarray(feats, np.float32)
+    T = feats.shape[0]
+    scores = np.zeros((T, ms.n_mixtures), np.float32)
+    best = np.zeros((T, ms.n_mixtures), np.uint32) if want_best else None
+    rc = lib().orc_gmm_simd_diag_max(C.byref(ms.c), _p(feats, C.c_float), C.c_long(T), _p(scores, C.c_float),
+                                     _p(best, C.c_uint32), int(threads))
+    if rc:
+        raise RuntimeError("orc_gmm_simd_diag_max failed: %d" % rc)
+    return (scores, best) if want_best else scores
+
+
 def gmm_batch_int_model(ms):
     """The quantised model: dict(means u8 [nDens x padded], consts s32 [nDens], variance f32 [padded], scale)."""
     n_dens = int(ms.a["mix_offsets"][-1])

@@ -256,6 +256,22 @@ def test_c2_model_diagonal_scorers(ref, oracle, name):
     assert (bestn != wbest).mean() < 1e-3
 
 
+@pytest.mark.parametrize("native", [False, True])
+def test_c2_model_simd_diagonal_maximum(ref, oracle, native):
+    """"SIMD-diagonal-maximum" (src/Mm/SimdFeatureScorer.cc): scores and best densities bit-identical in both builds
+    (integer distances; the f32 / f64 mixing of init() has no multiply-add to contract).  The reference's run-time
+    code generator is compiled with -DPROC_x86_64 (oracle/refbuild/Makefile): without it the scorer crashes."""
+    msd = synth.mixture_set()
+    ms = oracle.MixtureSet(**msd)
+    f = synth.features(400, 39)
+    got, best = ref.FeatureScorer(ms, "SIMD-diagonal-maximum", native=native).score(f, want_best=True)
+    want, wbest = oracle.gmm_simd_diag_max(ms, f, want_best=True)
+    assert np.array_equal(got, want) and np.array_equal(best, wbest)
+    # a quantised version of diagonal-maximum: same best density almost everywhere, scores within 10 %
+    exact, ebest = oracle.gmm_diag_max(ms, f, use_fma=False)
+    assert (np.abs(got - exact) / exact).max() < 0.1 and (best == ebest).mean() > 0.9
+
+
 def _ragged_model(dim, seed):
     rng = np.random.default_rng(seed)
     sizes = [0, 1, 3, 16, 2, 0, 7, 33, 1, 5]
@@ -283,6 +299,11 @@ def test_ragged_models_and_other_dimensions(ref, oracle, dim):
         nonempty = np.diff(msd["mix_offsets"]) > 0
         assert np.array_equal(got[:, nonempty], want[:, nonempty]), name
         assert np.array_equal(best[:, nonempty], wbest[:, nonempty]), name
+    # one quantised feature vector per covariance; features far outside the range of the means saturate at 0 / 255
+    for feats in (f, 4.0 * f):
+        got, best = ref.FeatureScorer(ms, "SIMD-diagonal-maximum").score(feats, want_best=True)
+        want, wbest = oracle.gmm_simd_diag_max(ms, feats, want_best=True)
+        assert np.array_equal(got[:, nonempty], want[:, nonempty]) and np.array_equal(best[:, nonempty], wbest[:, nonempty])
     pooled = dict(msd, dens_cov=np.zeros_like(msd["dens_cov"]), variances=msd["variances"][:1])
     ms1 = oracle.MixtureSet(**pooled)
     for name, fn in SCORERS[:3]:
