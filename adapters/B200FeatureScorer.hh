@@ -6,7 +6,7 @@
  * src/Onnx/OnnxFeatureScorer.{hh,cc}: addFeature() collects the segment, the first flush()/score() runs ONE
  * dense rb_gmm_score over all buffered frames, ContextScorer::score(e) is then a lookup into the T x nMix
  * matrix.  Selected with  feature-scorer-type = b200-batch-float | b200-diagonal-maximum | b200-diagonal-sum
- * | b200-batch-tensor | b200-batch-int | b200-preselection-batch-float | b200-preselection-batch-int (GmmFeatureScorer -> the rb_gmm calls)  or  b200-nn-batch-feature-scorer
+ * | b200-batch-tensor | b200-batch-int | b200-preselection-batch-float | b200-preselection-batch-int | b200-SIMD-diagonal-maximum (GmmFeatureScorer -> the rb_gmm calls)  or  b200-nn-batch-feature-scorer
  * (NnFeatureScorer -> the rb_nn calls, the drop-in for src/Nn/BatchFeatureScorer.{hh,cc}).
  */
 #ifndef _B200_FEATURE_SCORER_HH

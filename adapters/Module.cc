@@ -20,6 +20,7 @@ Module_::Module_() {
     f->registerFeatureScorer<FeatureScorerOf<RB_GMM_BATCH_INT>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 4, "b200-batch-int");
     f->registerFeatureScorer<FeatureScorerOf<RB_GMM_BATCH_PRESELECT>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 6, "b200-preselection-batch-float");
     f->registerFeatureScorer<FeatureScorerOf<RB_GMM_BATCH_PRESELECT_INT>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 7, "b200-preselection-batch-int");
+    f->registerFeatureScorer<FeatureScorerOf<RB_GMM_SIMD_DIAG_MAX>, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 8, "b200-SIMD-diagonal-maximum");
     f->registerFeatureScorer<NnFeatureScorer, Mm::MixtureSet, Mm::AbstractMixtureSetLoader>(0x500 + 5, "b200-nn-batch-feature-scorer");
     Flow::Registry::instance().registerFilter<MfccNode>();
     Flow::Registry::instance().registerFilter<NnForwardNode>();

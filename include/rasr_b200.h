@@ -247,7 +247,11 @@ typedef enum {
      * truncated to u8, no back-off score (a mixture without a scored density gets (f32)INT_MAX / scale).  Equal
      * distances at the selection boundary are resolved like the reference's std::sort (libstdc++ introsort restated,
      * rasr_b200/csrc/introsort.cuh): bit-identical scores. */
-    RB_GMM_BATCH_PRESELECT_INT = 6
+    RB_GMM_BATCH_PRESELECT_INT = 6,
+    /* Mm::SimdGaussDiagonalMaximumFeatureScorer ("SIMD-diagonal-maximum", src/Mm/SimdFeatureScorer.{hh,cc}): u8-quantised
+     * means, one u8-quantised copy of the feature vector per covariance, s32 distances, first best density reported;
+     * scores and densities bit-identical (feature dimension <= 64).  mixture_weight_scale / gaussian_scale must be 1. */
+    RB_GMM_SIMD_DIAG_MAX = 7
 } rb_gmm_mode;
 
 /* contraction: 1 = fused multiply-add where the reference's default build (gcc -O2 -march=native,

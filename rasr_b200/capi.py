@@ -18,6 +18,7 @@ STATUS = {0: "RB_OK", -1: "RB_ERR_INVALID", -2: "RB_ERR_NO_DEVICE", -3: "RB_ERR_
 
 GMM_BATCH_FLOAT, GMM_DIAG_MAX, GMM_DIAG_SUM, GMM_BATCH_TENSOR, GMM_BATCH_INT, GMM_BATCH_PRESELECT = 0, 1, 2, 3, 4, 5
 GMM_BATCH_PRESELECT_INT = 6
+GMM_SIMD_DIAG_MAX = 7
 ACT = {"linear": 0, "sigmoid": 1, "relu": 2, "rectified": 2, "softmax": 3, "tanh": 4}
 NN_F32, NN_BF16 = 0, 1
 

@@ -813,6 +813,11 @@ int  rb_gmm_presel_int_configure(rb_gmm_presel_int* h, int clusters, int select,
 void rb_gmm_presel_int_clustering(const rb_gmm_presel_int* h, uint32_t* cluster_of, float* cluster_means,
                                   int* n_clusters);
 
+struct rb_gmm_simd;  // gmm_simd.cu
+int  rb_gmm_simd_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_simd** out);
+void rb_gmm_simd_destroy(rb_gmm_simd* h);
+int  rb_gmm_simd_score(rb_gmm_simd* h, const float* d_feats, long T, float* d_scores, uint32_t* d_best, cudaStream_t stream);
+
 struct rb_gmm_tensor;  // gmm_tensor.cu
 int  rb_gmm_tensor_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream,
                           rb_gmm_tensor** out);
@@ -874,8 +879,11 @@ struct rb_gmm {
     rb_gmm_int*          quantised = nullptr;
     rb_gmm_presel*       presel    = nullptr;
     rb_gmm_presel_int*   preselInt = nullptr;
+    rb_gmm_simd*         simd      = nullptr;
 
     ~rb_gmm() {
+        if (simd)
+            rb_gmm_simd_destroy(simd);
         if (tensor)
             rb_gmm_tensor_destroy(tensor);
         if (quantised)
@@ -1255,7 +1263,7 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
     RB_REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
     RB_CHECK(validate(ms));
-    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_BATCH_PRESELECT_INT, "unknown gmm mode %d", mode);
+    RB_REQUIRE(mode >= RB_GMM_BATCH_FLOAT && mode <= RB_GMM_SIMD_DIAG_MAX, "unknown gmm mode %d", mode);
     rb_gmm* h = new (std::nothrow) rb_gmm();
     if (!h) {
         rb::set_error("out of host memory");
@@ -1281,6 +1289,13 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
     std::vector<float> rows, isd;
     if (mode == RB_GMM_BATCH_INT) {
         rc = rb_gmm_int_create(ms, h->dev, h->stream, &h->quantised);
+        if (rc != RB_OK)
+            return fail(rc);
+        *out = h;
+        return RB_OK;
+    }
+    if (mode == RB_GMM_SIMD_DIAG_MAX) {
+        rc = rb_gmm_simd_create(ms, h->dev, h->stream, &h->simd);
         if (rc != RB_OK)
             return fail(rc);
         *out = h;
@@ -1442,6 +1457,8 @@ int score_dev_impl(rb_gmm* h, const float* d_feats, long T, float* d_scores, flo
         rc = rb_gmm_presel_score(h->presel, d_feats, T, d_scores, s);
     else if (h->mode == RB_GMM_BATCH_PRESELECT_INT)
         rc = rb_gmm_presel_int_score(h->preselInt, d_feats, T, d_scores, s);
+    else if (h->mode == RB_GMM_SIMD_DIAG_MAX)
+        rc = rb_gmm_simd_score(h->simd, d_feats, T, d_scores, d_best, s);
     else
         rc = launch_simt(h, d_feats, T, d_scores, d_best, s);
     RB_CHECK(rc);
@@ -1460,7 +1477,7 @@ extern "C" int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* 
     RB_REQUIRE(d_feats && d_scores, "NULL device buffer");
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-    if (h->mode != RB_GMM_DIAG_MAX && h->mode != RB_GMM_DIAG_SUM)
+    if (h->mode != RB_GMM_DIAG_MAX && h->mode != RB_GMM_DIAG_SUM && h->mode != RB_GMM_SIMD_DIAG_MAX)
         RB_REQUIRE(d_best == nullptr, "this scorer mode does not report densities; use RB_GMM_DIAG_MAX");
     return score_dev_impl(h, d_feats, T, d_scores, nullptr, 0, d_best, s);
 }
