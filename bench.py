@@ -703,7 +703,7 @@ class Bench:
         scorer, d_in, d_out, msd = w["keep"]
         T, R = w["units"], self.R
         out = {}
-        for name in ("batch-tensor", "batch-float-direct", "diagonal-maximum"):
+        for name in ("batch-tensor", "batch-float-direct", "diagonal-maximum", "batch-int", "SIMD-diagonal-maximum"):
             if name == "batch-float-direct":
                 os.environ["RB_GMM_EXACT"] = "0"
             try:
@@ -726,6 +726,14 @@ class Bench:
             if name == "batch-tensor":
                 d.update(dtype="f16x3 split operands, f32 accumulate",
                          parity="<= 1e-4 relative to the reference scores (tests/test_gpu_gmm_tensor.py)")
+            elif name == "batch-int":
+                d.update(dtype="u8 x u8 -> s32 (IMMA)", parity="bit-identical (tests/test_gpu_gmm_int.py)",
+                         note="Mm::BatchIntFeatureScorer, the reference's quantised batch scorer")
+            elif name == "SIMD-diagonal-maximum":
+                d.update(dtype="u8 x u8 -> s32 (DP4A)",
+                         parity="scores and best-density indices bit-identical (tests/test_gpu_gmm_simd.py)",
+                         note="Mm::SimdGaussDiagonalMaximumFeatureScorer, the reference's quantised diagonal scorer "
+                              "(crashes in the reference's own x86-64 cmake build, oracle/refbuild/Makefile)")
             elif name == "diagonal-maximum":
                 d.update(dtype="f32", parity="scores and best-density indices bit-identical (tests/test_gpu_gmm_exact.py)",
                          note="Mm::GaussDiagonalMaximumFeatureScorer (per-density covariance) on the same model, through "

@@ -792,7 +792,8 @@ GmmKernel diag_kernel_for(int nq, bool fuse, bool sum) {
 // ==========================================================================================
 
 struct rb_gmm_int;  // gmm_int.cu
-int  rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_int** out);
+int  rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_int** out,
+                       bool simd = false);
 void rb_gmm_int_destroy(rb_gmm_int* h);
 int  rb_gmm_int_score(rb_gmm_int* h, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
 

@@ -52,8 +52,9 @@ struct IntParams {
     float*               scores;   // [T * nMix]
     long                 T;
     int                  nMix, nGroups, nFrameBlocks, vec4;
-    float                scale;     // scale_ = 2 * quantisation scale^2
+    float                scale;     // scale_ = 2 * quantisation scale^2 (simd: the quantisation scale^2)
     float                rcpScale;  // RN(1 / scale_); 0 if the three-instruction division is not proven for this scale
+    int                  simd;      // scores as Mm::SimdGaussDiagonalMaximumFeatureScorer forms them (gmm_simd.cu)
 };
 
 // setFeature: u8 = clip(round(f * isd * scale) + 128); 16 lanes per frame, 4 dims (one u32) per lane
@@ -102,7 +103,9 @@ __device__ __forceinline__ void imma_u8(int (&d)[4], const uint32_t (&a)[4], uin
 // (f32)b / scale_, correctly rounded.  For |b| < 2^24 the quotient is formed as q0 = a r, q = fma(fma(-s, q0, a), r, q0)
 // with r = RN(1/s) (Markstein); the host has checked this sequence against IEEE division for EVERY integer in that
 // range for this particular scale (rb_gmm_int_create), otherwise rcpScale is 0 and div.rn is used throughout.
-__device__ __forceinline__ float score_of(int b, float scale, float rcp) {
+__device__ __forceinline__ float score_of(int b, float scale, float rcp, int simd) {
+    if (simd)  // result.score = 0.5 * quantizedResult.first / scalingSquared_ in f64 (src/Mm/SimdFeatureScorer.cc:143)
+        return (float)(0.5 * (double)b / (double)scale);
     const float a = (float)b;
     if (rcp != 0.0f && (unsigned)(b + (1 << 24)) < (2u << 24)) {
         const float q0 = __fmul_rn(a, rcp);
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_int_kernel(const IntParams p)
                 }
                 // empty mixture: the reference's running minimum stays at INT_MAX (:479-481)
                 const int   bA = (flags & 2) ? INT_MAX : v2[0] + xsA, bB = (flags & 2) ? INT_MAX : v2[1] + xsB;
-                const float sA = score_of(bA, p.scale, p.rcpScale), sB = score_of(bB, p.scale, p.rcpScale);
+                const float sA = score_of(bA, p.scale, p.rcpScale, p.simd), sB = score_of(bB, p.scale, p.rcpScale, p.simd);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     best[j] = INT_MAX;
@@ -318,6 +321,7 @@ struct rb_gmm_int {
     rb::DeviceInfo dev;
     int            dim = 0, nMix = 0, nTiles = 0, ctasPerSm = 1, curGroups = -1;
     float          scale = 1.0f, rcpScale = 0.0f;
+    bool           simd = false;
     size_t         smemBytes = 0;
     std::vector<int> tilesOfMixture, groupsOf;
     rb::DevBuf<unsigned char> dTiles, dXq;
@@ -389,7 +393,7 @@ int choose_groups(const rb_gmm_int* h, long T, int slots) {
 
 }  // namespace
 
-int rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_int** out) {
+int rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_int** out, bool simd) {
     *out = nullptr;
     if (ms->n_covariances != 1) {
         rb::set_error("int feature scorer supports only globally pooled variance (got %u covariances)",
@@ -431,7 +435,10 @@ int rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaS
     const float scale        = (float)((double)255.0f / (1.25 * (double)intervalSize));
     const float scaleSquared = scale * scale;
     h->scale                 = (float)(2.0 * (double)scaleSquared);
-    {  // exhaustive proof of the fast division for this scale (33.5 M quotients, 0.06-0.2 s, once per model)
+    h->simd                  = simd;
+    if (simd)
+        h->scale = scaleSquared;  // scalingSquared_; the score is 0.5 * int / scalingSquared_ in f64
+    else {  // exhaustive proof of the fast division for this scale (33.5 M quotients, 0.06-0.2 s, once per model)
         const float r  = 1.0f / h->scale;
         const bool  ok = std::isfinite(r) && r != 0.0f &&
                         (__builtin_cpu_supports("fma") ? fast_division_exact_fma(h->scale, r)
@@ -476,8 +483,16 @@ int rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaS
                     tile[r * kRowBytes + d] = qv;
                     m2 += (int)qv * (int)qv;
                 }
-                const int c = (int)((double)logNormFactor - (double)h->scale * ms->mix_log_weight[e0 + i]);
-                cc[r]       = c + m2;
+                int c;
+                if (simd) {
+                    // createDensityElement (src/Mm/IntelOptimization.cc:39-49): Weight (f64) = f32 * -2 * f64, handed over
+                    // as Score (f32); constantWeight_ = (s32)(f32 + f32)
+                    const float sum = (float)((double)(scaleSquared * -2.0f) * ms->mix_log_weight[e0 + i]) + logNormFactor;
+                    c = std::fabs(sum) < 2147483648.0f ? (int)sum : INT_MIN;
+                }
+                else
+                    c = (int)((double)logNormFactor - (double)h->scale * ms->mix_log_weight[e0 + i]);
+                cc[r] = c + m2;
             }
             int flags = (t + 1 == nt ? 1 : 0) | (n == 0 ? 2 : 0);
             std::memcpy(tile + 8 * kRowBytes + 32, &flags, 4);
@@ -544,6 +559,7 @@ int rb_gmm_int_score(rb_gmm_int* h, const float* dFeats, long T, float* dScores,
     p.vec4         = (h->nMix % 4 == 0 && ((uintptr_t)dScores % 16 == 0)) ? 1 : 0;
     p.scale        = h->scale;
     p.rcpScale     = h->rcpScale;
+    p.simd         = h->simd ? 1 : 0;
     const long items = (long)p.nGroups * p.nFrameBlocks;
     gmm_int_kernel<<<(int)std::min<long>(items, slots), kThreads, h->smemBytes, s>>>(p);
     RB_LAUNCH_CHECK();

@@ -11,6 +11,9 @@
 // density as  c_k + sum_d (m_kd - x_cd)^2  in s32 over u8 means and keeps the first minimum over the densities of a
 // mixture; the result is (f32)(0.5 * int / scaling^2), evaluated in f64.  Integer arithmetic is exact, so
 //     c_k + sum_d (m_kd - x_cd)^2  =  (c_k + |m_k|^2) + |x_c|^2 - 2 m_k.x_c
+// Two kernels.  (1) Pooled covariance and scores only -- what the recognizer asks for: the IMMA kernel of gmm_int.cu
+// (mma.sync u8 x u8 -> s32 on the tensor cores) with this scorer's density constants and score formula.  (2) Everything
+// else (several covariances, best densities wanted): the kernel below,
 // with the u8 x u8 inner product on DP4A (4 products per instruction).  A thread owns two frames whose quantised
 // features stay in registers (pooled covariance, the usual RASR model) and walks the densities of a group of
 // mixtures staged in shared memory: every mean word is one broadcast LDS.128 for the whole CTA, so a (frame, density)
@@ -26,6 +29,12 @@ struct rb_gmm_simd;
 int  rb_gmm_simd_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_simd** out);
 void rb_gmm_simd_destroy(rb_gmm_simd* h);
 int  rb_gmm_simd_score(rb_gmm_simd* h, const float* d_feats, long T, float* d_scores, uint32_t* d_best, cudaStream_t stream);
+
+// gmm_int.cu: the tensor-core (IMMA) kernel of the batch-int scorer, with this scorer's constants and score formula
+struct rb_gmm_int;
+int  rb_gmm_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_int** out, bool simd);
+void rb_gmm_int_destroy(rb_gmm_int* h);
+int  rb_gmm_int_score(rb_gmm_int* h, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
 
 namespace {
 
@@ -48,6 +57,7 @@ struct SimdParams {
     uint32_t*       best;     // [T][nMix] or nullptr
     long            T;        // frames of this slice
     int             nMix, nGroups, nFrameBlocks;
+    int             vec4;     // nMix % 4 == 0, 16-byte aligned outputs: four mixtures per store
     float           scalingSquared;
 };
 
@@ -136,51 +146,77 @@ __global__ void __launch_bounds__(kThreads) gmm_simd_kernel(const SimdParams p) 
                 xs[f] = __ldg(p.xsq + t[f]);
             }
         }
-        for (int m = m0; m < m1; ++m) {
-            const uint32_t a = p.mixOff[m] - k0, b = p.mixOff[m + 1] - k0;
-            int      bestScore[kFpt];
-            uint32_t bestDns[kFpt];
+        // four mixtures at a time when the rows of the score matrix allow 16-byte stores (groups then start at
+        // multiples of 4): one STG.128 per frame instead of four scattered 4-byte stores
+        const int step = p.vec4 ? 4 : 1;
+        for (int mq = m0; mq < m1; mq += step) {
+            float    outS[kFpt][4];
+            uint32_t outB[kFpt][4];
+            for (int j = 0; j < step; ++j) {
+                const int      m = mq + j;
+                const uint32_t a = p.mixOff[m] - k0, b = p.mixOff[m + 1] - k0;
+                int      bestScore[kFpt];
+                uint32_t bestDns[kFpt];
 #pragma unroll
-            for (int f = 0; f < kFpt; ++f) {
-                bestScore[f] = INT_MAX;  // an empty mixture keeps Core::Type<int>::max and bestDensity = max
-                bestDns[f]   = 0xffffffffu;
-            }
-            for (uint32_t k = a; k < b; ++k) {
-                uint4 mean[NQ];
+                for (int f = 0; f < kFpt; ++f) {
+                    bestScore[f] = INT_MAX;  // an empty mixture keeps Core::Type<int>::max and bestDensity = max
+                    bestDns[f]   = 0xffffffffu;
+                }
+                for (uint32_t k = a; k < b; ++k) {
+                    uint4 mean[NQ];
 #pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    mean[q] = sMeans[(size_t)k * NQ + q];
-                const int c = sConst[k];
-                if (!ONE_COV) {
-                    const size_t row = (size_t)sCov[k] * p.T;
+                    for (int q = 0; q < NQ; ++q)
+                        mean[q] = sMeans[(size_t)k * NQ + q];
+                    const int c = sConst[k];
+                    if (!ONE_COV) {
+                        const size_t row = (size_t)sCov[k] * p.T;
+#pragma unroll
+                        for (int f = 0; f < kFpt; ++f) {
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q)
+                                x[f][q] = __ldg(p.xq + (row + t[f]) * NQ + q);
+                            xs[f] = __ldg(p.xsq + row + t[f]);
+                        }
+                    }
 #pragma unroll
                     for (int f = 0; f < kFpt; ++f) {
+                        int dot = 0;
 #pragma unroll
                         for (int q = 0; q < NQ; ++q)
-                            x[f][q] = __ldg(p.xq + (row + t[f]) * NQ + q);
-                        xs[f] = __ldg(p.xsq + row + t[f]);
+                            dot = dot16(mean[q], x[f][q], dot);
+                        const int score = c + xs[f] - 2 * dot;
+                        if (score < bestScore[f]) {  // the first minimum wins (:166-169)
+                            bestScore[f] = score;
+                            bestDns[f]   = k - a;
+                        }
                     }
                 }
 #pragma unroll
                 for (int f = 0; f < kFpt; ++f) {
-                    int dot = 0;
+                    // result.score = 0.5 * quantizedResult.first / scalingSquared_  (f64, then Score = f32)
+                    const float sc = (float)(0.5 * (double)bestScore[f] / (double)p.scalingSquared);
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q)
-                        dot = dot16(mean[q], x[f][q], dot);
-                    const int score = c + xs[f] - 2 * dot;
-                    if (score < bestScore[f]) {  // the first minimum wins (:166-169)
-                        bestScore[f] = score;
-                        bestDns[f]   = k - a;
-                    }
+                    for (int jj = 0; jj < 4; ++jj)  // static register indices
+                        if (jj == j) {
+                            outS[f][jj] = sc;
+                            outB[f][jj] = bestDns[f];
+                        }
                 }
             }
 #pragma unroll
             for (int f = 0; f < kFpt; ++f)
                 if (live[f]) {
-                    // result.score = 0.5 * quantizedResult.first / scalingSquared_  (f64, then Score = f32)
-                    p.scores[(size_t)t[f] * p.nMix + m] = (float)(0.5 * (double)bestScore[f] / (double)p.scalingSquared);
-                    if (p.best)
-                        p.best[(size_t)t[f] * p.nMix + m] = bestDns[f];
+                    const size_t at = (size_t)t[f] * p.nMix + mq;
+                    if (p.vec4) {
+                        *reinterpret_cast<float4*>(p.scores + at) = make_float4(outS[f][0], outS[f][1], outS[f][2], outS[f][3]);
+                        if (p.best)
+                            *reinterpret_cast<uint4*>(p.best + at) = make_uint4(outB[f][0], outB[f][1], outB[f][2], outB[f][3]);
+                    }
+                    else {
+                        p.scores[at] = outS[f][0];
+                        if (p.best)
+                            p.best[at] = outB[f][0];
+                    }
                 }
         }
     }
@@ -203,6 +239,13 @@ struct rb_gmm_simd {
     rb::DevBuf<int>       dConsts, dGrpMix, dXsq;
     rb::DevBuf<uint32_t>  dCov, dMixOff;
     rb::DevBuf<float>     dIsd;
+    // pooled covariance and no density output wanted: the same integers come out of the IMMA kernel of gmm_int.cu
+    // (u8 x u8 products on the tensor cores, 3.5 x the DP4A rate); the kernel above serves the rest
+    rb_gmm_int*           imma = nullptr;
+    ~rb_gmm_simd() {
+        if (imma)
+            rb_gmm_int_destroy(imma);
+    }
 };
 
 int rb_gmm_simd_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream, rb_gmm_simd** out) {
@@ -294,7 +337,7 @@ int rb_gmm_simd_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cuda
     size_t           used = 0, largest = 0;
     for (uint32_t m = 0; m < ms->n_mixtures; ++m) {
         const size_t bytes = (size_t)(ms->mix_offsets[m + 1] - ms->mix_offsets[m]) * (rowBytes + 8);
-        if (used && used + bytes > kGroupBytes) {
+        if (used && used + bytes > kGroupBytes && (ms->n_mixtures % 4 != 0 || m % 4 == 0)) {
             grpMix.push_back((int)m);
             used = 0;
         }
@@ -316,6 +359,14 @@ int rb_gmm_simd_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cuda
         rb::set_error("SIMD gmm model upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(RB_ERR_CUDA);
     }
+    bool pooled = nCov == 1;
+    for (uint32_t i = 0; i < ms->n_densities && pooled; ++i)
+        pooled = ms->dens_cov[i] == 0;
+    if (pooled && getenv("RB_GMM_SIMD_DP4A") == nullptr) {
+        int rc = rb_gmm_int_create(ms, dev, stream, &h->imma, true);
+        if (rc != RB_OK)
+            return fail(rc);
+    }
     *out = h;
     return RB_OK;
 }
@@ -336,6 +387,8 @@ static int launch_simd(rb_gmm_simd* h, const SimdParams& p, cudaStream_t s) {
 }
 
 int rb_gmm_simd_score(rb_gmm_simd* h, const float* dFeats, long T, float* dScores, uint32_t* dBest, cudaStream_t s) {
+    if (h->imma && !dBest)
+        return rb_gmm_int_score(h->imma, dFeats, T, dScores, s);
     // slices of frames: the table of quantised features [covariance][frame] stays below kTableBytes
     const size_t perFrame = (size_t)h->nCov * ((size_t)h->nq * 16 + 4);
     long         slice    = (long)std::max<size_t>(kBlockFrames, kTableBytes / perFrame / kBlockFrames * kBlockFrames);
@@ -364,6 +417,7 @@ int rb_gmm_simd_score(rb_gmm_simd* h, const float* dFeats, long T, float* dScore
         p.nGroups        = h->nGroups;
         p.nFrameBlocks   = (int)((n + kBlockFrames - 1) / kBlockFrames);
         p.scalingSquared = h->scalingSquared;
+        p.vec4           = (h->nMix % 4 == 0 && (uintptr_t)p.scores % 16 == 0 && (uintptr_t)p.best % 16 == 0) ? 1 : 0;
         int rc = h->nq == 1 ? launch_simd<1>(h, p, s)
                             : (h->nq == 2 ? launch_simd<2>(h, p, s) : (h->nq == 3 ? launch_simd<3>(h, p, s) : launch_simd<4>(h, p, s)));
         if (rc != RB_OK)

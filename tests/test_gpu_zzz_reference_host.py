@@ -101,6 +101,7 @@ def test_mfcc_node_with_dc_detection(ref):
 
 
 PAIRS = [("batch-diagonal-maximum-float", "b200-batch-float"), ("batch-diagonal-maximum-int", "b200-batch-int"),
+         ("SIMD-diagonal-maximum", "b200-SIMD-diagonal-maximum"),
          ("preselection-batch-float", "b200-preselection-batch-float"),
          ("preselection-batch-int", "b200-preselection-batch-int")]
 
@@ -127,7 +128,7 @@ def test_strict_variant_and_preselection_resources(ref, oms):
     assert np.array_equal(a, b)
     cfg = {"density-clustering.clusters": 64, "density-clustering.select-clusters": 8,
            "density-clustering.iterations": 3, "density-clustering.backoff-score": 777.0}
-    for theirs, ours in PAIRS[2:]:
+    for theirs, ours in PAIRS[3:]:
         a = ref.FeatureScorer(ms, theirs, cfg, native=True).score(f)
         b = ref.FeatureScorer(ms, ours, cfg, native=True).score(f)
         assert np.array_equal(a, b), ours
@@ -146,6 +147,10 @@ def test_diagonal_scorers_from_the_references_factory(ref, oms, diag):
     assert rel < 1e-6
     c = ref.FeatureScorer(ms, "b200-diagonal-maximum", native=True).score(f)
     assert float((np.abs(c - a) / np.abs(a)).max()) < 1e-6  # contracted variant: an ulp or two
+    # the quantised scorer with one quantised feature vector per covariance: integer arithmetic, identical bits
+    q = ref.FeatureScorer(ms, "SIMD-diagonal-maximum", native=True).score(f)
+    r = ref.FeatureScorer(ms, "b200-SIMD-diagonal-maximum", native=True).score(f)
+    assert np.array_equal(q, r)
 
 
 def test_tensor_mode_through_the_adapter(ref, oms):
