@@ -66,3 +66,13 @@ def reference_search_golden():
         c["entry_model"] = 0
         c["single_word"] = bool(c["single_word"])
     return cases
+
+
+@pytest.fixture(scope="session")
+def simd_golden_cases():
+    """models and frames behind tests/golden/ref_gmm_simd.npz (tests/golden/make_golden.py simd_scorer)"""
+    from rasr_b200 import synth
+    return {"c2": lambda: (synth.mixture_set(), synth.features(100000, 39)[:96]),
+            "ragged": lambda: (synth.ragged_mixture_set(dim=39, n_covariances=1), synth.features(64, 39, seed=5)),
+            "ragged_3cov": lambda: (synth.ragged_mixture_set(dim=24, n_covariances=3, seed=11),
+                                    synth.features(64, 24, seed=6))}

@@ -31,16 +31,31 @@ def scorers(ms, f, names, config=None):
         for native in (False, True):
             key = "%s/%s" % (name, "native" if native else "strict")
             sc = pyref.FeatureScorer(ms, name, config, native=native)
-            if name.startswith("diagonal"):
+            if name.startswith("diagonal") or name.startswith("SIMD"):
                 out[key], out[key + "/best"] = sc.score(f, want_best=True)
             else:
                 out[key] = sc.score(f)
     return out
 
 
+def simd_scorer():
+    """4c. "SIMD-diagonal-maximum" (scores and best densities) on the three models above -> ref_gmm_simd.npz
+    (python tests/golden/make_golden.py simd writes this file alone)"""
+    d = dict(source=SOURCE)
+    cases = (("c2", synth.mixture_set(), synth.features(100000, 39)[:96]),
+             ("ragged", synth.ragged_mixture_set(dim=39, n_covariances=1), synth.features(64, 39, seed=5)),
+             ("ragged_3cov", synth.ragged_mixture_set(dim=24, n_covariances=3, seed=11), synth.features(64, 24, seed=6)))
+    for tag, msd, f in cases:
+        for k, v in scorers(o.MixtureSet(**msd), f, ["SIMD-diagonal-maximum"]).items():
+            d["%s/%s" % (tag, k)] = v
+    np.savez_compressed(os.path.join(HERE, "ref_gmm_simd.npz"), **d)
+
+
 def main():
     o.build(ref=True)
     pyref.build()
+    if sys.argv[1:] == ["simd"]:
+        return simd_scorer()
     # 1. BASELINE config C1: the 10 s utterance through the reference's own flow files, 999 x 39
     n, seed = 160000, 1234
     x = synth.utterance(n, seed)
@@ -96,6 +111,7 @@ def main():
     f = synth.features(64, 24, seed=6)
     np.savez_compressed(os.path.join(HERE, "ref_gmm_ragged_3cov.npz"), source=SOURCE,
                         **scorers(ms, f, ["diagonal-maximum", "diagonal-sum"]))
+    simd_scorer()
     # 5. post-processing: signal-normalization -> sequence concatenation -> matrix multiplication (lda.flow wiring)
     ff = synth.features(300, 13, seed=5)
     M = np.random.default_rng(3).standard_normal((20, 65)).astype(np.float32)

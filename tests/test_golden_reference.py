@@ -89,6 +89,20 @@ def test_ragged_model_three_covariances(oracle):
     _check_scorers(oracle, g, ms, synth.features(64, 24, seed=6))
 
 
+@pytest.mark.parametrize("tag", ["c2", "ragged", "ragged_3cov"])
+def test_simd_diagonal_maximum(oracle, simd_golden_cases, tag):
+    """"SIMD-diagonal-maximum": integer arithmetic, so the strict and the contracted build of the reference agree and
+    the oracle reproduces both, best densities included"""
+    g = load("ref_gmm_simd.npz")
+    msd, f = simd_golden_cases[tag]()
+    s, b = oracle.gmm_simd_diag_max(oracle.MixtureSet(**msd), f, want_best=True)
+    nonempty = np.diff(msd["mix_offsets"]) > 0
+    for build in ("strict", "native"):
+        key = "%s/SIMD-diagonal-maximum/%s" % (tag, build)
+        assert np.array_equal(s[:, nonempty], g[key][:, nonempty])
+        assert np.array_equal(b[:, nonempty], g[key + "/best"][:, nonempty])
+
+
 def test_postprocessing(oracle):
     g = load("ref_postproc.npz")
     f = synth.features(300, 13, seed=5)

@@ -130,6 +130,20 @@ def test_ragged_model_three_covariances(diag):
                    "ragged_3cov", batch=False)
 
 
+@pytest.mark.parametrize("tag", ["c2", "ragged", "ragged_3cov"])
+def test_simd_diagonal_maximum(simd_golden_cases, tag):
+    """the reference's "SIMD-diagonal-maximum" scorer (object code, tests/golden/make_golden.py) vs RB_GMM_SIMD_DIAG_MAX:
+    scores through the IMMA kernel (pooled covariance) and, with densities, through the DP4A kernel -- bit for bit"""
+    g = load("ref_gmm_simd.npz")
+    msd, f = simd_golden_cases[tag]()
+    sc = mm.GmmScorer(mm.MixtureSet.from_dict(msd), "SIMD-diagonal-maximum")
+    nonempty = np.diff(msd["mix_offsets"]) > 0
+    want, wbest = g["%s/SIMD-diagonal-maximum/native" % tag], g["%s/SIMD-diagonal-maximum/native/best" % tag]
+    assert np.array_equal(sc.score(f)[:, nonempty], want[:, nonempty])
+    s, b = sc.score(f, want_density=True)
+    assert np.array_equal(s[:, nonempty], want[:, nonempty]) and np.array_equal(b[:, nonempty], wbest[:, nonempty])
+
+
 def test_postprocessing_against_the_references_nodes():
     g = load("ref_postproc.npz")
     f = synth.features(300, 13, seed=5)
