@@ -60,8 +60,7 @@ class GmmScorer:
     MODES = {"batch-float": capi.GMM_BATCH_FLOAT, "diagonal-maximum": capi.GMM_DIAG_MAX,
              "diagonal-sum": capi.GMM_DIAG_SUM, "batch-tensor": capi.GMM_BATCH_TENSOR,
              "batch-int": capi.GMM_BATCH_INT, "preselection-batch-float": capi.GMM_BATCH_PRESELECT,
-             "preselection-batch-int": capi.GMM_BATCH_PRESELECT_INT, "SIMD-diagonal-maximum": capi.GMM_SIMD_DIAG_MAX,
-             "simd-diagonal-maximum": capi.GMM_SIMD_DIAG_MAX}
+             "preselection-batch-int": capi.GMM_BATCH_PRESELECT_INT, "SIMD-diagonal-maximum": capi.GMM_SIMD_DIAG_MAX}
 
     def __init__(self, mixture_set, mode="batch-float", mixture_weight_scale=1.0, gaussian_scale=1.0,
                  contraction=True, device=0):

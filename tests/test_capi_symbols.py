@@ -84,3 +84,4 @@ def test_scorer_mode_constants_match_the_header():
     assert enum == {"RB_" + k: getattr(capi, k) for k in dir(capi) if k.startswith("GMM_")}
     assert sorted(mm.GmmScorer.MODES.values()) == sorted(enum.values())
     assert mm.GmmScorer.MODES["preselection-batch-int"] == enum["RB_GMM_BATCH_PRESELECT_INT"]
+    assert mm.GmmScorer.MODES["SIMD-diagonal-maximum"] == enum["RB_GMM_SIMD_DIAG_MAX"]  # name as in src/Mm/Module.cc:88
