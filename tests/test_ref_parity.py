@@ -385,6 +385,31 @@ def test_nn_batch_feature_scorer(ref, oracle, tmp_path, hidden):
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("name", ["nn-full-hybrid"])
+def test_nn_frame_at_a_time_scorers(ref, oracle, tmp_path, name):
+    """the reference's unbuffered Nn scorer (src/Nn/FeatureScorer.cc:187-253: the whole network per frame) computes the
+    function of nn-batch-feature-scorer: -(w_e.h + b_e - priori-scale * logprior_e), softmax not evaluated.  One oracle
+    (and one CUDA path, the b200-nn-batch-feature-scorer adapter) therefore stands for both.
+    (nn-on-demand-hybrid, :97-170, is meant to compute the same per requested output unit, but it cannot be run: its
+    forwardHiddenLayers() calls finishComputation() on the activation that LinearAndSoftmaxLayer::getScore then hands
+    to CudaMatrix::dotWithColumn, whose precondition X.isComputing_ aborts the process -- observed with the reference's
+    object code, src/Math/CudaMatrix.hh:1052.)"""
+    net = synth.network(dims=(20, 32, 24, 16), hidden="sigmoid", seed=3)
+    cfg = nn_files(tmp_path, net, "sigmoid")
+    io.write_vector("xml:" + str(tmp_path / "prior.xml"), net["log_prior"])
+    cfg.update({"prior-file": "xml:" + str(tmp_path / "prior.xml"), "priori-scale": 0.7})
+    ms = oracle.MixtureSet(**synth.mixture_set(dim=20, n_mixtures=16, densities_per_mixture=1))
+    x = synth.features(23, 20, seed=9, scale=1.0)
+    got = ref.FeatureScorer(ms, name, cfg).score(x)
+    want = oracle.nn_scores(net["dims"], net["acts"], net["weights"], net["biases"], net["log_prior"], 0.7, x,
+                            mode=oracle.NN_F32)
+    batch = ref.FeatureScorer(ms, "nn-batch-feature-scorer", dict(cfg, **{"buffer-size": 8})).score(x)
+    assert got.shape == (23, 16)
+    # matrix-vector instead of matrix-matrix products below the same layers: summation order may differ by an ulp
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
+    assert np.abs(got - batch).max() / np.abs(batch).max() < 2e-6
+
+
 def test_nn_prior_from_mixture_weights(ref, oracle, tmp_path):
     """without a prior file the prior is the relative mixture-weight mass of each class (Prior::setFromMixtureSet,
     src/Nn/Prior.cc:158-188)"""
