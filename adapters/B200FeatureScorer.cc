@@ -22,7 +22,7 @@ const Core::ParameterInt   GmmFeatureScorer::paramClusteringIterations("iteratio
 const Core::ParameterFloat GmmFeatureScorer::paramBackoffScore("backoff-score", "score used if no cluster is selected", 40000);
 const Core::ParameterFloat GmmFeatureScorer::paramGaussianScale("gaussian-scale", "scale of the Gaussian exponent (diagonal scorers)", 1.0);
 
-class FeatureScorer::ContextScorer : public Mm::FeatureScorer::ContextScorer {
+class FeatureScorer::ContextScorer : public Mm::FeatureScorer::ContextScorer, public DenseScoreRow {
 public:
     ContextScorer(const FeatureScorer* parent, u32 segment, u32 frame)
             : parent_(parent), segment_(segment), frame_(frame) {}
@@ -31,6 +31,9 @@ public:
     }
     virtual Mm::Score score(Mm::EmissionIndex e) const {
         return parent_->score(segment_, frame_, e);
+    }
+    virtual const f32* scoreRow() const {
+        return parent_->row(segment_, frame_);
     }
 
 private:
@@ -154,6 +157,13 @@ Mm::Score FeatureScorer::score(u32 segment, u32 frame, Mm::EmissionIndex e) cons
     if (frame >= nScored_)
         scoreBufferedFrames();
     return scores_[size_t(frame) * nMixtures_ + e];
+}
+
+const f32* FeatureScorer::row(u32 segment, u32 frame) const {
+    require_eq(segment, segment_);
+    if (frame >= nScored_)
+        scoreBufferedFrames();
+    return scores_.data() + size_t(frame) * nMixtures_;
 }
 
 // ---- Nn -------------------------------------------------------------------------------------------------------------

@@ -22,6 +22,16 @@
 
 namespace B200 {
 
+/** Implemented by the ContextScorers the b200 feature scorers hand out: the whole row of emission scores of the frame
+ *  at once.  A consumer that wants every score of a frame anyway (B200::LinearSearch::feed) takes the row instead of
+ *  nEmissions() virtual score(e) calls. */
+class DenseScoreRow {
+public:
+    virtual ~DenseScoreRow() {}
+    /** nEmissions() scores of this scorer's frame; valid until the feature scorer is reset() */
+    virtual const f32* scoreRow() const = 0;
+};
+
 /** Buffering half of the adapters: collects the segment, scores all frames not scored yet in one call of the
  *  subclass, answers ContextScorer::score(e) from the dense matrix. */
 class FeatureScorer : public Mm::FeatureScorer {
@@ -71,8 +81,9 @@ private:
     class ContextScorer;
     friend class ContextScorer;
 
-    Mm::Score score(u32 segment, u32 frame, Mm::EmissionIndex e) const;
-    void      scoreBufferedFrames() const;
+    Mm::Score  score(u32 segment, u32 frame, Mm::EmissionIndex e) const;
+    const f32* row(u32 segment, u32 frame) const;
+    void       scoreBufferedFrames() const;
 
 protected:
     /** scores [T x nMixtures_] of feats [T x dimension_], both row-major */

@@ -1,5 +1,7 @@
 #include "B200LinearSearch.hh"
 
+#include "B200FeatureScorer.hh"
+
 #include <Am/ClassicStateModel.hh>
 #include <Lattice/LatticeAdaptor.hh>
 #include <Lm/ScaledLanguageModel.hh>
@@ -19,6 +21,8 @@ LinearSearch::LinearSearch(const Core::Configuration& c)
           handle_(0),
           nEmissions_(0),
           time_(0),
+          nDenseRows_(0),
+          nScoreCalls_(0),
           decodedTime_(0) {
     log("using B200 linear search") << (singleWordRecognition_ ? " (single-word recognition)" : "");
 }
@@ -130,8 +134,15 @@ void LinearSearch::feed(const Mm::FeatureScorer::Scorer& emissionScores) {
     const size_t at = scores_.size();
     scores_.resize(at + nEmissions_);
     f32* row = scores_.data() + at;
-    for (u32 e = 0; e < nEmissions_; ++e)
-        row[e] = emissionScores->score(e);
+    if (const DenseScoreRow* dense = dynamic_cast<const DenseScoreRow*>(emissionScores.get())) {
+        std::memcpy(row, dense->scoreRow(), nEmissions_ * sizeof(f32));  // a b200 feature scorer: the row is there already
+        ++nDenseRows_;
+    }
+    else {
+        for (u32 e = 0; e < nEmissions_; ++e)
+            row[e] = emissionScores->score(e);
+        nScoreCalls_ += nEmissions_;
+    }
     ++time_;
 }
 
@@ -174,6 +185,15 @@ void LinearSearch::getCurrentBestSentence(Search::Traceback& result) const {
     Lm::extendHistoryByLemmaPronunciation(lm_, pronunciations_[words_.back()], h);
     result.push_back(Item(0, time_, Search::ScoreVector(am_.back(), lmScores_.back() + lm_->sentenceEndScore(h)), Item::Transit()));
     log("returning %zu words", words_.size());
+}
+
+void LinearSearch::resetStatistics() {
+    nDenseRows_ = nScoreCalls_ = 0;
+}
+
+void LinearSearch::logStatistics() const {
+    log("b200 linear search: %llu frames taken as dense score rows, %llu score() calls", (unsigned long long)nDenseRows_,
+        (unsigned long long)nScoreCalls_);
 }
 
 void LinearSearch::getPartialSentence(Search::Traceback& result) {

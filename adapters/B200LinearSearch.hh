@@ -41,8 +41,16 @@ public:
     virtual void getPartialSentence(Search::Traceback& result);
     virtual void getCurrentBestSentence(Search::Traceback& result) const;
     virtual Core::Ref<const Search::LatticeAdaptor> getCurrentWordLattice() const;
-    virtual void resetStatistics() {}
-    virtual void logStatistics() const {}
+    virtual void resetStatistics();
+    virtual void logStatistics() const;
+
+    /** frames whose scores arrived as a whole row from a b200 feature scorer / through score(e) calls */
+    u64 nDenseRows() const {
+        return nDenseRows_;
+    }
+    u64 nScoreCalls() const {
+        return nScoreCalls_;
+    }
 
 private:
     void decode() const;
@@ -57,6 +65,7 @@ private:
     u32                                           nEmissions_;
     HostBuffer                                    scores_;  // [time_ x nEmissions_] rows collected by feed()
     TimeframeIndex                                time_;
+    u64                                           nDenseRows_, nScoreCalls_;
     // result of the last decode (getCurrentBestSentence is const, like the reference's)
     mutable TimeframeIndex      decodedTime_;
     mutable std::vector<u32>    words_;

@@ -173,8 +173,10 @@ class FeatureScorer:
     oracle.pyoracle.MixtureSet (same C layout).  `config`: resources below the scorer's selection, e.g.
     {"density-clustering.clusters": 64, "buffer-size": 4}."""
 
-    def __init__(self, ms, scorer_type, config=None, native=False, selection=None):
-        self._L = lib(native)
+    def __init__(self, ms, scorer_type, config=None, native=False, selection=None, library=None):
+        # library: another self-contained copy of the reference's object code (search_lib()) instead of lib(native)
+        self._L = library or lib(native)
+        self._L.ref_mm_create.restype = C.c_void_p
         FeatureScorer._count = getattr(FeatureScorer, "_count", 0) + 1
         sel = selection or "feature-scorer-%d" % FeatureScorer._count
         for k, v in (config or {}).items():
@@ -325,6 +327,11 @@ def load_search_adapter():
             build()
         _search_adapter = C.CDLL(p, mode=C.RTLD_GLOBAL)
         _search_adapter.b200_search_adapter_register()
+        # the other adapters (feature scorers, Flow nodes) into the same host: INIT_MODULE(B200) registers them with the
+        # Mm / Flow factories of the search library, which carries the same reference objects as librasr_ref.so
+        a = C.CDLL(os.path.join(_HERE, "_ref", "libb200_adapters.so"), mode=C.RTLD_GLOBAL)
+        a.b200_adapters_register()
+        _search_adapter._others = a
     return _search_adapter
 
 
@@ -426,6 +433,16 @@ class LinearSearch:
         n = self._S.ref_search_run(self._h, _p(scores), C.c_long(T), self.n_emissions, _p(words), _p(times), _p(am),
                                    _p(lm), C.c_long(cap), _p(fin))
         return words[:n].copy(), times[:n].copy(), am[:n].copy(), lm[:n].copy(), fin
+
+    def run_features(self, feature_scorer, feats):
+        """the recognizer's loop: every feature vector through `feature_scorer` (a FeatureScorer made with
+        library=search_lib()), every scorer object it hands out into the search; then items()"""
+        feats = np.ascontiguousarray(feats, np.float32)
+        self._S.ref_search_run_features.restype = C.c_long
+        n = self._S.ref_search_run_features(self._h, C.c_void_p(feature_scorer._h), _p(feats), C.c_long(feats.shape[0]),
+                                            int(feats.shape[1]))
+        if n != feats.shape[0]:
+            raise RuntimeError("ref_search_run_features fed %d of %d frames" % (n, feats.shape[0]))
 
     def items(self, capacity=4096):
         """every item of getCurrentBestSentence after run(): (word or -2, time, acoustic, lm) arrays"""

@@ -316,6 +316,11 @@ void ref_mm_destroy(void* handle) {
     delete static_cast<MmHandle*>(handle);
 }
 
+/* the scorer object itself (an Mm::FeatureScorer*), for hosts that feed it to other reference code (ref_search.cc) */
+void* ref_mm_feature_scorer(void* handle) {
+    return static_cast<MmHandle*>(handle)->fs.get();
+}
+
 int ref_mm_n_mixtures(void* handle) {
     return static_cast<MmHandle*>(handle)->fs->nMixtures();
 }

@@ -29,6 +29,7 @@
 #include <Core/Configuration.hh>
 #include <Lm/LanguageModel.hh>
 #include <Lm/ScaledLanguageModel.hh>
+#include <Mm/Feature.hh>
 #include <Mm/FeatureScorer.hh>
 #include <Search/LinearSearch.hh>
 #include <Search/Traceback.hh>
@@ -40,7 +41,8 @@
 #include <string>
 #include <vector>
 
-extern "C" int ref_init(const char* log_file);
+extern "C" int   ref_init(const char* log_file);
+extern "C" void* ref_mm_feature_scorer(void* handle);  // ref_host.cc
 
 // ---------------------------------------------------------------------------------------------------------
 // stand-ins for symbols whose home translation units cannot be compiled here (see the header comment)
@@ -399,6 +401,32 @@ long ref_search_run(void* handle, const float* scores, long T, int n_emissions, 
         ++n;
     }
     return n;
+}
+
+/* The recognizer's loop (src/Speech/Recognizer.cc:271-281 processFeature, :197-205 finish) over one segment: the
+ * feature scorer of ref_mm_create (mm_handle) turns every feature vector into a scorer object -- buffered scorers get
+ * addFeature() until bufferFilled(), then getScorer() per further frame and flush() at the end -- and every scorer
+ * is fed to the search.  Read the result with ref_search_items. */
+long ref_search_run_features(void* handle, void* mm_handle, const float* feats, long T, int dim) {
+    SearchHandle*            h  = (SearchHandle*)handle;
+    const Mm::FeatureScorer& fs = *static_cast<const Mm::FeatureScorer*>(ref_mm_feature_scorer(mm_handle));
+    h->search->restart();
+    fs.reset();
+    long fed = 0;
+    for (long t = 0; t < T; ++t) {
+        Core::Ref<const Mm::Feature> f(new Mm::Feature(Mm::FeatureVector(feats + (size_t)t * dim, feats + (size_t)(t + 1) * dim)));
+        if (fs.isBuffered() && !fs.bufferFilled())
+            fs.addFeature(f);
+        else {
+            h->search->feed(fs.getScorer(f));
+            ++fed;
+        }
+    }
+    while (fs.isBuffered() && !fs.bufferEmpty()) {
+        h->search->feed(fs.flush());
+        ++fed;
+    }
+    return fed;
 }
 
 }  // extern "C"

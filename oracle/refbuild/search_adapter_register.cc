@@ -7,8 +7,16 @@
 
 extern "C" void ref_search_set_factory(void* factory);
 
+static B200::LinearSearch* newest = 0;
+
 static Search::SearchAlgorithm* makeB200LinearSearch(const Core::Configuration& c) {
-    return new B200::LinearSearch(c);
+    return newest = new B200::LinearSearch(c);
+}
+
+/* of the adapter created last: frames whose scores arrived as whole rows (out[0]) and score(e) calls made (out[1]) */
+extern "C" void b200_search_adapter_statistics(unsigned long long* out) {
+    out[0] = newest ? newest->nDenseRows() : 0;
+    out[1] = newest ? newest->nScoreCalls() : 0;
 }
 
 extern "C" void b200_search_adapter_register() {

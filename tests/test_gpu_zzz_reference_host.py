@@ -309,5 +309,9 @@ def test_linear_search_adapter_next_to_the_reference_search(diag):
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["ok"], out
-    assert set(out["items"]) == {"continuous", "continuous_scaled", "single_word", "single_word_noise", "single_word_ties"}
+    assert set(out["items"]) == {"continuous", "continuous_scaled", "single_word", "single_word_noise", "single_word_ties",
+                                 "whole_path"}
+    # whole_path: feature vectors -> b200-batch-float (adapter) -> B200::LinearSearch (adapter, dense score rows) against
+    # the reference's scorer feeding the reference's search, through the recognizer's own loop
+    assert out["items"]["whole_path"] > 0
     diag("search_adapter_in_reference_host", **{k: int(v) for k, v in out["items"].items()})
