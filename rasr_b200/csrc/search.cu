@@ -825,21 +825,22 @@ struct rb_search {
     uint32_t             maxEmis = 0;
     rb::DevBuf<float>    dTdp, dUnigram, dHypScore, dHypLm, dEndScore, dScores;
     rb::DevBuf<int>      dHypBkp, dBooks, dNBooks;  // dBooks: 8 words per frame (two int4 per book entry)
-    std::vector<int>     hostBooks;
+    rb::PinnedBuf<int>   hostBooks;  // page-locked: the copy back runs at the PCIe rate and does not stage
     // single-word recognition: W / nStates count the ENTRIES of the search (irregular words twice)
     bool                  single = false;
     uint32_t              nIrr   = 0;
     rb::DevBuf<uint8_t>   dFlags;
     rb::DevBuf<uint32_t>  dEntryWord, dIrrList;
     rb::DevBuf<int>       dIrrBooks, dNIrrBooks;
-    std::vector<int>      hostIrrBooks, nIrrBooks;
+    rb::PinnedBuf<int>    hostIrrBooks;
+    std::vector<int>      nIrrBooks;
     rb::DevBuf<int64_t>  dFrameOff;
     // results of the last decode, on the host
     std::vector<int64_t> frameOff;
     std::vector<int>     nBooks;
     // the record a back pointer names (>= 0: main book, <= -2: entry -2 - bkp of the irregular book) in segment f0
     const int* record(int64_t f0, int ref) const {
-        return ref >= 0 ? hostBooks.data() + (f0 + ref) * 8 : hostIrrBooks.data() + (f0 + (-2 - ref)) * 8;
+        return ref >= 0 ? hostBooks.p + (f0 + ref) * 8 : hostIrrBooks.p + (f0 + (-2 - ref)) * 8;
     }
     ~rb_search() {
         if (stream)
@@ -1129,13 +1130,13 @@ extern "C" int rb_search_decode_dev(rb_search* h, const float* d_scores, int n_e
         linear_search_kernel<<<n_utt, kThreads, p.useSmem ? smem : 0, s>>>(p);
     }
     RB_LAUNCH_CHECK();
-    h->hostBooks.resize((size_t)T * 8);
-    RB_CUDA(cudaMemcpyAsync(h->hostBooks.data(), h->dBooks.p, sizeof(int) * 8 * T, cudaMemcpyDeviceToHost, s));
+    RB_CHECK(h->hostBooks.reserve((size_t)T * 8));
+    RB_CUDA(cudaMemcpyAsync(h->hostBooks.p, h->dBooks.p, sizeof(int) * 8 * T, cudaMemcpyDeviceToHost, s));
     RB_CUDA(cudaMemcpyAsync(h->nBooks.data(), h->dNBooks.p, sizeof(int) * n_utt, cudaMemcpyDeviceToHost, s));
     if (h->single) {
-        h->hostIrrBooks.resize((size_t)T * 8);
+        RB_CHECK(h->hostIrrBooks.reserve((size_t)T * 8));
         h->nIrrBooks.assign(n_utt, 0);
-        RB_CUDA(cudaMemcpyAsync(h->hostIrrBooks.data(), h->dIrrBooks.p, sizeof(int) * 8 * T, cudaMemcpyDeviceToHost, s));
+        RB_CUDA(cudaMemcpyAsync(h->hostIrrBooks.p, h->dIrrBooks.p, sizeof(int) * 8 * T, cudaMemcpyDeviceToHost, s));
         RB_CUDA(cudaMemcpyAsync(h->nIrrBooks.data(), h->dNIrrBooks.p, sizeof(int) * n_utt, cudaMemcpyDeviceToHost, s));
     }
     RB_CUDA(cudaStreamSynchronize(s));

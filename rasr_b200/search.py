@@ -50,8 +50,8 @@ class LinearSearch:
         n_utt = self._fo.size - 1
         cap = max(1, int(self._fo[-1] - self._fo[0]))
         wo = np.zeros(n_utt + 1, np.int64)
-        words, times = np.zeros(cap, np.uint32), np.zeros(cap, np.int32)
-        am, lm = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        words, times = np.empty(cap, np.uint32), np.empty(cap, np.int32)  # filled up to the returned count
+        am, lm = np.empty(cap, np.float32), np.empty(cap, np.float32)
         n = capi.lib().rb_search_traceback_all(self._h, capi.ptr(wo), capi.ptr(words), capi.ptr(times), capi.ptr(am),
                                                capi.ptr(lm), cap)
         if n < 0:
