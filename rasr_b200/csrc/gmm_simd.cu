@@ -42,7 +42,8 @@ constexpr int    kThreads     = 256;
 constexpr int    kFpt         = 2;                  // frames per thread
 constexpr int    kBlockFrames = kThreads * kFpt;    // 512
 constexpr int    kMaxDim      = 64;
-constexpr size_t kGroupBytes  = 64 * 1024;          // shared memory of one mixture group (means + constants)
+constexpr size_t kGroupBytes  = 16 * 1024;          // shared memory of one mixture group (means + constants): small groups = many
+                                                    // work items also for the 2048..16384-frame slabs of the host-buffer calls
 constexpr size_t kTableBytes  = 256u << 20;         // quantised features of one slice of frames, all covariances
 
 struct SimdParams {
