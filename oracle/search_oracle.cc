@@ -107,7 +107,7 @@ extern "C" long orc_linear_search(const orc_lexicon* lx, const float* scores, lo
                 h[0].score   = 0;
             }
             h[0].score += h[0].lmScore;
-            tmp.resize(h.size());
+            tmp.resize(h.size(), Hypo{FLT_MAX, 0.0f, -1}); /* new elements: value-initialised in the reference, bkp = null */
             for (uint32_t sta = 1; sta < h.size(); ++sta) {
                 tmp[sta].score   = FLT_MAX;
                 tmp[sta].lmScore = 0;

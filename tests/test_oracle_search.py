@@ -114,3 +114,15 @@ def test_oracle_reproduces_reference_golden(oracle, reference_search_golden, nam
         a, b = int(ro[u]), int(ro[u + 1])
         assert np.array_equal(got["words"], c["words"][a:b]) and np.array_equal(got["times"], c["times"][a:b])
         assert np.array_equal(got["am"], c["am"][a:b]) and np.array_equal(got["lm"], c["lm"][a:b])
+
+
+def test_single_word_with_a_long_irregular_word_first(oracle):
+    """the scratch hypotheses of feed() (hypTmp, src/Search/LinearSearch.cc:238,303) start with a null back pointer; the
+    irregular book-keeping scan reads the back pointer of word ends that were never reached in the first frames"""
+    lex = synth.lexicon(50, 64, seed=3)
+    lex["word_regular"] = (np.arange(50) % 7 != 0).astype(np.uint8)  # word 0: irregular, several states
+    lex["single_word"] = True
+    rng = np.random.default_rng(0)
+    scores = (rng.random((120, 64)) * 25 + 2).astype(np.float32)
+    r = oracle.linear_search(lex, scores)
+    assert len(r["words"]) >= 1 and int(lex["word_regular"][r["words"]].sum()) <= 1

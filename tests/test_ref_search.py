@@ -95,6 +95,9 @@ CASES = [
     (30, 8, 40, 160, 18, dict(single_word=True, irregular=(0, 7, 8, 29))),   # noise words besides silence
     (30, 8, 40, 160, 19, dict(single_word=False, irregular=(0, 7, 8, 29))),  # the flag is inert without the mode
     (10, 4, 16, 120, 20, dict(single_word=True, irregular=tuple(range(10)))),  # nothing but irregular words
+    # the first pronunciations are long irregular words, no silence: word ends that are unreachable in the first frames
+    # are looked at by the irregular book keeping with a null back pointer
+    (20, 6, 32, 80, 22, dict(single_word=True, irregular=(0, 1), silence=False, max_len=5)),
 ]
 
 
