@@ -249,6 +249,7 @@ struct RefineParams {
     int          dim;       // DIAG_MAX: feature dimension (tail dims are summed sequentially)
     long         T;
     int          nMix, nGroups, nFrameBlocks;
+    float        emptyScore;  // score of a mixture without a candidate: FLT_MAX, or the preselection scorer's back-off score
 };
 
 constexpr int kStageQuads = 4;                    // mixtures staged per flush = 16
@@ -319,7 +320,9 @@ __global__ void __launch_bounds__(kThreads, 3) gmm_refine_kernel(const RefinePar
                     const float rs = batch_row_score<NB, FUSE>(base + j * ROWF, x);
                     best           = best < rs ? best : rs;
                 }
-                o[q] = best < FLT_MAX ? __fmul_rn(best, 0.5f) : best;
+                // (a mixture none of whose candidates was scored keeps FLT_MAX -- or gets the preselection scorer's back-off
+                // score, `if (s == max) s = backoffScore`; +inf / NaN pass through as the direct kernel leaves them)
+                o[q] = best < FLT_MAX ? __fmul_rn(best, 0.5f) : (best == FLT_MAX ? p.emptyScore : best);
             }
             // Scores leave through a per-warp staging tile [32 frames][kStageQuads quads]: a thread's own 16 bytes per
             // quad would be a store instruction touching 32 different lines, 1 KB apart; after the transpose four lanes
@@ -804,6 +807,8 @@ void rb_gmm_presel_destroy(rb_gmm_presel* h);
 int  rb_gmm_presel_score(rb_gmm_presel* h, const float* d_feats, long T, float* d_scores, cudaStream_t stream);
 int  rb_gmm_presel_configure(rb_gmm_presel* h, int clusters, int select, int iterations, float backoff, cudaStream_t s);
 void rb_gmm_presel_clustering(const rb_gmm_presel* h, uint32_t* cluster_of, float* cluster_means, int* n_clusters);
+int  rb_gmm_presel_select(rb_gmm_presel* h, const float* d_feats, long T, const uint32_t** active,
+                          const uint8_t** cluster_of, const uint32_t** offsets, float* backoff, cudaStream_t stream);
 
 struct rb_gmm_presel_int;  // gmm_presel_int.cu
 int  rb_gmm_presel_int_create(const rb_mixture_set* ms, const rb::DeviceInfo& dev, cudaStream_t stream,
@@ -831,6 +836,8 @@ int  rb_gmm_tensor_create_diag(const rb_mixture_set* ms, const float* rows, int 
 long rb_gmm_tensor_chunk(const rb_gmm_tensor* t);
 int  rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* d_feats, long n, const uint32_t** words, const float** xT,
                           long* pitch, cudaStream_t stream, cudaEvent_t after_split);
+int  rb_gmm_tensor_split(rb_gmm_tensor* t, const float* d_feats, long n, uint32_t** words, const float** xT, long* pitch,
+                         cudaStream_t stream);
 
 struct rb_gmm {
     rb::DeviceInfo dev;
@@ -1245,6 +1252,7 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
         p.nMix         = h->nMix;
         p.nGroups      = h->groupsOf[G];
         p.nFrameBlocks = (int)((n + kThreads - 1) / kThreads);
+        p.emptyScore   = FLT_MAX;
         const long items = (long)p.nGroups * p.nFrameBlocks;
         const int  grid  = (int)std::max<long>(p.nGroups, std::min<long>(items, h->refSlots));
         h->refine<<<grid, kThreads, h->refSmem, s>>>(p);
@@ -1253,6 +1261,81 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
             cudaEventRecord(h->tev[3], s);
             h->timed = true;
         }
+    }
+    return RB_OK;
+}
+
+// ---- density preselection through the refinement kernel ------------------------------------------------------------
+// "preselection-batch-float" scores, per frame, only the densities of the selected clusters with the arithmetic of
+// the batch-float scorer and gives a mixture without a scored density the back-off score
+// (src/Mm/BatchFeatureScorer.cc:286-315).  That is the refinement kernel's job description with a different source of
+// candidate sets: bit j of a (frame, mixture) word = "the cluster of the mixture's j-th density is active".
+__global__ void __launch_bounds__(256) presel_masks_kernel(const uint32_t* __restrict__ active, const uint8_t* __restrict__ clusterOf,
+                                                           const uint32_t* __restrict__ offsets, uint32_t* __restrict__ words,
+                                                           long pitch, long T, int nMix) {
+    const long total = (long)(nMix >> 2) * T;  // one thread per (quad of mixtures, frame); frames fastest: coalesced stores
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long t = i % T;
+        const int  q = (int)(i / T);
+        uint32_t   sel[8];
+        const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(active + t * 8)), s1 = __ldg(reinterpret_cast<const uint4*>(active + t * 8) + 1);
+        sel[0] = s0.x; sel[1] = s0.y; sel[2] = s0.z; sel[3] = s0.w;
+        sel[4] = s1.x; sel[5] = s1.y; sel[6] = s1.z; sel[7] = s1.w;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t a = __ldg(offsets + 4 * q + k), b = __ldg(offsets + 4 * q + k + 1);
+            uint32_t       m = 0;
+            for (uint32_t e = a; e < b; ++e) {
+                const uint32_t c = __ldg(clusterOf + e);
+                uint32_t       word = sel[0];  // sel[c >> 5] without a dynamically indexed register array
+#pragma unroll
+                for (int j = 1; j < 8; ++j)
+                    word = (c >> 5) == (uint32_t)j ? sel[j] : word;
+                m |= ((word >> (c & 31u)) & 1u) << (e - a);
+            }
+            w[k] = m;
+        }
+        reinterpret_cast<uint4*>(words)[(size_t)q * pitch + t] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+int launch_presel_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores, float* const* extra, int nExtra,
+                           cudaStream_t s) {
+    const long chunk = rb_gmm_tensor_chunk(h->tensor);
+    for (long a = 0; a < T; a += chunk) {
+        const long      n = std::min(chunk, T - a);
+        const uint32_t* active = nullptr;
+        const uint8_t*  clusterOf = nullptr;
+        const uint32_t* offsets = nullptr;
+        uint32_t*       words = nullptr;
+        RefineParams    p;
+        RB_CHECK(rb_gmm_presel_select(h->presel, dFeats + (size_t)a * h->dim, n, &active, &clusterOf, &offsets, &p.emptyScore, s));
+        RB_CHECK(rb_gmm_tensor_split(h->tensor, dFeats + (size_t)a * h->dim, n, &words, &p.xT, &p.pitch, s));
+        const long total = (long)(h->nMix >> 2) * n;
+        presel_masks_kernel<<<(int)std::min<long>((total + 255) / 256, (long)h->dev.sm_count * 16), 256, 0, s>>>(
+                active, clusterOf, offsets, words, p.pitch, n, h->nMix);
+        RB_LAUNCH_CHECK();
+        p.words        = words;
+        p.scores       = dScores + (size_t)a * h->nMix;
+        p.nExtra       = nExtra;
+        for (int e = 0; e < nExtra; ++e)
+            p.extra[e] = extra[e] + (size_t)a * h->nMix;
+        p.best         = nullptr;
+        p.dim          = h->dim;
+        const int G    = h->refGroups;
+        p.rows         = h->dRefRows.p;
+        p.grp_row      = h->dGrpRow.p + (size_t)G * kGroupStride;
+        p.grp_mix      = h->dGrpMix.p + (size_t)G * kGroupStride;
+        p.mix_row      = h->dMixRow.p;
+        p.T            = n;
+        p.nMix         = h->nMix;
+        p.nGroups      = h->groupsOf[G];
+        p.nFrameBlocks = (int)((n + kThreads - 1) / kThreads);
+        const long items = (long)p.nGroups * p.nFrameBlocks;
+        const int  grid  = (int)std::max<long>(p.nGroups, std::min<long>(items, h->refSlots));
+        h->refine<<<grid, kThreads, h->refSmem, s>>>(p);
+        RB_LAUNCH_CHECK();
     }
     return RB_OK;
 }
@@ -1306,8 +1389,12 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         rc = rb_gmm_presel_create(ms, h->fuse, h->dev, h->stream, &h->presel);
         if (rc != RB_OK)
             return fail(rc);
-        *out = h;
-        return RB_OK;
+        // models the refinement kernel covers (<= 32 densities per mixture, dimension <= 64 ...) are scored through it
+        // (launch_presel_two_pass); the batch-float tables below are set up for that.  Others keep presel_score_kernel.
+        if (ms->dim > 64 || ms->n_covariances != 1 || getenv("RB_GMM_PRESEL_DIRECT") != nullptr) {
+            *out = h;
+            return RB_OK;
+        }
     }
     if (mode == RB_GMM_BATCH_PRESELECT_INT) {
         rc = rb_gmm_presel_int_create(ms, h->dev, h->stream, &h->preselInt);
@@ -1316,7 +1403,7 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         *out = h;
         return RB_OK;
     }
-    if (mode == RB_GMM_BATCH_FLOAT || mode == RB_GMM_BATCH_TENSOR) {
+    if (mode == RB_GMM_BATCH_FLOAT || mode == RB_GMM_BATCH_TENSOR || mode == RB_GMM_BATCH_PRESELECT) {
         if (ms->dim > 64) {
             rb::set_error("batch scorer supports feature dimension <= 64 (got %u)", ms->dim);
             return fail(RB_ERR_UNSUPPORTED);
@@ -1412,7 +1499,7 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         if (rc != RB_OK)
             return fail(rc);
     }
-    if (mode == RB_GMM_BATCH_FLOAT) {
+    if (mode == RB_GMM_BATCH_FLOAT || mode == RB_GMM_BATCH_PRESELECT) {
         rc = setup_exact_two_pass(h, ms, rows.data(), false);
         if (rc != RB_OK)
             return fail(rc);
@@ -1448,6 +1535,13 @@ int score_dev_impl(rb_gmm* h, const float* d_feats, long T, float* d_scores, flo
             aligned = aligned && ((uintptr_t)extra[e] % 16) == 0;
         if (aligned)
             return launch_exact_two_pass(h, d_feats, T, d_scores, extra, nExtra, d_best, s);
+    }
+    if (h->mode == RB_GMM_BATCH_PRESELECT && h->refGroups > 0 && h->tensor && ((uintptr_t)d_scores % 16) == 0) {
+        bool aligned = true;
+        for (int e = 0; e < nExtra; ++e)
+            aligned = aligned && ((uintptr_t)extra[e] % 16) == 0;
+        if (aligned)
+            return launch_presel_two_pass(h, d_feats, T, d_scores, extra, nExtra, s);
     }
     int rc;
     if (h->mode == RB_GMM_BATCH_TENSOR)
@@ -1502,7 +1596,8 @@ int rb_gmm_reserve(rb_gmm* h, long frames) {
     if (!h || !h->tensor || frames <= 0)
         return RB_OK;
     RB_CUDA(cudaSetDevice(h->dev.ordinal));
-    return rb_gmm_tensor_reserve(h->tensor, frames, h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_DIAG_MAX);
+    return rb_gmm_tensor_reserve(h->tensor, frames, h->mode == RB_GMM_BATCH_FLOAT || h->mode == RB_GMM_DIAG_MAX ||
+                                                            h->mode == RB_GMM_BATCH_PRESELECT);
 }
 
 // Host-pointer entry point: frames are cut into slabs; H2D of slab i+1, scoring of slab i and D2H of

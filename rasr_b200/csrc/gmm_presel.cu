@@ -450,6 +450,42 @@ int rb_gmm_presel_score(rb_gmm_presel* h, const float* dFeats, long T, float* dS
     return RB_OK;
 }
 
+// The cluster selection alone (presel_select_kernel): *active = [T * 8] words, one bit per cluster; plus the tables a
+// consumer needs to turn it into candidate sets (gmm.cu: the refinement kernel of the exact batch-float route)
+int rb_gmm_presel_select(rb_gmm_presel* h, const float* dFeats, long T, const uint32_t** active,
+                         const uint8_t** clusterOf, const uint32_t** offsets, float* backoff, cudaStream_t s) {
+    RB_CHECK(h->dActive.reserve((size_t)T * 8));
+    PreselParams p;
+    p.feats        = dFeats;
+    p.isd          = h->dIsd.p;
+    p.means        = h->dMeans.p;
+    p.consts       = h->dConsts.p;
+    p.offsets      = h->dOffsets.p;
+    p.clusterOf    = h->dClusterOf.p;
+    p.densMix      = h->dDensMix.p;
+    p.clusterMeans = h->dClusterMeans.p;
+    p.active       = h->dActive.p;
+    p.scores       = nullptr;
+    p.T            = T;
+    p.dim          = h->dim;
+    p.padded       = h->padded;
+    p.nMix         = h->nMix;
+    p.nClusters    = h->nClusters;
+    p.nSelected    = h->nSelected;
+    p.fuse         = h->fuse ? 1 : 0;
+    p.backoff      = h->backoff;
+    const size_t smem = presel_pairs_offset(h->nClusters, h->padded) * 4 + (size_t)kSelWarps * 256 * sizeof(DistCluster);
+    RB_CUDA(cudaFuncSetAttribute(presel_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid1 = (int)std::min<long>((T + kSelWarps - 1) / kSelWarps, (long)h->dev.sm_count * 4);
+    presel_select_kernel<<<grid1, kSelWarps * 32, smem, s>>>(p);
+    RB_LAUNCH_CHECK();
+    *active    = h->dActive.p;
+    *clusterOf = h->dClusterOf.p;
+    *offsets   = h->dOffsets.p;
+    *backoff   = h->backoff;
+    return RB_OK;
+}
+
 void rb_gmm_presel_clustering(const rb_gmm_presel* h, uint32_t* cluster_of, float* cluster_means, int* n_clusters) {
     if (cluster_of)
         std::copy(h->clusterOf.begin(), h->clusterOf.end(), cluster_of);

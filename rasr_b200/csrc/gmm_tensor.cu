@@ -1050,6 +1050,23 @@ long rb_gmm_tensor_chunk(const rb_gmm_tensor* t) {
     return t->chunk;
 }
 
+// The operand split alone: the reference's scaled features, transposed (*xT, [dp x pitch]) and the (uninitialised) word
+// buffer [nMix / 4][pitch][4] for a caller that decides the candidate sets itself (density preselection, gmm.cu).
+int rb_gmm_tensor_split(rb_gmm_tensor* t, const float* dFeats, long n, uint32_t** words, const float** xT, long* pitch,
+                        cudaStream_t s) {
+    RB_REQUIRE(t->screenable && !t->diag, "this mixture set has no batch operand split");
+    RB_REQUIRE(n >= 1 && n <= t->chunk, "bad frame count for one pass");
+    RB_CHECK(ensure_capacity(t, n, true));
+    const int blocks = (int)std::min<long>((n + 31) / 32, (long)t->dev.sm_count * 16);
+    gmm_split_features_kernel<<<blocks, 256, 0, s>>>(dFeats, t->dIsd.p, t->dCentre.p, n, t->dim, t->dp, t->kPad, t->scale,
+                                                     t->dA.p, t->dXnorm.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p, t->cap);
+    RB_LAUNCH_CHECK();
+    *xT    = t->dXT.p;
+    *words = t->dWords.p;
+    *pitch = t->cap;
+    return RB_OK;
+}
+
 // Exact batch-float scoring, first half: for n <= chunk frames compute the candidate-density words (*words, laid out
 // [nMix / 4][pitch][4]) and the reference's scaled features, transposed ([dp x pitch], x' = fl(feat * isd)) (*xT).
 int rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* dFeats, long n, const uint32_t** words, const float** xT,

@@ -14,6 +14,16 @@ def both(oracle, msd):
     return oracle.MixtureSet(**msd), mm.MixtureSet.from_dict(msd)
 
 
+@pytest.fixture(params=["refinement", "direct"], autouse=True)
+def route(request, monkeypatch):
+    """both scoring routes: the candidate sets handed to the refinement kernel of the exact batch-float scorer (models it
+    covers: mixture count a multiple of 4, at most 32 densities per mixture), and presel_score_kernel (everything else;
+    RB_GMM_PRESEL_DIRECT forces it)"""
+    if request.param == "direct":
+        monkeypatch.setenv("RB_GMM_PRESEL_DIRECT", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("contraction", [True, False])
 def test_c2_shape_bit_exact(oracle, diag, contraction):
     msd = synth.mixture_set()
