@@ -1270,33 +1270,46 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
 // the batch-float scorer and gives a mixture without a scored density the back-off score
 // (src/Mm/BatchFeatureScorer.cc:286-315).  That is the refinement kernel's job description with a different source of
 // candidate sets: bit j of a (frame, mixture) word = "the cluster of the mixture's j-th density is active".
+constexpr int kMaskFrames = 64;  // frames per CTA of presel_masks_kernel
 __global__ void __launch_bounds__(256) presel_masks_kernel(const uint32_t* __restrict__ active, const uint8_t* __restrict__ clusterOf,
                                                            const uint32_t* __restrict__ offsets, uint32_t* __restrict__ words,
-                                                           long pitch, long T, int nMix) {
-    const long total = (long)(nMix >> 2) * T;  // one thread per (quad of mixtures, frame); frames fastest: coalesced stores
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long t = i % T;
-        const int  q = (int)(i / T);
-        uint32_t   sel[8];
-        const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(active + t * 8)), s1 = __ldg(reinterpret_cast<const uint4*>(active + t * 8) + 1);
-        sel[0] = s0.x; sel[1] = s0.y; sel[2] = s0.z; sel[3] = s0.w;
-        sel[4] = s1.x; sel[5] = s1.y; sel[6] = s1.z; sel[7] = s1.w;
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t a = __ldg(offsets + 4 * q + k), b = __ldg(offsets + 4 * q + k + 1);
-            uint32_t       m = 0;
-            for (uint32_t e = a; e < b; ++e) {
-                const uint32_t c = __ldg(clusterOf + e);
-                uint32_t       word = sel[0];  // sel[c >> 5] without a dynamically indexed register array
-#pragma unroll
-                for (int j = 1; j < 8; ++j)
-                    word = (c >> 5) == (uint32_t)j ? sel[j] : word;
-                m |= ((word >> (c & 31u)) & 1u) << (e - a);
-            }
-            w[k] = m;
+                                                           long pitch, long T, int nMix, int nDens) {
+    // shared: the cluster of every density (a byte each), the first density of every mixture, and the active-cluster
+    // bits of this CTA's 64 frames with a row stride of 9 words (bank = frame + word: conflict free for lanes = frames)
+    extern __shared__ __align__(16) unsigned char smemMask[];
+    uint8_t*  sCluster = smemMask;
+    uint32_t* sOff     = reinterpret_cast<uint32_t*>(smemMask + ((nDens + 15) & ~15));
+    uint32_t* sActive  = sOff + ((nMix + 1 + 3) & ~3);
+    for (int i = threadIdx.x; i < nDens; i += 256)
+        sCluster[i] = clusterOf[i];
+    for (int i = threadIdx.x; i <= nMix; i += 256)
+        sOff[i] = offsets[i];
+    const int nQuads = nMix >> 2;
+    for (long t0 = (long)blockIdx.x * kMaskFrames; t0 < T; t0 += (long)gridDim.x * kMaskFrames) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kMaskFrames * 8; i += 256) {
+            const long t = t0 + (i >> 3);
+            sActive[(i >> 3) * 9 + (i & 7)] = t < T ? active[t * 8 + (i & 7)] : 0u;
         }
-        reinterpret_cast<uint4*>(words)[(size_t)q * pitch + t] = make_uint4(w[0], w[1], w[2], w[3]);
+        __syncthreads();
+        const int  f = threadIdx.x & (kMaskFrames - 1);  // lanes of a warp = consecutive frames: coalesced 16-byte stores
+        const long t = t0 + f;
+        const uint32_t* sel = sActive + f * 9;
+        for (int q = threadIdx.x / kMaskFrames; q < nQuads; q += 256 / kMaskFrames) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t a = sOff[4 * q + k], b = sOff[4 * q + k + 1];
+                uint32_t       m = 0;
+                for (uint32_t e = a; e < b; ++e) {
+                    const uint32_t c = sCluster[e];  // the same density for the whole warp: a broadcast
+                    m |= ((sel[c >> 5] >> (c & 31u)) & 1u) << (e - a);
+                }
+                w[k] = m;
+            }
+            if (t < T)
+                reinterpret_cast<uint4*>(words)[(size_t)q * pitch + t] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 
@@ -1312,9 +1325,13 @@ int launch_presel_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScore
         RefineParams    p;
         RB_CHECK(rb_gmm_presel_select(h->presel, dFeats + (size_t)a * h->dim, n, &active, &clusterOf, &offsets, &p.emptyScore, s));
         RB_CHECK(rb_gmm_tensor_split(h->tensor, dFeats + (size_t)a * h->dim, n, &words, &p.xT, &p.pitch, s));
-        const long total = (long)(h->nMix >> 2) * n;
-        presel_masks_kernel<<<(int)std::min<long>((total + 255) / 256, (long)h->dev.sm_count * 16), 256, 0, s>>>(
-                active, clusterOf, offsets, words, p.pitch, n, h->nMix);
+        const int    nDens    = h->nRows;  // (every mixture has >= 1 density on this route: rows = densities)
+        const size_t smemMask = (size_t)((nDens + 15) & ~15) + sizeof(uint32_t) * (((size_t)h->nMix + 1 + 3) & ~(size_t)3) +
+                                sizeof(uint32_t) * kMaskFrames * 9;
+        RB_REQUIRE(smemMask <= h->dev.smem_optin - 1024, "preselection candidate sets: the model's tables need %zu bytes", smemMask);
+        RB_CUDA(cudaFuncSetAttribute(presel_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMask));
+        presel_masks_kernel<<<(int)std::min<long>((n + kMaskFrames - 1) / kMaskFrames, (long)h->dev.sm_count * 8), 256, smemMask, s>>>(
+                active, clusterOf, offsets, words, p.pitch, n, h->nMix, nDens);
         RB_LAUNCH_CHECK();
         p.words        = words;
         p.scores       = dScores + (size_t)a * h->nMix;
