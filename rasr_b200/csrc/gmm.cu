@@ -1271,6 +1271,10 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
 // (src/Mm/BatchFeatureScorer.cc:286-315).  That is the refinement kernel's job description with a different source of
 // candidate sets: bit j of a (frame, mixture) word = "the cluster of the mixture's j-th density is active".
 constexpr int kMaskFrames = 64;  // frames per CTA of presel_masks_kernel
+size_t presel_masks_smem(const rb_gmm* h) {  // cluster bytes + mixture offsets + the active bits of 64 frames
+    return (size_t)((h->nRows + 15) & ~15) + sizeof(uint32_t) * (((size_t)h->nMix + 1 + 3) & ~(size_t)3) +
+           sizeof(uint32_t) * kMaskFrames * 9;
+}
 __global__ void __launch_bounds__(256) presel_masks_kernel(const uint32_t* __restrict__ active, const uint8_t* __restrict__ clusterOf,
                                                            const uint32_t* __restrict__ offsets, uint32_t* __restrict__ words,
                                                            long pitch, long T, int nMix, int nDens) {
@@ -1326,9 +1330,7 @@ int launch_presel_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScore
         RB_CHECK(rb_gmm_presel_select(h->presel, dFeats + (size_t)a * h->dim, n, &active, &clusterOf, &offsets, &p.emptyScore, s));
         RB_CHECK(rb_gmm_tensor_split(h->tensor, dFeats + (size_t)a * h->dim, n, &words, &p.xT, &p.pitch, s));
         const int    nDens    = h->nRows;  // (every mixture has >= 1 density on this route: rows = densities)
-        const size_t smemMask = (size_t)((nDens + 15) & ~15) + sizeof(uint32_t) * (((size_t)h->nMix + 1 + 3) & ~(size_t)3) +
-                                sizeof(uint32_t) * kMaskFrames * 9;
-        RB_REQUIRE(smemMask <= h->dev.smem_optin - 1024, "preselection candidate sets: the model's tables need %zu bytes", smemMask);
+        const size_t smemMask = presel_masks_smem(h);
         RB_CUDA(cudaFuncSetAttribute(presel_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMask));
         presel_masks_kernel<<<(int)std::min<long>((n + kMaskFrames - 1) / kMaskFrames, (long)h->dev.sm_count * 8), 256, smemMask, s>>>(
                 active, clusterOf, offsets, words, p.pitch, n, h->nMix, nDens);
@@ -1553,7 +1555,8 @@ int score_dev_impl(rb_gmm* h, const float* d_feats, long T, float* d_scores, flo
         if (aligned)
             return launch_exact_two_pass(h, d_feats, T, d_scores, extra, nExtra, d_best, s);
     }
-    if (h->mode == RB_GMM_BATCH_PRESELECT && h->refGroups > 0 && h->tensor && ((uintptr_t)d_scores % 16) == 0) {
+    if (h->mode == RB_GMM_BATCH_PRESELECT && h->refGroups > 0 && h->tensor && ((uintptr_t)d_scores % 16) == 0 &&
+        presel_masks_smem(h) + 1024 <= h->dev.smem_optin) {
         bool aligned = true;
         for (int e = 0; e < nExtra; ++e)
             aligned = aligned && ((uintptr_t)extra[e] % 16) == 0;

@@ -111,17 +111,28 @@ __global__ void __launch_bounds__(kSelWarps * 32) presel_select_kernel(const Pre
             xs[d] = d < p.dim ? __fmul_rn(p.feats[t * p.dim + d], p.isd[d]) : 0.0f;
         __syncwarp();
         // distances: cluster c = lane + 32 k
-        uint32_t key[8];
+        // (the eight distances of a lane advance together: eight independent accumulation chains, one read of the
+        // feature element per dimension; every chain keeps the reference's sequential order over the dimensions)
+        uint32_t     key[8];
+        float        score[8];
+        const float* m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            score[k] = 0.0f;
+            m[k]     = cm + min(lane + 32 * k, p.nClusters - 1) * stride;
+        }
+        for (int d = 0; d < p.padded; ++d) {
+            const float xd = xs[d];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                score[k] = sq_acc(__fsub_rn(xd, m[k][d]), score[k], p.fuse);
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int c = lane + 32 * k;
             key[k]      = 0xffffffffu;
             if (c < p.nClusters) {
-                float        score = 0.0f;
-                const float* m     = cm + c * stride;
-                for (int d = 0; d < p.padded; ++d)
-                    score = sq_acc(__fsub_rn(xs[d], m[d]), score, p.fuse);
-                key[k]   = __float_as_uint(score);  // distances are >= 0: their bit patterns order like the values
+                key[k]   = __float_as_uint(score[k]);  // distances are >= 0: their bit patterns order like the values
                 pairs[c] = DistCluster{key[k], (uint32_t)c};
             }
         }
