@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "rasr_b200", "lib", "librasr_b200.so")
-KEYS = ["UTCHMMA", "UTCQMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "IMMA",
+KEYS = ["UTCHMMA", "UTCQMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "IMMA", "IDP",
         "HMMA", "LDSM", "LDS", "LDG", "STG", "REDUX", "SHFL", "MUFU", "BAR"]
 
 
@@ -44,7 +44,7 @@ def main():
     lines = ["# SASS summary of rasr_b200/lib/librasr_b200.so (sm_100a)", "",
              "`python scripts/sass_summary.py` (cuobjdump -sass, counted per kernel; columns with no hit anywhere are "
              "dropped).  UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG / UTMASTG = TMA tensor load / store, UBLKCP = "
-             "cp.async.bulk, SYNCS = mbarrier, FFMA2 / FADD2 = packed f32x2, IMMA = mma.sync u8.", ""]
+             "cp.async.bulk, SYNCS = mbarrier, FFMA2 / FADD2 = packed f32x2, IMMA = mma.sync u8, IDP = dp4a.", ""]
     used = [k for k in KEYS if any(counts[f][k] for f in order)]
     lines.append("| kernel | instr | " + " | ".join(used) + " |")
     lines.append("|---|---|" + "---|" * len(used))
