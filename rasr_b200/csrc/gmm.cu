@@ -1398,6 +1398,11 @@ extern "C" int rb_gmm_create(const rb_mixture_set* ms, int mode, float mixture_w
         return RB_OK;
     }
     if (mode == RB_GMM_SIMD_DIAG_MAX) {
+        if (mixture_weight_scale != 1.0f || gaussian_scale != 1.0f) {  // the reference's SIMD scorer has no such parameters
+            rb::set_error("RB_GMM_SIMD_DIAG_MAX takes no mixture-weight / gaussian scale (got %g, %g)", mixture_weight_scale,
+                          gaussian_scale);
+            return fail(RB_ERR_INVALID);
+        }
         rc = rb_gmm_simd_create(ms, h->dev, h->stream, &h->simd);
         if (rc != RB_OK)
             return fail(rc);
