@@ -250,6 +250,7 @@ struct RefineParams {
     long         T;
     int          nMix, nGroups, nFrameBlocks;
     float        emptyScore;  // score of a mixture without a candidate: FLT_MAX, or the preselection scorer's back-off score
+    const float* pooledIsd;   // DIAG_MAX, one covariance for all densities: its NQ*4 scaled 1/sqrt(var) (rows hold no copy)
 };
 
 constexpr int kStageQuads = 4;                    // mixtures staged per flush = 16
@@ -384,10 +385,21 @@ GmmRefineKernel refine_kernel_for(int nb, bool fuse) {
 __host__ __device__ constexpr int refine_diag_pitch(int nq) {
     return nq * 8 + 2;
 }
+// POOLED (every density uses the same covariance -- the usual RASR model): a row is [ mean | (w, logNorm) ] and the
+// common 1/sqrt(var) is read from one shared array -- the same address for every lane, a broadcast costing one wavefront
+// where the per-lane gather of a row segment costs two; 60 instead of 82 wavefronts per candidate, and half the rows'
+// shared memory (fewer mixture groups).  The arithmetic is unchanged.
+__host__ __device__ constexpr int refine_diag_pooled_pitch(int nq) {
+    return nq * 4 + 2;  // an odd number (2 NQ + 1) of 8-byte words: conflict-free per-lane row gathers
+}
 
-template<int NQ, bool FUSE>
+template<int NQ, bool FUSE, bool POOLED>
 __global__ void __launch_bounds__(kThreads, 2) gmm_refine_diag_kernel(const RefineParams p) {
-    constexpr int ROWF = refine_diag_pitch(NQ);
+    constexpr int ROWF = POOLED ? refine_diag_pooled_pitch(NQ) : refine_diag_pitch(NQ);
+    constexpr int TAILW = POOLED ? 2 * NQ : 4 * NQ;  // 8-byte word of (w, logNorm) within a row
+    __shared__ uint64_t sIsd[NQ * 2];
+    if (POOLED && threadIdx.x < NQ * 2)
+        sIsd[threadIdx.x] = pack2(p.pooledIsd[2 * threadIdx.x], p.pooledIsd[2 * threadIdx.x + 1]);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int g    = blockIdx.x % p.nGroups;
     const int row0 = p.grp_row[g], row1 = p.grp_row[g + 1];
@@ -460,14 +472,16 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_refine_diag_kernel(const Refi
                         if (qd < nFullQ) {
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
-                                const uint64_t e = mul2(sub2(r[2 * qd + h], xp[2 * qd + h]), r[2 * NQ + 2 * qd + h]);
+                                const uint64_t e = mul2(sub2(r[2 * qd + h], xp[2 * qd + h]),
+                                                        POOLED ? sIsd[2 * qd + h] : r[2 * NQ + 2 * qd + h]);
                                 s[h]             = FUSE ? fma2(e, e, s[h]) : sqadd2(e, s[h]);
                             }
                         }
                     }
                     float d = __fadd_rn(0.0f, __fadd_rn(__fadd_rn(lo2(s[0]), hi2(s[0])), __fadd_rn(lo2(s[1]), hi2(s[1]))));
                     if (nTail) {
-                        const uint64_t ma = r[2 * NQ - 2], mb = r[2 * NQ - 1], va = r[4 * NQ - 2], vb = r[4 * NQ - 1];
+                        const uint64_t ma = r[2 * NQ - 2], mb = r[2 * NQ - 1];
+                        const uint64_t va = POOLED ? sIsd[2 * NQ - 2] : r[4 * NQ - 2], vb = POOLED ? sIsd[2 * NQ - 1] : r[4 * NQ - 1];
                         const float    mt[4] = {lo2(ma), hi2(ma), lo2(mb), hi2(mb)};
                         const float    vt[4] = {lo2(va), hi2(va), lo2(vb), hi2(vb)};
 #pragma unroll
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_refine_diag_kernel(const Refi
                                 d             = sq_acc(e, d, FUSE);
                             }
                     }
-                    const uint64_t tail = r[4 * NQ];  // (w, logNorm)
+                    const uint64_t tail = r[TAILW];  // (w, logNorm)
                     const double   sc   = ((double)lo2(tail) + (double)hi2(tail)) + (double)d;
                     if ((double)best > sc) {
                         best = (float)sc;
@@ -514,21 +528,23 @@ __global__ void __launch_bounds__(kThreads, 2) gmm_refine_diag_kernel(const Refi
 }
 
 template<int N>
-GmmRefineKernel pick_refine_diag(bool fuse) {
-    return fuse ? gmm_refine_diag_kernel<N, true> : gmm_refine_diag_kernel<N, false>;
+GmmRefineKernel pick_refine_diag(bool fuse, bool pooled) {
+    if (pooled)
+        return fuse ? gmm_refine_diag_kernel<N, true, true> : gmm_refine_diag_kernel<N, false, true>;
+    return fuse ? gmm_refine_diag_kernel<N, true, false> : gmm_refine_diag_kernel<N, false, false>;
 }
-GmmRefineKernel refine_diag_kernel_for(int nq, bool fuse) {
+GmmRefineKernel refine_diag_kernel_for(int nq, bool fuse, bool pooled) {
     switch (nq) {
-        case 1: return pick_refine_diag<1>(fuse);
-        case 2: return pick_refine_diag<2>(fuse);
-        case 3: return pick_refine_diag<3>(fuse);
-        case 4: return pick_refine_diag<4>(fuse);
-        case 5: return pick_refine_diag<5>(fuse);
-        case 6: return pick_refine_diag<6>(fuse);
-        case 7: return pick_refine_diag<7>(fuse);
-        case 8: return pick_refine_diag<8>(fuse);
-        case 9: return pick_refine_diag<9>(fuse);
-        case 10: return pick_refine_diag<10>(fuse);
+        case 1: return pick_refine_diag<1>(fuse, pooled);
+        case 2: return pick_refine_diag<2>(fuse, pooled);
+        case 3: return pick_refine_diag<3>(fuse, pooled);
+        case 4: return pick_refine_diag<4>(fuse, pooled);
+        case 5: return pick_refine_diag<5>(fuse, pooled);
+        case 6: return pick_refine_diag<6>(fuse, pooled);
+        case 7: return pick_refine_diag<7>(fuse, pooled);
+        case 8: return pick_refine_diag<8>(fuse, pooled);
+        case 9: return pick_refine_diag<9>(fuse, pooled);
+        case 10: return pick_refine_diag<10>(fuse, pooled);
     }
     return nullptr;
 }
@@ -879,7 +895,8 @@ struct rb_gmm {
     size_t               refSmem = 0;
     long                 exactMinFrames = 2048;
     rb::DevBuf<int>      dMixRow;
-    rb::DevBuf<float>    dRefRows;
+    rb::DevBuf<float>    dRefRows, dRefIsd;
+    bool                 refPooled = false;  // DIAG_MAX refinement rows without the per-row 1/sqrt(var) copy
     rb::HostStager       stager;  // host-buffer calls with pageable score buffers
     rb::PinnedBuf<float> hFeats;  // ... and pageable feature buffers: copied here by several cores, then DMA
     cudaEvent_t          tev[4] = {nullptr, nullptr, nullptr, nullptr};  // rb_gmm_set_timing: around the three kernels
@@ -1162,7 +1179,11 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
         if (n == 0 || n > 32)
             return RB_OK;
     }
-    h->refine = diag ? refine_diag_kernel_for(h->nUnits, h->fuse) : refine_kernel_for(h->nUnits, h->fuse);
+    bool pooled = diag && ms->n_covariances == 1 && getenv("RB_GMM_DIAG_ROWS_WITH_ISD") == nullptr;
+    for (uint32_t i = 0; i < ms->n_densities && pooled; ++i)
+        pooled = ms->dens_cov[i] == 0;
+    h->refPooled = pooled;
+    h->refine = diag ? refine_diag_kernel_for(h->nUnits, h->fuse, pooled) : refine_kernel_for(h->nUnits, h->fuse);
     if (!h->refine)
         return RB_OK;
     rb_gmm_tensor* t = nullptr;
@@ -1174,7 +1195,8 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
         return RB_OK;  // e.g. non-finite parameters: the direct kernel reproduces the reference on those too
     }
     // fewest groups whose rows fit 48 KB (3-4 CTAs per SM); else up to 200 KB at lower occupancy
-    const int        pitch = diag ? refine_diag_pitch(h->nUnits) : refine_pitch(h->nUnits);
+    const int        pitch = diag ? (pooled ? refine_diag_pooled_pitch(h->nUnits) : refine_diag_pitch(h->nUnits))
+                                  : refine_pitch(h->nUnits);
     const int        used  = diag ? h->nUnits * 8 + 2 : h->nUnits * 8 + 1;  // leading floats of a direct-kernel row
     std::vector<int> mixRow(h->nMix + 1, 0);
     for (int m = 0; m < h->nMix; ++m)
@@ -1210,7 +1232,25 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
     std::vector<float> rrows((size_t)(h->nRows + 1) * pitch, 0.0f);
     for (int r = 0; r < h->nRows; ++r) {
         const float* src = rowsHost + (size_t)r * h->rowf;
-        std::copy(src, src + used, rrows.begin() + (size_t)r * pitch);
+        if (pooled) {  // [ mean | (w, logNorm) ]; the 1/sqrt(var) segment is the same in every row
+            std::copy(src, src + h->nUnits * 4, rrows.begin() + (size_t)r * pitch);
+            std::copy(src + h->nUnits * 8, src + h->nUnits * 8 + 2, rrows.begin() + (size_t)r * pitch + h->nUnits * 4);
+        }
+        else
+            std::copy(src, src + used, rrows.begin() + (size_t)r * pitch);
+    }
+    if (pooled) {
+        // (placeholder rows of empty mixtures carry no 1/sqrt(var): take it from the first real density)
+        std::vector<float> isdRow(h->nUnits * 4, 0.0f);
+        for (uint32_t m = 0, r = 0; m < ms->n_mixtures; r += h->rowsOfMixture[m], ++m)
+            if (ms->mix_offsets[m + 1] > ms->mix_offsets[m]) {
+                std::copy(rowsHost + (size_t)r * h->rowf + h->nUnits * 4, rowsHost + (size_t)r * h->rowf + h->nUnits * 8, isdRow.begin());
+                break;
+            }
+        if (h->dRefIsd.upload(isdRow, h->stream) != RB_OK) {
+            rb_gmm_tensor_destroy(t);
+            return RB_ERR_CUDA;
+        }
     }
     if (h->dRefRows.upload(rrows, h->stream) != RB_OK || h->dMixRow.upload(mixRow, h->stream) != RB_OK ||
         cudaStreamSynchronize(h->stream) != cudaSuccess) {
@@ -1253,6 +1293,7 @@ int launch_exact_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScores
         p.nGroups      = h->groupsOf[G];
         p.nFrameBlocks = (int)((n + kThreads - 1) / kThreads);
         p.emptyScore   = FLT_MAX;
+        p.pooledIsd    = h->refPooled ? h->dRefIsd.p : nullptr;
         const long items = (long)p.nGroups * p.nFrameBlocks;
         const int  grid  = (int)std::max<long>(p.nGroups, std::min<long>(items, h->refSlots));
         h->refine<<<grid, kThreads, h->refSmem, s>>>(p);
@@ -1341,6 +1382,7 @@ int launch_presel_two_pass(rb_gmm* h, const float* dFeats, long T, float* dScore
         for (int e = 0; e < nExtra; ++e)
             p.extra[e] = extra[e] + (size_t)a * h->nMix;
         p.best         = nullptr;
+        p.pooledIsd    = nullptr;
         p.dim          = h->dim;
         const int G    = h->refGroups;
         p.rows         = h->dRefRows.p;
