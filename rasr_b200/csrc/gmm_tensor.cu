@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) gmm_split_features_diag_kernel(const floa
                                                                       const float* __restrict__ vmax2, long T, int dim,
                                                                       int dp, int kPad, __half* __restrict__ A,
                                                                       float* __restrict__ thr, float thrA, float thrB,
-                                                                      float* __restrict__ xT, long pitch) {
+                                                                      float* __restrict__ xT, long pitch, int pooled) {
     const int  sub = threadIdx.x & 7;
     const long g0  = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 3;
     const long nG  = ((long)gridDim.x * blockDim.x) >> 3;
@@ -364,17 +364,22 @@ __global__ void __launch_bounds__(256) gmm_split_features_diag_kernel(const floa
         bad |= __shfl_xor_sync(0xffffffffu, bad, 4);
         if (t0 < T) {
             uint4* row = reinterpret_cast<uint4*>(A + (size_t)t * kPad);
+            // pooled covariance: sum_d v_d^2 xc_d^2 is the same for every density of the frame and cannot change which
+            // densities are candidates, so the x^2 group of the expansion is left out (K = 3 dp + 3 instead of 6 dp + 3)
+            const int first1 = pooled ? 0 : 3 * nChunk, ones = first1 + 3 * nChunk;
             if (sub < nChunk) {
                 const uint4 a2 = make_uint4(h2[0], h2[1], h2[2], h2[3]), a1 = make_uint4(h1[0], h1[1], h1[2], h1[3]);
-                row[sub]              = a2;
-                row[nChunk + sub]     = a2;
-                row[2 * nChunk + sub] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
-                row[3 * nChunk + sub] = a1;
-                row[4 * nChunk + sub] = a1;
-                row[5 * nChunk + sub] = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+                if (!pooled) {
+                    row[sub]              = a2;
+                    row[nChunk + sub]     = a2;
+                    row[2 * nChunk + sub] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+                }
+                row[first1 + sub]              = a1;
+                row[first1 + nChunk + sub]     = a1;
+                row[first1 + 2 * nChunk + sub] = make_uint4(l1[0], l1[1], l1[2], l1[3]);
             }
-            for (int c = 6 * nChunk + sub; c < (kPad >> 3); c += 8)
-                row[c] = c == 6 * nChunk ? make_uint4(0x3C003C00u, 0x00003C00u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+            for (int c = ones + sub; c < (kPad >> 3); c += 8)
+                row[c] = c == ones ? make_uint4(0x3C003C00u, 0x00003C00u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
             if (sub == 0)
                 thr[t] = (bad || !(qx < FLT_MAX)) ? __int_as_float(0x7f800000) : __fmaf_rn(qx, thrA, thrB);
         }
@@ -593,6 +598,7 @@ struct rb_gmm_tensor {
     rb::DevBuf<float>    dIsd, dCentre, dXnorm, dThr, dXT;
     rb::DevBuf<uint32_t> dWords;  // candidate sets of the screening pass, [nMix / 4][cap][4]
     bool                 diag = false;   // operands of the diagonal scorers (rb_gmm_tensor_create_diag)
+    bool                 pooled = false; // ... with one covariance for all densities: no x^2 group (K = 3 dp + 3)
     rb::DevBuf<float>    dVmax2;
     rb::DevBuf<uint32_t> dEndMask;
     rb::DevBuf<int>      dMixStart;
@@ -885,7 +891,12 @@ int rb_gmm_tensor_create_diag(const rb_mixture_set* ms, const float* rows, int r
     *out = nullptr;
     const unsigned D  = ms->dim;
     const int      dp = (int)rb::round_up(D, 8);
-    const int      kPad = (int)rb::round_up((size_t)6 * dp + 3, 64);
+    // one covariance for all densities: the x^2 group of the expansion is a per-frame constant and is dropped
+    bool pooled = ms->n_covariances == 1 && getenv("RB_GMM_DIAG_FULL_SCREEN") == nullptr;
+    for (uint32_t i = 0; i < ms->n_densities && pooled; ++i)
+        pooled = ms->dens_cov[i] == 0;
+    const int groups = pooled ? 3 : 6;
+    const int kPad   = (int)rb::round_up((size_t)groups * dp + 3, 64);
     if (kPad > 4 * rbgemm::BK) {
         rb::set_error("diagonal screening supports at most 40 dimensions (got %u)", D);
         return RB_ERR_UNSUPPORTED;
@@ -915,7 +926,8 @@ int rb_gmm_tensor_create_diag(const rb_mixture_set* ms, const float* rows, int r
     t->kPad = kPad;
     t->nMix = (int)ms->n_mixtures;
     t->seg  = (uniform && (n0 == 8 || n0 == 16 || n0 == 32)) ? (int)n0 : 0;
-    t->diag = true;
+    t->diag   = true;
+    t->pooled = pooled;
     std::vector<uint32_t> colEntry, colEnd;
     for (uint32_t m = 0; m < ms->n_mixtures; ++m) {
         const uint32_t e0 = ms->mix_offsets[m], n = ms->mix_offsets[m + 1] - e0;
@@ -983,17 +995,20 @@ int rb_gmm_tensor_create_diag(const rb_mixture_set* ms, const float* rows, int r
             const float  a = (float)(v2[(size_t)e * D + d] * scale), b = (float)(mm[(size_t)e * D + d] * scale);
             const __half ah = __float2half_rn(a), al = __float2half_rn(a - __half2float(ah));
             const __half bh = __float2half_rn(b), bl = __float2half_rn(b - __half2float(bh));
-            row[d]          = ah;
-            row[dp + d]     = al;
-            row[2 * dp + d] = ah;
-            row[3 * dp + d] = bh;
-            row[4 * dp + d] = bl;
-            row[5 * dp + d] = bh;
+            const int    first1 = pooled ? 0 : 3 * dp;
+            if (!pooled) {
+                row[d]          = ah;
+                row[dp + d]     = al;
+                row[2 * dp + d] = ah;
+            }
+            row[first1 + d]          = bh;
+            row[first1 + dp + d]     = bl;
+            row[first1 + 2 * dp + d] = bh;
         }
         double r = cc[e] * (double)scale, got = 0;
         for (int j = 0; j < 3; ++j) {
             const __half h  = __float2half_rn((float)r);
-            row[6 * dp + j] = h;
+            row[groups * dp + j] = h;
             r -= (double)__half2float(h);
             got += (double)__half2float(h);
         }
@@ -1077,7 +1092,8 @@ int rb_gmm_tensor_screen(rb_gmm_tensor* t, const float* dFeats, long n, const ui
     const int blocks = (int)std::min<long>((n + 31) / 32, (long)t->dev.sm_count * 16);
     if (t->diag)
         gmm_split_features_diag_kernel<<<blocks, 256, 0, s>>>(dFeats, t->dCentre.p, t->dVmax2.p, n, t->dim, t->dp, t->kPad,
-                                                              t->dA.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p, t->cap);
+                                                              t->dA.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p, t->cap,
+                                                              t->pooled ? 1 : 0);
     else
         gmm_split_features_kernel<<<blocks, 256, 0, s>>>(dFeats, t->dIsd.p, t->dCentre.p, n, t->dim, t->dp, t->kPad, t->scale,
                                                          t->dA.p, t->dXnorm.p, t->dThr.p, t->thrA, t->thrB, t->dXT.p,
