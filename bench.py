@@ -703,7 +703,8 @@ class Bench:
         scorer, d_in, d_out, msd = w["keep"]
         T, R = w["units"], self.R
         out = {}
-        for name in ("batch-tensor", "batch-float-direct", "diagonal-maximum", "batch-int", "SIMD-diagonal-maximum"):
+        for name in ("batch-tensor", "batch-float-direct", "diagonal-maximum", "batch-int", "SIMD-diagonal-maximum",
+                     "preselection-batch-float", "preselection-batch-int"):
             if name == "batch-float-direct":
                 os.environ["RB_GMM_EXACT"] = "0"
             try:
@@ -726,6 +727,12 @@ class Bench:
             if name == "batch-tensor":
                 d.update(dtype="f16x3 split operands, f32 accumulate",
                          parity="<= 1e-4 relative to the reference scores (tests/test_gpu_gmm_tensor.py)")
+            elif name.startswith("preselection"):
+                d.update(dtype="f32" if name.endswith("float") else "u8 x u8 -> s32",
+                         parity="bit-identical, clustering and back-off decisions included (tests/test_gpu_gmm_presel.py, "
+                                "tests/test_gpu_zz_gmm_presel_int.py)",
+                         note="the reference's density-preselection approximations (256 clusters, 32 selected), reproduced "
+                              "as they are; the float variant runs through the refinement kernel of the exact route")
             elif name == "batch-int":
                 d.update(dtype="u8 x u8 -> s32 (IMMA)", parity="bit-identical (tests/test_gpu_gmm_int.py)",
                          note="Mm::BatchIntFeatureScorer, the reference's quantised batch scorer")
