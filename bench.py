@@ -693,7 +693,7 @@ class Bench:
 
     # other formulations of the C2 scorer, timed the same way on the same buffers and reported beside the headline:
     #   batch-tensor        RB_GMM_BATCH_TENSOR, 1e-4 relative instead of bit-identical
-    #   batch-float-direct  the single direct-form kernel (RB_GMM_EXACT=0), what batches below 2048 frames and models
+    #   batch-float-direct  the single direct-form kernel (RB_GMM_EXACT=0), what models
     #                       the screening does not cover run on; FP32-issue bound
     #   diagonal-maximum    RASR's default scorer (per-density covariance, best density), exact, same route
     def gmm_variants(self, w, steps, warmup):

@@ -281,7 +281,7 @@ int rb_gmm_score_dev(rb_gmm* h, const float* d_feats, long T, float* d_scores, u
  * route of RB_GMM_BATCH_FLOAT stores to every destination from its last kernel (64 contiguous bytes per frame and store
  * instruction, crossing NVLink while the kernel is still computing); the other modes copy the finished matrix. */
 int rb_gmm_score_fanout_dev(rb_gmm* h, const float* d_feats, long T, int n_dst, float* const* d_dst, void* stream);
-/* measurement hook (bench.py): RB_GMM_BATCH_FLOAT scores batches of >= 2048 frames in three kernels (operand split,
+/* measurement hook (bench.py): RB_GMM_BATCH_FLOAT scores its batches in three kernels (operand split,
  * tensor-core screening of the candidate densities, exact evaluation of the candidates); with timing on, CUDA events
  * bracket them on the launching stream and rb_gmm_get_timing returns their durations of the last such call
  * (ms3 = split, screen, refine; waits for the call; RB_ERR_STATE if the last calls took the single direct kernel) */

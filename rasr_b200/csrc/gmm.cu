@@ -21,7 +21,8 @@
 //     add tree), so BATCH_FLOAT scores are bit-identical to the CPU path, contraction on or off.
 //   * the kernel is FP32-ALU bound (2 issue slots per (frame,density,dim)); see DESIGN.md.
 //
-// BATCH_FLOAT on batches of >= 2048 frames does not run that kernel: the reference's result for a mixture is a minimum,
+// BATCH_FLOAT on models the screening covers does not run that kernel (at any batch size: the route below is faster
+// from one frame on): the reference's result for a mixture is a minimum,
 // so gmm_tensor.cu screens the densities that can win with a split-precision tcgen05 product and gmm_refine_kernel
 // (below) evaluates only those, in the reference's operation order -- same bits, a sixteenth of the FP32 work
 // (rb_gmm_score_fanout_dev stores the result into several GPUs' windows at once).
@@ -893,7 +894,8 @@ struct rb_gmm {
     GmmRefineKernel      refine = nullptr;
     int                  refGroups = 0, refSlots = 0;
     size_t               refSmem = 0;
-    long                 exactMinFrames = 2048;
+    long                 exactMinFrames = 1;  // measured: the two-pass route is faster than the direct kernel from 1 frame on
+                                              // (23 vs 31 us per call up to 1000 frames, 27 vs 117 us for DIAG_MAX); RB_GMM_EXACT_MIN_FRAMES
     rb::DevBuf<int>      dMixRow;
     rb::DevBuf<float>    dRefRows, dRefIsd;
     bool                 refPooled = false;  // DIAG_MAX refinement rows without the per-row 1/sqrt(var) copy
@@ -1170,6 +1172,8 @@ int setup_exact_two_pass(rb_gmm* h, const rb_mixture_set* ms, const float* rowsH
     const char* env = getenv("RB_GMM_EXACT");
     if (env && atoi(env) == 0)
         return RB_OK;
+    if (const char* e = getenv("RB_GMM_EXACT_MIN_FRAMES"))
+        h->exactMinFrames = std::max(1, atoi(e));
     if (env && atoi(env) > 1)
         h->exactMinFrames = 1;  // tests: every call takes the two-pass route
     if (h->nMix % 4 != 0)

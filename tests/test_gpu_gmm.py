@@ -20,6 +20,15 @@ def both(oracle, msd):
     return oracle.MixtureSet(**msd), mm.MixtureSet.from_dict(msd)
 
 
+@pytest.fixture(params=["default", "direct"], autouse=True)
+def route(request, monkeypatch):
+    """every case twice: the default routing (tensor-core screening + exact refinement wherever the model allows it, at
+    any batch size) and the direct-form kernels alone (RB_GMM_EXACT=0: what ineligible models run on)"""
+    if request.param == "direct":
+        monkeypatch.setenv("RB_GMM_EXACT", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("contraction", [True, False])
 def test_batch_float_c2_shape_bit_exact(oracle, diag, contraction):
     """C2 geometry (39-dim, 256 mixtures x 16 densities) at a size the oracle finishes in seconds."""

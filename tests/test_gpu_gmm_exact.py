@@ -128,7 +128,7 @@ def test_non_finite_and_huge_frames_follow_the_direct_kernel():
 
 
 def test_small_calls_and_host_slabs(oracle):
-    """the host-buffer call cuts a segment into slabs of growing size: small slabs take the direct kernel, large ones
+    """the host-buffer call cuts a segment into slabs of growing size, and calls of any size (one frame included) take
     the two-pass route -- one matrix, the oracle's bits"""
     msd = synth.mixture_set(dim=39, n_mixtures=64, densities_per_mixture=16, seed=12)
     f = synth.features(9000, 39, seed=13)
