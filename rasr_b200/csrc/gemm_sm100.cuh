@@ -37,9 +37,14 @@ constexpr int SMEM_BYTES_TMA  = STAGES * STAGE_BYTES + 1024 + OUT_STAGE_BYTES + 
 enum { FMT_F16 = 0, FMT_BF16 = 1 };
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, K-major A and B
-__host__ __device__ constexpr uint32_t instr_desc(int fmt) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+__host__ __device__ constexpr uint32_t instr_desc(int fmt, int tileN = BN) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(tileN >> 3) << 17) |
            ((uint32_t)(BM >> 4) << 24);
+}
+// shared memory of the register-epilogue kernel with TN-column tiles (TN = BN, or 128 for batches whose 128 x 256
+// tiles would leave most SMs idle)
+__host__ __device__ constexpr int smem_bytes(int tileN) {
+    return STAGES * (A_BYTES + tileN * BK * 2) + 256 + 1024;
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
@@ -130,10 +135,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // the kernel stages each 32 x 32 f32 block in (128-byte swizzled) shared memory and hands it to the TMA unit, which
 // writes whole lines and clips at the matrix edges; the LSU never sees the row-strided stores that otherwise make a
 // wide f32 epilogue 2x longer than the MMAs of a tile.
-template<class Epi, bool TMA_STORE = false>
+template<class Epi, bool TMA_STORE = false, int TN = BN>
 __global__ void __launch_bounds__(THREADS, 1)
         gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOut, int M, int N, int K, uint32_t idesc, const Epi epi) {
+    static_assert(TN == BN || (TN == 128 && !TMA_STORE), "tile widths: 256, or 128 with the register epilogue");
+    constexpr int STAGE_BYTES = A_BYTES + TN * BK * 2;  // (shadows the namespace constant: this kernel's ring stage)
     // epilogue warps: eight (two per TMEM lane quarter) for the register epilogues; the TMA-store variant keeps four --
     // its staging boxes would cost a ring stage, and with three stages the score layer lost more (721 -> 790 us per
     // 18944 frames) than the second set of warps gave
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     uint32_t* tmemPtr    = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nMB = (M + BM - 1) / BM, nNB = (N + BN - 1) / BN, nTiles = nMB * nNB, nKB = K / BK;
+    const int nMB = (M + BM - 1) / BM, nNB = (N + TN - 1) / TN, nTiles = nMB * nNB, nKB = K / BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_expect_tx(&full[s], STAGE_BYTES);
                     tma_load_2d(sbase + s * STAGE_BYTES, &tmA, kb * BK, mb * BM, &full[s]);
-                    tma_load_2d(sbase + s * STAGE_BYTES + A_BYTES, &tmB, kb * BK, nb * BN, &full[s]);
+                    tma_load_2d(sbase + s * STAGE_BYTES + A_BYTES, &tmB, kb * BK, nb * TN, &full[s]);
                 }
             }
         }
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const uint32_t a = tc & 1u, aph = (tc >> 1) & 1u;
                 mbar_wait(&tempty[a], aph ^ 1u);
                 tc_fence_after();
-                const uint32_t dTmem = tmemBase + a * BN;
+                const uint32_t dTmem = tmemBase + a * TN;
                 for (int kb = 0; kb < nKB; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&full[s], ph);
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     else if (warp >= 4 && warp < 4 + EPI_WARPS) {
         const int q = warp & 3;          // TMEM lane quarter this warp may read
         const int h = (warp - 4) >> 2;   // eight warps: which half of the tile's columns
-        constexpr int CPW = BN / 32 / (EPI_WARPS / 4);  // 32-column chunks per warp
+        constexpr int CPW = TN / 32 / (EPI_WARPS / 4);  // 32-column chunks per warp
         uint32_t  tc = 0;
         // TMA-store staging: two 4 KB boxes per epilogue warp behind the operand ring (1024-byte aligned)
         const uint32_t outStage = sbase + STAGES * STAGE_BYTES + 1024 + (warp - 4) * 2 * 4096;
@@ -237,14 +244,14 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll 1
             for (int c = h * CPW; c < (h + 1) * CPW; c += 2) {  // two TMEM loads in flight per wait
                 float          v0[32], v1[32];
-                const uint32_t ta = tmemBase + ((uint32_t)(q * 32) << 16) + a * BN + c * 32;
+                const uint32_t ta = tmemBase + ((uint32_t)(q * 32) << 16) + a * TN + c * 32;
                 tmem_ld32_issue(ta, v0);
                 tmem_ld32_issue(ta + 32, v1);
                 tmem_ld_wait();
                 if constexpr (TMA_STORE) {
 #pragma unroll
                     for (int hlf = 0; hlf < 2; ++hlf) {
-                        const int col0 = nb * BN + (c + hlf) * 32;
+                        const int col0 = nb * TN + (c + hlf) * 32;
                         if (col0 >= N)  // warp-uniform: the whole box lies outside the matrix
                             continue;
                         float o[32];
@@ -268,8 +275,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                     }
                 }
                 else if (row < M) {
-                    epi.chunk(st, row, nb * BN + c * 32, v0);
-                    epi.chunk(st, row, nb * BN + c * 32 + 32, v1);
+                    epi.chunk(st, row, nb * TN + c * 32, v0);
+                    epi.chunk(st, row, nb * TN + c * 32 + 32, v1);
                 }
             }
             tc_fence_before();
@@ -329,14 +336,15 @@ inline int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
     return RB_OK;
 }
 
-template<class Epi>
+// tmB must have been made with TN-row boxes (make_map(..., TN, ...))
+template<class Epi, int TN = BN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int fmt, const Epi& epi, int smCount,
            cudaStream_t s) {
-    RB_CUDA(cudaFuncSetAttribute(gemm16_kernel<Epi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    RB_CUDA(cudaFuncSetAttribute(gemm16_kernel<Epi, false, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(TN)));
     RB_REQUIRE(K % BK == 0 && K > 0, "GEMM K=%d must be a positive multiple of %d", K, BK);
-    const int nTiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int nTiles = ((M + BM - 1) / BM) * ((N + TN - 1) / TN);
     const int grid   = std::min(nTiles, smCount);
-    gemm16_kernel<Epi, false><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmA, M, N, K, instr_desc(fmt), epi);
+    gemm16_kernel<Epi, false, TN><<<grid, THREADS, smem_bytes(TN), s>>>(tmA, tmB, tmA, M, N, K, instr_desc(fmt, TN), epi);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }

@@ -264,6 +264,7 @@ struct NnLayer {
     rb::DevBuf<float>         bias;   // [out]
     rb::DevBuf<float>         biasScore;  // top layer only: bias - priorScale * logPrior
     CUtensorMap               mapW;
+    CUtensorMap               mapW128;  // the same weights with 128-row boxes: hidden layers of small batches
 };
 
 struct rb_nn {
@@ -318,8 +319,15 @@ int forward_chunk(rb_nn* h, const float* dFeats, long T, float* dOut, bool score
                 epi.ldo  = h->layers[l + 1]->kPad;
                 epi.N    = ly->out;
                 epi.act  = ly->act;
-                RB_CHECK(rbgemm::launch(h->mapIn128[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
-                                        h->dev.sm_count, s));
+                // a segment-sized batch (1000 frames) makes 8 x 8 tiles of 128 x 256 out of a 2048-wide layer: 64 CTAs for
+                // 148 SMs.  With 128-column tiles there are twice as many (hidden layers 20 -> ~11 us each)
+                const long tiles256 = ((T + rbgemm::BM - 1) / rbgemm::BM) * ((ly->out + rbgemm::BN - 1) / rbgemm::BN);
+                if (tiles256 < h->dev.sm_count && getenv("RB_NN_WIDE_TILES") == nullptr)
+                    RB_CHECK((rbgemm::launch<EpiHiddenBf16, 128>(h->mapIn128[l], ly->mapW128, (int)T, ly->out, ly->kPad,
+                                                                 rbgemm::FMT_BF16, epi, h->dev.sm_count, s)));
+                else
+                    RB_CHECK(rbgemm::launch(h->mapIn128[l], ly->mapW, (int)T, ly->out, ly->kPad, rbgemm::FMT_BF16, epi,
+                                            h->dev.sm_count, s));
                 std::swap(cur, nxt);
             }
             else {
@@ -498,6 +506,9 @@ extern "C" int rb_nn_create(int n_layers, const int* dims, const int* act, const
             }
             rc = rbgemm::make_map(&ly->mapW, ly->wBf16.p, (uint64_t)ly->out, (uint64_t)ly->kPad, (uint64_t)ly->kPad,
                                   rbgemm::BN, true);
+            if (rc == RB_OK)
+                rc = rbgemm::make_map(&ly->mapW128, ly->wBf16.p, (uint64_t)ly->out, (uint64_t)ly->kPad, (uint64_t)ly->kPad,
+                                      128, true);
             if (rc != RB_OK)
                 return fail(rc);
         }
